@@ -1,0 +1,647 @@
+// =============================================================================
+// thcm_api.cu -- the C ABI of libthcm_b200.so (include/thcm_b200.h):
+//   * handle-based device API thcmb_* (context, residual, Jacobian, SpMV, vector kernels)
+//   * host drivers of the Krylov solvers: GMRES (GMRESSolver.H:81-255) and IDR(s) (IDRSolver.H:109-340)
+//   * the gfortran-mangled B1 symbols THCM.C binds (rhs_, matrix_, init_, setparcs_, ...)
+// Host code only orchestrates; all arithmetic on the timed path runs in CUDA kernels.  There is
+// no CPU fallback: without a usable device every entry point fails loudly.
+// =============================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include "thcm_internal.h"
+
+using namespace thcm;
+
+// ---- weak defaults of the callbacks the reference defines in C++ (THCM.C:2653,2690; GlobalDefinitions.C:145,154)
+extern "C" {
+__attribute__((weak)) void thcm_throw_error_(char* msg) { fprintf(stderr, "%s\n", msg); abort(); }
+__attribute__((weak)) void timer_start_(const char*) {}
+__attribute__((weak)) void timer_stop_(const char*) {}
+__attribute__((weak)) void thcm_forcing_integral_(double*, double*, int*, double* out) { *out = 0.0; }
+}
+
+namespace {
+
+void require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        fatal("no CUDA device available: the THCM B200 path has no CPU fallback (" + std::string(cudaGetErrorString(e)) + ")");
+    if (device >= n) fatal("CUDA device ordinal out of range");
+    THCM_CUDA(cudaSetDevice(device));
+}
+
+template <class T> void upload(T*& d, const std::vector<T>& h) {
+    if (d) { cudaFree(d); d = nullptr; }
+    if (h.empty()) return;
+    THCM_CUDA(cudaMalloc(&d, sizeof(T) * h.size()));
+    THCM_CUDA(cudaMemcpy(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+}
+
+void upload_params(thcmb_ctx* c) {
+    upload(c->d_jt, c->jt_host);
+    upload(c->d_kt, c->kt_host);
+    upload(c->d_frc, c->frc_local);
+}
+
+void refresh_params(thcmb_ctx* c) {  // forcing + lin (usrc.F90:178-179)
+    compute_forcing(c);
+    compute_tables(c);
+    compute_cob(c);
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    upload_params(c);
+}
+
+void build_static(thcmb_ctx* c) {
+    std::vector<uint32_t> nbmask; std::vector<uint8_t> surf, uvlive; std::vector<int> send_idx, recv_slot;
+    build_static_host(c, nbmask, surf, uvlive, send_idx, recv_slot);
+    upload(c->d_nbmask, nbmask); upload(c->d_surf, surf); upload(c->d_uvlive, uvlive);
+    upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
+    upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
+    if (c->d_val) cudaFree(c->d_val);
+    THCM_CUDA(cudaMalloc(&c->d_val, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
+    THCM_CUDA(cudaMemset(c->d_val, 0, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
+    size_t nh = (size_t)NUN * std::max(c->blk.nhalo_cells(), 1);
+    for (double** p : {&c->d_halo, &c->d_sendbuf, &c->d_recvbuf}) { if (*p) cudaFree(*p); *p = nullptr; }
+    THCM_CUDA(cudaMalloc(&c->d_halo, sizeof(double) * nh));
+    THCM_CUDA(cudaMemset(c->d_halo, 0, sizeof(double) * nh));
+    THCM_CUDA(cudaMalloc(&c->d_sendbuf, sizeof(double) * NUN * (size_t)std::max(c->nsend_cells, 1)));
+    THCM_CUDA(cudaMalloc(&c->d_recvbuf, sizeof(double) * NUN * (size_t)std::max(c->nrecv_cells, 1)));
+    upload_class_tables(class_tables(c->blk.periodic));
+}
+
+void stage_begin(thcmb_ctx* c) { THCM_CUDA(cudaEventRecord(c->ev0, c->stream)); }
+void stage_end(thcmb_ctx* c, const char* label) {  // device time under the reference's profile labels
+    THCM_CUDA(cudaEventRecord(c->ev1, c->stream));
+    THCM_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    THCM_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stage_ms[label] = ms;
+}
+
+}  // namespace
+
+namespace thcm {
+double* pool_vec(thcmb_ctx* c, size_t idx) {
+    while (c->krylov_pool.size() <= idx) {
+        double* p = nullptr;
+        THCM_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)c->blk.ndim()));
+        c->krylov_pool.push_back(p);
+    }
+    return c->krylov_pool[idx];
+}
+}  // namespace thcm
+
+extern "C" {
+
+void thcmb_default_settings(thcmb_settings* s) {
+    memset(s, 0, sizeof(*s));
+    s->N = s->M = s->L = 0;
+    s->hdim = 4000.0; s->qz = 1.0;                         // usr.F90:45-46, THCM.C defaults
+    s->ih = 0; s->vmix = 0; s->tap = 1; s->rho_mixing = 0; s->coriolis_on = 1;
+    s->TRES = 1; s->SRES = 1; s->iza = 2; s->ite = 1; s->its = 1; s->coupled_T = 0; s->coupled_S = 0; s->forcing_type = 0;
+    s->alphaT = 1.0e-04; s->alphaS = 7.6e-04;               // usr.F90:143-144
+    s->rank = 0; s->nranks = 1; s->device = 0;
+}
+
+thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
+    require_device(s->device);
+    if (s->vmix != 0) fatal("Mixing >= 1 (vmix_fun / vmix_jac, mix_imp.f) is not implemented on the B200 path yet; set Mixing = 0");
+    thcmb_ctx* c = new thcmb_ctx();
+    c->s = *s; c->device = s->device;
+    if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) fatal("domain decomposition produced an empty block");
+    THCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    THCM_CUDA(cudaEventCreate(&c->ev0)); THCM_CUDA(cudaEventCreate(&c->ev1));
+    size_t nm = (size_t)s->N * s->M;
+    for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
+    build_grid(c);
+    stpnt(c);
+    apply_landmask_rules(c, landm_global, false);
+    c->n_asm_blocks = (c->blk.ncell() + 31) / 32;
+    THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
+    THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
+    THCM_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 4096));
+    THCM_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+    THCM_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int)));
+    THCM_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 4096));
+    THCM_CUDA(cudaMalloc(&c->d_blockcnt, sizeof(int) * (size_t)(c->n_asm_blocks + 1)));
+    THCM_CUDA(cudaMalloc(&c->d_un, sizeof(double) * (size_t)c->blk.ndim()));
+    THCM_CUDA(cudaMalloc(&c->d_tmp, sizeof(double) * (size_t)c->blk.ndim()));
+    build_static(c);
+    refresh_params(c);
+    return c;
+}
+
+void thcmb_destroy(thcmb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl_destroy(c);
+    for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
+                    (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)c->d_halo, (void*)c->d_sendbuf, (void*)c->d_recvbuf,
+                    (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
+                    (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv})
+        if (p) cudaFree(p);
+    for (double* p : c->krylov_pool) cudaFree(p);
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void thcmb_local_block(const thcmb_ctx* c, int* i0, int* j0, int* n0, int* m0, int* npN, int* npM) {
+    *i0 = c->blk.i0; *j0 = c->blk.j0; *n0 = c->blk.n0; *m0 = c->blk.m0; *npN = c->blk.npN; *npM = c->blk.npM;
+}
+int thcmb_ndim_local(const thcmb_ctx* c) { return c->blk.ndim(); }
+long long thcmb_graph_nnz(const thcmb_ctx* c) { return c->gnnz; }
+void thcmb_get_graph(const thcmb_ctx* c, int* rowptr, int* col) {
+    memcpy(rowptr, c->rowptr_host.data(), sizeof(int) * c->rowptr_host.size());
+    memcpy(col, c->col_host.data(), sizeof(int) * c->col_host.size());
+}
+int thcmb_halo_size(const thcmb_ctx* c) { return NUN * c->blk.nhalo_cells(); }
+void thcmb_halo_gids(const thcmb_ctx* c, int* gids) { memcpy(gids, c->halo_gid.data(), sizeof(int) * c->halo_gid.size()); }
+void thcmb_local_gids(const thcmb_ctx* c, int* gids) { memcpy(gids, c->local_gid.data(), sizeof(int) * c->local_gid.size()); }
+
+void thcmb_set_par(thcmb_ctx* c, int idx, double val) {
+    if (idx >= 1 && idx <= NPAR) c->par[idx] = val;
+    refresh_params(c);
+}
+double thcmb_get_par(const thcmb_ctx* c, int idx) { return (idx >= 1 && idx <= NPAR) ? c->par[idx] : 0.0; }
+void thcmb_get_forcing(thcmb_ctx* c, double* frc) {
+    const std::vector<double>& f = c->frc_masked ? c->frc_local : c->frc_raw;
+    memcpy(frc, f.data(), sizeof(double) * f.size());
+}
+void thcmb_get_cob(thcmb_ctx* c, double* cob) { memcpy(cob, c->cob_local.data(), sizeof(double) * c->cob_local.size()); }
+
+int thcmb_nccl_unique_id(void* id128) { return nccl_unique_id(id128); }
+int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128); }
+
+int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x) { return halo_exchange(c, d_x); }
+
+int thcmb_rhs_dev(thcmb_ctx* c, const double* d_un, double* d_B) {
+    c->frc_masked = true;
+    halo_exchange(c, d_un);
+    return launch_assembly(c, MODE_RHS, d_un, d_B, nullptr, nullptr, nullptr);
+}
+int thcmb_residual_dev(thcmb_ctx* c, const double* d_un, double* d_F) {
+    c->frc_masked = true;
+    halo_exchange(c, d_un);
+    return launch_assembly(c, MODE_RHS | 0x100, d_un, d_F, nullptr, nullptr, nullptr);
+}
+int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un) {
+    c->frc_masked = true;
+    halo_exchange(c, d_un);
+    return launch_assembly(c, MODE_JAC_GRAPH, d_un, nullptr, nullptr, nullptr, nullptr);
+}
+const double* thcmb_jacobian_values(const thcmb_ctx* c) { return c->d_val; }
+const int* thcmb_graph_rowptr_dev(const thcmb_ctx* c) { return c->d_rowptr; }
+const int* thcmb_graph_col_dev(const thcmb_ctx* c) { return c->d_col; }
+
+long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, int* d_jcoA, double* d_coA) {
+    c->frc_masked = true;
+    halo_exchange(c, d_un);
+    launch_assembly(c, MODE_JAC_COUNT, d_un, nullptr, nullptr, nullptr, nullptr);
+    scan_block_counts(c);
+    launch_assembly(c, MODE_JAC_CRS, d_un, nullptr, d_begA, d_jcoA, d_coA);
+    int last = 0;
+    THCM_CUDA(cudaMemcpyAsync(&last, d_begA + c->blk.ndim(), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return (long long)last - 1;
+}
+
+int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y) {
+    halo_exchange(c, d_x);
+    return spmv(c, c->blk.ndim(), c->d_rowptr, c->d_col, c->d_val, d_x, c->d_halo, c->blk.ndim(), d_y);
+}
+int thcmb_csr_spmv_dev(thcmb_ctx* c, int nrow, const int* d_rowptr, const int* d_col, const double* d_val, const double* d_x, double* d_y) {
+    return spmv(c, nrow, d_rowptr, d_col, d_val, d_x, d_x, 0x7fffffff, d_y);
+}
+
+double thcmb_dot(thcmb_ctx* c, int n, const double* d_x, const double* d_y) {
+    dot_dev(c, n, d_x, d_y, c->d_scalars);
+    THCM_CUDA(cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return c->h_scalars[0];
+}
+double thcmb_nrm2(thcmb_ctx* c, int n, const double* d_x) { return std::sqrt(thcmb_dot(c, n, d_x, d_x)); }
+int thcmb_axpby(thcmb_ctx* c, int n, double a, const double* d_x, double b, double* d_y) { return axpby(c, n, a, d_x, b, d_y); }
+int thcmb_scale(thcmb_ctx* c, int n, double a, double* d_x) { return axpby(c, n, 0.0, d_x, a, d_x); }
+
+int thcmb_build_precon(thcmb_ctx* c, int kind) {
+    c->precon_kind = kind;
+    if (kind == 1) return build_blockdiag(c);
+    return kind == 0 ? 0 : -1;
+}
+int thcmb_apply_precon_dev(thcmb_ctx* c, const double* d_x, double* d_y) {
+    if (c->precon_kind == 1) return apply_blockdiag(c, d_x, d_y);
+    return copy(c, c->blk.ndim(), d_x, d_y);
+}
+
+void* thcmb_device_alloc(thcmb_ctx* c, long long bytes) {
+    void* p = nullptr;
+    THCM_CUDA(cudaSetDevice(c->device));
+    THCM_CUDA(cudaMalloc(&p, (size_t)std::max<long long>(bytes, 8)));
+    return p;
+}
+void thcmb_device_free(thcmb_ctx*, void* p) { if (p) cudaFree(p); }
+int thcmb_h2d(thcmb_ctx* c, void* d, const void* h, long long bytes) {
+    THCM_CUDA(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int thcmb_d2h(thcmb_ctx* c, void* h, const void* d, long long bytes) {
+    THCM_CUDA(cudaMemcpyAsync(h, d, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int thcmb_sync(thcmb_ctx* c) { THCM_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+void* thcmb_stream(thcmb_ctx* c) { return (void*)c->stream; }
+long long thcmb_launch_count(const thcmb_ctx* c) { return c->launches; }
+double thcmb_last_stage_ms(const thcmb_ctx* c, const char* label) {
+    auto it = c->stage_ms.find(label);
+    return it == c->stage_ms.end() ? -1.0 : it->second;
+}
+
+// =============================================================================
+// GMRES -- the algorithm of src/gmressolver/GMRESSolver.H:81-255 (right / flexible preconditioning,
+// modified Gram-Schmidt, Givens rotations, back substitution = minimiser scheme 'B').
+// The MGS chain runs without host syncs: every projection coefficient stays in device memory and is
+// consumed by the next fused (axpy + dot) kernel; one small D2H per iteration brings column i of H.
+// =============================================================================
+static void gen_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESSolver.H:258-279
+    if (dy == 0.0) { cs = 1.0; sn = 0.0; }
+    else if (std::abs(dy) > std::abs(dx)) { double t = dx / dy; sn = 1.0 / sqrt(1.0 + t * t); cs = t * sn; }
+    else { double t = dy / dx; cs = 1.0 / sqrt(1.0 + t * t); sn = t * cs; }
+}
+static void app_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESSolver.H:282-290
+    double t = cs * dx + sn * dy;
+    dy = -sn * dx + cs * dy;
+    dx = t;
+}
+
+int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags, double* hist,
+                int hist_cap, thcmb_krylov_result* res) {
+    const int n = c->blk.ndim();
+    const bool prec = flags & 1, flexible = flags & 4;
+    const int m = restart;
+    if (m + 2 > 4000) fatal("GMRES restart too large for the device scalar buffer");
+    auto applyA = [&](const double* v, double* out) { thcmb_spmv_dev(c, v, out); };
+    auto applyM = [&](const double* v, double* out) { thcmb_apply_precon_dev(c, v, out); };
+    long long n_matvec = 0;
+    int nh = 0;
+    auto push = [&](double r) { if (hist && nh < hist_cap) hist[nh] = r; nh++; };
+    // pool: 0 = r/tmp, 1 = tmp2, 2.. = V[0..m], then Z[0..m-1] when flexible+prec
+    double* r = pool_vec(c, 0);
+    double* tmp = pool_vec(c, 1);
+    auto V = [&](int i) { return pool_vec(c, 2 + i); };
+    auto Z = [&](int i) { return pool_vec(c, 2 + (m + 1) + i); };
+    std::vector<std::vector<double>> H(m + 1, std::vector<double>(m, 0.0));
+    std::vector<double> s(m + 1, 0.0), cs(m + 1, 0.0), sn(m + 1, 0.0), y;
+    double normb = thcmb_nrm2(c, n, d_b);
+    applyA(d_x, r); n_matvec++;
+    axpby(c, n, 1.0, d_b, -1.0, r);  // r = b - A x
+    double beta = thcmb_nrm2(c, n, r);
+    if (normb == 0.0) normb = 1;
+    double resid = beta / normb;
+    int iter = 0, status = 1;
+    if (resid <= tol) { status = 0; }
+    else {
+        while (iter <= maxit) {
+            beta = thcmb_nrm2(c, n, r);
+            copy(c, n, r, V(0));
+            axpby(c, n, 0.0, V(0), 1.0 / beta, V(0));  // r.scale(1/beta); V[0] = r
+            std::fill(s.begin(), s.end(), 0.0);
+            s[0] = beta;
+            int i, space = -1;
+            bool converged = false;
+            for (i = 0; i < m && iter <= maxit; i++, iter++) {
+                double* w = V(i + 1);
+                if (prec) {
+                    double* z = flexible ? Z(i) : tmp;
+                    applyM(V(i), z);
+                    applyA(z, w);
+                } else applyA(V(i), w);
+                n_matvec++;
+                // MGS (GMRESSolver.H:177-181): H[k][i] = w.V[k]; w -= H[k][i] V[k]
+                double* dh = c->d_scalars;  // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
+                dot_dev(c, n, w, V(0), dh + 0);
+                for (int k = 0; k < i; k++) mgs_step_dev(c, n, dh + k, V(k), V(k + 1), w, dh + k + 1);
+                axpy_negdev(c, n, dh + i, V(i), w);
+                dot_dev(c, n, w, w, dh + i + 1);
+                scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
+                THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
+                THCM_CUDA(cudaStreamSynchronize(c->stream));
+                for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];
+                H[i + 1][i] = c->h_scalars[i + 2];
+                space = i;
+                for (int k = 0; k < i; k++) app_rot(H[k][i], H[k + 1][i], cs[k], sn[k]);
+                gen_rot(H[i][i], H[i + 1][i], cs[i], sn[i]);
+                app_rot(H[i][i], H[i + 1][i], cs[i], sn[i]);
+                app_rot(s[i], s[i + 1], cs[i], sn[i]);
+                resid = std::abs(s[i + 1]) / normb;
+                push(resid);
+                if (resid < tol) { converged = true; break; }
+            }
+            // Update (GMRESSolver.H:293-313, 402-410): back substitution, x += sum y_j Z_j | V_j | M^-1 V y
+            y = s;
+            for (int a = space; a >= 0; a--) {
+                y[a] /= H[a][a];
+                for (int b2 = a - 1; b2 >= 0; b2--) y[b2] -= H[b2][a] * y[a];
+            }
+            if (!prec || flexible) {
+                for (int j = 0; j <= space; j++) axpby(c, n, y[j], (prec && flexible) ? Z(j) : V(j), 1.0, d_x);
+            } else {
+                fill(c, n, 0.0, tmp);
+                for (int j = 0; j <= space; j++) axpby(c, n, y[j], V(j), 1.0, tmp);
+                applyM(tmp, r);
+                axpby(c, n, 1.0, r, 1.0, d_x);
+            }
+            applyA(d_x, r); n_matvec++;
+            axpby(c, n, 1.0, d_b, -1.0, r);
+            if (converged || resid < tol) { status = 0; break; }
+        }
+    }
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    if (res) { res->status = status; res->iters = iter; res->resid = resid; res->nhist = std::min(nh, hist_cap); res->n_matvec = n_matvec; }
+    return status;
+}
+
+// =============================================================================
+// IDR(s) -- src/idrsolver/IDRSolver.H:109-340 (bi-orthogonalisation variant, right preconditioning,
+// no smoothing / residual replacement, fresh search space).  Shadow vectors come from the caller.
+// =============================================================================
+int thcmb_idrs(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int s, const double* d_P_raw, double* hist,
+               int hist_cap, thcmb_krylov_result* res) {
+    const int n = c->blk.ndim();
+    long long n_matvec = 0;
+    int nh = 0;
+    auto push = [&](double r) { if (hist && nh < hist_cap) hist[nh] = r; nh++; };
+    auto applyA = [&](const double* v, double* out) { thcmb_spmv_dev(c, v, out); n_matvec++; };
+    auto applyM = [&](const double* v, double* out) { thcmb_apply_precon_dev(c, v, out); };
+    auto dot = [&](const double* a, const double* b) { return thcmb_dot(c, n, a, b); };
+    auto update = [&](double* self, double a, const double* A, double b) { axpby(c, n, a, A, b, self); };  // self = a*A + b*self
+    // pool layout: r, v, t, P[s], G[s], U[s]
+    double* r = pool_vec(c, 0); double* v = pool_vec(c, 1); double* t = pool_vec(c, 2);
+    auto P = [&](int i) { return pool_vec(c, 3 + i); };
+    auto G = [&](int i) { return pool_vec(c, 3 + s + i); };
+    auto U = [&](int i) { return pool_vec(c, 3 + 2 * s + i); };
+    // createP (IDRSolver.H:84-104): Gram-Schmidt on the injected "random" vectors
+    for (int j = 0; j < s; j++) {
+        copy(c, n, d_P_raw + (size_t)j * n, P(j));
+        for (int k = 0; k < j; k++) { double alpha = dot(P(k), P(j)); update(P(j), -alpha, P(k), 1.0); }
+        double nr = std::sqrt(dot(P(j), P(j)));
+        update(P(j), 0.0, P(j), 1.0 / nr);
+    }
+    double normb = std::sqrt(dot(d_b, d_b));
+    double tolb = tol * normb;
+    applyA(d_x, r);
+    update(r, 1.0, d_b, -1.0);
+    double normr = std::sqrt(dot(r, r));
+    push(normr);
+    int flag = 0, jj = 0, iter = 0;
+    double om = 1.0;
+    std::vector<double> f(s, 0.0), gamma(s, 0.0);
+    std::vector<std::vector<double>> M(s, std::vector<double>(s, 0.0));
+    for (int i = 0; i < s; i++) copy(c, n, d_x, G(i));  // G(dim, Vector(*x_))
+    copy(c, n, r, t);
+    while (normr > tolb && iter < maxit) {
+        for (int i = 0; i < s; i++) f[i] = dot(r, P(i));
+        for (int k = 0; k < s; k++) {
+            copy(c, n, r, v);
+            if (jj > 0) {
+                for (int i = k; i < s; i++) {
+                    gamma[i] = f[i];
+                    for (int j = k; j < i; j++) gamma[i] = gamma[i] - M[i][j] * gamma[j];
+                    gamma[i] = gamma[i] / M[i][i];
+                    update(v, -gamma[i], G(i), 1.0);
+                }
+                applyM(v, t);
+                update(t, 0.0, t, om);  // t.scale(om)
+                for (int i = k; i < s; i++) update(t, gamma[i], U(i), 1.0);
+                copy(c, n, t, U(k));
+            } else {
+                applyM(v, U(k));
+            }
+            applyA(U(k), G(k));
+            for (int i = 0; i < k; i++) {
+                double alpha = dot(P(i), G(k)) / M[i][i];
+                update(G(k), -alpha, G(i), 1.0);
+                update(U(k), -alpha, U(i), 1.0);
+            }
+            for (int i = k; i < s; i++) M[i][k] = dot(G(k), P(i));
+            if (M[k][k] == 0) { flag = 3; goto done; }
+            {
+                double beta = f[k] / M[k][k];
+                update(r, -beta, G(k), 1.0);
+                update(d_x, beta, U(k), 1.0);
+                if (k < s - 1) for (int i = k + 1; i < s; i++) f[i] = f[i] - beta * M[i][k];
+            }
+            normr = std::sqrt(dot(r, r));
+            push(normr);
+            iter++;
+            if (normr < tolb || iter == maxit) break;
+        }
+        if (normr < tolb || iter == maxit) break;
+        jj++;
+        applyM(r, v);
+        applyA(v, t);
+        {   // calc_omega (IDRSolver.H:366-380)
+            double ns = std::sqrt(dot(r, r)), nt = std::sqrt(dot(t, t)), ts = dot(t, r);
+            double rho = std::abs(ts / (nt * ns));
+            om = ts / (nt * nt);
+            if (rho < 0.7) om = om * 0.7 / rho;
+        }
+        update(r, -om, t, 1.0);
+        update(d_x, om, v, 1.0);
+        normr = std::sqrt(dot(r, r));
+        push(normr);
+        iter++;
+    }
+done:
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    int status = flag ? -flag : (normr < tolb ? 0 : 1);
+    if (res) { res->status = status; res->iters = iter; res->resid = normr; res->nhist = std::min(nh, hist_cap); res->n_matvec = n_matvec; }
+    return status;
+}
+
+// One Newton step from host buffers: the end-to-end call (bench.py "e2e").
+int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart, int precon_kind,
+                      double* fnorm, thcmb_krylov_result* res) {
+    const int n = c->blk.ndim();
+    double* d_F = c->d_tmp;
+    double* d_dx = pool_vec(c, 2 + (size_t)(restart + 1) + (size_t)restart + 1);
+    THCM_CUDA(cudaMemcpyAsync(c->d_un, un_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    thcmb_residual_dev(c, c->d_un, d_F);          // F(x)
+    thcmb_jacobian_dev(c, c->d_un);               // J(x)
+    thcmb_build_precon(c, precon_kind);
+    axpby(c, n, 0.0, d_F, -1.0, d_F);             // solve J dx = -F (Ocean.C:1052-1055 pattern)
+    double fn = thcmb_nrm2(c, n, d_F);
+    if (fnorm) *fnorm = fn;
+    fill(c, n, 0.0, d_dx);
+    int rc = thcmb_gmres(c, d_F, d_dx, tol, maxit, restart, precon_kind ? (1 | 4) : 0, nullptr, 0, res);
+    THCM_CUDA(cudaMemcpyAsync(dx_host, d_dx, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+// =============================================================================
+// B1: the reference's Fortran symbols (one global instance per process, host pointers)
+// =============================================================================
+static thcmb_settings g_set;
+static bool g_have_global = false;
+static std::vector<int> g_landm_global;
+static thcmb_ctx* g_ctx = nullptr;
+static int *g_dbeg = nullptr, *g_djco = nullptr; static double* g_dco = nullptr;
+
+static thcmb_ctx* G() { if (!g_ctx) fatal("THCM not initialised: call init_ first"); return g_ctx; }
+
+// reads a land mask in the format of topo.F90:41-64 (per level k=0..l+1: one header line, rows j=m+1..0 of n+2 digits)
+static bool read_mask_file(const char* path, int n, int m, int l, std::vector<int>& out) {
+    std::ifstream f(path);
+    if (!f) return false;
+    out.assign((size_t)(n + 2) * (m + 2) * (l + 2), LAND);
+    std::string line;
+    for (int k = 0; k <= l + 1; k++) {
+        if (!std::getline(f, line)) return false;
+        for (int j = m + 1; j >= 0; j--) {
+            if (!std::getline(f, line)) return false;
+            for (int i = 0; i <= n + 1 && i < (int)line.size(); i++)
+                out[(size_t)i + (size_t)(n + 2) * (j + (size_t)(m + 2) * k)] = line[i] - '0';
+        }
+    }
+    return true;
+}
+
+void __m_global_MOD_initialize(int* N, int* M, int* L, double* xmin, double* xmax, double* ymin, double* ymax, double* hdim,
+                               double* qz, int* periodic, int* itopo, int* flat, int* rd_mask, int* TRES, int* SRES, int* iza,
+                               int* ite, int* its, int* rd_spertm, int* coupled_T, int* coupled_S, int* forcing_type,
+                               const char* maskfile, const char*, const char*, const char*, const char*) {
+    thcmb_default_settings(&g_set);
+    g_set.N = *N; g_set.M = *M; g_set.L = *L;
+    g_set.xmin = *xmin; g_set.xmax = *xmax; g_set.ymin = *ymin; g_set.ymax = *ymax; g_set.hdim = *hdim; g_set.qz = *qz;
+    g_set.periodic = *periodic; g_set.TRES = *TRES; g_set.SRES = *SRES; g_set.iza = *iza; g_set.ite = *ite; g_set.its = *its;
+    g_set.coupled_T = *coupled_T; g_set.coupled_S = *coupled_S; g_set.forcing_type = *forcing_type;
+    (void)itopo; (void)rd_spertm;
+    int n = *N, m = *M, l = *L;
+    g_landm_global.assign((size_t)(n + 2) * (m + 2) * (l + 2), OCEAN);
+    if (*rd_mask && maskfile && maskfile[0]) {
+        // the reference resolves mkmask/<file> below its DATA_DIR (global.F90 locate_file); here the caller passes
+        // a path, or sets THCM_DATA_DIR
+        std::string p = maskfile;
+        if (!read_mask_file(p.c_str(), n, m, l, g_landm_global)) {
+            const char* dd = getenv("THCM_DATA_DIR");
+            std::string p2 = std::string(dd ? dd : ".") + "/mkmask/" + maskfile;
+            if (!read_mask_file(p2.c_str(), n, m, l, g_landm_global)) fatal("cannot read land mask " + p + " / " + p2);
+        }
+        // land inversion fix of readmask (topo.F90:94-103)
+        auto LMg = [&](int i, int j, int k) -> int& { return g_landm_global[(size_t)i + (size_t)(n + 2) * (j + (size_t)(m + 2) * k)]; };
+        for (int i = 1; i <= n; i++) for (int j = 1; j <= m; j++) for (int k = l; k >= 2; k--)
+            if (LMg(i, j, k) == LAND && LMg(i, j, k - 1) == OCEAN) LMg(i, j, k - 1) = LAND;
+        if (*flat) for (int k = 1; k <= l - 1; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++) LMg(i, j, k) = LMg(i, j, l);
+    }
+    g_have_global = true;
+}
+void __m_global_MOD_get_landm(int* landm) { memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size()); }
+void __m_global_MOD_finalize(void) { g_landm_global.clear(); g_have_global = false; }
+
+void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, double* ymin, double* ymax, double* alphaT, double* alphaS,
+           int* ih, int* vmix, int* tap, int* rho_mixing, int* coriolis_on, int* periodic, int* landm, double* taux, double* tauy,
+           double* tatm, double* emip, double* spert) {
+    (void)nmlglob;
+    if (!g_have_global) thcmb_default_settings(&g_set);
+    thcmb_settings s = g_set;
+    // the library sees the caller's (sub)domain as its whole world, like the Fortran it replaces.  NOTE: temfun/salfun
+    // use the GLOBAL ymin/ymax of m_global (forcing.F90:424-449); on a single rank they coincide with the local ones.
+    s.N = *n; s.M = *m; s.L = *l; s.xmin = *xmin; s.xmax = *xmax;
+    if (!g_have_global) { s.ymin = *ymin; s.ymax = *ymax; }
+    if (g_have_global && (s.ymin != *ymin || s.ymax != *ymax))
+        fatal("init_: sub-domain bounds differ from the global ones; multi-rank runs must use the thcmb_* API (DESIGN.md)");
+    s.alphaT = *alphaT; s.alphaS = *alphaS; s.ih = *ih; s.vmix = *vmix; s.tap = *tap; s.rho_mixing = *rho_mixing;
+    s.coriolis_on = *coriolis_on; s.periodic = *periodic; s.rank = 0; s.nranks = 1;
+    if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }  // THCM is a singleton that replaces the previous instance (THCM.H:76-84)
+    g_ctx = thcmb_create(&s, landm);
+    size_t nm = (size_t)s.N * s.M;
+    memcpy(g_ctx->taux.data(), taux, sizeof(double) * nm); memcpy(g_ctx->tauy.data(), tauy, sizeof(double) * nm);
+    memcpy(g_ctx->tatm.data(), tatm, sizeof(double) * nm); memcpy(g_ctx->emip.data(), emip, sizeof(double) * nm);
+    memcpy(g_ctx->spert.data(), spert, sizeof(double) * nm);
+    refresh_params(g_ctx);
+}
+void finalize_(void) {
+    if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }
+    for (void* p : {(void*)g_dbeg, (void*)g_djco, (void*)g_dco}) if (p) cudaFree(p);
+    g_dbeg = g_djco = nullptr; g_dco = nullptr;
+}
+void __m_mat_MOD_get_array_sizes(int* nrows, int* nnz) {  // mat.F90:56-68
+    *nrows = G()->blk.ndim();
+    *nnz = G()->blk.ndim() * (NUN * NP + 1);
+}
+void __m_mat_MOD_set_pointers(int* nrows, int* nnz, int* begA, int* jcoA, double* coA, double* coB, int*, int*, double*) {
+    (void)nrows; (void)nnz;
+    thcmb_ctx* c = G();
+    c->begA = begA; c->jcoA = jcoA; c->coA = coA; c->coB = coB;
+}
+void rhs_(double* un, double* B) {
+    thcmb_ctx* c = G();
+    const int n = c->blk.ndim();
+    timer_start_("nlin_rhs+boundaries+matAvec");
+    THCM_CUDA(cudaMemcpyAsync(c->d_un, un, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c);
+    thcmb_rhs_dev(c, c->d_un, c->d_tmp);
+    stage_end(c, "nlin_rhs+boundaries+matAvec");
+    THCM_CUDA(cudaMemcpyAsync(B, c->d_tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    timer_stop_("nlin_rhs+boundaries+matAvec");
+}
+void fillcolb_(void) {
+    thcmb_ctx* c = G();
+    if (!c->coB) fatal("fillcolb_: set_pointers was not called");
+    memcpy(c->coB, c->cob_local.data(), sizeof(double) * c->cob_local.size());
+}
+void matrix_(double* un) {
+    thcmb_ctx* c = G();
+    if (!c->begA) fatal("matrix_: set_pointers was not called");
+    const int n = c->blk.ndim();
+    timer_start_("nlin_jac+boundaries+fillcolA");
+    if (!g_dbeg) {
+        THCM_CUDA(cudaMalloc(&g_dbeg, sizeof(int) * (size_t)(n + 1)));
+        THCM_CUDA(cudaMalloc(&g_djco, sizeof(int) * (size_t)c->gnnz));
+        THCM_CUDA(cudaMalloc(&g_dco, sizeof(double) * (size_t)c->gnnz));
+    }
+    fillcolb_();
+    THCM_CUDA(cudaMemcpyAsync(c->d_un, un, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    stage_begin(c);
+    long long nnz = thcmb_jacobian_crs_dev(c, c->d_un, g_dbeg, g_djco, g_dco);
+    stage_end(c, "nlin_jac+boundaries+fillcolA");
+    THCM_CUDA(cudaMemcpyAsync(c->begA, g_dbeg, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaMemcpyAsync(c->jcoA, g_djco, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaMemcpyAsync(c->coA, g_dco, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    timer_stop_("nlin_jac+boundaries+fillcolA");
+}
+void setparcs_(int* idx, double* val) { thcmb_set_par(G(), *idx, *val); }
+void getparcs_(int* idx, double* val) { if (*idx >= 1 && *idx <= NPAR) *val = G()->par[*idx]; }
+void setsres_(int* sres) { thcmb_ctx* c = G(); c->s.SRES = *sres; refresh_params(c); }
+void set_landmask_(int* landm, int* periodic, int* reinit) {
+    thcmb_ctx* c = G();
+    c->s.periodic = *periodic; c->blk.periodic = *periodic; c->blk.wrap_x = (*periodic && c->blk.npN == 1) ? 1 : 0;
+    apply_landmask_rules(c, landm, true);
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    build_static(c);
+    if (g_dbeg) { cudaFree(g_dbeg); cudaFree(g_djco); cudaFree(g_dco); g_dbeg = g_djco = nullptr; g_dco = nullptr; }
+    if (*reinit == 1) refresh_params(c);
+    else { compute_cob(c); }
+}
+void get_forcing_(double* frc) { thcmb_get_forcing(G(), frc); }
+static void insert_field(std::vector<double>& dst, const double* f) { memcpy(dst.data(), f, sizeof(double) * dst.size()); }
+void __m_inserts_MOD_insert_taux(double* f) { insert_field(G()->taux, f); }
+void __m_inserts_MOD_insert_tauy(double* f) { insert_field(G()->tauy, f); }
+void __m_inserts_MOD_insert_atmosphere_t(double* f) { insert_field(G()->tatm, f); }
+void __m_inserts_MOD_insert_emip(double* f) { insert_field(G()->emip, f); }
+void __m_mix_MOD_set_vmix_fix(int* fix) { G()->vmix_fix = *fix; }
+
+}  // extern "C"

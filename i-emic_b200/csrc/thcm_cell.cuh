@@ -1,0 +1,395 @@
+// =============================================================================
+// thcm_cell.cuh -- per-(cell,row) evaluation of the THCM dependency block: state access with the
+// ghost rules of usol, row evaluation (lin + nonlinear atoms) and `boundaries`.  Pure functions of
+// the kernel arguments, shared by all assembly kernels (thcm_assembly.cu).  THCM_HD lets the unit
+// test tests/emu/emu_cell.cpp compile the very same functions for the host to check them against
+// the oracle without a GPU (a test of the device code, not a CPU fallback: the library itself only
+// ever instantiates them in __global__ kernels).
+// =============================================================================
+#pragma once
+#include "thcm_internal.h"
+#include "thcm_slots.h"
+#ifdef __CUDACC__
+#define THCM_HD __host__ __device__ __forceinline__
+#else
+#define THCM_HD inline
+#endif
+#ifdef __CUDA_ARCH__
+#define THCM_LDG(p) __ldg(p)
+#else
+#define THCM_LDG(p) (*(p))
+#endif
+
+namespace thcm {
+
+constexpr int CELLS_PER_BLOCK = 32;
+constexpr int ASM_THREADS = 32 * NUN;
+constexpr double DROP_TOL = 1.0e-10;  // assemble.F90:115
+
+struct AsmArgs {
+    DevBlock b;
+    DevTables t;
+    const double* un;        // owned state, 6 interleaved unknowns per cell
+    const double* halo;      // halo state (nranks > 1)
+    const uint32_t* nbmask;
+    const uint8_t* surf;
+    const uint8_t* uvlive;
+    const double* frc;
+    const int* rowptr;       // static graph
+    double* val;
+    int* blockcnt;           // JAC_COUNT out / JAC_CRS in (exclusive scan)
+    int* begA; int* jcoA; double* coA;
+    double* out;             // RHS
+    double sign;             // RHS: +1 -> B (rhs_), -1 -> F = -B (THCM.C:1011)
+};
+
+// ---------------------------------------------------------------------------
+// state access with the ghost rules of usol (usrc.F90:1014-1121), GLOBAL 1-based indices
+// ---------------------------------------------------------------------------
+struct Cell {
+    int gi, gj, k;   // global Fortran indices of this cell (1-based)
+    int li, lj;      // local 0-based
+};
+
+THCM_HD double raw(const AsmArgs& a, int gi, int gj, int k, int var /*0..5*/) {
+    const DevBlock& b = a.b;
+    int ie = gi - 1 - b.i0, je = gj - 1 - b.j0, kk = k - 1;
+    if (b.wrap_x) { if (ie < 0) ie += b.n0; else if (ie >= b.n0) ie -= b.n0; }
+    if (ie >= 0 && ie < b.n0 && je >= 0 && je < b.m0)
+        return a.un[(size_t)NUN * (((size_t)kk * b.m0 + je) * b.n0 + ie) + var];
+    // halo slot (mirror of thcm::halo_slot)
+    int wrow = b.n0 + b.halo_w + b.halo_e, hs;
+    if (je == -1) hs = kk * b.hk + (ie + b.halo_w);
+    else if (je == b.m0) hs = kk * b.hk + b.halo_s * wrow + (ie + b.halo_w);
+    else if (ie == -1) hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + je;
+    else hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + b.halo_w * b.m0 + je;
+    return a.halo[(size_t)NUN * hs + var];
+}
+
+// t, s (var 4, 5): no-flux mirror in y and (non-periodic) x, periodic copy otherwise (usrc.F90:1046-1100)
+THCM_HD double TS(const AsmArgs& a, int gi, int gj, int k, int var) {
+    const DevBlock& b = a.b;
+    if (gj < 1) gj = 1; else if (gj > b.M) gj = b.M;
+    if (!b.periodic) { if (gi < 1) gi = 1; else if (gi > b.N) gi = b.N; }
+    if (k < 1) k = 1; else if (k > b.L) k = b.L;
+    return raw(a, gi, gj, k, var);
+}
+// w (var 2): w(i,j,0) = w(i,j,l) = 0 for i in 1..n; the periodic ghost columns 0 and n+1 are copied BEFORE
+// w(:,:,l) is zeroed, so they keep the raw top-level value (usrc.F90:1051-1052 vs :1093)
+THCM_HD double WW_(const AsmArgs& a, int gi, int gj, int k) {
+    const DevBlock& b = a.b;
+    if (k < 1 || k > b.L || gj < 1 || gj > b.M) return 0.0;
+    if (gi >= 1 && gi <= b.N) return k == b.L ? 0.0 : raw(a, gi, gj, k, 2);
+    return b.periodic ? raw(a, gi, gj, k, 2) : 0.0;
+}
+// u, v (var 0, 1) on cell corners: usol's no-slip zeroing is precomputed as the uvlive box; corner 0 in a
+// periodic domain is the raw copy of corner N (usrc.F90:1049-1050) with its OWN zeroing rule
+THCM_HD double UV(const AsmArgs& a, int ic, int jc, int k, int var) {
+    const DevBlock& b = a.b;
+    if (k < 1 || k > b.L) return 0.0;   // ghost levels only feed entries that `boundaries` removes
+    int bn = b.n0 + 2, bm = b.m0 + 2;
+    int bi = ic - b.i0, bj = jc - b.j0;
+    if (!a.uvlive[((size_t)(k - 1) * bm + bj) * bn + bi]) return 0.0;
+    return raw(a, ic, jc, k, var);
+}
+
+template <int N> struct IntC { static constexpr int value = N; };
+template <int I, int N, class F> THCM_HD void static_for(F&& f) {
+    if constexpr (I < N) { f(IntC<I>{}); static_for<I + 1, N>(f); }
+}
+
+// E[slot_of(R,loc,col)] with a compile-time check that the entry is structural
+template <int R, int LOC, int COL> THCM_HD double& entref(double* E) {
+    static_assert(slot_of(R, LOC, COL) >= 0, "not a structural entry of this row");
+    return E[slot_of(R, LOC, COL)];
+}
+#define ENT(loc, col) entref<R, loc, col>(E)
+
+// ---------------------------------------------------------------------------
+// row evaluation: An = Al (lin, usrc.F90:690-785) + nonlinear atoms (usrc.F90:842-882 | 950-1007)
+// ---------------------------------------------------------------------------
+template <int R, bool JAC>
+THCM_HD void eval_row(double* E, const AsmArgs& a, const Cell& c, double sm) {
+    const DevTables& t = a.t;
+    const int gi = c.gi, gj = c.gj, k = c.k, N = a.b.N, M = a.b.M, L = a.b.L;
+    auto JT = [&](int tb, int j) { return THCM_LDG(t.jt + (size_t)tb * t.jstride + j); };
+    auto KT = [&](int tb, int kk) { return THCM_LDG(t.kt + (size_t)tb * t.kstride + kk); };
+    const double epsr = t.epsr;
+#pragma unroll
+    for (int q = 0; q < RowSlots<R>::N; q++) E[q] = 0.0;
+
+    if constexpr (R == UU || R == VV) {
+        // lin atoms exist for j = 1..m-1 only (spf.F90:34,45,62,68; 98,108,124,130), uzz/vzz for all j
+        const bool jin = gj <= M - 1;
+        const double tdz8 = KT(K_TDZI8, k);
+        // w averages of unlin(5)/vnlin(5) (spf.F90:618-628, 741-751)
+        double w23 = (WW_(a, gi, gj, k) + WW_(a, gi, gj + 1, k) + WW_(a, gi + 1, gj, k) + WW_(a, gi + 1, gj + 1, k)) * tdz8;
+        double w14 = -(WW_(a, gi, gj, k - 1) + WW_(a, gi, gj + 1, k - 1) + WW_(a, gi + 1, gj, k - 1) + WW_(a, gi + 1, gj + 1, k - 1)) * tdz8;
+        double w5 = w14 + w23;
+        const double c2x = JT(J_C2X, gj), c2y = JT(J_C2Y, gj), tanv = JT(J_TANYV, gj);
+        if constexpr (R == UU) {
+            // ---- Al(UU,UU) = -EH*(uxx+uyy+ucsi) - EV*uzz ----
+            double l2 = jin ? JT(J_LU2, gj) : 0.0, l4 = jin ? JT(J_LU4, gj) : 0.0, l6 = jin ? JT(J_LU6, gj) : 0.0;
+            double l5 = (jin ? JT(J_LU5, gj) : 0.0) - KT(K_ZU5, k);
+            double l14 = -0.0 - KT(K_ZU14, k), l23 = -0.0 - KT(K_ZU23, k);
+            // ---- nonlinear: epsr*(uux|Urux + uvy1 + uwz + uvy2) ----
+            double a8 = gi <= N - 1 ? (JAC ? 2 * UV(a, gi + 1, gj, k, 0) * c2x : UV(a, gi + 1, gj, k, 0) * c2x) : 0.0;
+            double a2 = gi >= 2 ? (JAC ? -2 * UV(a, gi - 1, gj, k, 0) * c2x : -UV(a, gi - 1, gj, k, 0) * c2x) : 0.0;
+            double a4 = gj >= 2 ? -UV(a, gi, gj - 1, k, 1) * JT(J_COSYV, gj - 1) * c2y : 0.0;
+            double a6 = gj <= M - 1 ? UV(a, gi, gj + 1, k, 1) * JT(J_COSYV, gj + 1) * c2y : 0.0;
+            double uvy2 = UV(a, gi, gj, k, 1) * tanv;
+            ENT(2, UU) = l2 + epsr * a2;
+            ENT(8, UU) = l2 + epsr * a8;
+            ENT(4, UU) = l4 + epsr * a4;
+            ENT(6, UU) = l6 + epsr * a6;
+            ENT(5, UU) = l5 + epsr * (w5 + uvy2);
+            ENT(14, UU) = l14 + epsr * w14;
+            ENT(23, UU) = l23 + epsr * w23;
+            // ---- Al(UU,VV) = -fv - EH*vxs ; Al(UU,PP) = px ----
+            double luv2 = jin ? JT(J_LUV2, gj) : 0.0, luv8 = jin ? JT(J_LUV8, gj) : 0.0, luv5 = jin ? -JT(J_CORV, gj) : 0.0;
+            double px = jin ? c2x : 0.0;
+            ENT(5, PP) = -px; ENT(6, PP) = -px; ENT(8, PP) = px; ENT(9, PP) = px;
+            if constexpr (JAC) {
+                // An(UU,VV) += epsr*(Urvy1 + Urvy2), An(UU,WW) += epsr*Urwz (usrc.F90:951-952)
+                double b4 = gj >= 2 ? -UV(a, gi, gj - 1, k, 0) * JT(J_COSYV, gj - 1) * c2y : 0.0;
+                double b6 = gj <= M - 1 ? UV(a, gi, gj + 1, k, 0) * JT(J_COSYV, gj + 1) * c2y : 0.0;
+                double b5 = UV(a, gi, gj, k, 0) * tanv;
+                ENT(2, VV) = luv2; ENT(8, VV) = luv8;
+                ENT(4, VV) = 0.0 + epsr * b4; ENT(6, VV) = 0.0 + epsr * b6;
+                ENT(5, VV) = luv5 + epsr * b5;
+                double u0 = UV(a, gi, gj, k, 0);
+                double up = (u0 + UV(a, gi, gj, k + 1, 0)) * tdz8, dn = -(u0 + UV(a, gi, gj, k - 1, 0)) * tdz8;
+                double eu = epsr * up, ed = epsr * dn;
+                ENT(5, WW) = eu; ENT(6, WW) = eu; ENT(8, WW) = eu; ENT(9, WW) = eu;
+                ENT(14, WW) = ed; ENT(15, WW) = ed; ENT(17, WW) = ed; ENT(18, WW) = ed;
+            } else {
+                ENT(2, VV) = luv2; ENT(8, VV) = luv8; ENT(5, VV) = luv5;
+            }
+        } else {
+            // ---- Al(VV,VV) = -EH*(vxx+vyy+vcsi) - EV*vzz ----
+            double l2 = jin ? JT(J_LV2, gj) : 0.0, l4 = jin ? JT(J_LV4, gj) : 0.0, l6 = jin ? JT(J_LV6, gj) : 0.0;
+            double l5 = (jin ? JT(J_LV5, gj) : 0.0) - KT(K_ZU5, k);
+            double l14 = -0.0 - KT(K_ZU14, k), l23 = -0.0 - KT(K_ZU23, k);
+            // nonlinear: epsr*(uvx + vvy|Vrvy + vwz)
+            double a8 = gi <= N - 1 ? UV(a, gi + 1, gj, k, 0) * c2x : 0.0;
+            double a2 = gi >= 2 ? -UV(a, gi - 1, gj, k, 0) * c2x : 0.0;
+            double a6 = gj <= M - 1 ? (JAC ? 2 * UV(a, gi, gj + 1, k, 1) * JT(J_COSYV, gj + 1) * c2y : UV(a, gi, gj + 1, k, 1) * JT(J_COSYV, gj + 1) * c2y) : 0.0;
+            double a4 = gj >= 2 ? (JAC ? -2 * UV(a, gi, gj - 1, k, 1) * JT(J_COSYV, gj - 1) * c2y : -UV(a, gi, gj - 1, k, 1) * JT(J_COSYV, gj - 1) * c2y) : 0.0;
+            ENT(2, VV) = l2 + epsr * a2;
+            ENT(8, VV) = l2 + epsr * a8;
+            ENT(4, VV) = l4 + epsr * a4;
+            ENT(6, VV) = l6 + epsr * a6;
+            ENT(5, VV) = l5 + epsr * w5;
+            ENT(14, VV) = l14 + epsr * w14;
+            ENT(23, VV) = l23 + epsr * w23;
+            // ---- Al(VV,UU) = fu - EH*uxs ; Al(VV,PP) = py ----
+            double lvu2 = jin ? JT(J_LVU2, gj) : 0.0, lvu8 = jin ? JT(J_LVU8, gj) : 0.0, lvu5 = jin ? JT(J_CORV, gj) : 0.0;
+            double py = jin ? t.dyi : 0.0;
+            ENT(5, PP) = -py; ENT(8, PP) = -py; ENT(6, PP) = py; ENT(9, PP) = py;
+            double u0 = UV(a, gi, gj, k, 0);
+            if constexpr (JAC) {
+                // An(VV,UU) += epsr*(Urt2 + uVrx), An(VV,WW) += epsr*Vrwz (usrc.F90:965-967)
+                double b8 = gi <= N - 1 ? UV(a, gi + 1, gj, k, 1) * c2x : 0.0;
+                double b2 = gi >= 2 ? -UV(a, gi - 1, gj, k, 1) * c2x : 0.0;
+                ENT(2, UU) = lvu2 + epsr * b2; ENT(8, UU) = lvu8 + epsr * b8;
+                ENT(5, UU) = lvu5 + epsr * (2 * u0 * tanv);
+                double v0 = UV(a, gi, gj, k, 1);
+                double up = (v0 + UV(a, gi, gj, k + 1, 1)) * tdz8, dn = -(v0 + UV(a, gi, gj, k - 1, 1)) * tdz8;
+                double eu = epsr * up, ed = epsr * dn;
+                ENT(5, WW) = eu; ENT(6, WW) = eu; ENT(8, WW) = eu; ENT(9, WW) = eu;
+                ENT(14, WW) = ed; ENT(15, WW) = ed; ENT(17, WW) = ed; ENT(18, WW) = ed;
+            } else {
+                ENT(2, UU) = lvu2; ENT(8, UU) = lvu8;
+                ENT(5, UU) = lvu5 + epsr * (u0 * tanv);   // ut2 (usrc.F90:853)
+            }
+        }
+    } else if constexpr (R == WW) {
+        // Al(WW,PP) = pz ; Al(WW,TT) = -Ra(1+xes*alpt1) tbc/2 ; Al(WW,SS) = lambda Ra tbc/2 (usrc.F90:716-718)
+        ENT(5, PP) = KT(K_WP5, k); ENT(23, PP) = KT(K_WP23, k);
+        double lt = t.cWT * sm / 2., ls = t.cWS * sm / 2.;
+        double q5 = 0.0, q23 = 0.0, r5 = 0.0, r23 = 0.0;
+        if (k <= L - 1) {  // wnlin fills k = 1..l-1 only (spf.F90:503-539)
+            double t0 = TS(a, gi, gj, k, 4), t1 = TS(a, gi, gj, k + 1, 4);
+            if constexpr (JAC) {
+                q5 = (t0 + t1) / 2.; q23 = q5;
+                double s2 = t0 + t1; r5 = 0.375 * (s2 * s2); r23 = r5;
+            } else {
+                q23 = t1 / 4.; q5 = (t0 + 2 * t1) / 4.;
+                r5 = 0.125 * (t0 * t0 + 3 * t1 * t0 + 3 * t1 * t1); r23 = 0.125 * t1 * t1;
+            }
+        }
+        ENT(5, TT) = lt - t.c2 * q5 + t.c3 * r5;
+        ENT(23, TT) = lt - t.c2 * q23 + t.c3 * r23;
+        ENT(5, SS) = ls; ENT(23, SS) = ls;
+    } else if constexpr (R == PP) {
+        // Al(PP,UU) = uxc, Al(PP,VV) = vyc, Al(PP,WW) = wzc (usrc.F90:726-728, spf.F90:152-178)
+        double cp = JT(J_CP, gj), pa = JT(J_PVA, gj), pb = JT(J_PVB, gj);
+        ENT(2, UU) = -cp; ENT(4, UU) = cp; ENT(1, UU) = -cp; ENT(5, UU) = cp;
+        ENT(4, VV) = -pa; ENT(2, VV) = pb; ENT(1, VV) = -pa; ENT(5, VV) = pb;
+        ENT(5, WW) = KT(K_PW5, k); ENT(14, WW) = KT(K_PW14, k);
+    } else {
+        // ---- T / S rows: Al = -ph*(txx+tyy) - pv*tzz + RES*bi*tc (usrc.F90:758,785) ----
+        constexpr int var = (R == TT) ? 4 : 5;
+        const double c4x = JT(J_C4X, gj), c4y = JT(J_C4Y, gj), cv0 = JT(J_COSYV, gj - 1), cv1 = JT(J_COSYV, gj);
+        const double dfz = KT(K_DFZT, k), tdzi = t.tdzi2;
+        double l2 = JT(J_TT2, gj) * sm, l4 = JT(J_TT4, gj) * sm, l6 = JT(J_TT6, gj) * sm;
+        double l5 = JT(J_TT5, gj) * sm - KT(K_ZT5, k) * sm + KT(R == TT ? K_RT : K_RS, k);
+        double l14 = -0.0 - KT(K_ZT14, k) * sm, l23 = -0.0 - KT(K_ZT23, k) * sm;
+        // tnlin(3): Utrx, tnlin(5): Vtry, tnlin(7): Wtrz -- identical in rhs and jacobian (usrc.F90:869-872, 983-991)
+        double x2 = -(UV(a, gi - 1, gj, k, 0) + UV(a, gi - 1, gj - 1, k, 0)) * c4x * sm;
+        double x8 = (UV(a, gi, gj, k, 0) + UV(a, gi, gj - 1, k, 0)) * c4x * sm;
+        double x5 = x2 + x8;
+        double y4 = -(UV(a, gi, gj - 1, k, 1) + UV(a, gi - 1, gj - 1, k, 1)) * c4y * cv0 * sm;
+        double y6 = (UV(a, gi, gj, k, 1) + UV(a, gi - 1, gj, k, 1)) * c4y * cv1 * sm;
+        double y5 = y4 + y6;
+        double z14 = -WW_(a, gi, gj, k - 1) * sm * tdzi / dfz;
+        double z23 = WW_(a, gi, gj, k) * sm * tdzi / dfz;
+        double z5 = z14 + z23;
+        ENT(2, R) = l2 + x2; ENT(8, R) = l2 + x8;
+        ENT(4, R) = l4 + y4; ENT(6, R) = l6 + y6;
+        ENT(5, R) = l5 + x5 + y5 + z5;
+        ENT(14, R) = l14 + z14; ENT(23, R) = l23 + z23;
+        if constexpr (JAC) {
+            // tnlin(2): urTx, tnlin(4): vrTy, tnlin(6): wrTz (usrc.F90:988-990, 1004-1006)
+            double tc = TS(a, gi, gj, k, var);
+            double ux_w = -(tc + TS(a, gi - 1, gj, k, var)) * c4x * sm;
+            double ux_e = (TS(a, gi + 1, gj, k, var) + tc) * c4x * sm;
+            ENT(2, UU) = ux_w; ENT(4, UU) = ux_e; ENT(1, UU) = ux_w; ENT(5, UU) = ux_e;
+            double vy_s = -c4y * (tc + TS(a, gi, gj - 1, k, var)) * cv0 * sm;
+            double vy_n = c4y * (TS(a, gi, gj + 1, k, var) + tc) * cv1 * sm;
+            ENT(4, VV) = vy_s; ENT(1, VV) = vy_s; ENT(5, VV) = vy_n; ENT(2, VV) = vy_n;
+            ENT(14, WW) = -tdzi * sm * (tc + TS(a, gi, gj, k - 1, var)) / dfz;
+            ENT(5, WW) = k <= L - 1 ? tdzi * sm * (TS(a, gi, gj, k + 1, var) + tc) / dfz : 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// boundaries (boundary.F90:80-387) on the structural entries of row R.  Written as a transliteration
+// of the reference's statement sequence; statements that touch structurally-zero entries vanish at
+// compile time (slot_of(...) < 0).  nb: bit loc-1 = neighbour loc is LAND (bit 4: centre not OCEAN),
+// bits 27..31 = southee, easteast, northee, nnorthee, landm(i,j+2,k).
+// ---------------------------------------------------------------------------
+template <int R, int DST, int SRC, int COL> THCM_HD void addcol(double* E) {
+    if constexpr (slot_of(R, SRC, COL) >= 0) {
+        static_assert(slot_of(R, DST, COL) >= 0, "fold target must be a structural entry");
+        E[slot_of(R, DST, COL)] = E[slot_of(R, DST, COL)] + E[slot_of(R, SRC, COL)];
+    }
+}
+template <int R, int LOC, int COL> THCM_HD void setent(double* E, double v) {
+    if constexpr (slot_of(R, LOC, COL) >= 0) E[slot_of(R, LOC, COL)] = v;
+}
+template <int R, int LOC> THCM_HD void zloc(double* E) {
+    setent<R, LOC, 1>(E, 0.0); setent<R, LOC, 2>(E, 0.0); setent<R, LOC, 3>(E, 0.0);
+    setent<R, LOC, 4>(E, 0.0); setent<R, LOC, 5>(E, 0.0); setent<R, LOC, 6>(E, 0.0);
+}
+template <int R, int LOC> THCM_HD void zuv(double* E) { setent<R, LOC, UU>(E, 0.0); setent<R, LOC, VV>(E, 0.0); }
+template <int R, int ROW> THCM_HD void zrow(double* E) {
+    if constexpr (R == ROW) {
+#pragma unroll
+        for (int q = 0; q < RowSlots<R>::N; q++) E[q] = 0.0;
+    }
+}
+// "row ROW becomes the identity row": An(:,ROW,:)=0; An(5,:,ROW)=0; An(5,ROW,ROW)=1 (boundary.F90:256-266 etc.)
+template <int R, int ROW> THCM_HD void identity_row(double* E) {
+    zrow<R, ROW>(E);
+    setent<R, 5, ROW>(E, 0.0);
+    if constexpr (R == ROW) E[slot_of(R, 5, ROW)] = 1.0;
+}
+
+template <int R>
+THCM_HD void boundaries(double* E, uint32_t nb, bool i_lt_n, bool j_lt_m) {
+    auto land = [&](int loc) { return (nb >> (loc - 1)) & 1u; };
+    const bool southee = (nb >> 27) & 1u, easteast = (nb >> 28) & 1u, northee = (nb >> 29) & 1u, nnorthee = (nb >> 30) & 1u,
+               nn2 = (nb >> 31) & 1u;
+    if (!land(5)) {  // centre == OCEAN
+        if (land(14)) {  // bottom
+            if (land(11) && land(10) && land(13)) { addcol<R, 1, 10, UU>(E); addcol<R, 1, 10, VV>(E); }
+            zuv<R, 10>(E);
+            if (land(11) && land(18) && land(15)) { addcol<R, 2, 11, UU>(E); addcol<R, 2, 11, VV>(E); }  // sic: neastb, boundary.F90:91
+            zuv<R, 11>(E);
+            if (land(17) && land(16) && land(13)) { addcol<R, 4, 13, UU>(E); addcol<R, 4, 13, VV>(E); }
+            zuv<R, 13>(E);
+            if (land(17) && land(18) && land(15)) { addcol<R, 5, 14, UU>(E); addcol<R, 5, 14, VV>(E); }
+            addcol<R, 5, 14, TT>(E); addcol<R, 5, 14, SS>(E);
+            zloc<R, 14>(E);
+        }
+        if (land(10)) zloc<R, 10>(E);
+        if (land(11)) zloc<R, 11>(E);
+        if (land(12)) zloc<R, 12>(E);
+        if (land(13)) zloc<R, 13>(E);
+        if (land(15)) zloc<R, 15>(E);
+        if (land(16)) zloc<R, 16>(E);
+        if (land(17)) zloc<R, 17>(E);
+        if (land(18)) zloc<R, 18>(E);
+        if (land(23)) {  // top
+            if (land(20) && land(19) && land(22)) { addcol<R, 1, 19, UU>(E); addcol<R, 1, 19, VV>(E); }
+            zuv<R, 19>(E);
+            if (land(20) && land(21) && land(24)) { addcol<R, 2, 20, UU>(E); addcol<R, 2, 20, VV>(E); }
+            zuv<R, 20>(E);
+            if (land(26) && land(25) && land(22)) { addcol<R, 4, 22, UU>(E); addcol<R, 4, 22, VV>(E); }
+            zuv<R, 22>(E);
+            if (land(26) && land(27) && land(24)) { addcol<R, 5, 23, UU>(E); addcol<R, 5, 23, VV>(E); }
+            addcol<R, 5, 23, TT>(E); addcol<R, 5, 23, SS>(E);
+            zloc<R, 23>(E);
+            zrow<R, WW>(E);
+            // 1e-10 placeholders that the strict threshold later drops (boundary.F90:173-176, assemble.F90:115)
+            setent<R, 5, WW>(E, 1.0e-10); setent<R, 6, WW>(E, 1.0e-10); setent<R, 8, WW>(E, 1.0e-10); setent<R, 9, WW>(E, 1.0e-10);
+            if constexpr (R == WW) E[slot_of(R, 5, WW)] = 1.0;
+        }
+        if (land(19)) zloc<R, 19>(E);
+        if (land(20)) zloc<R, 20>(E);
+        if (land(21)) zloc<R, 21>(E);
+        if (land(22)) zloc<R, 22>(E);
+        if (land(24)) zloc<R, 24>(E);
+        if (land(25)) zloc<R, 25>(E);
+        if (land(26)) zloc<R, 26>(E);
+        if (land(27)) zloc<R, 27>(E);
+        if (land(1)) zuv<R, 1>(E);
+        if (land(2)) { addcol<R, 5, 2, TT>(E); addcol<R, 5, 2, SS>(E); zloc<R, 2>(E); zuv<R, 1>(E); }
+        if (land(3)) { zuv<R, 2>(E); zuv<R, 3>(E); }
+        else if (j_lt_m) { if (nn2) zuv<R, 3>(E); }
+        if (land(4)) { addcol<R, 5, 4, SS>(E); addcol<R, 5, 4, TT>(E); zloc<R, 4>(E); zuv<R, 1>(E); }
+        if (land(6)) {
+            zuv<R, 2>(E);
+            if constexpr (R == PP) { setent<R, 2, UU>(E, 0.0); setent<R, 2, VV>(E, 0.0); setent<R, 5, UU>(E, 0.0); setent<R, 5, VV>(E, 0.0); }
+            identity_row<R, VV>(E);
+            identity_row<R, UU>(E);
+            addcol<R, 5, 6, SS>(E); addcol<R, 5, 6, TT>(E);
+            zloc<R, 6>(E);
+        } else if (j_lt_m) {
+            if (nn2) { zuv<R, 3>(E); zuv<R, 6>(E); }
+        }
+        if (land(7)) { zuv<R, 4>(E); zuv<R, 7>(E); }
+        else if (i_lt_n) { if (southee) zuv<R, 7>(E); }
+        if (land(8)) {
+            zuv<R, 4>(E);
+            if constexpr (R == PP) { setent<R, 4, UU>(E, 0.0); setent<R, 4, VV>(E, 0.0); setent<R, 5, UU>(E, 0.0); setent<R, 5, VV>(E, 0.0); }
+            identity_row<R, UU>(E);
+            identity_row<R, VV>(E);
+            addcol<R, 5, 8, SS>(E); addcol<R, 5, 8, TT>(E);
+            zloc<R, 8>(E);
+            zuv<R, 7>(E);
+        } else if (i_lt_n) {
+            if (easteast) { zuv<R, 7>(E); zuv<R, 8>(E); }
+        }
+        if (land(9)) {
+            identity_row<R, UU>(E);
+            identity_row<R, VV>(E);
+            zuv<R, 7>(E);
+        } else if (i_lt_n || j_lt_m) {
+            if (i_lt_n) {
+                if (northee) { zuv<R, 8>(E); zuv<R, 9>(E); }
+                else if (j_lt_m) { if (nnorthee) zuv<R, 9>(E); }
+            }
+            if (j_lt_m) { if (nn2) { zuv<R, 6>(E); zuv<R, 9>(E); } }
+        }
+    } else {  // centre on land: identity rows (boundary.F90:381-386)
+#pragma unroll
+        for (int q = 0; q < RowSlots<R>::N; q++) E[q] = 0.0;
+        E[slot_of(R, 5, R)] = 1.0;
+    }
+}
+
+
+}  // namespace thcm

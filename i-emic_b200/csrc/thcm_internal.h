@@ -1,0 +1,193 @@
+// Internal declarations of libthcm_b200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/thcm_b200.h"
+
+namespace thcm {
+
+// par.F90:17-81
+constexpr int NUN = 6, NP = 27, NPAR = 30;
+enum { AL_T = 1, RAYL, EK_V, EK_H, ROSB, MIXP, RESC, SPL1, HMTP, SUNP, PE_H, PE_V, P_VC, LAMB, SALT, WIND, TEMP,
+       BIOT, COMB, ARCL, NLES, IFRICB, CONT, ENER, ALPC, CMPR, FPER, SPER, MKAP, SPL2 };
+enum { UU = 1, VV, WW, PP, TT, SS };
+enum { OCEAN = 0, LAND = 1, WATER = 2, PERIO = 3 };
+
+// ---- 1-D coefficient tables (host-computed with glibc libm, uploaded on every parameter change) ----
+// j-tables are indexed by GLOBAL j in 0..M+1, k-tables by k in 0..L+1.
+enum JT {
+    J_LU2, J_LU4, J_LU6, J_LU5,      // Al(UU,UU): -(EH*uxx2), -(EH*uyy4), -(EH*uyy6), -(EH*((uxx5+uyy5)+ucsi5))
+    J_LUV2, J_LUV8,                  // Al(UU,VV) loc 2/8: -(EH*vxs)
+    J_CORV,                          // sin(yv)*coriolis_on
+    J_C2X, J_C2Y,                    // 1/(2 cos(yv) dx), 1/(2 cos(yv) dy)
+    J_COSYV, J_TANYV,                // cos(yv_j), tan(yv_j)
+    J_LV2, J_LV4, J_LV6, J_LV5,      // Al(VV,VV)
+    J_LVU2, J_LVU8,                  // Al(VV,UU) loc 2/8: -(EH*uxs)
+    J_CP,                            // 1/(2 cos(y) dx)            (pderiv 1)
+    J_PVA, J_PVB,                    // cos(yv_{j-1})*c, cos(yv_j)*c with c = 1/(2 cos(y) dy)  (pderiv 2)
+    J_TT2, J_TT4, J_TT6, J_TT5,      // Al(TT,TT)=Al(SS,SS) horizontal part at surface-mask 1
+    J_C4X, J_C4Y,                    // 1/(4 cos(y) dx), 1/(4 cos(y) dy)
+    J_COUNT
+};
+enum KT {
+    K_ZU5, K_ZU14, K_ZU23,           // EV*uzz(5|14|23)
+    K_TDZI8,                         // 1/(8 dfzT dz)
+    K_WP5, K_WP23,                   // gradp(3)
+    K_PW5, K_PW14,                   // pderiv(3)
+    K_ZT5, K_ZT14, K_ZT23,           // pv*tzz(5|14|23) at surface-mask 1
+    K_DFZT,
+    K_RT, K_RS,                      // (TRES*bi)*tc5, (SRES*bi)*sc5
+    K_COUNT
+};
+
+struct DevTables {
+    const double* jt;  // [J_COUNT][jstride]
+    const double* kt;  // [K_COUNT][kstride]
+    int jstride, kstride;
+    double epsr, dyi, cWT, cWS, c2, c3, tdzi2;
+};
+
+// ---- local block of the global grid (TRIOS_Domain.C:201-315 decomposition, global indexing kept) ----
+struct Block {
+    int N, M, L;        // global sizes
+    int i0, j0;         // 0-based global offset of the first owned cell
+    int n0, m0;         // owned cells in x, y (full depth L)
+    int npN, npM, pidN, pidM, rank, nranks;
+    int periodic;       // global periodicity in x
+    int wrap_x;         // periodic and a single rank in x: wrap by index, no x-halo
+    int halo_w, halo_e, halo_s, halo_n;  // 1 if a halo strip exists on that side
+    // halo cells per level: south row, north row (both n0 + halo_w + halo_e wide incl. corners), west col, east col
+    int hk;             // halo cells per k level
+    int ncell() const { return n0 * m0 * L; }
+    int ndim() const { return NUN * ncell(); }
+    int nhalo_cells() const { return hk * L; }
+};
+
+// device view used by the assembly kernels
+struct DevBlock {
+    int N, M, L, i0, j0, n0, m0, periodic, wrap_x, halo_w, halo_e, halo_s, halo_n, hk, ncell;
+};
+
+// class tables: position of every canonical slot inside the sorted graph row, per boundary class
+// class bits: 1 i==first, 2 i==last, 4 j==first, 8 j==last, 16 k==first, 32 k==last (GLOBAL indices)
+constexpr int NCLASS = 64;
+constexpr int NSLOT_TOTAL = 104;
+struct ClassTables {
+    int8_t pos[NCLASS][NSLOT_TOTAL];  // position within its row, -1 = not in graph (clipped)
+    uint8_t rowlen[NCLASS][NUN];
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace thcm
+
+struct thcmb_ctx {
+    thcmb_settings s;
+    thcm::Block blk;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // ---- host model state ----
+    double par[thcm::NPAR + 1];
+    double dx, dy, dz, QTnd, QSnd;
+    std::vector<double> x, y, z, xu, yv, zw, ze, zwe, dfzT, dfzW;  // GLOBAL grid, Fortran index = vector index
+    std::vector<int> landm;  // GLOBAL (0:N+1,0:M+1,0:L+1) after init's frame rules
+    std::vector<double> taux, tauy, tatm, emip, spert, adapted_emip;  // GLOBAL N*M surface fields
+    std::vector<double> frc_local;   // owned rows, masked by the rows `boundaries` turns into identity rows
+    std::vector<double> frc_raw;     // owned rows, as `forcing` leaves it
+    bool frc_masked = false;         // get_forcing_ semantics (boundary.F90 zeroes Frc lazily inside rhs/matrix)
+    std::vector<double> cob_local;
+    std::vector<double> jt_host, kt_host;
+    thcm::DevTables tab;
+    // ---- static device data ----
+    double *d_jt = nullptr, *d_kt = nullptr;
+    uint32_t* d_nbmask = nullptr;   // per owned cell
+    uint8_t* d_surf = nullptr;      // per owned column: 1 - landm(i,j,L)
+    uint8_t* d_uvlive = nullptr;    // (n0+2)(m0+2)L corner box: 1 if usol keeps u,v there
+    uint8_t* d_cls = nullptr;       // per owned cell: boundary class (0..63)
+    double* d_frc = nullptr;        // owned rows (masked)
+    int *d_rowptr = nullptr, *d_col = nullptr;  // static graph, local column ids
+    double* d_val = nullptr;        // Jacobian values in graph order
+    long long gnnz = 0;
+    std::vector<int> rowptr_host, col_host, halo_gid, local_gid;
+    // ---- halo exchange ----
+    double *d_halo = nullptr;       // 6*nhalo doubles, laid out per Block::hk
+    double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+    int* d_send_idx = nullptr;      // owned-cell ids to pack, grouped by neighbour
+    int* d_recv_slot = nullptr;     // halo slot for every received cell, grouped by neighbour
+    struct Peer { int rank; int send_off, send_cnt, recv_off, recv_cnt; };
+    std::vector<Peer> peers;
+    int nsend_cells = 0, nrecv_cells = 0;
+    void* nccl_comm = nullptr;
+    // ---- workspaces ----
+    double* d_un = nullptr;         // staging for host-pointer entry points
+    double* d_tmp = nullptr;
+    double* d_partial = nullptr;    // reduction partials
+    double* d_scalars = nullptr;    // device scalars (dot results, H column)
+    double* h_scalars = nullptr;    // pinned
+    unsigned int* d_counter = nullptr;
+    int* d_blockcnt = nullptr;      // CRS count per assembly block
+    int n_asm_blocks = 0;
+    double* d_minv = nullptr;       // block-diagonal inverse, 36 per cell
+    int precon_kind = 0;
+    std::vector<double*> krylov_pool;  // device vectors reused across solves
+    long long launches = 0;
+    std::map<std::string, double> stage_ms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // borrowed host CRS pointers (m_mat::set_pointers)
+    int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
+    int vmix_fix = 1;
+};
+
+namespace thcm {
+// host side (thcm_host.cpp)
+void set_error(const std::string& msg);
+void fatal(const std::string& msg);
+bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b);
+void build_grid(thcmb_ctx* c);
+void stpnt(thcmb_ctx* c);
+void apply_landmask_rules(thcmb_ctx* c, const int* landm_in, bool fix_inversion);
+void compute_forcing(thcmb_ctx* c);
+void compute_tables(thcmb_ctx* c);
+void compute_cob(thcmb_ctx* c);
+const ClassTables& class_tables(int periodic);
+int halo_slot(const Block& b, int ie, int je, int k);  // extended local coords (-1..n0, -1..m0); -1 if not a halo cell
+// device side
+void upload_class_tables(const ClassTables& t);
+int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA);
+enum { MODE_RHS = 0, MODE_JAC_GRAPH = 1, MODE_JAC_COUNT = 2, MODE_JAC_CRS = 3 };
+int scan_block_counts(thcmb_ctx* c);
+int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
+         int nlocal, double* y);
+int halo_exchange(thcmb_ctx* c, const double* d_x);
+// vector kernels (device-scalar flavours keep the Krylov inner loops free of host syncs)
+int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out);
+int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
+int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out);
+int nccl_unique_id(void* id128);
+int nccl_init(thcmb_ctx* c, const void* id128);
+void nccl_destroy(thcmb_ctx* c);
+void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<uint8_t>& surf, std::vector<uint8_t>& uvlive,
+                       std::vector<int>& send_idx, std::vector<int>& recv_slot);
+const std::string& last_error();
+int axpby(thcmb_ctx* c, int n, double a, const double* x, double b, double* y);
+int axpy_negdev(thcmb_ctx* c, int n, const double* d_h, const double* x, double* y);          // y -= (*d_h) x
+int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, double* d_nrm);   // x /= sqrt(*d_nrm2)
+int copy(thcmb_ctx* c, int n, const double* x, double* y);
+int fill(thcmb_ctx* c, int n, double a, double* x);
+int build_blockdiag(thcmb_ctx* c);
+int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
+double* pool_vec(thcmb_ctx* c, size_t idx);
+}  // namespace thcm
+
+#define THCM_CUDA(call)                                                                           \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            thcm::fatal(std::string("CUDA error ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                        std::to_string(__LINE__));                                                \
+    } while (0)

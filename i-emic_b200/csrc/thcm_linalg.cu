@@ -1,0 +1,325 @@
+// =============================================================================
+// thcm_linalg.cu -- FP64 CSR SpMV, Krylov vector kernels, halo pack/unpack, 6x6 block-diagonal
+// preconditioner.  Replaces Epetra_CrsMatrix::Apply (Ocean.C:1369-1374), matAvec (matetc.F90:147-166)
+// and Epetra_MultiVector::Dot/Norm2/Update/Scale as used by GMRESSolver.H:177-187 / IDRSolver.H.
+// All kernels are HBM-bandwidth bound; none is a dense contraction (no tensor cores).
+// =============================================================================
+#include <cstdio>
+#include <dlfcn.h>
+#include "thcm_internal.h"
+
+namespace thcm {
+
+constexpr int NSM = 148;  // B200: 148 SMs; persistent-style grids are sized in multiples of this
+
+// ---------------------------------------------------------------------------
+// SpMV: CSR-vector with 8 lanes per row (rows hold 7..24 entries, THCM.C:2320-2325).
+// Column ids >= nlocal address the halo buffer.
+// ---------------------------------------------------------------------------
+constexpr int SPMV_LANES = 8;
+constexpr int SPMV_THREADS = 256;
+
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
+                                                                 const double* __restrict__ val, const double* __restrict__ x,
+                                                                 const double* __restrict__ halo, int nlocal, double* __restrict__ y) {
+    const int sub = threadIdx.x & (SPMV_LANES - 1);
+    const int rows_per_block = SPMV_THREADS / SPMV_LANES;
+    for (int row = blockIdx.x * rows_per_block + (threadIdx.x / SPMV_LANES); row < nrow; row += gridDim.x * rows_per_block) {
+        const int b = rp[row], e = rp[row + 1];
+        double s = 0.0;
+        for (int q = b + sub; q < e; q += SPMV_LANES) {
+            const int cidx = __ldg(col + q);
+            const double xv = cidx < nlocal ? __ldg(x + cidx) : __ldg(halo + (cidx - nlocal));
+            s += __ldg(val + q) * xv;
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 4, SPMV_LANES);
+        s += __shfl_xor_sync(0xffffffffu, s, 2, SPMV_LANES);
+        s += __shfl_xor_sync(0xffffffffu, s, 1, SPMV_LANES);
+        if (sub == 0) y[row] = s;
+    }
+}
+
+int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
+         int nlocal, double* y) {
+    const int rows_per_block = SPMV_THREADS / SPMV_LANES;
+    long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
+    int grid = (int)std::min<long long>(want, (long long)NSM * 64);
+    if (grid < 1) grid = 1;
+    spmv_csr_kernel<<<grid, SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y);
+    c->launches++;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// reductions: per-block partials (warp shuffle -> shared) -> the last block to finish sums the
+// partials in a fixed order (deterministic) and writes the device scalar.  No host sync.
+// ---------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_BLOCKS = NSM * 4;
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double wsum[RED_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < RED_THREADS / 32 ? wsum[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    __syncthreads();
+    return s;  // valid in thread 0
+}
+
+__device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out) {
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = blocksum;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) v += ((volatile double*)partial)[i];
+        double s = block_sum(v);
+        if (threadIdx.x == 0) { *out = s; *counter = 0u; }
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS) dot_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                                           double* partial, unsigned int* counter, double* out) {
+    double v = 0.0;
+    if ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) {   // 16-byte aligned: 128-bit loads
+        const int n2 = n >> 1;
+        const double2* x2 = reinterpret_cast<const double2*>(x);
+        const double2* y2 = reinterpret_cast<const double2*>(y);
+        for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n2; i += gridDim.x * RED_THREADS) {
+            double2 a = x2[i], b = y2[i];
+            v += a.x * b.x; v += a.y * b.y;
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) v += x[n - 1] * y[n - 1];
+    } else {
+        for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) v += x[i] * y[i];
+    }
+    double s = block_sum(v);
+    finish_reduction(s, partial, counter, out);
+}
+
+// fused modified Gram-Schmidt step (GMRESSolver.H:177-181): w -= h_k * v_k ; h_next = w . v_next
+// (h_k read from device memory: the previous reduction result; bitwise the same operations as dot + update)
+__global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int n, const double* __restrict__ hk, const double* __restrict__ vk,
+                                                                const double* __restrict__ vnext, double* __restrict__ w,
+                                                                double* partial, unsigned int* counter, double* out) {
+    const double h = *hk;
+    double v = 0.0;
+    for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
+        double wi = -h * vk[i] + 1.0 * w[i];   // update(-H, V[k], 1.0): this = a*A + b*this
+        w[i] = wi;
+        v += wi * vnext[i];
+    }
+    double s = block_sum(v);
+    finish_reduction(s, partial, counter, out);
+}
+
+__global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i] + b * y[i];
+}
+__global__ void axpy_negdev_kernel(int n, const double* __restrict__ h, const double* __restrict__ x, double* __restrict__ y) {
+    const double a = -(*h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i] + 1.0 * y[i];
+}
+// x *= 1/sqrt(nrm2) ; nrm = sqrt(nrm2)   (H[i+1][i] = w.norm(); w.scale(1.0 / H[i+1][i]), GMRESSolver.H:185-186)
+__global__ void scale_invsqrt_kernel(int n, const double* __restrict__ nrm2, double* __restrict__ x, double* nrm_out) {
+    const double nrm = sqrt(*nrm2);
+    const double a = 1.0 / nrm;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = a * x[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
+}
+__global__ void copy_kernel(int n, const double* __restrict__ x, double* __restrict__ y) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = x[i];
+}
+__global__ void fill_kernel(int n, double a, double* __restrict__ x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = a;
+}
+
+static inline int ew_grid(int n) {
+    long long want = ((long long)n + 255) / 256;
+    return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 16));
+}
+
+int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out) {
+    dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, x, y, c->d_partial, c->d_counter, d_out);
+    c->launches++;
+    return allreduce_dev(c, d_out, 1);
+}
+int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out) {
+    mgs_step_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, d_hk, vk, vnext, w, c->d_partial, c->d_counter, d_out);
+    c->launches++;
+    return allreduce_dev(c, d_out, 1);
+}
+int axpby(thcmb_ctx* c, int n, double a, const double* x, double b, double* y) {
+    axpby_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x, b, y); c->launches++; return 0;
+}
+int axpy_negdev(thcmb_ctx* c, int n, const double* d_h, const double* x, double* y) {
+    axpy_negdev_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, d_h, x, y); c->launches++; return 0;
+}
+int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, double* d_nrm) {
+    scale_invsqrt_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, d_nrm2, x, d_nrm); c->launches++; return 0;
+}
+int copy(thcmb_ctx* c, int n, const double* x, double* y) {
+    copy_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, x, y); c->launches++; return 0;
+}
+int fill(thcmb_ctx* c, int n, double a, double* x) {
+    fill_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x); c->launches++; return 0;
+}
+
+// ---------------------------------------------------------------------------
+// halo exchange (replaces Epetra_Import of TRIOS_Domain.C:599 / the column-map import of
+// Epetra_CrsMatrix::Apply): pack -> grouped ncclSend/ncclRecv -> unpack, all on the context's stream.
+// NCCL is bound lazily with dlopen so that single-GPU use has no NCCL dependency.
+// ---------------------------------------------------------------------------
+__global__ void halo_pack_kernel(int ncells, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ buf) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells * NUN; t += gridDim.x * blockDim.x) {
+        int cidx = t / NUN, v = t - cidx * NUN;
+        buf[t] = x[(size_t)NUN * idx[cidx] + v];
+    }
+}
+__global__ void halo_unpack_kernel(int ncells, const int* __restrict__ slot, const double* __restrict__ buf, double* __restrict__ halo) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells * NUN; t += gridDim.x * blockDim.x) {
+        int cidx = t / NUN, v = t - cidx * NUN;
+        halo[(size_t)NUN * slot[cidx] + v] = buf[t];
+    }
+}
+
+struct Id128 { char b[128]; };  // ncclUniqueId (nccl.h: struct { char internal[128]; }), passed by value
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) { set_error("cannot dlopen libnccl.so.2"); return false; }
+    auto sym = [&](const char* s) { return dlsym(g_nccl.lib, s); };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+    g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Send && g_nccl.Recv && g_nccl.AllReduce;
+}
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+int nccl_unique_id(void* id128) { if (!nccl_load()) return -1; return g_nccl.GetUniqueId(id128); }
+int nccl_init(thcmb_ctx* c, const void* id128) {
+    if (!nccl_load()) return -1;
+    Id128 id; memcpy(id.b, id128, 128);
+    THCM_CUDA(cudaSetDevice(c->device));
+    int rc = g_nccl.CommInitRank(&c->nccl_comm, c->blk.nranks, id, c->blk.rank);
+    if (rc != 0) set_error("ncclCommInitRank failed rc=" + std::to_string(rc));
+    return rc;
+}
+void nccl_destroy(thcmb_ctx* c) { if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm); c->nccl_comm = nullptr; }
+
+int allreduce_dev(thcmb_ctx* c, double* d_buf, int count) {
+    if (c->blk.nranks == 1) return 0;
+    if (!c->nccl_comm) fatal("nranks > 1 but thcmb_nccl_init was not called");
+    return g_nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, c->nccl_comm, c->stream);
+}
+
+int halo_exchange(thcmb_ctx* c, const double* d_x) {
+    if (c->blk.nranks == 1) return 0;
+    if (!c->nccl_comm) fatal("nranks > 1 but thcmb_nccl_init was not called");
+    if (c->nsend_cells > 0) {
+        halo_pack_kernel<<<ew_grid(c->nsend_cells * NUN), 256, 0, c->stream>>>(c->nsend_cells, c->d_send_idx, d_x, c->d_sendbuf);
+        c->launches++;
+    }
+    g_nccl.GroupStart();
+    for (auto& p : c->peers) {
+        if (p.send_cnt) g_nccl.Send(c->d_sendbuf + (size_t)NUN * p.send_off, (size_t)NUN * p.send_cnt, NCCL_FLOAT64, p.rank, c->nccl_comm, c->stream);
+        if (p.recv_cnt) g_nccl.Recv(c->d_recvbuf + (size_t)NUN * p.recv_off, (size_t)NUN * p.recv_cnt, NCCL_FLOAT64, p.rank, c->nccl_comm, c->stream);
+    }
+    g_nccl.GroupEnd();
+    if (c->nrecv_cells > 0) {
+        halo_unpack_kernel<<<ew_grid(c->nrecv_cells * NUN), 256, 0, c->stream>>>(c->nrecv_cells, c->d_recv_slot, c->d_recvbuf, c->d_halo);
+        c->launches++;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// 6x6 block-diagonal preconditioner (first step): extract the in-cell block
+// of the stored Jacobian, invert it with partial pivoting (w and p rows have no diagonal entry on
+// ocean cells, spf.F90:176,340), fall back to the identity when a block is numerically singular.
+// ---------------------------------------------------------------------------
+__global__ void blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
+                                       double* __restrict__ minv) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncell) return;
+    double A[NUN][NUN], B[NUN][NUN];
+    for (int r = 0; r < NUN; r++) for (int q = 0; q < NUN; q++) { A[r][q] = 0.0; B[r][q] = r == q ? 1.0 : 0.0; }
+    for (int r = 0; r < NUN; r++) {
+        int row = NUN * cell + r;
+        for (int q = rp[row]; q < rp[row + 1]; q++) {
+            int cc = col[q] - NUN * cell;
+            if (cc >= 0 && cc < NUN) A[r][cc] = val[q];
+        }
+    }
+    bool singular = false;
+    for (int p = 0; p < NUN; p++) {
+        int piv = p; double best = fabs(A[p][p]);
+        for (int r = p + 1; r < NUN; r++) if (fabs(A[r][p]) > best) { best = fabs(A[r][p]); piv = r; }
+        if (best < 1e-14) { singular = true; break; }
+        if (piv != p) for (int q = 0; q < NUN; q++) { double t = A[p][q]; A[p][q] = A[piv][q]; A[piv][q] = t; t = B[p][q]; B[p][q] = B[piv][q]; B[piv][q] = t; }
+        double d = 1.0 / A[p][p];
+        for (int q = 0; q < NUN; q++) { A[p][q] *= d; B[p][q] *= d; }
+        for (int r = 0; r < NUN; r++) if (r != p) {
+            double f = A[r][p];
+            if (f != 0.0) for (int q = 0; q < NUN; q++) { A[r][q] -= f * A[p][q]; B[r][q] -= f * B[p][q]; }
+        }
+    }
+    for (int r = 0; r < NUN; r++) for (int q = 0; q < NUN; q++)
+        minv[(size_t)cell * 36 + r * NUN + q] = singular ? (r == q ? 1.0 : 0.0) : B[r][q];
+}
+__global__ void blockdiag_apply_kernel(int ncell, const double* __restrict__ minv, const double* __restrict__ x, double* __restrict__ y) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell * NUN) return;
+    int cell = t / NUN, r = t - cell * NUN;
+    const double* M = minv + (size_t)cell * 36 + r * NUN;
+    const double* xc = x + (size_t)cell * NUN;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NUN; q++) s += M[q] * xc[q];
+    y[t] = s;
+}
+int build_blockdiag(thcmb_ctx* c) {
+    int ncell = c->blk.ncell();
+    if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));
+    blockdiag_build_kernel<<<(ncell + 127) / 128, 128, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_minv);
+    c->launches++;
+    return 0;
+}
+int apply_blockdiag(thcmb_ctx* c, const double* x, double* y) {
+    int n = c->blk.ndim();
+    blockdiag_apply_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->blk.ncell(), c->d_minv, x, y);
+    c->launches++;
+    return 0;
+}
+
+}  // namespace thcm

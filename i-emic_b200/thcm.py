@@ -1,0 +1,473 @@
+"""Host-side mirror of the reference's THCM / Ocean interface over the C ABI (include/thcm_b200.h).
+
+* :class:`THCM`   -- src/ocean/THCM.{H,C}: ``evaluate(soln, rhs, computeJac)``, ``getJacobian``,
+  ``setParameter/getParameter``, the static maximal graph, the domain decomposition queries.
+* :class:`Ocean`  -- the ``Model`` API (src/utils/Model.H:54-117, src/ocean/Ocean.C:1070-1391):
+  ``computeRHS``, ``computeJacobian``, ``applyMatrix``, ``solve``, ``getState/getRHS/getSolution``,
+  ``setPar/getPar``.
+* :class:`FortranABI` -- the gfortran-mangled symbols ``THCM.C`` binds (``init_``, ``rhs_``,
+  ``matrix_``, ...) with host numpy buffers, exactly as the reference's C++ would call them.
+
+PyTorch only provides device memory (``torch.float64`` CUDA tensors) and ``torch.distributed`` for
+exchanging the NCCL id; every kernel is in ``libthcm_b200.so``.  No CPU fallback exists.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from .params import par_index
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libthcm_b200.so")
+
+
+class Settings(C.Structure):
+    """thcmb_settings (include/thcm_b200.h).  Angles in radians."""
+    _fields_ = [("N", C.c_int), ("M", C.c_int), ("L", C.c_int),
+                ("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
+                ("hdim", C.c_double), ("qz", C.c_double), ("periodic", C.c_int),
+                ("ih", C.c_int), ("vmix", C.c_int), ("tap", C.c_int), ("rho_mixing", C.c_int), ("coriolis_on", C.c_int),
+                ("TRES", C.c_int), ("SRES", C.c_int), ("iza", C.c_int), ("ite", C.c_int), ("its", C.c_int),
+                ("coupled_T", C.c_int), ("coupled_S", C.c_int), ("forcing_type", C.c_int),
+                ("alphaT", C.c_double), ("alphaS", C.c_double),
+                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int)]
+
+    PI = 3.14159265358979323846  # THCMdefs.H:19
+
+    @classmethod
+    def from_degrees(cls, n, m, l, xmin, xmax, ymin, ymax, periodic=False, hdim=4000.0, qz=1.0, **kw):
+        """Bounds in degrees are converted like THCM.C:203-206 (value * PI_ / 180.0)."""
+        s = cls()
+        s.N, s.M, s.L = n, m, l
+        s.xmin, s.xmax = xmin * cls.PI / 180.0, xmax * cls.PI / 180.0
+        s.ymin, s.ymax = ymin * cls.PI / 180.0, ymax * cls.PI / 180.0
+        s.hdim, s.qz, s.periodic = hdim, qz, int(periodic)
+        s.ih, s.vmix, s.tap, s.rho_mixing, s.coriolis_on = 0, 0, 1, 0, 1
+        s.TRES, s.SRES, s.iza, s.ite, s.its = 1, 1, 2, 1, 1
+        s.coupled_T = s.coupled_S = s.forcing_type = 0
+        s.alphaT, s.alphaS = 1.0e-04, 7.6e-04
+        s.rank, s.nranks, s.device = 0, 1, 0
+        for k, v in kw.items():
+            if not hasattr(s, k):
+                raise KeyError(k)
+            setattr(s, k, v)
+        return s
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class KrylovResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("iters", C.c_int), ("resid", C.c_double), ("nhist", C.c_int),
+                ("n_matvec", C.c_longlong)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads libthcm_b200.so.  Fails loudly when it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "The THCM B200 path has no CPU fallback.")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, ip, dp, ll, i, d = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_longlong, C.c_int, C.c_double
+    sp = C.POINTER(Settings)
+    sig = {
+        "thcmb_default_settings": (None, [sp]),
+        "thcmb_create": (vp, [sp, vp]), "thcmb_destroy": (None, [vp]), "thcmb_last_error": (C.c_char_p, []),
+        "thcmb_local_block": (None, [vp, ip, ip, ip, ip, ip, ip]), "thcmb_ndim_local": (i, [vp]),
+        "thcmb_graph_nnz": (ll, [vp]), "thcmb_get_graph": (None, [vp, vp, vp]), "thcmb_halo_size": (i, [vp]),
+        "thcmb_halo_gids": (None, [vp, vp]), "thcmb_local_gids": (None, [vp, vp]),
+        "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
+        "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
+        "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
+        "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
+        "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
+        "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
+        "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
+        "thcmb_dot": (d, [vp, i, vp, vp]), "thcmb_nrm2": (d, [vp, i, vp]), "thcmb_axpby": (i, [vp, i, d, vp, d, vp]),
+        "thcmb_scale": (i, [vp, i, d, vp]), "thcmb_build_precon": (i, [vp, i]), "thcmb_apply_precon_dev": (i, [vp, vp, vp]),
+        "thcmb_gmres": (i, [vp, vp, vp, d, i, i, i, vp, i, C.POINTER(KrylovResult)]),
+        "thcmb_idrs": (i, [vp, vp, vp, d, i, i, vp, vp, i, C.POINTER(KrylovResult)]),
+        "thcmb_newton_step": (i, [vp, vp, vp, d, i, i, i, dp, C.POINTER(KrylovResult)]),
+        "thcmb_device_alloc": (vp, [vp, ll]), "thcmb_device_free": (None, [vp, vp]),
+        "thcmb_h2d": (i, [vp, vp, vp, ll]), "thcmb_d2h": (i, [vp, vp, vp, ll]), "thcmb_sync": (i, [vp]),
+        "thcmb_stream": (vp, [vp]), "thcmb_launch_count": (ll, [vp]), "thcmb_last_stage_ms": (d, [vp, C.c_char_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t):
+    """Device pointer of a torch CUDA float64/int32 tensor (or a raw int)."""
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if not t.is_cuda:
+        raise ValueError("expected a CUDA tensor: the THCM B200 path has no CPU fallback")
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class THCM:
+    """Mirror of the reference's THCM class (src/ocean/THCM.H) on one rank of the 2-D decomposition."""
+
+    def __init__(self, settings, landm, comm=None):
+        """settings: Settings; landm: int32[L+2, M+2, N+2] GLOBAL mask (the array THCM.C:389 reads from
+        m_global::get_landm).  comm: None or an initialised torch.distributed process group; when
+        settings.nranks > 1 it is used once to broadcast the NCCL unique id."""
+        import torch
+        self._torch = torch
+        self.L_ = load_library()
+        self.settings = settings
+        landm = np.ascontiguousarray(landm, dtype=np.int32)
+        assert landm.shape == (settings.L + 2, settings.M + 2, settings.N + 2), landm.shape
+        self.ctx = self.L_.thcmb_create(C.byref(settings), _np_ptr(landm))
+        if not self.ctx:
+            raise RuntimeError("thcmb_create failed: " + self.L_.thcmb_last_error().decode())
+        self.device = torch.device("cuda", settings.device)
+        self.ndim = self.L_.thcmb_ndim_local(self.ctx)
+        self.nnz = self.L_.thcmb_graph_nnz(self.ctx)
+        self.stream = torch.cuda.ExternalStream(self.L_.thcmb_stream(self.ctx), device=self.device)
+        if settings.nranks > 1:
+            self._init_nccl(comm)
+
+    def _init_nccl(self, comm):
+        import torch.distributed as dist
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if self.settings.rank == 0:
+            rc = self.L_.thcmb_nccl_unique_id(_np_ptr(idbuf))
+            if rc != 0:
+                raise RuntimeError("ncclGetUniqueId failed")
+        obj = [idbuf.tobytes() if self.settings.rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0, group=comm)
+        idbuf = np.frombuffer(obj[0], dtype=np.uint8).copy()
+        rc = self.L_.thcmb_nccl_init(self.ctx, _np_ptr(idbuf))
+        if rc != 0:
+            raise RuntimeError("thcmb_nccl_init failed: " + self.L_.thcmb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L_.thcmb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- decomposition / graph (TRIOS_Domain.H:114-247, THCM.C:2300-2580) ----
+    def local_block(self):
+        v = [C.c_int() for _ in range(6)]
+        self.L_.thcmb_local_block(self.ctx, *[C.byref(x) for x in v])
+        return dict(zip(("i0", "j0", "n0", "m0", "npN", "npM"), [x.value for x in v]))
+
+    def graph(self):
+        rowptr = np.empty(self.ndim + 1, dtype=np.int32)
+        col = np.empty(self.nnz, dtype=np.int32)
+        self.L_.thcmb_get_graph(self.ctx, _np_ptr(rowptr), _np_ptr(col))
+        return rowptr, col
+
+    def local_gids(self):
+        g = np.empty(self.ndim, dtype=np.int32)
+        self.L_.thcmb_local_gids(self.ctx, _np_ptr(g))
+        return g
+
+    def halo_gids(self):
+        g = np.empty(self.L_.thcmb_halo_size(self.ctx), dtype=np.int32)
+        self.L_.thcmb_halo_gids(self.ctx, _np_ptr(g))
+        return g
+
+    # ---- parameters (THCM.C:1945-1969) ----
+    def setParameter(self, name, value):
+        self.L_.thcmb_set_par(self.ctx, par_index(name), float(value))
+
+    def getParameter(self, name):
+        return self.L_.thcmb_get_par(self.ctx, par_index(name))
+
+    def getForcing(self):
+        f = np.empty(self.ndim)
+        self.L_.thcmb_get_forcing(self.ctx, _np_ptr(f))
+        return f
+
+    def getMassDiagonal(self):
+        """coB of fillcolB (assemble.F90:18-54), THCM::evaluateB."""
+        f = np.empty(self.ndim)
+        self.L_.thcmb_get_cob(self.ctx, _np_ptr(f))
+        return f
+
+    # ---- hot path ----
+    def new_vector(self):
+        return self._torch.zeros(self.ndim, dtype=self._torch.float64, device=self.device)
+
+    def _pre(self):
+        # the library runs on its own stream: order it after work queued on torch's current stream
+        self._torch.cuda.current_stream(self.device).synchronize()
+
+    def sync(self):
+        self.L_.thcmb_sync(self.ctx)
+
+    def evaluate(self, soln, rhs=None, computeJac=False):
+        """THCM::evaluate (THCM.C:957-1199): rhs <- F(soln) = A(u)u + mix - Frc (C++ sign), Jacobian values
+        into the static graph.  soln / rhs: CUDA float64 tensors of the owned unknowns."""
+        self._pre()
+        if rhs is not None:
+            self.L_.thcmb_residual_dev(self.ctx, _dev_ptr(soln), _dev_ptr(rhs))
+        if computeJac:
+            self.L_.thcmb_jacobian_dev(self.ctx, _dev_ptr(soln))
+        self.sync()
+        return True
+
+    def rhs_fortran_sign(self, soln, out):
+        self._pre()
+        self.L_.thcmb_rhs_dev(self.ctx, _dev_ptr(soln), _dev_ptr(out))
+        self.sync()
+
+    def getJacobian(self):
+        """(rowptr, col, values) of the local Jacobian: numpy graph + a CUDA tensor copy of the values."""
+        torch = self._torch
+        rowptr, col = self.graph()
+        val = torch.from_numpy(self.jacobian_values_host()).to(self.device)
+        return rowptr, col, val
+
+    def jacobian_values_host(self):
+        tmp = np.empty(self.nnz)
+        self.L_.thcmb_d2h(self.ctx, _np_ptr(tmp), C.c_void_p(self.L_.thcmb_jacobian_values(self.ctx)), self.nnz * 8)
+        return tmp
+
+    def jacobian_crs(self, soln):
+        """Fortran-order thresholded CRS (begA, jcoA, coA), 1-based, as matrix_ fills it (assemble.F90:57-139)."""
+        torch = self._torch
+        self._pre()
+        beg = torch.empty(self.ndim + 1, dtype=torch.int32, device=self.device)
+        jco = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+        co = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        nnz = self.L_.thcmb_jacobian_crs_dev(self.ctx, _dev_ptr(soln), _dev_ptr(beg), _dev_ptr(jco), _dev_ptr(co))
+        return beg, jco[:nnz], co[:nnz]
+
+    def applyMatrix(self, v, out):
+        self._pre()
+        self.L_.thcmb_spmv_dev(self.ctx, _dev_ptr(v), _dev_ptr(out))
+        self.sync()
+
+    def dot(self, x, y):
+        self._pre()
+        return self.L_.thcmb_dot(self.ctx, x.numel(), _dev_ptr(x), _dev_ptr(y))
+
+    def norm(self, x):
+        self._pre()
+        return self.L_.thcmb_nrm2(self.ctx, x.numel(), _dev_ptr(x))
+
+    def update(self, y, a, x, b):
+        """y = a*x + b*y (Vector::update of GMRESSolverDecl.H:12-14)."""
+        self._pre()
+        self.L_.thcmb_axpby(self.ctx, y.numel(), float(a), _dev_ptr(x), float(b), _dev_ptr(y))
+        self.sync()
+
+    def buildPreconditioner(self, kind=1):
+        self.L_.thcmb_build_precon(self.ctx, int(kind))
+        self.sync()
+
+    def applyPrecon(self, v, out):
+        self._pre()
+        self.L_.thcmb_apply_precon_dev(self.ctx, _dev_ptr(v), _dev_ptr(out))
+        self.sync()
+
+    def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096):
+        """GMRESSolver::solve (src/gmressolver/GMRESSolver.H:81-255).  Returns (KrylovResult, history)."""
+        self._pre()
+        hist = np.zeros(hist_cap)
+        res = KrylovResult()
+        flags = (1 if prec else 0) | (4 if flexible else 0)
+        self.L_.thcmb_gmres(self.ctx, _dev_ptr(b), _dev_ptr(x), tol, maxit, restart, flags, _np_ptr(hist), hist_cap, C.byref(res))
+        return res, hist[:res.nhist].copy()
+
+    def idrs(self, b, x, P_raw, tol=1e-8, maxit=500, s=4, hist_cap=4096):
+        """IDRSolver::solve (src/idrsolver/IDRSolver.H:109-340); P_raw: (s, ndim) CUDA tensor."""
+        self._pre()
+        hist = np.zeros(hist_cap)
+        res = KrylovResult()
+        self.L_.thcmb_idrs(self.ctx, _dev_ptr(b), _dev_ptr(x), tol, maxit, s, _dev_ptr(P_raw), _np_ptr(hist), hist_cap, C.byref(res))
+        return res, hist[:res.nhist].copy()
+
+    def newton_step(self, un_host, dx_host, tol=1e-4, maxit=500, restart=400, precon=1):
+        """End-to-end Newton step from pinned host buffers (torch CPU tensors or numpy arrays)."""
+        res = KrylovResult()
+        fn = C.c_double()
+        up = un_host.data_ptr() if hasattr(un_host, "data_ptr") else un_host.ctypes.data
+        dp = dx_host.data_ptr() if hasattr(dx_host, "data_ptr") else dx_host.ctypes.data
+        self.L_.thcmb_newton_step(self.ctx, C.c_void_p(up), C.c_void_p(dp), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
+        return res, fn.value
+
+    def launch_count(self):
+        return self.L_.thcmb_launch_count(self.ctx)
+
+
+class Ocean:
+    """The Model API of the reference (src/utils/Model.H:54-117) as implemented by Ocean (Ocean.C)."""
+
+    def __init__(self, settings, landm, comm=None, solver_params=None):
+        self.thcm = THCM(settings, landm, comm)
+        t = self.thcm
+        self.state_ = t.new_vector()
+        self.rhs_ = t.new_vector()
+        self.sol_ = t.new_vector()
+        sp = dict(tol=1e-4, maxit=500, restart=400, precon=1)  # run/ocean/solver_params.xml: FGMRES 1e-4, 500 its
+        sp.update(solver_params or {})
+        self.solver_params = sp
+        self.jac_valid = False
+        self.precon_valid = False
+
+    def getState(self, mode="V"):
+        return self.state_ if mode == "V" else self.state_.clone()
+
+    def getRHS(self, mode="V"):
+        return self.rhs_ if mode == "V" else self.rhs_.clone()
+
+    def getSolution(self, mode="V"):
+        return self.sol_ if mode == "V" else self.sol_.clone()
+
+    def setPar(self, name, value):
+        self.thcm.setParameter(name, value)
+        self.jac_valid = False
+
+    def getPar(self, name):
+        return self.thcm.getParameter(name)
+
+    def computeRHS(self):      # Ocean.C:1277-1295
+        self.thcm.evaluate(self.state_, self.rhs_, False)
+
+    def computeJacobian(self):  # Ocean.C:1297-1309
+        self.thcm.evaluate(self.state_, None, True)
+        self.jac_valid, self.precon_valid = True, False
+
+    def computeMassMat(self):
+        return self.thcm.getMassDiagonal()
+
+    def applyMatrix(self, v, out):  # Ocean.C:1369-1374
+        self.thcm.applyMatrix(v, out)
+
+    def buildPreconditioner(self):  # Ocean.C:1377-1391
+        if not self.precon_valid:
+            self.thcm.buildPreconditioner(self.solver_params["precon"])
+            self.precon_valid = True
+
+    def applyPrecon(self, v, out):
+        self.buildPreconditioner()
+        self.thcm.applyPrecon(v, out)
+
+    def solve(self, rhs=None):  # Ocean.C:1070-1147: sol_ = J^{-1} rhs with preconditioned FGMRES, zero initial guess
+        b = self.rhs_ if rhs is None else rhs
+        self.buildPreconditioner()
+        self.sol_.zero_()
+        sp = self.solver_params
+        res, hist = self.thcm.gmres(b, self.sol_, tol=sp["tol"], maxit=sp["maxit"], restart=sp["restart"],
+                                    prec=sp["precon"] != 0, flexible=True)
+        self.last_solve = res
+        self.last_history = hist
+        return res.status
+
+
+class FortranABI:
+    """The gfortran symbols of the B1 boundary (THCM.C:49-176) bound with host numpy buffers."""
+
+    def __init__(self):
+        L = load_library()
+        self.L_ = L
+        ip, dp, vp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p
+        L.init_.restype = None
+        L.init_.argtypes = [ip] * 4 + [dp] * 6 + [ip] * 6 + [vp] + [vp] * 5
+        L.rhs_.restype = None; L.rhs_.argtypes = [vp, vp]
+        L.matrix_.restype = None; L.matrix_.argtypes = [vp]
+        L.fillcolb_.restype = None; L.fillcolb_.argtypes = []
+        L.finalize_.restype = None; L.finalize_.argtypes = []
+        L.setparcs_.restype = None; L.setparcs_.argtypes = [ip, dp]
+        L.getparcs_.restype = None; L.getparcs_.argtypes = [ip, dp]
+        L.get_forcing_.restype = None; L.get_forcing_.argtypes = [vp]
+        L.set_landmask_.restype = None; L.set_landmask_.argtypes = [vp, ip, ip]
+        L.__m_mat_MOD_get_array_sizes.restype = None; L.__m_mat_MOD_get_array_sizes.argtypes = [ip, ip]
+        L.__m_mat_MOD_set_pointers.restype = None; L.__m_mat_MOD_set_pointers.argtypes = [ip, ip] + [vp] * 7
+        L.__m_global_MOD_initialize.restype = None
+        L.__m_global_MOD_initialize.argtypes = [ip] * 3 + [dp] * 6 + [ip] * 13 + [C.c_char_p] * 5
+
+    def global_initialize(self, s, maskfile=b""):
+        i, d = C.c_int, C.c_double
+        a = [i(s.N), i(s.M), i(s.L), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.hdim), d(s.qz), i(s.periodic), i(0), i(0),
+             i(1 if maskfile else 0), i(s.TRES), i(s.SRES), i(s.iza), i(s.ite), i(s.its), i(0), i(s.coupled_T), i(s.coupled_S),
+             i(s.forcing_type)]
+        self.L_.__m_global_MOD_initialize(*[C.byref(x) for x in a], maskfile, b"", b"", b"", b"")
+
+    def init(self, s, landm):
+        """init_ for a single-rank domain (usrc.F90:6-139), followed by get_array_sizes / set_pointers like THCM.C:619-638."""
+        i, d = C.c_int, C.c_double
+        n, m, l = s.N, s.M, s.L
+        self.n, self.m, self.l = n, m, l
+        landm = np.ascontiguousarray(landm, dtype=np.int32)
+        z = np.zeros(n * m)
+        a = [i(n), i(m), i(l), i(n * m * l), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.alphaT), d(s.alphaS), i(s.ih), i(s.vmix),
+             i(s.tap), i(s.rho_mixing), i(s.coriolis_on), i(s.periodic)]
+        self.L_.init_(*[C.byref(x) for x in a], _np_ptr(landm), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z))
+        nrows, nnz = i(), i()
+        self.L_.__m_mat_MOD_get_array_sizes(C.byref(nrows), C.byref(nnz))
+        self.ndim = nrows.value
+        # the reference allocates ndim*(6*27+1) entries (mat.F90:56-68); rows never hold more than 24
+        cap = self.ndim * 24 + 1
+        self.begA = np.zeros(self.ndim + 1, dtype=np.int32)
+        self.jcoA = np.zeros(cap, dtype=np.int32)
+        self.coA = np.zeros(cap)
+        self.coB = np.zeros(self.ndim)
+        self.begF = np.zeros(self.ndim + 1, dtype=np.int32); self.jcoF = np.zeros(self.ndim, dtype=np.int32); self.coF = np.zeros(self.ndim)
+        capi = i(cap)
+        self.L_.__m_mat_MOD_set_pointers(C.byref(nrows), C.byref(capi), _np_ptr(self.begA), _np_ptr(self.jcoA), _np_ptr(self.coA),
+                                         _np_ptr(self.coB), _np_ptr(self.begF), _np_ptr(self.jcoF), _np_ptr(self.coF))
+
+    def setparcs(self, idx, val):
+        self.L_.setparcs_(C.byref(C.c_int(par_index(idx))), C.byref(C.c_double(val)))
+
+    def getparcs(self, idx):
+        v = C.c_double()
+        self.L_.getparcs_(C.byref(C.c_int(par_index(idx))), C.byref(v))
+        return v.value
+
+    def rhs(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        B = np.empty_like(un)
+        self.L_.rhs_(_np_ptr(un), _np_ptr(B))
+        return B
+
+    def matrix(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        self.L_.matrix_(_np_ptr(un))
+        nnz = self.begA[self.ndim] - 1
+        return self.begA.copy(), self.jcoA[:nnz].copy(), self.coA[:nnz].copy(), self.coB.copy()
+
+    def get_forcing(self):
+        f = np.empty(self.ndim)
+        self.L_.get_forcing_(_np_ptr(f))
+        return f
+
+    def finalize(self):
+        self.L_.finalize_()

@@ -1,0 +1,204 @@
+/* =============================================================================
+ * thcm_b200.h -- C ABI of libthcm_b200.so, the B200-native THCM Newton-step path.
+ *
+ * Two layers:
+ *
+ *  B1  The gfortran-mangled symbols that the reference's src/ocean/THCM.C binds
+ *      (extern "C" list THCM.C:49-176, name mangling src/utils/my_f2c.H:15-17).
+ *      Same names, same by-pointer arguments, same semantics (caller-owned CRS
+ *      buffers, no return codes, one global instance per process).  They take
+ *      HOST pointers; host<->device copies happen inside.
+ *
+ *  B1' A handle-based device API (thcmb_*) so that residual, Jacobian, SpMV and
+ *      the Krylov vectors never leave HBM.  All pointers named d_* are DEVICE
+ *      pointers; everything else is host memory.
+ *
+ * All reals are IEEE FP64, all integers 32-bit.  Unknown ordering (matetc.F90:123):
+ *   row = 6*((k-1)*n*m + (j-1)*n + (i-1)) + XX,  XX in {u=1,v,w,p,T,S=6}.
+ * No CPU fallback exists: every compute entry point fails loudly (thcm_throw_error_
+ * callback if installed, else abort()) when no CUDA device is usable.
+ * ========================================================================== */
+#ifndef THCM_B200_H
+#define THCM_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* --------------------------------------------------------------------------
+ * B1: reference Fortran symbols (host pointers)
+ * ------------------------------------------------------------------------ */
+
+/* replaces m_global::initialize, src/ocean/global.F90:65-157 (THCM.C:331-338).
+ * Angles in radians.  File names are accepted but only the mask file is read
+ * (data/ in the reference holds nothing else); rd_mask=0 leaves an all-ocean mask. */
+void __m_global_MOD_initialize(int* N, int* M, int* L, double* xmin, double* xmax, double* ymin, double* ymax,
+                               double* hdim, double* qz, int* periodic, int* itopo, int* flat, int* rd_mask,
+                               int* TRES, int* SRES, int* iza, int* ite, int* its, int* rd_spertm,
+                               int* coupled_T, int* coupled_S, int* forcing_type,
+                               const char* maskfile, const char* spertmaskfile, const char* windfile,
+                               const char* sstfile, const char* sssfile);
+/* replaces m_global::get_landm (THCM.C:389): (N+2)(M+2)(L+2) ints, i fastest */
+void __m_global_MOD_get_landm(int* landm);
+void __m_global_MOD_finalize(void);
+
+/* replaces SUBROUTINE init, src/ocean/usrc.F90:6-139 (called THCM.C:603-611) */
+void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, double* ymin, double* ymax,
+           double* alphaT, double* alphaS, int* ih, int* vmix, int* tap, int* rho_mixing, int* coriolis_on,
+           int* periodic, int* landm, double* taux, double* tauy, double* tatm, double* emip, double* spert);
+/* replaces SUBROUTINE finalize, usrc.F90:143-160 */
+void finalize_(void);
+/* replaces m_mat::get_array_sizes / set_pointers, src/ocean/mat.F90:56-103 (THCM.C:619-638) */
+void __m_mat_MOD_get_array_sizes(int* nrows, int* nnz);
+void __m_mat_MOD_set_pointers(int* nrows, int* nnz, int* begA, int* jcoA, double* coA, double* coB,
+                              int* begF, int* jcoF, double* coF);
+/* replaces SUBROUTINE rhs(un,B), usrc.F90:523-603 (THCM.C:1001): B has the THCM sign, C++ negates */
+void rhs_(double* un, double* B);
+/* replaces SUBROUTINE matrix(un), usrc.F90:449-521 (THCM.C:1066): fills begA/jcoA/coA (1-based,
+ * Fortran entry order, |a|>1e-10 thresholded) and coB through the borrowed pointers */
+void matrix_(double* un);
+/* replaces SUBROUTINE fillcolB, src/ocean/assemble.F90:18-54 (THCM.C:1209) */
+void fillcolb_(void);
+/* replaces setparcs/getparcs, usrc.F90:163-198: idx 1..30 (par.F90:38-67); set re-runs forcing+lin */
+void setparcs_(int* idx, double* val);
+void getparcs_(int* idx, double* val);
+/* replaces setsres, usrc.F90:434-446 */
+void setsres_(int* sres);
+/* replaces set_landmask, usrc.F90:353-418 */
+void set_landmask_(int* landm, int* periodic, int* reinit);
+/* replaces get_forcing, src/ocean/forcing.F90:220-233 */
+void get_forcing_(double* frc);
+/* replace m_inserts::insert_{taux,tauy,atmosphere_t,emip}, src/ocean/inserts.F90 (no recompute until next setparcs) */
+void __m_inserts_MOD_insert_taux(double* f);
+void __m_inserts_MOD_insert_tauy(double* f);
+void __m_inserts_MOD_insert_atmosphere_t(double* f);
+void __m_inserts_MOD_insert_emip(double* f);
+/* replaces m_mix::set_vmix_fix, src/ocean/mix.F90:52-59 */
+void __m_mix_MOD_set_vmix_fix(int* fix);
+
+/* Callbacks the reference's Fortran calls back into C++ (THCM.C:2653,2690; GlobalDefinitions.C:145,154).
+ * When the library is linked against the reference these resolve to its definitions; standalone,
+ * weak defaults inside the library are used. */
+void thcm_forcing_integral_(double* field, double* y, int* landm, double* out);
+void thcm_throw_error_(char* msg);
+void timer_start_(const char* label);
+void timer_stop_(const char* label);
+
+/* --------------------------------------------------------------------------
+ * B1': handle-based device API
+ * ------------------------------------------------------------------------ */
+typedef struct thcmb_ctx thcmb_ctx;
+
+typedef struct thcmb_settings {
+    /* global domain (global.F90:65-157); angles in radians */
+    int N, M, L;
+    double xmin, xmax, ymin, ymax, hdim, qz;
+    int periodic;
+    /* model flags (usr.F90:50-85) */
+    int ih, vmix, tap, rho_mixing, coriolis_on, TRES, SRES, iza, ite, its, coupled_T, coupled_S, forcing_type;
+    double alphaT, alphaS;
+    /* domain decomposition (TRIOS_Domain.C:201-315): this process is rank `rank` of `nranks` */
+    int rank, nranks;
+    /* CUDA device ordinal to use */
+    int device;
+} thcmb_settings;
+
+void thcmb_default_settings(thcmb_settings* s);
+
+/* landm_global: (N+2)(M+2)(L+2) ints, i fastest, values OCEAN 0 / LAND 1 / WATER 2 / PERIO 3 (par.F90:78-81).
+ * Every rank passes the same global mask (replaces the bcast+import of THCM.C:378-565). Returns NULL on error. */
+thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global);
+void thcmb_destroy(thcmb_ctx* c);
+const char* thcmb_last_error(void);
+
+/* decomposition queries (TRIOS_Domain.H:114-247 subset) */
+void thcmb_local_block(const thcmb_ctx* c, int* i0, int* j0, int* n0, int* m0, int* npN, int* npM);
+int thcmb_ndim_local(const thcmb_ctx* c);  /* 6*n0*m0*L owned unknowns */
+long long thcmb_graph_nnz(const thcmb_ctx* c);
+/* static maximal graph of the owned rows (THCM.C:2300-2580): 0-based CSR, columns sorted ascending by global id;
+ * col[] holds LOCAL column ids: < ndim_local owned, >= ndim_local halo slot (see thcmb_halo_gids) */
+void thcmb_get_graph(const thcmb_ctx* c, int* rowptr, int* col);
+int thcmb_halo_size(const thcmb_ctx* c);              /* number of halo unknowns (6 per halo cell) */
+void thcmb_halo_gids(const thcmb_ctx* c, int* gids);  /* global id of each halo unknown */
+void thcmb_local_gids(const thcmb_ctx* c, int* gids); /* global id of each owned unknown (standard map) */
+
+/* parameters (setparcs/getparcs); set recomputes forcing and the linear tables */
+void thcmb_set_par(thcmb_ctx* c, int idx, double val);
+double thcmb_get_par(const thcmb_ctx* c, int idx);
+void thcmb_get_forcing(thcmb_ctx* c, double* frc_host);
+void thcmb_get_cob(thcmb_ctx* c, double* cob_host);
+
+/* NCCL plumbing for nranks>1: the caller creates a 128-byte ncclUniqueId on rank 0 (thcmb_nccl_unique_id),
+ * broadcasts it (torch.distributed) and every rank calls thcmb_nccl_init. */
+int thcmb_nccl_unique_id(void* id128);
+int thcmb_nccl_init(thcmb_ctx* c, const void* id128);
+
+/* ---- hot path, device pointers, asynchronous on the context's stream ---- */
+/* halo exchange of a state/Krylov vector (width 1, edges+corners, periodic wrap): fills the context's halo buffer */
+int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x);
+/* F(x): d_F = +A(u)u + mix - Frc  (the sign Ocean::computeRHS returns, THCM.C:1011); does its own halo exchange */
+int thcmb_residual_dev(thcmb_ctx* c, const double* d_un, double* d_F);
+/* THCM-sign residual exactly as rhs_ returns it (B = -Au - mix + Frc, masked) */
+int thcmb_rhs_dev(thcmb_ctx* c, const double* d_un, double* d_B);
+/* Jacobian values into the static graph (explicit zeros kept), stored inside the context */
+int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un);
+const double* thcmb_jacobian_values(const thcmb_ctx* c);   /* device pointer, graph order */
+const int* thcmb_graph_rowptr_dev(const thcmb_ctx* c);
+const int* thcmb_graph_col_dev(const thcmb_ctx* c);
+/* Fortran-order thresholded CRS on the device (count -> scan -> fill); returns nnz, arrays 1-based like matrix_ */
+long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, int* d_jcoA, double* d_coA);
+/* y = J x on the stored Jacobian (Ocean::applyMatrix, Ocean.C:1369-1374), with halo exchange when nranks>1 */
+int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y);
+/* generic CSR SpMV on caller-provided device arrays (0-based) */
+int thcmb_csr_spmv_dev(thcmb_ctx* c, int nrow, const int* d_rowptr, const int* d_col, const double* d_val,
+                       const double* d_x, double* d_y);
+
+/* vector kernels (Epetra_MultiVector::Dot/Norm2/Update/Scale as used by GMRESSolver.H / IDRSolver.H);
+ * dot/nrm2 all-reduce over ranks and return on the host */
+double thcmb_dot(thcmb_ctx* c, int n, const double* d_x, const double* d_y);
+double thcmb_nrm2(thcmb_ctx* c, int n, const double* d_x);
+int thcmb_axpby(thcmb_ctx* c, int n, double a, const double* d_x, double b, double* d_y); /* y = a x + b y */
+int thcmb_scale(thcmb_ctx* c, int n, double a, double* d_x);
+
+/* preconditioner for the in-library Krylov solvers: 0 identity, 1 6x6 block-diagonal of the stored Jacobian */
+int thcmb_build_precon(thcmb_ctx* c, int kind);
+int thcmb_apply_precon_dev(thcmb_ctx* c, const double* d_x, double* d_y);
+
+typedef struct thcmb_krylov_result {
+    int status;          /* 0 converged, 1 not converged, <0 breakdown */
+    int iters;
+    double resid;        /* final (relative for GMRES, absolute for IDR) implicit residual */
+    int nhist;           /* entries written to hist */
+    long long n_matvec;
+} thcmb_krylov_result;
+
+/* Restarted right-preconditioned (F)GMRES with modified Gram-Schmidt and Givens rotations: the algorithm of
+ * src/gmressolver/GMRESSolver.H:81-255 (minimiser scheme 'B').  d_b, d_x on device; hist (host, may be NULL)
+ * receives the scaled residual after every inner iteration.  flags: bit0 precondition, bit2 flexible. */
+int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags,
+                double* hist, int hist_cap, thcmb_krylov_result* res);
+/* IDR(s) with bi-orthogonalisation: src/idrsolver/IDRSolver.H:109-340.  d_P_raw: s vectors (s x ndim) that
+ * replace Vector::random() in createP (IDRSolver.H:84-104); orthonormalised on the device. */
+int thcmb_idrs(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int s, const double* d_P_raw,
+               double* hist, int hist_cap, thcmb_krylov_result* res);
+
+/* One Newton step from HOST buffers (the end-to-end call): H2D un, F(un), J(un), solve J dx = -F with
+ * preconditioned GMRES, D2H dx.  Returns the Krylov result; fnorm receives ||F||_2. */
+int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart,
+                      int precon_kind, double* fnorm, thcmb_krylov_result* res);
+
+/* utilities */
+void* thcmb_device_alloc(thcmb_ctx* c, long long bytes);
+void thcmb_device_free(thcmb_ctx* c, void* p);
+int thcmb_h2d(thcmb_ctx* c, void* d_dst, const void* h_src, long long bytes);
+int thcmb_d2h(thcmb_ctx* c, void* h_dst, const void* d_src, long long bytes);
+int thcmb_sync(thcmb_ctx* c);
+void* thcmb_stream(thcmb_ctx* c);               /* cudaStream_t the hot path runs on */
+long long thcmb_launch_count(const thcmb_ctx* c); /* kernels launched by this library so far */
+/* per-stage device time in ms of the last call, by the reference's profile labels (GlobalDefinitions.C:145-172):
+ * "nlin_rhs+boundaries+matAvec", "nlin_jac+boundaries+fillcolA", "matAvec", ... ; returns -1 if unknown */
+double thcmb_last_stage_ms(const thcmb_ctx* c, const char* label);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THCM_B200_H */

@@ -1,0 +1,86 @@
+"""Shared test cases: grids, masks, parameters and seeded states.
+
+Every case is a (Settings, landm, params) triple that can be handed unchanged to the oracle
+(oracle.oracle.OracleTHCM), to the CPU emulation of the device functions (tests/emu) and to the CUDA
+library (iemic_b200.THCM / FortranABI)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import iemic_b200  # noqa: E402
+from iemic_b200 import Settings, read_mask, synthetic_global_mask, all_ocean_mask, PAR_INDEX  # noqa: E402
+
+MASKS = os.path.join(ROOT, "tests", "golden", "masks")
+SEED = 20261017
+
+# parameter block of test/ocean/ocean_params.xml ("Starting Parameters") + SURVEY 8d
+DEFAULT_PARS = {"COMB": 1.0, "WIND": 1.0, "TEMP": 10.0, "SALT": 1.0}
+
+
+def natl8(**kw):      # test/ocean/ocean_params.xml: 8x8x4, North Atlantic box, non-periodic
+    s = Settings.from_degrees(8, 8, 4, 286, 350, 10, 74, periodic=False, hdim=4000.0, qz=1.0, **kw)
+    return s, read_mask(os.path.join(MASKS, "mask_natl8"), 8, 8, 4)
+
+
+def test6x6x4(**kw):
+    s = Settings.from_degrees(6, 6, 4, 286, 350, 10, 74, periodic=False, hdim=4000.0, qz=1.0, **kw)
+    return s, read_mask(os.path.join(MASKS, "test6x6x4"), 6, 6, 4)
+
+
+def gateway16(**kw):  # test/ocean/reft_ocean_params.xml: 16x16x16 periodic, mask_gateway
+    s = Settings.from_degrees(16, 16, 16, 0, 360, -60, 60, periodic=True, hdim=4000.0, qz=1.0, **kw)
+    return s, read_mask(os.path.join(MASKS, "mask_gateway"), 16, 16, 16)
+
+
+def global4deg(**kw):  # run/ocean/global/ocean_params.xml:21-42 with data/mkmask/mask_global_96x38x12
+    s = Settings.from_degrees(96, 38, 12, 0, 359.99, -85.5, 85.5, periodic=True, hdim=5000.0, qz=2.25, **kw)
+    return s, read_mask(os.path.join(MASKS, "mask_global_96x38x12"), 96, 38, 12)
+
+
+def global_synth(n, m, l, **kw):  # 2, 1, 0.5 degree synthetic grids
+    base = read_mask(os.path.join(MASKS, "mask_global_96x38x12"), 96, 38, 12)
+    s = Settings.from_degrees(n, m, l, 0, 359.99, -85.5, 85.5, periodic=True, hdim=5000.0, qz=2.25, **kw)
+    return s, synthetic_global_mask(base, n, m, l, periodic=True)
+
+
+def box(n, m, l, periodic, seed=0, land_frac=0.0, **kw):
+    """Random-topography box: stresses every branch of `boundaries` (isolated cells, steps, seams)."""
+    xmax = 359.99 if periodic else 350
+    s = Settings.from_degrees(n, m, l, 0 if periodic else 286, xmax, -60 if periodic else 10, 60 if periodic else 74,
+                              periodic=periodic, hdim=4000.0, qz=1.8 if seed % 2 else 1.0, **kw)
+    landm = all_ocean_mask(n, m, l, periodic=False)
+    if land_frac > 0:
+        rng = np.random.default_rng(1000 + seed)
+        depth = np.where(rng.random((m, n)) < land_frac, rng.integers(0, l + 1, size=(m, n)), 0)  # land levels from the bottom
+        for k in range(1, l + 1):
+            landm[k, 1:m + 1, 1:n + 1][depth >= k] = 1
+    if periodic:
+        both = (landm[:, :, 1] == 0) & (landm[:, :, n] == 0)
+        landm[:, :, 0][both] = 3
+        landm[:, :, n + 1][both] = 3
+    return s, landm
+
+
+def random_state(s, landm, scale=0.01, seed=SEED, zero_on_land=True):
+    """un = scale * N(0,1), zero on LAND cells."""
+    rng = np.random.default_rng(seed)
+    n, m, l = s.N, s.M, s.L
+    un = scale * rng.standard_normal(6 * n * m * l)
+    if zero_on_land:
+        land = (landm[1:l + 1, 1:m + 1, 1:n + 1] != 0).reshape(-1)
+        un.reshape(-1, 6)[land, :] = 0.0
+    return un
+
+
+def smooth_state(s, value=1.234):  # test_ocean.C:141
+    return np.full(6 * s.N * s.M * s.L, value)
+
+
+def apply_pars(obj, pars, setter="setpar"):
+    for k, v in pars.items():
+        getattr(obj, setter)(PAR_INDEX[k], v)

@@ -1,0 +1,113 @@
+"""ctypes front-end of tests/emu/libthcm_emu.so: the library's device functions compiled for the host (a unit-test
+harness for `pytest -m "not gpu"`, see emu_cell.cpp).  Built on demand with g++."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_CSRC = os.path.join(_ROOT, "i-emic_b200", "csrc")
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libthcm_emu.so")
+    srcs = [os.path.join(_HERE, "emu_cell.cpp"), os.path.join(_CSRC, "thcm_host.cpp")]
+    deps = srcs + [os.path.join(_CSRC, f) for f in ("thcm_cell.cuh", "thcm_internal.h", "thcm_slots.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I" + cuda_inc, "-o", so] + srcs,
+                       check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
+        for name, res, args in [("emu_create", vp, [vp, vp]), ("emu_destroy", None, [vp]), ("emu_set_par", None, [vp, i, d]),
+                                ("emu_get_par", d, [vp, i]), ("emu_ndim", i, [vp]), ("emu_gnnz", ll, [vp]), ("emu_halo_size", i, [vp]),
+                                ("emu_block", None, [vp, vp]), ("emu_graph", None, [vp, vp, vp]), ("emu_halo_gids", None, [vp, vp]),
+                                ("emu_local_gids", None, [vp, vp]), ("emu_get_forcing", None, [vp, vp, i]), ("emu_get_cob", None, [vp, vp]),
+                                ("emu_plan_sizes", None, [vp, vp, vp, vp]), ("emu_plan", None, [vp, vp, vp, vp]),
+                                ("emu_jacobian", None, [vp, vp, vp, vp]), ("emu_crs", ll, [vp, vp, vp, vp, vp, vp]),
+                                ("emu_rhs", None, [vp, vp, vp, vp])]:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EmuTHCM:
+    def __init__(self, settings, landm):
+        self.L_ = lib()
+        landm = np.ascontiguousarray(landm, dtype=np.int32)
+        self.h = self.L_.emu_create(C.byref(settings), _p(landm))
+        assert self.h
+        self.ndim = self.L_.emu_ndim(self.h)
+        self.nnz = self.L_.emu_gnnz(self.h)
+        self.nhalo = self.L_.emu_halo_size(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L_.emu_destroy(self.h)
+            self.h = None
+
+    def setpar(self, idx, v):
+        self.L_.emu_set_par(self.h, idx, float(v))
+
+    def getpar(self, idx):
+        return self.L_.emu_get_par(self.h, idx)
+
+    def block(self):
+        out = np.zeros(9, dtype=np.int32)
+        self.L_.emu_block(self.h, _p(out))
+        return dict(zip(("i0", "j0", "n0", "m0", "npN", "npM", "pidN", "pidM", "hk"), out.tolist()))
+
+    def graph(self):
+        rowptr = np.empty(self.ndim + 1, dtype=np.int32); col = np.empty(self.nnz, dtype=np.int32)
+        self.L_.emu_graph(self.h, _p(rowptr), _p(col))
+        return rowptr, col
+
+    def local_gids(self):
+        g = np.empty(self.ndim, dtype=np.int32); self.L_.emu_local_gids(self.h, _p(g)); return g
+
+    def halo_gids(self):
+        g = np.empty(max(self.nhalo, 1), dtype=np.int32); self.L_.emu_halo_gids(self.h, _p(g)); return g[:self.nhalo]
+
+    def forcing(self, masked=True):
+        f = np.empty(self.ndim); self.L_.emu_get_forcing(self.h, _p(f), int(masked)); return f
+
+    def cob(self):
+        f = np.empty(self.ndim); self.L_.emu_get_cob(self.h, _p(f)); return f
+
+    def plan(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.L_.emu_plan_sizes(self.h, C.byref(a), C.byref(b), C.byref(c))
+        peers = np.zeros((max(a.value, 1), 5), dtype=np.int32); send = np.zeros(max(b.value, 1), dtype=np.int32); recv = np.zeros(max(c.value, 1), dtype=np.int32)
+        self.L_.emu_plan(self.h, _p(peers), _p(send), _p(recv))
+        return peers[:a.value], send[:b.value], recv[:c.value]
+
+    def _halo(self, halo):
+        return np.ascontiguousarray(halo, dtype=np.float64) if halo is not None else np.zeros(max(self.nhalo, 1))
+
+    def jacobian(self, un, halo=None):
+        un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
+        val = np.empty(self.nnz); self.L_.emu_jacobian(self.h, _p(un), _p(h), _p(val)); return val
+
+    def crs(self, un, halo=None):
+        un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
+        beg = np.empty(self.ndim + 1, dtype=np.int32); jco = np.empty(self.nnz, dtype=np.int32); co = np.empty(self.nnz)
+        nnz = self.L_.emu_crs(self.h, _p(un), _p(h), _p(beg), _p(jco), _p(co))
+        return beg, jco[:nnz].copy(), co[:nnz].copy()
+
+    def rhs(self, un, halo=None):
+        un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
+        B = np.empty(self.ndim); self.L_.emu_rhs(self.h, _p(un), _p(h), _p(B)); return B

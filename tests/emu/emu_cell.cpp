@@ -1,0 +1,170 @@
+// =============================================================================
+// emu_cell.cpp -- CPU UNIT TEST HARNESS for the device code (test infrastructure only).
+//
+// Compiles the library's own per-cell device functions (i-emic_b200/csrc/thcm_cell.cuh: eval_row,
+// boundaries, the usol ghost rules) and host setup (thcm_host.cpp) with g++ and runs them cell by
+// cell in the order the CUDA kernels use, so that `pytest -m "not gpu"` can compare the kernel
+// arithmetic, the class/slot tables, the static graph and the halo plan with the oracle on a box
+// without a GPU.  It is NOT part of libthcm_b200.so and is never a fallback for it.
+// =============================================================================
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../i-emic_b200/csrc/thcm_cell.cuh"
+
+using namespace thcm;
+
+extern "C" void thcm_throw_error_(char* msg) { fprintf(stderr, "emu: %s\n", msg); }
+
+namespace {
+struct Emu {
+    thcmb_ctx c;
+    std::vector<uint32_t> nbmask; std::vector<uint8_t> surf, uvlive; std::vector<int> send_idx, recv_slot;
+};
+
+AsmArgs make_args(Emu* e, const double* un, const double* halo) {
+    thcmb_ctx* c = &e->c;
+    const Block& b = c->blk;
+    AsmArgs a;
+    a.b = DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
+    a.t = c->tab; a.t.jt = c->jt_host.data(); a.t.kt = c->kt_host.data();
+    a.un = un; a.halo = halo; a.nbmask = e->nbmask.data(); a.surf = e->surf.data(); a.uvlive = e->uvlive.data();
+    a.frc = c->frc_local.data(); a.rowptr = c->rowptr_host.data();
+    a.val = nullptr; a.blockcnt = nullptr; a.begA = nullptr; a.jcoA = nullptr; a.coA = nullptr; a.out = nullptr; a.sign = 1.0;
+    return a;
+}
+
+// one (cell,row): the sequence of do_row() in thcm_assembly.cu
+template <int R, bool JAC>
+void cell_row(const AsmArgs& a, int cell, double* E, Cell& c, int& cls, uint32_t& nb) {
+    const DevBlock& b = a.b;
+    int li = cell % b.n0, r = cell / b.n0, lj = r % b.m0, k0 = r / b.m0;
+    c.li = li; c.lj = lj; c.gi = b.i0 + li + 1; c.gj = b.j0 + lj + 1; c.k = k0 + 1;
+    nb = a.nbmask[cell];
+    double sm = (double)(int)(int8_t)a.surf[lj * b.n0 + li];
+    cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) | (c.k == b.L ? 32 : 0);
+    if (!((nb >> 4) & 1u)) eval_row<R, JAC>(E, a, c, sm);
+    boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
+    for (int q = 0; q < RowSlots<R>::N; q++) E[q] = std::fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
+}
+
+template <int R>
+void jac_row(Emu* e, const AsmArgs& a, int cell, double* val, int* beg_cnt, std::vector<int>* jco, std::vector<double>* co) {
+    double E[RowSlots<R>::N]; Cell c{0, 0, 0, 0, 0}; int cls; uint32_t nb;
+    cell_row<R, true>(a, cell, E, c, cls, nb);
+    const ClassTables& ct = class_tables(a.b.periodic);
+    int base = a.rowptr[NUN * cell + R - 1];
+    int cnt = 0;
+    for (int q = 0; q < RowSlots<R>::N; q++) {
+        int p = ct.pos[cls][ROW_OFF[R - 1] + q];
+        if (val && p >= 0) val[base + p] = E[q];
+        if (E[q] != 0.0) {
+            cnt++;
+            if (jco) {
+                int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
+                int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
+                if (a.b.periodic) { if (gi2 == 0) gi2 = a.b.N; else if (gi2 == a.b.N + 1) gi2 = 1; }
+                jco->push_back(NUN * ((k2 - 1) * a.b.N * a.b.M + a.b.N * (gj2 - 1) + gi2 - 1) + col);
+                co->push_back(E[q]);
+            }
+        }
+    }
+    if (beg_cnt) beg_cnt[NUN * cell + R - 1] = cnt;
+}
+
+template <int R>
+void rhs_row(const AsmArgs& a, int cell, double* out) {
+    const DevBlock& b = a.b;
+    double E[RowSlots<R>::N]; Cell c{0, 0, 0, 0, 0}; int cls; uint32_t nb;
+    cell_row<R, false>(a, cell, E, c, cls, nb);
+    double s = 0.0;
+    for (int q = 0; q < RowSlots<R>::N; q++) {
+        int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
+        int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
+        bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
+        if (E[q] != 0.0 && inside) s = E[q] * raw(a, gi2, gj2, k2, col - 1) + s;
+    }
+    int row = NUN * cell + R - 1;
+    double B = -s - 0.0 + a.frc[row] - 0.0;
+    B = B * (((nb >> 4) & 1u) ? 0.0 : 1.0);
+    out[row] = a.sign * B;
+}
+}  // namespace
+
+extern "C" {
+
+void* emu_create(const thcmb_settings* s, const int* landm) {
+    Emu* e = new Emu();
+    thcmb_ctx* c = &e->c;
+    c->s = *s;
+    if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) { delete e; return nullptr; }
+    size_t nm = (size_t)s->N * s->M;
+    for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
+    build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false);
+    build_static_host(c, e->nbmask, e->surf, e->uvlive, e->send_idx, e->recv_slot);
+    compute_forcing(c); compute_tables(c); compute_cob(c);
+    return e;
+}
+void emu_destroy(void* h) { delete (Emu*)h; }
+void emu_set_par(void* h, int idx, double v) { thcmb_ctx* c = &((Emu*)h)->c; c->par[idx] = v; compute_forcing(c); compute_tables(c); compute_cob(c); }
+double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
+int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
+long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }
+int emu_halo_size(void* h) { return NUN * ((Emu*)h)->c.blk.nhalo_cells(); }
+void emu_block(void* h, int* out) { const Block& b = ((Emu*)h)->c.blk; int v[] = {b.i0, b.j0, b.n0, b.m0, b.npN, b.npM, b.pidN, b.pidM, b.hk}; memcpy(out, v, sizeof(v)); }
+void emu_graph(void* h, int* rowptr, int* col) {
+    thcmb_ctx* c = &((Emu*)h)->c;
+    memcpy(rowptr, c->rowptr_host.data(), sizeof(int) * c->rowptr_host.size());
+    memcpy(col, c->col_host.data(), sizeof(int) * c->col_host.size());
+}
+void emu_halo_gids(void* h, int* g) { thcmb_ctx* c = &((Emu*)h)->c; memcpy(g, c->halo_gid.data(), sizeof(int) * c->halo_gid.size()); }
+void emu_local_gids(void* h, int* g) { thcmb_ctx* c = &((Emu*)h)->c; memcpy(g, c->local_gid.data(), sizeof(int) * c->local_gid.size()); }
+void emu_get_forcing(void* h, double* f, int masked) { thcmb_ctx* c = &((Emu*)h)->c; memcpy(f, (masked ? c->frc_local : c->frc_raw).data(), sizeof(double) * c->frc_local.size()); }
+void emu_get_cob(void* h, double* f) { thcmb_ctx* c = &((Emu*)h)->c; memcpy(f, c->cob_local.data(), sizeof(double) * c->cob_local.size()); }
+// halo plan: returns number of peers; arrays sized by emu_plan_sizes
+void emu_plan_sizes(void* h, int* npeers, int* nsend, int* nrecv) { Emu* e = (Emu*)h; *npeers = (int)e->c.peers.size(); *nsend = e->c.nsend_cells; *nrecv = e->c.nrecv_cells; }
+void emu_plan(void* h, int* peers5, int* send_idx, int* recv_slot) {
+    Emu* e = (Emu*)h;
+    for (size_t p = 0; p < e->c.peers.size(); p++) {
+        auto& q = e->c.peers[p];
+        int v[5] = {q.rank, q.send_off, q.send_cnt, q.recv_off, q.recv_cnt};
+        memcpy(peers5 + 5 * p, v, sizeof(v));
+    }
+    memcpy(send_idx, e->send_idx.data(), sizeof(int) * e->send_idx.size());
+    memcpy(recv_slot, e->recv_slot.data(), sizeof(int) * e->recv_slot.size());
+}
+
+void emu_jacobian(void* h, const double* un, const double* halo, double* val) {
+    Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
+    for (long long q = 0; q < e->c.gnnz; q++) val[q] = 0.0;
+    for (int cell = 0; cell < a.b.ncell; cell++) {
+        jac_row<1>(e, a, cell, val, nullptr, nullptr, nullptr); jac_row<2>(e, a, cell, val, nullptr, nullptr, nullptr);
+        jac_row<3>(e, a, cell, val, nullptr, nullptr, nullptr); jac_row<4>(e, a, cell, val, nullptr, nullptr, nullptr);
+        jac_row<5>(e, a, cell, val, nullptr, nullptr, nullptr); jac_row<6>(e, a, cell, val, nullptr, nullptr, nullptr);
+    }
+}
+// Fortran-order thresholded CRS (1-based); returns nnz
+long long emu_crs(void* h, const double* un, const double* halo, int* beg, int* jco, double* co) {
+    Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
+    std::vector<int> j; std::vector<double> v; std::vector<int> cnt(NUN * a.b.ncell);
+    for (int cell = 0; cell < a.b.ncell; cell++) {
+        jac_row<1>(e, a, cell, nullptr, cnt.data(), &j, &v); jac_row<2>(e, a, cell, nullptr, cnt.data(), &j, &v);
+        jac_row<3>(e, a, cell, nullptr, cnt.data(), &j, &v); jac_row<4>(e, a, cell, nullptr, cnt.data(), &j, &v);
+        jac_row<5>(e, a, cell, nullptr, cnt.data(), &j, &v); jac_row<6>(e, a, cell, nullptr, cnt.data(), &j, &v);
+    }
+    int acc = 1;
+    for (int r = 0; r < NUN * a.b.ncell; r++) { beg[r] = acc; acc += cnt[r]; }
+    beg[NUN * a.b.ncell] = acc;
+    memcpy(jco, j.data(), sizeof(int) * j.size()); memcpy(co, v.data(), sizeof(double) * v.size());
+    return (long long)j.size();
+}
+void emu_rhs(void* h, const double* un, const double* halo, double* B) {
+    Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
+    for (int cell = 0; cell < a.b.ncell; cell++) {
+        rhs_row<1>(a, cell, B); rhs_row<2>(a, cell, B); rhs_row<3>(a, cell, B);
+        rhs_row<4>(a, cell, B); rhs_row<5>(a, cell, B); rhs_row<6>(a, cell, B);
+    }
+}
+}  // extern "C"
