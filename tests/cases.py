@@ -77,6 +77,30 @@ def random_state(s, landm, scale=0.01, seed=SEED, zero_on_land=True):
     return un
 
 
+def dirichlet_mask(s, landm):
+    """True for unknowns whose row `boundaries` turns into an identity row (boundary.F90): every unknown of a
+    non-ocean cell, u and v next to north / east / north-east land, w under a land (or surface) lid."""
+    n, m, l = s.N, s.M, s.L
+    lm = landm
+    c = lm[1:-1, 1:-1, 1:-1]
+    d = np.zeros((l, m, n, 6), bool)
+    d[c != 0] = True
+    uv = (lm[1:-1, 2:, 1:-1] == 1) | (lm[1:-1, 1:-1, 2:] == 1) | (lm[1:-1, 2:, 2:] == 1)
+    d[..., 0] |= uv
+    d[..., 1] |= uv
+    top = lm[2:, 1:-1, 1:-1].copy()
+    top[-1] = 1  # the surface lid: landm(:,:,l+1) = LAND (usrc.F90:107)
+    d[..., 2] |= top == 1
+    return d.reshape(-1)
+
+
+def consistent_state(s, landm, scale=0.01, seed=SEED):
+    """Random state on the constraint manifold: all Dirichlet unknowns are 0, as in any state the solver produces."""
+    un = random_state(s, landm, scale=scale, seed=seed)
+    un[dirichlet_mask(s, landm)] = 0.0
+    return un
+
+
 def smooth_state(s, value=1.234):  # test_ocean.C:141
     return np.full(6 * s.N * s.M * s.L, value)
 

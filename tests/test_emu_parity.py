@@ -1,0 +1,175 @@
+"""CPU tests of the library's device functions and host setup (tests/emu = thcm_cell.cuh + thcm_host.cpp compiled for
+the host) against the oracle: bit-exact residual, Fortran-order CRS (pattern, row order, values), graph-order Jacobian,
+mass diagonal, forcing -- on one block and on every block of 2/4/8-rank decompositions with halos filled from the global
+state (which checks the decomposition, the static graph with halo columns and the halo plan without a GPU)."""
+import numpy as np
+import pytest
+
+import cases
+from cases import PAR_INDEX as P
+from oracle.oracle import OracleTHCM
+from emu.emu import EmuTHCM
+
+CASES = {
+    "natl8": cases.natl8,
+    "test6x6x4": cases.test6x6x4,
+    "gateway16": cases.gateway16,
+    "global4deg": cases.global4deg,
+    "box_p": lambda **kw: cases.box(7, 6, 5, True, seed=3, land_frac=0.3, **kw),
+    "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
+    "box_p_open": lambda **kw: cases.box(9, 5, 3, True, seed=4, land_frac=0.0, **kw),
+    "box_tiny": lambda **kw: cases.box(3, 2, 2, True, seed=5, land_frac=0.2, **kw),
+}
+PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
+
+
+def setup(name, pars=PARS, **kw):
+    s, landm = CASES[name](**kw)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    for k, v in pars.items():
+        o.setpar(P[k], v)
+        e.setpar(P[k], v)
+    return s, landm, o, e
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("state", ["random_raw", "consistent", "smooth"])
+def test_single_block_bit_exact(name, state):
+    s, landm, o, e = setup(name)
+    x = {"random_raw": lambda: cases.random_state(s, landm, scale=0.3, zero_on_land=False),
+         "consistent": lambda: cases.consistent_state(s, landm, scale=0.01),
+         "smooth": lambda: cases.smooth_state(s)}[state]()
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    bo, jo, co, cob = o.matrix(x)
+    be, je, ce = e.crs(x)
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)   # pattern, row order, values
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0
+    ro, cco = o.graph()
+    re_, ce_ = e.graph()
+    assert np.array_equal(ro, re_) and np.array_equal(cco, ce_)
+    assert np.array_equal(vo, e.jacobian(x))
+    assert np.array_equal(cob, e.cob())
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))
+
+
+def test_parameters_and_forcing_follow_setpar():
+    s, landm, o, e = setup("natl8", pars={})
+    for idx in range(1, 31):
+        assert o.getpar(idx) == e.getpar(idx)
+    f0 = e.forcing(masked=False)
+    assert np.all(f0 == 0.0)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        e.setpar(P[k], v)
+    assert np.count_nonzero(e.forcing(masked=False)) > 0
+    x = cases.random_state(s, landm)
+    o.rhs(x)  # boundaries zeroes Frc rows lazily inside rhs/matrix (boundary.F90:167,256,...)
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))
+
+
+@pytest.mark.parametrize("name,flags", [("natl8", dict(TRES=0, SRES=0)), ("gateway16", dict(ih=1)),
+                                         ("box_p", dict(coriolis_on=0, forcing_type=2)), ("box_np", dict(forcing_type=1, SRES=0))])
+def test_model_flags(name, flags):
+    s, landm, o, e = setup(name, **flags)
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "box_np", "box_p_open"])
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):
+    """Every rank's block, with its halo filled from the global state, must give exactly the owned rows of the 1-rank
+    answer (the multi-GPU path reproduces the global result on any GPU count)."""
+    s, landm, o, _ = setup(name)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    B = o.rhs(x)
+    vo, _ = o.jacobian_graph(x)
+    ro, cco = o.graph()
+    bo, jo, co, cob = o.matrix(x)
+    seen = np.zeros(o.ndim, int)
+    for rank in range(nranks):
+        sr, _ = CASES[name](rank=rank, nranks=nranks)
+        e = EmuTHCM(sr, landm)
+        for k, v in PARS.items():
+            e.setpar(P[k], v)
+        gid = e.local_gids()
+        seen[gid] += 1
+        hg = e.halo_gids()
+        halo = np.where(hg >= 0, x[np.maximum(hg, 0)], np.nan)   # unused halo slots stay NaN: must never be read
+        xl = x[gid]
+        assert np.array_equal(e.rhs(xl, halo), B[gid])
+        # graph rows: same global columns in the same (ascending) order, same values
+        rp, col = e.graph()
+        val = e.jacobian(xl, halo)
+        gcol = np.where(col < e.ndim, gid[np.minimum(col, e.ndim - 1)], hg[np.maximum(col - e.ndim, 0)])
+        for r in range(0, e.ndim, max(1, e.ndim // 997)):
+            g = gid[r]
+            assert np.array_equal(gcol[rp[r]:rp[r + 1]], cco[ro[g]:ro[g + 1]])
+            assert np.array_equal(val[rp[r]:rp[r + 1]], vo[ro[g]:ro[g + 1]])
+        lens_ok = np.array_equal(np.diff(rp), np.diff(ro)[gid])
+        assert lens_ok
+        # all values at once (rows are contiguous per owned row)
+        idx = np.concatenate([np.arange(ro[g], ro[g + 1]) for g in gid[:: max(1, e.ndim // 5000)]])
+        idl = np.concatenate([np.arange(rp[r], rp[r + 1]) for r in range(0, e.ndim, max(1, e.ndim // 5000))])
+        assert np.array_equal(val[idl], vo[idx])
+        # Fortran-order CRS with global 1-based columns
+        be, je, ce = e.crs(xl, halo)
+        for r in range(0, e.ndim, max(1, e.ndim // 499)):
+            g = gid[r]
+            assert np.array_equal(je[be[r] - 1:be[r + 1] - 1], jo[bo[g] - 1:bo[g + 1] - 1])
+            assert np.array_equal(ce[be[r] - 1:be[r + 1] - 1], co[bo[g] - 1:bo[g + 1] - 1])
+        assert np.array_equal(e.cob(), cob[gid])
+    assert np.all(seen == 1)   # the blocks tile the global index space exactly once
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+@pytest.mark.parametrize("name", ["gateway16", "box_np", "global4deg"])
+def test_halo_plan_is_consistent(name, nranks):
+    """What rank p packs for rank q is exactly what q unpacks, slot by slot (global ids match)."""
+    _, landm = CASES[name]()
+    emus = []
+    for rank in range(nranks):
+        sr, _ = CASES[name](rank=rank, nranks=nranks)
+        emus.append(EmuTHCM(sr, landm))
+    plans = [e.plan() for e in emus]
+    for p, e in enumerate(emus):
+        peers, send, recv = plans[p]
+        gid = e.local_gids().reshape(-1, 6)[:, 0] // 6       # global cell id of every owned cell
+        hg = e.halo_gids().reshape(-1, 6)
+        for (q, so, sc, ro_, rc) in peers:
+            qpeers, qsend, qrecv = plans[q]
+            row = [r for r in qpeers if r[0] == p]
+            assert len(row) == 1
+            _, qso, qsc, qro, qrc = row[0]
+            assert sc == qrc and rc == qsc
+            sent_cells = gid[send[so:so + sc]]
+            qhg = emus[q].halo_gids().reshape(-1, 6)
+            want = qhg[qrecv[qro:qro + qrc], 0] // 6
+            ok = qhg[qrecv[qro:qro + qrc], 0] >= 0
+            assert np.array_equal(sent_cells[ok], want[ok])
+        # every halo slot that the graph references is received from exactly one peer
+        used = np.unique(np.nonzero(hg[:, 0] >= 0)[0])
+        assert set(used).issubset(set(recv.tolist()))
+        assert len(set(recv.tolist())) == len(recv)
+
+
+def test_decomp2d_matches_reference_rule():
+    """TRIOS_Domain.C:201-315 incl. the r_min = 100 quirk; SURVEY.md section 8e block shapes."""
+    def blocks(n, m, l, nranks):
+        out = []
+        for r in range(nranks):
+            s = cases.Settings.from_degrees(n, m, l, 0, 359.99, -85.5, 85.5, periodic=True, rank=r, nranks=nranks)
+            e = EmuTHCM(s, cases.all_ocean_mask(n, m, l, True))
+            out.append(e.block())
+        return out
+    b8 = blocks(360, 152, 2, 8)
+    assert {(b["npN"], b["npM"]) for b in b8} == {(4, 2)} and {(b["n0"], b["m0"]) for b in b8} == {(90, 76)}
+    b2 = blocks(360, 152, 2, 2)
+    assert {(b["npN"], b["npM"]) for b in b2} == {(2, 1)} and {(b["n0"], b["m0"]) for b in b2} == {(180, 152)}
+    b4 = blocks(360, 152, 2, 4)
+    assert {(b["npN"], b["npM"]) for b in b4} == {(4, 1)} and {(b["n0"], b["m0"]) for b in b4} == {(90, 152)}
+    # remainders go to the first ranks (TRIOS_Domain.C:267-273)
+    b3 = blocks(10, 7, 2, 3)
+    assert sum(b["n0"] * b["m0"] for b in b3) == 70

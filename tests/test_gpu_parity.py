@@ -1,0 +1,287 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI of libthcm_b200.so,
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):  CRS sparsity pattern and row ordering bit-exact; Jacobian and residual values
+<= 1e-12 relative per nonzero (we assert bit-exact, stricter); SpMV <= 1e-13 relative in the 2-norm; GMRES / IDR(s)
+residual histories <= 1e-10 with iteration counts within +-1 of the reference's own templates."""
+import numpy as np
+import pytest
+
+import cases
+from cases import PAR_INDEX as P
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "natl8": cases.natl8,
+    "test6x6x4": cases.test6x6x4,
+    "gateway16": cases.gateway16,
+    "global4deg": cases.global4deg,
+    "box_p": lambda **kw: cases.box(7, 6, 5, True, seed=3, land_frac=0.3, **kw),
+    "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
+    "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw),   # ragged last assembly block
+    "box_tiny": lambda **kw: cases.box(3, 2, 2, True, seed=5, land_frac=0.2, **kw),
+}
+PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    iemic_b200.load_library()
+    return iemic_b200
+
+
+def setup(gpu, name, pars=PARS, **kw):
+    from oracle.oracle import OracleTHCM
+    s, landm = CASES[name](**kw)
+    o = OracleTHCM(s, landm)
+    t = gpu.THCM(s, landm)
+    for k, v in pars.items():
+        o.setpar(P[k], v)
+        t.setParameter(k, v)
+    return s, landm, o, t
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("state", ["random_raw", "consistent", "smooth"])
+def test_residual_and_jacobian_bit_exact(gpu, name, state):
+    s, landm, o, t = setup(gpu, name)
+    x = {"random_raw": lambda: cases.random_state(s, landm, scale=0.3, zero_on_land=False),
+         "consistent": lambda: cases.consistent_state(s, landm, scale=0.01),
+         "smooth": lambda: cases.smooth_state(s)}[state]()
+    xd = dev(x)
+    B = o.rhs(x)
+    out = t.new_vector()
+    t.rhs_fortran_sign(xd, out)
+    assert np.array_equal(out.cpu().numpy(), B)                     # rhs_ sign
+    F = t.new_vector()
+    t.evaluate(xd, F, True)                                         # THCM::evaluate: C++ sign + Jacobian
+    assert np.array_equal(F.cpu().numpy(), -B)
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0
+    ro, co_ = o.graph()
+    rp, col = t.graph()
+    assert np.array_equal(ro, rp) and np.array_equal(co_, col)      # maximal graph, sorted rows
+    assert np.array_equal(t.jacobian_values_host(), vo)             # values incl. explicit zeros
+    bo, jo, cf, cob = o.matrix(x)
+    beg, jco, coA = t.jacobian_crs(xd)
+    assert np.array_equal(beg.cpu().numpy(), bo)                    # row pointer (1-based)
+    assert np.array_equal(jco.cpu().numpy(), jo)                    # pattern and Fortran entry order
+    assert np.array_equal(coA.cpu().numpy(), cf)                    # values
+    assert np.array_equal(t.getMassDiagonal(), cob)
+    assert np.array_equal(t.getForcing(), o.forcing())
+    t.close()
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "global4deg"])
+def test_fortran_abi_drop_in(gpu, name):
+    """rhs_ / matrix_ / setparcs_ / get_forcing_ with host buffers exactly as THCM.C calls them (THCM.C:603-638, 1001, 1066)."""
+    from oracle.oracle import OracleTHCM
+    s, landm = CASES[name]()
+    o = OracleTHCM(s, landm)
+    f = gpu.FortranABI()
+    f.global_initialize(s)
+    f.init(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        f.setparcs(k, v)
+        assert f.getparcs(k) == v
+    for idx in range(1, 31):
+        assert f.getparcs(idx) == o.getpar(idx)
+    x = cases.random_state(s, landm, scale=0.2, zero_on_land=False)
+    assert np.array_equal(f.rhs(x), o.rhs(x))
+    beg, jco, co, cob = f.matrix(x)
+    bo, jo, cf, cobo = o.matrix(x)
+    assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf) and np.array_equal(cob, cobo)
+    assert np.array_equal(f.get_forcing(), o.forcing())
+    f.finalize()
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
+def test_spmv_and_vector_kernels(gpu, name):
+    from oracle.oracle import spmv, matavec
+    s, landm, o, t = setup(gpu, name)
+    x = cases.random_state(s, landm, scale=0.2)
+    xd = dev(x)
+    t.evaluate(xd, None, True)
+    rp, col = o.graph()
+    val, _ = o.jacobian_graph(x)
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal(t.ndim)
+    y = t.new_vector()
+    t.applyMatrix(dev(v), y)
+    yo = spmv(rp, col, val, v)
+    assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
+    # the Fortran-order CRS gives the same product (matAvec, matetc.F90:147-166)
+    bo, jo, cf, _ = o.matrix(x)
+    ym = matavec(bo, jo, cf, v)
+    assert np.linalg.norm(y.cpu().numpy() - ym) <= 1e-13 * np.linalg.norm(ym)
+    w = rng.standard_normal(t.ndim)
+    vd, wd = dev(v), dev(w)
+    assert abs(t.dot(vd, wd) - float(v @ w)) <= 1e-13 * np.linalg.norm(v) * np.linalg.norm(w)
+    assert abs(t.norm(vd) - np.linalg.norm(v)) <= 1e-14 * np.linalg.norm(v)
+    t.update(wd, 0.37, vd, -1.25)                                    # this = a*A + b*this
+    assert np.array_equal(wd.cpu().numpy(), 0.37 * v + -1.25 * w)
+    t.close()
+
+
+def blockdiag_inverse(rp, col, val, ndim):
+    """numpy twin of the preconditioner definition: inverse of the in-cell 6x6 block, identity when singular."""
+    import scipy.sparse as sp
+    J = sp.csr_matrix((val, col, rp), shape=(ndim, ndim))
+    ncell = ndim // 6
+    minv = np.zeros((ncell, 6, 6))
+    for c in range(ncell):
+        A = J[6 * c:6 * c + 6, 6 * c:6 * c + 6].toarray()
+        try:
+            if abs(np.linalg.det(A)) < 1e-300 or np.linalg.cond(A) > 1e13:
+                raise np.linalg.LinAlgError
+            minv[c] = np.linalg.inv(A)
+        except np.linalg.LinAlgError:
+            minv[c] = np.eye(6)
+    return minv
+
+
+@pytest.mark.parametrize("name,prec", [("natl8", 0), ("natl8", 1), ("gateway16", 1), ("box_np", 1)])
+def test_gmres_history_matches_reference_templates(gpu, name, prec):
+    """Residual history of the CUDA GMRES against the reference's unmodified GMRESSolver.H driven by the oracle's CSR."""
+    from oracle.oracle import kref_gmres
+    s, landm, o, t = setup(gpu, name)
+    x = cases.consistent_state(s, landm, scale=0.1)
+    xd = dev(x)
+    F = t.new_vector()
+    t.evaluate(xd, F, True)
+    rp, col = o.graph()
+    val, _ = o.jacobian_graph(x)
+    b = -(-o.rhs(x))
+    t.buildPreconditioner(prec)
+    minv = None
+    if prec:
+        # hand the reference solver the SAME block inverses the GPU built, so only the Krylov arithmetic is compared
+        e = np.eye(t.ndim // 6 * 6).reshape(-1)[: 0]  # placeholder to keep flake quiet
+        cols = []
+        for q in range(6):
+            unit = np.zeros(t.ndim); unit[q::6] = 1.0
+            out = t.new_vector(); t.applyPrecon(dev(unit), out)
+            cols.append(out.cpu().numpy().reshape(-1, 6))
+        minv = np.stack(cols, axis=2)   # [cell, r, q]
+        ref = blockdiag_inverse(rp, col, val, t.ndim)
+        nonsing = np.array([not np.array_equal(ref[c], np.eye(6)) or np.array_equal(minv[c], np.eye(6)) for c in range(len(ref))])
+        assert np.allclose(minv[nonsing], ref[nonsing], rtol=1e-8, atol=1e-10)
+    tol, maxit, restart = 1e-8, 80, 40
+    kr = kref_gmres(rp, col, val, b, np.zeros(t.ndim), tol=tol, maxit=maxit, restart=restart, prec_kind=prec, minv=minv, flexible=True)
+    sol = t.new_vector()
+    res, hist = t.gmres(dev(b), sol, tol=tol, maxit=maxit, restart=restart, prec=bool(prec), flexible=True)
+    ref_hist = kr["hist"]
+    # the reference prints the residual at the START of each inner iteration (GMRESSolver.H:148-149): entry 0 is the initial
+    # residual, and the first entry after a restart repeats the last one; drop those to align with per-iteration values
+    assert abs(res.iters - kr["iters"]) <= 1
+    k = min(len(hist), 25)
+    ref_iter = ref_hist[1:]
+    assert np.abs(hist[:k] - ref_iter[:k]).max() <= 1e-10
+    assert abs(res.resid - kr["resid"]) <= 1e-10 or (res.status == 0 and kr["rc"] == 0)
+    t.close()
+
+
+@pytest.mark.parametrize("name,prec", [("natl8", 1), ("box_np", 1)])
+def test_idrs_history_matches_reference_templates(gpu, name, prec):
+    from oracle.oracle import kref_idrs
+    s, landm, o, t = setup(gpu, name)
+    x = cases.consistent_state(s, landm, scale=0.1)
+    F = t.new_vector()
+    t.evaluate(dev(x), F, True)
+    rp, col = o.graph()
+    val, _ = o.jacobian_graph(x)
+    b = o.rhs(x)
+    t.buildPreconditioner(prec)
+    cols = []
+    for q in range(6):
+        unit = np.zeros(t.ndim); unit[q::6] = 1.0
+        out = t.new_vector(); t.applyPrecon(dev(unit), out)
+        cols.append(out.cpu().numpy().reshape(-1, 6))
+    minv = np.stack(cols, axis=2)
+    sdim = 4
+    Praw = np.random.default_rng(11).standard_normal((sdim, t.ndim))
+    kr = kref_idrs(rp, col, val, b, np.zeros(t.ndim), Praw, tol=1e-8, maxit=40, s=sdim, prec_kind=prec, minv=minv)
+    sol = t.new_vector()
+    res, hist = t.idrs(dev(b), sol, dev(Praw), tol=1e-8, maxit=40, s=sdim)
+    k = min(len(hist), len(kr["hist"]), 12)
+    scale = kr["hist"][0]
+    assert np.abs(hist[:k] - kr["hist"][:k]).max() <= 1e-10 * scale
+    t.close()
+
+
+def test_full_size_properties_1deg(gpu):
+    """BASELINE config 4 (360x152x24): properties that do not need the oracle -- identity rows, FD consistency of J with F
+    along a random direction, salt conservation of the S columns, SpMV linearity, CRS == graph product."""
+    s, landm = cases.global_synth(360, 152, 24)
+    t = gpu.THCM(s, landm)
+    for k, v in PARS.items():
+        t.setParameter(k, v)
+    x = cases.consistent_state(s, landm, scale=0.05)
+    dmask = cases.dirichlet_mask(s, landm)
+    xd = dev(x)
+    F0 = t.new_vector()
+    t.evaluate(xd, F0, True)
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal(t.ndim); d[dmask] = 0.0
+    dd = dev(d)
+    Jd = t.new_vector(); t.applyMatrix(dd, Jd)
+    h = 1e-5
+    Fp, Fm = t.new_vector(), t.new_vector()
+    t.evaluate(dev(x + h * d), Fp, False); t.evaluate(dev(x - h * d), Fm, False)
+    fd = ((Fp - Fm) / (2 * h)).cpu().numpy()
+    ocean_rows = np.repeat((landm[1:-1, 1:-1, 1:-1] == 0).reshape(-1), 6)
+    err = np.linalg.norm((fd - Jd.cpu().numpy())[ocean_rows]) / np.linalg.norm(Jd.cpu().numpy()[ocean_rows])
+    assert err < 1e-6
+    # Dirichlet rows are identity rows: (J e)_r = e_r
+    e = np.zeros(t.ndim); e[dmask] = rng.standard_normal(int(dmask.sum()))
+    Je = t.new_vector(); t.applyMatrix(dev(e), Je)
+    assert np.array_equal(Je.cpu().numpy()[dmask], e[dmask])
+    # linearity
+    a, b = rng.standard_normal(t.ndim), rng.standard_normal(t.ndim)
+    ya, yb, yab = t.new_vector(), t.new_vector(), t.new_vector()
+    t.applyMatrix(dev(a), ya); t.applyMatrix(dev(b), yb); t.applyMatrix(dev(2.0 * a - 3.0 * b), yab)
+    lin = (2.0 * ya - 3.0 * yb - yab).norm().item() / yab.norm().item()
+    assert lin < 1e-13
+    # salt conservation: w^T J restricted to S columns below the top two levels (test_ocean.C:262-300)
+    n, m, l = s.N, s.M, s.L
+    rowptr, col, val = t.getJacobian()
+    import scipy.sparse as sp
+    J = sp.csr_matrix((val.cpu().numpy(), col, rowptr), shape=(t.ndim, t.ndim))
+    yv = np.array([s.ymin + (j + 0.5) * (s.ymax - s.ymin) / m for j in range(m)])
+    w = np.zeros((l, m, n, 6))
+    w[..., 5] = np.cos(yv)[None, :, None] * (landm[1:-1, 1:-1, 1:-1] == 0)
+    # dfzT_k weights: recover them from the continuity row (pderiv 3: +-1/(dz dfzT_k)) -- any positive weight per level that
+    # makes the vertical fluxes telescope; use the exact grid function
+    qz = s.qz
+    ze = np.array([-1.0 + (k + 0.5) / l for k in range(l)])
+    dfzT = qz / (np.tanh(qz) * np.cosh(qz * (ze + 1)) ** 2) if qz > 1.0 else 1.0 + (1.0 - qz) * (1.0 - 2.0 * ze)
+    w[..., 5] *= dfzT[:, None, None]
+    colint = (J.T @ w.reshape(-1)).reshape(l, m, n, 6)[..., 5]
+    assert np.abs(colint[: l - 2]).max() < 1e-7
+    # Fortran-order CRS product == graph-order product
+    from oracle.oracle import matavec
+    beg, jco, coA = t.jacobian_crs(xd)
+    ycrs = matavec(beg.cpu().numpy(), jco.cpu().numpy(), coA.cpu().numpy(), a)
+    assert np.linalg.norm(ycrs - ya.cpu().numpy()) <= 1e-13 * np.linalg.norm(ycrs)
+    t.close()
+
+
+def test_missing_extension_fails_loudly(gpu, tmp_path):
+    import iemic_b200.thcm as th
+    saved = th._lib
+    th._lib = None
+    try:
+        with pytest.raises(ImportError):
+            th.load_library(str(tmp_path / "nope.so"))
+    finally:
+        th._lib = saved
