@@ -408,17 +408,21 @@ class FortranABI:
         L.getparcs_.restype = None; L.getparcs_.argtypes = [ip, dp]
         L.get_forcing_.restype = None; L.get_forcing_.argtypes = [vp]
         L.set_landmask_.restype = None; L.set_landmask_.argtypes = [vp, ip, ip]
-        L.__m_mat_MOD_get_array_sizes.restype = None; L.__m_mat_MOD_get_array_sizes.argtypes = [ip, ip]
-        L.__m_mat_MOD_set_pointers.restype = None; L.__m_mat_MOD_set_pointers.argtypes = [ip, ip] + [vp] * 7
-        L.__m_global_MOD_initialize.restype = None
-        L.__m_global_MOD_initialize.argtypes = [ip] * 3 + [dp] * 6 + [ip] * 13 + [C.c_char_p] * 5
+        # module procedures: fetched with getattr (a literal L.__m_... inside a class body would be name-mangled by Python)
+        self._get_array_sizes = getattr(L, "__m_mat_MOD_get_array_sizes")
+        self._get_array_sizes.restype = None; self._get_array_sizes.argtypes = [ip, ip]
+        self._set_pointers = getattr(L, "__m_mat_MOD_set_pointers")
+        self._set_pointers.restype = None; self._set_pointers.argtypes = [ip, ip] + [vp] * 7
+        self._global_initialize = getattr(L, "__m_global_MOD_initialize")
+        self._global_initialize.restype = None
+        self._global_initialize.argtypes = [ip] * 3 + [dp] * 6 + [ip] * 13 + [C.c_char_p] * 5
 
     def global_initialize(self, s, maskfile=b""):
         i, d = C.c_int, C.c_double
         a = [i(s.N), i(s.M), i(s.L), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.hdim), d(s.qz), i(s.periodic), i(0), i(0),
              i(1 if maskfile else 0), i(s.TRES), i(s.SRES), i(s.iza), i(s.ite), i(s.its), i(0), i(s.coupled_T), i(s.coupled_S),
              i(s.forcing_type)]
-        self.L_.__m_global_MOD_initialize(*[C.byref(x) for x in a], maskfile, b"", b"", b"", b"")
+        self._global_initialize(*[C.byref(x) for x in a], maskfile, b"", b"", b"", b"")
 
     def init(self, s, landm):
         """init_ for a single-rank domain (usrc.F90:6-139), followed by get_array_sizes / set_pointers like THCM.C:619-638."""
@@ -431,7 +435,7 @@ class FortranABI:
              i(s.tap), i(s.rho_mixing), i(s.coriolis_on), i(s.periodic)]
         self.L_.init_(*[C.byref(x) for x in a], _np_ptr(landm), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z))
         nrows, nnz = i(), i()
-        self.L_.__m_mat_MOD_get_array_sizes(C.byref(nrows), C.byref(nnz))
+        self._get_array_sizes(C.byref(nrows), C.byref(nnz))
         self.ndim = nrows.value
         # the reference allocates ndim*(6*27+1) entries (mat.F90:56-68); rows never hold more than 24
         cap = self.ndim * 24 + 1
@@ -441,7 +445,7 @@ class FortranABI:
         self.coB = np.zeros(self.ndim)
         self.begF = np.zeros(self.ndim + 1, dtype=np.int32); self.jcoF = np.zeros(self.ndim, dtype=np.int32); self.coF = np.zeros(self.ndim)
         capi = i(cap)
-        self.L_.__m_mat_MOD_set_pointers(C.byref(nrows), C.byref(capi), _np_ptr(self.begA), _np_ptr(self.jcoA), _np_ptr(self.coA),
+        self._set_pointers(C.byref(nrows), C.byref(capi), _np_ptr(self.begA), _np_ptr(self.jcoA), _np_ptr(self.coA),
                                          _np_ptr(self.coB), _np_ptr(self.begF), _np_ptr(self.jcoF), _np_ptr(self.coF))
 
     def setparcs(self, idx, val):

@@ -184,7 +184,9 @@ def kref_gmres(rowptr, col, val, b, x0, tol=1e-4, maxit=500, restart=400, prec_k
     n = len(b)
     x = np.array(x0, dtype=np.float64)
     hist = np.zeros(hist_cap); nh = C.c_int(); it = C.c_int(); fr = C.c_double(); nmv = C.c_long()
-    flags = (1 if prec_kind else 0) | (4 if flexible else 0)
+    # the reference's flexible path reads Z[j], which is only filled when preconditioning is on (GMRESSolver.H:160-164,
+    # 237-238): 'no preconditioner' is therefore run as prec = identity (prec_kind 0), never with the flag off
+    flags = 1 | (4 if flexible else 0)
     mv = np.ascontiguousarray(minv) if minv is not None else np.zeros(1)
     rc = klib().kref_gmres(n, _p(rowptr), _p(col), _p(val), prec_kind, 6, _p(mv), _p(np.ascontiguousarray(b)), _p(x), tol, maxit, restart,
                            flags, _p(hist), hist_cap, C.byref(nh), C.byref(it), C.byref(fr), C.byref(nmv))

@@ -179,7 +179,7 @@ def test_gmres_history_matches_reference_templates(gpu, name, prec):
     tol, maxit, restart = 1e-8, 80, 40
     kr = kref_gmres(rp, col, val, b, np.zeros(t.ndim), tol=tol, maxit=maxit, restart=restart, prec_kind=prec, minv=minv, flexible=True)
     sol = t.new_vector()
-    res, hist = t.gmres(dev(b), sol, tol=tol, maxit=maxit, restart=restart, prec=bool(prec), flexible=True)
+    res, hist = t.gmres(dev(b), sol, tol=tol, maxit=maxit, restart=restart, prec=True, flexible=True)  # prec 0 = identity
     ref_hist = kr["hist"]
     # the reference prints the residual at the START of each inner iteration (GMRESSolver.H:148-149): entry 0 is the initial
     # residual, and the first entry after a restart repeats the last one; drop those to align with per-iteration values
