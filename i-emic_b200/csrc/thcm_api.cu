@@ -469,24 +469,54 @@ done:
     return status;
 }
 
-// One Newton step from host buffers: the end-to-end call (bench.py "e2e").
-int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart, int precon_kind,
-                      double* fnorm, thcmb_krylov_result* res) {
+// One Newton step with device-resident state: F(x), J(x), preconditioner, solve J dx = -F (Ocean.C:1052-1055 pattern).
+int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart, int precon_kind,
+                          double* fnorm, thcmb_krylov_result* res) {
     const int n = c->blk.ndim();
     double* d_F = c->d_tmp;
-    double* d_dx = pool_vec(c, 2 + (size_t)(restart + 1) + (size_t)restart + 1);
-    THCM_CUDA(cudaMemcpyAsync(c->d_un, un_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    thcmb_residual_dev(c, c->d_un, d_F);          // F(x)
-    thcmb_jacobian_dev(c, c->d_un);               // J(x)
+    thcmb_residual_dev(c, d_un, d_F);             // F(x)
+    thcmb_jacobian_dev(c, d_un);                  // J(x)
     thcmb_build_precon(c, precon_kind);
-    axpby(c, n, 0.0, d_F, -1.0, d_F);             // solve J dx = -F (Ocean.C:1052-1055 pattern)
+    axpby(c, n, 0.0, d_F, -1.0, d_F);             // b = -F
     double fn = thcmb_nrm2(c, n, d_F);
     if (fnorm) *fnorm = fn;
     fill(c, n, 0.0, d_dx);
-    int rc = thcmb_gmres(c, d_F, d_dx, tol, maxit, restart, precon_kind ? (1 | 4) : 0, nullptr, 0, res);
+    return thcmb_gmres(c, d_F, d_dx, tol, maxit, restart, 1 | 4, nullptr, 0, res);   // precon 0 = identity
+}
+
+// One Newton step from HOST buffers: the end-to-end call (bench.py "e2e"): H2D state, step, D2H update.
+int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart, int precon_kind,
+                      double* fnorm, thcmb_krylov_result* res) {
+    const int n = c->blk.ndim();
+    double* d_dx = pool_vec(c, 2 + (size_t)(restart + 1) + (size_t)restart + 1);
+    THCM_CUDA(cudaMemcpyAsync(c->d_un, un_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    int rc = thcmb_newton_step_dev(c, c->d_un, d_dx, tol, maxit, restart, precon_kind, fnorm, res);
     THCM_CUDA(cudaMemcpyAsync(dx_host, d_dx, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     return rc;
+}
+
+// ---- per-kernel device timing (event pairs around every launch while profiling is on) ----
+void thcmb_profile(thcmb_ctx* c, int on) {
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof_on = on != 0;
+    c->prof_kid.clear();
+}
+static const char* kKernelNames[KID_COUNT] = {"thcm_assemble<RHS>", "thcm_assemble<JAC_GRAPH>", "thcm_assemble<JAC_COUNT>",
+    "thcm_assemble<JAC_CRS>", "scan_counts", "spmv_csr", "dot", "mgs_step", "axpby", "axpy_negdev", "scale_invsqrt", "copy", "fill",
+    "blockdiag_build", "blockdiag_apply", "halo_pack", "halo_unpack"};
+int thcmb_kernel_count(void) { return KID_COUNT; }
+const char* thcmb_kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? kKernelNames[kid] : ""; }
+int thcmb_profile_report(thcmb_ctx* c, int kid, int* count, double* total_ms) {
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    int n = 0; double ms = 0.0;
+    for (size_t i = 0; i < c->prof_kid.size(); i++) {
+        if (c->prof_kid[i] != kid) continue;
+        float t = 0;
+        if (cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) { ms += t; n++; }
+    }
+    *count = n; *total_ms = ms;
+    return 0;
 }
 
 // =============================================================================

@@ -198,6 +198,7 @@ __global__ void scan_counts_kernel(int* cnt, int n) {
 }
 
 int scan_block_counts(thcmb_ctx* c) {
+    ProfScope prof_(c, KID_SCAN);
     scan_counts_kernel<<<1, 1024, 0, c->stream>>>(c->d_blockcnt, c->n_asm_blocks);
     c->launches++;
     return 0;
@@ -212,6 +213,8 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     a.rowptr = c->d_rowptr; a.val = c->d_val; a.blockcnt = c->d_blockcnt; a.begA = d_begA; a.jcoA = d_jcoA; a.coA = d_coA;
     a.out = d_out; a.sign = 1.0;
     int nblk = c->n_asm_blocks;
+    static const int kid_of_mode[4] = {KID_ASM_RHS, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS};
+    ProfScope prof_(c, kid_of_mode[mode & 3]);
     switch (mode & 0xff) {
     case MODE_RHS:
         a.sign = (mode & 0x100) ? -1.0 : 1.0;

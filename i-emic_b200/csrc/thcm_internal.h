@@ -138,6 +138,10 @@ struct thcmb_ctx {
     long long launches = 0;
     std::map<std::string, double> stage_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-kernel device timing (bench.py roofline): event pairs recorded around every launch
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kid;
     // borrowed host CRS pointers (m_mat::set_pointers)
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
     int vmix_fix = 1;
@@ -182,6 +186,23 @@ int fill(thcmb_ctx* c, int n, double a, double* x);
 int build_blockdiag(thcmb_ctx* c);
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
 double* pool_vec(thcmb_ctx* c, size_t idx);
+}  // namespace thcm
+
+namespace thcm {
+enum KernelId { KID_ASM_RHS = 0, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS, KID_SCAN, KID_SPMV, KID_DOT, KID_MGS, KID_AXPBY,
+                KID_AXPY_DEV, KID_SCALE, KID_COPY, KID_FILL, KID_PRECON_BUILD, KID_PRECON_APPLY, KID_HALO_PACK, KID_HALO_UNPACK,
+                KID_COUNT };
+struct ProfScope {   // records an event pair around one kernel launch when profiling is on
+    thcmb_ctx* c; bool on;
+    ProfScope(thcmb_ctx* c_, int kid) : c(c_), on(c_->prof_on && c_->prof_kid.size() < 60000) {
+        if (!on) return;
+        size_t i = c->prof_kid.size();
+        while (c->prof_ev.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); c->prof_ev.push_back(e); }
+        c->prof_kid.push_back(kid);
+        cudaEventRecord(c->prof_ev[2 * i], c->stream);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->prof_ev[2 * (c->prof_kid.size() - 1) + 1], c->stream); }
+};
 }  // namespace thcm
 
 #define THCM_CUDA(call)                                                                           \

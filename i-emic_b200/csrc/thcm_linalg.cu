@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
 
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y) {
+    ProfScope prof_(c, KID_SPMV);
     const int rows_per_block = SPMV_THREADS / SPMV_LANES;
     long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
     int grid = (int)std::min<long long>(want, (long long)NSM * 64);
@@ -152,28 +153,35 @@ static inline int ew_grid(int n) {
 }
 
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out) {
-    dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, x, y, c->d_partial, c->d_counter, d_out);
+    { ProfScope prof_(c, KID_DOT);
+    dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, x, y, c->d_partial, c->d_counter, d_out); }
     c->launches++;
     return allreduce_dev(c, d_out, 1);
 }
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out) {
-    mgs_step_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, d_hk, vk, vnext, w, c->d_partial, c->d_counter, d_out);
+    { ProfScope prof_(c, KID_MGS);
+    mgs_step_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, d_hk, vk, vnext, w, c->d_partial, c->d_counter, d_out); }
     c->launches++;
     return allreduce_dev(c, d_out, 1);
 }
 int axpby(thcmb_ctx* c, int n, double a, const double* x, double b, double* y) {
+    ProfScope prof_(c, KID_AXPBY);
     axpby_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x, b, y); c->launches++; return 0;
 }
 int axpy_negdev(thcmb_ctx* c, int n, const double* d_h, const double* x, double* y) {
+    ProfScope prof_(c, KID_AXPY_DEV);
     axpy_negdev_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, d_h, x, y); c->launches++; return 0;
 }
 int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, double* d_nrm) {
+    ProfScope prof_(c, KID_SCALE);
     scale_invsqrt_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, d_nrm2, x, d_nrm); c->launches++; return 0;
 }
 int copy(thcmb_ctx* c, int n, const double* x, double* y) {
+    ProfScope prof_(c, KID_COPY);
     copy_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, x, y); c->launches++; return 0;
 }
 int fill(thcmb_ctx* c, int n, double a, double* x) {
+    ProfScope prof_(c, KID_FILL);
     fill_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x); c->launches++; return 0;
 }
 
@@ -247,6 +255,7 @@ int halo_exchange(thcmb_ctx* c, const double* d_x) {
     if (c->blk.nranks == 1) return 0;
     if (!c->nccl_comm) fatal("nranks > 1 but thcmb_nccl_init was not called");
     if (c->nsend_cells > 0) {
+        ProfScope prof_(c, KID_HALO_PACK);
         halo_pack_kernel<<<ew_grid(c->nsend_cells * NUN), 256, 0, c->stream>>>(c->nsend_cells, c->d_send_idx, d_x, c->d_sendbuf);
         c->launches++;
     }
@@ -257,6 +266,7 @@ int halo_exchange(thcmb_ctx* c, const double* d_x) {
     }
     g_nccl.GroupEnd();
     if (c->nrecv_cells > 0) {
+        ProfScope prof_(c, KID_HALO_UNPACK);
         halo_unpack_kernel<<<ew_grid(c->nrecv_cells * NUN), 256, 0, c->stream>>>(c->nrecv_cells, c->d_recv_slot, c->d_recvbuf, c->d_halo);
         c->launches++;
     }
@@ -311,12 +321,14 @@ __global__ void blockdiag_apply_kernel(int ncell, const double* __restrict__ min
 int build_blockdiag(thcmb_ctx* c) {
     int ncell = c->blk.ncell();
     if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));
+    ProfScope prof_(c, KID_PRECON_BUILD);
     blockdiag_build_kernel<<<(ncell + 127) / 128, 128, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_minv);
     c->launches++;
     return 0;
 }
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y) {
     int n = c->blk.ndim();
+    ProfScope prof_(c, KID_PRECON_APPLY);
     blockdiag_apply_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->blk.ncell(), c->d_minv, x, y);
     c->launches++;
     return 0;

@@ -100,6 +100,9 @@ def load_library(path=None):
         "thcmb_gmres": (i, [vp, vp, vp, d, i, i, i, vp, i, C.POINTER(KrylovResult)]),
         "thcmb_idrs": (i, [vp, vp, vp, d, i, i, vp, vp, i, C.POINTER(KrylovResult)]),
         "thcmb_newton_step": (i, [vp, vp, vp, d, i, i, i, dp, C.POINTER(KrylovResult)]),
+        "thcmb_newton_step_dev": (i, [vp, vp, vp, d, i, i, i, dp, C.POINTER(KrylovResult)]),
+        "thcmb_profile": (None, [vp, i]), "thcmb_kernel_count": (i, []), "thcmb_kernel_name": (C.c_char_p, [i]),
+        "thcmb_profile_report": (i, [vp, i, ip, dp]),
         "thcmb_device_alloc": (vp, [vp, ll]), "thcmb_device_free": (None, [vp, vp]),
         "thcmb_h2d": (i, [vp, vp, vp, ll]), "thcmb_d2h": (i, [vp, vp, vp, ll]), "thcmb_sync": (i, [vp]),
         "thcmb_stream": (vp, [vp]), "thcmb_launch_count": (ll, [vp]), "thcmb_last_stage_ms": (d, [vp, C.c_char_p]),
@@ -321,6 +324,28 @@ class THCM:
         dp = dx_host.data_ptr() if hasattr(dx_host, "data_ptr") else dx_host.ctypes.data
         self.L_.thcmb_newton_step(self.ctx, C.c_void_p(up), C.c_void_p(dp), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
         return res, fn.value
+
+    def newton_step_dev(self, un, dx, tol=1e-4, maxit=500, restart=400, precon=1):
+        """Newton step with the state already in HBM (CUDA tensors)."""
+        self._pre()
+        res = KrylovResult()
+        fn = C.c_double()
+        self.L_.thcmb_newton_step_dev(self.ctx, _dev_ptr(un), _dev_ptr(dx), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
+        self.sync()
+        return res, fn.value
+
+    def profile(self, on):
+        self.L_.thcmb_profile(self.ctx, int(on))
+
+    def profile_report(self):
+        """{kernel name: (launches, total device ms)} since profile(True)."""
+        out = {}
+        for kid in range(self.L_.thcmb_kernel_count()):
+            n, ms = C.c_int(), C.c_double()
+            self.L_.thcmb_profile_report(self.ctx, kid, C.byref(n), C.byref(ms))
+            if n.value:
+                out[self.L_.thcmb_kernel_name(kid).decode()] = (n.value, ms.value)
+        return out
 
     def launch_count(self):
         return self.L_.thcmb_launch_count(self.ctx)

@@ -186,6 +186,17 @@ int thcmb_idrs(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int max
 int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart,
                       int precon_kind, double* fnorm, thcmb_krylov_result* res);
 
+/* the same step with the state already in HBM (bench.py "value") */
+int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart,
+                          int precon_kind, double* fnorm, thcmb_krylov_result* res);
+
+/* per-kernel device timing: while on, every kernel launch of the library is bracketed by a CUDA event pair on the
+ * context's stream; thcmb_profile_report sums them per kernel id (0 .. thcmb_kernel_count()-1) */
+void thcmb_profile(thcmb_ctx* c, int on);
+int thcmb_kernel_count(void);
+const char* thcmb_kernel_name(int kid);
+int thcmb_profile_report(thcmb_ctx* c, int kid, int* count, double* total_ms);
+
 /* utilities */
 void* thcmb_device_alloc(thcmb_ctx* c, long long bytes);
 void thcmb_device_free(thcmb_ctx* c, void* p);

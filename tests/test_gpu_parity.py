@@ -214,8 +214,11 @@ def test_idrs_history_matches_reference_templates(gpu, name, prec):
     sol = t.new_vector()
     res, hist = t.idrs(dev(b), sol, dev(Praw), tol=1e-8, maxit=40, s=sdim)
     k = min(len(hist), len(kr["hist"]), 12)
-    scale = kr["hist"][0]
-    assert np.abs(hist[:k] - kr["hist"][:k]).max() <= 1e-10 * scale
+    # IDR(s) residual norms are erratic on this (singular, block-diagonally preconditioned) system and grow by 40x before
+    # they fall: compare relative to the running maximum of the reference history
+    scale = np.maximum.accumulate(kr["hist"][:k])
+    assert np.all(np.abs(hist[:k] - kr["hist"][:k]) <= 1e-10 * scale)
+    assert abs(res.iters - kr["iters"]) <= 1
     t.close()
 
 
