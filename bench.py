@@ -263,7 +263,7 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = t.launch_count()
-    ms, wall, res = timed(step_dev, a.steps)
+    ms, wall, (res, _fn) = timed(step_dev, a.steps)
     launches = t.launch_count() - l0
     for _ in range(2):
         step_e2e()

@@ -122,7 +122,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     build_grid(c);
     stpnt(c);
     apply_landmask_rules(c, landm_global, false);
-    c->n_asm_blocks = (c->blk.ncell() + 31) / 32;
+    c->n_asm_blocks = asm_block_count(c->blk);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
     THCM_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 4096));

@@ -14,9 +14,12 @@
 //   JAC_COUNT : JAC_GRAPH + number of |a|>1e-10 entries per assembly block
 //   JAC_CRS   : Fortran-order thresholded CRS begA/jcoA/coA (1-based), after the block-count scan
 //
-// Mapping: block = 32 consecutive owned cells x 6 warps; warp r evaluates row type r (u,v,w,p,T,S)
-// for the 32 cells (no intra-warp divergence on the row type), results are staged in shared memory
-// at their final offsets and written out by the whole block as one contiguous, coalesced range.
+// Tile = TI consecutive cells of one (j,k) grid line.  Phase 1: all 192 threads stage the 3x3x(TI+2)
+// neighbourhood -- fields as usol leaves them -- and the j/k slices of the metric tables into shared
+// memory with independent 16-byte loads (one latency exposure instead of ~60 dependent ones).
+// Phase 2: warp r evaluates row type r (u,v,w,p,T,S) for the TI cells from shared memory only (no
+// divergence on the row type).  Phase 3: results, staged in shared memory at their final offsets,
+// leave as one contiguous coalesced range per block.
 // HBM traffic per cell: 48 B state + 5 B masks in, 832 B values out.
 // =============================================================================
 #include <cstdio>
@@ -28,32 +31,80 @@ __constant__ ClassTables c_cls;
 
 void upload_class_tables(const ClassTables& t) { THCM_CUDA(cudaMemcpyToSymbol(c_cls, &t, sizeof(ClassTables))); }
 
-// ---------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------
+constexpr int TI = CELLS_PER_BLOCK;   // 32 cells per tile
+constexpr int TW = TI + 2;            // staged width (one neighbour column each side)
+
+template <int NSV> struct SmemIn {
+    double st[NSV][3][3][TW];         // [field][dk+1][dj+1][x]
+    double tj[J_COUNT][3];            // j-tables at gj-1, gj, gj+1
+    double tk[K_COUNT];               // k-tables at k
+};
 template <int MODE> struct Smem;
-template <> struct Smem<MODE_RHS> { double dummy; };
-template <> struct Smem<MODE_JAC_GRAPH> { double v[CELLS_PER_BLOCK * NSLOT_TOTAL]; };
-template <> struct Smem<MODE_JAC_COUNT> { double v[CELLS_PER_BLOCK * NSLOT_TOTAL]; int cnt[NUN]; };
-template <> struct Smem<MODE_JAC_CRS> { double v[CELLS_PER_BLOCK * NSLOT_TOTAL]; int c[CELLS_PER_BLOCK * NSLOT_TOTAL]; int off[CELLS_PER_BLOCK * NUN + 1]; };
+template <> struct Smem<MODE_RHS> { SmemIn<SV_NRHS> in; };
+template <> struct Smem<MODE_JAC_GRAPH> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; };
+template <> struct Smem<MODE_JAC_COUNT> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; int cnt[NUN]; };
+template <> struct Smem<MODE_JAC_CRS> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; int c[TI * NSLOT_TOTAL]; int off[TI * NUN + 1]; };
+
+template <int NSV> struct SmemTile {
+    const SmemIn<NSV>* in; int lane;
+    __device__ __forceinline__ double operator()(int sv, int di, int dj, int dk) const { return in->st[sv][dk + 1][dj + 1][lane + 1 + di]; }
+};
+template <int NSV> struct SmemTabs {
+    const SmemIn<NSV>* in;
+    __device__ __forceinline__ double jt(int tb, int dj) const { return in->tj[tb][dj + 1]; }
+    __device__ __forceinline__ double kt(int tb) const { return in->tk[tb]; }
+};
+
+struct TileGeom { int cell0, ncell, gi0, gj, k, lj; };   // first owned cell, count, global (1-based) origin
+
+__device__ __forceinline__ TileGeom tile_geom(const DevBlock& b) {
+    const int nbx = (b.n0 + TI - 1) / TI;
+    int ib = blockIdx.x % nbx, rest = blockIdx.x / nbx;
+    int lj = rest % b.m0, k0 = rest / b.m0;
+    TileGeom g;
+    g.cell0 = (k0 * b.m0 + lj) * b.n0 + ib * TI;
+    g.ncell = min(TI, b.n0 - ib * TI);
+    g.gi0 = b.i0 + ib * TI + 1; g.gj = b.j0 + lj + 1; g.k = k0 + 1; g.lj = lj;
+    return g;
+}
+
+template <int NSV>
+__device__ __forceinline__ void stage_inputs(const AsmArgs& a, const TileGeom& g, SmemIn<NSV>& in) {
+    // positions: 3 levels x 3 rows x (ncell + 2) columns; each thread stages whole positions (all fields of a cell
+    // come from the same 48-byte record)
+    const int w = g.ncell + 2, npos = 9 * w;
+    for (int p = threadIdx.x; p < npos; p += ASM_THREADS) {
+        int x = p % w, r = p / w, dj = r % 3 - 1, dk = r / 3 - 1;
+        double out[NSV];
+        stage_position<NSV>(a, g.gi0 - 1 + x, g.gj + dj, g.k + dk, out);
+#pragma unroll
+        for (int sv = 0; sv < NSV; sv++) in.st[sv][dk + 1][dj + 1][x] = out[sv];
+    }
+    const DevTables& t = a.t;
+    for (int q = threadIdx.x; q < J_COUNT * 3 + K_COUNT; q += ASM_THREADS) {
+        if (q < J_COUNT * 3) { int tb = q / 3, d = q % 3; in.tj[tb][d] = __ldg(t.jt + (size_t)tb * t.jstride + g.gj + d - 1); }
+        else { int tb = q - J_COUNT * 3; in.tk[tb] = __ldg(t.kt + (size_t)tb * t.kstride + g.k); }
+    }
+}
 
 template <int R, int MODE>
-__device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, int cell0, int ncell_blk, int lane) {
+__device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const TileGeom& g, int lane) {
+    constexpr int NSV = MODE == MODE_RHS ? SV_NRHS : SV_NJAC;
     const DevBlock& b = a.b;
-    const int cell = cell0 + lane;
-    const bool active = lane < ncell_blk;
+    const int cell = g.cell0 + lane;
+    const bool active = lane < g.ncell;
     double E[RowSlots<R>::N];
     Cell c{0, 0, 0, 0, 0};
     int cls = 0;
     uint32_t nb = 0;
+    SmemTile<NSV> tile{&sh.in, lane};
     if (active) {
-        int li = cell % b.n0, r = cell / b.n0, lj = r % b.m0, k0 = r / b.m0;
-        c.li = li; c.lj = lj; c.gi = b.i0 + li + 1; c.gj = b.j0 + lj + 1; c.k = k0 + 1;
+        c.li = cell % b.n0; c.lj = g.lj; c.gi = g.gi0 + lane; c.gj = g.gj; c.k = g.k;
         nb = a.nbmask[cell];
-        double sm = (double)(int)(int8_t)a.surf[lj * b.n0 + li];
+        double sm = (double)(int)(int8_t)a.surf[g.lj * b.n0 + c.li];
         cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) |
               (c.k == b.L ? 32 : 0);
-        if (!((nb >> 4) & 1u)) eval_row<R, MODE != MODE_RHS>(E, a, c, sm);
+        if (!((nb >> 4) & 1u)) eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
         boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
         // strict threshold of fillcolA (assemble.F90:115); the graph keeps explicit zeros instead
 #pragma unroll
@@ -70,7 +121,7 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, int cel
                 int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
                 // a kept entry always points inside the domain (the dummy LAND frame removes the others)
                 bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
-                if (E[q] != 0.0 && inside) s = E[q] * raw(a, gi2, gj2, k2, col - 1) + s;
+                if (E[q] != 0.0 && inside) s = E[q] * tile(SV_RAW + col - 1, loc_di(loc), loc_dj(loc), loc_dk(loc)) + s;
             });
             // B = -Au - mix + Frc - p0*(1-par(RESC))*ures ; B *= (1 - landm) (usrc.F90:576-591)
             int row = NUN * cell + R - 1;
@@ -80,7 +131,7 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, int cel
         }
         return;
     } else {
-        const int g0 = a.rowptr[NUN * cell0];
+        const int g0 = a.rowptr[NUN * g.cell0];
         if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
             int cnt = 0;
             if (active) {
@@ -116,7 +167,7 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, int cel
                 int excl = incl - tot;
 #pragma unroll
                 for (int r = 0; r < NUN; r++) sh.off[lane * NUN + r] = excl + loc[r];
-                if (lane == 31) sh.off[CELLS_PER_BLOCK * NUN] = incl;
+                if (lane == 31) sh.off[TI * NUN] = incl;
             }
             __syncthreads();
             if (active) {
@@ -141,28 +192,30 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, int cel
 
 template <int MODE>
 __global__ void __launch_bounds__(ASM_THREADS) thcm_assemble_kernel(const AsmArgs a) {
-    __shared__ Smem<MODE> sh;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem<MODE>& sh = *reinterpret_cast<Smem<MODE>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell0 = blockIdx.x * CELLS_PER_BLOCK;
-    const int ncell_blk = min(CELLS_PER_BLOCK, a.b.ncell - cell0);
+    const TileGeom g = tile_geom(a.b);
+    stage_inputs(a, g, sh.in);
+    __syncthreads();
     switch (warp) {
-    case 0: do_row<1, MODE>(a, sh, cell0, ncell_blk, lane); break;
-    case 1: do_row<2, MODE>(a, sh, cell0, ncell_blk, lane); break;
-    case 2: do_row<3, MODE>(a, sh, cell0, ncell_blk, lane); break;
-    case 3: do_row<4, MODE>(a, sh, cell0, ncell_blk, lane); break;
-    case 4: do_row<5, MODE>(a, sh, cell0, ncell_blk, lane); break;
-    default: do_row<6, MODE>(a, sh, cell0, ncell_blk, lane); break;
+    case 0: do_row<1, MODE>(a, sh, g, lane); break;
+    case 1: do_row<2, MODE>(a, sh, g, lane); break;
+    case 2: do_row<3, MODE>(a, sh, g, lane); break;
+    case 3: do_row<4, MODE>(a, sh, g, lane); break;
+    case 4: do_row<5, MODE>(a, sh, g, lane); break;
+    default: do_row<6, MODE>(a, sh, g, lane); break;
     }
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
         __syncthreads();
-        const int g0 = a.rowptr[NUN * cell0], g1 = a.rowptr[NUN * (cell0 + ncell_blk)];
+        const int g0 = a.rowptr[NUN * g.cell0], g1 = a.rowptr[NUN * (g.cell0 + g.ncell)];
         for (int q = threadIdx.x; q < g1 - g0; q += ASM_THREADS) a.val[g0 + q] = sh.v[q];
         if constexpr (MODE == MODE_JAC_COUNT) {
             if (threadIdx.x == 0) a.blockcnt[blockIdx.x] = sh.cnt[0] + sh.cnt[1] + sh.cnt[2] + sh.cnt[3] + sh.cnt[4] + sh.cnt[5];
         }
     } else if constexpr (MODE == MODE_JAC_CRS) {
         __syncthreads();
-        const int bbase = a.blockcnt[blockIdx.x], tot = sh.off[CELLS_PER_BLOCK * NUN];
+        const int bbase = a.blockcnt[blockIdx.x], tot = sh.off[TI * NUN];
         for (int q = threadIdx.x; q < tot; q += ASM_THREADS) { a.coA[bbase + q] = sh.v[q]; a.jcoA[bbase + q] = sh.c[q]; }
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) a.begA[NUN * a.b.ncell] = bbase + tot + 1;
     }
@@ -197,11 +250,22 @@ __global__ void scan_counts_kernel(int* cnt, int n) {
     }
 }
 
+int asm_block_count(const Block& b) { return ((b.n0 + TI - 1) / TI) * b.m0 * b.L; }
+
 int scan_block_counts(thcmb_ctx* c) {
     ProfScope prof_(c, KID_SCAN);
     scan_counts_kernel<<<1, 1024, 0, c->stream>>>(c->d_blockcnt, c->n_asm_blocks);
     c->launches++;
     return 0;
+}
+
+template <int MODE> static void launch_mode(thcmb_ctx* c, const AsmArgs& a, int nblk) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        THCM_CUDA(cudaFuncSetAttribute(thcm_assemble_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<MODE>)));
+        attr_set = true;
+    }
+    thcm_assemble_kernel<MODE><<<nblk, ASM_THREADS, sizeof(Smem<MODE>), c->stream>>>(a);
 }
 
 int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA) {
@@ -218,10 +282,10 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     switch (mode & 0xff) {
     case MODE_RHS:
         a.sign = (mode & 0x100) ? -1.0 : 1.0;
-        thcm_assemble_kernel<MODE_RHS><<<nblk, ASM_THREADS, 0, c->stream>>>(a); break;
-    case MODE_JAC_GRAPH: thcm_assemble_kernel<MODE_JAC_GRAPH><<<nblk, ASM_THREADS, 0, c->stream>>>(a); break;
-    case MODE_JAC_COUNT: thcm_assemble_kernel<MODE_JAC_COUNT><<<nblk, ASM_THREADS, 0, c->stream>>>(a); break;
-    case MODE_JAC_CRS: thcm_assemble_kernel<MODE_JAC_CRS><<<nblk, ASM_THREADS, 0, c->stream>>>(a); break;
+        launch_mode<MODE_RHS>(c, a, nblk); break;
+    case MODE_JAC_GRAPH: launch_mode<MODE_JAC_GRAPH>(c, a, nblk); break;
+    case MODE_JAC_COUNT: launch_mode<MODE_JAC_COUNT>(c, a, nblk); break;
+    case MODE_JAC_CRS: launch_mode<MODE_JAC_CRS>(c, a, nblk); break;
     default: return -1;
     }
     c->launches++;

@@ -67,7 +67,7 @@ THCM_HD double raw(const AsmArgs& a, int gi, int gj, int k, int var /*0..5*/) {
 }
 
 // t, s (var 4, 5): no-flux mirror in y and (non-periodic) x, periodic copy otherwise (usrc.F90:1046-1100)
-THCM_HD double TS(const AsmArgs& a, int gi, int gj, int k, int var) {
+THCM_HD double ts_value(const AsmArgs& a, int gi, int gj, int k, int var) {
     const DevBlock& b = a.b;
     if (gj < 1) gj = 1; else if (gj > b.M) gj = b.M;
     if (!b.periodic) { if (gi < 1) gi = 1; else if (gi > b.N) gi = b.N; }
@@ -76,7 +76,7 @@ THCM_HD double TS(const AsmArgs& a, int gi, int gj, int k, int var) {
 }
 // w (var 2): w(i,j,0) = w(i,j,l) = 0 for i in 1..n; the periodic ghost columns 0 and n+1 are copied BEFORE
 // w(:,:,l) is zeroed, so they keep the raw top-level value (usrc.F90:1051-1052 vs :1093)
-THCM_HD double WW_(const AsmArgs& a, int gi, int gj, int k) {
+THCM_HD double w_value(const AsmArgs& a, int gi, int gj, int k) {
     const DevBlock& b = a.b;
     if (k < 1 || k > b.L || gj < 1 || gj > b.M) return 0.0;
     if (gi >= 1 && gi <= b.N) return k == b.L ? 0.0 : raw(a, gi, gj, k, 2);
@@ -84,7 +84,7 @@ THCM_HD double WW_(const AsmArgs& a, int gi, int gj, int k) {
 }
 // u, v (var 0, 1) on cell corners: usol's no-slip zeroing is precomputed as the uvlive box; corner 0 in a
 // periodic domain is the raw copy of corner N (usrc.F90:1049-1050) with its OWN zeroing rule
-THCM_HD double UV(const AsmArgs& a, int ic, int jc, int k, int var) {
+THCM_HD double uv_value(const AsmArgs& a, int ic, int jc, int k, int var) {
     const DevBlock& b = a.b;
     if (k < 1 || k > b.L) return 0.0;   // ghost levels only feed entries that `boundaries` removes
     int bn = b.n0 + 2, bm = b.m0 + 2;
@@ -92,6 +92,92 @@ THCM_HD double UV(const AsmArgs& a, int ic, int jc, int k, int var) {
     if (!a.uvlive[((size_t)(k - 1) * bm + bj) * bn + bi]) return 0.0;
     return raw(a, ic, jc, k, var);
 }
+
+// ---------------------------------------------------------------------------
+// Staged fields.  The kernels first stage, for every cell of a tile and its 26 neighbours, the fields exactly as
+// usol leaves them (u, v with the no-slip zeroing, w with its lid/bottom rule, t, s with the no-flux mirrors) --
+// and, for the residual, the raw unknowns the matrix-vector product multiplies -- into shared memory with
+// independent, coalesced loads; the row evaluation then reads shared memory only.
+// ---------------------------------------------------------------------------
+enum { SV_U = 0, SV_V, SV_W, SV_T, SV_S, SV_NJAC = 5, SV_RAW = 5, SV_NRHS = 11 };
+
+// value of staged field sv at the global position (gi, gj, k), which may lie one cell outside the domain
+THCM_HD double stage_value(const AsmArgs& a, int sv, int gi, int gj, int k) {
+    const DevBlock& b = a.b;
+    if (sv <= SV_V) {
+        if (gi > b.N || gj > b.M) return 0.0;     // corners N+1 / M+1 do not exist (never read by a kept entry)
+        return uv_value(a, gi, gj, k, sv);
+    }
+    if (sv == SV_W) return w_value(a, gi, gj, k);
+    if (sv <= SV_S) return ts_value(a, gi, gj, k, sv - SV_T + 4);
+    // raw unknown sv - SV_RAW: only positions inside the domain (with periodic wrap) are ever multiplied
+    bool inside = gj >= 1 && gj <= b.M && k >= 1 && k <= b.L && (b.periodic || (gi >= 1 && gi <= b.N));
+    return inside ? raw(a, gi, gj, k, sv - SV_RAW) : 0.0;
+}
+
+// All staged fields of ONE position with unconditional, independent loads (what the kernels execute): the six raw
+// unknowns of the clamped / wrapped source cell (always a valid address) + one uvlive byte, then selects.  Must agree
+// with stage_value() for every sv (checked on the host by tests/emu: emu_check_staging).
+template <int NSV>
+THCM_HD void stage_position(const AsmArgs& a, int gi, int gj, int k, double* out) {
+    const DevBlock& b = a.b;
+    // source cell: TS clamping (no-flux mirror); inside the domain (incl. the periodic wrap) it is the cell itself
+    int cj = gj < 1 ? 1 : (gj > b.M ? b.M : gj);
+    int ck = k < 1 ? 1 : (k > b.L ? b.L : k);
+    int ci = gi;
+    if (!b.periodic) ci = gi < 1 ? 1 : (gi > b.N ? b.N : gi);
+    int ie = ci - 1 - b.i0, je = cj - 1 - b.j0, kk = ck - 1;
+    if (b.wrap_x) { if (ie < 0) ie += b.n0; else if (ie >= b.n0) ie -= b.n0; }
+    const double* src;
+    if (ie >= 0 && ie < b.n0 && je >= 0 && je < b.m0) src = a.un + (size_t)NUN * (((size_t)kk * b.m0 + je) * b.n0 + ie);
+    else {
+        int wrow = b.n0 + b.halo_w + b.halo_e, hs;
+        if (je == -1) hs = kk * b.hk + (ie + b.halo_w);
+        else if (je == b.m0) hs = kk * b.hk + b.halo_s * wrow + (ie + b.halo_w);
+        else if (ie == -1) hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + je;
+        else hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + b.halo_w * b.m0 + je;
+        src = a.halo + (size_t)NUN * hs;
+    }
+    double r[NUN];
+#ifdef __CUDA_ARCH__
+    const double2* s2 = reinterpret_cast<const double2*>(src);   // cells are 48-byte records, 16-byte aligned
+    double2 q0 = __ldg(s2), q1 = __ldg(s2 + 1), q2 = __ldg(s2 + 2);
+    r[0] = q0.x; r[1] = q0.y; r[2] = q1.x; r[3] = q1.y; r[4] = q2.x; r[5] = q2.y;
+#else
+    for (int v = 0; v < NUN; v++) r[v] = src[v];
+#endif
+    // u, v: corner (gi, gj) exists for gi <= N, gj <= M; liveness from the precomputed usol rule
+    int bi = gi - b.i0, bj = gj - b.j0;
+    bool corner = gi <= b.N && gj <= b.M && k >= 1 && k <= b.L;
+    int bic = bi < 0 ? 0 : (bi > b.n0 + 1 ? b.n0 + 1 : bi), bjc = bj < 0 ? 0 : (bj > b.m0 + 1 ? b.m0 + 1 : bj);
+    bool live = a.uvlive[((size_t)kk * (b.m0 + 2) + bjc) * (b.n0 + 2) + bic] != 0;
+    live = live && corner;
+    out[SV_U] = live ? r[0] : 0.0;
+    out[SV_V] = live ? r[1] : 0.0;
+    // w (usrc.F90:1051-1052, 1093-1094)
+    bool win = k >= 1 && k <= b.L && gj >= 1 && gj <= b.M;
+    bool wi = (gi >= 1 && gi <= b.N) ? (k != b.L) : (b.periodic != 0);
+    out[SV_W] = (win && wi) ? r[2] : 0.0;
+    out[SV_T] = r[4];
+    out[SV_S] = r[5];
+    if constexpr (NSV > SV_NJAC) {
+        bool inside = gj >= 1 && gj <= b.M && k >= 1 && k <= b.L && (b.periodic || (gi >= 1 && gi <= b.N));
+#pragma unroll
+        for (int v = 0; v < NUN; v++) out[SV_RAW + v] = inside ? r[v] : 0.0;
+    }
+}
+
+// tile / table accessors used by the host emulation and as the reference semantics of the shared-memory ones:
+//   tile(sv, di, dj, dk)  staged field at the neighbour offset;  tabs.jt(table, dj), tabs.kt(table)
+struct DirectTile {
+    const AsmArgs& a; int gi, gj, k;
+    THCM_HD double operator()(int sv, int di, int dj, int dk) const { return stage_value(a, sv, gi + di, gj + dj, k + dk); }
+};
+struct DirectTabs {
+    const DevTables& t; int gj, k;
+    THCM_HD double jt(int tb, int dj) const { return THCM_LDG(t.jt + (size_t)tb * t.jstride + gj + dj); }
+    THCM_HD double kt(int tb) const { return THCM_LDG(t.kt + (size_t)tb * t.kstride + k); }
+};
 
 template <int N> struct IntC { static constexpr int value = N; };
 template <int I, int N, class F> THCM_HD void static_for(F&& f) {
@@ -108,12 +194,15 @@ template <int R, int LOC, int COL> THCM_HD double& entref(double* E) {
 // ---------------------------------------------------------------------------
 // row evaluation: An = Al (lin, usrc.F90:690-785) + nonlinear atoms (usrc.F90:842-882 | 950-1007)
 // ---------------------------------------------------------------------------
-template <int R, bool JAC>
-THCM_HD void eval_row(double* E, const AsmArgs& a, const Cell& c, double sm) {
-    const DevTables& t = a.t;
-    const int gi = c.gi, gj = c.gj, k = c.k, N = a.b.N, M = a.b.M, L = a.b.L;
-    auto JT = [&](int tb, int j) { return THCM_LDG(t.jt + (size_t)tb * t.jstride + j); };
-    auto KT = [&](int tb, int kk) { return THCM_LDG(t.kt + (size_t)tb * t.kstride + kk); };
+template <int R, bool JAC, class Tile, class Tabs>
+THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const Cell& c, double sm, const Tile& tile, const Tabs& tabs) {
+    const int gi = c.gi, gj = c.gj, k = c.k, N = blk.N, M = blk.M, L = blk.L;
+    const int a = 0;  // (the accessors below keep the call shape of the global-memory versions)
+    auto JT = [&](int tb, int j) { return tabs.jt(tb, j - gj); };
+    auto KT = [&](int tb, int kk) { (void)kk; return tabs.kt(tb); };
+    auto UV = [&](int, int ic, int jc, int kk, int var) { return tile(var, ic - gi, jc - gj, kk - k); };
+    auto WW_ = [&](int, int ic, int jc, int kk) { return tile(SV_W, ic - gi, jc - gj, kk - k); };
+    auto TS = [&](int, int ic, int jc, int kk, int var) { return tile(SV_T + var - 4, ic - gi, jc - gj, kk - k); };
     const double epsr = t.epsr;
 #pragma unroll
     for (int q = 0; q < RowSlots<R>::N; q++) E[q] = 0.0;

@@ -165,6 +165,7 @@ void upload_class_tables(const ClassTables& t);
 int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA);
 enum { MODE_RHS = 0, MODE_JAC_GRAPH = 1, MODE_JAC_COUNT = 2, MODE_JAC_CRS = 3 };
 int scan_block_counts(thcmb_ctx* c);
+int asm_block_count(const Block& b);
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y);
 int halo_exchange(thcmb_ctx* c, const double* d_x);

@@ -34,7 +34,7 @@ def lib():
                                 ("emu_local_gids", None, [vp, vp]), ("emu_get_forcing", None, [vp, vp, i]), ("emu_get_cob", None, [vp, vp]),
                                 ("emu_plan_sizes", None, [vp, vp, vp, vp]), ("emu_plan", None, [vp, vp, vp, vp]),
                                 ("emu_jacobian", None, [vp, vp, vp, vp]), ("emu_crs", ll, [vp, vp, vp, vp, vp, vp]),
-                                ("emu_rhs", None, [vp, vp, vp, vp])]:
+                                ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -107,6 +107,10 @@ class EmuTHCM:
         beg = np.empty(self.ndim + 1, dtype=np.int32); jco = np.empty(self.nnz, dtype=np.int32); co = np.empty(self.nnz)
         nnz = self.L_.emu_crs(self.h, _p(un), _p(h), _p(beg), _p(jco), _p(co))
         return beg, jco[:nnz].copy(), co[:nnz].copy()
+
+    def check_staging(self, un, halo=None):
+        un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
+        return self.L_.emu_check_staging(self.h, _p(un), _p(h))
 
     def rhs(self, un, halo=None):
         un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)

@@ -45,7 +45,7 @@ void cell_row(const AsmArgs& a, int cell, double* E, Cell& c, int& cls, uint32_t
     nb = a.nbmask[cell];
     double sm = (double)(int)(int8_t)a.surf[lj * b.n0 + li];
     cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) | (c.k == b.L ? 32 : 0);
-    if (!((nb >> 4) & 1u)) eval_row<R, JAC>(E, a, c, sm);
+    if (!((nb >> 4) & 1u)) eval_row<R, JAC>(E, a.t, a.b, c, sm, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
     boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
     for (int q = 0; q < RowSlots<R>::N; q++) E[q] = std::fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
 }
@@ -84,7 +84,7 @@ void rhs_row(const AsmArgs& a, int cell, double* out) {
         int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
         int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
         bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
-        if (E[q] != 0.0 && inside) s = E[q] * raw(a, gi2, gj2, k2, col - 1) + s;
+        if (E[q] != 0.0 && inside) s = E[q] * stage_value(a, SV_RAW + col - 1, gi2, gj2, k2) + s;
     }
     int row = NUN * cell + R - 1;
     double B = -s - 0.0 + a.frc[row] - 0.0;
@@ -159,6 +159,26 @@ long long emu_crs(void* h, const double* un, const double* halo, int* beg, int* 
     beg[NUN * a.b.ncell] = acc;
     memcpy(jco, j.data(), sizeof(int) * j.size()); memcpy(co, v.data(), sizeof(double) * v.size());
     return (long long)j.size();
+}
+// stage_position (the unconditional-load form the kernels run) against stage_value (the reference semantics) for every
+// owned cell, all 27 neighbour positions and all 11 staged fields; returns the number of mismatches
+long long emu_check_staging(void* h, const double* un, const double* halo) {
+    Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
+    const DevBlock& b = a.b;
+    long long bad = 0;
+    for (int cell = 0; cell < b.ncell; cell++) {
+        int li = cell % b.n0, r = cell / b.n0, lj = r % b.m0, k0 = r / b.m0;
+        int gi = b.i0 + li + 1, gj = b.j0 + lj + 1, k = k0 + 1;
+        for (int dk = -1; dk <= 1; dk++) for (int dj = -1; dj <= 1; dj++) for (int di = -1; di <= 1; di++) {
+            double out[SV_NRHS];
+            stage_position<SV_NRHS>(a, gi + di, gj + dj, k + dk, out);
+            for (int sv = 0; sv < SV_NRHS; sv++) {
+                double ref = stage_value(a, sv, gi + di, gj + dj, k + dk);
+                if (!(out[sv] == ref)) bad++;
+            }
+        }
+    }
+    return bad;
 }
 void emu_rhs(void* h, const double* un, const double* halo, double* B) {
     Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
