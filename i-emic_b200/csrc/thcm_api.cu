@@ -273,6 +273,35 @@ double thcmb_last_stage_ms(const thcmb_ctx* c, const char* label) {
 // The MGS chain runs without host syncs: every projection coefficient stays in device memory and is
 // consumed by the next fused (axpy + dot) kernel; one small D2H per iteration brings column i of H.
 // =============================================================================
+// Optional L2 residency hint (THCM_L2_PERSIST=1): pins the vector that an MGS chain rewrites i+2 times in the persisting
+// part of the 126 MB L2, so that only the basis vectors stream from HBM.
+static void l2_persist(thcmb_ctx* c, const void* base, size_t bytes) {
+    static int enabled = -1;
+    static size_t max_win = 0;
+    if (enabled < 0) {
+        const char* e = getenv("THCM_L2_PERSIST");
+        enabled = (e && atoi(e) != 0) ? 1 : 0;
+        if (enabled) {
+            cudaDeviceProp p; int dev = 0;
+            cudaGetDevice(&dev); cudaGetDeviceProperties(&p, dev);
+            size_t want = std::min<size_t>((size_t)p.persistingL2CacheMaxSize, (size_t)96 << 20);
+            if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) enabled = 0;
+            max_win = std::min<size_t>(want, (size_t)p.accessPolicyMaxWindowSize);
+            fprintf(stderr, "thcm_b200: L2 persistence %s (persisting max %zu MB, window max %zu MB)\n", enabled ? "on" : "off",
+                    (size_t)p.persistingL2CacheMaxSize >> 20, (size_t)p.accessPolicyMaxWindowSize >> 20);
+        }
+    }
+    if (!enabled) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = base ? std::min(bytes, max_win) : 0;
+    attr.accessPolicyWindow.hitRatio = base ? (float)std::min(1.0, (double)max_win / (double)std::max<size_t>(bytes, 1)) : 0.f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+}
+
 static void gen_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESSolver.H:258-279
     if (dy == 0.0) { cs = 1.0; sn = 0.0; }
     else if (std::abs(dy) > std::abs(dx)) { double t = dx / dy; sn = 1.0 / sqrt(1.0 + t * t); cs = t * sn; }
@@ -329,11 +358,13 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                 n_matvec++;
                 // MGS (GMRESSolver.H:177-181): H[k][i] = w.V[k]; w -= H[k][i] V[k]
                 double* dh = c->d_scalars;  // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
+                l2_persist(c, w, (size_t)n * sizeof(double));   // w is re-read and re-written by every kernel of the chain
                 dot_dev(c, n, w, V(0), dh + 0);
                 for (int k = 0; k < i; k++) mgs_step_dev(c, n, dh + k, V(k), V(k + 1), w, dh + k + 1);
                 axpy_negdev(c, n, dh + i, V(i), w);
                 dot_dev(c, n, w, w, dh + i + 1);
                 scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
+                l2_persist(c, nullptr, 0);
                 THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
                 THCM_CUDA(cudaStreamSynchronize(c->stream));
                 for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];

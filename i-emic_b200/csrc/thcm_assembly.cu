@@ -41,8 +41,11 @@ template <int NSV> struct SmemIn {
 };
 template <int MODE> struct Smem;
 template <> struct Smem<MODE_RHS> { SmemIn<SV_NRHS> in; };
-template <> struct Smem<MODE_JAC_GRAPH> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; };
-template <> struct Smem<MODE_JAC_COUNT> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; int cnt[NUN]; };
+// graph-mode output staging: cell-major with an ODD stride (105 doubles) so that the 32 lanes of a warp, each writing
+// entry p of its own cell, hit distinct 8-byte banks (stride 104 would be an 8-way conflict per half-warp)
+constexpr int VSTRIDE = NSLOT_TOTAL + 1;
+template <> struct Smem<MODE_JAC_GRAPH> { SmemIn<SV_NJAC> in; double v[TI * VSTRIDE]; int cstart[TI + 1]; };
+template <> struct Smem<MODE_JAC_COUNT> { SmemIn<SV_NJAC> in; double v[TI * VSTRIDE]; int cstart[TI + 1]; int cnt[NUN]; };
 template <> struct Smem<MODE_JAC_CRS> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; int c[TI * NSLOT_TOTAL]; int off[TI * NUN + 1]; };
 
 template <int NSV> struct SmemTile {
@@ -105,7 +108,12 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
         cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) |
               (c.k == b.L ? 32 : 0);
         if (!((nb >> 4) & 1u)) eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
-        boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
+    }
+    // open ocean away from the bottom and the lid: no LAND among the 27 (+5) neighbours of any cell of the warp, so every
+    // statement of `boundaries` is a no-op -- skip its ~60 predicated blocks (warp-uniform branch)
+    const bool open_ocean = __all_sync(0xffffffffu, !active || nb == 0u);
+    if (active) {
+        if (!open_ocean) boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
         // strict threshold of fillcolA (assemble.F90:115); the graph keeps explicit zeros instead
 #pragma unroll
         for (int q = 0; q < RowSlots<R>::N; q++) E[q] = fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
@@ -131,17 +139,30 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
         }
         return;
     } else {
-        const int g0 = a.rowptr[NUN * g.cell0];
         if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
             int cnt = 0;
+            // interior cells (the bulk): graph positions are compile-time constants; edge classes go through the table
+            const bool interior = __all_sync(0xffffffffu, !active || cls == 0);
             if (active) {
-                const int base = a.rowptr[NUN * cell + R - 1] - g0;
-                static_for<0, RowSlots<R>::N>([&](auto qc) {
-                    constexpr int q = decltype(qc)::value;
-                    int p = c_cls.pos[cls][ROW_OFF[R - 1] + q];
-                    if (p >= 0) sh.v[base + p] = E[q];
-                    if (E[q] != 0.0) cnt++;
-                });
+                if (interior) {
+                    double* dst = sh.v + lane * VSTRIDE + ROW_OFF[R - 1];
+                    static_for<0, RowSlots<R>::N>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        dst[interior_pos(R, q)] = E[q];
+                        if (E[q] != 0.0) cnt++;
+                    });
+                } else {
+                    int rowoff = 0;   // offset of row R inside the cell's block of the graph = sum of the shorter rows' lengths
+#pragma unroll
+                    for (int r = 0; r < R - 1; r++) rowoff += c_cls.rowlen[cls][r];
+                    const int base = lane * VSTRIDE + rowoff;
+                    static_for<0, RowSlots<R>::N>([&](auto qc) {
+                        constexpr int q = decltype(qc)::value;
+                        int p = c_cls.pos[cls][ROW_OFF[R - 1] + q];
+                        if (p >= 0) sh.v[base + p] = E[q];
+                        if (E[q] != 0.0) cnt++;
+                    });
+                }
             }
             if constexpr (MODE == MODE_JAC_COUNT) {
 #pragma unroll
@@ -197,6 +218,10 @@ __global__ void __launch_bounds__(ASM_THREADS) thcm_assemble_kernel(const AsmArg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileGeom g = tile_geom(a.b);
     stage_inputs(a, g, sh.in);
+    if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
+        // start of every cell's entries relative to the tile's first entry (cells at domain edges hold clipped rows)
+        if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = a.rowptr[NUN * (g.cell0 + threadIdx.x)] - a.rowptr[NUN * g.cell0];
+    }
     __syncthreads();
     switch (warp) {
     case 0: do_row<1, MODE>(a, sh, g, lane); break;
@@ -208,8 +233,20 @@ __global__ void __launch_bounds__(ASM_THREADS) thcm_assemble_kernel(const AsmArg
     }
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
         __syncthreads();
-        const int g0 = a.rowptr[NUN * g.cell0], g1 = a.rowptr[NUN * (g.cell0 + g.ncell)];
-        for (int q = threadIdx.x; q < g1 - g0; q += ASM_THREADS) a.val[g0 + q] = sh.v[q];
+        const int g0 = a.rowptr[NUN * g.cell0], tot = sh.cstart[g.ncell];
+        if (tot == g.ncell * NSLOT_TOTAL) {   // nothing clipped: cell = q / 104
+            for (int q = threadIdx.x; q < tot; q += ASM_THREADS) {
+                int cl = q / NSLOT_TOTAL;
+                a.val[g0 + q] = sh.v[cl * VSTRIDE + (q - cl * NSLOT_TOTAL)];
+            }
+        } else {
+            for (int q = threadIdx.x; q < tot; q += ASM_THREADS) {
+                int cl = min(q / NSLOT_TOTAL, g.ncell - 1);      // a few steps off at clipped edges
+                while (q < sh.cstart[cl]) cl--;
+                while (q >= sh.cstart[cl + 1]) cl++;
+                a.val[g0 + q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
+            }
+        }
         if constexpr (MODE == MODE_JAC_COUNT) {
             if (threadIdx.x == 0) a.blockcnt[blockIdx.x] = sh.cnt[0] + sh.cnt[1] + sh.cnt[2] + sh.cnt[3] + sh.cnt[4] + sh.cnt[5];
         }

@@ -16,37 +16,66 @@ constexpr int NSM = 148;  // B200: 148 SMs; persistent-style grids are sized in 
 // SpMV: CSR-vector with 8 lanes per row (rows hold 7..24 entries, THCM.C:2320-2325).
 // Column ids >= nlocal address the halo buffer.
 // ---------------------------------------------------------------------------
-constexpr int SPMV_LANES = 8;
 constexpr int SPMV_THREADS = 256;
 
+// LANES lanes share a row; every lane first issues its first UNROLL (col, val) loads -- predicated, independent --
+// then the x gathers, then the products: all loads of a row are in flight together (rows are short, so a plain
+// loop exposes one memory latency per iteration and leaves the kernel latency-bound at full occupancy).
+template <int LANES, int UNROLL>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
                                                                  const double* __restrict__ val, const double* __restrict__ x,
                                                                  const double* __restrict__ halo, int nlocal, double* __restrict__ y) {
-    const int sub = threadIdx.x & (SPMV_LANES - 1);
-    const int rows_per_block = SPMV_THREADS / SPMV_LANES;
-    for (int row = blockIdx.x * rows_per_block + (threadIdx.x / SPMV_LANES); row < nrow; row += gridDim.x * rows_per_block) {
-        const int b = rp[row], e = rp[row + 1];
+    const int sub = threadIdx.x & (LANES - 1);
+    constexpr int rows_per_block = SPMV_THREADS / LANES;
+    for (int row = blockIdx.x * rows_per_block + (threadIdx.x / LANES); row < nrow; row += gridDim.x * rows_per_block) {
+        const int b = __ldg(rp + row), e = __ldg(rp + row + 1);
+        int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int q = b + sub + u * LANES;
+            const bool ok = q < e;
+            cc[u] = ok ? __ldg(col + q) : -1;
+            vv[u] = ok ? __ldg(val + q) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+            xx[u] = cc[u] < 0 ? 0.0 : (cc[u] < nlocal ? __ldg(x + cc[u]) : __ldg(halo + (cc[u] - nlocal)));
         double s = 0.0;
-        for (int q = b + sub; q < e; q += SPMV_LANES) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) s += vv[u] * xx[u];
+        for (int q = b + sub + UNROLL * LANES; q < e; q += LANES) {   // rows longer than UNROLL*LANES (generic CSR)
             const int cidx = __ldg(col + q);
             const double xv = cidx < nlocal ? __ldg(x + cidx) : __ldg(halo + (cidx - nlocal));
             s += __ldg(val + q) * xv;
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 4, SPMV_LANES);
-        s += __shfl_xor_sync(0xffffffffu, s, 2, SPMV_LANES);
-        s += __shfl_xor_sync(0xffffffffu, s, 1, SPMV_LANES);
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
         if (sub == 0) y[row] = s;
     }
+}
+
+static int spmv_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("THCM_SPMV_VARIANT"); v = e ? atoi(e) : 2; }   // 2 = 4 lanes x 6 entries: best on B200 (profiles/)
+    return v;
 }
 
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y) {
     ProfScope prof_(c, KID_SPMV);
-    const int rows_per_block = SPMV_THREADS / SPMV_LANES;
-    long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
-    int grid = (int)std::min<long long>(want, (long long)NSM * 64);
-    if (grid < 1) grid = 1;
-    spmv_csr_kernel<<<grid, SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y);
+    auto grid_for = [&](int lanes) {
+        const int rows_per_block = SPMV_THREADS / lanes;
+        long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
+        return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 64));
+    };
+    switch (spmv_variant()) {
+    case 0: spmv_csr_kernel<8, 1><<<grid_for(8), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    case 2: spmv_csr_kernel<4, 6><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    case 3: spmv_csr_kernel<4, 3><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    case 4: spmv_csr_kernel<16, 2><<<grid_for(16), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    case 5: spmv_csr_kernel<2, 12><<<grid_for(2), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    default: spmv_csr_kernel<8, 3><<<grid_for(8), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
+    }
     c->launches++;
     return 0;
 }
@@ -56,7 +85,7 @@ int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* va
 // partials in a fixed order (deterministic) and writes the device scalar.  No host sync.
 // ---------------------------------------------------------------------------
 constexpr int RED_THREADS = 256;
-constexpr int RED_BLOCKS = NSM * 4;
+constexpr int RED_BLOCKS = NSM * 8;
 
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double wsum[RED_THREADS / 32];
@@ -117,10 +146,28 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int n, const doub
                                                                 double* partial, unsigned int* counter, double* out) {
     const double h = *hk;
     double v = 0.0;
-    for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
-        double wi = -h * vk[i] + 1.0 * w[i];   // update(-H, V[k], 1.0): this = a*A + b*this
-        w[i] = wi;
-        v += wi * vnext[i];
+    if (((((uintptr_t)vk) | ((uintptr_t)vnext) | ((uintptr_t)w)) & 15) == 0) {   // 128-bit path
+        const int n2 = n >> 1;
+        const double2* vk2 = reinterpret_cast<const double2*>(vk);
+        const double2* vn2 = reinterpret_cast<const double2*>(vnext);
+        double2* w2 = reinterpret_cast<double2*>(w);
+        for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n2; i += gridDim.x * RED_THREADS) {
+            double2 a = vk2[i], ww = w2[i], b = vn2[i];
+            ww.x = -h * a.x + 1.0 * ww.x;   // update(-H, V[k], 1.0): this = a*A + b*this
+            ww.y = -h * a.y + 1.0 * ww.y;
+            w2[i] = ww;
+            v += ww.x * b.x; v += ww.y * b.y;
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+            double wi = -h * vk[n - 1] + 1.0 * w[n - 1];
+            w[n - 1] = wi; v += wi * vnext[n - 1];
+        }
+    } else {
+        for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
+            double wi = -h * vk[i] + 1.0 * w[i];
+            w[i] = wi;
+            v += wi * vnext[i];
+        }
     }
     double s = block_sum(v);
     finish_reduction(s, partial, counter, out);

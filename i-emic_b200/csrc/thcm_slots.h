@@ -63,4 +63,17 @@ constexpr int loc_di(int loc) { return ((loc - 1) % 9) / 3 - 1; }
 constexpr int loc_dj(int loc) { return (loc - 1) % 3 - 1; }
 constexpr int loc_dk(int loc) { return loc < 10 ? 0 : (loc < 19 ? -1 : 1); }
 
+// position of slot q of row R inside the sorted maximal-graph row of an INTERIOR cell (nothing clipped, no periodic
+// reordering): Epetra sorts a row by global column id, i.e. by (k2, j2, i2, unknown)
+constexpr int interior_key(int R, int q) {
+    return (((loc_dk(row_slots(R)[q].loc) + 1) * 3 + (loc_dj(row_slots(R)[q].loc) + 1)) * 3 + (loc_di(row_slots(R)[q].loc) + 1)) * 8 +
+           row_slots(R)[q].col;
+}
+constexpr int interior_pos(int R, int q) {
+    int r = 0;
+    for (int p = 0; p < ROW_NSLOT[R - 1]; p++)
+        if (interior_key(R, p) < interior_key(R, q)) r++;
+    return r;
+}
+
 }  // namespace thcm
