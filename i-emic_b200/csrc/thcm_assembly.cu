@@ -14,12 +14,15 @@
 //   JAC_COUNT : JAC_GRAPH + number of |a|>1e-10 entries per assembly block
 //   JAC_CRS   : Fortran-order thresholded CRS begA/jcoA/coA (1-based), after the block-count scan
 //
-// Tile = TI consecutive cells of one (j,k) grid line.  Phase 1: all 192 threads stage the 3x3x(TI+2)
-// neighbourhood -- fields as usol leaves them -- and the j/k slices of the metric tables into shared
-// memory with independent 16-byte loads (one latency exposure instead of ~60 dependent ones).
-// Phase 2: warp r evaluates row type r (u,v,w,p,T,S) for the TI cells from shared memory only (no
-// divergence on the row type).  Phase 3: results, staged in shared memory at their final offsets,
-// leave as one contiguous coalesced range per block.
+// Tile = TI = 32 consecutive cells of one (j,k) grid line.
+//  Phase 1 (all threads): stage the 3x3x(TI+2) neighbourhood -- fields as usol leaves them -- and the j/k slices of
+//    the metric tables in shared memory.  Nine row descriptors are resolved once per block; positions inside the owned
+//    block take a 3-instruction fast path (3 x LDG.128 + one mask byte), only edge columns / halo / mirror rows run
+//    the general rule.  One latency exposure instead of ~60 dependent ones.
+//  Phase 2: warp r evaluates row type(s) r for the 32 cells from shared memory only: u | v | w+p | T | S
+//    (24 | 22 | 18 | 20 | 20 entries: balanced, no divergence on the row type).
+//  Phase 3: the tile's values, staged in shared memory cell by cell, leave through the TMA unit: one
+//    cp.async.bulk.global.shared::cta of 832 B per cell (SASS UBLKCP) -- clipped edge tiles use a plain coalesced loop.
 // HBM traffic per cell: 48 B state + 5 B masks in, 832 B values out.
 // =============================================================================
 #include <cstdio>
@@ -33,19 +36,28 @@ void upload_class_tables(const ClassTables& t) { THCM_CUDA(cudaMemcpyToSymbol(c_
 
 constexpr int TI = CELLS_PER_BLOCK;   // 32 cells per tile
 constexpr int TW = TI + 2;            // staged width (one neighbour column each side)
+// graph-mode output staging: cell-major, stride 106 doubles = 848 B: a multiple of 16 B (TMA bulk store source alignment)
+// and only a 2-way bank conflict when the 32 lanes of a warp each write entry p of their own cell (104 would be 8-way)
+constexpr int VSTRIDE = NSLOT_TOTAL + 2;
+
+constexpr __host__ __device__ int mode_warps(int mode) { return mode == MODE_JAC_CRS ? 6 : 5; }
+
+struct RowDesc {            // one of the 9 staged grid lines (dj, dk) of a tile
+    const double* rec;      // record of position x = 1 when the line lies inside the owned block, else nullptr
+    const uint8_t* live;    // uvlive byte of position x = 1
+    int wlive;              // k + dk != L
+};
 
 template <int NSV> struct SmemIn {
     double st[NSV][3][3][TW];         // [field][dk+1][dj+1][x]
     double tj[J_COUNT][3];            // j-tables at gj-1, gj, gj+1
     double tk[K_COUNT];               // k-tables at k
+    RowDesc row[9];
 };
 template <int MODE> struct Smem;
 template <> struct Smem<MODE_RHS> { SmemIn<SV_NRHS> in; };
-// graph-mode output staging: cell-major with an ODD stride (105 doubles) so that the 32 lanes of a warp, each writing
-// entry p of its own cell, hit distinct 8-byte banks (stride 104 would be an 8-way conflict per half-warp)
-constexpr int VSTRIDE = NSLOT_TOTAL + 1;
-template <> struct Smem<MODE_JAC_GRAPH> { SmemIn<SV_NJAC> in; double v[TI * VSTRIDE]; int cstart[TI + 1]; };
-template <> struct Smem<MODE_JAC_COUNT> { SmemIn<SV_NJAC> in; double v[TI * VSTRIDE]; int cstart[TI + 1]; int cnt[NUN]; };
+template <> struct Smem<MODE_JAC_GRAPH> { SmemIn<SV_NJAC> in; alignas(16) double v[TI * VSTRIDE]; int cstart[TI + 1]; };
+template <> struct Smem<MODE_JAC_COUNT> { SmemIn<SV_NJAC> in; alignas(16) double v[TI * VSTRIDE]; int cstart[TI + 1]; int cnt[NUN]; };
 template <> struct Smem<MODE_JAC_CRS> { SmemIn<SV_NJAC> in; double v[TI * NSLOT_TOTAL]; int c[TI * NSLOT_TOTAL]; int off[TI * NUN + 1]; };
 
 template <int NSV> struct SmemTile {
@@ -71,22 +83,42 @@ __device__ __forceinline__ TileGeom tile_geom(const DevBlock& b) {
     return g;
 }
 
-template <int NSV>
+template <int NSV, int NT>
 __device__ __forceinline__ void stage_inputs(const AsmArgs& a, const TileGeom& g, SmemIn<NSV>& in) {
-    // positions: 3 levels x 3 rows x (ncell + 2) columns; each thread stages whole positions (all fields of a cell
-    // come from the same 48-byte record)
-    const int w = g.ncell + 2, npos = 9 * w;
-    for (int p = threadIdx.x; p < npos; p += ASM_THREADS) {
-        int x = p % w, r = p / w, dj = r % 3 - 1, dk = r / 3 - 1;
-        double out[NSV];
-        stage_position<NSV>(a, g.gi0 - 1 + x, g.gj + dj, g.k + dk, out);
-#pragma unroll
-        for (int sv = 0; sv < NSV; sv++) in.st[sv][dk + 1][dj + 1][x] = out[sv];
+    const DevBlock& b = a.b;
+    // ---- row descriptors: which of the 9 grid lines lie inside the owned block (=> contiguous 48-byte records) ----
+    if (threadIdx.x < 9) {
+        int dj = (int)threadIdx.x % 3 - 1, dk = (int)threadIdx.x / 3 - 1;
+        int gj2 = g.gj + dj, k2 = g.k + dk, je = gj2 - 1 - b.j0;
+        RowDesc d{nullptr, nullptr, 0};
+        if (je >= 0 && je < b.m0 && k2 >= 1 && k2 <= b.L) {   // inside the block implies inside the domain
+            size_t cell = ((size_t)(k2 - 1) * b.m0 + je) * b.n0 + (g.gi0 - 1 - b.i0);
+            d.rec = a.un + (size_t)NUN * cell;
+            d.live = a.uvlive + ((size_t)(k2 - 1) * (b.m0 + 2) + (gj2 - b.j0)) * (b.n0 + 2) + (g.gi0 - b.i0);
+            d.wlive = k2 != b.L;
+        }
+        in.row[threadIdx.x] = d;
     }
     const DevTables& t = a.t;
-    for (int q = threadIdx.x; q < J_COUNT * 3 + K_COUNT; q += ASM_THREADS) {
+    for (int q = threadIdx.x; q < J_COUNT * 3 + K_COUNT; q += NT) {
         if (q < J_COUNT * 3) { int tb = q / 3, d = q % 3; in.tj[tb][d] = __ldg(t.jt + (size_t)tb * t.jstride + g.gj + d - 1); }
         else { int tb = q - J_COUNT * 3; in.tk[tb] = __ldg(t.kt + (size_t)tb * t.kstride + g.k); }
+    }
+    __syncthreads();
+    // ---- positions: 9 lines x (ncell + 2) columns ----
+    const int w = g.ncell + 2;
+    for (int p = threadIdx.x; p < 9 * TW; p += NT) {
+        const int r = p / TW, x = p - r * TW;
+        if (x >= w) continue;
+        const int dj = r % 3 - 1, dk = r / 3 - 1;
+        const RowDesc d = in.row[r];
+        double out[NSV];
+        if (d.rec != nullptr && x >= 1 && x <= g.ncell)
+            stage_regular<NSV>(d.rec + (size_t)NUN * (x - 1), d.live[x - 1] != 0, d.wlive != 0, out);
+        else
+            stage_position<NSV>(a, g.gi0 - 1 + x, g.gj + dj, g.k + dk, out);
+#pragma unroll
+        for (int sv = 0; sv < NSV; sv++) in.st[sv][dk + 1][dj + 1][x] = out[sv];
     }
 }
 
@@ -211,40 +243,63 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
     }
 }
 
+// TMA bulk store shared -> global (SASS UBLKCP); source and destination 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, int bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(ASM_THREADS) thcm_assemble_kernel(const AsmArgs a) {
+__global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(const AsmArgs a) {
+    constexpr int NT = 32 * mode_warps(MODE);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem<MODE>& sh = *reinterpret_cast<Smem<MODE>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileGeom g = tile_geom(a.b);
-    stage_inputs(a, g, sh.in);
+    stage_inputs<MODE == MODE_RHS ? SV_NRHS : SV_NJAC, NT>(a, g, sh.in);
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
         // start of every cell's entries relative to the tile's first entry (cells at domain edges hold clipped rows)
         if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = a.rowptr[NUN * (g.cell0 + threadIdx.x)] - a.rowptr[NUN * g.cell0];
     }
     __syncthreads();
-    switch (warp) {
-    case 0: do_row<1, MODE>(a, sh, g, lane); break;
-    case 1: do_row<2, MODE>(a, sh, g, lane); break;
-    case 2: do_row<3, MODE>(a, sh, g, lane); break;
-    case 3: do_row<4, MODE>(a, sh, g, lane); break;
-    case 4: do_row<5, MODE>(a, sh, g, lane); break;
-    default: do_row<6, MODE>(a, sh, g, lane); break;
+    if constexpr (MODE == MODE_JAC_CRS) {
+        switch (warp) {
+        case 0: do_row<1, MODE>(a, sh, g, lane); break;
+        case 1: do_row<2, MODE>(a, sh, g, lane); break;
+        case 2: do_row<3, MODE>(a, sh, g, lane); break;
+        case 3: do_row<4, MODE>(a, sh, g, lane); break;
+        case 4: do_row<5, MODE>(a, sh, g, lane); break;
+        default: do_row<6, MODE>(a, sh, g, lane); break;
+        }
+    } else {   // 5 warps: u | v | w + p | T | S
+        switch (warp) {
+        case 0: do_row<1, MODE>(a, sh, g, lane); break;
+        case 1: do_row<2, MODE>(a, sh, g, lane); break;
+        case 2: do_row<3, MODE>(a, sh, g, lane); do_row<4, MODE>(a, sh, g, lane); break;
+        case 3: do_row<5, MODE>(a, sh, g, lane); break;
+        default: do_row<6, MODE>(a, sh, g, lane); break;
+        }
     }
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
-        __syncthreads();
         const int g0 = a.rowptr[NUN * g.cell0], tot = sh.cstart[g.ncell];
-        if (tot == g.ncell * NSLOT_TOTAL) {   // nothing clipped: cell = q / 104
-            for (int q = threadIdx.x; q < tot; q += ASM_THREADS) {
-                int cl = q / NSLOT_TOTAL;
-                a.val[g0 + q] = sh.v[cl * VSTRIDE + (q - cl * NSLOT_TOTAL)];
+        double* gdst = a.val + g0;
+        const bool bulk = tot == g.ncell * NSLOT_TOTAL && (((uintptr_t)gdst) & 15) == 0;   // nothing clipped, aligned
+        if (bulk) {
+            // generic-proxy writes (STS) must be visible to the async proxy before the TMA unit reads them
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x < g.ncell) {
+                bulk_store(gdst + (size_t)threadIdx.x * NSLOT_TOTAL, sh.v + threadIdx.x * VSTRIDE, NSLOT_TOTAL * (int)sizeof(double));
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // smem must stay valid until it has been read
             }
         } else {
-            for (int q = threadIdx.x; q < tot; q += ASM_THREADS) {
+            __syncthreads();
+            for (int q = threadIdx.x; q < tot; q += NT) {
                 int cl = min(q / NSLOT_TOTAL, g.ncell - 1);      // a few steps off at clipped edges
                 while (q < sh.cstart[cl]) cl--;
                 while (q >= sh.cstart[cl + 1]) cl++;
-                a.val[g0 + q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
+                gdst[q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
             }
         }
         if constexpr (MODE == MODE_JAC_COUNT) {
@@ -253,7 +308,7 @@ __global__ void __launch_bounds__(ASM_THREADS) thcm_assemble_kernel(const AsmArg
     } else if constexpr (MODE == MODE_JAC_CRS) {
         __syncthreads();
         const int bbase = a.blockcnt[blockIdx.x], tot = sh.off[TI * NUN];
-        for (int q = threadIdx.x; q < tot; q += ASM_THREADS) { a.coA[bbase + q] = sh.v[q]; a.jcoA[bbase + q] = sh.c[q]; }
+        for (int q = threadIdx.x; q < tot; q += NT) { a.coA[bbase + q] = sh.v[q]; a.jcoA[bbase + q] = sh.c[q]; }
         if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) a.begA[NUN * a.b.ncell] = bbase + tot + 1;
     }
 }
@@ -302,11 +357,12 @@ template <int MODE> static void launch_mode(thcmb_ctx* c, const AsmArgs& a, int 
         THCM_CUDA(cudaFuncSetAttribute(thcm_assemble_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<MODE>)));
         attr_set = true;
     }
-    thcm_assemble_kernel<MODE><<<nblk, ASM_THREADS, sizeof(Smem<MODE>), c->stream>>>(a);
+    thcm_assemble_kernel<MODE><<<nblk, 32 * mode_warps(MODE), sizeof(Smem<MODE>), c->stream>>>(a);
 }
 
 int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA) {
     const Block& b = c->blk;
+    if ((((uintptr_t)d_un) & 15) != 0) fatal("state vector must be 16-byte aligned (cells are read as 3 x 128-bit loads)");
     AsmArgs a;
     a.b = DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
     a.t = c->tab; a.t.jt = c->d_jt; a.t.kt = c->d_kt;

@@ -167,6 +167,29 @@ THCM_HD void stage_position(const AsmArgs& a, int gi, int gj, int k, double* out
     }
 }
 
+// Fast path of the staging for a position that lies INSIDE the owned block (the bulk of a tile): `rec` is the cell's
+// 48-byte record, `live` its uvlive byte, wlive = (k != L).  Equals stage_position()/stage_value() there (tests/emu).
+template <int NSV>
+THCM_HD void stage_regular(const double* rec, bool live, bool wlive, double* out) {
+    double r[NUN];
+#ifdef __CUDA_ARCH__
+    const double2* s2 = reinterpret_cast<const double2*>(rec);
+    double2 q0 = __ldg(s2), q1 = __ldg(s2 + 1), q2 = __ldg(s2 + 2);
+    r[0] = q0.x; r[1] = q0.y; r[2] = q1.x; r[3] = q1.y; r[4] = q2.x; r[5] = q2.y;
+#else
+    for (int v = 0; v < NUN; v++) r[v] = rec[v];
+#endif
+    out[SV_U] = live ? r[0] : 0.0;
+    out[SV_V] = live ? r[1] : 0.0;
+    out[SV_W] = wlive ? r[2] : 0.0;
+    out[SV_T] = r[4];
+    out[SV_S] = r[5];
+    if constexpr (NSV > SV_NJAC) {
+#pragma unroll
+        for (int v = 0; v < NUN; v++) out[SV_RAW + v] = r[v];
+    }
+}
+
 // tile / table accessors used by the host emulation and as the reference semantics of the shared-memory ones:
 //   tile(sv, di, dj, dk)  staged field at the neighbour offset;  tabs.jt(table, dj), tabs.kt(table)
 struct DirectTile {

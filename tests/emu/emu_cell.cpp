@@ -176,6 +176,15 @@ long long emu_check_staging(void* h, const double* un, const double* halo) {
                 double ref = stage_value(a, sv, gi + di, gj + dj, k + dk);
                 if (!(out[sv] == ref)) bad++;
             }
+            // the fast path the kernels take for positions inside the owned block (thcm_assembly.cu stage_inputs)
+            int ie = li + di, je = lj + dj, k2 = k + dk;
+            if (ie >= 0 && ie < b.n0 && je >= 0 && je < b.m0 && k2 >= 1 && k2 <= b.L) {
+                size_t cc = ((size_t)(k2 - 1) * b.m0 + je) * b.n0 + ie;
+                bool live = a.uvlive[((size_t)(k2 - 1) * (b.m0 + 2) + (gj + dj - b.j0)) * (b.n0 + 2) + (gi + di - b.i0)] != 0;
+                double fast[SV_NRHS];
+                stage_regular<SV_NRHS>(a.un + (size_t)NUN * cc, live, k2 != b.L, fast);
+                for (int sv = 0; sv < SV_NRHS; sv++) if (!(fast[sv] == out[sv])) bad++;
+            }
         }
     }
     return bad;
