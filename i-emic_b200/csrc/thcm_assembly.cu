@@ -16,9 +16,9 @@
 //
 // Tile = TI = 32 consecutive cells of one (j,k) grid line.
 //  Phase 1 (all threads): stage the 3x3x(TI+2) neighbourhood -- fields as usol leaves them -- and the j/k slices of
-//    the metric tables in shared memory.  Nine row descriptors are resolved once per block; positions inside the owned
-//    block take a 3-instruction fast path (3 x LDG.128 + one mask byte), only edge columns / halo / mirror rows run
-//    the general rule.  One latency exposure instead of ~60 dependent ones.
+//    the metric tables in shared memory.  Positions inside the owned block take a fast path (3 x LDG.128 + one mask
+//    byte), only edge columns / halo / mirror rows run the general rule; all loads of a block are issued together:
+//    one latency exposure instead of ~60 dependent ones.
 //  Phase 2: warp r evaluates row type(s) r for the 32 cells from shared memory only: u | v | w+p | T | S
 //    (24 | 22 | 18 | 20 | 20 entries: balanced, no divergence on the row type).
 //  Phase 3: the tile's values, staged in shared memory cell by cell, leave through the TMA unit: one
@@ -42,17 +42,10 @@ constexpr int VSTRIDE = NSLOT_TOTAL + 2;
 
 constexpr __host__ __device__ int mode_warps(int mode) { return mode == MODE_JAC_CRS ? 6 : 5; }
 
-struct RowDesc {            // one of the 9 staged grid lines (dj, dk) of a tile
-    const double* rec;      // record of position x = 1 when the line lies inside the owned block, else nullptr
-    const uint8_t* live;    // uvlive byte of position x = 1
-    int wlive;              // k + dk != L
-};
-
 template <int NSV> struct SmemIn {
     double st[NSV][3][3][TW];         // [field][dk+1][dj+1][x]
     double tj[J_COUNT][3];            // j-tables at gj-1, gj, gj+1
     double tk[K_COUNT];               // k-tables at k
-    RowDesc row[9];
 };
 template <int MODE> struct Smem;
 template <> struct Smem<MODE_RHS> { SmemIn<SV_NRHS> in; };
@@ -86,44 +79,35 @@ __device__ __forceinline__ TileGeom tile_geom(const DevBlock& b) {
 template <int NSV, int NT>
 __device__ __forceinline__ void stage_inputs(const AsmArgs& a, const TileGeom& g, SmemIn<NSV>& in) {
     const DevBlock& b = a.b;
-    // ---- row descriptors: which of the 9 grid lines lie inside the owned block (=> contiguous 48-byte records) ----
-    if (threadIdx.x < 9) {
-        int dj = (int)threadIdx.x % 3 - 1, dk = (int)threadIdx.x / 3 - 1;
-        int gj2 = g.gj + dj, k2 = g.k + dk, je = gj2 - 1 - b.j0;
-        RowDesc d{nullptr, nullptr, 0};
-        if (je >= 0 && je < b.m0 && k2 >= 1 && k2 <= b.L) {   // inside the block implies inside the domain
-            size_t cell = ((size_t)(k2 - 1) * b.m0 + je) * b.n0 + (g.gi0 - 1 - b.i0);
-            d.rec = a.un + (size_t)NUN * cell;
-            d.live = a.uvlive + ((size_t)(k2 - 1) * (b.m0 + 2) + (gj2 - b.j0)) * (b.n0 + 2) + (g.gi0 - b.i0);
-            d.wlive = k2 != b.L;
+    // ---- positions: 9 grid lines (dj, dk) x (ncell + 2) columns.  A line inside the owned block is a run of contiguous
+    //      48-byte records (fast path); the descriptor is recomputed per position (a dozen integer ops) so that every
+    //      global load of the block -- records, mask bytes, table slices -- is in flight at once: ONE latency exposure ----
+    const int w = g.ncell + 2;
+    for (int p = threadIdx.x; p < 9 * TW; p += NT) {
+        const int r = p / TW, x = p - r * TW;
+        if (x >= w) continue;
+        const int dj = r % 3 - 1, dk = r / 3 - 1;
+        const int gj2 = g.gj + dj, k2 = g.k + dk, je = gj2 - 1 - b.j0;
+        double out[NSV];
+        if (je >= 0 && je < b.m0 && k2 >= 1 && k2 <= b.L && x >= 1 && x <= g.ncell) {   // inside the block => inside the domain
+            const size_t cell = ((size_t)(k2 - 1) * b.m0 + je) * b.n0 + (g.gi0 - 1 - b.i0) + (x - 1);
+            const uint8_t live = __ldg(a.uvlive + ((size_t)(k2 - 1) * (b.m0 + 2) + (gj2 - b.j0)) * (b.n0 + 2) + (g.gi0 - b.i0) + (x - 1));
+            stage_regular<NSV>(a.un + (size_t)NUN * cell, live != 0, k2 != b.L, out);
+        } else {
+            stage_position<NSV>(a, g.gi0 - 1 + x, g.gj + dj, g.k + dk, out);
         }
-        in.row[threadIdx.x] = d;
+#pragma unroll
+        for (int sv = 0; sv < NSV; sv++) in.st[sv][dk + 1][dj + 1][x] = out[sv];
     }
     const DevTables& t = a.t;
     for (int q = threadIdx.x; q < J_COUNT * 3 + K_COUNT; q += NT) {
         if (q < J_COUNT * 3) { int tb = q / 3, d = q % 3; in.tj[tb][d] = __ldg(t.jt + (size_t)tb * t.jstride + g.gj + d - 1); }
         else { int tb = q - J_COUNT * 3; in.tk[tb] = __ldg(t.kt + (size_t)tb * t.kstride + g.k); }
     }
-    __syncthreads();
-    // ---- positions: 9 lines x (ncell + 2) columns ----
-    const int w = g.ncell + 2;
-    for (int p = threadIdx.x; p < 9 * TW; p += NT) {
-        const int r = p / TW, x = p - r * TW;
-        if (x >= w) continue;
-        const int dj = r % 3 - 1, dk = r / 3 - 1;
-        const RowDesc d = in.row[r];
-        double out[NSV];
-        if (d.rec != nullptr && x >= 1 && x <= g.ncell)
-            stage_regular<NSV>(d.rec + (size_t)NUN * (x - 1), d.live[x - 1] != 0, d.wlive != 0, out);
-        else
-            stage_position<NSV>(a, g.gi0 - 1 + x, g.gj + dj, g.k + dk, out);
-#pragma unroll
-        for (int sv = 0; sv < NSV; sv++) in.st[sv][dk + 1][dj + 1][x] = out[sv];
-    }
 }
 
 template <int R, int MODE>
-__device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const TileGeom& g, int lane) {
+__device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const TileGeom& g, int lane, uint32_t nb_in, double sm) {
     constexpr int NSV = MODE == MODE_RHS ? SV_NRHS : SV_NJAC;
     const DevBlock& b = a.b;
     const int cell = g.cell0 + lane;
@@ -135,8 +119,7 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
     SmemTile<NSV> tile{&sh.in, lane};
     if (active) {
         c.li = cell % b.n0; c.lj = g.lj; c.gi = g.gi0 + lane; c.gj = g.gj; c.k = g.k;
-        nb = a.nbmask[cell];
-        double sm = (double)(int)(int8_t)a.surf[g.lj * b.n0 + c.li];
+        nb = nb_in;
         cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) |
               (c.k == b.L ? 32 : 0);
         if (!((nb >> 4) & 1u)) eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
@@ -256,32 +239,39 @@ __global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(co
     Smem<MODE>& sh = *reinterpret_cast<Smem<MODE>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const TileGeom g = tile_geom(a.b);
+    // per-cell mask words are fetched before the staging so that their latency overlaps it (lane <-> cell)
+    uint32_t nb = 0; double sm = 0.0; int g0 = 0;
+    if (lane < g.ncell) {
+        nb = __ldg(a.nbmask + g.cell0 + lane);
+        sm = (double)(int)(int8_t)__ldg(a.surf + g.lj * a.b.n0 + (g.cell0 + lane) % a.b.n0);
+    }
+    if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) g0 = __ldg(a.rowptr + NUN * g.cell0);
     stage_inputs<MODE == MODE_RHS ? SV_NRHS : SV_NJAC, NT>(a, g, sh.in);
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
         // start of every cell's entries relative to the tile's first entry (cells at domain edges hold clipped rows)
-        if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = a.rowptr[NUN * (g.cell0 + threadIdx.x)] - a.rowptr[NUN * g.cell0];
+        if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x)) - g0;
     }
     __syncthreads();
     if constexpr (MODE == MODE_JAC_CRS) {
         switch (warp) {
-        case 0: do_row<1, MODE>(a, sh, g, lane); break;
-        case 1: do_row<2, MODE>(a, sh, g, lane); break;
-        case 2: do_row<3, MODE>(a, sh, g, lane); break;
-        case 3: do_row<4, MODE>(a, sh, g, lane); break;
-        case 4: do_row<5, MODE>(a, sh, g, lane); break;
-        default: do_row<6, MODE>(a, sh, g, lane); break;
+        case 0: do_row<1, MODE>(a, sh, g, lane, nb, sm); break;
+        case 1: do_row<2, MODE>(a, sh, g, lane, nb, sm); break;
+        case 2: do_row<3, MODE>(a, sh, g, lane, nb, sm); break;
+        case 3: do_row<4, MODE>(a, sh, g, lane, nb, sm); break;
+        case 4: do_row<5, MODE>(a, sh, g, lane, nb, sm); break;
+        default: do_row<6, MODE>(a, sh, g, lane, nb, sm); break;
         }
     } else {   // 5 warps: u | v | w + p | T | S
         switch (warp) {
-        case 0: do_row<1, MODE>(a, sh, g, lane); break;
-        case 1: do_row<2, MODE>(a, sh, g, lane); break;
-        case 2: do_row<3, MODE>(a, sh, g, lane); do_row<4, MODE>(a, sh, g, lane); break;
-        case 3: do_row<5, MODE>(a, sh, g, lane); break;
-        default: do_row<6, MODE>(a, sh, g, lane); break;
+        case 0: do_row<1, MODE>(a, sh, g, lane, nb, sm); break;
+        case 1: do_row<2, MODE>(a, sh, g, lane, nb, sm); break;
+        case 2: do_row<3, MODE>(a, sh, g, lane, nb, sm); do_row<4, MODE>(a, sh, g, lane, nb, sm); break;
+        case 3: do_row<5, MODE>(a, sh, g, lane, nb, sm); break;
+        default: do_row<6, MODE>(a, sh, g, lane, nb, sm); break;
         }
     }
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
-        const int g0 = a.rowptr[NUN * g.cell0], tot = sh.cstart[g.ncell];
+        const int tot = sh.cstart[g.ncell];
         double* gdst = a.val + g0;
         const bool bulk = tot == g.ncell * NSLOT_TOTAL && (((uintptr_t)gdst) & 15) == 0;   // nothing clipped, aligned
         if (bulk) {
