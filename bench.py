@@ -313,8 +313,19 @@ def main():
         e["share_of_step"] = e["launches_per_step"] * avg / step_ms
         kernels[name] = e
     dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/summarize.py), null when not captured
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if a.gpus == 1 and [n, m, l] == list(GRID):
+            traffic = tr.get(dom, {}).get("dram_bytes")
+            for kname, e in kernels.items():
+                if kname in tr:
+                    e["ncu_dram_bytes"] = tr[kname]["dram_bytes"]
+    except Exception:
+        pass
     roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom].get("gbs"), "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom].get("frac_of_peak"), "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom].get("frac_of_peak"), "traffic": traffic, "peak_source": peak_src,
             "alg_bytes_per_launch": kernels[dom].get("alg_bytes"), "avg_launch_ms": kernels[dom]["avg_ms"],
             "share_of_step": kernels[dom]["share_of_step"]}
     line = {"metric": "newton_step_seconds", "value": step_ms * 1e-3, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
