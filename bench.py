@@ -188,7 +188,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     iters = a.gmres_iters
     config = {"workload": workload_name(n, m, l, iters), "grid": [n, m, l], "gmres_iters": iters, "precon": "6x6 block-diagonal",
-              "parallelism": f"lon x lat block partition over {a.gpus} GPU(s) (Decomp2D)", "l2": "working set (Jacobian 1.6 GB + Krylov basis) >> 126 MB L2; no flush needed"}
+              "parallelism": f"lon x lat block partition over {a.gpus} GPU(s) (Decomp2D), halo: NCCL send/recv, dots: fused reduction + P2P all-reduce over NVLink", "l2": "working set (Jacobian 1.6 GB + Krylov basis) >> 126 MB L2; no flush needed"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -201,6 +201,13 @@ def main():
                 "e2e": {"value": r["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return 0
+
+    # libraries (NCCL, torch) may print to stdout: keep the real stdout for the ONE JSON line, send the rest to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     import numpy as np
     import torch
@@ -344,7 +351,7 @@ def main():
             line["cpu_baseline"] = {"value": r["value"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"], "stages_s": r["stages_s"]}
         except Exception as ex:  # the baseline must never take the benchmark line down
             line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
-    print(json.dumps(line))
+    emit(line)
     t.close()
     if world > 1:
         torch.distributed.destroy_process_group()

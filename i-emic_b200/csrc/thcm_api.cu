@@ -141,6 +141,7 @@ void thcmb_destroy(thcmb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_close(c);
     nccl_destroy(c);
     for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
                     (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)c->d_halo, (void*)c->d_sendbuf, (void*)c->d_recvbuf,
@@ -180,6 +181,8 @@ void thcmb_get_cob(thcmb_ctx* c, double* cob) { memcpy(cob, c->cob_local.data(),
 
 int thcmb_nccl_unique_id(void* id128) { return nccl_unique_id(id128); }
 int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128); }
+int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64) { return p2p_local_handle(c, handle64); }
+int thcmb_p2p_open(thcmb_ctx* c, const void* handles_all) { return p2p_open(c, handles_all); }
 
 int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x) { return halo_exchange(c, d_x); }
 

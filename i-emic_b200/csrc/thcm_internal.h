@@ -123,6 +123,12 @@ struct thcmb_ctx {
     std::vector<Peer> peers;
     int nsend_cells = 0, nrecv_cells = 0;
     void* nccl_comm = nullptr;
+    // fused reduction + all-reduce over NVLink peer memory (thcm_linalg.cu)
+    bool p2p_on = false;
+    void* d_mailbox = nullptr;
+    void* d_peer_mailboxes = nullptr;
+    std::vector<void*> p2p_peer_ptrs;
+    unsigned long long p2p_seq = 0;
     // ---- workspaces ----
     double* d_un = nullptr;         // staging for host-pointer entry points
     double* d_tmp = nullptr;
@@ -176,6 +182,9 @@ int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, cons
 int nccl_unique_id(void* id128);
 int nccl_init(thcmb_ctx* c, const void* id128);
 void nccl_destroy(thcmb_ctx* c);
+int p2p_local_handle(thcmb_ctx* c, void* handle64);
+int p2p_open(thcmb_ctx* c, const void* handles_all);
+void p2p_close(thcmb_ctx* c);
 void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<uint8_t>& surf, std::vector<uint8_t>& uvlive,
                        std::vector<int>& send_idx, std::vector<int>& recv_slot);
 const std::string& last_error();

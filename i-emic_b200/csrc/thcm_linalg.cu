@@ -103,8 +103,26 @@ __device__ __forceinline__ double block_sum(double v) {
     return s;  // valid in thread 0
 }
 
-__device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out) {
+// ---------------------------------------------------------------------------
+// Fused reduction + cross-GPU all-reduce over NVLink peer memory.
+// Every rank owns a small mailbox (cudaMalloc + CUDA IPC, mapped by all peers).  The LAST block of a reduction kernel
+// -- the one that sums the per-block partials -- stores the rank's sum straight into every peer's mailbox (P2P store over
+// NVLink), then polls its own mailbox for the peers' sums and adds them in rank order (bitwise identical on all ranks).
+// One kernel does the local reduction and the collective: no NCCL launch (~10 us) per Krylov dot product.
+// Slots are double-buffered by the parity of a sequence number that all ranks advance in lockstep (SPMD).
+// ---------------------------------------------------------------------------
+struct P2PSlot { double val; unsigned long long seq; };
+struct P2PArgs {
+    int nranks, rank;
+    P2PSlot* mine;            // [2][MAX_RANKS]
+    P2PSlot* const* peers;    // device array [nranks] of peer mailboxes (entry `rank` unused)
+    unsigned long long seq;   // > 0
+};
+constexpr int P2P_MAX_RANKS = 16;
+
+__device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     __shared__ bool last;
+    __shared__ double peer_val[P2P_MAX_RANKS];
     if (threadIdx.x == 0) {
         partial[blockIdx.x] = blocksum;
         __threadfence();
@@ -116,12 +134,41 @@ __device__ __forceinline__ void finish_reduction(double blocksum, double* partia
         double v = 0.0;
         for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) v += ((volatile double*)partial)[i];
         double s = block_sum(v);
-        if (threadIdx.x == 0) { *out = s; *counter = 0u; }
+        if (pa.nranks <= 1) {
+            if (threadIdx.x == 0) { *out = s; *counter = 0u; }
+            return;
+        }
+        __shared__ double mysum;
+        if (threadIdx.x == 0) { mysum = s; *counter = 0u; }
+        __syncthreads();
+        const int par = (int)(pa.seq & 1ull);
+        if (threadIdx.x < pa.nranks) {
+            const int r = threadIdx.x;
+            if (r == pa.rank) peer_val[r] = mysum;
+            else {
+                // push: value, system-scope fence, then the sequence flag
+                volatile P2PSlot* dst = pa.peers[r] + par * P2P_MAX_RANKS + pa.rank;
+                dst->val = mysum;
+                __threadfence_system();
+                dst->seq = pa.seq;
+                // pull: wait for peer r's flag in my own mailbox
+                volatile P2PSlot* src = pa.mine + par * P2P_MAX_RANKS + r;
+                while (src->seq != pa.seq) { }
+                __threadfence_system();
+                peer_val[r] = src->val;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int r = 0; r < pa.nranks; r++) tot += peer_val[r];   // fixed rank order: identical bits on every rank
+            *out = tot;
+        }
     }
 }
 
 __global__ void __launch_bounds__(RED_THREADS) dot_kernel(int n, const double* __restrict__ x, const double* __restrict__ y,
-                                                           double* partial, unsigned int* counter, double* out) {
+                                                           double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     double v = 0.0;
     if ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) {   // 16-byte aligned: 128-bit loads
         const int n2 = n >> 1;
@@ -136,14 +183,14 @@ __global__ void __launch_bounds__(RED_THREADS) dot_kernel(int n, const double* _
         for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) v += x[i] * y[i];
     }
     double s = block_sum(v);
-    finish_reduction(s, partial, counter, out);
+    finish_reduction(s, partial, counter, out, pa);
 }
 
 // fused modified Gram-Schmidt step (GMRESSolver.H:177-181): w -= h_k * v_k ; h_next = w . v_next
 // (h_k read from device memory: the previous reduction result; bitwise the same operations as dot + update)
 __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int n, const double* __restrict__ hk, const double* __restrict__ vk,
                                                                 const double* __restrict__ vnext, double* __restrict__ w,
-                                                                double* partial, unsigned int* counter, double* out) {
+                                                                double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     const double h = *hk;
     double v = 0.0;
     if (((((uintptr_t)vk) | ((uintptr_t)vnext) | ((uintptr_t)w)) & 15) == 0) {   // 128-bit path
@@ -170,7 +217,7 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int n, const doub
         }
     }
     double s = block_sum(v);
-    finish_reduction(s, partial, counter, out);
+    finish_reduction(s, partial, counter, out, pa);
 }
 
 __global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
@@ -199,17 +246,67 @@ static inline int ew_grid(int n) {
     return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 16));
 }
 
+static P2PArgs p2p_args(thcmb_ctx* c) {
+    P2PArgs pa{1, 0, nullptr, nullptr, 0ull};
+    if (c->p2p_on) {
+        pa.nranks = c->blk.nranks; pa.rank = c->blk.rank;
+        pa.mine = (P2PSlot*)c->d_mailbox; pa.peers = (P2PSlot* const*)c->d_peer_mailboxes;
+        pa.seq = ++c->p2p_seq;
+    }
+    return pa;
+}
+
+// CUDA IPC plumbing of the mailboxes (one cudaMalloc per rank, mapped by every peer of the same node)
+int p2p_local_handle(thcmb_ctx* c, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (c->blk.nranks > P2P_MAX_RANKS) return -1;
+    if (!c->d_mailbox) {
+        THCM_CUDA(cudaMalloc(&c->d_mailbox, sizeof(P2PSlot) * 2 * P2P_MAX_RANKS));
+        THCM_CUDA(cudaMemset(c->d_mailbox, 0, sizeof(P2PSlot) * 2 * P2P_MAX_RANKS));
+        THCM_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, c->d_mailbox);
+    if (e != cudaSuccess) { set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); return -2; }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int p2p_open(thcmb_ctx* c, const void* handles_all) {
+    std::vector<void*> ptrs(c->blk.nranks, nullptr);
+    for (int r = 0; r < c->blk.nranks; r++) {
+        if (r == c->blk.rank) { ptrs[r] = c->d_mailbox; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles_all + 64 * (size_t)r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&ptrs[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); cudaGetLastError(); return -1; }
+    }
+    THCM_CUDA(cudaMalloc(&c->d_peer_mailboxes, sizeof(void*) * ptrs.size()));
+    THCM_CUDA(cudaMemcpy(c->d_peer_mailboxes, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice));
+    c->p2p_peer_ptrs = ptrs;
+    c->p2p_seq = 0;
+    c->p2p_on = true;
+    return 0;
+}
+void p2p_close(thcmb_ctx* c) {
+    for (int r = 0; r < (int)c->p2p_peer_ptrs.size(); r++)
+        if (r != c->blk.rank && c->p2p_peer_ptrs[r]) cudaIpcCloseMemHandle(c->p2p_peer_ptrs[r]);
+    c->p2p_peer_ptrs.clear();
+    if (c->d_peer_mailboxes) cudaFree(c->d_peer_mailboxes);
+    if (c->d_mailbox) cudaFree(c->d_mailbox);
+    c->d_peer_mailboxes = nullptr; c->d_mailbox = nullptr; c->p2p_on = false;
+}
+
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out) {
     { ProfScope prof_(c, KID_DOT);
-    dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, x, y, c->d_partial, c->d_counter, d_out); }
+    dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, x, y, c->d_partial, c->d_counter, d_out, p2p_args(c)); }
     c->launches++;
-    return allreduce_dev(c, d_out, 1);
+    return c->p2p_on ? 0 : allreduce_dev(c, d_out, 1);
 }
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out) {
     { ProfScope prof_(c, KID_MGS);
-    mgs_step_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, d_hk, vk, vnext, w, c->d_partial, c->d_counter, d_out); }
+    mgs_step_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, d_hk, vk, vnext, w, c->d_partial, c->d_counter, d_out, p2p_args(c)); }
     c->launches++;
-    return allreduce_dev(c, d_out, 1);
+    return c->p2p_on ? 0 : allreduce_dev(c, d_out, 1);
 }
 int axpby(thcmb_ctx* c, int n, double a, const double* x, double b, double* y) {
     ProfScope prof_(c, KID_AXPBY);

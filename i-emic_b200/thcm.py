@@ -91,6 +91,7 @@ def load_library(path=None):
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
+        "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]),
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
@@ -169,6 +170,22 @@ class THCM:
         rc = self.L_.thcmb_nccl_init(self.ctx, _np_ptr(idbuf))
         if rc != 0:
             raise RuntimeError("thcmb_nccl_init failed: " + self.L_.thcmb_last_error().decode())
+        # fused reduction + all-reduce over NVLink peer memory (CUDA IPC mailboxes); THCM_P2P=0 keeps plain NCCL
+        self.p2p = False
+        if os.environ.get("THCM_P2P", "1") != "0":
+            h = np.zeros(64, dtype=np.uint8)
+            ok = self.L_.thcmb_p2p_local_handle(self.ctx, _np_ptr(h)) == 0
+            allh = [None] * self.settings.nranks
+            dist.all_gather_object(allh, (ok, h.tobytes()), group=comm)
+            if all(o for o, _ in allh):
+                buf = np.frombuffer(b"".join(b for _, b in allh), dtype=np.uint8).copy()
+                ok = self.L_.thcmb_p2p_open(self.ctx, _np_ptr(buf)) == 0
+            flags = [None] * self.settings.nranks
+            dist.all_gather_object(flags, bool(ok), group=comm)
+            if not all(flags):
+                raise RuntimeError("P2P mailbox setup failed on some rank (set THCM_P2P=0 to use NCCL all-reduce): "
+                                   + self.L_.thcmb_last_error().decode())
+            self.p2p = True
 
     def close(self):
         if getattr(self, "ctx", None):

@@ -131,6 +131,11 @@ void thcmb_get_cob(thcmb_ctx* c, double* cob_host);
  * broadcasts it (torch.distributed) and every rank calls thcmb_nccl_init. */
 int thcmb_nccl_unique_id(void* id128);
 int thcmb_nccl_init(thcmb_ctx* c, const void* id128);
+/* Optional (same node, NVLink): fused reduction + all-reduce over peer memory.  Every rank exports the CUDA IPC handle
+ * (64 bytes) of its mailbox, the caller all-gathers them (nranks x 64 bytes, rank order) and hands them back; from then
+ * on dot products / MGS steps finish their cross-GPU sum inside the reduction kernel instead of calling ncclAllReduce. */
+int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64);
+int thcmb_p2p_open(thcmb_ctx* c, const void* handles_all);
 
 /* ---- hot path, device pointers, asynchronous on the context's stream ---- */
 /* halo exchange of a state/Krylov vector (width 1, edges+corners, periodic wrap): fills the context's halo buffer */
