@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
     ap.add_argument("--gmres-iters", type=int, default=50)
     ap.add_argument("--precon", type=int, default=1)
+    ap.add_argument("--ortho", default="dgks", choices=["mgs", "dgks"],
+                    help="GMRES orthogonalisation: mgs = src/gmressolver template, dgks = batched Gram-Schmidt as Belos uses in Ocean::solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -227,6 +229,9 @@ def main():
     t = iemic_b200.THCM(s, landm, comm)
     for k, v in PARS.items():
         t.setParameter(k, v)
+    t.set_ortho(a.ortho)
+    config["gmres_orthogonalisation"] = ("batched Gram-Schmidt + DGKS criterion (Belos 'DGKS', Ocean.C:977-1024)" if a.ortho == "dgks"
+                                         else "modified Gram-Schmidt (GMRESSolver.H:177-181)")
     xg = cases.consistent_state(s, landm, scale=0.05)
     x_local = xg[t.local_gids()]
     xd = torch.from_numpy(x_local).cuda()
@@ -304,7 +309,9 @@ def main():
         "spmv_csr": nnz_loc * 12 + ndim_loc * 20,
         "thcm_assemble<JAC_GRAPH>": ncell_loc * 49 + 8 * nnz_loc,
         "thcm_assemble<RHS>": ncell_loc * 145,
-        "mgs_step": 32 * ndim_loc, "dot": 16 * ndim_loc, "axpby": 24 * ndim_loc, "axpy_negdev": 24 * ndim_loc,
+        "mgs_step": 32 * ndim_loc, "dot": 16 * ndim_loc,
+        # batched Gram-Schmidt: a pass over nv basis vectors + w; nv averages (iters+1)/2 over a cycle
+        "multi_dot": int(8 * ndim_loc * ((iters + 1) / 2 * (1 + 1 / 8) + 0)), "multi_axpy": int(8 * ndim_loc * ((iters + 1) / 2 + 2)), "axpby": 24 * ndim_loc, "axpy_negdev": 24 * ndim_loc,
         "scale_invsqrt": 16 * ndim_loc, "copy": 16 * ndim_loc, "fill": 8 * ndim_loc,
         "blockdiag_apply": (36 + 12) * 8 * ncell_loc, "blockdiag_build": ncell_loc * 36 * 8 + 12 * nnz_loc,
     }

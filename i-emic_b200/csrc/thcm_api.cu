@@ -183,6 +183,7 @@ int thcmb_nccl_unique_id(void* id128) { return nccl_unique_id(id128); }
 int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128); }
 int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64) { return p2p_local_handle(c, handle64); }
 int thcmb_p2p_open(thcmb_ctx* c, const void* handles_all) { return p2p_open(c, handles_all); }
+void thcmb_set_ortho(thcmb_ctx* c, int mode) { c->gmres_ortho = mode; }
 
 int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x) { return halo_exchange(c, d_x); }
 
@@ -319,8 +320,10 @@ static void app_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESS
 int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags, double* hist,
                 int hist_cap, thcmb_krylov_result* res) {
     const int n = c->blk.ndim();
-    const bool prec = flags & 1, flexible = flags & 4;
+    const bool prec = flags & 1, flexible = flags & 4, batched = flags & 8;
     const int m = restart;
+    long long n_reorth = 0;
+    if (batched && m > 63) fatal("batched (DGKS) orthogonalisation supports GMRES restart <= 63");
     if (m + 2 > 4000) fatal("GMRES restart too large for the device scalar buffer");
     auto applyA = [&](const double* v, double* out) { thcmb_spmv_dev(c, v, out); };
     auto applyM = [&](const double* v, double* out) { thcmb_apply_precon_dev(c, v, out); };
@@ -359,19 +362,46 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     applyA(z, w);
                 } else applyA(V(i), w);
                 n_matvec++;
-                // MGS (GMRESSolver.H:177-181): H[k][i] = w.V[k]; w -= H[k][i] V[k]
-                double* dh = c->d_scalars;  // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
-                l2_persist(c, w, (size_t)n * sizeof(double));   // w is re-read and re-written by every kernel of the chain
-                dot_dev(c, n, w, V(0), dh + 0);
-                for (int k = 0; k < i; k++) mgs_step_dev(c, n, dh + k, V(k), V(k + 1), w, dh + k + 1);
-                axpy_negdev(c, n, dh + i, V(i), w);
-                dot_dev(c, n, w, w, dh + i + 1);
-                scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
-                l2_persist(c, nullptr, 0);
-                THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
-                THCM_CUDA(cudaStreamSynchronize(c->stream));
-                for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];
-                H[i + 1][i] = c->h_scalars[i + 2];
+                double* dh = c->d_scalars;
+                if (!batched) {
+                    // MGS (GMRESSolver.H:177-181): H[k][i] = w.V[k]; w -= H[k][i] V[k]
+                    // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
+                    l2_persist(c, w, (size_t)n * sizeof(double));   // w is re-read and re-written by every kernel of the chain
+                    dot_dev(c, n, w, V(0), dh + 0);
+                    for (int k = 0; k < i; k++) mgs_step_dev(c, n, dh + k, V(k), V(k + 1), w, dh + k + 1);
+                    axpy_negdev(c, n, dh + i, V(i), w);
+                    dot_dev(c, n, w, w, dh + i + 1);
+                    scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
+                    l2_persist(c, nullptr, 0);
+                    THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaStreamSynchronize(c->stream));
+                    for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];
+                    H[i + 1][i] = c->h_scalars[i + 2];
+                } else {
+                    // batched Gram-Schmidt with the DGKS re-orthogonalisation criterion (Belos "DGKS", Ocean.C:977-1024):
+                    // pass 1: h1 = V^T w (+ w.w) in one reduction, w -= V h1; a second pass only if ||w|| dropped below
+                    // ||w_old||/sqrt(2) -- decided on the device, identically on every rank.
+                    const int nv = i + 1, S = 80;   // dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] final ||w||^2, [3S+1] ||w||
+                    std::vector<double*> vp(nv);
+                    for (int k = 0; k < nv; k++) vp[k] = V(k);
+                    if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
+                    THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));
+                    multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
+                    multi_axpy_dev(c, n, nv, vp.data(), dh, nullptr, w);
+                    dot_dev(c, n, w, w, dh + S);
+                    dgks_flag_dev(c, dh + nv, dh + S, c->d_flags);
+                    multi_dot_dev(c, n, nv, vp.data(), w, c->d_flags, dh + 2 * S);
+                    multi_axpy_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w);
+                    dot_dev(c, n, w, w, dh + 3 * S);
+                    scale_invsqrt_dev(c, n, dh + 3 * S, w, dh + 3 * S + 1);
+                    THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (3 * S + 2), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaMemcpyAsync(c->h_scalars + 3 * S + 2, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaStreamSynchronize(c->stream));
+                    const bool second = *reinterpret_cast<int*>(c->h_scalars + 3 * S + 2) != 0;
+                    for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k] + (second ? c->h_scalars[2 * S + k] : 0.0);
+                    H[i + 1][i] = c->h_scalars[3 * S + 1];
+                    if (second) n_reorth++;
+                }
                 space = i;
                 for (int k = 0; k < i; k++) app_rot(H[k][i], H[k + 1][i], cs[k], sn[k]);
                 gen_rot(H[i][i], H[i + 1][i], cs[i], sn[i]);
@@ -515,7 +545,7 @@ int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double
     double fn = thcmb_nrm2(c, n, d_F);
     if (fnorm) *fnorm = fn;
     fill(c, n, 0.0, d_dx);
-    return thcmb_gmres(c, d_F, d_dx, tol, maxit, restart, 1 | 4, nullptr, 0, res);   // precon 0 = identity
+    return thcmb_gmres(c, d_F, d_dx, tol, maxit, restart, 1 | 4 | (c->gmres_ortho ? 8 : 0), nullptr, 0, res);   // precon 0 = identity
 }
 
 // One Newton step from HOST buffers: the end-to-end call (bench.py "e2e"): H2D state, step, D2H update.
@@ -538,7 +568,7 @@ void thcmb_profile(thcmb_ctx* c, int on) {
 }
 static const char* kKernelNames[KID_COUNT] = {"thcm_assemble<RHS>", "thcm_assemble<JAC_GRAPH>", "thcm_assemble<JAC_COUNT>",
     "thcm_assemble<JAC_CRS>", "scan_counts", "spmv_csr", "dot", "mgs_step", "axpby", "axpy_negdev", "scale_invsqrt", "copy", "fill",
-    "blockdiag_build", "blockdiag_apply", "halo_pack", "halo_unpack"};
+    "blockdiag_build", "blockdiag_apply", "halo_pack", "halo_unpack", "multi_dot", "multi_axpy"};
 int thcmb_kernel_count(void) { return KID_COUNT; }
 const char* thcmb_kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? kKernelNames[kid] : ""; }
 int thcmb_profile_report(thcmb_ctx* c, int kid, int* count, double* total_ms) {

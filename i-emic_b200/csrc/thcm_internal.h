@@ -128,7 +128,9 @@ struct thcmb_ctx {
     void* d_mailbox = nullptr;
     void* d_peer_mailboxes = nullptr;
     std::vector<void*> p2p_peer_ptrs;
-    unsigned long long p2p_seq = 0;
+    unsigned long long p2p_seq = 0, p2p_vseq = 0;
+    double* d_mdpartial = nullptr;   // multi_dot partials
+    int* d_flags = nullptr;          // device flags (DGKS second-pass decision)
     // ---- workspaces ----
     double* d_un = nullptr;         // staging for host-pointer entry points
     double* d_tmp = nullptr;
@@ -151,6 +153,7 @@ struct thcmb_ctx {
     // borrowed host CRS pointers (m_mat::set_pointers)
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
     int vmix_fix = 1;
+    int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 
 namespace thcm {
@@ -178,6 +181,9 @@ int halo_exchange(thcmb_ctx* c, const double* d_x);
 // vector kernels (device-scalar flavours keep the Krylov inner loops free of host syncs)
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out);
 int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
+int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out);
+int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w);
+int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out);
 int nccl_unique_id(void* id128);
 int nccl_init(thcmb_ctx* c, const void* id128);
@@ -201,7 +207,7 @@ double* pool_vec(thcmb_ctx* c, size_t idx);
 namespace thcm {
 enum KernelId { KID_ASM_RHS = 0, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS, KID_SCAN, KID_SPMV, KID_DOT, KID_MGS, KID_AXPBY,
                 KID_AXPY_DEV, KID_SCALE, KID_COPY, KID_FILL, KID_PRECON_BUILD, KID_PRECON_APPLY, KID_HALO_PACK, KID_HALO_UNPACK,
-                KID_COUNT };
+                KID_MULTIDOT, KID_MULTIAXPY, KID_COUNT };
 struct ProfScope {   // records an event pair around one kernel launch when profiling is on
     thcmb_ctx* c; bool on;
     ProfScope(thcmb_ctx* c_, int kid) : c(c_), on(c_->prof_on && c_->prof_kid.size() < 60000) {

@@ -119,6 +119,7 @@ struct P2PArgs {
     unsigned long long seq;   // > 0
 };
 constexpr int P2P_MAX_RANKS = 16;
+constexpr size_t P2P_MAILBOX_BYTES = 1024 + (size_t)(64 + 8 + 2) * 8 * 2 * P2P_MAX_RANKS;   // scalar slots + vector slots (multi_dot)
 
 __device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     __shared__ bool last;
@@ -261,8 +262,8 @@ int p2p_local_handle(thcmb_ctx* c, void* handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (c->blk.nranks > P2P_MAX_RANKS) return -1;
     if (!c->d_mailbox) {
-        THCM_CUDA(cudaMalloc(&c->d_mailbox, sizeof(P2PSlot) * 2 * P2P_MAX_RANKS));
-        THCM_CUDA(cudaMemset(c->d_mailbox, 0, sizeof(P2PSlot) * 2 * P2P_MAX_RANKS));
+        THCM_CUDA(cudaMalloc(&c->d_mailbox, P2P_MAILBOX_BYTES));
+        THCM_CUDA(cudaMemset(c->d_mailbox, 0, P2P_MAILBOX_BYTES));
         THCM_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -327,6 +328,156 @@ int copy(thcmb_ctx* c, int n, const double* x, double* y) {
 int fill(thcmb_ctx* c, int n, double a, double* x) {
     ProfScope prof_(c, KID_FILL);
     fill_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x); c->launches++; return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Batched (classical) Gram-Schmidt pass, the orthogonalisation Belos uses on the reference's production path
+// (Ocean.C:977-1024: "Orthogonalization" = "DGKS"): ALL projections h = V^T w of an iteration in ONE reduction kernel
+// (+ w.w), then ONE update kernel w -= V h.  Per iteration this is 2-4 dependent global reductions instead of the i+2
+// of modified Gram-Schmidt -- the latency that decides multi-GPU efficiency (hard part 5).
+// The cross-GPU sum of the nv+1 partial results is fused into the reduction kernel (peer mailboxes, as above).
+// ---------------------------------------------------------------------------
+constexpr int MD_MAXV = 64;            // projections per kernel (GMRES restart <= 63 in this mode)
+constexpr int MD_CHUNK = 8;
+constexpr int MD_BLOCKS = NSM * 4;
+struct VecList { const double* v[MD_MAXV]; int nv; };
+struct P2PVecSlot { double val[MD_MAXV + 8]; unsigned long long seq; unsigned long long pad; };
+constexpr size_t P2P_VEC_OFFSET = 1024;   // byte offset of the vector slots inside the mailbox allocation
+static_assert(P2P_MAILBOX_BYTES == P2P_VEC_OFFSET + sizeof(P2PVecSlot) * 2 * P2P_MAX_RANKS, "mailbox layout");
+
+__global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList vl, const double* __restrict__ w, const int* __restrict__ skip,
+                                                                 double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
+    __shared__ double red[RED_THREADS / 32][MD_CHUNK + 1];
+    __shared__ bool last;
+    const int nv = vl.nv, stride = MD_MAXV + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool skipped = skip != nullptr && *skip == 0;     // conditional second pass (DGKS criterion), uniform over the grid
+    if (!skipped) {
+        for (int c0 = 0; c0 < nv; c0 += MD_CHUNK) {
+            const int nc = min(MD_CHUNK, nv - c0);
+            double acc[MD_CHUNK + 1];
+#pragma unroll
+            for (int q = 0; q <= MD_CHUNK; q++) acc[q] = 0.0;
+            for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
+                const double wi = w[i];
+#pragma unroll
+                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) acc[q] += wi * vl.v[c0 + q][i];
+                if (c0 == 0) acc[MD_CHUNK] += wi * wi;
+            }
+#pragma unroll
+            for (int q = 0; q <= MD_CHUNK; q++) {
+                double v = acc[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) red[warp][q] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x <= MD_CHUNK) {
+                double v = 0.0;
+                for (int ww = 0; ww < RED_THREADS / 32; ww++) v += red[ww][threadIdx.x];
+                if (threadIdx.x < nc) partial[(size_t)blockIdx.x * stride + c0 + threadIdx.x] = v;
+                if (threadIdx.x == MD_CHUNK && c0 == 0) partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    // ---- last block: fixed-order sum of the per-block partials, then the cross-GPU exchange ----
+    __shared__ double mine[MD_MAXV + 1];
+    for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
+        const int col = q < nv ? q : MD_MAXV;
+        double v = 0.0;
+        if (!skipped) for (int b = 0; b < (int)gridDim.x; b++) v += ((volatile double*)partial)[(size_t)b * stride + col];
+        mine[q] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+    __syncthreads();
+    if (pa.nranks > 1) {
+        const int par = (int)(pa.seq & 1ull);
+        P2PVecSlot* my_slots = (P2PVecSlot*)((char*)pa.mine + P2P_VEC_OFFSET);
+        if (threadIdx.x < pa.nranks && threadIdx.x != pa.rank) {
+            const int r = threadIdx.x;
+            volatile P2PVecSlot* dst = (P2PVecSlot*)((char*)pa.peers[r] + P2P_VEC_OFFSET) + par * P2P_MAX_RANKS + pa.rank;
+            for (int q = 0; q <= nv; q++) dst->val[q] = mine[q];
+            __threadfence_system();
+            dst->seq = pa.seq;
+            volatile P2PVecSlot* src = my_slots + par * P2P_MAX_RANKS + r;
+            while (src->seq != pa.seq) { }
+            __threadfence_system();
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
+            double tot = 0.0;
+            for (int r = 0; r < pa.nranks; r++)
+                tot += (r == pa.rank) ? mine[q] : ((volatile P2PVecSlot*)(my_slots + par * P2P_MAX_RANKS + r))->val[q];
+            out[q] = tot;      // out[0..nv-1] = V^T w, out[nv] = w.w
+        }
+    } else {
+        for (int q = threadIdx.x; q <= nv; q += RED_THREADS) out[q] = mine[q];
+    }
+}
+
+// w -= sum_q h[q] v_q  (applied in q order);  skipped when *skip == 0
+__global__ void __launch_bounds__(256) multi_axpy_kernel(int n, VecList vl, const double* __restrict__ h, const int* __restrict__ skip,
+                                                          double* __restrict__ w) {
+    __shared__ double hs[MD_MAXV];
+    if (skip != nullptr && *skip == 0) return;
+    for (int q = threadIdx.x; q < vl.nv; q += blockDim.x) hs[q] = h[q];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double wi = w[i];
+        for (int c0 = 0; c0 < vl.nv; c0 += MD_CHUNK) {
+            double vv[MD_CHUNK];
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) vv[q] = (c0 + q < vl.nv) ? vl.v[c0 + q][i] : 0.0;
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) if (c0 + q < vl.nv) wi = wi - hs[c0 + q] * vv[q];
+        }
+        w[i] = wi;
+    }
+}
+
+// DGKS criterion on the device: need2 = (ww_new < 0.5 * ww_old)  (Belos DGKS dep_tol = 1/sqrt(2) on the norms)
+__global__ void dgks_flag_kernel(const double* ww_old, const double* ww_new, int* flag) { *flag = (*ww_new < 0.5 * (*ww_old)) ? 1 : 0; }
+
+static P2PArgs p2p_vec_args(thcmb_ctx* c) {
+    P2PArgs pa{1, 0, nullptr, nullptr, 0ull};
+    if (c->p2p_on) {
+        pa.nranks = c->blk.nranks; pa.rank = c->blk.rank;
+        pa.mine = (P2PSlot*)c->d_mailbox; pa.peers = (P2PSlot* const*)c->d_peer_mailboxes;
+        pa.seq = ++c->p2p_vseq;
+    }
+    return pa;
+}
+
+int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out) {
+    if (nv > MD_MAXV) fatal("multi_dot: too many vectors (GMRES restart must be <= 63 with batched orthogonalisation)");
+    VecList vl; vl.nv = nv;
+    for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
+    if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
+    { ProfScope prof_(c, KID_MULTIDOT);
+      multi_dot_kernel<<<MD_BLOCKS, RED_THREADS, 0, c->stream>>>(n, vl, w, d_skip, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c)); }
+    c->launches++;
+    return c->p2p_on ? 0 : allreduce_dev(c, d_out, nv + 1);
+}
+int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w) {
+    VecList vl; vl.nv = nv;
+    for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
+    ProfScope prof_(c, KID_MULTIAXPY);
+    multi_axpy_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, vl, d_h, d_skip, w);
+    c->launches++;
+    return 0;
+}
+int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag) {
+    dgks_flag_kernel<<<1, 1, 0, c->stream>>>(ww_old, ww_new, d_flag);
+    c->launches++;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------

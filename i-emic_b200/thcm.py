@@ -91,7 +91,7 @@ def load_library(path=None):
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
-        "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]),
+        "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]), "thcmb_set_ortho": (None, [vp, i]),
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
@@ -316,12 +316,12 @@ class THCM:
         self.L_.thcmb_apply_precon_dev(self.ctx, _dev_ptr(v), _dev_ptr(out))
         self.sync()
 
-    def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096):
+    def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096, ortho="mgs"):
         """GMRESSolver::solve (src/gmressolver/GMRESSolver.H:81-255).  Returns (KrylovResult, history)."""
         self._pre()
         hist = np.zeros(hist_cap)
         res = KrylovResult()
-        flags = (1 if prec else 0) | (4 if flexible else 0)
+        flags = (1 if prec else 0) | (4 if flexible else 0) | (8 if ortho == "dgks" else 0)
         self.L_.thcmb_gmres(self.ctx, _dev_ptr(b), _dev_ptr(x), tol, maxit, restart, flags, _np_ptr(hist), hist_cap, C.byref(res))
         return res, hist[:res.nhist].copy()
 
@@ -341,6 +341,10 @@ class THCM:
         dp = dx_host.data_ptr() if hasattr(dx_host, "data_ptr") else dx_host.ctypes.data
         self.L_.thcmb_newton_step(self.ctx, C.c_void_p(up), C.c_void_p(dp), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
         return res, fn.value
+
+    def set_ortho(self, mode):
+        """Orthogonalisation of the Newton-step GMRES: 'mgs' (GMRESSolver.H) or 'dgks' (batched, Belos-style)."""
+        self.L_.thcmb_set_ortho(self.ctx, 1 if mode == "dgks" else 0)
 
     def newton_step_dev(self, un, dx, tol=1e-4, maxit=500, restart=400, precon=1):
         """Newton step with the state already in HBM (CUDA tensors)."""

@@ -178,7 +178,9 @@ typedef struct thcmb_krylov_result {
 
 /* Restarted right-preconditioned (F)GMRES with modified Gram-Schmidt and Givens rotations: the algorithm of
  * src/gmressolver/GMRESSolver.H:81-255 (minimiser scheme 'B').  d_b, d_x on device; hist (host, may be NULL)
- * receives the scaled residual after every inner iteration.  flags: bit0 precondition, bit2 flexible. */
+ * receives the scaled residual after every inner iteration.  flags: bit0 precondition, bit2 flexible,
+ * bit3 batched Gram-Schmidt with the DGKS criterion (the orthogonalisation Belos uses on the reference's production path,
+ * Ocean.C:977-1024) instead of the template's modified Gram-Schmidt: 2-4 global reductions per iteration instead of i+2. */
 int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags,
                 double* hist, int hist_cap, thcmb_krylov_result* res);
 /* IDR(s) with bi-orthogonalisation: src/idrsolver/IDRSolver.H:109-340.  d_P_raw: s vectors (s x ndim) that
@@ -191,6 +193,8 @@ int thcmb_idrs(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int max
 int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart,
                       int precon_kind, double* fnorm, thcmb_krylov_result* res);
 
+/* orthogonalisation used by thcmb_newton_step*: 0 = modified Gram-Schmidt (GMRESSolver.H:177-181), 1 = batched DGKS */
+void thcmb_set_ortho(thcmb_ctx* c, int mode);
 /* the same step with the state already in HBM (bench.py "value") */
 int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart,
                           int precon_kind, double* fnorm, thcmb_krylov_result* res);

@@ -288,3 +288,28 @@ def test_missing_extension_fails_loudly(gpu, tmp_path):
             th.load_library(str(tmp_path / "nope.so"))
     finally:
         th._lib = saved
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16"])
+def test_gmres_dgks_mode_matches_mgs_history(gpu, name):
+    """The batched Gram-Schmidt / DGKS mode (Belos-style, fewer global reductions) against the template's MGS on the GPU
+    and against the reference template itself: same residual history to 1e-10, same iteration count +-1."""
+    from oracle.oracle import kref_gmres
+    s, landm, o, t = setup(gpu, name)
+    x = cases.consistent_state(s, landm, scale=0.1)
+    F = t.new_vector()
+    t.evaluate(dev(x), F, True)
+    rp, col = o.graph()
+    val, _ = o.jacobian_graph(x)
+    b = o.rhs(x)
+    t.buildPreconditioner(0)
+    tol, maxit, restart = 1e-8, 60, 30
+    kr = kref_gmres(rp, col, val, b, np.zeros(t.ndim), tol=tol, maxit=maxit, restart=restart, prec_kind=0)
+    s1, s2 = t.new_vector(), t.new_vector()
+    r1, h1 = t.gmres(dev(b), s1, tol=tol, maxit=maxit, restart=restart, ortho="mgs")
+    r2, h2 = t.gmres(dev(b), s2, tol=tol, maxit=maxit, restart=restart, ortho="dgks")
+    k = min(len(h1), len(h2), len(kr["hist"]) - 1, 25)
+    assert abs(r1.iters - r2.iters) <= 1 and abs(r2.iters - kr["iters"]) <= 1
+    assert np.abs(h1[:k] - h2[:k]).max() <= 1e-10
+    assert np.abs(h2[:k] - kr["hist"][1:k + 1]).max() <= 1e-10
+    t.close()
