@@ -358,10 +358,21 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
             double acc[MD_CHUNK + 1];
 #pragma unroll
             for (int q = 0; q <= MD_CHUNK; q++) acc[q] = 0.0;
-            for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
-                const double wi = w[i];
+            // 128-bit loads (all Krylov vectors come from cudaMalloc: 256-byte aligned; n is even: 6 unknowns per cell)
+            const int n2 = n >> 1;
+            const double2* w2 = reinterpret_cast<const double2*>(w);
+            for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n2; i += gridDim.x * RED_THREADS) {
+                const double2 wi = w2[i];
+                double2 vv[MD_CHUNK];
 #pragma unroll
-                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) acc[q] += wi * vl.v[c0 + q][i];
+                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) vv[q] = reinterpret_cast<const double2*>(vl.v[c0 + q])[i];
+#pragma unroll
+                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) { acc[q] += wi.x * vv[q].x; acc[q] += wi.y * vv[q].y; }
+                if (c0 == 0) { acc[MD_CHUNK] += wi.x * wi.x; acc[MD_CHUNK] += wi.y * wi.y; }
+            }
+            if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+                const double wi = w[n - 1];
+                for (int q = 0; q < nc; q++) acc[q] += wi * vl.v[c0 + q][n - 1];
                 if (c0 == 0) acc[MD_CHUNK] += wi * wi;
             }
 #pragma unroll
