@@ -47,6 +47,8 @@ void upload_params(thcmb_ctx* c) {
     upload(c->d_jt, c->jt_host);
     upload(c->d_kt, c->kt_host);
     upload(c->d_frc, c->frc_local);
+    upload(c->d_jrec, c->jrec_host);
+    upload(c->d_krec, c->krec_host);
 }
 
 void refresh_params(thcmb_ctx* c) {  // forcing + lin (usrc.F90:178-179)
@@ -61,6 +63,9 @@ void build_static(thcmb_ctx* c) {
     std::vector<uint32_t> nbmask; std::vector<uint8_t> surf, uvlive; std::vector<int> send_idx, recv_slot;
     build_static_host(c, nbmask, surf, uvlive, send_idx, recv_slot);
     upload(c->d_nbmask, nbmask); upload(c->d_surf, surf); upload(c->d_uvlive, uvlive);
+    std::vector<TileDesc> tdesc;
+    build_tile_descs(c, nbmask, surf, uvlive, tdesc);
+    upload(c->d_tdesc, tdesc);
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
     if (c->d_val) cudaFree(c->d_val);
@@ -123,6 +128,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     stpnt(c);
     apply_landmask_rules(c, landm_global, false);
     c->n_asm_blocks = asm_block_count(c->blk);
+    if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
     THCM_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 4096));
@@ -146,7 +152,8 @@ void thcmb_destroy(thcmb_ctx* c) {
     for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
                     (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)c->d_halo, (void*)c->d_sendbuf, (void*)c->d_recvbuf,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
-                    (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv})
+                    (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
+                    (void*)c->d_krec})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);

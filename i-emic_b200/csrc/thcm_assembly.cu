@@ -25,6 +25,8 @@
 //    cp.async.bulk.global.shared::cta of 832 B per cell (SASS UBLKCP) -- clipped edge tiles use a plain coalesced loop.
 // HBM traffic per cell: 48 B state + 5 B masks in, 832 B values out.
 // =============================================================================
+#include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include "thcm_cell.cuh"
 
@@ -63,18 +65,7 @@ template <int NSV> struct SmemTabs {
     __device__ __forceinline__ double kt(int tb) const { return in->tk[tb]; }
 };
 
-struct TileGeom { int cell0, ncell, gi0, gj, k, lj; };   // first owned cell, count, global (1-based) origin
-
-__device__ __forceinline__ TileGeom tile_geom(const DevBlock& b) {
-    const int nbx = (b.n0 + TI - 1) / TI;
-    int ib = blockIdx.x % nbx, rest = blockIdx.x / nbx;
-    int lj = rest % b.m0, k0 = rest / b.m0;
-    TileGeom g;
-    g.cell0 = (k0 * b.m0 + lj) * b.n0 + ib * TI;
-    g.ncell = min(TI, b.n0 - ib * TI);
-    g.gi0 = b.i0 + ib * TI + 1; g.gj = b.j0 + lj + 1; g.k = k0 + 1; g.lj = lj;
-    return g;
-}
+__device__ __forceinline__ TileGeom tile_geom(const DevBlock& b) { return tile_geom_of(b, blockIdx.x); }
 
 template <int NSV, int NT>
 __device__ __forceinline__ void stage_inputs(const AsmArgs& a, const TileGeom& g, SmemIn<NSV>& in) {
@@ -303,6 +294,431 @@ __global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(co
     }
 }
 
+
+// =============================================================================
+// Persistent, TMA-pipelined Jacobian kernel (MODE_JAC_GRAPH).
+//
+// One CTA = 5 consumer warps (row types u | v | w+p | T | S for the 32 cells of a tile) + a loader warp + a storer
+// warp, looping over tiles; no __syncthreads in the steady state, all hand-offs go through mbarriers:
+//   loader  : per tile, cp.async.bulk (TMA) of the 9 grid lines of raw 48-byte state records (1 run per line, 2-3 at
+//             the periodic seam / block edges), the tile descriptor (neighbour masks, usol liveness bits) and the j / k
+//             table records into stage s; waits for the bytes (mbarrier complete_tx), applies usol's no-slip / lid
+//             zeroing in place from the descriptor bits, then signals `ready[s]`.  Runs one tile ahead of the consumers.
+//   consumer: waits `ready[s]`, evaluates its row(s) from shared memory into registers, releases the stage (`empty[s]`),
+//             applies `boundaries` + the drop threshold, waits until the previous tile's values have left the output
+//             staging (`outempty`), writes its entries at their final graph offsets, signals `outfull`.
+//   storer  : waits `outfull`, sends the tile out with one 832-byte TMA bulk store per cell, signals `outempty` when
+//             the TMA unit has read the staging.
+// Clipped tiles (k = 1 / k = L planes, non-periodic edges) leave through a coalesced generic copy by the consumers.
+// =============================================================================
+constexpr int PIPE_NSTAGE = 2;
+constexpr int PIPE_CONS = 5;
+constexpr int PIPE_THREADS = 32 * (PIPE_CONS + 2);
+
+struct alignas(16) PipeStage {
+    double rec[9][TW][NUN];        // raw records, line r = (dk+1)*3 + (dj+1); u,v,w zeroed in place where usol does
+    TileDesc desc;
+    double tj[J_COUNT][JREC];
+    double tk[K_COUNT];
+};
+static_assert(sizeof(PipeStage) % 16 == 0 && offsetof(PipeStage, desc) % 16 == 0 && offsetof(PipeStage, tj) % 16 == 0 &&
+              offsetof(PipeStage, tk) % 16 == 0, "bulk-copy destinations must be 16-byte aligned");
+struct alignas(16) PipeSmem {
+    PipeStage st[PIPE_NSTAGE];
+    double v[TI * VSTRIDE];
+    int cstart[TI + 2];
+    int outinfo[4];                // g0, ncell, fast
+    unsigned long long bar_raw[PIPE_NSTAGE], bar_ready[PIPE_NSTAGE], bar_empty[PIPE_NSTAGE], bar_outfull, bar_outempty;
+#ifdef THCM_PIPE_DEBUG
+    volatile int prog[8][32];
+#endif
+};
+#ifdef THCM_PIPE_DEBUG
+#define PROG(pt) sh.prog[threadIdx.x >> 5][lane] = (pt);
+#else
+#define PROG(pt)
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity, int tag = 0) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > (tag == 4 ? 1000000000ll : (tag == 1 || tag == 3) ? 2000000000ll : 4000000000ll)) {           // a lost hand-off must fail loudly, never hang the GPU
+            if ((threadIdx.x & 31) == 0) printf("thcm_jac_pipe: block %d warp %d stuck at wait %d (parity %u)\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct PipeTile {
+    const PipeStage* st; int lane;
+    __device__ __forceinline__ double operator()(int sv, int di, int dj, int dk) const {
+        return st->rec[(dk + 1) * 3 + (dj + 1)][lane + 1 + di][sv <= SV_W ? sv : sv + 1];   // u v w . T S
+    }
+};
+struct PipeTabs {
+    const PipeStage* st;
+    __device__ __forceinline__ double jt(int tb, int dj) const { return st->tj[tb][dj + 1]; }
+    __device__ __forceinline__ double kt(int tb) const { return st->tk[tb]; }
+};
+
+template <int R>
+__device__ __forceinline__ void pipe_eval(const AsmArgs& a, const PipeStage& st, const TileGeom& g, int lane, uint32_t nb, double sm,
+                                          double* E) {
+    if (lane < g.ncell && !((nb >> 4) & 1u)) {
+        Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
+        eval_row<R, true>(E, a.t, a.b, c, sm, PipeTile{&st, lane}, PipeTabs{&st});
+    }
+}
+// open_ocean / interior are TILE-uniform (descriptor flag, tile geometry): no warp votes, inactive lanes of a ragged tile
+// just skip the bodies
+template <int R>
+__device__ __forceinline__ void pipe_finish(const AsmArgs& a, const TileGeom& g, int lane, uint32_t nb, bool open_ocean, double* E) {
+    if (lane < g.ncell) {
+        if (!open_ocean) boundaries<R>(E, nb, g.gi0 + lane < a.b.N, g.gj < a.b.M);
+#pragma unroll
+        for (int q = 0; q < RowSlots<R>::N; q++) E[q] = fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
+    }
+}
+template <int R>
+__device__ __forceinline__ void pipe_emit(const AsmArgs& a, double* v, const TileGeom& g, int lane, bool interior, const double* E) {
+    if (lane < g.ncell) {
+        if (interior) {
+            double* dst = v + lane * VSTRIDE + ROW_OFF[R - 1];
+            static_for<0, RowSlots<R>::N>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                dst[interior_pos(R, q)] = E[q];
+            });
+        } else {
+            const int gi = g.gi0 + lane;
+            const int cls = (gi == 1 ? 1 : 0) | (gi == a.b.N ? 2 : 0) | (g.gj == 1 ? 4 : 0) | (g.gj == a.b.M ? 8 : 0) | (g.k == 1 ? 16 : 0) |
+                            (g.k == a.b.L ? 32 : 0);
+            int rowoff = 0;
+#pragma unroll
+            for (int r = 0; r < R - 1; r++) rowoff += c_cls.rowlen[cls][r];
+            const int base = lane * VSTRIDE + rowoff;
+            static_for<0, RowSlots<R>::N>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                int p = c_cls.pos[cls][ROW_OFF[R - 1] + q];
+                if (p >= 0) v[base + p] = E[q];
+            });
+        }
+    }
+}
+
+template <int RA, int RB>
+__device__ __forceinline__ void pipe_consumer(const AsmArgs& a, PipeSmem& sh, int lane) {
+    constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
+        const int s = it % PIPE_NSTAGE;
+        const uint32_t n = it / PIPE_NSTAGE;
+        PipeStage& st = sh.st[s];
+        const TileGeom g = tile_geom_of(a.b, tile);
+        mbar_wait(&sh.bar_ready[s], n & 1, 1);
+        const uint32_t nb = st.desc.nbmask[lane];
+        const double sm = (double)((st.desc.surfbits >> lane) & 1u);
+        const bool fast = (st.desc.flags & 1u) != 0, open_ocean = (st.desc.flags & 2u) != 0;
+        // every cell of the tile away from the domain faces: graph positions are compile-time constants
+        const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
+        const int g0 = st.desc.g0, tot = st.desc.tot;
+        double EA[NA], EB[NB];
+        PROG(1)
+        pipe_eval<RA>(a, st, g, lane, nb, sm, EA);
+        if constexpr (RB != RA) pipe_eval<RB>(a, st, g, lane, nb, sm, EB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.bar_empty[s]);          // the stage may be refilled
+        PROG(2)
+        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+        if constexpr (RB != RA) pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+        PROG(3)
+        if (it >= 1) mbar_wait(&sh.bar_outempty, (it - 1) & 1, 2); // previous tile has left the output staging
+        pipe_emit<RA>(a, sh.v, g, lane, interior, EA);
+        PROG(4)
+        if constexpr (RB != RA) pipe_emit<RB>(a, sh.v, g, lane, interior, EB);
+        PROG(5)
+        if (fast) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // STS visible to the TMA unit
+        } else {
+            // clipped / unaligned tile: coalesced generic copy by the consumer warps
+            if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x)) - g0;
+            PROG(6)
+            __syncwarp();
+            PROG(7)
+            asm volatile("bar.sync 1, %0;\n" ::"n"(32 * PIPE_CONS) : "memory");
+            PROG(8)
+            double* gdst = a.val + g0;
+            for (int q = threadIdx.x; q < tot; q += 32 * PIPE_CONS) {
+                int cl = min(q / NSLOT_TOTAL, g.ncell - 1);
+                while (q < sh.cstart[cl]) cl--;
+                while (q >= sh.cstart[cl + 1]) cl++;
+                gdst[q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
+            }
+        }
+        PROG(fast ? 10 : 9)
+        if (RA == 1 && lane == 0) { sh.outinfo[0] = g0; sh.outinfo[1] = g.ncell; sh.outinfo[2] = fast ? 1 : 0; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.bar_outfull);
+    }
+}
+
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(PIPE_THREADS, CTAS_PER_SM) thcm_jac_pipe_kernel(const AsmArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PipeSmem& sh = *reinterpret_cast<PipeSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PIPE_NSTAGE; s++) { mbar_init(&sh.bar_raw[s], 1); mbar_init(&sh.bar_ready[s], 1); mbar_init(&sh.bar_empty[s], PIPE_CONS); }
+        mbar_init(&sh.bar_outfull, PIPE_CONS); mbar_init(&sh.bar_outempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == PIPE_CONS) {
+        // ---------------- loader ----------------
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
+            const int s = it % PIPE_NSTAGE;
+            const uint32_t n = it / PIPE_NSTAGE;
+            PipeStage& st = sh.st[s];
+            if (n >= 1) mbar_wait(&sh.bar_empty[s], (n - 1) & 1, 3);
+            const TileGeom g = tile_geom_of(a.b, tile);
+            const int w = g.ncell + 2;
+            if (lane == 0)
+                mbar_expect_tx(&sh.bar_raw[s], (uint32_t)(9 * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
+            __syncwarp();
+            if (lane < 9) {
+                LineSeg seg[3];
+                const int ns = line_plan(a.b, g, lane, seg);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                    if (q < ns)
+                        bulk_load(&st.rec[lane][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
+                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar_raw[s]);
+            } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar_raw[s]);
+            else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar_raw[s]);
+            else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar_raw[s]);
+            mbar_wait(&sh.bar_raw[s], n & 1, 4);
+            // usol in place: no-slip zeroing of u,v, lid / bottom / ghost-column rule of w (descriptor bits)
+            for (int p = lane; p < 9 * TW; p += 32) {
+                const int r = p / TW, x = p - r * TW;
+                if (x < w) {
+                    if (!((st.desc.uvbits[r] >> x) & 1ull)) *reinterpret_cast<double2*>(&st.rec[r][x][0]) = make_double2(0.0, 0.0);
+                    if (!((st.desc.wbits[r] >> x) & 1ull)) st.rec[r][x][2] = 0.0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.bar_ready[s]);
+        }
+    } else if (warp == PIPE_CONS + 1) {
+        // ---------------- storer ----------------
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
+#ifdef THCM_PIPE_DEBUG
+            {
+                uint32_t done = 0; const long long t0 = clock64();
+                while (!done) {
+                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                                 : "=r"(done) : "r"(smem_u32(&sh.bar_outfull)), "r"((uint32_t)(it & 1)) : "memory");
+                    if (!done && clock64() - t0 > 1000000000ll) {
+                        if (lane == 0) for (int w = 0; w < 5; w++) {
+                            int mn = 99, mx = -1, l0 = sh.prog[w][0];
+                            for (int l = 0; l < 32; l++) { int v = sh.prog[w][l]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+                            printf("blk %d it %d warp %d prog lane0 %d min %d max %d\n", blockIdx.x, it, w, l0, mn, mx);
+                        }
+                        __trap();
+                    }
+                }
+            }
+#else
+            mbar_wait(&sh.bar_outfull, it & 1, 5);
+#endif
+            const int g0 = sh.outinfo[0], ncell = sh.outinfo[1], fast = sh.outinfo[2];
+            if (fast && lane < ncell) {
+                bulk_store(a.val + g0 + (size_t)lane * NSLOT_TOTAL, sh.v + lane * VSTRIDE, NSLOT_TOTAL * (int)sizeof(double));
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.bar_outempty);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    } else {
+        switch (warp) {
+        case 0: pipe_consumer<1, 1>(a, sh, lane); break;
+        case 1: pipe_consumer<2, 2>(a, sh, lane); break;
+        case 2: pipe_consumer<3, 4>(a, sh, lane); break;
+        case 3: pipe_consumer<5, 5>(a, sh, lane); break;
+        default: pipe_consumer<6, 6>(a, sh, lane); break;
+        }
+    }
+}
+
+template <int CTAS_PER_SM> static void launch_jac_pipe_t(thcmb_ctx* c, const AsmArgs& a) {
+    static int grid_per_dev = 0;
+    if (!grid_per_dev) {
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_pipe_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
+        int nsm = 0, occ = 0;
+        THCM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+        THCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, thcm_jac_pipe_kernel<CTAS_PER_SM>, PIPE_THREADS, sizeof(PipeSmem)));
+        if (occ < 1) fatal("pipelined assembly kernel does not fit on this device");
+        grid_per_dev = nsm * std::min(occ, CTAS_PER_SM);
+    }
+    int grid = std::min(grid_per_dev, a.ntile);
+    thcm_jac_pipe_kernel<CTAS_PER_SM><<<grid, PIPE_THREADS, sizeof(PipeSmem), c->stream>>>(a);
+}
+static void launch_jac_pipe(thcmb_ctx* c, const AsmArgs& a) {
+    if (c->asm_pipe == 3) launch_jac_pipe_t<3>(c, a); else launch_jac_pipe_t<2>(c, a);
+}
+
+// =============================================================================
+// One-block-per-tile Jacobian kernel with TMA staging (MODE_JAC_GRAPH default).  Same three phases as
+// thcm_assemble_kernel, but
+//   * phase 1 is nine cp.async.bulk line copies (+ descriptor + table records) issued by one warp and awaited on an
+//     mbarrier by everybody, followed by the in-place usol fix-up from the descriptor bits: ~30 instead of ~240
+//     instructions per warp, no index arithmetic per position;
+//   * tile-uniform facts (open ocean, interior, all land) come from the host-built descriptor flags instead of warp votes;
+//   * tiles that are entirely LAND (identity rows: a state-independent pattern) skip staging and evaluation altogether.
+// The persistent variant above measured SLOWER on the B200 (instruction-fetch bound: five row types x 2-3 CTAs do not share
+// the 32 KB L1.5 instruction cache the way 4-5 co-scheduled blocks do, ncu stall_no_instruction 16 of 28 cycles per issue).
+// =============================================================================
+struct alignas(16) TmaSmem {
+    PipeStage st;
+    double v[TI * VSTRIDE];
+    int cstart[TI + 2];
+    unsigned long long bar;
+};
+
+__device__ __forceinline__ constexpr int diag_pos(int R) { return ROW_OFF[R - 1] + interior_pos(R, slot_of(R, 5, R)); }
+
+template <int RA, int RB>
+__device__ __forceinline__ void tma_rows(const AsmArgs& a, TmaSmem& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
+    constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
+    const uint32_t nb = sh.st.desc.nbmask[lane];
+    const double sm = (double)((sh.st.desc.surfbits >> lane) & 1u);
+    double EA[NA], EB[NB];
+    pipe_eval<RA>(a, sh.st, g, lane, nb, sm, EA);
+    pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+    pipe_emit<RA>(a, sh.v, g, lane, interior, EA);
+    if constexpr (RB != RA) {
+        pipe_eval<RB>(a, sh.st, g, lane, nb, sm, EB);
+        pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+        pipe_emit<RB>(a, sh.v, g, lane, interior, EB);
+    }
+}
+
+template <int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(32 * PIPE_CONS, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
+    constexpr int NT = 32 * PIPE_CONS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TmaSmem& sh = *reinterpret_cast<TmaSmem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const uint32_t flags = __ldg(&a.tdesc[tile].flags);
+    const TileGeom g = tile_geom_of(a.b, tile);
+    const bool fast = (flags & 1u) != 0, open_ocean = (flags & 2u) != 0, all_land = (flags & 4u) != 0;
+    const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
+    int g0, tot;
+    if (all_land && interior && fast) {
+        // identity rows only: zeros with a one on each of the six diagonals of every cell
+        g0 = __ldg(&a.tdesc[tile].g0); tot = g.ncell * NSLOT_TOTAL;
+        double2* v2 = reinterpret_cast<double2*>(sh.v);
+        for (int i = threadIdx.x; i < g.ncell * (VSTRIDE / 2); i += NT) v2[i] = make_double2(0.0, 0.0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < g.ncell * NUN; i += NT) {
+            const int cell = i / NUN, r = i - cell * NUN;
+            const int dp = r == 0 ? diag_pos(1) : r == 1 ? diag_pos(2) : r == 2 ? diag_pos(3) : r == 3 ? diag_pos(4) : r == 4 ? diag_pos(5) : diag_pos(6);
+            sh.v[cell * VSTRIDE + dp] = 1.0;
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            mbar_init(&sh.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        PipeStage& st = sh.st;
+        const int w = g.ncell + 2;
+        if (warp == 0) {
+            if (lane == 0)
+                mbar_expect_tx(&sh.bar, (uint32_t)(9 * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
+            __syncwarp();
+            if (lane < 9) {
+                LineSeg seg[3];
+                const int ns = line_plan(a.b, g, lane, seg);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                    if (q < ns)
+                        bulk_load(&st.rec[lane][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
+                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar);
+            } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar);
+            else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar);
+            else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar);
+        }
+        mbar_wait(&sh.bar, 0, 4);
+        // usol in place: no-slip zeroing of u,v, lid / bottom / ghost-column rule of w (descriptor bits)
+        for (int p = threadIdx.x; p < 9 * TW; p += NT) {
+            const int r = p / TW, x = p - r * TW;
+            if (x < w) {
+                if (!((st.desc.uvbits[r] >> x) & 1ull)) *reinterpret_cast<double2*>(&st.rec[r][x][0]) = make_double2(0.0, 0.0);
+                if (!((st.desc.wbits[r] >> x) & 1ull)) st.rec[r][x][2] = 0.0;
+            }
+        }
+        __syncthreads();
+        g0 = st.desc.g0; tot = st.desc.tot;
+        switch (warp) {
+        case 0: tma_rows<1, 1>(a, sh, g, lane, open_ocean, interior); break;
+        case 1: tma_rows<2, 2>(a, sh, g, lane, open_ocean, interior); break;
+        case 2: tma_rows<3, 4>(a, sh, g, lane, open_ocean, interior); break;
+        case 3: tma_rows<5, 5>(a, sh, g, lane, open_ocean, interior); break;
+        default: tma_rows<6, 6>(a, sh, g, lane, open_ocean, interior); break;
+        }
+    }
+    double* gdst = a.val + g0;
+    if (fast) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < g.ncell) {
+            bulk_store(gdst + (size_t)threadIdx.x * NSLOT_TOTAL, sh.v + threadIdx.x * VSTRIDE, NSLOT_TOTAL * (int)sizeof(double));
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        }
+    } else {
+        if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x)) - g0;
+        __syncthreads();
+        for (int q = threadIdx.x; q < tot; q += NT) {
+            int cl = min(q / NSLOT_TOTAL, g.ncell - 1);
+            while (q < sh.cstart[cl]) cl--;
+            while (q >= sh.cstart[cl + 1]) cl++;
+            gdst[q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
+        }
+    }
+}
+
+template <int BLOCKS_PER_SM> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
+        attr_set = true;
+    }
+    thcm_jac_tma_kernel<BLOCKS_PER_SM><<<a.ntile, 32 * PIPE_CONS, sizeof(TmaSmem), c->stream>>>(a);
+}
+
 // exclusive scan of the per-block CRS counts (one block; n_blocks <= a few 1e5)
 __global__ void scan_counts_kernel(int* cnt, int n) {
     __shared__ int warp_tot[32];
@@ -359,6 +775,7 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     a.un = d_un; a.halo = c->d_halo; a.nbmask = c->d_nbmask; a.surf = c->d_surf; a.uvlive = c->d_uvlive; a.frc = c->d_frc;
     a.rowptr = c->d_rowptr; a.val = c->d_val; a.blockcnt = c->d_blockcnt; a.begA = d_begA; a.jcoA = d_jcoA; a.coA = d_coA;
     a.out = d_out; a.sign = 1.0;
+    a.tdesc = c->d_tdesc; a.jrec = c->d_jrec; a.krec = c->d_krec; a.ntile = c->n_asm_blocks;
     int nblk = c->n_asm_blocks;
     static const int kid_of_mode[4] = {KID_ASM_RHS, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS};
     ProfScope prof_(c, kid_of_mode[mode & 3]);
@@ -366,7 +783,12 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     case MODE_RHS:
         a.sign = (mode & 0x100) ? -1.0 : 1.0;
         launch_mode<MODE_RHS>(c, a, nblk); break;
-    case MODE_JAC_GRAPH: launch_mode<MODE_JAC_GRAPH>(c, a, nblk); break;
+    case MODE_JAC_GRAPH:
+        if (c->asm_pipe == 1) launch_jac_tma<5>(c, a);
+        else if (c->asm_pipe == 4) launch_jac_tma<4>(c, a);
+        else if (c->asm_pipe >= 2) launch_jac_pipe(c, a);
+        else launch_mode<MODE_JAC_GRAPH>(c, a, nblk);
+        break;
     case MODE_JAC_COUNT: launch_mode<MODE_JAC_COUNT>(c, a, nblk); break;
     case MODE_JAC_CRS: launch_mode<MODE_JAC_CRS>(c, a, nblk); break;
     default: return -1;

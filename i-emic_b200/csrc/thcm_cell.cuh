@@ -41,6 +41,9 @@ struct AsmArgs {
     int* begA; int* jcoA; double* coA;
     double* out;             // RHS
     double sign;             // RHS: +1 -> B (rhs_), -1 -> F = -B (THCM.C:1011)
+    const TileDesc* tdesc;   // pipelined kernel: per-tile descriptors, per-j / per-k table records
+    const double* jrec; const double* krec;
+    int ntile;
 };
 
 // ---------------------------------------------------------------------------
@@ -115,29 +118,49 @@ THCM_HD double stage_value(const AsmArgs& a, int sv, int gi, int gj, int k) {
     return inside ? raw(a, gi, gj, k, sv - SV_RAW) : 0.0;
 }
 
-// All staged fields of ONE position with unconditional, independent loads (what the kernels execute): the six raw
-// unknowns of the clamped / wrapped source cell (always a valid address) + one uvlive byte, then selects.  Must agree
-// with stage_value() for every sv (checked on the host by tests/emu: emu_check_staging).
-template <int NSV>
-THCM_HD void stage_position(const AsmArgs& a, int gi, int gj, int k, double* out) {
-    const DevBlock& b = a.b;
-    // source cell: TS clamping (no-flux mirror); inside the domain (incl. the periodic wrap) it is the cell itself
+// Source record of ONE staged position: the clamped (no-flux mirror) / wrapped cell whose six raw unknowns feed the
+// staged fields; always a valid record of the owned state (`halo` = 0, idx = cell) or of the halo buffer (`halo` = 1,
+// idx = slot, mirror of thcm::halo_slot).
+struct PosSrc { int halo; long long idx; };
+THCM_HD PosSrc position_source(const DevBlock& b, int gi, int gj, int k) {
     int cj = gj < 1 ? 1 : (gj > b.M ? b.M : gj);
     int ck = k < 1 ? 1 : (k > b.L ? b.L : k);
     int ci = gi;
     if (!b.periodic) ci = gi < 1 ? 1 : (gi > b.N ? b.N : gi);
     int ie = ci - 1 - b.i0, je = cj - 1 - b.j0, kk = ck - 1;
     if (b.wrap_x) { if (ie < 0) ie += b.n0; else if (ie >= b.n0) ie -= b.n0; }
-    const double* src;
-    if (ie >= 0 && ie < b.n0 && je >= 0 && je < b.m0) src = a.un + (size_t)NUN * (((size_t)kk * b.m0 + je) * b.n0 + ie);
-    else {
-        int wrow = b.n0 + b.halo_w + b.halo_e, hs;
-        if (je == -1) hs = kk * b.hk + (ie + b.halo_w);
-        else if (je == b.m0) hs = kk * b.hk + b.halo_s * wrow + (ie + b.halo_w);
-        else if (ie == -1) hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + je;
-        else hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + b.halo_w * b.m0 + je;
-        src = a.halo + (size_t)NUN * hs;
-    }
+    if (ie >= 0 && ie < b.n0 && je >= 0 && je < b.m0) return PosSrc{0, ((long long)kk * b.m0 + je) * b.n0 + ie};
+    int wrow = b.n0 + b.halo_w + b.halo_e, hs;
+    if (je == -1) hs = kk * b.hk + (ie + b.halo_w);
+    else if (je == b.m0) hs = kk * b.hk + b.halo_s * wrow + (ie + b.halo_w);
+    else if (ie == -1) hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + je;
+    else hs = kk * b.hk + (b.halo_s + b.halo_n) * wrow + b.halo_w * b.m0 + je;
+    return PosSrc{1, (long long)hs};
+}
+// what usol keeps of the record at this position: bit 0 u,v survive (corner exists and no-slip rule, usrc.F90:1104-1119),
+// bit 1 w survives (lid / bottom / ghost-column rule, usrc.F90:1051-1052, 1093-1094), bit 2 the position lies inside the
+// domain (incl. the periodic wrap): only then does matAvec multiply its raw unknowns
+enum { POS_UV = 1, POS_W = 2, POS_INSIDE = 4 };
+THCM_HD unsigned position_flags(const DevBlock& b, const uint8_t* uvlive, int gi, int gj, int k) {
+    int ck = k < 1 ? 1 : (k > b.L ? b.L : k);
+    int bi = gi - b.i0, bj = gj - b.j0;
+    bool corner = gi <= b.N && gj <= b.M && k >= 1 && k <= b.L;
+    int bic = bi < 0 ? 0 : (bi > b.n0 + 1 ? b.n0 + 1 : bi), bjc = bj < 0 ? 0 : (bj > b.m0 + 1 ? b.m0 + 1 : bj);
+    bool live = uvlive[((size_t)(ck - 1) * (b.m0 + 2) + bjc) * (b.n0 + 2) + bic] != 0;
+    bool win = k >= 1 && k <= b.L && gj >= 1 && gj <= b.M;
+    bool wi = (gi >= 1 && gi <= b.N) ? (k != b.L) : (b.periodic != 0);
+    bool inside = gj >= 1 && gj <= b.M && k >= 1 && k <= b.L && (b.periodic || (gi >= 1 && gi <= b.N));
+    return ((live && corner) ? POS_UV : 0u) | ((win && wi) ? POS_W : 0u) | (inside ? POS_INSIDE : 0u);
+}
+
+// All staged fields of ONE position with unconditional, independent loads (what the kernels execute): the six raw
+// unknowns of the clamped / wrapped source cell (always a valid address) + one uvlive byte, then selects.  Must agree
+// with stage_value() for every sv (checked on the host by tests/emu: emu_check_staging).
+template <int NSV>
+THCM_HD void stage_position(const AsmArgs& a, int gi, int gj, int k, double* out) {
+    const DevBlock& b = a.b;
+    const PosSrc ps = position_source(b, gi, gj, k);
+    const double* src = (ps.halo ? a.halo : a.un) + (size_t)NUN * ps.idx;
     double r[NUN];
 #ifdef __CUDA_ARCH__
     const double2* s2 = reinterpret_cast<const double2*>(src);   // cells are 48-byte records, 16-byte aligned
@@ -146,24 +169,15 @@ THCM_HD void stage_position(const AsmArgs& a, int gi, int gj, int k, double* out
 #else
     for (int v = 0; v < NUN; v++) r[v] = src[v];
 #endif
-    // u, v: corner (gi, gj) exists for gi <= N, gj <= M; liveness from the precomputed usol rule
-    int bi = gi - b.i0, bj = gj - b.j0;
-    bool corner = gi <= b.N && gj <= b.M && k >= 1 && k <= b.L;
-    int bic = bi < 0 ? 0 : (bi > b.n0 + 1 ? b.n0 + 1 : bi), bjc = bj < 0 ? 0 : (bj > b.m0 + 1 ? b.m0 + 1 : bj);
-    bool live = a.uvlive[((size_t)kk * (b.m0 + 2) + bjc) * (b.n0 + 2) + bic] != 0;
-    live = live && corner;
-    out[SV_U] = live ? r[0] : 0.0;
-    out[SV_V] = live ? r[1] : 0.0;
-    // w (usrc.F90:1051-1052, 1093-1094)
-    bool win = k >= 1 && k <= b.L && gj >= 1 && gj <= b.M;
-    bool wi = (gi >= 1 && gi <= b.N) ? (k != b.L) : (b.periodic != 0);
-    out[SV_W] = (win && wi) ? r[2] : 0.0;
+    const unsigned fl = position_flags(b, a.uvlive, gi, gj, k);
+    out[SV_U] = (fl & POS_UV) ? r[0] : 0.0;
+    out[SV_V] = (fl & POS_UV) ? r[1] : 0.0;
+    out[SV_W] = (fl & POS_W) ? r[2] : 0.0;
     out[SV_T] = r[4];
     out[SV_S] = r[5];
     if constexpr (NSV > SV_NJAC) {
-        bool inside = gj >= 1 && gj <= b.M && k >= 1 && k <= b.L && (b.periodic || (gi >= 1 && gi <= b.N));
 #pragma unroll
-        for (int v = 0; v < NUN; v++) out[SV_RAW + v] = inside ? r[v] : 0.0;
+        for (int v = 0; v < NUN; v++) out[SV_RAW + v] = (fl & POS_INSIDE) ? r[v] : 0.0;
     }
 }
 
@@ -188,6 +202,41 @@ THCM_HD void stage_regular(const double* rec, bool live, bool wlive, double* out
 #pragma unroll
         for (int v = 0; v < NUN; v++) out[SV_RAW + v] = r[v];
     }
+}
+
+// ---------------------------------------------------------------------------
+// Tiles.  A tile is TI = 32 consecutive cells of one (j,k) grid line of the owned block; the kernels stage its
+// 3 x 3 x (TI+2) neighbourhood.  Line r = (dk+1)*3 + (dj+1) of that neighbourhood is, in global memory, ONE contiguous
+// run of 48-byte records (two or three runs at the periodic seam / block edges): what the TMA loader copies.
+// ---------------------------------------------------------------------------
+constexpr int TILE_CELLS = CELLS_PER_BLOCK;
+constexpr int TILE_W = TILE_CELLS + 2;
+struct TileGeom { int cell0, ncell, gi0, gj, k, lj; };   // first owned cell, count, global (1-based) origin
+THCM_HD int tiles_per_row(const DevBlock& b) { return (b.n0 + TILE_CELLS - 1) / TILE_CELLS; }
+THCM_HD TileGeom tile_geom_of(const DevBlock& b, int tile) {
+    const int nbx = tiles_per_row(b);
+    int ib = tile % nbx, rest = tile / nbx;
+    int lj = rest % b.m0, k0 = rest / b.m0;
+    TileGeom g;
+    g.cell0 = (k0 * b.m0 + lj) * b.n0 + ib * TILE_CELLS;
+    g.ncell = b.n0 - ib * TILE_CELLS < TILE_CELLS ? b.n0 - ib * TILE_CELLS : TILE_CELLS;
+    g.gi0 = b.i0 + ib * TILE_CELLS + 1; g.gj = b.j0 + lj + 1; g.k = k0 + 1; g.lj = lj;
+    return g;
+}
+struct LineSeg { int halo; long long idx; int x0, n; };   // n records from un / halo record idx to staged columns x0..
+THCM_HD int line_plan(const DevBlock& b, const TileGeom& g, int r, LineSeg* seg) {
+    const int dj = r % 3 - 1, dk = r / 3 - 1;
+    const PosSrc m = position_source(b, g.gi0, g.gj + dj, g.k + dk);             // owned columns: always one run
+    const PosSrc w = position_source(b, g.gi0 - 1, g.gj + dj, g.k + dk);
+    const PosSrc e = position_source(b, g.gi0 + g.ncell, g.gj + dj, g.k + dk);
+    int n = 0;
+    LineSeg mid{m.halo, m.idx, 1, g.ncell};
+    if (w.halo == m.halo && w.idx == m.idx - 1) { mid.idx = m.idx - 1; mid.x0 = 0; mid.n++; }
+    else { seg[n].halo = w.halo; seg[n].idx = w.idx; seg[n].x0 = 0; seg[n].n = 1; n++; }
+    if (e.halo == m.halo && e.idx == m.idx + g.ncell) mid.n++;
+    else { seg[n].halo = e.halo; seg[n].idx = e.idx; seg[n].x0 = g.ncell + 1; seg[n].n = 1; n++; }
+    seg[n++] = mid;
+    return n;
 }
 
 // tile / table accessors used by the host emulation and as the reference semantics of the shared-memory ones:

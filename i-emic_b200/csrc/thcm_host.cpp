@@ -8,8 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include "thcm_internal.h"
-#include "thcm_slots.h"
+#include "thcm_cell.cuh"
 
 extern "C" void thcm_throw_error_(char* msg);
 
@@ -359,6 +358,12 @@ void compute_tables(thcmb_ctx* c) {
         KTB(K_RT, k) = s.TRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:758, tderiv(1)
         KTB(K_RS, k) = s.SRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:785, tderiv(2)
     }
+    // per-j / per-k records of the pipelined kernel: the three j-neighbour values of every j-table, all k-tables of level k
+    c->jrec_host.assign((size_t)(m + 2) * J_COUNT * JREC, 0.0);
+    for (int j = 1; j <= m; j++) for (int tb = 0; tb < J_COUNT; tb++) for (int d = 0; d < JREC; d++)
+        c->jrec_host[((size_t)j * J_COUNT + tb) * JREC + d] = JTB(tb, j + d - 1);
+    c->krec_host.assign((size_t)(l + 2) * K_COUNT, 0.0);
+    for (int k = 0; k <= l + 1; k++) for (int tb = 0; tb < K_COUNT; tb++) c->krec_host[(size_t)k * K_COUNT + tb] = KTB(tb, k);
     DevTables& t = c->tab;
     t.jstride = js; t.kstride = ks;
     t.epsr = par[ROSB];
@@ -427,6 +432,40 @@ static int owner_of(const Block& me, int gi, int gj) {
     };
     int pn = find(gi, me.N, me.npN), pm = find(gj, me.M, me.npM);
     return pm * me.npN + pn;
+}
+
+DevBlock dev_block(const Block& b) {
+    return DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
+}
+
+// Per-tile descriptors of the pipelined assembly kernel (needs the static graph: call after build_static_host)
+void build_tile_descs(const thcmb_ctx* c, const std::vector<uint32_t>& nbmask, const std::vector<uint8_t>& surf,
+                      const std::vector<uint8_t>& uvlive, std::vector<TileDesc>& out) {
+    const DevBlock b = dev_block(c->blk);
+    const int ntile = tiles_per_row(b) * b.m0 * b.L;
+    out.assign(ntile, TileDesc{});
+    for (int t = 0; t < ntile; t++) {
+        const TileGeom g = tile_geom_of(b, t);
+        TileDesc& d = out[t];
+        for (int x = 0; x < g.ncell; x++) {
+            d.nbmask[x] = nbmask[g.cell0 + x];
+            if (surf[(size_t)g.lj * b.n0 + (g.cell0 + x) % b.n0]) d.surfbits |= 1u << x;
+        }
+        for (int r = 0; r < 9; r++) for (int x = 0; x < g.ncell + 2; x++) {
+            unsigned fl = position_flags(b, uvlive.data(), g.gi0 - 1 + x, g.gj + r % 3 - 1, g.k + r / 3 - 1);
+            if (fl & POS_UV) d.uvbits[r] |= 1ull << x;
+            if (fl & POS_W) d.wbits[r] |= 1ull << x;
+        }
+        d.g0 = c->rowptr_host[(size_t)NUN * g.cell0];
+        d.tot = c->rowptr_host[(size_t)NUN * (g.cell0 + g.ncell)] - d.g0;
+        if (d.tot == g.ncell * NSLOT_TOTAL && (d.g0 & 1) == 0) d.flags |= 1u;
+        bool open_ocean = true;   // no LAND among the 27 (+5) neighbours of any cell: every statement of `boundaries` is a no-op
+        for (int x = 0; x < g.ncell; x++) open_ocean = open_ocean && d.nbmask[x] == 0u;
+        if (open_ocean) d.flags |= 2u;
+        bool all_land = true;      // identity rows only (boundary.F90:381-386): a state-independent pattern
+        for (int x = 0; x < g.ncell; x++) all_land = all_land && ((d.nbmask[x] >> 4) & 1u);
+        if (all_land) d.flags |= 4u;
+    }
 }
 
 // Static per-cell data, graph and halo plan.  Host arrays are returned to the caller (thcm_api.cu uploads them).

@@ -80,6 +80,22 @@ struct ClassTables {
     uint8_t rowlen[NCLASS][NUN];
 };
 
+// Static per-tile descriptor of the pipelined assembly kernel (host-built from the land mask, one TMA bulk load per tile):
+// the per-cell neighbour masks and, for each of the 9 staged grid lines, which positions keep u,v / w after usol.
+struct alignas(16) TileDesc {
+    uint32_t nbmask[32];   // per cell of the tile (0 beyond ncell)
+    uint64_t uvbits[9];    // bit x (0..33) of line r: u,v survive usol's no-slip rule at staged column x
+    uint64_t wbits[9];     // likewise for w (lid / bottom / ghost-column rule)
+    uint32_t surfbits;     // bit lane: 1 - landm(i,j,L) of the cell's column
+    uint32_t flags;        // bit 0: nothing clipped and the tile's first entry is 16-byte aligned (TMA bulk store);
+                           // bit 1: open ocean (all neighbour masks zero: `boundaries` is a no-op for the whole tile);
+                           // bit 2: every cell of the tile is LAND
+    int32_t g0;            // graph offset of the tile's first entry
+    int32_t tot;           // number of graph entries of the tile
+};
+static_assert(sizeof(TileDesc) == 288, "TileDesc is copied with cp.async.bulk (16-byte multiples)");
+constexpr int JREC = 3;   // j-table record: [J_COUNT][3] values at gj-1, gj, gj+1
+
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
 };
@@ -109,6 +125,12 @@ struct thcmb_ctx {
     uint8_t* d_surf = nullptr;      // per owned column: 1 - landm(i,j,L)
     uint8_t* d_uvlive = nullptr;    // (n0+2)(m0+2)L corner box: 1 if usol keeps u,v there
     uint8_t* d_cls = nullptr;       // per owned cell: boundary class (0..63)
+    thcm::TileDesc* d_tdesc = nullptr;  // per tile (pipelined assembly kernel)
+    double *d_jrec = nullptr, *d_krec = nullptr;   // per-j / per-k table records (one bulk load each)
+    std::vector<double> jrec_host, krec_host;
+    unsigned int* d_tilectr = nullptr;
+    int asm_pipe = 1;               // Jacobian kernel: 1 block per tile with TMA staging (default), 0 block per tile with
+                                    // per-position loads, 2 / 3 persistent TMA-pipelined kernel at 2 / 3 CTAs per SM
     double* d_frc = nullptr;        // owned rows (masked)
     int *d_rowptr = nullptr, *d_col = nullptr;  // static graph, local column ids
     double* d_val = nullptr;        // Jacobian values in graph order
@@ -191,6 +213,9 @@ void nccl_destroy(thcmb_ctx* c);
 int p2p_local_handle(thcmb_ctx* c, void* handle64);
 int p2p_open(thcmb_ctx* c, const void* handles_all);
 void p2p_close(thcmb_ctx* c);
+DevBlock dev_block(const Block& b);
+void build_tile_descs(const thcmb_ctx* c, const std::vector<uint32_t>& nbmask, const std::vector<uint8_t>& surf,
+                      const std::vector<uint8_t>& uvlive, std::vector<TileDesc>& out);
 void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<uint8_t>& surf, std::vector<uint8_t>& uvlive,
                        std::vector<int>& send_idx, std::vector<int>& recv_slot);
 const std::string& last_error();

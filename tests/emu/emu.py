@@ -34,7 +34,8 @@ def lib():
                                 ("emu_local_gids", None, [vp, vp]), ("emu_get_forcing", None, [vp, vp, i]), ("emu_get_cob", None, [vp, vp]),
                                 ("emu_plan_sizes", None, [vp, vp, vp, vp]), ("emu_plan", None, [vp, vp, vp, vp]),
                                 ("emu_jacobian", None, [vp, vp, vp, vp]), ("emu_crs", ll, [vp, vp, vp, vp, vp, vp]),
-                                ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp])]:
+                                ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp]),
+                                ("emu_check_tiles", ll, [vp, vp, vp]), ("emu_fast_tiles", ll, [vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -111,6 +112,14 @@ class EmuTHCM:
     def check_staging(self, un, halo=None):
         un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
         return self.L_.emu_check_staging(self.h, _p(un), _p(h))
+
+    def check_tiles(self, un, halo=None):
+        un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)
+        return self.L_.emu_check_tiles(self.h, _p(un), _p(h))
+
+    def fast_tiles(self):
+        tot = C.c_longlong()
+        return self.L_.emu_fast_tiles(self.h, C.byref(tot)), tot.value
 
     def rhs(self, un, halo=None):
         un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)

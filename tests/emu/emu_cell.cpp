@@ -189,6 +189,68 @@ long long emu_check_staging(void* h, const double* un, const double* halo) {
     }
     return bad;
 }
+// The pipelined kernel's staging, replayed on the host: the loader's bulk copies (line_plan), the in-place usol fix-up
+// from the tile descriptor bits and the consumers' record accessor, against stage_value(); plus the descriptor's masks
+// and graph offsets and the per-j / per-k table records.  Returns the number of mismatches.
+long long emu_check_tiles(void* h, const double* un, const double* halo) {
+    Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
+    const DevBlock& b = a.b;
+    std::vector<TileDesc> td;
+    build_tile_descs(&e->c, e->nbmask, e->surf, e->uvlive, td);
+    const int ntile = tiles_per_row(b) * b.m0 * b.L;
+    long long bad = 0;
+    if ((int)td.size() != ntile) return -1;
+    std::vector<double> rec(9 * TILE_W * NUN);
+    for (int t = 0; t < ntile; t++) {
+        const TileGeom g = tile_geom_of(b, t);
+        const TileDesc& d = td[t];
+        std::fill(rec.begin(), rec.end(), -7.77e77);
+        long long copied = 0;
+        for (int r = 0; r < 9; r++) {
+            LineSeg seg[3];
+            int ns = line_plan(b, g, r, seg);
+            for (int q = 0; q < ns; q++) {
+                const double* src = (seg[q].halo ? halo : un) + (size_t)NUN * seg[q].idx;
+                if (seg[q].halo && !halo) { bad++; continue; }
+                for (int i = 0; i < seg[q].n * NUN; i++) rec[((size_t)r * TILE_W + seg[q].x0) * NUN + i] = src[i];
+                copied += seg[q].n;
+            }
+        }
+        if (copied != 9ll * (g.ncell + 2)) bad++;
+        for (int r = 0; r < 9; r++) for (int x = 0; x < g.ncell + 2; x++) {
+            double* p = &rec[((size_t)r * TILE_W + x) * NUN];
+            if (!((d.uvbits[r] >> x) & 1ull)) { p[0] = 0.0; p[1] = 0.0; }
+            if (!((d.wbits[r] >> x) & 1ull)) p[2] = 0.0;
+            for (int sv = 0; sv < SV_NJAC; sv++) {
+                double got = p[sv <= SV_W ? sv : sv + 1];
+                double ref = stage_value(a, sv, g.gi0 - 1 + x, g.gj + r % 3 - 1, g.k + r / 3 - 1);
+                if (!(got == ref)) bad++;
+            }
+        }
+        for (int x = 0; x < TILE_CELLS; x++) {
+            uint32_t nb = x < g.ncell ? a.nbmask[g.cell0 + x] : 0u;
+            if (d.nbmask[x] != nb) bad++;
+            unsigned sf = x < g.ncell ? a.surf[(size_t)g.lj * b.n0 + (g.cell0 + x) % b.n0] : 0;
+            if (((d.surfbits >> x) & 1u) != sf) bad++;
+        }
+        if (d.g0 != a.rowptr[NUN * g.cell0] || d.tot != a.rowptr[NUN * (g.cell0 + g.ncell)] - d.g0) bad++;
+        for (int tb = 0; tb < J_COUNT; tb++) for (int dd = 0; dd < JREC; dd++)
+            if (!(e->c.jrec_host[((size_t)g.gj * J_COUNT + tb) * JREC + dd] == a.t.jt[(size_t)tb * a.t.jstride + g.gj + dd - 1])) bad++;
+        for (int tb = 0; tb < K_COUNT; tb++)
+            if (!(e->c.krec_host[(size_t)g.k * K_COUNT + tb] == a.t.kt[(size_t)tb * a.t.kstride + g.k])) bad++;
+    }
+    return bad;
+}
+// fraction of tiles that take the TMA bulk-store path (nothing clipped, 16-byte aligned): returns count, writes total
+long long emu_fast_tiles(void* h, long long* total) {
+    Emu* e = (Emu*)h;
+    std::vector<TileDesc> td;
+    build_tile_descs(&e->c, e->nbmask, e->surf, e->uvlive, td);
+    long long f = 0;
+    for (auto& d : td) f += d.flags & 1u;
+    *total = (long long)td.size();
+    return f;
+}
 void emu_rhs(void* h, const double* un, const double* halo, double* B) {
     Emu* e = (Emu*)h; AsmArgs a = make_args(e, un, halo);
     for (int cell = 0; cell < a.b.ncell; cell++) {

@@ -41,6 +41,7 @@ def test_single_block_bit_exact(name, state):
          "smooth": lambda: cases.smooth_state(s)}[state]()
     assert np.array_equal(o.rhs(x), e.rhs(x))
     assert e.check_staging(x) == 0   # the kernels' unconditional-load staging == the usol ghost rules
+    assert e.check_tiles(x) == 0     # the pipelined kernel's TMA line plan + descriptor fix-up == the usol ghost rules
     bo, jo, co, cob = o.matrix(x)
     be, je, ce = e.crs(x)
     assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)   # pattern, row order, values
@@ -101,6 +102,7 @@ def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):
         halo = np.where(hg >= 0, x[np.maximum(hg, 0)], np.nan)   # unused halo slots stay NaN: must never be read
         xl = x[gid]
         assert e.check_staging(xl, np.nan_to_num(halo, nan=12345.0)) == 0
+        assert e.check_tiles(xl, np.nan_to_num(halo, nan=12345.0)) == 0
         assert np.array_equal(e.rhs(xl, halo), B[gid])
         # graph rows: same global columns in the same (ascending) order, same values
         rp, col = e.graph()

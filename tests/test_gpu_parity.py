@@ -81,6 +81,22 @@ def test_residual_and_jacobian_bit_exact(gpu, name, state):
     t.close()
 
 
+@pytest.mark.parametrize("name", ["global4deg", "box_p33", "box_np", "gateway16", "box_tiny"])
+@pytest.mark.parametrize("variant", ["0", "1", "4", "2", "3"])
+def test_jacobian_kernel_variants_bit_exact(gpu, name, variant, monkeypatch):
+    """Every Jacobian kernel -- one block per tile with per-position loads (THCM_ASM_PIPE=0), with TMA staging at 5 / 4
+    blocks per SM (1, the default / 4) and the persistent TMA-pipelined one at 2 / 3 CTAs per SM -- must give the oracle's
+    values bit for bit, repeatedly (the pipelined kernel recycles its stages)."""
+    monkeypatch.setenv("THCM_ASM_PIPE", variant)
+    s, landm, o, t = setup(gpu, name)
+    for seed in (1, 2):
+        x = cases.random_state(s, landm, scale=0.3, zero_on_land=False, seed=seed)
+        t.evaluate(dev(x), None, True)
+        vo, missing = o.jacobian_graph(x)
+        assert missing == 0 and np.array_equal(t.jacobian_values_host(), vo)
+    t.close()
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "global4deg"])
 def test_fortran_abi_drop_in(gpu, name):
     """rhs_ / matrix_ / setparcs_ / get_forcing_ with host buffers exactly as THCM.C calls them (THCM.C:603-638, 1001, 1066)."""
