@@ -397,11 +397,13 @@ __device__ __forceinline__ void pipe_finish(const AsmArgs& a, const TileGeom& g,
         for (int q = 0; q < RowSlots<R>::N; q++) E[q] = fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
     }
 }
-template <int R>
+// SEG_ROW0: first row type staged in `v` (the staging holds rows SEG_ROW0..6 or a prefix of them), VS: doubles per cell
+template <int R, int SEG_ROW0 = 1, int VS = VSTRIDE>
 __device__ __forceinline__ void pipe_emit(const AsmArgs& a, double* v, const TileGeom& g, int lane, bool interior, const double* E) {
     if (lane < g.ncell) {
         if (interior) {
-            double* dst = v + lane * VSTRIDE + ROW_OFF[R - 1];
+            constexpr int off = ROW_OFF[R - 1] - ROW_OFF[SEG_ROW0 - 1];
+            double* dst = v + lane * VS + off;
             static_for<0, RowSlots<R>::N>([&](auto qc) {
                 constexpr int q = decltype(qc)::value;
                 dst[interior_pos(R, q)] = E[q];
@@ -410,10 +412,10 @@ __device__ __forceinline__ void pipe_emit(const AsmArgs& a, double* v, const Til
             const int gi = g.gi0 + lane;
             const int cls = (gi == 1 ? 1 : 0) | (gi == a.b.N ? 2 : 0) | (g.gj == 1 ? 4 : 0) | (g.gj == a.b.M ? 8 : 0) | (g.k == 1 ? 16 : 0) |
                             (g.k == a.b.L ? 32 : 0);
-            int rowoff = 0;
+            int rowoff = 0;   // offset of row R from the first staged row = sum of the rows' clipped lengths in between
 #pragma unroll
-            for (int r = 0; r < R - 1; r++) rowoff += c_cls.rowlen[cls][r];
-            const int base = lane * VSTRIDE + rowoff;
+            for (int r = SEG_ROW0 - 1; r < R - 1; r++) rowoff += c_cls.rowlen[cls][r];
+            const int base = lane * VS + rowoff;
             static_for<0, RowSlots<R>::N>([&](auto qc) {
                 constexpr int q = decltype(qc)::value;
                 int p = c_cls.pos[cls][ROW_OFF[R - 1] + q];
@@ -598,53 +600,64 @@ static void launch_jac_pipe(thcmb_ctx* c, const AsmArgs& a) {
 // The persistent variant above measured SLOWER on the B200 (instruction-fetch bound: five row types x 2-3 CTAs do not share
 // the 32 KB L1.5 instruction cache the way 4-5 co-scheduled blocks do, ncu stall_no_instruction 16 of 28 cycles per issue).
 // =============================================================================
-struct alignas(16) TmaSmem {
+// Row groups: A = u | v | w+p (64 entries, bytes [0, 512) of an interior cell's 832-byte record), B = T | S (40 entries,
+// bytes [512, 832)).  One kernel per group: every SM then runs at most three (two) distinct instruction streams, which fit
+// the 32 KB L1.5 instruction cache (with all five in one kernel the top stall was no_instruction), blocks are smaller
+// (more tiles in flight per SM) and the group boundary is a 32-byte sector boundary of the record.
+template <int GROUP> struct RowGroup;
+template <> struct RowGroup<0> { static constexpr int ROW0 = 1, ROW1 = 4, NWARP = 3, LEN = 64, VS = 66; };
+template <> struct RowGroup<1> { static constexpr int ROW0 = 5, ROW1 = 6, NWARP = 2, LEN = 40, VS = 42; };
+
+template <int GROUP> struct alignas(16) TmaSmem {
     PipeStage st;
-    double v[TI * VSTRIDE];
+    double v[TI * RowGroup<GROUP>::VS];
     int cstart[TI + 2];
     unsigned long long bar;
 };
 
 __device__ __forceinline__ constexpr int diag_pos(int R) { return ROW_OFF[R - 1] + interior_pos(R, slot_of(R, 5, R)); }
 
-template <int RA, int RB>
-__device__ __forceinline__ void tma_rows(const AsmArgs& a, TmaSmem& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
+template <int GROUP, int RA, int RB>
+__device__ __forceinline__ void tma_rows(const AsmArgs& a, TmaSmem<GROUP>& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
+    using G = RowGroup<GROUP>;
     constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
     const uint32_t nb = sh.st.desc.nbmask[lane];
     const double sm = (double)((sh.st.desc.surfbits >> lane) & 1u);
     double EA[NA], EB[NB];
     pipe_eval<RA>(a, sh.st, g, lane, nb, sm, EA);
     pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-    pipe_emit<RA>(a, sh.v, g, lane, interior, EA);
+    pipe_emit<RA, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EA);
     if constexpr (RB != RA) {
         pipe_eval<RB>(a, sh.st, g, lane, nb, sm, EB);
         pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-        pipe_emit<RB>(a, sh.v, g, lane, interior, EB);
+        pipe_emit<RB, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EB);
     }
 }
 
-template <int BLOCKS_PER_SM>
-__global__ void __launch_bounds__(32 * PIPE_CONS, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
-    constexpr int NT = 32 * PIPE_CONS;
+template <int GROUP, int BLOCKS_PER_SM>
+__global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
+    using G = RowGroup<GROUP>;
+    constexpr int NT = 32 * G::NWARP;
+    constexpr int SEG0 = ROW_OFF[G::ROW0 - 1];   // first entry of the group inside an interior cell record
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TmaSmem& sh = *reinterpret_cast<TmaSmem*>(smem_raw);
+    TmaSmem<GROUP>& sh = *reinterpret_cast<TmaSmem<GROUP>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const uint32_t flags = __ldg(&a.tdesc[tile].flags);
+    const int g0 = __ldg(&a.tdesc[tile].g0);
     const TileGeom g = tile_geom_of(a.b, tile);
     const bool fast = (flags & 1u) != 0, open_ocean = (flags & 2u) != 0, all_land = (flags & 4u) != 0;
     const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
-    int g0, tot;
     if (all_land && interior && fast) {
-        // identity rows only: zeros with a one on each of the six diagonals of every cell
-        g0 = __ldg(&a.tdesc[tile].g0); tot = g.ncell * NSLOT_TOTAL;
+        // identity rows only: zeros with a one on the diagonal of every row of the group
         double2* v2 = reinterpret_cast<double2*>(sh.v);
-        for (int i = threadIdx.x; i < g.ncell * (VSTRIDE / 2); i += NT) v2[i] = make_double2(0.0, 0.0);
+        for (int i = threadIdx.x; i < g.ncell * (G::VS / 2); i += NT) v2[i] = make_double2(0.0, 0.0);
         __syncthreads();
-        for (int i = threadIdx.x; i < g.ncell * NUN; i += NT) {
-            const int cell = i / NUN, r = i - cell * NUN;
-            const int dp = r == 0 ? diag_pos(1) : r == 1 ? diag_pos(2) : r == 2 ? diag_pos(3) : r == 3 ? diag_pos(4) : r == 4 ? diag_pos(5) : diag_pos(6);
-            sh.v[cell * VSTRIDE + dp] = 1.0;
+        constexpr int NR = G::ROW1 - G::ROW0 + 1;
+        for (int i = threadIdx.x; i < g.ncell * NR; i += NT) {
+            const int cell = i / NR, r = G::ROW0 + (i - cell * NR);
+            const int dp = r == 1 ? diag_pos(1) : r == 2 ? diag_pos(2) : r == 3 ? diag_pos(3) : r == 4 ? diag_pos(4) : r == 5 ? diag_pos(5) : diag_pos(6);
+            sh.v[cell * G::VS + dp - SEG0] = 1.0;
         }
     } else {
         if (threadIdx.x == 0) {
@@ -680,43 +693,53 @@ __global__ void __launch_bounds__(32 * PIPE_CONS, BLOCKS_PER_SM) thcm_jac_tma_ke
             }
         }
         __syncthreads();
-        g0 = st.desc.g0; tot = st.desc.tot;
-        switch (warp) {
-        case 0: tma_rows<1, 1>(a, sh, g, lane, open_ocean, interior); break;
-        case 1: tma_rows<2, 2>(a, sh, g, lane, open_ocean, interior); break;
-        case 2: tma_rows<3, 4>(a, sh, g, lane, open_ocean, interior); break;
-        case 3: tma_rows<5, 5>(a, sh, g, lane, open_ocean, interior); break;
-        default: tma_rows<6, 6>(a, sh, g, lane, open_ocean, interior); break;
+        if constexpr (GROUP == 0) {
+            switch (warp) {
+            case 0: tma_rows<0, 1, 1>(a, sh, g, lane, open_ocean, interior); break;
+            case 1: tma_rows<0, 2, 2>(a, sh, g, lane, open_ocean, interior); break;
+            default: tma_rows<0, 3, 4>(a, sh, g, lane, open_ocean, interior); break;
+            }
+        } else {
+            if (warp == 0) tma_rows<1, 5, 5>(a, sh, g, lane, open_ocean, interior);
+            else tma_rows<1, 6, 6>(a, sh, g, lane, open_ocean, interior);
         }
     }
-    double* gdst = a.val + g0;
     if (fast) {
+        // nothing clipped: the group's segment of every cell record leaves as one TMA bulk store
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
         if (threadIdx.x < g.ncell) {
-            bulk_store(gdst + (size_t)threadIdx.x * NSLOT_TOTAL, sh.v + threadIdx.x * VSTRIDE, NSLOT_TOTAL * (int)sizeof(double));
+            bulk_store(a.val + g0 + (size_t)threadIdx.x * NSLOT_TOTAL + SEG0, sh.v + threadIdx.x * G::VS, G::LEN * (int)sizeof(double));
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         }
     } else {
-        if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x)) - g0;
+        // clipped / unaligned tile: per cell, the group's rows are the entries [rowptr[6c + ROW0-1], rowptr[6c + ROW1])
+        if (threadIdx.x < g.ncell) {
+            sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x) + G::ROW0 - 1);
+            if (threadIdx.x == 0) sh.cstart[TI + 1] = 0;
+        }
         __syncthreads();
-        for (int q = threadIdx.x; q < tot; q += NT) {
-            int cl = min(q / NSLOT_TOTAL, g.ncell - 1);
-            while (q < sh.cstart[cl]) cl--;
-            while (q >= sh.cstart[cl + 1]) cl++;
-            gdst[q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
+        for (int q = threadIdx.x; q < g.ncell * G::LEN; q += NT) {
+            const int cl = q / G::LEN, e = q - cl * G::LEN;
+            const int lo = sh.cstart[cl], hi = __ldg(a.rowptr + NUN * (g.cell0 + cl) + G::ROW1);
+            if (e < hi - lo) a.val[lo + e] = sh.v[cl * G::VS + e];
         }
     }
 }
 
-template <int BLOCKS_PER_SM> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
+template <int GROUP, int BLOCKS_PER_SM> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<GROUP>)));
         attr_set = true;
     }
-    thcm_jac_tma_kernel<BLOCKS_PER_SM><<<a.ntile, 32 * PIPE_CONS, sizeof(TmaSmem), c->stream>>>(a);
+    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(TmaSmem<GROUP>), c->stream>>>(a);
+}
+template <int BA, int BB> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
+    launch_jac_tma_group<0, BA>(c, a);
+    launch_jac_tma_group<1, BB>(c, a);
+    c->launches++;   // two kernels per assembly
 }
 
 // exclusive scan of the per-block CRS counts (one block; n_blocks <= a few 1e5)
@@ -784,8 +807,8 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
         a.sign = (mode & 0x100) ? -1.0 : 1.0;
         launch_mode<MODE_RHS>(c, a, nblk); break;
     case MODE_JAC_GRAPH:
-        if (c->asm_pipe == 1) launch_jac_tma<5>(c, a);
-        else if (c->asm_pipe == 4) launch_jac_tma<4>(c, a);
+        if (c->asm_pipe == 1) launch_jac_tma<6, 8>(c, a);
+        else if (c->asm_pipe == 4) launch_jac_tma<5, 6>(c, a);
         else if (c->asm_pipe >= 2) launch_jac_pipe(c, a);
         else launch_mode<MODE_JAC_GRAPH>(c, a, nblk);
         break;
