@@ -315,12 +315,17 @@ constexpr int PIPE_NSTAGE = 2;
 constexpr int PIPE_CONS = 5;
 constexpr int PIPE_THREADS = 32 * (PIPE_CONS + 2);
 
-struct alignas(16) PipeStage {
-    double rec[9][TW][NUN];        // raw records, line r = (dk+1)*3 + (dj+1); u,v,w zeroed in place where usol does
+// LINES: bit r set = grid line r = (dk+1)*3 + (dj+1) of the 3x3 neighbourhood is staged (compacted in bit order)
+constexpr __host__ __device__ int popc9(int m) { int c = 0; for (int i = 0; i < 9; i++) c += (m >> i) & 1; return c; }
+template <int LINES> struct alignas(16) Stage {
+    static constexpr int MASK = LINES, NL = popc9(LINES);
+    static constexpr __host__ __device__ int slot(int r) { return popc9(LINES & ((1 << r) - 1)); }
+    double rec[NL][TW][NUN];       // raw records; u,v,w zeroed in place where usol does
     TileDesc desc;
     double tj[J_COUNT][JREC];
     double tk[K_COUNT];
 };
+using PipeStage = Stage<0x1ff>;
 static_assert(sizeof(PipeStage) % 16 == 0 && offsetof(PipeStage, desc) % 16 == 0 && offsetof(PipeStage, tj) % 16 == 0 &&
               offsetof(PipeStage, tk) % 16 == 0, "bulk-copy destinations must be 16-byte aligned");
 struct alignas(16) PipeSmem {
@@ -350,13 +355,13 @@ __device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity, int tag = 0) {
-    uint32_t done = 0;
+    uint32_t done = 0, polls = 0;
     const long long t0 = clock64();
     while (true) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        if (clock64() - t0 > (tag == 4 ? 1000000000ll : (tag == 1 || tag == 3) ? 2000000000ll : 4000000000ll)) {           // a lost hand-off must fail loudly, never hang the GPU
+        if ((++polls & 255u) == 0 && clock64() - t0 > (tag == 4 ? 1000000000ll : (tag == 1 || tag == 3) ? 2000000000ll : 4000000000ll)) {           // a lost hand-off must fail loudly, never hang the GPU
             if ((threadIdx.x & 31) == 0) printf("thcm_jac_pipe: block %d warp %d stuck at wait %d (parity %u)\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
             __trap();
         }
@@ -367,24 +372,24 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                  ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct PipeTile {
-    const PipeStage* st; int lane;
+template <class ST> struct PipeTile {
+    const ST* st; int lane;
     __device__ __forceinline__ double operator()(int sv, int di, int dj, int dk) const {
-        return st->rec[(dk + 1) * 3 + (dj + 1)][lane + 1 + di][sv <= SV_W ? sv : sv + 1];   // u v w . T S
+        return st->rec[ST::slot((dk + 1) * 3 + (dj + 1))][lane + 1 + di][sv <= SV_W ? sv : sv + 1];   // u v w . T S
     }
 };
-struct PipeTabs {
-    const PipeStage* st;
+template <class ST> struct PipeTabs {
+    const ST* st;
     __device__ __forceinline__ double jt(int tb, int dj) const { return st->tj[tb][dj + 1]; }
     __device__ __forceinline__ double kt(int tb) const { return st->tk[tb]; }
 };
 
-template <int R>
-__device__ __forceinline__ void pipe_eval(const AsmArgs& a, const PipeStage& st, const TileGeom& g, int lane, uint32_t nb, double sm,
+template <int R, class ST>
+__device__ __forceinline__ void pipe_eval(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, uint32_t nb, double sm,
                                           double* E) {
     if (lane < g.ncell && !((nb >> 4) & 1u)) {
         Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
-        eval_row<R, true>(E, a.t, a.b, c, sm, PipeTile{&st, lane}, PipeTabs{&st});
+        eval_row<R, true>(E, a.t, a.b, c, sm, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
     }
 }
 // open_ocean / interior are TILE-uniform (descriptor flag, tile geometry): no warp votes, inactive lanes of a ragged tile
@@ -605,11 +610,13 @@ static void launch_jac_pipe(thcmb_ctx* c, const AsmArgs& a) {
 // the 32 KB L1.5 instruction cache (with all five in one kernel the top stall was no_instruction), blocks are smaller
 // (more tiles in flight per SM) and the group boundary is a 32-byte sector boundary of the record.
 template <int GROUP> struct RowGroup;
-template <> struct RowGroup<0> { static constexpr int ROW0 = 1, ROW1 = 4, NWARP = 3, LEN = 64, VS = 66; };
-template <> struct RowGroup<1> { static constexpr int ROW0 = 5, ROW1 = 6, NWARP = 2, LEN = 40, VS = 42; };
+// LINES: the grid lines the group's rows read (eval_row): u,v rows -- u,v on level k (dj -1..1) and k+-1 (dj 0), w on levels
+// k-1, k at dj 0, 1; w row -- T on k, k+1; T,S rows -- u,v on level k (dj -1, 0), w on k-1, k, T/S on the 7-point star
+template <> struct RowGroup<0> { static constexpr int ROW0 = 1, ROW1 = 4, NWARP = 3, LEN = 64, VS = 66, LINES = 0xBE; };
+template <> struct RowGroup<1> { static constexpr int ROW0 = 5, ROW1 = 6, NWARP = 2, LEN = 40, VS = 42, LINES = 0xBA; };
 
 template <int GROUP> struct alignas(16) TmaSmem {
-    PipeStage st;
+    Stage<RowGroup<GROUP>::LINES> st;
     double v[TI * RowGroup<GROUP>::VS];
     int cstart[TI + 2];
     unsigned long long bar;
@@ -643,9 +650,39 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     TmaSmem<GROUP>& sh = *reinterpret_cast<TmaSmem<GROUP>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
-    const uint32_t flags = __ldg(&a.tdesc[tile].flags);
-    const int g0 = __ldg(&a.tdesc[tile].g0);
+    using ST = Stage<G::LINES>;
+    ST& st = sh.st;
     const TileGeom g = tile_geom_of(a.b, tile);
+    const int w = g.ncell + 2;
+    // the loads go out before anything is known about the tile (one latency exposure): per staged grid line one
+    // cp.async.bulk run of raw records (two or three at the seam / block edges), the descriptor and the table records
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            mbar_expect_tx(&sh.bar, (uint32_t)(ST::NL * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
+        __syncwarp();
+        if (lane < 9) {
+            if ((G::LINES >> lane) & 1) {
+                LineSeg seg[3];
+                const int ns = line_plan(a.b, g, lane, seg);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                    if (q < ns)
+                        bulk_load(&st.rec[ST::slot(lane)][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
+                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar);
+            }
+        } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar);
+        else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar);
+        else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar);
+        mbar_wait(&sh.bar, 0, 4);   // one warp polls, the others sleep at the barrier
+    }
+    __syncthreads();
+    const uint32_t flags = st.desc.flags;
+    const int g0 = st.desc.g0;
     const bool fast = (flags & 1u) != 0, open_ocean = (flags & 2u) != 0, all_land = (flags & 4u) != 0;
     const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
     if (all_land && interior && fast) {
@@ -660,36 +697,15 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
             sh.v[cell * G::VS + dp - SEG0] = 1.0;
         }
     } else {
-        if (threadIdx.x == 0) {
-            mbar_init(&sh.bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
-        __syncthreads();
-        PipeStage& st = sh.st;
-        const int w = g.ncell + 2;
-        if (warp == 0) {
-            if (lane == 0)
-                mbar_expect_tx(&sh.bar, (uint32_t)(9 * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
-            __syncwarp();
-            if (lane < 9) {
-                LineSeg seg[3];
-                const int ns = line_plan(a.b, g, lane, seg);
-#pragma unroll
-                for (int q = 0; q < 3; q++)
-                    if (q < ns)
-                        bulk_load(&st.rec[lane][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
-                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar);
-            } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar);
-            else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar);
-            else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar);
-        }
-        mbar_wait(&sh.bar, 0, 4);
         // usol in place: no-slip zeroing of u,v, lid / bottom / ghost-column rule of w (descriptor bits)
-        for (int p = threadIdx.x; p < 9 * TW; p += NT) {
-            const int r = p / TW, x = p - r * TW;
+        for (int p = threadIdx.x; p < ST::NL * TW; p += NT) {
+            const int sl = p / TW, x = p - sl * TW;
+            int r = 0;   // grid line held by slot sl
+#pragma unroll
+            for (int i = 0, c = 0; i < 9; i++) if ((G::LINES >> i) & 1) { if (c == sl) r = i; c++; }
             if (x < w) {
-                if (!((st.desc.uvbits[r] >> x) & 1ull)) *reinterpret_cast<double2*>(&st.rec[r][x][0]) = make_double2(0.0, 0.0);
-                if (!((st.desc.wbits[r] >> x) & 1ull)) st.rec[r][x][2] = 0.0;
+                if (!((st.desc.uvbits[r] >> x) & 1ull)) *reinterpret_cast<double2*>(&st.rec[sl][x][0]) = make_double2(0.0, 0.0);
+                if (!((st.desc.wbits[r] >> x) & 1ull)) st.rec[sl][x][2] = 0.0;
             }
         }
         __syncthreads();
@@ -807,8 +823,8 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
         a.sign = (mode & 0x100) ? -1.0 : 1.0;
         launch_mode<MODE_RHS>(c, a, nblk); break;
     case MODE_JAC_GRAPH:
-        if (c->asm_pipe == 1) launch_jac_tma<6, 8>(c, a);
-        else if (c->asm_pipe == 4) launch_jac_tma<5, 6>(c, a);
+        if (c->asm_pipe == 1) launch_jac_tma<8, 11>(c, a);
+        else if (c->asm_pipe == 4) launch_jac_tma<6, 8>(c, a);
         else if (c->asm_pipe >= 2) launch_jac_pipe(c, a);
         else launch_mode<MODE_JAC_GRAPH>(c, a, nblk);
         break;
