@@ -68,13 +68,17 @@ void build_static(thcmb_ctx* c) {
     upload(c->d_tdesc, tdesc);
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
+    upload(c->d_send_dst, c->send_dst_host); upload(c->d_send_peer, c->send_peer_host);
     if (c->d_val) cudaFree(c->d_val);
     THCM_CUDA(cudaMalloc(&c->d_val, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
     THCM_CUDA(cudaMemset(c->d_val, 0, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
     size_t nh = (size_t)NUN * std::max(c->blk.nhalo_cells(), 1);
-    for (double** p : {&c->d_halo, &c->d_sendbuf, &c->d_recvbuf}) { if (*p) cudaFree(*p); *p = nullptr; }
-    THCM_CUDA(cudaMalloc(&c->d_halo, sizeof(double) * nh));
-    THCM_CUDA(cudaMemset(c->d_halo, 0, sizeof(double) * nh));
+    for (double** p : {&c->d_sendbuf, &c->d_recvbuf}) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (!c->halo_p2p) {   // (with the P2P halo push the buffers live in the IPC-shared allocation and keep their size)
+        if (c->d_halo) cudaFree(c->d_halo);
+        THCM_CUDA(cudaMalloc(&c->d_halo, sizeof(double) * nh));
+        THCM_CUDA(cudaMemset(c->d_halo, 0, sizeof(double) * nh));
+    }
     THCM_CUDA(cudaMalloc(&c->d_sendbuf, sizeof(double) * NUN * (size_t)std::max(c->nsend_cells, 1)));
     THCM_CUDA(cudaMalloc(&c->d_recvbuf, sizeof(double) * NUN * (size_t)std::max(c->nrecv_cells, 1)));
     upload_class_tables(class_tables(c->blk.periodic));
@@ -150,7 +154,8 @@ void thcmb_destroy(thcmb_ctx* c) {
     p2p_close(c);
     nccl_destroy(c);
     for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
-                    (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)c->d_halo, (void*)c->d_sendbuf, (void*)c->d_recvbuf,
+                    (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)(c->halo_p2p ? nullptr : c->d_halo), (void*)c->d_sendbuf,
+                    (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec})

@@ -559,7 +559,7 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
         }
     }
     // ---- halo plan: recv lists in my slot order, send lists in the peer's slot order ----
-    c->peers.clear(); send_idx.clear(); recv_slot.clear();
+    c->peers.clear(); send_idx.clear(); recv_slot.clear(); c->send_dst_host.clear(); c->send_peer_host.clear();
     if (b.nranks > 1) {
         auto halo_cells = [&](const Block& bb, std::vector<int>& gi_, std::vector<int>& gj_, std::vector<int>& k_, std::vector<int>& slot_) {
             for (int k = 0; k < bb.L; k++) for (int je = -1; je <= bb.m0; je++) for (int ie = -1; ie <= bb.n0; ie++) {
@@ -586,8 +586,11 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
             std::vector<int> pgi, pgj, pk, pslot;
             halo_cells(pb, pgi, pgj, pk, pslot);
             for (size_t q = 0; q < pslot.size(); q++)
-                if (owner_of(b, pgi[q], pgj[q]) == b.rank)
+                if (owner_of(b, pgi[q], pgj[q]) == b.rank) {
                     send_idx.push_back((pk[q] * b.m0 + (pgj[q] - b.j0)) * b.n0 + (pgi[q] - b.i0));
+                    c->send_dst_host.push_back(pslot[q]);                 // where the cell lives in the peer's halo buffer
+                    c->send_peer_host.push_back((int)c->peers.size());    // index into c->peers (this peer is appended below)
+                }
             peer.send_cnt = (int)send_idx.size() - peer.send_off;
             peer.recv_cnt = (int)recv_slot.size() - peer.recv_off;
             if (peer.send_cnt || peer.recv_cnt) c->peers.push_back(peer);

@@ -141,6 +141,15 @@ struct thcmb_ctx {
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
     int* d_send_idx = nullptr;      // owned-cell ids to pack, grouped by neighbour
     int* d_recv_slot = nullptr;     // halo slot for every received cell, grouped by neighbour
+    // direct halo push over NVLink peer memory (thcm_linalg.cu): destination slot in the PEER's halo buffer and peer index
+    // of every packed cell; the halo buffers (two, alternating) live inside the IPC-shared mailbox allocation
+    std::vector<int> send_dst_host, send_peer_host;
+    int *d_send_dst = nullptr, *d_send_peer = nullptr;
+    bool halo_p2p = false;
+    double* d_halo_p2p[2] = {nullptr, nullptr};
+    double** d_peer_halo = nullptr;  // device array [2][npeers]: peer halo buffer base per parity
+    unsigned long long halo_seq = 0;
+    unsigned int* d_halo_counter = nullptr;
     struct Peer { int rank; int send_off, send_cnt, recv_off, recv_cnt; };
     std::vector<Peer> peers;
     int nsend_cells = 0, nrecv_cells = 0;

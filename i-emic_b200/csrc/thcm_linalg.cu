@@ -111,15 +111,39 @@ __device__ __forceinline__ double block_sum(double v) {
 // One kernel does the local reduction and the collective: no NCCL launch (~10 us) per Krylov dot product.
 // Slots are double-buffered by the parity of a sequence number that all ranks advance in lockstep (SPMD).
 // ---------------------------------------------------------------------------
-struct P2PSlot { double val; unsigned long long seq; };
+// Wire format = NCCL's LL protocol: a double travels as ONE 16-byte store {lo32, flag, hi32, flag}; each 8-byte half
+// carries its own copy of the flag (the low 32 bits of the sequence number), so the receiver needs no fence and no
+// second round trip: it polls the 16 bytes until both flags match (only 8-byte store atomicity is assumed).
+struct alignas(16) P2PSlot { unsigned int lo, f0, hi, f1; };
 struct P2PArgs {
     int nranks, rank;
-    P2PSlot* mine;            // [2][MAX_RANKS]
+    P2PSlot* mine;            // scalar slots [2][MAX_RANKS], then the vector slots (multi_dot)
     P2PSlot* const* peers;    // device array [nranks] of peer mailboxes (entry `rank` unused)
     unsigned long long seq;   // > 0
 };
 constexpr int P2P_MAX_RANKS = 16;
-constexpr size_t P2P_MAILBOX_BYTES = 1024 + (size_t)(64 + 8 + 2) * 8 * 2 * P2P_MAX_RANKS;   // scalar slots + vector slots (multi_dot)
+constexpr int P2P_VEC_LEN = 64 + 1;       // MD_MAXV projections + w.w
+constexpr size_t P2P_VEC_OFFSET = 1024;   // byte offset of the vector slots inside the mailbox allocation
+constexpr size_t P2P_MAILBOX_BYTES = P2P_VEC_OFFSET + sizeof(P2PSlot) * 2 * P2P_MAX_RANKS * P2P_VEC_LEN;
+static_assert(sizeof(P2PSlot) * 2 * P2P_MAX_RANKS <= P2P_VEC_OFFSET, "mailbox layout");
+// the IPC-shared allocation continues with the halo flags [2][MAX_RANKS] (u64 sequence numbers) and the two halo buffers
+constexpr size_t P2P_HALOFLAG_OFFSET = (P2P_MAILBOX_BYTES + 255) / 256 * 256;
+constexpr size_t P2P_HALO_OFFSET = P2P_HALOFLAG_OFFSET + 256;
+static_assert(2 * P2P_MAX_RANKS * sizeof(unsigned long long) <= 256, "halo flag area");
+static inline size_t p2p_halo_bytes(const thcmb_ctx* c) { return ((size_t)NUN * std::max(c->blk.nhalo_cells(), 1) * sizeof(double) + 255) / 256 * 256; }
+
+__device__ __forceinline__ void ll_store(P2PSlot* dst, double v, unsigned int flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "r"((unsigned int)b), "r"(flag),
+                 "r"((unsigned int)(b >> 32)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const P2PSlot* src, unsigned int flag) {
+    unsigned int lo, f0, hi, f1;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+    } while (f0 != flag || f1 != flag);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
 
 __device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     __shared__ bool last;
@@ -143,20 +167,13 @@ __device__ __forceinline__ void finish_reduction(double blocksum, double* partia
         if (threadIdx.x == 0) { mysum = s; *counter = 0u; }
         __syncthreads();
         const int par = (int)(pa.seq & 1ull);
+        const unsigned int flag = (unsigned int)pa.seq;
         if (threadIdx.x < pa.nranks) {
             const int r = threadIdx.x;
             if (r == pa.rank) peer_val[r] = mysum;
             else {
-                // push: value, system-scope fence, then the sequence flag
-                volatile P2PSlot* dst = pa.peers[r] + par * P2P_MAX_RANKS + pa.rank;
-                dst->val = mysum;
-                __threadfence_system();
-                dst->seq = pa.seq;
-                // pull: wait for peer r's flag in my own mailbox
-                volatile P2PSlot* src = pa.mine + par * P2P_MAX_RANKS + r;
-                while (src->seq != pa.seq) { }
-                __threadfence_system();
-                peer_val[r] = src->val;
+                ll_store(pa.peers[r] + par * P2P_MAX_RANKS + pa.rank, mysum, flag);          // push into peer r's mailbox
+                peer_val[r] = ll_wait(pa.mine + par * P2P_MAX_RANKS + r, flag);              // pull peer r's sum from mine
             }
         }
         __syncthreads();
@@ -262,8 +279,9 @@ int p2p_local_handle(thcmb_ctx* c, void* handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (c->blk.nranks > P2P_MAX_RANKS) return -1;
     if (!c->d_mailbox) {
-        THCM_CUDA(cudaMalloc(&c->d_mailbox, P2P_MAILBOX_BYTES));
-        THCM_CUDA(cudaMemset(c->d_mailbox, 0, P2P_MAILBOX_BYTES));
+        const size_t bytes = P2P_HALO_OFFSET + 2 * p2p_halo_bytes(c);
+        THCM_CUDA(cudaMalloc(&c->d_mailbox, bytes));
+        THCM_CUDA(cudaMemset(c->d_mailbox, 0, bytes));
         THCM_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -286,6 +304,28 @@ int p2p_open(thcmb_ctx* c, const void* handles_all) {
     c->p2p_peer_ptrs = ptrs;
     c->p2p_seq = 0;
     c->p2p_on = true;
+    // halo push: my two halo buffers inside the shared allocation, and for every neighbour the address of ITS buffers
+    // (their size is the neighbour's own: read it from the neighbour's block geometry)
+    const char* env = getenv("THCM_HALO_P2P");
+    if (!env || atoi(env) != 0) {
+        THCM_CUDA(cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < 2; b++) c->d_halo_p2p[b] = (double*)((char*)c->d_mailbox + P2P_HALO_OFFSET + b * p2p_halo_bytes(c));
+        if (c->d_halo) cudaFree(c->d_halo);
+        c->d_halo = c->d_halo_p2p[0];
+        std::vector<double*> ph(2 * std::max<size_t>(c->peers.size(), 1), nullptr);
+        for (size_t q = 0; q < c->peers.size(); q++) {
+            thcmb_ctx tmp; tmp.blk = Block();
+            if (!decomp2d(c->blk.nranks, c->peers[q].rank, c->blk.N, c->blk.M, c->blk.L, c->blk.periodic, tmp.blk)) fatal("halo push: bad peer block");
+            const size_t pb = p2p_halo_bytes(&tmp);
+            for (int b = 0; b < 2; b++) ph[b * c->peers.size() + q] = (double*)((char*)ptrs[c->peers[q].rank] + P2P_HALO_OFFSET + b * pb);
+        }
+        THCM_CUDA(cudaMalloc(&c->d_peer_halo, sizeof(double*) * ph.size()));
+        THCM_CUDA(cudaMemcpy(c->d_peer_halo, ph.data(), sizeof(double*) * ph.size(), cudaMemcpyHostToDevice));
+        THCM_CUDA(cudaMalloc(&c->d_halo_counter, sizeof(unsigned int)));
+        THCM_CUDA(cudaMemset(c->d_halo_counter, 0, sizeof(unsigned int)));
+        c->halo_seq = 0;
+        c->halo_p2p = true;
+    }
     return 0;
 }
 void p2p_close(thcmb_ctx* c) {
@@ -293,8 +333,10 @@ void p2p_close(thcmb_ctx* c) {
         if (r != c->blk.rank && c->p2p_peer_ptrs[r]) cudaIpcCloseMemHandle(c->p2p_peer_ptrs[r]);
     c->p2p_peer_ptrs.clear();
     if (c->d_peer_mailboxes) cudaFree(c->d_peer_mailboxes);
+    if (c->d_peer_halo) cudaFree(c->d_peer_halo);
+    if (c->halo_p2p) c->d_halo = nullptr;   // lived inside the mailbox allocation
     if (c->d_mailbox) cudaFree(c->d_mailbox);
-    c->d_peer_mailboxes = nullptr; c->d_mailbox = nullptr; c->p2p_on = false;
+    c->d_peer_mailboxes = nullptr; c->d_mailbox = nullptr; c->d_peer_halo = nullptr; c->p2p_on = false; c->halo_p2p = false;
 }
 
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out) {
@@ -340,11 +382,12 @@ int fill(thcmb_ctx* c, int n, double a, double* x) {
 constexpr int MD_MAXV = 64;            // projections per kernel (GMRES restart <= 63 in this mode)
 constexpr int MD_CHUNK = 8;
 constexpr int MD_BLOCKS = NSM * 4;
+static_assert(P2P_VEC_LEN == MD_MAXV + 1, "mailbox layout");
 struct VecList { const double* v[MD_MAXV]; int nv; };
-struct P2PVecSlot { double val[MD_MAXV + 8]; unsigned long long seq; unsigned long long pad; };
-constexpr size_t P2P_VEC_OFFSET = 1024;   // byte offset of the vector slots inside the mailbox allocation
-static_assert(P2P_MAILBOX_BYTES == P2P_VEC_OFFSET + sizeof(P2PVecSlot) * 2 * P2P_MAX_RANKS, "mailbox layout");
 
+// grid = (slices, chunks): block (x, y) accumulates the projections of chunk y (8 basis vectors, + w.w for chunk 0)
+// over slice x of the vectors.  All chunks are in flight at once: one latency-bound sweep instead of nv/8 sequential ones
+// (what limited this kernel on the 1/8-size vectors of an 8-GPU run).
 __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList vl, const double* __restrict__ w, const int* __restrict__ skip,
                                                                  double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
     __shared__ double red[RED_THREADS / 32][MD_CHUNK + 1];
@@ -353,80 +396,83 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool skipped = skip != nullptr && *skip == 0;     // conditional second pass (DGKS criterion), uniform over the grid
     if (!skipped) {
-        for (int c0 = 0; c0 < nv; c0 += MD_CHUNK) {
-            const int nc = min(MD_CHUNK, nv - c0);
-            double acc[MD_CHUNK + 1];
+        const int c0 = blockIdx.y * MD_CHUNK;
+        const int nc = min(MD_CHUNK, nv - c0);
+        double acc[MD_CHUNK + 1];
 #pragma unroll
-            for (int q = 0; q <= MD_CHUNK; q++) acc[q] = 0.0;
-            // 128-bit loads (all Krylov vectors come from cudaMalloc: 256-byte aligned; n is even: 6 unknowns per cell)
-            const int n2 = n >> 1;
-            const double2* w2 = reinterpret_cast<const double2*>(w);
-            for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n2; i += gridDim.x * RED_THREADS) {
-                const double2 wi = w2[i];
-                double2 vv[MD_CHUNK];
+        for (int q = 0; q <= MD_CHUNK; q++) acc[q] = 0.0;
+        // 128-bit loads (all Krylov vectors come from cudaMalloc: 256-byte aligned; n is even: 6 unknowns per cell)
+        const int n2 = n >> 1;
+        const double2* w2 = reinterpret_cast<const double2*>(w);
+        for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n2; i += gridDim.x * RED_THREADS) {
+            const double2 wi = w2[i];
+            double2 vv[MD_CHUNK];
 #pragma unroll
-                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) vv[q] = reinterpret_cast<const double2*>(vl.v[c0 + q])[i];
+            for (int q = 0; q < MD_CHUNK; q++) if (q < nc) vv[q] = reinterpret_cast<const double2*>(vl.v[c0 + q])[i];
 #pragma unroll
-                for (int q = 0; q < MD_CHUNK; q++) if (q < nc) { acc[q] += wi.x * vv[q].x; acc[q] += wi.y * vv[q].y; }
-                if (c0 == 0) { acc[MD_CHUNK] += wi.x * wi.x; acc[MD_CHUNK] += wi.y * wi.y; }
-            }
-            if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-                const double wi = w[n - 1];
-                for (int q = 0; q < nc; q++) acc[q] += wi * vl.v[c0 + q][n - 1];
-                if (c0 == 0) acc[MD_CHUNK] += wi * wi;
-            }
+            for (int q = 0; q < MD_CHUNK; q++) if (q < nc) { acc[q] += wi.x * vv[q].x; acc[q] += wi.y * vv[q].y; }
+            if (c0 == 0) { acc[MD_CHUNK] += wi.x * wi.x; acc[MD_CHUNK] += wi.y * wi.y; }
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+            const double wi = w[n - 1];
+            for (int q = 0; q < nc; q++) acc[q] += wi * vl.v[c0 + q][n - 1];
+            if (c0 == 0) acc[MD_CHUNK] += wi * wi;
+        }
 #pragma unroll
-            for (int q = 0; q <= MD_CHUNK; q++) {
-                double v = acc[q];
+        for (int q = 0; q <= MD_CHUNK; q++) {
+            double v = acc[q];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) red[warp][q] = v;
-            }
-            __syncthreads();
-            if (threadIdx.x <= MD_CHUNK) {
-                double v = 0.0;
-                for (int ww = 0; ww < RED_THREADS / 32; ww++) v += red[ww][threadIdx.x];
-                if (threadIdx.x < nc) partial[(size_t)blockIdx.x * stride + c0 + threadIdx.x] = v;
-                if (threadIdx.x == MD_CHUNK && c0 == 0) partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
-            }
-            __syncthreads();
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x <= MD_CHUNK) {
+            double v = 0.0;
+            for (int ww = 0; ww < RED_THREADS / 32; ww++) v += red[ww][threadIdx.x];
+            if (threadIdx.x < nc) partial[(size_t)blockIdx.x * stride + c0 + threadIdx.x] = v;
+            if (threadIdx.x == MD_CHUNK && c0 == 0) partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
         }
     }
     if (threadIdx.x == 0) {
         __threadfence();
         unsigned int t = atomicAdd(counter, 1u);
-        last = (t == gridDim.x - 1);
+        last = (t == gridDim.x * gridDim.y - 1);
     }
     __syncthreads();
     if (!last) return;
-    // ---- last block: fixed-order sum of the per-block partials, then the cross-GPU exchange ----
+    // ---- last block: fixed-order sum of the per-slice partials, then the cross-GPU exchange ----
     __shared__ double mine[MD_MAXV + 1];
     for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
         const int col = q < nv ? q : MD_MAXV;
         double v = 0.0;
-        if (!skipped) for (int b = 0; b < (int)gridDim.x; b++) v += ((volatile double*)partial)[(size_t)b * stride + col];
+        if (!skipped) {
+            const volatile double* pc = partial + col;
+            int b = 0;
+            for (; b + 8 <= (int)gridDim.x; b += 8) {   // eight loads in flight, summed in slice order
+                double t0 = pc[(size_t)(b + 0) * stride], t1 = pc[(size_t)(b + 1) * stride], t2 = pc[(size_t)(b + 2) * stride], t3 = pc[(size_t)(b + 3) * stride];
+                double t4 = pc[(size_t)(b + 4) * stride], t5 = pc[(size_t)(b + 5) * stride], t6 = pc[(size_t)(b + 6) * stride], t7 = pc[(size_t)(b + 7) * stride];
+                v += t0; v += t1; v += t2; v += t3; v += t4; v += t5; v += t6; v += t7;
+            }
+            for (; b < (int)gridDim.x; b++) v += pc[(size_t)b * stride];
+        }
         mine[q] = v;
     }
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
     if (pa.nranks > 1) {
         const int par = (int)(pa.seq & 1ull);
-        P2PVecSlot* my_slots = (P2PVecSlot*)((char*)pa.mine + P2P_VEC_OFFSET);
-        if (threadIdx.x < pa.nranks && threadIdx.x != pa.rank) {
-            const int r = threadIdx.x;
-            volatile P2PVecSlot* dst = (P2PVecSlot*)((char*)pa.peers[r] + P2P_VEC_OFFSET) + par * P2P_MAX_RANKS + pa.rank;
-            for (int q = 0; q <= nv; q++) dst->val[q] = mine[q];
-            __threadfence_system();
-            dst->seq = pa.seq;
-            volatile P2PVecSlot* src = my_slots + par * P2P_MAX_RANKS + r;
-            while (src->seq != pa.seq) { }
-            __threadfence_system();
+        const unsigned int flag = (unsigned int)pa.seq;
+        const size_t slot0 = P2P_VEC_OFFSET / sizeof(P2PSlot) + (size_t)par * P2P_MAX_RANKS * P2P_VEC_LEN;
+        // push: every (peer, value) pair is one 16-byte LL store, spread over the block
+        for (int t = threadIdx.x; t < pa.nranks * (nv + 1); t += RED_THREADS) {
+            const int r = t / (nv + 1), q = t - r * (nv + 1);
+            if (r != pa.rank) ll_store(pa.peers[r] + slot0 + (size_t)pa.rank * P2P_VEC_LEN + q, mine[q], flag);
         }
-        __syncthreads();
+        // pull: value q of every peer from my own mailbox, summed in rank order (identical bits on every rank)
         for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
             double tot = 0.0;
             for (int r = 0; r < pa.nranks; r++)
-                tot += (r == pa.rank) ? mine[q] : ((volatile P2PVecSlot*)(my_slots + par * P2P_MAX_RANKS + r))->val[q];
+                tot += (r == pa.rank) ? mine[q] : ll_wait(pa.mine + slot0 + (size_t)r * P2P_VEC_LEN + q, flag);
             out[q] = tot;      // out[0..nv-1] = V^T w, out[nv] = w.w
         }
     } else {
@@ -473,7 +519,9 @@ int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
     { ProfScope prof_(c, KID_MULTIDOT);
-      multi_dot_kernel<<<MD_BLOCKS, RED_THREADS, 0, c->stream>>>(n, vl, w, d_skip, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c)); }
+      const int nchunk = std::max(1, (nv + MD_CHUNK - 1) / MD_CHUNK);
+      const int slices = std::max(NSM / 2, MD_BLOCKS / nchunk);
+      multi_dot_kernel<<<dim3(slices, nchunk), RED_THREADS, 0, c->stream>>>(n, vl, w, d_skip, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c)); }
     c->launches++;
     return c->p2p_on ? 0 : allreduce_dev(c, d_out, nv + 1);
 }
@@ -507,6 +555,44 @@ __global__ void halo_unpack_kernel(int ncells, const int* __restrict__ slot, con
         int cidx = t / NUN, v = t - cidx * NUN;
         halo[(size_t)NUN * slot[cidx] + v] = buf[t];
     }
+}
+
+// Halo exchange as ONE kernel over NVLink peer memory: every boundary cell is stored straight into the neighbour's halo
+// buffer (no pack / NCCL send-recv / unpack: three launches and two staging copies less per operator application); the
+// last block to finish publishes a sequence flag in every neighbour's mailbox and waits for theirs, so the halo is complete
+// when the kernel ends.  Two halo buffers alternate by the parity of the sequence number: a neighbour that runs ahead
+// writes exchange s+1 into the other buffer while this rank still reads exchange s.
+constexpr int HALO_MAX_PEERS = 8;
+struct HaloPeers { int n; int rank[HALO_MAX_PEERS]; unsigned char send[HALO_MAX_PEERS], recv[HALO_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* __restrict__ idx, const int* __restrict__ dst_slot,
+                                                         const int* __restrict__ peer, const double* __restrict__ x, double* const* peer_halo,
+                                                         HaloPeers hp, int myrank, char* const* peer_base, char* my_base,
+                                                         unsigned long long seq, unsigned int* counter) {
+    __shared__ bool last;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells * (NUN / 2); t += gridDim.x * blockDim.x) {
+        const int cidx = t / (NUN / 2), v = t - cidx * (NUN / 2);   // 16-byte pieces: records are 48 bytes, 16-byte aligned
+        const double2 val = reinterpret_cast<const double2*>(x + (size_t)NUN * idx[cidx])[v];
+        reinterpret_cast<double2*>(peer_halo[peer[cidx]] + (size_t)NUN * dst_slot[cidx])[v] = val;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x < hp.n) {
+        const int q = threadIdx.x;
+        if (hp.send[q]) {
+            volatile unsigned long long* f = (volatile unsigned long long*)(peer_base[hp.rank[q]] + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + myrank;
+            *f = seq;
+        }
+        if (hp.recv[q]) {
+            volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[q];
+            while (*f != seq) { }
+        }
+    }
+    __threadfence_system();
+    if (threadIdx.x == 0) *counter = 0u;
 }
 
 struct Id128 { char b[128]; };  // ncclUniqueId (nccl.h: struct { char internal[128]; }), passed by value
@@ -559,6 +645,22 @@ int allreduce_dev(thcmb_ctx* c, double* d_buf, int count) {
 
 int halo_exchange(thcmb_ctx* c, const double* d_x) {
     if (c->blk.nranks == 1) return 0;
+    if (c->halo_p2p) {
+        if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 8 neighbours");
+        if ((((uintptr_t)d_x) & 15) != 0) fatal("halo push: vector must be 16-byte aligned");
+        HaloPeers hp; hp.n = (int)c->peers.size();
+        for (int q = 0; q < hp.n; q++) { hp.rank[q] = c->peers[q].rank; hp.send[q] = c->peers[q].send_cnt > 0; hp.recv[q] = c->peers[q].recv_cnt > 0; }
+        const unsigned long long seq = ++c->halo_seq;
+        const int par = (int)(seq & 1ull);
+        ProfScope prof_(c, KID_HALO_PACK);
+        const int grid = std::max(1, std::min(ew_grid(c->nsend_cells * (NUN / 2)), NSM));
+        halo_push_kernel<<<grid, 256, 0, c->stream>>>(c->nsend_cells, c->d_send_idx, c->d_send_dst, c->d_send_peer, d_x,
+                                                      c->d_peer_halo + (size_t)par * c->peers.size(), hp, c->blk.rank,
+                                                      (char* const*)c->d_peer_mailboxes, (char*)c->d_mailbox, seq, c->d_halo_counter);
+        c->launches++;
+        c->d_halo = c->d_halo_p2p[par];
+        return 0;
+    }
     if (!c->nccl_comm) fatal("nranks > 1 but thcmb_nccl_init was not called");
     if (c->nsend_cells > 0) {
         ProfScope prof_(c, KID_HALO_PACK);

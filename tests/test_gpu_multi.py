@@ -53,8 +53,17 @@ def worker(rank, world, port, name, outdir):
     t.buildPreconditioner(1)
     sol = t.new_vector()
     res, hist = t.gmres(F, sol, tol=1e-8, maxit=30, restart=15)
+    # batched DGKS orthogonalisation (multi_dot with the fused LL all-reduce over peer memory)
+    sol2 = t.new_vector()
+    res2, hist2 = t.gmres(F, sol2, tol=1e-8, maxit=30, restart=15, ortho="dgks")
+    # back-to-back operator applications with no reduction in between: the two alternating halo buffers of the P2P push
+    y2, y3 = t.new_vector(), t.new_vector()
+    for _ in range(5):
+        t.applyMatrix(y, y2)
+        t.applyMatrix(y2, y3)
     np.savez(os.path.join(outdir, f"r{rank}.npz"), gid=gid, F=F.cpu().numpy(), val=val, rp=rp, col=col, hg=t.halo_gids(),
-             y=y.cpu().numpy(), nrm=nrm, hist=hist, sol=sol.cpu().numpy(), iters=res.iters)
+             y=y.cpu().numpy(), nrm=nrm, hist=hist, sol=sol.cpu().numpy(), iters=res.iters, hist2=hist2, iters2=res2.iters,
+             y3=y3.cpu().numpy())
     t.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -89,8 +98,11 @@ def test_multi_gpu_reproduces_global_answer(name, tmp_path):
     t1.buildPreconditioner(1)
     sol1 = t1.new_vector()
     res1, hist1 = t1.gmres(F1, sol1, tol=1e-8, maxit=30, restart=15)
+    res1d, hist1d = t1.gmres(F1, t1.new_vector(), tol=1e-8, maxit=30, restart=15, ortho="dgks")
+    y3o = spmv(ro, co, vo, spmv(ro, co, vo, yo))
     seen = np.zeros(o.ndim, int)
     y_all = np.zeros(o.ndim)
+    y3_all = np.zeros(o.ndim)
     for r in range(world):
         d = np.load(tmp_path / f"r{r}.npz")
         gid = d["gid"]
@@ -103,6 +115,11 @@ def test_multi_gpu_reproduces_global_answer(name, tmp_path):
         k = min(len(hist1), len(d["hist"]))
         assert abs(int(d["iters"]) - res1.iters) <= 1
         assert np.abs(d["hist"][:k] - hist1[:k]).max() <= 1e-10
+        k = min(len(hist1d), len(d["hist2"]))
+        assert abs(int(d["iters2"]) - res1d.iters) <= 1
+        assert np.abs(d["hist2"][:k] - hist1d[:k]).max() <= 1e-10
+        y3_all[gid] = d["y3"]
     assert np.all(seen == 1)
+    assert np.linalg.norm(y3_all - y3o) <= 1e-12 * np.linalg.norm(y3o)
     assert np.linalg.norm(y_all - yo) <= 1e-13 * np.linalg.norm(yo)
     t1.close()
