@@ -399,12 +399,19 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
                     THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));
                     multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
-                    multi_axpy_dev(c, n, nv, vp.data(), dh, nullptr, w);
-                    dot_dev(c, n, w, w, dh + S);
-                    dgks_flag_dev(c, dh + nv, dh + S, c->d_flags);
-                    multi_dot_dev(c, n, nv, vp.data(), w, c->d_flags, dh + 2 * S);
-                    multi_axpy_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w);
-                    dot_dev(c, n, w, w, dh + 3 * S);
+                    if (c->p2p_on || c->blk.nranks == 1) {
+                        // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
+                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh, nullptr, w, dh + S, dh + nv, c->d_flags, dh + 3 * S);
+                        multi_dot_dev(c, n, nv, vp.data(), w, c->d_flags, dh + 2 * S);
+                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
+                    } else {   // plain NCCL all-reduces (THCM_P2P=0)
+                        multi_axpy_dev(c, n, nv, vp.data(), dh, nullptr, w);
+                        dot_dev(c, n, w, w, dh + S);
+                        dgks_flag_dev(c, dh + nv, dh + S, c->d_flags);
+                        multi_dot_dev(c, n, nv, vp.data(), w, c->d_flags, dh + 2 * S);
+                        multi_axpy_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w);
+                        dot_dev(c, n, w, w, dh + 3 * S);
+                    }
                     scale_invsqrt_dev(c, n, dh + 3 * S, w, dh + 3 * S + 1);
                     THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (3 * S + 2), cudaMemcpyDeviceToHost, c->stream));
                     THCM_CUDA(cudaMemcpyAsync(c->h_scalars + 3 * S + 2, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -159,7 +159,7 @@ struct thcmb_ctx {
     void* d_mailbox = nullptr;
     void* d_peer_mailboxes = nullptr;
     std::vector<void*> p2p_peer_ptrs;
-    unsigned long long p2p_seq = 0, p2p_vseq = 0;
+    unsigned long long* d_p2p_seq = nullptr;   // device counters of completed exchanges: [0] scalar slots, [1] vector slots
     double* d_mdpartial = nullptr;   // multi_dot partials
     int* d_flags = nullptr;          // device flags (DGKS second-pass decision)
     // ---- workspaces ----
@@ -214,6 +214,8 @@ int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out
 int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
 int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out);
 int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w);
+int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out);
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out);
 int nccl_unique_id(void* id128);

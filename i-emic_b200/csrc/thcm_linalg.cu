@@ -119,7 +119,8 @@ struct P2PArgs {
     int nranks, rank;
     P2PSlot* mine;            // scalar slots [2][MAX_RANKS], then the vector slots (multi_dot)
     P2PSlot* const* peers;    // device array [nranks] of peer mailboxes (entry `rank` unused)
-    unsigned long long seq;   // > 0
+    unsigned long long* seq;  // DEVICE counter of completed exchanges: advanced by the kernel that really exchanges, so a
+                              // pass that every rank skips on the device (DGKS) keeps the slot parity alternating
 };
 constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_VEC_LEN = 64 + 1;       // MD_MAXV projections + w.w
@@ -145,7 +146,14 @@ __device__ __forceinline__ double ll_wait(const P2PSlot* src, unsigned int flag)
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
-__device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
+// optional epilogue of a reduction (DGKS, thcmb_gmres): flag = (result < 0.5 * *ww_old), *final_out = result
+struct RedEpilogue { const double* ww_old; int* flag_out; double* final_out; };
+__device__ __forceinline__ void red_epilogue(double tot, const RedEpilogue ep) {
+    if (ep.flag_out) *ep.flag_out = (tot < 0.5 * (*ep.ww_old)) ? 1 : 0;
+    if (ep.final_out) *ep.final_out = tot;
+}
+__device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa,
+                                                 const RedEpilogue ep = RedEpilogue{nullptr, nullptr, nullptr}) {
     __shared__ bool last;
     __shared__ double peer_val[P2P_MAX_RANKS];
     if (threadIdx.x == 0) {
@@ -160,14 +168,15 @@ __device__ __forceinline__ void finish_reduction(double blocksum, double* partia
         for (int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS) v += ((volatile double*)partial)[i];
         double s = block_sum(v);
         if (pa.nranks <= 1) {
-            if (threadIdx.x == 0) { *out = s; *counter = 0u; }
+            if (threadIdx.x == 0) { *out = s; *counter = 0u; red_epilogue(s, ep); }
             return;
         }
         __shared__ double mysum;
+        const unsigned long long seq = *pa.seq + 1ull;
         if (threadIdx.x == 0) { mysum = s; *counter = 0u; }
         __syncthreads();
-        const int par = (int)(pa.seq & 1ull);
-        const unsigned int flag = (unsigned int)pa.seq;
+        const int par = (int)(seq & 1ull);
+        const unsigned int flag = (unsigned int)seq;
         if (threadIdx.x < pa.nranks) {
             const int r = threadIdx.x;
             if (r == pa.rank) peer_val[r] = mysum;
@@ -181,6 +190,8 @@ __device__ __forceinline__ void finish_reduction(double blocksum, double* partia
             double tot = 0.0;
             for (int r = 0; r < pa.nranks; r++) tot += peer_val[r];   // fixed rank order: identical bits on every rank
             *out = tot;
+            *pa.seq = seq;
+            red_epilogue(tot, ep);
         }
     }
 }
@@ -265,11 +276,11 @@ static inline int ew_grid(int n) {
 }
 
 static P2PArgs p2p_args(thcmb_ctx* c) {
-    P2PArgs pa{1, 0, nullptr, nullptr, 0ull};
+    P2PArgs pa{1, 0, nullptr, nullptr, nullptr};
     if (c->p2p_on) {
         pa.nranks = c->blk.nranks; pa.rank = c->blk.rank;
         pa.mine = (P2PSlot*)c->d_mailbox; pa.peers = (P2PSlot* const*)c->d_peer_mailboxes;
-        pa.seq = ++c->p2p_seq;
+        pa.seq = c->d_p2p_seq;
     }
     return pa;
 }
@@ -302,7 +313,8 @@ int p2p_open(thcmb_ctx* c, const void* handles_all) {
     THCM_CUDA(cudaMalloc(&c->d_peer_mailboxes, sizeof(void*) * ptrs.size()));
     THCM_CUDA(cudaMemcpy(c->d_peer_mailboxes, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice));
     c->p2p_peer_ptrs = ptrs;
-    c->p2p_seq = 0;
+    THCM_CUDA(cudaMalloc(&c->d_p2p_seq, 2 * sizeof(unsigned long long)));
+    THCM_CUDA(cudaMemset(c->d_p2p_seq, 0, 2 * sizeof(unsigned long long)));
     c->p2p_on = true;
     // halo push: my two halo buffers inside the shared allocation, and for every neighbour the address of ITS buffers
     // (their size is the neighbour's own: read it from the neighbour's block geometry)
@@ -334,6 +346,8 @@ void p2p_close(thcmb_ctx* c) {
     c->p2p_peer_ptrs.clear();
     if (c->d_peer_mailboxes) cudaFree(c->d_peer_mailboxes);
     if (c->d_peer_halo) cudaFree(c->d_peer_halo);
+    if (c->d_p2p_seq) cudaFree(c->d_p2p_seq);
+    c->d_p2p_seq = nullptr;
     if (c->halo_p2p) c->d_halo = nullptr;   // lived inside the mailbox allocation
     if (c->d_mailbox) cudaFree(c->d_mailbox);
     c->d_peer_mailboxes = nullptr; c->d_mailbox = nullptr; c->d_peer_halo = nullptr; c->p2p_on = false; c->halo_p2p = false;
@@ -394,8 +408,11 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
     __shared__ bool last;
     const int nv = vl.nv, stride = MD_MAXV + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool skipped = skip != nullptr && *skip == 0;     // conditional second pass (DGKS criterion), uniform over the grid
-    if (!skipped) {
+    // conditional second pass (DGKS criterion): the flag is the same on every rank (it derives from all-reduced values), so
+    // a skipped pass leaves the grid -- and the cross-GPU exchange -- entirely; `out` was zeroed by the caller
+    const bool skipped = skip != nullptr && *skip == 0;
+    if (skipped) return;
+    {
         const int c0 = blockIdx.y * MD_CHUNK;
         const int nc = min(MD_CHUNK, nv - c0);
         double acc[MD_CHUNK + 1];
@@ -457,11 +474,12 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
         }
         mine[q] = v;
     }
+    const unsigned long long seq = pa.nranks > 1 ? *pa.seq + 1ull : 0ull;
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
     if (pa.nranks > 1) {
-        const int par = (int)(pa.seq & 1ull);
-        const unsigned int flag = (unsigned int)pa.seq;
+        const int par = (int)(seq & 1ull);
+        const unsigned int flag = (unsigned int)seq;
         const size_t slot0 = P2P_VEC_OFFSET / sizeof(P2PSlot) + (size_t)par * P2P_MAX_RANKS * P2P_VEC_LEN;
         // push: every (peer, value) pair is one 16-byte LL store, spread over the block
         for (int t = threadIdx.x; t < pa.nranks * (nv + 1); t += RED_THREADS) {
@@ -475,6 +493,7 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
                 tot += (r == pa.rank) ? mine[q] : ll_wait(pa.mine + slot0 + (size_t)r * P2P_VEC_LEN + q, flag);
             out[q] = tot;      // out[0..nv-1] = V^T w, out[nv] = w.w
         }
+        if (threadIdx.x == 0) *pa.seq = seq;
     } else {
         for (int q = threadIdx.x; q <= nv; q += RED_THREADS) out[q] = mine[q];
     }
@@ -500,15 +519,41 @@ __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, VecList vl, cons
     }
 }
 
+// fused: w -= V h, then ww = w.w of the UPDATED w in the same sweep (+ cross-GPU sum, + the DGKS decision in the epilogue):
+// one pass over w and one kernel less per orthogonalisation pass than multi_axpy followed by dot
+__global__ void __launch_bounds__(RED_THREADS) multi_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h, const int* __restrict__ skip,
+                                                                      double* __restrict__ w, double* partial, unsigned int* counter, double* out,
+                                                                      const P2PArgs pa, const RedEpilogue ep) {
+    __shared__ double hs[MD_MAXV];
+    if (skip != nullptr && *skip == 0) return;
+    for (int q = threadIdx.x; q < vl.nv; q += blockDim.x) hs[q] = h[q];
+    __syncthreads();
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double wi = w[i];
+        for (int c0 = 0; c0 < vl.nv; c0 += MD_CHUNK) {
+            double vv[MD_CHUNK];
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) vv[q] = (c0 + q < vl.nv) ? vl.v[c0 + q][i] : 0.0;
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) if (c0 + q < vl.nv) wi = wi - hs[c0 + q] * vv[q];
+        }
+        w[i] = wi;
+        acc += wi * wi;
+    }
+    double s = block_sum(acc);
+    finish_reduction(s, partial, counter, out, pa, ep);
+}
+
 // DGKS criterion on the device: need2 = (ww_new < 0.5 * ww_old)  (Belos DGKS dep_tol = 1/sqrt(2) on the norms)
 __global__ void dgks_flag_kernel(const double* ww_old, const double* ww_new, int* flag) { *flag = (*ww_new < 0.5 * (*ww_old)) ? 1 : 0; }
 
 static P2PArgs p2p_vec_args(thcmb_ctx* c) {
-    P2PArgs pa{1, 0, nullptr, nullptr, 0ull};
+    P2PArgs pa{1, 0, nullptr, nullptr, nullptr};
     if (c->p2p_on) {
         pa.nranks = c->blk.nranks; pa.rank = c->blk.rank;
         pa.mine = (P2PSlot*)c->d_mailbox; pa.peers = (P2PSlot* const*)c->d_peer_mailboxes;
-        pa.seq = ++c->p2p_vseq;
+        pa.seq = c->d_p2p_seq + 1;
     }
     return pa;
 }
@@ -531,6 +576,18 @@ int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const doubl
     ProfScope prof_(c, KID_MULTIAXPY);
     multi_axpy_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, vl, d_h, d_skip, w);
     c->launches++;
+    return 0;
+}
+int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out) {
+    VecList vl; vl.nv = nv;
+    for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
+    { ProfScope prof_(c, KID_MULTIAXPY);
+      const int grid = std::min(ew_grid(n), RED_BLOCKS);
+      multi_axpy_dot_kernel<<<grid, RED_THREADS, 0, c->stream>>>(n, vl, d_h, d_skip, w, c->d_partial, c->d_counter, d_ww, p2p_args(c),
+                                                                 RedEpilogue{d_ww_old, d_flag_out, d_final_out}); }
+    c->launches++;
+    if (!c->p2p_on && c->blk.nranks > 1) fatal("multi_axpy_dot needs the P2P mailboxes on multi-GPU runs (THCM_P2P=1)");
     return 0;
 }
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag) {
