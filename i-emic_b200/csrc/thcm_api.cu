@@ -69,6 +69,20 @@ void build_static(thcmb_ctx* c) {
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
     upload(c->d_send_dst, c->send_dst_host); upload(c->d_send_peer, c->send_peer_host);
+    {   // boundary cells (a stencil neighbour lies in the halo) and their rows, for the SpMV split around the exchange
+        const Block& b = c->blk;
+        std::vector<unsigned char> bcell((size_t)std::max(b.ncell(), 1), 0);
+        std::vector<int> brows;
+        for (int k = 0; k < b.L; k++) for (int lj = 0; lj < b.m0; lj++) for (int li = 0; li < b.n0; li++) {
+            const bool edge = (b.halo_w && li == 0) || (b.halo_e && li == b.n0 - 1) || (b.halo_s && lj == 0) || (b.halo_n && lj == b.m0 - 1);
+            if (!edge) continue;
+            const int cell = (k * b.m0 + lj) * b.n0 + li;
+            bcell[cell] = 1;
+            for (int r = 0; r < NUN; r++) brows.push_back(NUN * cell + r);
+        }
+        c->n_brows = (int)brows.size();
+        upload(c->d_bcell, bcell); upload(c->d_brows, brows);
+    }
     if (c->d_val) cudaFree(c->d_val);
     THCM_CUDA(cudaMalloc(&c->d_val, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
     THCM_CUDA(cudaMemset(c->d_val, 0, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
@@ -126,6 +140,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) fatal("domain decomposition produced an empty block");
     THCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     THCM_CUDA(cudaEventCreate(&c->ev0)); THCM_CUDA(cudaEventCreate(&c->ev1));
+    for (auto& e : c->ev_slot) THCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     size_t nm = (size_t)s->N * s->M;
     for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
     build_grid(c);
@@ -133,6 +148,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     apply_landmask_rules(c, landm_global, false);
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
+    if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
     THCM_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 4096));
@@ -155,7 +171,7 @@ void thcmb_destroy(thcmb_ctx* c) {
     nccl_destroy(c);
     for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
                     (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)(c->halo_p2p ? nullptr : c->d_halo), (void*)c->d_sendbuf,
-                    (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter,
+                    (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter, (void*)c->d_bcell, (void*)c->d_brows,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec})
@@ -163,6 +179,7 @@ void thcmb_destroy(thcmb_ctx* c) {
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (auto e : c->ev_slot) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -231,6 +248,13 @@ long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, 
 }
 
 int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y) {
+    if (c->halo_p2p && c->blk.nranks > 1 && c->spmv_overlap) {
+        // push my boundary cells to the neighbours, run the rows that need no halo while theirs arrive, then the rest
+        halo_exchange(c, d_x, false);
+        spmv_part(c, 0, d_x, d_y);
+        halo_wait(c);
+        return spmv_part(c, 1, d_x, d_y);
+    }
     halo_exchange(c, d_x);
     return spmv(c, c->blk.ndim(), c->d_rowptr, c->d_col, c->d_val, d_x, c->d_halo, c->blk.ndim(), d_y);
 }
@@ -366,7 +390,11 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
             s[0] = beta;
             int i, space = -1;
             bool converged = false;
-            for (i = 0; i < m && iter <= maxit; i++, iter++) {
+            // ---- one Arnoldi step on the device: w = A M^-1 v_i, orthogonalised against V[0..i], V[i+1] = w / ||w||, and the
+            //      column of H copied to pinned host slot `slot` (async).  MGS follows GMRESSolver.H:177-187 statement by
+            //      statement; batched = classical Gram-Schmidt with the DGKS criterion (Belos "DGKS", Ocean.C:977-1024).
+            constexpr int S = 80, HSLOT = 256;   // batched dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] ||w||^2, [3S+1] ||w||
+            auto enqueue = [&](int i, int slot) {
                 double* w = V(i + 1);
                 if (prec) {
                     double* z = flexible ? Z(i) : tmp;
@@ -375,8 +403,8 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                 } else applyA(V(i), w);
                 n_matvec++;
                 double* dh = c->d_scalars;
+                double* hs = c->h_scalars + (size_t)slot * HSLOT;
                 if (!batched) {
-                    // MGS (GMRESSolver.H:177-181): H[k][i] = w.V[k]; w -= H[k][i] V[k]
                     // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
                     l2_persist(c, w, (size_t)n * sizeof(double));   // w is re-read and re-written by every kernel of the chain
                     dot_dev(c, n, w, V(0), dh + 0);
@@ -386,14 +414,8 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
                     l2_persist(c, nullptr, 0);
                     THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
-                    THCM_CUDA(cudaStreamSynchronize(c->stream));
-                    for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];
-                    H[i + 1][i] = c->h_scalars[i + 2];
                 } else {
-                    // batched Gram-Schmidt with the DGKS re-orthogonalisation criterion (Belos "DGKS", Ocean.C:977-1024):
-                    // pass 1: h1 = V^T w (+ w.w) in one reduction, w -= V h1; a second pass only if ||w|| dropped below
-                    // ||w_old||/sqrt(2) -- decided on the device, identically on every rank.
-                    const int nv = i + 1, S = 80;   // dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] final ||w||^2, [3S+1] ||w||
+                    const int nv = i + 1;
                     std::vector<double*> vp(nv);
                     for (int k = 0; k < nv; k++) vp[k] = V(k);
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
@@ -413,12 +435,23 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                         dot_dev(c, n, w, w, dh + 3 * S);
                     }
                     scale_invsqrt_dev(c, n, dh + 3 * S, w, dh + 3 * S + 1);
-                    THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (3 * S + 2), cudaMemcpyDeviceToHost, c->stream));
-                    THCM_CUDA(cudaMemcpyAsync(c->h_scalars + 3 * S + 2, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaMemcpyAsync(hs, dh, sizeof(double) * (3 * S + 2), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaMemcpyAsync(hs + 3 * S + 2, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                    THCM_CUDA(cudaEventRecord(c->ev_slot[slot], c->stream));
+                }
+            };
+            // ---- host part of step i: column i of H, Givens rotations, residual estimate (GMRESSolver.H:190-199)
+            auto process = [&](int i, int slot) -> bool {
+                if (!batched) {
                     THCM_CUDA(cudaStreamSynchronize(c->stream));
-                    const bool second = *reinterpret_cast<int*>(c->h_scalars + 3 * S + 2) != 0;
-                    for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k] + (second ? c->h_scalars[2 * S + k] : 0.0);
-                    H[i + 1][i] = c->h_scalars[3 * S + 1];
+                    for (int k = 0; k <= i; k++) H[k][i] = c->h_scalars[k];
+                    H[i + 1][i] = c->h_scalars[i + 2];
+                } else {
+                    const double* hs = c->h_scalars + (size_t)slot * HSLOT;
+                    THCM_CUDA(cudaEventSynchronize(c->ev_slot[slot]));
+                    const bool second = *reinterpret_cast<const int*>(hs + 3 * S + 2) != 0;
+                    for (int k = 0; k <= i; k++) H[k][i] = hs[k] + (second ? hs[2 * S + k] : 0.0);
+                    H[i + 1][i] = hs[3 * S + 1];
                     if (second) n_reorth++;
                 }
                 space = i;
@@ -428,7 +461,22 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                 app_rot(s[i], s[i + 1], cs[i], sn[i]);
                 resid = std::abs(s[i + 1]) / normb;
                 push(resid);
-                if (resid < tol) { converged = true; break; }
+                return resid < tol;
+            };
+            if (!batched) {
+                for (i = 0; i < m && iter <= maxit; i++, iter++) {
+                    enqueue(i, 0);
+                    if (process(i, 0)) { converged = true; break; }
+                }
+            } else {
+                // software-pipelined by one step: step i+1 is queued before the host waits for the scalars of step i, so the
+                // device never idles on the host's Givens update (a step queued past convergence is simply not used)
+                for (i = 0; i < m && iter <= maxit; i++, iter++) {
+                    enqueue(i, i & 1);
+                    if (i > 0 && process(i - 1, (i - 1) & 1)) { converged = true; break; }
+                }
+                if (converged) iter--;
+                else if (i > 0 && process(i - 1, (i - 1) & 1)) { converged = true; iter--; }
             }
             // Update (GMRESSolver.H:293-313, 402-410): back substitution, x += sum y_j Z_j | V_j | M^-1 V y
             y = s;

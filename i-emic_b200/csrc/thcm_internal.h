@@ -150,6 +150,9 @@ struct thcmb_ctx {
     double** d_peer_halo = nullptr;  // device array [2][npeers]: peer halo buffer base per parity
     unsigned long long halo_seq = 0;
     unsigned int* d_halo_counter = nullptr;
+    unsigned char* d_bcell = nullptr;   // per owned cell: 1 if a row of the cell can reference a halo column
+    int* d_brows = nullptr; int n_brows = 0;   // rows of those cells
+    int spmv_overlap = 1;
     struct Peer { int rank; int send_off, send_cnt, recv_off, recv_cnt; };
     std::vector<Peer> peers;
     int nsend_cells = 0, nrecv_cells = 0;
@@ -177,6 +180,7 @@ struct thcmb_ctx {
     long long launches = 0;
     std::map<std::string, double> stage_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};   // pipelined GMRES: scalars of step i have reached the host
     // optional per-kernel device timing (bench.py roofline): event pairs recorded around every launch
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
@@ -208,7 +212,9 @@ int scan_block_counts(thcmb_ctx* c);
 int asm_block_count(const Block& b);
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y);
-int halo_exchange(thcmb_ctx* c, const double* d_x);
+int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait = true);
+int halo_wait(thcmb_ctx* c);
+int spmv_part(thcmb_ctx* c, int part, const double* x, double* y);
 // vector kernels (device-scalar flavours keep the Krylov inner loops free of host syncs)
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out);
 int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);

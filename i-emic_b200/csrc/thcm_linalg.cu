@@ -21,14 +21,25 @@ constexpr int SPMV_THREADS = 256;
 // LANES lanes share a row; every lane first issues its first UNROLL (col, val) loads -- predicated, independent --
 // then the x gathers, then the products: all loads of a row are in flight together (rows are short, so a plain
 // loop exposes one memory latency per iteration and leaves the kernel latency-bound at full occupancy).
-template <int LANES, int UNROLL>
+// SEL: 0 every row; 1 rows of cells NOT flagged in `bcell` (interior rows: no halo column -- they run while the halo is
+// still in flight); 2 the rows listed in `rowlist` (rows of the boundary cells, after the halo has arrived)
+template <int LANES, int UNROLL, int SEL = 0>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
                                                                  const double* __restrict__ val, const double* __restrict__ x,
-                                                                 const double* __restrict__ halo, int nlocal, double* __restrict__ y) {
+                                                                 const double* __restrict__ halo, int nlocal, double* __restrict__ y,
+                                                                 const unsigned char* __restrict__ bcell = nullptr,
+                                                                 const int* __restrict__ rowlist = nullptr) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
-    for (int row = blockIdx.x * rows_per_block + (threadIdx.x / LANES); row < nrow; row += gridDim.x * rows_per_block) {
-        const int b = __ldg(rp + row), e = __ldg(rp + row + 1);
+    // the loop bound is warp-uniform and rows that do not take part stay in the body with an empty range: the full-mask
+    // shuffles below must be reached by every lane of the warp
+    for (int base = blockIdx.x * rows_per_block; base < nrow; base += gridDim.x * rows_per_block) {
+        const int r0 = base + (threadIdx.x / LANES);
+        bool act = r0 < nrow;
+        int row = act ? r0 : 0;
+        if constexpr (SEL == 1) act = act && __ldg(bcell + row / NUN) == 0;
+        if constexpr (SEL == 2) row = act ? __ldg(rowlist + r0) : 0;
+        const int b = act ? __ldg(rp + row) : 0, e = act ? __ldg(rp + row + 1) : 0;
         int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
@@ -50,7 +61,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
-        if (sub == 0) y[row] = s;
+        if (sub == 0 && act) y[row] = s;
     }
 }
 
@@ -58,6 +69,23 @@ static int spmv_variant() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("THCM_SPMV_VARIANT"); v = e ? atoi(e) : 2; }   // 2 = 4 lanes x 6 entries: best on B200 (profiles/)
     return v;
+}
+
+// operator application split around the halo exchange (multi-GPU): interior rows, then -- after the wait -- boundary rows
+int spmv_part(thcmb_ctx* c, int part, const double* x, double* y) {
+    ProfScope prof_(c, KID_SPMV);
+    const int n = c->blk.ndim();
+    if (part == 0) {
+        const int rows_per_block = SPMV_THREADS / 4;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)n + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
+        spmv_csr_kernel<4, 6, 1><<<grid, SPMV_THREADS, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, c->d_halo, n, y, c->d_bcell, nullptr);
+    } else if (c->n_brows > 0) {
+        const int rows_per_block = SPMV_THREADS / 4;
+        const int grid = std::max(1, (c->n_brows + rows_per_block - 1) / rows_per_block);
+        spmv_csr_kernel<4, 6, 2><<<grid, SPMV_THREADS, 0, c->stream>>>(c->n_brows, c->d_rowptr, c->d_col, c->d_val, x, c->d_halo, n, y, nullptr, c->d_brows);
+    }
+    c->launches++;
+    return 0;
 }
 
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
@@ -459,21 +487,28 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
     if (!last) return;
     // ---- last block: fixed-order sum of the per-slice partials, then the cross-GPU exchange ----
     __shared__ double mine[MD_MAXV + 1];
-    for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
-        const int col = q < nv ? q : MD_MAXV;
-        double v = 0.0;
-        if (!skipped) {
+    __shared__ double seg[3][MD_MAXV + 1];
+    // three threads per column, each summing a contiguous third of the slices with eight loads in flight; the thirds are
+    // then added in order: a fixed summation tree, identical on every launch
+    {
+        const int t3 = threadIdx.x / (MD_MAXV + 1), q = threadIdx.x - t3 * (MD_MAXV + 1);
+        if (t3 < 3 && q <= nv) {
+            const int col = q < nv ? q : MD_MAXV;
+            const int ns = (int)gridDim.x, b0 = (int)((long long)ns * t3 / 3), b1 = (int)((long long)ns * (t3 + 1) / 3);
             const volatile double* pc = partial + col;
-            int b = 0;
-            for (; b + 8 <= (int)gridDim.x; b += 8) {   // eight loads in flight, summed in slice order
-                double t0 = pc[(size_t)(b + 0) * stride], t1 = pc[(size_t)(b + 1) * stride], t2 = pc[(size_t)(b + 2) * stride], t3 = pc[(size_t)(b + 3) * stride];
+            double v = 0.0;
+            int b = b0;
+            for (; b + 8 <= b1; b += 8) {
+                double t0 = pc[(size_t)(b + 0) * stride], t1 = pc[(size_t)(b + 1) * stride], t2 = pc[(size_t)(b + 2) * stride], t3v = pc[(size_t)(b + 3) * stride];
                 double t4 = pc[(size_t)(b + 4) * stride], t5 = pc[(size_t)(b + 5) * stride], t6 = pc[(size_t)(b + 6) * stride], t7 = pc[(size_t)(b + 7) * stride];
-                v += t0; v += t1; v += t2; v += t3; v += t4; v += t5; v += t6; v += t7;
+                v += t0; v += t1; v += t2; v += t3v; v += t4; v += t5; v += t6; v += t7;
             }
-            for (; b < (int)gridDim.x; b++) v += pc[(size_t)b * stride];
+            for (; b < b1; b++) v += pc[(size_t)b * stride];
+            seg[t3][q] = v;
         }
-        mine[q] = v;
     }
+    __syncthreads();
+    for (int q = threadIdx.x; q <= nv; q += RED_THREADS) mine[q] = (seg[0][q] + seg[1][q]) + seg[2][q];
     const unsigned long long seq = pa.nranks > 1 ? *pa.seq + 1ull : 0ull;
     if (threadIdx.x == 0) *counter = 0u;
     __syncthreads();
@@ -624,18 +659,20 @@ struct HaloPeers { int n; int rank[HALO_MAX_PEERS]; unsigned char send[HALO_MAX_
 __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* __restrict__ idx, const int* __restrict__ dst_slot,
                                                          const int* __restrict__ peer, const double* __restrict__ x, double* const* peer_halo,
                                                          HaloPeers hp, int myrank, char* const* peer_base, char* my_base,
-                                                         unsigned long long seq, unsigned int* counter) {
+                                                         unsigned long long seq, unsigned int* counter, int wait) {
     __shared__ bool last;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells * (NUN / 2); t += gridDim.x * blockDim.x) {
         const int cidx = t / (NUN / 2), v = t - cidx * (NUN / 2);   // 16-byte pieces: records are 48 bytes, 16-byte aligned
         const double2 val = reinterpret_cast<const double2*>(x + (size_t)NUN * idx[cidx])[v];
         reinterpret_cast<double2*>(peer_halo[peer[cidx]] + (size_t)NUN * dst_slot[cidx])[v] = val;
     }
-    __threadfence_system();
+    // one system-scope fence per block, by the thread that has observed the whole block's stores through the barrier
+    // (fences are cumulative); a fence per thread made this kernel ~3x slower
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) { __threadfence_system(); last = atomicAdd(counter, 1u) == gridDim.x - 1; }
     __syncthreads();
     if (!last) return;
+    __threadfence_system();
     const int par = (int)(seq & 1ull);
     if (threadIdx.x < hp.n) {
         const int q = threadIdx.x;
@@ -643,13 +680,22 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
             volatile unsigned long long* f = (volatile unsigned long long*)(peer_base[hp.rank[q]] + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + myrank;
             *f = seq;
         }
-        if (hp.recv[q]) {
+        if (wait && hp.recv[q]) {
             volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[q];
             while (*f != seq) { }
         }
     }
     __threadfence_system();
     if (threadIdx.x == 0) *counter = 0u;
+}
+// second half of a split exchange: the neighbours' flags of exchange `seq` (the operator's interior rows ran meanwhile)
+__global__ void halo_wait_kernel(HaloPeers hp, char* my_base, unsigned long long seq) {
+    const int par = (int)(seq & 1ull);
+    if (threadIdx.x < hp.n && hp.recv[threadIdx.x]) {
+        volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[threadIdx.x];
+        while (*f != seq) { }
+    }
+    __threadfence_system();
 }
 
 struct Id128 { char b[128]; };  // ncclUniqueId (nccl.h: struct { char internal[128]; }), passed by value
@@ -700,20 +746,30 @@ int allreduce_dev(thcmb_ctx* c, double* d_buf, int count) {
     return g_nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_FLOAT64, NCCL_SUM, c->nccl_comm, c->stream);
 }
 
-int halo_exchange(thcmb_ctx* c, const double* d_x) {
+static HaloPeers halo_peers(const thcmb_ctx* c) {
+    HaloPeers hp; hp.n = (int)c->peers.size();
+    for (int q = 0; q < hp.n; q++) { hp.rank[q] = c->peers[q].rank; hp.send[q] = c->peers[q].send_cnt > 0; hp.recv[q] = c->peers[q].recv_cnt > 0; }
+    return hp;
+}
+int halo_wait(thcmb_ctx* c) {
+    ProfScope prof_(c, KID_HALO_UNPACK);
+    halo_wait_kernel<<<1, 32, 0, c->stream>>>(halo_peers(c), (char*)c->d_mailbox, c->halo_seq);
+    c->launches++;
+    return 0;
+}
+int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
     if (c->blk.nranks == 1) return 0;
     if (c->halo_p2p) {
         if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 8 neighbours");
         if ((((uintptr_t)d_x) & 15) != 0) fatal("halo push: vector must be 16-byte aligned");
-        HaloPeers hp; hp.n = (int)c->peers.size();
-        for (int q = 0; q < hp.n; q++) { hp.rank[q] = c->peers[q].rank; hp.send[q] = c->peers[q].send_cnt > 0; hp.recv[q] = c->peers[q].recv_cnt > 0; }
+        HaloPeers hp = halo_peers(c);
         const unsigned long long seq = ++c->halo_seq;
         const int par = (int)(seq & 1ull);
         ProfScope prof_(c, KID_HALO_PACK);
         const int grid = std::max(1, std::min(ew_grid(c->nsend_cells * (NUN / 2)), NSM));
         halo_push_kernel<<<grid, 256, 0, c->stream>>>(c->nsend_cells, c->d_send_idx, c->d_send_dst, c->d_send_peer, d_x,
                                                       c->d_peer_halo + (size_t)par * c->peers.size(), hp, c->blk.rank,
-                                                      (char* const*)c->d_peer_mailboxes, (char*)c->d_mailbox, seq, c->d_halo_counter);
+                                                      (char* const*)c->d_peer_mailboxes, (char*)c->d_mailbox, seq, c->d_halo_counter, wait ? 1 : 0);
         c->launches++;
         c->d_halo = c->d_halo_p2p[par];
         return 0;
