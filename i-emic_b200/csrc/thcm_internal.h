@@ -152,7 +152,7 @@ struct thcmb_ctx {
     unsigned int* d_halo_counter = nullptr;
     unsigned char* d_bcell = nullptr;   // per owned cell: 1 if a row of the cell can reference a halo column
     int* d_brows = nullptr; int n_brows = 0;   // rows of those cells
-    int spmv_overlap = 1;
+    int spmv_overlap = 0;               // 1: split the SpMV around the halo exchange (measured slower at 8 GPUs: two small kernels more)
     struct Peer { int rank; int send_off, send_cnt, recv_off, recv_cnt; };
     std::vector<Peer> peers;
     int nsend_cells = 0, nrecv_cells = 0;

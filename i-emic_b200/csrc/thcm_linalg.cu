@@ -672,7 +672,9 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
     if (threadIdx.x == 0) { __threadfence_system(); last = atomicAdd(counter, 1u) == gridDim.x - 1; }
     __syncthreads();
     if (!last) return;
-    __threadfence_system();
+    // every block's stores were performed at the neighbours (its system fence completed) before it bumped the counter this
+    // block has just read: the flags can follow with a device-scope fence only -- system fences cost ~5 us each here
+    __threadfence();
     const int par = (int)(seq & 1ull);
     if (threadIdx.x < hp.n) {
         const int q = threadIdx.x;
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
             while (*f != seq) { }
         }
     }
-    __threadfence_system();
+    if (wait) __threadfence_system();
     if (threadIdx.x == 0) *counter = 0u;
 }
 // second half of a split exchange: the neighbours' flags of exchange `seq` (the operator's interior rows ran meanwhile)

@@ -30,8 +30,17 @@ with open(f"profiles/launches_{tag}_summary.csv", "w") as f:
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"\"{k}\",{n},{us:.1f},{us / n:.2f},{us / tot:.4f}\n")
 # ---- full capture: the metrics the roofline discussion uses ----
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rr = list(csv.reader(raw.splitlines()))
+import glob
+rr = None
+for rep in sorted(glob.glob(f"gpurun_out/prof_{tag}*.ncu-rep")):   # one or several captures of the same round
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if rr is None:
+        rr = part
+    else:
+        pix = {c: i for i, c in enumerate(part[0])}
+        for r in part[2:]:
+            rr.append([r[pix[c]] if c in pix else "" for c in rr[0]])
 h, units = rr[0], rr[1]
 ix = {c: i for i, c in enumerate(h)}
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -47,6 +56,24 @@ for r in rr[2:]:
         continue
     out.append({"kernel": name, **{w: (r[ix[w]] + " " + units[ix[w]]) for w in want if w in ix}})
 json.dump(out, open(f"profiles/ncu_full_{tag}_summary.json", "w"), indent=1)
+# ---- DRAM traffic per launch of the kernels bench.py reports (roofline.traffic) ----
+def _num(v):
+    val, unit = v.split()[0], (v.split() + [""])[1]
+    return float(val.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+names = {"spmv_csr_kernel": "spmv_csr", "multi_dot_kernel": "multi_dot", "multi_axpy_dot_kernel": "multi_axpy", "blockdiag_apply_kernel": "blockdiag_apply",
+         "dot_kernel": "dot", "thcm_assemble_kernel<0>": "thcm_assemble<RHS>"}
+traffic = {}
+for o in out:
+    k = o["kernel"].replace("void ", "").replace("thcm::", "")
+    key = next((v for n_, v in names.items() if k.startswith(n_)), None)
+    b = _num(o["dram__bytes_read.sum"]) + _num(o["dram__bytes_write.sum"])
+    if k.startswith("thcm_jac_tma_kernel"):   # the Jacobian is two launches (row groups): sum them
+        e = traffic.setdefault("thcm_assemble<JAC_GRAPH>", {"dram_bytes": 0.0, "parts": [], "source": f"profiles/ncu_full_{tag}_summary.json"})
+        if k not in e["parts"]:
+            e["parts"].append(k); e["dram_bytes"] += b
+    elif key and key not in traffic:
+        traffic[key] = {"dram_bytes": b, "duration": o["gpu__time_duration.sum"], "source": f"profiles/ncu_full_{tag}_summary.json"}
+json.dump(traffic, open("profiles/ncu_traffic.json", "w"), indent=1)
 print(open(f"profiles/launches_{tag}_summary.csv").read())
 for o in out:
     print(o["kernel"], o["gpu__time_duration.sum"], "read", o["dram__bytes_read.sum"], "write", o["dram__bytes_write.sum"])
