@@ -134,7 +134,6 @@ void thcmb_default_settings(thcmb_settings* s) {
 
 thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     require_device(s->device);
-    if (s->vmix != 0) fatal("Mixing >= 1 (vmix_fun / vmix_jac, mix_imp.f) is not implemented on the B200 path yet; set Mixing = 0");
     thcmb_ctx* c = new thcmb_ctx();
     c->s = *s; c->device = s->device;
     if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) fatal("domain decomposition produced an empty block");
@@ -146,6 +145,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     build_grid(c);
     stpnt(c);
     apply_landmask_rules(c, landm_global, false);
+    vmix_init(c);      // usrc.F90:133
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
@@ -213,21 +213,36 @@ int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128
 int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64) { return p2p_local_handle(c, handle64); }
 int thcmb_p2p_open(thcmb_ctx* c, const void* handles_all) { return p2p_open(c, handles_all); }
 void thcmb_set_ortho(thcmb_ctx* c, int mode) { c->gmres_ortho = mode; }
+void thcmb_set_vmix_fix(thcmb_ctx* c, int fix) { c->vmix_fix = fix; }   /* m_mix::set_vmix_fix, mix.F90:52-59 */
+void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4) { out4[0] = c->vmix_flag; out4[1] = c->vmix_temp; out4[2] = c->vmix_salt; out4[3] = c->vmix_fix; }
 
 int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x) { return halo_exchange(c, d_x); }
 
+// vmix_control (mix_imp.f:139-169), called from rhs / matrix when Mixing = 2 and the partition is not fixed
+// (usrc.F90:496, 558): which of the T and S fields are non-zero decides whether their mixing terms are on
+static void vmix_control(thcmb_ctx* c, const double* d_un) {
+    if (c->vmix_flag < 2 || c->vmix_fix != 0) return;
+    double nrm2[2];
+    field_sumsq(c, d_un, nrm2);
+    vmix_set_flags(c, std::sqrt(nrm2[0]) > 1.0e-12 ? 1 : 0, std::sqrt(nrm2[1]) > 1.0e-12 ? 1 : 0);
+    compute_tables(c);   // only the mixing switches of c->tab change (kernel arguments, no upload needed)
+}
+
 int thcmb_rhs_dev(thcmb_ctx* c, const double* d_un, double* d_B) {
     c->frc_masked = true;
+    vmix_control(c, d_un);
     halo_exchange(c, d_un);
     return launch_assembly(c, MODE_RHS, d_un, d_B, nullptr, nullptr, nullptr);
 }
 int thcmb_residual_dev(thcmb_ctx* c, const double* d_un, double* d_F) {
     c->frc_masked = true;
+    vmix_control(c, d_un);
     halo_exchange(c, d_un);
     return launch_assembly(c, MODE_RHS | 0x100, d_un, d_F, nullptr, nullptr, nullptr);
 }
 int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un) {
     c->frc_masked = true;
+    vmix_control(c, d_un);
     halo_exchange(c, d_un);
     return launch_assembly(c, MODE_JAC_GRAPH, d_un, nullptr, nullptr, nullptr, nullptr);
 }
@@ -237,6 +252,7 @@ const int* thcmb_graph_col_dev(const thcmb_ctx* c) { return c->d_col; }
 
 long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, int* d_jcoA, double* d_coA) {
     c->frc_masked = true;
+    vmix_control(c, d_un);
     halo_exchange(c, d_un);
     launch_assembly(c, MODE_JAC_COUNT, d_un, nullptr, nullptr, nullptr, nullptr);
     scan_block_counts(c);
@@ -794,7 +810,7 @@ void set_landmask_(int* landm, int* periodic, int* reinit) {
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     build_static(c);
     if (g_dbeg) { cudaFree(g_dbeg); cudaFree(g_djco); cudaFree(g_dco); g_dbeg = g_djco = nullptr; g_dco = nullptr; }
-    if (*reinit == 1) refresh_params(c);
+    if (*reinit == 1) { vmix_init(c); refresh_params(c); }   // usrc.F90:410-415
     else { compute_cob(c); }
 }
 void get_forcing_(double* frc) { thcmb_get_forcing(G(), frc); }

@@ -113,7 +113,10 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
         nb = nb_in;
         cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) |
               (c.k == b.L ? 32 : 0);
-        if (!((nb >> 4) & 1u)) eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
+        if (!((nb >> 4) & 1u)) {
+            eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
+            if constexpr (MODE != MODE_RHS && (R == TT || R == SS)) vmix_jac<R>(E, a.t, c, nb, tile, SmemTabs<NSV>{&sh.in});   // usrc.F90:489-508
+        }
     }
     // open ocean away from the bottom and the lid: no LAND among the 27 (+5) neighbours of any cell of the warp, so every
     // statement of `boundaries` is a no-op -- skip its ~60 predicated blocks (warp-uniform branch)
@@ -139,7 +142,9 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
             });
             // B = -Au - mix + Frc - p0*(1-par(RESC))*ures ; B *= (1 - landm) (usrc.F90:576-591)
             int row = NUN * cell + R - 1;
-            double B = -s - 0.0 + a.frc[row] - 0.0;
+            double mixv = 0.0;
+            if constexpr (R == TT || R == SS) mixv = vmix_rhs<R>(a.t, c, nb, tile, SmemTabs<NSV>{&sh.in});   // vmix_fun, usrc.F90:551-571
+            double B = -s - mixv + a.frc[row] - 0.0;
             B = B * (((nb >> 4) & 1u) ? 0.0 : 1.0);
             a.out[row] = a.sign * B;
         }
@@ -390,6 +395,7 @@ __device__ __forceinline__ void pipe_eval(const AsmArgs& a, const ST& st, const 
     if (lane < g.ncell && !((nb >> 4) & 1u)) {
         Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
         eval_row<R, true>(E, a.t, a.b, c, sm, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
+        if constexpr (R == TT || R == SS) vmix_jac<R>(E, a.t, c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});   // usrc.F90:489-508
     }
 }
 // open_ocean / interior are TILE-uniform (descriptor flag, tile geometry): no warp votes, inactive lanes of a ragged tile

@@ -426,6 +426,103 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
 }
 
 // ---------------------------------------------------------------------------
+// Tracer mixing (mix_imp.f) with the shipped parameters (MIXP = MKAP = 0, ALPC = 1: no neutral physics, no GM, no
+// "consistent" mixing): what remains of vmix_fun is the implicit vertical mixing / convective adjustment
+//   Ftimp(k) = -tprstb(-drhodzt(k), SPL1) * P_VC * dtdzt(k)            on the top face of cell k   (mix_imp.f:489-492)
+//   mix_T    = (Ftimp(k) - Ftimp(k-1)) / (dz * dfzT(k))                                            (mix_imp.f:517-524)
+// a function of T,S in the cell and its two vertical neighbours only.  tt / ss = T, S at k-1, k, k+1 as usol leaves them;
+// oc[3] = isoc (OCEAN or PERIO) of the three cells.  Operation order follows the reference statement by statement.
+// The only transcendental is tanh: the host tests (tests/emu) run this very code with glibc's tanh and are bit-exact
+// against the oracle; on the device CUDA's tanh may differ in the last bit (see DESIGN.md for the tolerance).
+// ---------------------------------------------------------------------------
+struct MixTabs { double dfzT, dfzW, dfzWm; int k; };
+THCM_HD double mix_tprstb(double grad, double fac) {   // mix_imp.f:837-857
+    double a = -grad * fac;
+    double th = tanh(a * a * a);
+    return th > 0.0 ? th : 0.0;
+}
+// var = 4: temperature row, 5: salinity row
+THCM_HD double vmix_value(const DevTables& t, int var, const double* tt, const double* ss, const double* oc, const MixTabs& mt) {
+    if (!(var == 4 ? t.mix_temp : t.mix_salt)) return 0.0;
+    constexpr double alpt1 = 2.93, alpt2 = 8.3e-02, alpt3 = 6.6e-04;   // usr.F90:151-153
+    double rho[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+        rho[q] = t.mix_lambda * ss[q] - tt[q] - t.mix_xes * (alpt1 * tt[q] + alpt2 * tt[q] * tt[q] - alpt3 * tt[q] * tt[q] * tt[q]);
+    double Ft[2], Fs[2];   // [0]: face k-1 (below), [1]: face k (above)
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        if (f == 0 && mt.k == 1) { Ft[0] = 0.0; Fs[0] = 0.0; continue; }       // Ftimp(:,:,0) is never set
+        const double dzw = t.mix_dz * (f == 0 ? mt.dfzWm : mt.dfzW);
+        const double io = oc[f + 1] * oc[f];
+        const double drho = io * (rho[f + 1] - rho[f]) / dzw;
+        const double dtz = io * (tt[f + 1] - tt[f]) / dzw;
+        const double dsz = io * (ss[f + 1] - ss[f]) / dzw;
+        if (t.mix_kvc != 0.0) {
+            Ft[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dtz);
+            Fs[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dsz);
+        } else { Ft[f] = 0.0; Fs[f] = 0.0; }
+    }
+    double mix = 0.0;   // the zonal, meridional and explicit vertical differences are exact zeros with these parameters
+    if (var == 4) {
+        if (t.mix_rho) mix = ((Ft[1] - Ft[0]) - (Fs[1] - Fs[0]) * t.mix_lambda) / (2.0 * t.mix_dz * mt.dfzT) + mix;
+        else mix = (Ft[1] - Ft[0]) / (t.mix_dz * mt.dfzT) + mix;
+    } else {
+        if (t.mix_rho) mix = ((Fs[1] - Fs[0]) - (Ft[1] - Ft[0]) / t.mix_lambda) / (2.0 * t.mix_dz * mt.dfzT) + mix;
+        else mix = (Fs[1] - Fs[0]) / (t.mix_dz * mt.dfzT) + mix;
+    }
+    return mix;
+}
+// gathers the column and evaluates the mixing term of row R (TT or SS) of one cell; nb = the cell's neighbour mask
+template <int R, class Tile, class Tabs>
+THCM_HD double vmix_rhs(const DevTables& t, const Cell& c, uint32_t nb, const Tile& tile, const Tabs& tabs) {
+    static_assert(R == TT || R == SS, "mixing acts on the tracer rows");
+    if (!(t.mix_temp | t.mix_salt)) return 0.0;
+    double tt[3], ss[3], oc[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { tt[q] = tile(SV_T, 0, 0, q - 1); ss[q] = tile(SV_S, 0, 0, q - 1); }
+    oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = ((nb >> 4) & 1u) ? 0.0 : 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
+    const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
+    return vmix_value(t, R == TT ? 4 : 5, tt, ss, oc, mt);
+}
+// vmix_jac (mix_imp.f:729-815): forward differences, eps = 1e-8, of vmix_fun w.r.t. the T,S unknowns of the OCEAN cells
+// among the neighbours -- here k-1, k, k+1 -- added to An(loc, R, TT|SS) for loc = 14, 5, 23 BEFORE `boundaries`.
+// (The reference perturbs whole colour groups at once; no row meets two columns of a group, so the quotient is the same.)
+template <int R, class Tile, class Tabs>
+THCM_HD void vmix_jac(double* E, const DevTables& t, const Cell& c, uint32_t nb, const Tile& tile, const Tabs& tabs) {
+    static_assert(R == TT || R == SS, "mixing acts on the tracer rows");
+    if (!(R == TT ? t.mix_temp : t.mix_salt)) return;
+    if ((nb >> 4) & 1u) return;                      // rows of OCEAN cells only (vmix_el_1/2)
+    double tt[3], ss[3], oc[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { tt[q] = tile(SV_T, 0, 0, q - 1); ss[q] = tile(SV_S, 0, 0, q - 1); }
+    oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
+    const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
+    constexpr int var = R == TT ? 4 : 5;
+    const double eps = 1.0e-08;
+    const double f0 = vmix_value(t, var, tt, ss, oc, mt);
+    constexpr int locs[3] = {14, 5, 23};
+    static_for<0, 3>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        // the neighbour is a column only if it is an OCEAN cell of the domain (k-1 >= 1, k+1 <= L: the frame is LAND)
+        if (oc[q] != 0.0) {
+            if (t.mix_temp) {
+                double tp[3] = {tt[0], tt[1], tt[2]};
+                tp[q] = tt[q] + eps;
+                double d = vmix_value(t, var, tp, ss, oc, mt) - f0;
+                E[slot_of(R, locs[q], TT)] = E[slot_of(R, locs[q], TT)] + d / eps;
+            }
+            if (t.mix_salt) {
+                double sp[3] = {ss[0], ss[1], ss[2]};
+                sp[q] = ss[q] + eps;
+                double d = vmix_value(t, var, tt, sp, oc, mt) - f0;
+                E[slot_of(R, locs[q], SS)] = E[slot_of(R, locs[q], SS)] + d / eps;
+            }
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------
 // boundaries (boundary.F90:80-387) on the structural entries of row R.  Written as a transliteration
 // of the reference's statement sequence; statements that touch structurally-zero entries vanish at
 // compile time (slot_of(...) < 0).  nb: bit loc-1 = neighbour loc is LAND (bit 4: centre not OCEAN),

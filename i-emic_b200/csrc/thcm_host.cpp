@@ -357,6 +357,7 @@ void compute_tables(thcmb_ctx* c) {
         KTB(K_DFZT, k) = dfzT[k];
         KTB(K_RT, k) = s.TRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:758, tderiv(1)
         KTB(K_RS, k) = s.SRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:785, tderiv(2)
+        KTB(K_DFZW, k) = dfzW[k]; KTB(K_DFZWM, k) = dfzW[k - 1];        // dCdzt, mix_imp.f:613-641
     }
     // per-j / per-k records of the pipelined kernel: the three j-neighbour values of every j-table, all k-tables of level k
     c->jrec_host.assign((size_t)(m + 2) * J_COUNT * JREC, 0.0);
@@ -372,6 +373,36 @@ void compute_tables(thcmb_ctx* c) {
     t.cWS = lambda * Ra;                                                // usrc.F90:718
     t.c2 = Ra * xes * alpt2; t.c3 = Ra * xes * alpt3;                   // usrc.F90:862-863, 975-976
     t.tdzi2 = 1.0 / (2 * dz);                                           // tnlin(6,7)
+    // tracer mixing (vmix_fun, mix_imp.f:231-562): only the implicit vertical mixing of the shipped parameter set is built
+    const bool mix_on = c->vmix_flag >= 1 && c->vmix_dim > 0;
+    if (c->vmix_flag >= 1 && (par[MIXP] != 0.0 || par[MKAP] != 0.0 || par[ALPC] != 1.0))
+        fatal("Mixing >= 1 with MIXP != 0 (neutral physics), MKAP != 0 (Gent-McWilliams) or ALPC != 1 (consistent vertical mixing) "
+              "is not implemented on the B200 path; the shipped defaults (implicit vertical mixing / convective adjustment) are");
+    t.mix_lambda = lambda; t.mix_xes = xes; t.mix_kvc = par[P_VC]; t.mix_fac = s.alphaT * par[SPL1]; t.mix_dz = dz;
+    t.mix_temp = mix_on ? c->vmix_temp : 0; t.mix_salt = mix_on ? c->vmix_salt : 0;
+    t.mix_rho = (s.rho_mixing && xes == 0.0) ? 1 : 0;
+}
+
+// mix_imp.f:61-100 (vmix_init) with the pair count of vmix_part (mix_imp.f:171-228): mixing is applied only when the
+// pattern is non-empty, i.e. when the block owns at least one OCEAN cell
+void vmix_init(thcmb_ctx* c) {
+    const int vm = c->s.vmix;
+    if (vm < 0 || vm > 2) fatal("Mixing must be 0, 1 or 2");
+    c->vmix_flag = vm; c->vmix_fix = vm == 2 ? 0 : 1;
+    c->vmix_temp = c->vmix_salt = vm == 1 ? 1 : 0;
+    bool ocean = false;
+    for (int k = 1; k <= c->s.L && !ocean; k++) for (int j = 1; j <= c->s.M && !ocean; j++) for (int i = 1; i <= c->s.N; i++)
+        if (LM(c, i, j, k) == OCEAN) { ocean = true; break; }
+    c->vmix_dim = (vm == 1 && ocean) ? 1 : 0;
+    c->vmix_has_ocean = ocean;
+}
+// vmix_control (mix_imp.f:139-169) once the field norms are known
+void vmix_set_flags(thcmb_ctx* c, int temp, int salt) {
+    if (c->vmix_temp != temp || c->vmix_salt != salt) {
+        c->vmix_temp = temp; c->vmix_salt = salt;
+        if (c->vmix_temp != 0) c->vmix_dim = c->vmix_has_ocean ? 1 : 0;   // vmix_part (the reference tests vmix_temp twice, :163)
+    }
+    c->vmix_fix = 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ enum KT {
     K_ZT5, K_ZT14, K_ZT23,           // pv*tzz(5|14|23) at surface-mask 1
     K_DFZT,
     K_RT, K_RS,                      // (TRES*bi)*tc5, (SRES*bi)*sc5
+    K_DFZW, K_DFZWM,                 // dfzW(k), dfzW(k-1)  (tracer mixing, mix_imp.f:613-641)
     K_COUNT
 };
 
@@ -48,6 +49,10 @@ struct DevTables {
     const double* kt;  // [K_COUNT][kstride]
     int jstride, kstride;
     double epsr, dyi, cWT, cWS, c2, c3, tdzi2;
+    // tracer mixing (mix_imp.f): implicit vertical mixing / convective adjustment.  mix_temp / mix_salt = vmix_temp / vmix_salt
+    // (0 when mixing is off), mix_fac = alphaT * SPL1 (tprstb), mix_rho = rho_mixing .and. xes == 0
+    double mix_lambda, mix_xes, mix_kvc, mix_fac, mix_dz;
+    int mix_temp, mix_salt, mix_rho;
 };
 
 // ---- local block of the global grid (TRIOS_Domain.C:201-315 decomposition, global indexing kept) ----
@@ -187,7 +192,8 @@ struct thcmb_ctx {
     std::vector<int> prof_kid;
     // borrowed host CRS pointers (m_mat::set_pointers)
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
-    int vmix_fix = 1;
+    int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
+    bool vmix_has_ocean = false;
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 
@@ -201,6 +207,8 @@ void stpnt(thcmb_ctx* c);
 void apply_landmask_rules(thcmb_ctx* c, const int* landm_in, bool fix_inversion);
 void compute_forcing(thcmb_ctx* c);
 void compute_tables(thcmb_ctx* c);
+void vmix_init(thcmb_ctx* c);
+void vmix_set_flags(thcmb_ctx* c, int temp, int salt);
 void compute_cob(thcmb_ctx* c);
 const ClassTables& class_tables(int periodic);
 int halo_slot(const Block& b, int ie, int je, int k);  // extended local coords (-1..n0, -1..m0); -1 if not a halo cell
@@ -214,6 +222,7 @@ int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* va
          int nlocal, double* y);
 int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait = true);
 int halo_wait(thcmb_ctx* c);
+int field_sumsq(thcmb_ctx* c, const double* d_un, double* h_out2);   // global sum of squares of the T and S fields
 int spmv_part(thcmb_ctx* c, int part, const double* x, double* y);
 // vector kernels (device-scalar flavours keep the Krylov inner loops free of host syncs)
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out);

@@ -580,6 +580,29 @@ __global__ void __launch_bounds__(RED_THREADS) multi_axpy_dot_kernel(int n, VecL
     finish_reduction(s, partial, counter, out, pa, ep);
 }
 
+// sum of squares of the T and S fields of an interleaved state vector (vmix_control, mix_imp.f:149-155); rare (once per
+// continuation step with Mixing = 2), so plain atomics + a host read
+__global__ void field_sumsq_kernel(int ncell, const double* __restrict__ un, double* out2) {
+    double t = 0.0, s = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        const double a = un[(size_t)NUN * c + 4], b = un[(size_t)NUN * c + 5];
+        t += a * a; s += b * b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, o); s += __shfl_xor_sync(0xffffffffu, s, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out2, t); atomicAdd(out2 + 1, s); }
+}
+int field_sumsq(thcmb_ctx* c, const double* d_un, double* h_out2) {
+    double* d = c->d_scalars + 4000;
+    THCM_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(double), c->stream));
+    field_sumsq_kernel<<<NSM * 4, 256, 0, c->stream>>>(c->blk.ncell(), d_un, d);
+    c->launches++;
+    if (c->blk.nranks > 1) allreduce_dev(c, d, 2);
+    THCM_CUDA(cudaMemcpyAsync(h_out2, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // DGKS criterion on the device: need2 = (ww_new < 0.5 * ww_old)  (Belos DGKS dep_tol = 1/sqrt(2) on the norms)
 __global__ void dgks_flag_kernel(const double* ww_old, const double* ww_new, int* flag) { *flag = (*ww_new < 0.5 * (*ww_old)) ? 1 : 0; }
 

@@ -92,6 +92,7 @@ def load_library(path=None):
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
         "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]), "thcmb_set_ortho": (None, [vp, i]),
+        "thcmb_set_vmix_fix": (None, [vp, i]), "thcmb_get_vmix_flags": (None, [vp, vp]),
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
@@ -341,6 +342,15 @@ class THCM:
         dp = dx_host.data_ptr() if hasattr(dx_host, "data_ptr") else dx_host.ctypes.data
         self.L_.thcmb_newton_step(self.ctx, C.c_void_p(up), C.c_void_p(dp), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
         return res, fn.value
+
+    def set_vmix_fix(self, fix):
+        """m_mix::set_vmix_fix (THCM.C:2639-2647): 0 lets the next rhs / matrix call re-decide the Mixing = 2 partition."""
+        self.L_.thcmb_set_vmix_fix(self.ctx, int(fix))
+
+    def vmix_flags(self):
+        out = np.zeros(4, dtype=np.int32)
+        self.L_.thcmb_get_vmix_flags(self.ctx, _np_ptr(out))
+        return dict(zip(("flag", "temp", "salt", "fix"), out.tolist()))
 
     def set_ortho(self, mode):
         """Orthogonalisation of the Newton-step GMRES: 'mgs' (GMRESSolver.H) or 'dgks' (batched, Belos-style)."""

@@ -195,6 +195,10 @@ int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, doub
 
 /* orthogonalisation used by thcmb_newton_step*: 0 = modified Gram-Schmidt (GMRESSolver.H:177-181), 1 = batched DGKS */
 void thcmb_set_ortho(thcmb_ctx* c, int mode);
+/* tracer mixing (Mixing = 1, 2; mix_imp.f): m_mix::set_vmix_fix (mix.F90:52-59, THCM.C:2639-2647) and the current
+ * {vmix_flag, vmix_temp, vmix_salt, vmix_fix} */
+void thcmb_set_vmix_fix(thcmb_ctx* c, int fix);
+void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4);
 /* the same step with the state already in HBM (bench.py "value") */
 int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart,
                           int precon_kind, double* fnorm, thcmb_krylov_result* res);

@@ -54,7 +54,9 @@ def lib():
                                 ("oracle_get_grid", None, [vp] * 9), ("oracle_set_field", None, [vp, i, vp]),
                                 ("oracle_graph", i, [i, i, i, i, vp, vp]),
                                 ("oracle_scatter_to_graph", ll, [i, vp, vp, vp, vp, vp, vp]),
-                                ("oracle_spmv", None, [i, vp, vp, vp, vp, vp]), ("oracle_matavec", None, [i, vp, vp, vp, vp, vp])]:
+                                ("oracle_spmv", None, [i, vp, vp, vp, vp, vp]), ("oracle_matavec", None, [i, vp, vp, vp, vp, vp]),
+                                ("oracle_set_vmix_fix", None, [vp, i]), ("oracle_vmix_fun", None, [vp, vp, vp]),
+                                ("oracle_vmix_flags", None, [vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -109,6 +111,21 @@ class OracleTHCM:
 
     def getpar(self, idx):
         return self.L_.oracle_getpar(self.h, int(idx))
+
+    def set_vmix_fix(self, fix):
+        self.L_.oracle_set_vmix_fix(self.h, int(fix))
+
+    def vmix_flags(self):
+        out = np.zeros(4, dtype=np.int32)
+        self.L_.oracle_vmix_flags(self.h, _p(out))
+        return dict(zip(("flag", "temp", "salt", "fix"), out.tolist()))
+
+    def vmix_fun(self, un):
+        """Divergence of the diffusive tracer flux (mix_imp.f:231-562) with the current vmix_temp / vmix_salt flags."""
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        mix = np.empty(self.ndim)
+        self.L_.oracle_vmix_fun(self.h, _p(un), _p(mix))
+        return mix
 
     def rhs(self, un):
         """Fortran-sign residual B = -Au - mix + Frc (usrc.F90:523-603)."""

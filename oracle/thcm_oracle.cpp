@@ -1160,6 +1160,7 @@ struct Oracle {
         atmos_coef();
         forcing();
         lin();
+        vmix_init();   // usrc.F90:133
     }
 
     // usrc.F90:79-107 / 353-408
@@ -1180,25 +1181,255 @@ struct Oracle {
         for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++) { lm(i, j, 0) = LAND; lm(i, j, l + 1) = LAND; }
     }
 
-    // ---------------- usrc.F90:449-521 (Mixing=0 path) ----------------
+
+    // =====================================================================================
+    // Tracer mixing (mix_imp.f).  vmix_flag / vmix_temp / vmix_salt / vmix_fix as in mix_imp.f:61-100, mix.F90.
+    // =====================================================================================
+    int vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_fix = 1;
+    int vmix_dim = 0;   // number of (row, column) pairs of the mixing pattern (vmix_part): mixing is applied only when > 0
+    // mix_imp.f:171-228 with vmix_el_1/2 (mix_imp.f:860-1048): only the COUNT of pairs matters here
+    void vmix_part() {
+        long cnt = 0;
+        for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+            if (lm(i, j, k) != OCEAN) continue;
+            int tel = 0;
+            for (int dk = -1; dk <= 1; dk++) for (int dj = -1; dj <= 1; dj++) for (int di = -1; di <= 1; di++) {
+                int kind = lm(i + di, j + dj, k + dk);
+                if (kind == OCEAN || kind == PERIO) tel++;
+            }
+            if (vmix_flag == 1) cnt += 4 * tel;
+            else cnt += (long)tel * ((vmix_temp ? 1 + vmix_salt : 0) + (vmix_salt ? 1 + vmix_temp : 0));
+        }
+        vmix_dim = cnt > 0 ? 1 : 0;
+    }
+    // mix_imp.f:61-100
+    void vmix_init() {
+        if (vmix == 0) { vmix_flag = 0; vmix_fix = 1; }
+        else if (vmix == 1) { vmix_flag = 1; vmix_fix = 1; }
+        else if (vmix == 2) { vmix_flag = 2; vmix_fix = 0; }
+        else vmix_flag = -1;
+        if (vmix_flag == 1) { vmix_temp = 1; vmix_salt = 1; vmix_part(); } else { vmix_temp = 0; vmix_salt = 0; }
+    }
+    // mix_imp.f:139-169 (l2nrm, mix_sup.F90: sqrt of the sum of squares over the n*m*l field values)
+    void vmix_control(const double* un) {
+        auto l2 = [&](int XX) { double a = 0.0; for (int q = XX - 1; q < ndim; q += NUN) a += un[q] * un[q]; return std::sqrt(a); };
+        int test_temp = l2(TT) > 1.0e-12 ? 1 : 0, test_salt = l2(SS) > 1.0e-12 ? 1 : 0;
+        if (vmix_temp != test_temp || vmix_salt != test_salt) {
+            vmix_temp = test_temp; vmix_salt = test_salt;
+            if ((vmix_temp != 0) && (vmix_temp != 0)) vmix_part();   // (sic: the reference tests vmix_temp twice, mix_imp.f:163)
+        }
+        vmix_fix = 1;
+    }
+    // mix_imp.f:817-835
+    inline double isoc(int i, int j, int k) { int v = lm(i, j, k); return (v == OCEAN || v == PERIO) ? 1.0 : 0.0; }
+    // mix_imp.f:837-857
+    inline double tprstb(double grad, double spl) const {
+        double fac = alphaT * spl;
+        double a = -grad * fac;
+        return std::max(std::tanh(a * a * a), 0.0);
+    }
+    // mix_imp.f:675-727
+    void tprslp(double drdh, double& drdz, double spl, double& slp, double& tpr) const {
+        const double width = 1.0, epsln = 1.0e-20;
+        if (drdz == 0.0) drdz = epsln;
+        slp = -drdh / drdz;
+        double absslp = std::sqrt(slp * slp);
+        double delta = (r0dim / hdim) * spl;
+        double sd = width * delta;
+        if (tap == 1) { tpr = absslp > delta ? (delta / absslp) * (delta / absslp) : 1.0; }
+        else if (tap == 2) { tpr = 0.5 * (1.0 - std::tanh((absslp - delta) / sd)); }
+        else if (tap == 3) {
+            if (absslp < delta - sd && drdz < 0.0) tpr = 1.0;
+            else if (absslp >= delta - sd && absslp < delta && drdz < 0.0) { double dum = (absslp - (delta - sd)) / sd; tpr = 1.0 - 3.0 * (dum * dum) + 2.0 * (dum * dum * dum); }
+            else tpr = 0.0;
+        } else tpr = 1.0;
+    }
+    // mix_imp.f:231-562
+    void vmix_fun(const double* un, double* mix) {
+        Fields f(n, m, l);
+        usol(un, f.u, f.v, f.w, f.p, f.t, f.s);
+        Arr3 &t = f.t, &s = f.s;
+        Arr3 dtdxe(0, n, 0, m + 1, 0, l + 1), dsdxe(0, n, 0, m + 1, 0, l + 1), dtdyn(0, n + 1, 0, m, 0, l + 1), dsdyn(0, n + 1, 0, m, 0, l + 1),
+            dtdzt(0, n + 1, 0, m + 1, 0, l), dsdzt(0, n + 1, 0, m + 1, 0, l), rho(0, n + 1, 0, m + 1, 0, l + 1),
+            drhods(0, n + 1, 0, m + 1, 0, l + 1), drhodt(0, n + 1, 0, m + 1, 0, l + 1), drhodzt(0, n + 1, 0, m + 1, 0, l);
+        Arr3 Ftxe(0, n, 1, m, 1, l), Fsxe(0, n, 1, m, 1, l), Ftyn(1, n, 0, m, 1, l), Fsyn(1, n, 0, m, 1, l), Ftzt(1, n, 1, m, 0, l),
+            Fszt(1, n, 1, m, 0, l), Ftimp(1, n, 1, m, 0, l), Fsimp(1, n, 1, m, 0, l);
+        const double xes = par[NLES], lambda = par[LAMB], piso = par[MIXP] * par[PE_H], pgm = par[MKAP] * par[PE_H],
+                     eps = (1.0 - par[ALPC]) * par[ENER] * par[PE_V], kvc = par[P_VC], sp1 = par[SPL1], sp2 = par[SPL2];
+        const double epsln = 1.0e-20;
+        // mix_imp.f:564-641
+        auto dCdxt = [&](Arr3& C, Arr3& d) { for (int k = 0; k <= l + 1; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n; i++)
+            d(i, j, k) = isoc(i + 1, j, k) * isoc(i, j, k) * (C(i + 1, j, k) - C(i, j, k)) / (dx * std::cos(y[j])); };
+        auto dCdyt = [&](Arr3& C, Arr3& d) { for (int k = 0; k <= l + 1; k++) for (int j = 0; j <= m; j++) for (int i = 0; i <= n + 1; i++)
+            d(i, j, k) = isoc(i, j + 1, k) * isoc(i, j, k) * (C(i, j + 1, k) - C(i, j, k)) / dy; };
+        auto dCdzt = [&](Arr3& C, Arr3& d) { for (int k = 0; k <= l; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++)
+            d(i, j, k) = isoc(i, j, k + 1) * isoc(i, j, k) * (C(i, j, k + 1) - C(i, j, k)) / (dz * dfzW[k]); };
+        dCdxt(t, dtdxe); dCdxt(s, dsdxe); dCdyt(t, dtdyn); dCdyt(s, dsdyn); dCdzt(t, dtdzt); dCdzt(s, dsdzt);
+        for (size_t q = 0; q < rho.a.size(); q++) {
+            double tt = t.a[q];
+            rho.a[q] = lambda * s.a[q] - tt - xes * (alpt1 * tt + alpt2 * tt * tt - alpt3 * tt * tt * tt);
+            drhodt.a[q] = -1.0 - xes * (alpt1 + 2.0 * alpt2 * tt - 3.0 * alpt3 * (tt * tt));   // drhodC, mix_imp.f:643-673
+            drhods.a[q] = lambda;
+        }
+        dCdzt(rho, drhodzt);
+        const bool npgm = (piso != 0.0) || (pgm != 0.0);
+        // east-face flux of neutral physics + GM at (i,j,k) (identical statements at i = 0 and in the interior)
+        auto east_face = [&](int i, int j, int k) {
+            double dumt = 0.0, dums = 0.0;
+            for (int kr = 0; kr <= 1; kr++) for (int ip = 0; ip <= 1; ip++) {
+                double drdh = (drhodt(i + ip, j, k) * dtdxe(i, j, k) + drhods(i + ip, j, k) * dsdxe(i, j, k));
+                double drdz = (drhodt(i + ip, j, k) * dtdzt(i + ip, j, k - 1 + kr) + drhods(i + ip, j, k) * dsdzt(i + ip, j, k - 1 + kr));
+                double slp, tpr; tprslp(drdh, drdz, sp2, slp, tpr);
+                dumt = dumt + dfzW[k - 1 + kr] * (tpr * (piso) * dtdxe(i, j, k) + tpr * (piso - pgm) * slp * dtdzt(i + ip, j, k - 1 + kr));
+                dums = dums + dfzW[k - 1 + kr] * (tpr * (piso) * dsdxe(i, j, k) + tpr * (piso - pgm) * slp * dsdzt(i + ip, j, k - 1 + kr));
+            }
+            Ftxe(i, j, k) = Ftxe(i, j, k) - dumt / (4 * dfzT[k]);
+            Fsxe(i, j, k) = Fsxe(i, j, k) - dums / (4 * dfzT[k]);
+        };
+        for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) {
+            if (npgm) east_face(0, j, k);
+            for (int i = 1; i <= n; i++) {
+                if (npgm) {
+                    east_face(i, j, k);
+                    double dumt = 0.0, dums = 0.0;   // north face
+                    for (int kr = 0; kr <= 1; kr++) for (int jq = 0; jq <= 1; jq++) {
+                        double drdh = (drhodt(i, j + jq, k) * dtdyn(i, j, k) + drhods(i, j + jq, k) * dsdyn(i, j, k));
+                        double drdz = (drhodt(i, j + jq, k) * dtdzt(i, j + jq, k - 1 + kr) + drhods(i, j + jq, k) * dsdzt(i, j + jq, k - 1 + kr));
+                        double slp, tpr; tprslp(drdh, drdz, sp2, slp, tpr);
+                        dumt = dumt + dfzW[k - 1 + kr] * std::cos(y[j + jq]) * (tpr * (piso) * dtdyn(i, j, k) + tpr * (piso - pgm) * slp * dtdzt(i, j + jq, k - 1 + kr));
+                        dums = dums + dfzW[k - 1 + kr] * std::cos(y[j + jq]) * (tpr * (piso) * dsdyn(i, j, k) + tpr * (piso - pgm) * slp * dsdzt(i, j + jq, k - 1 + kr));
+                    }
+                    Ftyn(i, j, k) = Ftyn(i, j, k) - dumt / (4 * dfzT[k] * std::cos(yv[j]));
+                    Fsyn(i, j, k) = Fsyn(i, j, k) - dums / (4 * dfzT[k] * std::cos(yv[j]));
+                    dumt = 0.0; dums = 0.0;          // top face, zonal variations
+                    for (int ip = 0; ip <= 1; ip++) for (int kr = 0; kr <= 1; kr++) {
+                        double drdh = (drhodt(i, j, k + kr) * dtdxe(i - 1 + ip, j, k + kr) + drhods(i, j, k + kr) * dsdxe(i - 1 + ip, j, k + kr));
+                        double drdz = (drhodt(i, j, k + kr) * dtdzt(i, j, k) + drhods(i, j, k + kr) * dsdzt(i, j, k));
+                        double slp, tpr; tprslp(drdh, drdz, sp2, slp, tpr);
+                        dumt = dumt + (tpr * (piso) * slp * slp * dtdzt(i, j, k) + tpr * (piso + pgm) * slp * dtdxe(i - 1 + ip, j, k + kr));
+                        dums = dums + (tpr * (piso) * slp * slp * dsdzt(i, j, k) + tpr * (piso + pgm) * slp * dsdxe(i - 1 + ip, j, k + kr));
+                    }
+                    Ftzt(i, j, k) = Ftzt(i, j, k) - dumt / 4;
+                    Fszt(i, j, k) = Fszt(i, j, k) - dums / 4;
+                    dumt = 0.0; dums = 0.0;          // top face, meridional variations
+                    for (int jq = 0; jq <= 1; jq++) for (int kr = 0; kr <= 1; kr++) {
+                        double drdh = (drhodt(i, j, k + kr) * dtdyn(i, j - 1 + jq, k + kr) + drhods(i, j, k + kr) * dsdyn(i, j - 1 + jq, k + kr));
+                        double drdz = (drhodt(i, j, k + kr) * dtdzt(i, j, k) + drhods(i, j, k + kr) * dsdzt(i, j, k));
+                        double slp, tpr; tprslp(drdh, drdz, sp2, slp, tpr);
+                        dumt = dumt + (tpr * (piso) * slp * slp * dtdzt(i, j, k) + tpr * (piso + pgm) * slp * dtdyn(i, j - 1 + jq, k + kr));
+                        dums = dums + (tpr * (piso) * slp * slp * dsdzt(i, j, k) + tpr * (piso + pgm) * slp * dsdyn(i, j - 1 + jq, k + kr));
+                    }
+                    Ftzt(i, j, k) = Ftzt(i, j, k) - dumt / 4;
+                    Fszt(i, j, k) = Fszt(i, j, k) - dums / 4;
+                }
+                if (eps != 0.0) {   // consistent vertical mixing
+                    Ftzt(i, j, k) = Ftzt(i, j, k) + tprstb(drhodzt(i, j, k), sp1) * eps * dtdzt(i, j, k) / (drhodzt(i, j, k) - epsln);
+                    Fszt(i, j, k) = Fszt(i, j, k) + tprstb(drhodzt(i, j, k), sp1) * eps * dsdzt(i, j, k) / (drhodzt(i, j, k) - epsln);
+                }
+                if (kvc != 0.0) {   // implicit vertical mixing / convective adjustment
+                    Ftimp(i, j, k) = -tprstb(-drhodzt(i, j, k), sp1) * kvc * dtdzt(i, j, k);
+                    Fsimp(i, j, k) = -tprstb(-drhodzt(i, j, k), sp1) * kvc * dsdzt(i, j, k);
+                }
+            }
+        }
+        // divergence of the fluxes (mix_imp.f:495-560)
+        for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+            int row = find_row2(i, j, k, TT) - 1;
+            mix[row] = 0.0;
+            if (vmix_temp == 1) {
+                mix[row] = (Ftxe(i, j, k) - Ftxe(i - 1, j, k)) / (dx * std::cos(y[j])) + mix[row];
+                mix[row] = (Ftyn(i, j, k) * std::cos(yv[j]) - Ftyn(i, j - 1, k) * std::cos(yv[j - 1])) / (dy * std::cos(y[j])) + mix[row];
+                mix[row] = (Ftzt(i, j, k) - Ftzt(i, j, k - 1)) / (dz * dfzT[k]) + mix[row];
+                if (rho_mixing && xes == 0.0)
+                    mix[row] = ((Ftimp(i, j, k) - Ftimp(i, j, k - 1)) - (Fsimp(i, j, k) - Fsimp(i, j, k - 1)) * lambda) / (2.0 * dz * dfzT[k]) + mix[row];
+                else
+                    mix[row] = (Ftimp(i, j, k) - Ftimp(i, j, k - 1)) / (dz * dfzT[k]) + mix[row];
+            }
+            row = find_row2(i, j, k, SS) - 1;
+            mix[row] = 0.0;
+            if (vmix_salt == 1) {
+                mix[row] = (Fsxe(i, j, k) - Fsxe(i - 1, j, k)) / (dx * std::cos(y[j])) + mix[row];
+                mix[row] = (Fsyn(i, j, k) * std::cos(yv[j]) - Fsyn(i, j - 1, k) * std::cos(yv[j - 1])) / (dy * std::cos(y[j])) + mix[row];
+                mix[row] = (Fszt(i, j, k) - Fszt(i, j, k - 1)) / (dz * dfzT[k]) + mix[row];
+                if (rho_mixing && xes == 0.0)
+                    mix[row] = ((Fsimp(i, j, k) - Fsimp(i, j, k - 1)) - (Ftimp(i, j, k) - Ftimp(i, j, k - 1)) / lambda) / (2.0 * dz * dfzT[k]) + mix[row];
+                else
+                    mix[row] = (Fsimp(i, j, k) - Fsimp(i, j, k - 1)) / (dz * dfzT[k]) + mix[row];
+            }
+        }
+    }
+    // mix_imp.f:729-815: forward-difference Jacobian of vmix_fun over groups of structurally orthogonal columns
+    // (Coleman-More).  The reference colours the pattern of vmix_el_1/2 (mix_imp.f:860-1048: T,S rows of OCEAN cells x T,S
+    // unknowns of their OCEAN/PERIO neighbours among the 27) with MINPACK's DSM; since no row meets two columns of one
+    // group, fjac(row,col) = (mix(un + eps e_group)(row) - mix(un)(row)) / eps does not depend on WHICH valid colouring is
+    // used -- here: colour = (i, j, k) position modulo 3 (with extra colours closing a periodic ring) x {T,S}.
+    void vmix_jac(const double* un) {
+        const double eps = 1.0e-08;
+        std::vector<double> mix(ndim, 0.0), mixd(ndim, 0.0), und(ndim), d(ndim);
+        vmix_fun(un, mix.data());
+        auto ring = [&](int i, int nn, bool per) { if (!per || nn % 3 == 0) return (i - 1) % 3; int full = nn - nn % 3; return i <= full ? (i - 1) % 3 : 3 + (i - 1 - full); };
+        const int ci = (periodic && n % 3 != 0) ? 3 + n % 3 : 3;
+        if (periodic && n < 4 && n % 3 != 0) { fprintf(stderr, "thcm_oracle: vmix_jac needs n >= 4 on periodic grids\n"); std::abort(); }
+        for (int var = 0; var < 2; var++) for (int gk = 0; gk < 3; gk++) for (int gj = 0; gj < 3; gj++) for (int gi = 0; gi < ci; gi++) {
+            if ((var == 0 && !vmix_temp) || (var == 1 && !vmix_salt)) continue;
+            std::fill(d.begin(), d.end(), 0.0);
+            bool any = false;
+            for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+                if ((k - 1) % 3 != gk || (j - 1) % 3 != gj || ring(i, n, periodic) != gi) continue;
+                if (lm(i, j, k) != OCEAN) continue;            // only unknowns of OCEAN cells are columns (vmix_el)
+                d[find_row2(i, j, k, var == 0 ? TT : SS) - 1] = eps; any = true;
+            }
+            if (!any) continue;
+            for (int q = 0; q < ndim; q++) und[q] = un[q] + d[q];
+            vmix_fun(und.data(), mixd.data());
+            for (int q = 0; q < ndim; q++) mixd[q] = mixd[q] - mix[q];
+            // fdjs: fjac(row, col) = mixd(row) / d(col) for the columns of this group; an(s,ie,je,ix,iy,iz) += fjac
+            for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+                if (lm(i, j, k) != OCEAN) continue;            // rows of OCEAN cells only
+                for (int h = 1; h <= 27; h++) {
+                    int di = (h - 1) / 9 - 1, dj = ((h - 1) / 3) % 3 - 1, dk = (h - 1) % 3 - 1;   // any enumeration of the 27 offsets
+                    int i2 = i + di, j2 = j + dj, k2 = k + dk;
+                    int kind = lm(i2, j2, k2);
+                    if (kind == PERIO) i2 = i - di * (n - 1);
+                    else if (kind != OCEAN) continue;
+                    if (j2 < 1 || j2 > m || k2 < 1 || k2 > l || i2 < 1 || i2 > n) continue;
+                    if ((k2 - 1) % 3 != gk || (j2 - 1) % 3 != gj || ring(i2, n, periodic) != gi) continue;
+                    int loc = 1 + (dj + 1) + 3 * (di + 1) + 9 * (dk == 0 ? 0 : (dk == -1 ? 1 : 2));
+                    int je = var == 0 ? TT : SS;
+                    if (vmix_temp) An[aidx(loc, TT, je, i, j, k)] += mixd[find_row2(i, j, k, TT) - 1] / eps;
+                    if (vmix_salt) An[aidx(loc, SS, je, i, j, k)] += mixd[find_row2(i, j, k, SS) - 1] / eps;
+                }
+            }
+        }
+    }
+
+    // ---------------- usrc.F90:449-521 ----------------
     void matrix(const double* un) {
         An = Al;
         fillcolB();
         nlin_jac(un);
+        if (vmix_flag >= 1) {
+            if (vmix_fix == 0 && vmix_flag >= 2) vmix_control(un);
+            if ((vmix_temp == 1 || vmix_salt == 1) && vmix_dim > 0) vmix_jac(un);
+        }
         boundaries();
         fillcolA();
     }
 
-    // ---------------- usrc.F90:523-603 (Mixing=0 path) ----------------
+    // ---------------- usrc.F90:523-603 ----------------
     void rhs(const double* un, double* B) {
-        std::vector<double> Au(ndim);
+        std::vector<double> Au(ndim), mix(ndim, 0.0);
         An = Al;
         nlin_rhs(un);
         boundaries();
         fillcolA();
         matAvec(un, Au.data());
-        const double mix = 0.0, ures = 0.0;
-        for (int r = 0; r < ndim; r++) B[r] = -Au[r] - mix + Frc[r] - p0 * (1 - par[RESC]) * ures;
+        if (vmix_flag >= 1) {
+            if (vmix_fix == 0 && vmix_flag >= 2) vmix_control(un);
+            if ((vmix_temp == 1 || vmix_salt == 1) && vmix_dim > 0) vmix_fun(un, mix.data());
+        }
+        const double ures = 0.0;
+        for (int r = 0; r < ndim; r++) B[r] = -Au[r] - mix[r] + Frc[r] - p0 * (1 - par[RESC]) * ures;
         for (int i = 1; i <= n; i++) for (int j = 1; j <= m; j++) for (int k = 1; k <= l; k++) for (int k1 = 1; k1 <= NUN; k1++) {
             int row = find_row2(i, j, k, k1);
             B[row - 1] = B[row - 1] * (1 - lm(i, j, k));
@@ -1287,13 +1518,16 @@ void* oracle_create(int n, int m, int l, double xmin, double xmax, double ymin, 
     o->periodic = s->periodic != 0; o->ih = s->ih; o->vmix = s->vmix; o->tap = s->tap; o->rho_mixing = s->rho_mixing;
     o->coriolis_on = s->coriolis_on; o->TRES = s->TRES; o->SRES = s->SRES; o->iza = s->iza; o->ite = s->ite; o->its = s->its;
     o->coupled_T = s->coupled_T; o->coupled_S = s->coupled_S; o->forcing_type = s->forcing_type;
-    if (o->vmix != 0) { fprintf(stderr, "thcm_oracle: Mixing>=1 not restated yet (vmix must be 0)\n"); delete o; return nullptr; }
+    if (o->vmix < 0 || o->vmix > 2) { fprintf(stderr, "thcm_oracle: Mixing must be 0, 1 or 2\n"); delete o; return nullptr; }
     // init() needs n,m,l before set_landmask_raw touches lm()
     o->n = n; o->m = m; o->l = l;
     o->init(n, m, l, xmin, xmax, ymin, ymax, landm);
     return o;
 }
 void oracle_destroy(void* h) { delete (Oracle*)h; }
+void oracle_set_vmix_fix(void* h, int fix) { ((Oracle*)h)->vmix_fix = fix; }   // mix.F90:52-59
+void oracle_vmix_fun(void* h, const double* un, double* mix) { Oracle* o = (Oracle*)h; for (int q = 0; q < o->ndim; q++) mix[q] = 0.0; o->vmix_fun(un, mix); }
+void oracle_vmix_flags(void* h, int* out) { Oracle* o = (Oracle*)h; out[0] = o->vmix_flag; out[1] = o->vmix_temp; out[2] = o->vmix_salt; out[3] = o->vmix_fix; }
 int oracle_ndim(void* h) { return ((Oracle*)h)->ndim; }
 // usrc.F90:163-198
 void oracle_setpar(void* h, int idx, double val) {

@@ -35,7 +35,8 @@ def lib():
                                 ("emu_plan_sizes", None, [vp, vp, vp, vp]), ("emu_plan", None, [vp, vp, vp, vp]),
                                 ("emu_jacobian", None, [vp, vp, vp, vp]), ("emu_crs", ll, [vp, vp, vp, vp, vp, vp]),
                                 ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp]),
-                                ("emu_check_tiles", ll, [vp, vp, vp]), ("emu_fast_tiles", ll, [vp, vp])]:
+                                ("emu_check_tiles", ll, [vp, vp, vp]), ("emu_fast_tiles", ll, [vp, vp]),
+                                ("emu_vmix_control", None, [vp, i, i]), ("emu_set_vmix_fix", None, [vp, i])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -120,6 +121,12 @@ class EmuTHCM:
     def fast_tiles(self):
         tot = C.c_longlong()
         return self.L_.emu_fast_tiles(self.h, C.byref(tot)), tot.value
+
+    def vmix_control(self, un_global):
+        """vmix_control with the GLOBAL field norms (what the library all-reduces), mix_imp.f:139-169."""
+        t = np.sqrt(np.sum(np.asarray(un_global)[4::6] ** 2)) > 1.0e-12
+        s = np.sqrt(np.sum(np.asarray(un_global)[5::6] ** 2)) > 1.0e-12
+        self.L_.emu_vmix_control(self.h, int(t), int(s))
 
     def rhs(self, un, halo=None):
         un = np.ascontiguousarray(un, dtype=np.float64); h = self._halo(halo)

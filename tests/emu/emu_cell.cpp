@@ -45,7 +45,10 @@ void cell_row(const AsmArgs& a, int cell, double* E, Cell& c, int& cls, uint32_t
     nb = a.nbmask[cell];
     double sm = (double)(int)(int8_t)a.surf[lj * b.n0 + li];
     cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) | (c.k == b.L ? 32 : 0);
-    if (!((nb >> 4) & 1u)) eval_row<R, JAC>(E, a.t, a.b, c, sm, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
+    if (!((nb >> 4) & 1u)) {
+        eval_row<R, JAC>(E, a.t, a.b, c, sm, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
+        if constexpr (JAC && (R == TT || R == SS)) vmix_jac<R>(E, a.t, c, nb, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
+    }
     boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
     for (int q = 0; q < RowSlots<R>::N; q++) E[q] = std::fabs(E[q]) > DROP_TOL ? E[q] : 0.0;
 }
@@ -87,7 +90,9 @@ void rhs_row(const AsmArgs& a, int cell, double* out) {
         if (E[q] != 0.0 && inside) s = E[q] * stage_value(a, SV_RAW + col - 1, gi2, gj2, k2) + s;
     }
     int row = NUN * cell + R - 1;
-    double B = -s - 0.0 + a.frc[row] - 0.0;
+    double mixv = 0.0;
+    if constexpr (R == TT || R == SS) mixv = vmix_rhs<R>(a.t, c, nb, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
+    double B = -s - mixv + a.frc[row] - 0.0;
     B = B * (((nb >> 4) & 1u) ? 0.0 : 1.0);
     out[row] = a.sign * B;
 }
@@ -102,12 +107,15 @@ void* emu_create(const thcmb_settings* s, const int* landm) {
     if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) { delete e; return nullptr; }
     size_t nm = (size_t)s->N * s->M;
     for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
-    build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false);
+    build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false); vmix_init(c);
     build_static_host(c, e->nbmask, e->surf, e->uvlive, e->send_idx, e->recv_slot);
     compute_forcing(c); compute_tables(c); compute_cob(c);
     return e;
 }
 void emu_destroy(void* h) { delete (Emu*)h; }
+// vmix_control (mix_imp.f:139-169) on the GLOBAL field norms the caller passes in (0/1 flags), and the fix flag
+void emu_vmix_control(void* h, int temp, int salt) { thcmb_ctx* c = &((Emu*)h)->c; if (c->vmix_flag >= 2 && c->vmix_fix == 0) { vmix_set_flags(c, temp, salt); compute_tables(c); } }
+void emu_set_vmix_fix(void* h, int fix) { ((Emu*)h)->c.vmix_fix = fix; }
 void emu_set_par(void* h, int idx, double v) { thcmb_ctx* c = &((Emu*)h)->c; c->par[idx] = v; compute_forcing(c); compute_tables(c); compute_cob(c); }
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }

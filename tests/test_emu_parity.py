@@ -79,6 +79,34 @@ def test_model_flags(name, flags):
     assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
 
 
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "box_np", "global4deg"])
+@pytest.mark.parametrize("vmix,rho_mixing,xes", [(1, 0, 1.0), (1, 1, 0.0), (2, 0, 0.0)])
+def test_tracer_mixing_bit_exact(name, vmix, rho_mixing, xes):
+    """Mixing = 1, 2 (mix_imp.f: implicit vertical mixing / convective adjustment + its forward-difference Jacobian): the
+    device functions, compiled for the host with glibc's tanh, against the oracle's whole-field vmix_fun / vmix_jac."""
+    s, landm, o, e = setup(name, pars=dict(cases.DEFAULT_PARS, NLES=xes), vmix=vmix, rho_mixing=rho_mixing)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    e.vmix_control(x)
+    assert np.array_equal(o.rhs(x), e.rhs(x))             # (Mixing = 2: the oracle decides its partition inside rhs)
+    assert np.abs(o.vmix_fun(x)).max() > 0
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    bo, jo, co, _ = o.matrix(x)
+    be, je, ce = e.crs(x)
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
+
+
+def test_mixing_partition_follows_the_fields():
+    """Mixing = 2 (vmix_control, mix_imp.f:139-169): a zero temperature field switches the temperature mixing off, and --
+    because the reference only re-partitions when the TEMPERATURE flag is set (:163) -- leaves the pair count at zero."""
+    s, landm, o, e = setup("natl8", vmix=2)
+    x = cases.random_state(s, landm, scale=0.3)
+    x[4::6] = 0.0
+    e.vmix_control(x)
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert o.vmix_flags() == {"flag": 2, "temp": 0, "salt": 1, "fix": 1}
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "box_np", "box_p_open"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):

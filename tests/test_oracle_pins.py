@@ -8,7 +8,11 @@ Jacobian / residual vectors and cannot be built here, so these known-answer chec
   * salt conservation: S-column integrals of J = 0   test_ocean.C:242-316, thcm_utils.F90:285-309
   * salt advection integral = 0                      integrals.F90:17-51, test_ocean.C:247-252
   * every Fortran CRS entry lies in the maximal graph, row lengths 24/22/7/11/20/20   THCM.C:2320-2325, 2354-2549
+  * the converged state the reference ships for its own regression test (test/ocean/ocean_reference.h5, Mixing = 2)
+    is a root of the restated F to Newton accuracy                                   src/tests/reft_ocean.C:59-89
+  * tracer mixing conserves heat and salt column by column; FD-vs-Jacobian with mixing on          mix_imp.f:231-562
 """
+import os
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -191,3 +195,70 @@ def test_identity_rows_on_land_and_walls():
                 for v in ident:
                     row = J.getrow(r0 + v)
                     assert row.nnz == 1 and row.indices[0] == r0 + v and row.data[0] == 1.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own converged state (reft_ocean: 16x16x16, periodic, mask_gateway, Mixing = 2, continuation in
+# "Combined Forcing" to 0.02 with Newton tolerance 1e-2; test/ocean/reft_ocean_params.xml, reft_continuation_params.xml).
+# tests/golden/ocean_reference_state.f64 = the `State` dataset of test/ocean/ocean_reference.h5
+# (tests/golden/extract_reference_state.py).  A state PRODUCED BY THE REFERENCE must be a root of the restated residual.
+# ------------------------------------------------------------------------------------------------------------------
+def reft_case(vmix=2):
+    s = cases.Settings.from_degrees(16, 16, 16, 300, 340, 20, 60, periodic=True, hdim=4000.0, qz=1.0, vmix=vmix, forcing_type=2)
+    mask = cases.read_mask(os.path.join(cases.MASKS, "mask_gateway"), 16, 16, 16)
+    pars = {"COMB": 0.02, "SUNP": 0.0, "SALT": 0.1, "WIND": 1.0, "TEMP": 10.0, "SPL1": 2.0e3, "SPL2": 0.01}
+    state = np.fromfile(os.path.join(cases.ROOT, "tests", "golden", "ocean_reference_state.f64"), dtype="<f8")
+    return s, mask, pars, state
+
+
+def test_reference_converged_state_is_a_root_of_the_oracle():
+    s, mask, pars, state = reft_case()
+    _, _, o = make((s, mask), pars)
+    # per-field 2-norms the reference test itself checks (reft_ocean.C:59-89, tolerance 1e-3)
+    want = [0.0979069, 0.0224030, 0.3858530, 0.0346863, 3.5162058, 0.0351621]
+    assert np.allclose([np.linalg.norm(state[q::6]) for q in range(6)], want, atol=1e-6)
+    Fx, F0 = o.rhs(state), o.rhs(np.zeros(o.ndim))
+    # measured: |F(x*)| = 1.8e-4 against |F(0)| = 19.8 (the continuation's Newton tolerance is 1e-2)
+    assert np.linalg.norm(Fx) < 1e-4 * np.linalg.norm(F0)
+    # momentum, continuity and hydrostatic rows are converged far below the tracer rows: a tight pin of lin / nlin_rhs /
+    # boundaries / forcing for u, v, w, p
+    for q, tol in ((0, 1e-6), (1, 1e-9), (2, 1e-8), (3, 1e-12)):
+        assert np.linalg.norm(Fx[q::6]) < tol
+    # without the mixing term the same state is NOT a root (850x larger residual): the pin covers vmix_fun
+    _, _, o0 = make(reft_case(vmix=0)[:2], pars)
+    assert np.linalg.norm(o0.rhs(state)) > 500 * np.linalg.norm(Fx)
+    assert o.vmix_flags() == {"flag": 2, "temp": 1, "salt": 1, "fix": 1}
+
+
+MIX_CASES = {"natl8": cases.natl8, "gateway16": cases.gateway16,
+             "box_p": lambda **kw: cases.box(7, 6, 5, True, seed=3, land_frac=0.3, **kw)}
+
+
+@pytest.mark.parametrize("name", list(MIX_CASES))
+@pytest.mark.parametrize("rho_mixing", [0, 1])
+def test_mixing_conserves_heat_and_salt_per_column(name, rho_mixing):
+    """Vertical mixing moves tracer between the cells of a column only: sum_k mix(i,j,k) dfzT(k) = (F(l) - F(0)) / dz = 0."""
+    s, landm, o = make(MIX_CASES[name], dict(cases.DEFAULT_PARS, NLES=0.0), vmix=1, rho_mixing=rho_mixing)
+    x = cases.random_state(s, landm, scale=0.3)
+    mix = o.vmix_fun(x).reshape(s.L, s.M, s.N, 6)
+    dfzT = o.grid()["dfzT"][1:]
+    assert np.abs(mix[..., :4]).max() == 0.0
+    assert np.abs(mix[..., 4:]).max() > 1.0
+    for q in (4, 5):
+        col = (mix[..., q] * dfzT[:, None, None]).sum(axis=0)
+        assert np.abs(col).max() < 1e-10 * np.abs(mix[..., q]).max()
+
+
+@pytest.mark.parametrize("name", list(MIX_CASES))
+def test_fd_jacobian_with_mixing(name):
+    """J (incl. the forward-difference mixing block, eps = 1e-8) against central differences of F on the constraint manifold."""
+    s, landm, o = make(MIX_CASES[name], dict(cases.DEFAULT_PARS, NLES=1.0), vmix=1)
+    d = cases.dirichlet_mask(s, landm)
+    x = cases.random_state(s, landm, scale=0.3); x[d] = 0.0
+    J, _ = csr_from_fortran(o, x)
+    v = np.random.default_rng(1).standard_normal(o.ndim); v[d] = 0.0
+    h = 1e-6
+    fd = (F(o, x + h * v) - F(o, x - h * v)) / (2 * h)
+    assert np.linalg.norm(J @ v - fd) < 1e-5 * np.linalg.norm(fd)
+    val, missing = o.jacobian_graph(x)
+    assert missing == 0      # the mixing entries (T,S at k-1, k, k+1) lie inside the maximal graph
