@@ -485,6 +485,26 @@ THCM_HD double vmix_rhs(const DevTables& t, const Cell& c, uint32_t nb, const Ti
     const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
     return vmix_value(t, R == TT ? 4 : 5, tt, ss, oc, mt);
 }
+// one column pair of the forward-difference block: T and S of the cell at vertical offset Q-1 (stencil position LOC)
+template <int R, int LOC, int Q>
+THCM_HD void vmix_fd_one(double* E, const DevTables& t, int var, double f0, const double* tt, const double* ss, const double* oc,
+                         const MixTabs& mt) {
+    const double eps = 1.0e-08;
+    // the neighbour is a column only if it is an OCEAN cell of the domain (k-1 >= 1, k+1 <= L: the frame is LAND)
+    if (oc[Q] == 0.0) return;
+    if (t.mix_temp) {
+        double tp[3] = {tt[0], tt[1], tt[2]};
+        tp[Q] = tt[Q] + eps;
+        const double d = vmix_value(t, var, tp, ss, oc, mt) - f0;
+        entref<R, LOC, TT>(E) = entref<R, LOC, TT>(E) + d / eps;
+    }
+    if (t.mix_salt) {
+        double sp[3] = {ss[0], ss[1], ss[2]};
+        sp[Q] = ss[Q] + eps;
+        const double d = vmix_value(t, var, tt, sp, oc, mt) - f0;
+        entref<R, LOC, SS>(E) = entref<R, LOC, SS>(E) + d / eps;
+    }
+}
 // vmix_jac (mix_imp.f:729-815): forward differences, eps = 1e-8, of vmix_fun w.r.t. the T,S unknowns of the OCEAN cells
 // among the neighbours -- here k-1, k, k+1 -- added to An(loc, R, TT|SS) for loc = 14, 5, 23 BEFORE `boundaries`.
 // (The reference perturbs whole colour groups at once; no row meets two columns of a group, so the quotient is the same.)
@@ -499,27 +519,10 @@ THCM_HD void vmix_jac(double* E, const DevTables& t, const Cell& c, uint32_t nb,
     oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
     const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
     constexpr int var = R == TT ? 4 : 5;
-    const double eps = 1.0e-08;
     const double f0 = vmix_value(t, var, tt, ss, oc, mt);
-    constexpr int locs[3] = {14, 5, 23};
-    static_for<0, 3>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        // the neighbour is a column only if it is an OCEAN cell of the domain (k-1 >= 1, k+1 <= L: the frame is LAND)
-        if (oc[q] != 0.0) {
-            if (t.mix_temp) {
-                double tp[3] = {tt[0], tt[1], tt[2]};
-                tp[q] = tt[q] + eps;
-                double d = vmix_value(t, var, tp, ss, oc, mt) - f0;
-                E[slot_of(R, locs[q], TT)] = E[slot_of(R, locs[q], TT)] + d / eps;
-            }
-            if (t.mix_salt) {
-                double sp[3] = {ss[0], ss[1], ss[2]};
-                sp[q] = ss[q] + eps;
-                double d = vmix_value(t, var, tt, sp, oc, mt) - f0;
-                E[slot_of(R, locs[q], SS)] = E[slot_of(R, locs[q], SS)] + d / eps;
-            }
-        }
-    });
+    vmix_fd_one<R, 14, 0>(E, t, var, f0, tt, ss, oc, mt);
+    vmix_fd_one<R, 5, 1>(E, t, var, f0, tt, ss, oc, mt);
+    vmix_fd_one<R, 23, 2>(E, t, var, f0, tt, ss, oc, mt);
 }
 
 // ---------------------------------------------------------------------------
