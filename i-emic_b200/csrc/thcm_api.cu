@@ -213,6 +213,43 @@ int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128
 int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64) { return p2p_local_handle(c, handle64); }
 int thcmb_p2p_open(thcmb_ctx* c, const void* handles_all) { return p2p_open(c, handles_all); }
 void thcmb_set_ortho(thcmb_ctx* c, int mode) { c->gmres_ortho = mode; }
+/* THCM::RecomputeScaling (THCM.C:1781-1834): average diagonal block of the stored Jacobian (device reduction), summed over the
+ * ranks and divided by their number, m_scaling::compute, inverted into Trilinos' convention, T and S scaled alike */
+int thcmb_recompute_scaling(thcmb_ctx* c, double* row_scaling, double* col_scaling, double* db36_out) {
+    double ldb[36], gdb[36];
+    average_block(c, ldb);
+    memcpy(gdb, ldb, sizeof(gdb));
+    if (c->blk.nranks > 1) {
+        double* d = c->d_scalars + 3900;
+        THCM_CUDA(cudaMemcpyAsync(d, ldb, sizeof(ldb), cudaMemcpyHostToDevice, c->stream));
+        allreduce_dev(c, d, 36);
+        THCM_CUDA(cudaMemcpyAsync(gdb, d, sizeof(gdb), cudaMemcpyDeviceToHost, c->stream));
+        THCM_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    for (int q = 0; q < 36; q++) gdb[q] /= c->blk.nranks;
+    if (db36_out) memcpy(db36_out, gdb, sizeof(gdb));
+    const int n = c->blk.ndim();
+    const bool ok = scaling_compute(c, gdb, row_scaling, col_scaling);
+    for (int i = 0; i < n; i++) { row_scaling[i] = 1.0 / row_scaling[i]; col_scaling[i] = 1.0 / col_scaling[i]; }
+    for (int i = TT - 1; i < n; i += NUN) {
+        double mean = 0.5 * (row_scaling[i] + row_scaling[i + 1]);
+        row_scaling[i] = mean; row_scaling[i + 1] = mean;
+        mean = 0.5 * (col_scaling[i] + col_scaling[i + 1]);
+        col_scaling[i] = mean; col_scaling[i + 1] = mean;
+    }
+    return ok ? 0 : 1;
+}
+/* THCM::getIntCondCoeff (THCM.C:2608-2637): coefficients of the salinity integral condition on the owned S rows (0 elsewhere);
+ * returns their 1-norm = the local part of the total volume */
+double thcmb_intcond_coeff(const thcmb_ctx* c, double* coeff) {
+    const int n = c->blk.ndim();
+    for (int i = 0; i < n; i++) coeff[i] = 0.0;
+    std::vector<double> val((size_t)c->blk.ncell()); std::vector<int> ind((size_t)c->blk.ncell());
+    const int len = intcond_scaling(c, val.data(), ind.data());
+    double vol = 0.0;
+    for (int q = 0; q < len; q++) { coeff[ind[q] - 1] = val[q]; vol += std::fabs(val[q]); }
+    return vol;
+}
 void thcmb_set_vmix_fix(thcmb_ctx* c, int fix) { c->vmix_fix = fix; }   /* m_mix::set_vmix_fix, mix.F90:52-59 */
 void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4) { out4[0] = c->vmix_flag; out4[1] = c->vmix_temp; out4[2] = c->vmix_salt; out4[3] = c->vmix_fix; }
 
@@ -820,5 +857,9 @@ void __m_inserts_MOD_insert_tauy(double* f) { insert_field(G()->tauy, f); }
 void __m_inserts_MOD_insert_atmosphere_t(double* f) { insert_field(G()->tatm, f); }
 void __m_inserts_MOD_insert_emip(double* f) { insert_field(G()->emip, f); }
 void __m_mix_MOD_set_vmix_fix(int* fix) { G()->vmix_fix = *fix; }
+/* m_scaling (scaling.F90:29-105) on the Jacobian of the last matrix_ call, m_thcm_utils::intcond_scaling (thcm_utils.F90:285-309) */
+void __m_scaling_MOD_average_block(double* db) { average_block(G(), db); }
+void __m_scaling_MOD_compute(double* db, double* rowscales, double* colscales) { scaling_compute(G(), db, rowscales, colscales); }
+void __m_thcm_utils_MOD_intcond_scaling(double* values, int* indices, int* len) { *len = intcond_scaling(G(), values, indices); }
 
 }  // extern "C"

@@ -465,6 +465,83 @@ static int owner_of(const Block& me, int gi, int gj) {
     return pm * me.npN + pn;
 }
 
+// ---------------------------------------------------------------------------------------------
+// THCM row / column scaling (scaling.F90:70-279, the LAPACK variant that is compiled): inverse of the average diagonal
+// block (dgetrf + dgetri there; Gauss-Jordan with partial pivoting here, equal up to rounding), then the "special for
+// oceanography" formulas.  Setup frequency (once per preconditioner build), plain host code.
+// ---------------------------------------------------------------------------------------------
+static bool scaling_scal(double* mat /* (6,6) column-major: in the block, out its inverse */, double* dr, double* dc) {
+    auto M = [&](int i, int j) -> double& { return mat[(i - 1) + NUN * (j - 1)]; };
+    double Anorm = 0.0;
+    for (int i = 1; i <= NUN; i++) { double r = 0.0; for (int j = 1; j <= NUN; j++) r += std::fabs(M(i, j)); Anorm = std::max(Anorm, r); }
+    double a[36], inv[36];
+    memcpy(a, mat, sizeof(a));
+    for (int q = 0; q < 36; q++) inv[q] = 0.0;
+    for (int i = 0; i < NUN; i++) inv[i + NUN * i] = 1.0;
+    auto A = [&](int i, int j) -> double& { return a[i + NUN * j]; };
+    auto B = [&](int i, int j) -> double& { return inv[i + NUN * j]; };
+    bool singular = false;
+    for (int p = 0; p < NUN && !singular; p++) {
+        int piv = p; double best = std::fabs(A(p, p));
+        for (int r = p + 1; r < NUN; r++) if (std::fabs(A(r, p)) > best) { best = std::fabs(A(r, p)); piv = r; }
+        if (best == 0.0) { singular = true; break; }
+        if (piv != p) for (int j = 0; j < NUN; j++) { std::swap(A(p, j), A(piv, j)); std::swap(B(p, j), B(piv, j)); }
+        double d = 1.0 / A(p, p);
+        for (int j = 0; j < NUN; j++) { A(p, j) *= d; B(p, j) *= d; }
+        for (int r = 0; r < NUN; r++) if (r != p) { double f = A(r, p); if (f != 0.0) for (int j = 0; j < NUN; j++) { A(r, j) -= f * A(p, j); B(r, j) -= f * B(p, j); } }
+    }
+    double inorm = 0.0;
+    for (int i = 0; i < NUN; i++) { double r = 0.0; for (int j = 0; j < NUN; j++) r += std::fabs(B(i, j)); inorm = std::max(inorm, r); }
+    const double rcond = singular ? 0.0 : 1.0 / (Anorm * inorm);
+    if (1.0 + rcond == 1.0) return false;    // "diagonal block is singular up to working precision" (scaling.F90:222-225)
+    memcpy(mat, inv, sizeof(inv));
+    dr[0] = 1.0; dc[0] = 1.0;
+    double idc = std::sqrt(M(1, 1) / M(2, 2));
+    dr[1] = 1 / idc; dc[1] = dr[1];
+    double idr = std::sqrt(std::fabs(M(1, 1) / M(4, 4)));
+    dr[3] = 1 / idr; dc[3] = dr[3];
+    if (std::fabs(M(4, 3)) > std::fabs(M(3, 3))) idr = M(1, 1) / (idr * M(4, 3));
+    else idr = std::sqrt(std::fabs(M(1, 1) / M(3, 3)));
+    dr[2] = 2 / idr; dc[2] = dr[2];
+    if (std::fabs(M(4, 5) * M(5, 4)) < .01 * std::fabs(M(4, 4) * M(5, 5))) { M(4, 5) = 1; M(5, 4) = 1; }
+    idc = std::sqrt(std::fabs(M(1, 1) * M(4, 5) / (M(5, 4) * M(5, 5))));
+    idr = M(1, 1) / (idc * M(5, 5));
+    dr[4] = 1 / idr; dc[4] = 1 / idc;
+    if (std::fabs(M(4, 6) * M(6, 4)) < .01 * std::fabs(M(4, 4) * M(6, 6))) { M(4, 6) = 1; M(6, 4) = 1; }
+    idc = std::sqrt(std::fabs(M(1, 1) * M(4, 6) / (M(6, 4) * M(6, 6))));
+    idr = M(1, 1) / (idc * M(6, 6));
+    dr[5] = 1 / idr; dc[5] = 1 / idc;
+    return true;
+}
+// m_scaling::compute (scaling.F90:70-105) for the owned rows of this block
+bool scaling_compute(const thcmb_ctx* c, const double* db36, double* row_scaling, double* col_scaling) {
+    double db[36], rs[NUN], cs[NUN];
+    memcpy(db, db36, sizeof(db));
+    for (int q = 0; q < NUN; q++) { rs[q] = 1.0; cs[q] = 1.0; }
+    const bool ok = scaling_scal(db, rs, cs);
+    const Block& b = c->blk;
+    thcmb_ctx* cc = const_cast<thcmb_ctx*>(c);
+    for (int k = 0; k < b.L; k++) for (int lj = 0; lj < b.m0; lj++) for (int li = 0; li < b.n0; li++) {
+        const bool oc = LM(cc, b.i0 + li + 1, b.j0 + lj + 1, k + 1) == OCEAN;
+        const size_t cell = ((size_t)k * b.m0 + lj) * b.n0 + li;
+        for (int q = 0; q < NUN; q++) { row_scaling[cell * NUN + q] = oc ? rs[q] : 1.0; col_scaling[cell * NUN + q] = oc ? cs[q] : 1.0; }
+    }
+    return ok;
+}
+// m_thcm_utils::intcond_scaling (thcm_utils.F90:285-309): cos(y_j) dfzT_k on the S rows of the owned OCEAN cells, 1-based LOCAL rows
+int intcond_scaling(const thcmb_ctx* c, double* val, int* ind) {
+    const Block& b = c->blk;
+    thcmb_ctx* cc = const_cast<thcmb_ctx*>(c);
+    int v = 0;
+    for (int k = 0; k < b.L; k++) for (int lj = 0; lj < b.m0; lj++) for (int li = 0; li < b.n0; li++) {
+        if (LM(cc, b.i0 + li + 1, b.j0 + lj + 1, k + 1) != OCEAN) continue;
+        val[v] = std::cos(c->y[b.j0 + lj + 1]) * c->dfzT[k + 1];
+        ind[v] = NUN * (((k * b.m0) + lj) * b.n0 + li) + SS;
+        v++;
+    }
+    return v;
+}
+
 DevBlock dev_block(const Block& b) {
     return DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
 }

@@ -251,6 +251,9 @@ int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, doub
 int copy(thcmb_ctx* c, int n, const double* x, double* y);
 int fill(thcmb_ctx* c, int n, double a, double* x);
 int build_blockdiag(thcmb_ctx* c);
+int average_block(thcmb_ctx* c, double* db36);
+bool scaling_compute(const thcmb_ctx* c, const double* db36, double* row_scaling, double* col_scaling);
+int intcond_scaling(const thcmb_ctx* c, double* val, int* ind);
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
 double* pool_vec(thcmb_ctx* c, size_t idx);
 }  // namespace thcm

@@ -864,6 +864,66 @@ __global__ void blockdiag_apply_kernel(int ncell, const double* __restrict__ min
     for (int q = 0; q < NUN; q++) s += M[q] * xc[q];
     y[t] = s;
 }
+// m_scaling::average_block (scaling.F90:29-64): sum of the in-cell 6x6 blocks of the Jacobian over the OCEAN cells (+ their
+// count).  Per-block partials in a fixed reduction tree; the host adds the partials in block order (setup frequency).
+constexpr int AVG_THREADS = 128;
+__global__ void __launch_bounds__(AVG_THREADS) average_block_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col,
+                                                                     const double* __restrict__ val, const uint32_t* __restrict__ nbmask,
+                                                                     double* __restrict__ partial /* [grid][37] */) {
+    __shared__ double wsum[AVG_THREADS / 32][37];
+    double A[NUN * NUN + 1];
+#pragma unroll
+    for (int q = 0; q <= NUN * NUN; q++) A[q] = 0.0;
+    for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncell; cell += gridDim.x * blockDim.x) {
+        if ((nbmask[cell] >> 4) & 1u) continue;            // landm(ix,iy,iz) == OCEAN only
+        A[NUN * NUN] += 1.0;
+        for (int r = 0; r < NUN; r++) {
+            const int row = NUN * cell + r;
+            for (int q = rp[row]; q < rp[row + 1]; q++) {
+                const int cc = col[q] - NUN * cell;
+                if (cc >= 0 && cc < NUN) {
+#pragma unroll
+                    for (int r2 = 0; r2 < NUN; r2++)
+#pragma unroll
+                        for (int c2 = 0; c2 < NUN; c2++) if (r2 == r && c2 == cc) A[r2 * NUN + c2] += val[q];
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q <= NUN * NUN; q++) {
+        double v = A[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NUN * NUN) {
+        double v = 0.0;
+        for (int w = 0; w < AVG_THREADS / 32; w++) v += wsum[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * 37 + threadIdx.x] = v;
+    }
+}
+// db[(ii-1) + 6*(jj-1)] (Fortran layout) = local average block, as the reference's average_block leaves it
+int average_block(thcmb_ctx* c, double* db36) {
+    const int ncell = c->blk.ncell();
+    const int grid = std::max(1, std::min((ncell + AVG_THREADS - 1) / AVG_THREADS, NSM * 4));
+    double* d_part = nullptr;
+    THCM_CUDA(cudaMalloc(&d_part, sizeof(double) * 37 * (size_t)grid));
+    average_block_kernel<<<grid, AVG_THREADS, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_nbmask, d_part);
+    c->launches++;
+    std::vector<double> part((size_t)37 * grid);
+    THCM_CUDA(cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_part);
+    double sum[37];
+    for (int q = 0; q < 37; q++) { sum[q] = 0.0; for (int b = 0; b < grid; b++) sum[q] += part[(size_t)b * 37 + q]; }
+    const double nl = sum[36];
+    for (int r = 0; r < NUN; r++) for (int cc = 0; cc < NUN; cc++) db36[r + NUN * cc] = nl > 0 ? sum[r * NUN + cc] / nl : 0.0;
+    return 0;
+}
+
 int build_blockdiag(thcmb_ctx* c) {
     int ncell = c->blk.ncell();
     if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));

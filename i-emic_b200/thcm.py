@@ -93,6 +93,7 @@ def load_library(path=None):
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
         "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]), "thcmb_set_ortho": (None, [vp, i]),
         "thcmb_set_vmix_fix": (None, [vp, i]), "thcmb_get_vmix_flags": (None, [vp, vp]),
+        "thcmb_recompute_scaling": (i, [vp, vp, vp, vp]), "thcmb_intcond_coeff": (d, [vp, vp]),
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
@@ -343,6 +344,19 @@ class THCM:
         self.L_.thcmb_newton_step(self.ctx, C.c_void_p(up), C.c_void_p(dp), tol, maxit, restart, precon, C.byref(fn), C.byref(res))
         return res, fn.value
 
+    def recomputeScaling(self):
+        """THCM::RecomputeScaling (THCM.C:1781-1834) on the stored Jacobian: (rowScaling, colScaling, averaged 6x6 block)."""
+        self._pre()
+        rs, cs, db = np.empty(self.ndim), np.empty(self.ndim), np.empty(36)
+        rc = self.L_.thcmb_recompute_scaling(self.ctx, _np_ptr(rs), _np_ptr(cs), _np_ptr(db))
+        return rs, cs, db.reshape(6, 6).T.copy(), rc == 0
+
+    def getIntCondCoeff(self):
+        """THCM::getIntCondCoeff (THCM.C:2608-2637): (coefficient vector on the owned rows, local volume)."""
+        coeff = np.empty(self.ndim)
+        vol = self.L_.thcmb_intcond_coeff(self.ctx, _np_ptr(coeff))
+        return coeff, vol
+
     def set_vmix_fix(self, fix):
         """m_mix::set_vmix_fix (THCM.C:2639-2647): 0 lets the next rhs / matrix call re-decide the Mixing = 2 partition."""
         self.L_.thcmb_set_vmix_fix(self.ctx, int(fix))
@@ -528,6 +542,25 @@ class FortranABI:
         f = np.empty(self.ndim)
         self.L_.get_forcing_(_np_ptr(f))
         return f
+
+    def average_block(self):
+        """m_scaling::average_block on the Jacobian of the last matrix_ call (THCM.C:1798); (6,6) [row, col]."""
+        db = np.zeros(36)
+        getattr(self.L_, "__m_scaling_MOD_average_block")(_np_ptr(db))
+        return db.reshape(6, 6).T.copy()
+
+    def compute_scaling(self, db):
+        """m_scaling::compute (THCM.C:1807)."""
+        dbf = np.ascontiguousarray(np.asarray(db, dtype=np.float64).T).reshape(-1)
+        rs, cs = np.empty(self.ndim), np.empty(self.ndim)
+        getattr(self.L_, "__m_scaling_MOD_compute")(_np_ptr(dbf), _np_ptr(rs), _np_ptr(cs))
+        return rs, cs
+
+    def intcond_scaling(self):
+        """m_thcm_utils::intcond_scaling (THCM.C:2619)."""
+        val = np.empty(self.ndim // 6); ind = np.empty(self.ndim // 6, dtype=np.int32); n = C.c_int()
+        getattr(self.L_, "__m_thcm_utils_MOD_intcond_scaling")(_np_ptr(val), _np_ptr(ind), C.byref(n))
+        return val[:n.value].copy(), ind[:n.value].copy()
 
     def finalize(self):
         self.L_.finalize_()

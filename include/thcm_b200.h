@@ -74,6 +74,14 @@ void __m_inserts_MOD_insert_atmosphere_t(double* f);
 void __m_inserts_MOD_insert_emip(double* f);
 /* replaces m_mix::set_vmix_fix, src/ocean/mix.F90:52-59 */
 void __m_mix_MOD_set_vmix_fix(int* fix);
+/* replace m_scaling::average_block / compute (src/ocean/scaling.F90:29-105; THCM.C:106-107, 1798-1807): the local average
+ * 6x6 diagonal block of the Jacobian of the last matrix_ call over the OCEAN cells, db(nun,nun) column-major; and the THCM
+ * row / column scaling vectors built from the (globally averaged) block */
+void __m_scaling_MOD_average_block(double* db);
+void __m_scaling_MOD_compute(double* db, double* rowscales, double* colscales);
+/* replaces m_thcm_utils::intcond_scaling (src/ocean/thcm_utils.F90:285-309; THCM.C:119, 2619): cos(y_j) dfzT_k on the S rows
+ * of the OCEAN cells (1-based local row ids) */
+void __m_thcm_utils_MOD_intcond_scaling(double* values, int* indices, int* len);
 
 /* Callbacks the reference's Fortran calls back into C++ (THCM.C:2653,2690; GlobalDefinitions.C:145,154).
  * When the library is linked against the reference these resolve to its definitions; standalone,
@@ -198,6 +206,12 @@ void thcmb_set_ortho(thcmb_ctx* c, int mode);
 /* tracer mixing (Mixing = 1, 2; mix_imp.f): m_mix::set_vmix_fix (mix.F90:52-59, THCM.C:2639-2647) and the current
  * {vmix_flag, vmix_temp, vmix_salt, vmix_fix} */
 void thcmb_set_vmix_fix(thcmb_ctx* c, int fix);
+/* THCM::RecomputeScaling (THCM.C:1781-1834) on the stored Jacobian: host vectors of ndim_local entries in Trilinos' convention
+ * (the inverse of THCM's), T and S scaled alike; db36_out (optional) = the averaged block, column-major.  Returns 1 when the
+ * block is singular to working precision (the reference then leaves the scaling unset; here it is the identity). */
+int thcmb_recompute_scaling(thcmb_ctx* c, double* row_scaling, double* col_scaling, double* db36_out);
+/* THCM::getIntCondCoeff (THCM.C:2608-2637): integral-condition coefficients on the owned S rows; returns the local volume */
+double thcmb_intcond_coeff(const thcmb_ctx* c, double* coeff);
 void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4);
 /* the same step with the state already in HBM (bench.py "value") */
 int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart,

@@ -55,6 +55,8 @@ def lib():
                                 ("oracle_graph", i, [i, i, i, i, vp, vp]),
                                 ("oracle_scatter_to_graph", ll, [i, vp, vp, vp, vp, vp, vp]),
                                 ("oracle_spmv", None, [i, vp, vp, vp, vp, vp]), ("oracle_matavec", None, [i, vp, vp, vp, vp, vp]),
+                                ("oracle_average_block", None, [vp, vp]), ("oracle_compute_scaling", i, [vp, vp, vp, vp]),
+                                ("oracle_intcond_scaling", i, [vp, vp, vp]),
                                 ("oracle_set_vmix_fix", None, [vp, i]), ("oracle_vmix_fun", None, [vp, vp, vp]),
                                 ("oracle_vmix_flags", None, [vp, vp])]:
             fn = getattr(L, name)
@@ -111,6 +113,25 @@ class OracleTHCM:
 
     def getpar(self, idx):
         return self.L_.oracle_getpar(self.h, int(idx))
+
+    def average_block(self):
+        """m_scaling::average_block (scaling.F90:29-64) on the Jacobian of the last matrix() call; (6,6), [row, col]."""
+        db = np.zeros(36)
+        self.L_.oracle_average_block(self.h, _p(db))
+        return db.reshape(6, 6).T.copy()
+
+    def compute_scaling(self, db):
+        """m_scaling::compute (scaling.F90:70-105): (row_scaling, col_scaling) as THCM (not Trilinos) defines them."""
+        dbf = np.ascontiguousarray(np.asarray(db, dtype=np.float64).T).reshape(-1)   # column-major for the Fortran layout
+        rs, cs = np.empty(self.ndim), np.empty(self.ndim)
+        ok = self.L_.oracle_compute_scaling(self.h, _p(dbf), _p(rs), _p(cs))
+        return rs, cs, bool(ok)
+
+    def intcond_scaling(self):
+        """thcm_utils.F90:285-309: (values, 1-based S-row indices) of the integral-condition coefficients."""
+        val = np.empty(self.n * self.m * self.l); ind = np.empty(self.n * self.m * self.l, dtype=np.int32)
+        k = self.L_.oracle_intcond_scaling(self.h, _p(val), _p(ind))
+        return val[:k].copy(), ind[:k].copy()
 
     def set_vmix_fix(self, fix):
         self.L_.oracle_set_vmix_fix(self.h, int(fix))

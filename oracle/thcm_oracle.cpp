@@ -1403,6 +1403,91 @@ struct Oracle {
         }
     }
 
+    // ---------------- scaling.F90:29-64: average diagonal 6x6 block over the OCEAN cells, from the CRS Jacobian ----------------
+    void average_block(double* db /* (nun,nun) column-major */) {
+        for (int q = 0; q < NUN * NUN; q++) db[q] = 0.0;
+        int nl = 0;
+        for (int i = 1; i <= ndim; i++) {
+            int ii = (i - 1) % NUN + 1, cell = (i - 1) / NUN;
+            int ix = cell % n + 1, iy = (cell / n) % m + 1, iz = cell / (n * m) + 1;
+            if (lm(ix, iy, iz) != OCEAN) continue;
+            if (ii == PP) nl++;
+            for (int j = begA[i - 1]; j <= begA[i] - 1; j++) {
+                int c = jcoA[j - 1];
+                if ((c - 1) / NUN == cell) { int jj = (c - 1) % NUN + 1; db[(ii - 1) + NUN * (jj - 1)] += coA[j - 1]; }
+            }
+        }
+        if (nl > 0) for (int q = 0; q < NUN * NUN; q++) db[q] = db[q] / nl;
+    }
+    // scaling.F90:185-279 (the LAPACK variant that is compiled): dgetrf + dgetri = inverse by LU with partial pivoting -- here
+    // plain Gauss-Jordan with partial pivoting (equal up to rounding) -- then the "special for oceanography" formulas
+    static bool scal(double* mat /* (6,6) column-major, overwritten by its inverse */, double* dr, double* dc) {
+        const int N6 = NUN;
+        auto M = [&](int i, int j) -> double& { return mat[(i - 1) + N6 * (j - 1)]; };
+        double Anorm = 0.0;
+        for (int i = 1; i <= N6; i++) { double r = 0.0; for (int j = 1; j <= N6; j++) r += std::fabs(M(i, j)); Anorm = std::max(Anorm, r); }
+        double inv[36];
+        for (int q = 0; q < 36; q++) inv[q] = 0.0;
+        for (int i = 0; i < N6; i++) inv[i + N6 * i] = 1.0;
+        double a[36]; std::memcpy(a, mat, sizeof(a));
+        auto A = [&](int i, int j) -> double& { return a[i + N6 * j]; };
+        auto B = [&](int i, int j) -> double& { return inv[i + N6 * j]; };
+        bool singular = false;
+        for (int p = 0; p < N6 && !singular; p++) {
+            int piv = p; double best = std::fabs(A(p, p));
+            for (int r = p + 1; r < N6; r++) if (std::fabs(A(r, p)) > best) { best = std::fabs(A(r, p)); piv = r; }
+            if (best == 0.0) { singular = true; break; }
+            if (piv != p) for (int j = 0; j < N6; j++) { std::swap(A(p, j), A(piv, j)); std::swap(B(p, j), B(piv, j)); }
+            double d = 1.0 / A(p, p);
+            for (int j = 0; j < N6; j++) { A(p, j) *= d; B(p, j) *= d; }
+            for (int r = 0; r < N6; r++) if (r != p) { double f = A(r, p); if (f != 0.0) for (int j = 0; j < N6; j++) { A(r, j) -= f * A(p, j); B(r, j) -= f * B(p, j); } }
+        }
+        double inorm = 0.0;
+        for (int i = 0; i < N6; i++) { double r = 0.0; for (int j = 0; j < N6; j++) r += std::fabs(B(i, j)); inorm = std::max(inorm, r); }
+        double rcond = singular ? 0.0 : 1.0 / (Anorm * inorm);
+        if (1.0 + rcond == 1.0) return false;   // "diagonal block is singular up to working precision": dr, dc stay unset
+        std::memcpy(mat, inv, sizeof(inv));
+        dr[0] = 1.0; dc[0] = 1.0;
+        double idc = std::sqrt(M(1, 1) / M(2, 2));
+        dr[1] = 1 / idc; dc[1] = dr[1];
+        double idr = std::sqrt(std::fabs(M(1, 1) / M(4, 4)));
+        dr[3] = 1 / idr; dc[3] = dr[3];
+        if (std::fabs(M(4, 3)) > std::fabs(M(3, 3))) idr = M(1, 1) / (idr * M(4, 3));
+        else idr = std::sqrt(std::fabs(M(1, 1) / M(3, 3)));
+        dr[2] = 2 / idr; dc[2] = dr[2];
+        if (std::fabs(M(4, 5) * M(5, 4)) < .01 * std::fabs(M(4, 4) * M(5, 5))) { M(4, 5) = 1; M(5, 4) = 1; }
+        idc = std::sqrt(std::fabs(M(1, 1) * M(4, 5) / (M(5, 4) * M(5, 5))));
+        idr = M(1, 1) / (idc * M(5, 5));
+        dr[4] = 1 / idr; dc[4] = 1 / idc;
+        if (std::fabs(M(4, 6) * M(6, 4)) < .01 * std::fabs(M(4, 4) * M(6, 6))) { M(4, 6) = 1; M(6, 4) = 1; }
+        idc = std::sqrt(std::fabs(M(1, 1) * M(4, 6) / (M(6, 4) * M(6, 6))));
+        idr = M(1, 1) / (idc * M(6, 6));
+        dr[5] = 1 / idr; dc[5] = 1 / idc;
+        return true;
+    }
+    // scaling.F90:70-105
+    bool compute_scaling(const double* db_in, double* row_scaling, double* col_scaling) {
+        double db[36], rs[NUN], cs[NUN];
+        std::memcpy(db, db_in, sizeof(db));
+        for (int q = 0; q < NUN; q++) { rs[q] = 1.0; cs[q] = 1.0; }
+        bool ok = scal(db, rs, cs);
+        for (int i = 1; i <= ndim; i++) {
+            int ii = (i - 1) % NUN + 1, cell = (i - 1) / NUN;
+            int ix = cell % n + 1, iy = (cell / n) % m + 1, iz = cell / (n * m) + 1;
+            bool oc = lm(ix, iy, iz) == OCEAN;
+            row_scaling[i - 1] = oc ? rs[ii - 1] : 1.0;
+            col_scaling[i - 1] = oc ? cs[ii - 1] : 1.0;
+        }
+        return ok;
+    }
+    // thcm_utils.F90:285-309
+    int intcond_scaling(double* val, int* ind) {
+        int v = 0;
+        for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++)
+            if (lm(i, j, k) == OCEAN) { val[v] = std::cos(y[j]) * dfzT[k]; ind[v] = find_row2(i, j, k, SS); v++; }
+        return v;
+    }
+
     // ---------------- usrc.F90:449-521 ----------------
     void matrix(const double* un) {
         An = Al;
@@ -1525,6 +1610,9 @@ void* oracle_create(int n, int m, int l, double xmin, double xmax, double ymin, 
     return o;
 }
 void oracle_destroy(void* h) { delete (Oracle*)h; }
+void oracle_average_block(void* h, double* db) { ((Oracle*)h)->average_block(db); }
+int oracle_compute_scaling(void* h, const double* db, double* rs, double* cs) { return ((Oracle*)h)->compute_scaling(db, rs, cs) ? 1 : 0; }
+int oracle_intcond_scaling(void* h, double* val, int* ind) { return ((Oracle*)h)->intcond_scaling(val, ind); }
 void oracle_set_vmix_fix(void* h, int fix) { ((Oracle*)h)->vmix_fix = fix; }   // mix.F90:52-59
 void oracle_vmix_fun(void* h, const double* un, double* mix) { Oracle* o = (Oracle*)h; for (int q = 0; q < o->ndim; q++) mix[q] = 0.0; o->vmix_fun(un, mix); }
 void oracle_vmix_flags(void* h, int* out) { Oracle* o = (Oracle*)h; out[0] = o->vmix_flag; out[1] = o->vmix_temp; out[2] = o->vmix_salt; out[3] = o->vmix_fix; }

@@ -146,6 +146,31 @@ def test_reference_converged_state_is_a_root_on_the_device(gpu):
     t.close()
 
 
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg"])
+def test_scaling_and_integral_condition(gpu, name):
+    """THCM::RecomputeScaling (m_scaling::average_block + compute, scaling.F90) and getIntCondCoeff (thcm_utils.F90:285-309):
+    the average diagonal block is a device reduction over the stored Jacobian (summation order differs: 1e-13), the rest is
+    the reference's formulas."""
+    s, landm, o, t = setup(gpu, name)
+    x = cases.consistent_state(s, landm, scale=0.05)
+    t.evaluate(dev(x), None, True)
+    o.matrix(x)
+    dbo = o.average_block()
+    rs, cs, db, ok = t.recomputeScaling()
+    assert ok and np.abs(db - dbo).max() <= 1e-13 * np.abs(dbo).max()
+    rso, cso, oko = o.compute_scaling(dbo)
+    assert oko
+    rso, cso = 1.0 / rso, 1.0 / cso                                   # Trilinos' convention (THCM.C:1812-1816)
+    for v in (rso, cso):                                              # T and S scaled alike (THCM.C:1822-1830)
+        mean = 0.5 * (v[4::6] + v[5::6]); v[4::6] = mean; v[5::6] = mean
+    assert np.allclose(rs, rso, rtol=1e-11, atol=0) and np.allclose(cs, cso, rtol=1e-11, atol=0)
+    coeff, vol = t.getIntCondCoeff()
+    val, ind = o.intcond_scaling()
+    want = np.zeros(o.ndim); want[ind - 1] = val
+    assert np.array_equal(coeff, want) and vol == np.abs(val).sum()
+    t.close()
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "global4deg"])
 def test_fortran_abi_drop_in(gpu, name):
     """rhs_ / matrix_ / setparcs_ / get_forcing_ with host buffers exactly as THCM.C calls them (THCM.C:603-638, 1001, 1066)."""
@@ -167,6 +192,16 @@ def test_fortran_abi_drop_in(gpu, name):
     bo, jo, cf, cobo = o.matrix(x)
     assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf) and np.array_equal(cob, cobo)
     assert np.array_equal(f.get_forcing(), o.forcing())
+    # m_scaling / m_thcm_utils symbols THCM.C binds (THCM.C:106-107, 119)
+    dbo = o.average_block()
+    db = f.average_block()
+    assert np.abs(db - dbo).max() <= 1e-13 * np.abs(dbo).max()
+    rs, cs = f.compute_scaling(dbo)
+    rso, cso, _ = o.compute_scaling(dbo)
+    assert np.allclose(rs, rso, rtol=1e-11, atol=0) and np.allclose(cs, cso, rtol=1e-11, atol=0)
+    val, ind = f.intcond_scaling()
+    vo, io = o.intcond_scaling()
+    assert np.array_equal(val, vo) and np.array_equal(ind, io)
     f.finalize()
 
 
