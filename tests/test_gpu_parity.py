@@ -167,7 +167,7 @@ def test_scaling_and_integral_condition(gpu, name):
     coeff, vol = t.getIntCondCoeff()
     val, ind = o.intcond_scaling()
     want = np.zeros(o.ndim); want[ind - 1] = val
-    assert np.array_equal(coeff, want) and vol == np.abs(val).sum()
+    assert np.array_equal(coeff, want) and abs(vol - np.abs(val).sum()) <= 1e-12 * vol   # (Norm1: summation order)
     t.close()
 
 
