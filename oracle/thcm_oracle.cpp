@@ -11,13 +11,19 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
 // arm may load this library.  The product (i-emic_b200/csrc) never links it.
 //
-// PARITY PIN STATUS: the reference ships no golden Jacobian/residual vectors
-// and cannot be built here (no gfortran/MPI/Trilinos) => "golden parity
-// unpinned"; this restatement is pinned by the reference's own invariants
-// (tests/test_oracle_*.py): exact mass-matrix values (test_ocean.C:61-125),
-// FD-vs-analytic Jacobian (TestDefinitions.H:32-87), salt conservation
-// integrals (test_ocean.C:242-316), maximal-graph containment
-// (THCM.C:2320-2549), the stored converged state (reft_ocean.C:59-89).
+// PARITY PIN STATUS: the reference cannot be built here (no gfortran / MPI /
+// Trilinos) and ships no golden Jacobian / residual vectors, but it ships ONE
+// reference-produced vector: the converged state of its regression test
+// (test/ocean/ocean_reference.h5, src/tests/reft_ocean.C:59-89; committed as
+// tests/golden/ocean_reference_state.f64).  That state is a root of the
+// restated residual to Newton accuracy (|F(x*)| = 1.8e-4 vs |F(0)| = 19.8;
+// u,v,w,p rows <= 4e-8; 850x larger without the mixing term): the RESIDUAL is
+// pinned by reference data (tests/test_oracle_pins.py).  The JACOBIAN has no
+// reference vector => "golden parity unpinned" for it; it is pinned against
+// that residual by finite differences and by the reference's own invariants:
+// exact mass-matrix values (test_ocean.C:61-125), FD-vs-analytic Jacobian
+// (TestDefinitions.H:32-87), salt conservation integrals (test_ocean.C:242-316),
+// maximal-graph containment (THCM.C:2320-2549).
 //
 // Every routine cites the reference file:line it follows (relative to
 // /root/reference/src/ocean unless stated).  Compile with
