@@ -149,6 +149,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
+    if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
     THCM_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 4096));
@@ -474,7 +475,14 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
                     THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));
                     multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
-                    if (c->p2p_on || c->blk.nranks == 1) {
+                    if ((c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0) {
+                        // CGS2 with the basis read three times instead of four: w' = w - V h1 and h2 = V^T w', w'.w' in ONE sweep
+                        // (+ all-reduce + DGKS decision); the second update only when the decision asks for it.  h2 lands in
+                        // dh[2S..] and is used by the host only when the flag is set.
+                        fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S);
+                        THCM_CUDA(cudaMemcpyAsync(dh + S, dh + 2 * S + nv, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // ww_new
+                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
+                    } else if (c->p2p_on || c->blk.nranks == 1) {
                         // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh, nullptr, w, dh + S, dh + nv, c->d_flags, dh + 3 * S);
                         multi_dot_dev(c, n, nv, vp.data(), w, c->d_flags, dh + 2 * S);

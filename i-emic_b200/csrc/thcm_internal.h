@@ -194,6 +194,7 @@ struct thcmb_ctx {
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
+    int fused_cgs2 = 1;             // DGKS: first update + second projection in one sweep over the basis (THCM_FUSED_CGS2=0: separate)
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 
@@ -230,6 +231,8 @@ int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
 int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out);
 int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w);
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out);
+int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
                        const double* d_ww_old, int* d_flag_out, double* d_final_out);
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out);

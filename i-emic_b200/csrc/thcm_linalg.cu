@@ -427,6 +427,61 @@ constexpr int MD_BLOCKS = NSM * 4;
 static_assert(P2P_VEC_LEN == MD_MAXV + 1, "mailbox layout");
 struct VecList { const double* v[MD_MAXV]; int nv; };
 
+// Tail of the batched reductions, run by the LAST block of the grid: fixed-order sum of the per-slice partials
+// (nslices x [MD_MAXV+1]), the cross-GPU exchange (LL stores into the peers' mailboxes), out[0..nv-1] and out[nv], epilogue.
+__device__ __forceinline__ void multi_tail(int nslices, int nv, const double* partial, unsigned int* counter, double* out,
+                                           const P2PArgs pa, const RedEpilogue ep) {
+    constexpr int stride = MD_MAXV + 1;
+    const int nthreads = blockDim.x;
+    __shared__ double mine[MD_MAXV + 1];
+    __shared__ double seg[3][MD_MAXV + 1];
+    // three threads per column, each summing a contiguous third of the slices with eight loads in flight; the thirds are
+    // then added in order: a fixed summation tree, identical on every launch
+    for (int idx = threadIdx.x; idx < 3 * (MD_MAXV + 1); idx += nthreads) {
+        const int t3 = idx / (MD_MAXV + 1), q = idx - t3 * (MD_MAXV + 1);
+        if (q <= nv) {
+            const int col = q < nv ? q : MD_MAXV;
+            const int ns = nslices, b0 = (int)((long long)ns * t3 / 3), b1 = (int)((long long)ns * (t3 + 1) / 3);
+            const volatile double* pc = partial + col;
+            double v = 0.0;
+            int b = b0;
+            for (; b + 8 <= b1; b += 8) {
+                double t0 = pc[(size_t)(b + 0) * stride], t1 = pc[(size_t)(b + 1) * stride], t2 = pc[(size_t)(b + 2) * stride], t3v = pc[(size_t)(b + 3) * stride];
+                double t4 = pc[(size_t)(b + 4) * stride], t5 = pc[(size_t)(b + 5) * stride], t6 = pc[(size_t)(b + 6) * stride], t7 = pc[(size_t)(b + 7) * stride];
+                v += t0; v += t1; v += t2; v += t3v; v += t4; v += t5; v += t6; v += t7;
+            }
+            for (; b < b1; b++) v += pc[(size_t)b * stride];
+            seg[t3][q] = v;
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q <= nv; q += nthreads) mine[q] = (seg[0][q] + seg[1][q]) + seg[2][q];
+    const unsigned long long seq = pa.nranks > 1 ? *pa.seq + 1ull : 0ull;
+    if (threadIdx.x == 0) *counter = 0u;
+    __syncthreads();
+    if (pa.nranks > 1) {
+        const int par = (int)(seq & 1ull);
+        const unsigned int flag = (unsigned int)seq;
+        const size_t slot0 = P2P_VEC_OFFSET / sizeof(P2PSlot) + (size_t)par * P2P_MAX_RANKS * P2P_VEC_LEN;
+        // push: every (peer, value) pair is one 16-byte LL store, spread over the block
+        for (int t = threadIdx.x; t < pa.nranks * (nv + 1); t += nthreads) {
+            const int r = t / (nv + 1), q = t - r * (nv + 1);
+            if (r != pa.rank) ll_store(pa.peers[r] + slot0 + (size_t)pa.rank * P2P_VEC_LEN + q, mine[q], flag);
+        }
+        // pull: value q of every peer from my own mailbox, summed in rank order (identical bits on every rank)
+        for (int q = threadIdx.x; q <= nv; q += nthreads) {
+            double tot = 0.0;
+            for (int r = 0; r < pa.nranks; r++)
+                tot += (r == pa.rank) ? mine[q] : ll_wait(pa.mine + slot0 + (size_t)r * P2P_VEC_LEN + q, flag);
+            out[q] = tot;      // out[0..nv-1] = V^T w, out[nv] = w.w
+            if (q == nv) red_epilogue(tot, ep);
+        }
+        if (threadIdx.x == 0) *pa.seq = seq;
+    } else {
+        for (int q = threadIdx.x; q <= nv; q += nthreads) { out[q] = mine[q]; if (q == nv) red_epilogue(mine[q], ep); }
+    }
+}
+
 // grid = (slices, chunks): block (x, y) accumulates the projections of chunk y (8 basis vectors, + w.w for chunk 0)
 // over slice x of the vectors.  All chunks are in flight at once: one latency-bound sweep instead of nv/8 sequential ones
 // (what limited this kernel on the 1/8-size vectors of an 8-GPU run).
@@ -485,53 +540,87 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
     }
     __syncthreads();
     if (!last) return;
-    // ---- last block: fixed-order sum of the per-slice partials, then the cross-GPU exchange ----
-    __shared__ double mine[MD_MAXV + 1];
-    __shared__ double seg[3][MD_MAXV + 1];
-    // three threads per column, each summing a contiguous third of the slices with eight loads in flight; the thirds are
-    // then added in order: a fixed summation tree, identical on every launch
-    {
-        const int t3 = threadIdx.x / (MD_MAXV + 1), q = threadIdx.x - t3 * (MD_MAXV + 1);
-        if (t3 < 3 && q <= nv) {
-            const int col = q < nv ? q : MD_MAXV;
-            const int ns = (int)gridDim.x, b0 = (int)((long long)ns * t3 / 3), b1 = (int)((long long)ns * (t3 + 1) / 3);
-            const volatile double* pc = partial + col;
-            double v = 0.0;
-            int b = b0;
-            for (; b + 8 <= b1; b += 8) {
-                double t0 = pc[(size_t)(b + 0) * stride], t1 = pc[(size_t)(b + 1) * stride], t2 = pc[(size_t)(b + 2) * stride], t3v = pc[(size_t)(b + 3) * stride];
-                double t4 = pc[(size_t)(b + 4) * stride], t5 = pc[(size_t)(b + 5) * stride], t6 = pc[(size_t)(b + 6) * stride], t7 = pc[(size_t)(b + 7) * stride];
-                v += t0; v += t1; v += t2; v += t3v; v += t4; v += t5; v += t6; v += t7;
+    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, RedEpilogue{nullptr, nullptr, nullptr});
+}
+
+// Fused first update + second projection of classical Gram-Schmidt with re-orthogonalisation (CGS2 / DGKS):
+//   w' = w - V h1   and, in the same sweep over the basis,   h2 = V^T w',  ww' = w'.w'
+// Every thread owns two elements (one double2).  The update needs all nv basis values of its elements before w' is known;
+// they are parked in the thread's own shared-memory column and read back by the projection, whose nv partial sums live
+// in registers (fully unrolled, NVCAP of them) across all tiles of the thread.  The basis is read from HBM ONCE for both:
+// three passes over V per iteration (dot, this kernel, second update) instead of four.  No block barrier in the loop.
+constexpr int FUSED_THREADS = 128;
+template <int NVCAP>
+__global__ void __launch_bounds__(FUSED_THREADS) fused_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h1, double* __restrict__ w,
+                                                                        double* partial, unsigned int* counter, double* out,
+                                                                        const P2PArgs pa, const RedEpilogue ep) {
+    extern __shared__ __align__(16) unsigned char fsm_raw[];
+    double2* vs = reinterpret_cast<double2*>(fsm_raw);          // [nv][FUSED_THREADS]: column t belongs to thread t
+    const int nv = vl.nv, n2 = n >> 1;
+    __shared__ double hs[MD_MAXV];
+    __shared__ double red[FUSED_THREADS / 32][NVCAP + 1];
+    __shared__ bool last;
+    for (int q = threadIdx.x; q < nv; q += FUSED_THREADS) hs[q] = h1[q];
+    __syncthreads();
+    double acc[NVCAP];
+#pragma unroll
+    for (int q = 0; q < NVCAP; q++) acc[q] = 0.0;
+    double wwacc = 0.0;
+    double2* w2 = reinterpret_cast<double2*>(w);
+    double2* mycol = vs + threadIdx.x;
+    for (int i = blockIdx.x * FUSED_THREADS + threadIdx.x; i < n2; i += gridDim.x * FUSED_THREADS) {
+        double2 wi = w2[i];
+#pragma unroll
+        for (int c0 = 0; c0 < NVCAP; c0 += MD_CHUNK) {
+            if (c0 < nv) {
+                double2 vv[MD_CHUNK];
+#pragma unroll
+                for (int q = 0; q < MD_CHUNK; q++)
+                    if (c0 + q < nv) vv[q] = reinterpret_cast<const double2*>(vl.v[c0 + q])[i];
+#pragma unroll
+                for (int q = 0; q < MD_CHUNK; q++)
+                    if (c0 + q < nv) {
+                        mycol[(size_t)(c0 + q) * FUSED_THREADS] = vv[q];
+                        wi.x = wi.x - hs[c0 + q] * vv[q].x;
+                        wi.y = wi.y - hs[c0 + q] * vv[q].y;
+                    }
             }
-            for (; b < b1; b++) v += pc[(size_t)b * stride];
-            seg[t3][q] = v;
         }
+        w2[i] = wi;
+        wwacc += wi.x * wi.x; wwacc += wi.y * wi.y;
+#pragma unroll
+        for (int q = 0; q < NVCAP; q++)
+            if (q < nv) {
+                const double2 v = mycol[(size_t)q * FUSED_THREADS];
+                acc[q] += wi.x * v.x; acc[q] += wi.y * v.y;
+            }
+    }
+    // per-block results: warp shuffle tree, then the warps in order
+    constexpr int stride = MD_MAXV + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q <= NVCAP; q++) {
+        double v = q < NVCAP ? acc[q < NVCAP ? q : 0] : wwacc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][q] = v;
     }
     __syncthreads();
-    for (int q = threadIdx.x; q <= nv; q += RED_THREADS) mine[q] = (seg[0][q] + seg[1][q]) + seg[2][q];
-    const unsigned long long seq = pa.nranks > 1 ? *pa.seq + 1ull : 0ull;
-    if (threadIdx.x == 0) *counter = 0u;
-    __syncthreads();
-    if (pa.nranks > 1) {
-        const int par = (int)(seq & 1ull);
-        const unsigned int flag = (unsigned int)seq;
-        const size_t slot0 = P2P_VEC_OFFSET / sizeof(P2PSlot) + (size_t)par * P2P_MAX_RANKS * P2P_VEC_LEN;
-        // push: every (peer, value) pair is one 16-byte LL store, spread over the block
-        for (int t = threadIdx.x; t < pa.nranks * (nv + 1); t += RED_THREADS) {
-            const int r = t / (nv + 1), q = t - r * (nv + 1);
-            if (r != pa.rank) ll_store(pa.peers[r] + slot0 + (size_t)pa.rank * P2P_VEC_LEN + q, mine[q], flag);
-        }
-        // pull: value q of every peer from my own mailbox, summed in rank order (identical bits on every rank)
-        for (int q = threadIdx.x; q <= nv; q += RED_THREADS) {
-            double tot = 0.0;
-            for (int r = 0; r < pa.nranks; r++)
-                tot += (r == pa.rank) ? mine[q] : ll_wait(pa.mine + slot0 + (size_t)r * P2P_VEC_LEN + q, flag);
-            out[q] = tot;      // out[0..nv-1] = V^T w, out[nv] = w.w
-        }
-        if (threadIdx.x == 0) *pa.seq = seq;
-    } else {
-        for (int q = threadIdx.x; q <= nv; q += RED_THREADS) out[q] = mine[q];
+    if (threadIdx.x <= NVCAP) {
+        double v = 0.0;
+        for (int ww = 0; ww < FUSED_THREADS / 32; ww++) v += red[ww][threadIdx.x];
+        if (threadIdx.x < nv) partial[(size_t)blockIdx.x * stride + threadIdx.x] = v;
+        if (threadIdx.x == NVCAP) partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, ep);
 }
 
 // w -= sum_q h[q] v_q  (applied in q order);  skipped when *skip == 0
@@ -646,6 +735,38 @@ int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
                                                                  RedEpilogue{d_ww_old, d_flag_out, d_final_out}); }
     c->launches++;
     if (!c->p2p_on && c->blk.nranks > 1) fatal("multi_axpy_dot needs the P2P mailboxes on multi-GPU runs (THCM_P2P=1)");
+    return 0;
+}
+// w -= V h1 ; out[0..nv) = V^T w (updated w) ; out[nv] = w.w ; *flag = out[nv] < 0.5 * *ww_old ; *final = out[nv]
+template <int NVCAP>
+static void launch_fused(thcmb_ctx* c, int n, const VecList& vl, const double* d_h1, double* w, double* d_out, const RedEpilogue& ep) {
+    const size_t smem = (size_t)vl.nv * FUSED_THREADS * sizeof(double2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        THCM_CUDA(cudaFuncSetAttribute(fused_axpy_dot_kernel<NVCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NVCAP * FUSED_THREADS * sizeof(double2))));
+        attr_set = true;
+    }
+    int occ = 0;
+    THCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_axpy_dot_kernel<NVCAP>, FUSED_THREADS, smem));
+    const int n2 = n >> 1;
+    const int grid = std::max(1, std::min(std::min((n2 + FUSED_THREADS - 1) / FUSED_THREADS, NSM * std::max(occ, 1)), MD_BLOCKS));
+    fused_axpy_dot_kernel<NVCAP><<<grid, FUSED_THREADS, smem, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+}
+int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out) {
+    if (nv > MD_MAXV) fatal("fused_axpy_dot: too many vectors");
+    if (n & 1) fatal("fused_axpy_dot: vector length must be even (6 unknowns per cell)");
+    if (!c->p2p_on && c->blk.nranks > 1) fatal("fused_axpy_dot needs the P2P mailboxes on multi-GPU runs (THCM_P2P=1)");
+    VecList vl; vl.nv = nv;
+    for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
+    if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
+    const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out};
+    { ProfScope prof_(c, KID_MULTIAXPY);
+      if (nv <= 16) launch_fused<16>(c, n, vl, d_h1, w, d_out, ep);
+      else if (nv <= 32) launch_fused<32>(c, n, vl, d_h1, w, d_out, ep);
+      else if (nv <= 48) launch_fused<48>(c, n, vl, d_h1, w, d_out, ep);
+      else launch_fused<64>(c, n, vl, d_h1, w, d_out, ep); }
+    c->launches++;
     return 0;
 }
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag) {
