@@ -49,6 +49,7 @@ void upload_params(thcmb_ctx* c) {
     upload(c->d_frc, c->frc_local);
     upload(c->d_jrec, c->jrec_host);
     upload(c->d_krec, c->krec_host);
+    upload(c->d_msi, c->msi_local);
 }
 
 void refresh_params(thcmb_ctx* c) {  // forcing + lin (usrc.F90:178-179)
@@ -140,12 +141,11 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     THCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     THCM_CUDA(cudaEventCreate(&c->ev0)); THCM_CUDA(cudaEventCreate(&c->ev1));
     for (auto& e : c->ev_slot) THCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    size_t nm = (size_t)s->N * s->M;
-    for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
     build_grid(c);
     stpnt(c);
     apply_landmask_rules(c, landm_global, false);
     vmix_init(c);      // usrc.F90:133
+    init_surface_fields(c);   // allocate_usr + atmos_coef (usrc.F90:118-134)
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
@@ -175,7 +175,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter, (void*)c->d_bcell, (void*)c->d_brows,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
-                    (void*)c->d_krec})
+                    (void*)c->d_krec, (void*)c->d_msi})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -202,6 +202,10 @@ void thcmb_set_par(thcmb_ctx* c, int idx, double val) {
     if (idx >= 1 && idx <= NPAR) c->par[idx] = val;
     refresh_params(c);
 }
+/* coupled mode: m_inserts::insert_* on GLOBAL N*M fields, set_atmos_parameters / set_seaice_parameters (usrc.F90:254-350) */
+void thcmb_insert_field(thcmb_ctx* c, int which, const double* field_global) { insert_surface_field(c, which, field_global); }
+void thcmb_set_atmos_parameters(thcmb_ctx* c, const double* pars18) { set_atmos_parameters(c, pars18); refresh_params(c); }
+void thcmb_set_seaice_parameters(thcmb_ctx* c, const double* pars7) { set_seaice_parameters(c, pars7); refresh_params(c); }
 double thcmb_get_par(const thcmb_ctx* c, int idx) { return (idx >= 1 && idx <= NPAR) ? c->par[idx] : 0.0; }
 void thcmb_get_forcing(thcmb_ctx* c, double* frc) {
     const std::vector<double>& f = c->frc_masked ? c->frc_local : c->frc_raw;
@@ -859,11 +863,22 @@ void set_landmask_(int* landm, int* periodic, int* reinit) {
     else { compute_cob(c); }
 }
 void get_forcing_(double* frc) { thcmb_get_forcing(G(), frc); }
-static void insert_field(std::vector<double>& dst, const double* f) { memcpy(dst.data(), f, sizeof(double) * dst.size()); }
-void __m_inserts_MOD_insert_taux(double* f) { insert_field(G()->taux, f); }
-void __m_inserts_MOD_insert_tauy(double* f) { insert_field(G()->tauy, f); }
-void __m_inserts_MOD_insert_atmosphere_t(double* f) { insert_field(G()->tatm, f); }
-void __m_inserts_MOD_insert_emip(double* f) { insert_field(G()->emip, f); }
+/* m_inserts (inserts.F90:11-281; THCM.C:85-98): n*m surface fields, i fastest; no recompute until the next setparcs */
+void __m_inserts_MOD_insert_taux(double* f) { insert_surface_field(G(), SF_TAUX, f); }
+void __m_inserts_MOD_insert_tauy(double* f) { insert_surface_field(G(), SF_TAUY, f); }
+void __m_inserts_MOD_insert_atmosphere_t(double* f) { insert_surface_field(G(), SF_TATM, f); }
+void __m_inserts_MOD_insert_atmosphere_q(double* f) { insert_surface_field(G(), SF_QATM, f); }
+void __m_inserts_MOD_insert_atmosphere_a(double* f) { insert_surface_field(G(), SF_ALBE, f); }
+void __m_inserts_MOD_insert_atmosphere_p(double* f) { insert_surface_field(G(), SF_PATM, f); }
+void __m_inserts_MOD_insert_seaice_q(double* f) { insert_surface_field(G(), SF_QSA, f); }
+void __m_inserts_MOD_insert_seaice_m(double* f) { insert_surface_field(G(), SF_MSI, f); }
+void __m_inserts_MOD_insert_seaice_g(double* f) { insert_surface_field(G(), SF_GSI, f); }
+void __m_inserts_MOD_insert_emip(double* f) { insert_surface_field(G(), SF_EMIP, f); }
+void __m_inserts_MOD_insert_adapted_emip(double* f) { insert_surface_field(G(), SF_ADAPTED_EMIP, f); }
+void __m_inserts_MOD_insert_emip_pert(double* f) { insert_surface_field(G(), SF_SPERT, f); }
+/* usrc.F90:254-350 (Ocean.C:48-49, 1486, 1507): the structs are Atmosphere::CommPars (18 doubles) / SeaIce::CommPars (7) */
+void set_atmos_parameters_(void* pars) { thcmb_set_atmos_parameters(G(), (const double*)pars); }
+void set_seaice_parameters_(void* pars) { thcmb_set_seaice_parameters(G(), (const double*)pars); }
 void __m_mix_MOD_set_vmix_fix(int* fix) { G()->vmix_fix = *fix; }
 /* m_scaling (scaling.F90:29-105) on the Jacobian of the last matrix_ call, m_thcm_utils::intcond_scaling (thcm_utils.F90:285-309) */
 void __m_scaling_MOD_average_block(double* db) { average_block(G(), db); }

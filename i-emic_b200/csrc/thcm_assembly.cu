@@ -816,7 +816,7 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     if ((((uintptr_t)d_un) & 15) != 0) fatal("state vector must be 16-byte aligned (cells are read as 3 x 128-bit loads)");
     AsmArgs a;
     a.b = DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
-    a.t = c->tab; a.t.jt = c->d_jt; a.t.kt = c->d_kt;
+    a.t = c->tab; a.t.jt = c->d_jt; a.t.kt = c->d_kt; a.t.msi = c->d_msi;
     a.un = d_un; a.halo = c->d_halo; a.nbmask = c->d_nbmask; a.surf = c->d_surf; a.uvlive = c->d_uvlive; a.frc = c->d_frc;
     a.rowptr = c->d_rowptr; a.val = c->d_val; a.blockcnt = c->d_blockcnt; a.begA = d_begA; a.jcoA = d_jcoA; a.coA = d_coA;
     a.out = d_out; a.sign = 1.0;

@@ -394,7 +394,18 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
         const double c4x = JT(J_C4X, gj), c4y = JT(J_C4Y, gj), cv0 = JT(J_COSYV, gj - 1), cv1 = JT(J_COSYV, gj);
         const double dfz = KT(K_DFZT, k), tdzi = t.tdzi2;
         double l2 = JT(J_TT2, gj) * sm, l4 = JT(J_TT4, gj) * sm, l6 = JT(J_TT6, gj) * sm;
-        double l5 = JT(J_TT5, gj) * sm - KT(K_ZT5, k) * sm + KT(R == TT ? K_RT : K_RS, k);
+        double l5 = JT(J_TT5, gj) * sm - KT(K_ZT5, k) * sm;
+        // restoring term TRES*bi*tc | SRES*bi*sc, or -- coupled to an external atmosphere / sea ice (usrc.F90:742-783) -- the
+        // sensible + latent heat flux and sea-ice terms of the surface level (tc = sc = 1 and mc = msi at k = l, else 0, so
+        // the lower levels only add exact zeros); TT,SS / SS,TT centre entries below
+        const bool cpl = (R == TT ? t.coupled_T : t.coupled_S) && k == L;
+        const double mc = cpl ? THCM_LDG(t.msi + (size_t)c.lj * blk.n0 + c.li) : 0.0;
+        if (cpl) {
+            if constexpr (R == TT) l5 = l5 + t.cpl_ooa + t.cpl_dedt_t + mc * (t.cpl_qtz - t.cpl_ooa - t.cpl_dedt_t);
+            else l5 = l5 - mc * t.cpl_pq * t.cpl_zeta * t.cpl_a0 / t.cpl_rl;
+        } else {
+            l5 = l5 + KT(R == TT ? K_RT : K_RS, k);
+        }
         double l14 = -0.0 - KT(K_ZT14, k) * sm, l23 = -0.0 - KT(K_ZT23, k) * sm;
         // tnlin(3): Utrx, tnlin(5): Vtry, tnlin(7): Wtrz -- identical in rhs and jacobian (usrc.F90:869-872, 983-991)
         double x2 = -(UV(a, gi - 1, gj, k, 0) + UV(a, gi - 1, gj - 1, k, 0)) * c4x * sm;
@@ -410,6 +421,14 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
         ENT(4, R) = l4 + y4; ENT(6, R) = l6 + y6;
         ENT(5, R) = l5 + x5 + y5 + z5;
         ENT(14, R) = l14 + z14; ENT(23, R) = l23 + z23;
+        if (cpl) {
+            if constexpr (R == TT) {
+                ENT(5, SS) = t.cpl_ts * mc;                                  // Al(TT,SS) = -QTnd*zeta*a0*mc (usrc.F90:755)
+            } else {
+                const double QSoa = -t.cpl_dedt_s, QSos = t.cpl_pq * t.cpl_zeta / t.cpl_rl;
+                ENT(5, TT) = QSoa + mc * (QSos - QSoa);                      // Al(SS,TT) (usrc.F90:774-783)
+            }
+        }
         if constexpr (JAC) {
             // tnlin(2): urTx, tnlin(4): vrTy, tnlin(6): wrTz (usrc.F90:988-990, 1004-1006)
             double tc = TS(a, gi, gj, k, var);

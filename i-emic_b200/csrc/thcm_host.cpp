@@ -29,9 +29,11 @@ void fatal(const std::string& msg) {
 // usr.F90:132-160
 static constexpr double PI = 3.14159265358979323846;
 static constexpr double omegadim = 7.292e-05, r0dim = 6.37e+06, udim = 0.1e+00, gdim = 9.8e+00, rhodim = 1.024e+03,
-                        deltas = 1.0, s0 = 35.0, cp0 = 4.2e+03, alpt1 = 2.93, alpt2 = 8.3e-02, alpt3 = 6.6e-04,
+                        t0 = 15, deltat = 1.0, deltas = 1.0, s0 = 35.0, cp0 = 4.2e+03, alpt1 = 2.93, alpt2 = 8.3e-02, alpt3 = 6.6e-04,
                         ah = 2.5e+05, av = 1.0e-03, kappah = 1.0e+03, kappav = 1.0e-04;
 static constexpr double zmin = -1.0, zmax = 0.0;
+// atm.F90:5-19 (the values the ocean uses in coupled mode)
+static constexpr double rhoa = 1.25, ce = 1.3e-03, ch = 0.94 * ce, cpa = 1000., uw = 8.5, c0 = 0.43, sun0 = 1360., lv = 2.5e+06;
 
 // ---------------------------------------------------------------------------------------------
 // TRIOS::Domain::Decomp2D (src/trios/TRIOS_Domain.C:201-315): factor nprocs = npN x npM minimising
@@ -205,7 +207,6 @@ void compute_forcing(thcmb_ctx* c) {
     const Block& b = c->blk;
     const double* par = c->par;
     int n = s.N, m = s.M, l = s.L;
-    if (s.coupled_T || s.coupled_S) fatal("coupled_T/coupled_S = 1 (external atmosphere / sea ice) is not implemented on the B200 path yet");
     auto F2 = [&](std::vector<double>& f, int i, int j) -> double& { return f[(size_t)(i - 1) + (size_t)n * (j - 1)]; };
     if (s.iza == 2)
         for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) { F2(c->taux, i, j) = wfun(c->yv[j], 1); F2(c->tauy, i, j) = wfun(c->yv[j], 2); }
@@ -216,13 +217,16 @@ void compute_forcing(thcmb_ctx* c) {
         for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) F2(c->tatm, i, j) = temfun(c, c->y[j]);
         if (s.TRES == 0) temcor = qint(c, c->tatm);
     }
-    double gamma = par[COMB] * par[SALT] * (1 - s.SRES + s.SRES * par[BIOT]);
+    double gamma;
+    if (s.coupled_S == 1) gamma = par[COMB] * par[SALT];
+    else gamma = par[COMB] * par[SALT] * (1 - s.SRES + s.SRES * par[BIOT]);
     double salcor = 0.0, adapted_salcor = 0.0, spertcor = 0.0;
     if (s.its == 1) {
         for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) F2(c->emip, i, j) = salfun(c, c->y[j]) * (1 - LM(c, i, j, l));
-        if (s.SRES == 0) salcor = qint(c, c->emip);
+        if (s.SRES == 0 && s.coupled_S == 0) salcor = qint(c, c->emip);
     }
-    if (s.SRES == 0) { adapted_salcor = qint(c, c->adapted_emip); spertcor = qint(c, c->spert); }
+    if (s.SRES == 0 && s.coupled_S == 0) { adapted_salcor = qint(c, c->adapted_emip); spertcor = qint(c, c->spert); }
+    const double pQSnd = par[COMB] * par[SALT] * c->QSnd;
 
     c->frc_raw.assign(b.ndim(), 0.0);
     auto row = [&](int gi, int gj, int k, int XX) {  // 1-based global cell -> local owned row (0-based)
@@ -233,10 +237,24 @@ void compute_forcing(thcmb_ctx* c) {
             c->frc_raw[row(gi, gj, l, UU)] = sigma * F2(c->taux, gi, gj);
             c->frc_raw[row(gi, gj, l, VV)] = sigma * F2(c->tauy, gi, gj);
         }
-        c->frc_raw[row(gi, gj, l, TT)] = etabi * (F2(c->tatm, gi, gj) - temcor);
-        c->frc_raw[row(gi, gj, l, SS)] = gamma * (1 - par[HMTP]) * (F2(c->emip, gi, gj) - salcor) +
-                                         gamma * par[HMTP] * (F2(c->adapted_emip, gi, gj) - adapted_salcor) +
-                                         par[SPER] * (1 - s.SRES + s.SRES * par[BIOT]) * (F2(c->spert, gi, gj) - spertcor);
+        if (s.coupled_T == 1) {   // externally coupled atmosphere / sea ice (forcing.F90:66-80)
+            double QToa = par[COMB] * par[SUNP] * c->suno[gj] * (1 - c->atm_albe0 - c->atm_albed * F2(c->albe, gi, gj)) +
+                          c->atm_Ooa * F2(c->tatm, gi, gj) + c->atm_lvsc * c->atm_eta * c->atm_qdim * F2(c->qatm, gi, gj) -
+                          c->atm_lvsc * c->atm_eo0;
+            double QTos = c->QTnd * c->ice_zeta * (c->ice_a0 * s0 - t0);
+            c->frc_raw[row(gi, gj, l, TT)] = (QToa + F2(c->msi, gi, gj) * (QTos - QToa)) * (1 - LM(c, gi, gj, l));
+        } else {
+            c->frc_raw[row(gi, gj, l, TT)] = etabi * (F2(c->tatm, gi, gj) - temcor);
+        }
+        if (s.coupled_S == 1) {   // forcing.F90:152-164
+            double QSoa = pQSnd * (c->atm_eo0 - c->atm_eta * c->atm_qdim * F2(c->qatm, gi, gj) - F2(c->patm, gi, gj));
+            double QSos = pQSnd * (c->ice_zeta * (c->ice_a0 * s0 - t0) - c->ice_Qvar * F2(c->qsa, gi, gj) - c->ice_Q0) / (rhodim * c->ice_Lf);
+            c->frc_raw[row(gi, gj, l, SS)] = (QSoa + F2(c->msi, gi, gj) * (QSos - QSoa) - F2(c->gsi, gi, gj)) * (1 - LM(c, gi, gj, l));
+        } else {
+            c->frc_raw[row(gi, gj, l, SS)] = gamma * (1 - par[HMTP]) * (F2(c->emip, gi, gj) - salcor) +
+                                             gamma * par[HMTP] * (F2(c->adapted_emip, gi, gj) - adapted_salcor) +
+                                             par[SPER] * (1 - s.SRES + s.SRES * par[BIOT]) * (F2(c->spert, gi, gj) - spertcor);
+        }
         // forcing.F90:199-209: the w-row forcing is built from internal_temp/internal_salt, which are identically
         // zero unless Levitus data files are read (none ship with the reference) => Frc(w) = 0.
     }
@@ -245,6 +263,61 @@ void compute_forcing(thcmb_ctx* c) {
         for (int XX = 1; XX <= NUN; XX++)
             if (frc_row_zeroed(c, gi, gj, k, XX)) c->frc_local[row(gi, gj, k, XX)] = 0.0;
     c->frc_masked = false;
+}
+
+// usrc.F90:1200-1240: the members of m_atm the ocean reads (Ooa, Os, suno); nus and lvsc wait for set_atmos_parameters
+void atmos_coef(thcmb_ctx* c) {
+    const int m = c->s.M;
+    const double muoa = rhoa * ch * cpa * uw;
+    c->atm_Os = sun0 * c0 / 4 * c->QTnd;
+    c->atm_Ooa = muoa * c->QTnd;
+    c->atm_nus = 0.0;
+    c->atm_lvsc = 0.0;
+    c->suno.assign(m + 1, 0.0);
+    for (int j = 1; j <= m; j++) {
+        const double sj = std::sin(c->y[j]);
+        c->suno[j] = c->atm_Os * (1 - .482 * (3 * (sj * sj) - 1.) / 2.);
+    }
+}
+
+// m_inserts (inserts.F90:11-281): GLOBAL N*M surface field, i fastest.  The E-P fields are masked by the surface land
+// mask (:179,198,217); q / a / p / g are only taken when the matching coupling flag is on (:45,66,87,145).  Like the
+// reference, nothing is recomputed until the next setparcs / set_*_parameters call.
+void insert_surface_field(thcmb_ctx* c, int which, const double* f) {
+    std::vector<double>* dst[SF_COUNT] = {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip,
+                                          &c->qatm, &c->albe, &c->patm, &c->qsa, &c->msi, &c->gsi};
+    if (which < 0 || which >= SF_COUNT) fatal("insert_surface_field: unknown field");
+    const thcmb_settings& s = c->s;
+    if (which == SF_QATM && !(s.coupled_T == 1 || s.coupled_S == 1)) return;
+    if (which == SF_ALBE && s.coupled_T != 1) return;
+    if ((which == SF_PATM || which == SF_GSI) && s.coupled_S != 1) return;
+    const bool masked = which == SF_EMIP || which == SF_SPERT || which == SF_ADAPTED_EMIP;
+    size_t pos = 0;
+    for (int j = 1; j <= s.M; j++) for (int i = 1; i <= s.N; i++, pos++)
+        (*dst[which])[pos] = masked ? f[pos] * (1 - LM(c, i, j, s.L)) : f[pos];
+}
+// usrc.F90:254-310: the 18 doubles of Atmosphere::CommPars (tdim qdim nuq eta dqso dqsi dqdt Eo0 Ei0 Cs t0o t0i a0 da tauf
+// tauc comb albf); nus and lvsc are frozen at the COMB / SALT / TEMP values of the moment of the call.  The caller re-runs
+// forcing + lin (refresh_params).
+void set_atmos_parameters(thcmb_ctx* c, const double* p) {
+    c->atm_qdim = p[1]; c->atm_nuq = p[2]; c->atm_eta = p[3]; c->atm_dqso = p[4]; c->atm_eo0 = p[7];
+    c->atm_albe0 = p[12]; c->atm_albed = p[13];
+    c->atm_nus = c->par[COMB] * c->par[SALT] * c->atm_eta * c->atm_qdim * c->QSnd;
+    c->atm_lvsc = c->par[COMB] * c->par[TEMP] * rhodim * lv * c->QTnd;
+}
+// usrc.F90:313-350: the 7 doubles of SeaIce::CommPars (zeta a0 Lf s0 rhoo Qvar Q0)
+void set_seaice_parameters(thcmb_ctx* c, const double* p) {
+    c->ice_zeta = p[0]; c->ice_a0 = p[1]; c->ice_Lf = p[2]; c->ice_Qvar = p[5]; c->ice_Q0 = p[6];
+    if (p[3] != s0) fprintf(stderr, "thcm_b200: WARNING conflicting reference salinity s0\n");
+    if (p[4] != rhodim) fprintf(stderr, "thcm_b200: WARNING conflicting sea water density rhodim\n");
+}
+// allocation of the surface fields of m_usr (usr.F90 allocate_usr) + atmos_coef, between stpnt and forcing (usrc.F90:118-131)
+void init_surface_fields(thcmb_ctx* c) {
+    const size_t nm = (size_t)c->s.N * c->s.M;
+    for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip, &c->qatm, &c->albe, &c->patm, &c->msi,
+                    &c->gsi, &c->qsa})
+        f->assign(nm, 0.0);
+    atmos_coef(c);
 }
 
 // assemble.F90:18-54 on the owned rows
@@ -355,8 +428,9 @@ void compute_tables(thcmb_ctx* c) {
         double tzz14 = h2 * rdz2i, tzz23 = (k < l) ? h1 * rdz2i : 0.0, tzz5 = -(tzz14 + tzz23);  // tderiv(5)
         KTB(K_ZT5, k) = pv * tzz5; KTB(K_ZT14, k) = pv * tzz14; KTB(K_ZT23, k) = pv * tzz23;
         KTB(K_DFZT, k) = dfzT[k];
-        KTB(K_RT, k) = s.TRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:758, tderiv(1)
-        KTB(K_RS, k) = s.SRES * bi * (k == l ? 1.0 : 0.0);              // usrc.F90:785, tderiv(2)
+        // restoring term, absent from the coupled branches (usrc.F90:745-758, 771-785)
+        KTB(K_RT, k) = s.coupled_T == 1 ? 0.0 : s.TRES * bi * (k == l ? 1.0 : 0.0);   // usrc.F90:758, tderiv(1)
+        KTB(K_RS, k) = s.coupled_S == 1 ? 0.0 : s.SRES * bi * (k == l ? 1.0 : 0.0);   // usrc.F90:785, tderiv(2)
         KTB(K_DFZW, k) = dfzW[k]; KTB(K_DFZWM, k) = dfzW[k - 1];        // dCdzt, mix_imp.f:613-641
     }
     // per-j / per-k records of the pipelined kernel: the three j-neighbour values of every j-table, all k-tables of level k
@@ -373,6 +447,21 @@ void compute_tables(thcmb_ctx* c) {
     t.cWS = lambda * Ra;                                                // usrc.F90:718
     t.c2 = Ra * xes * alpt2; t.c3 = Ra * xes * alpt3;                   // usrc.F90:862-863, 975-976
     t.tdzi2 = 1.0 / (2 * dz);                                           // tnlin(6,7)
+    // coupled mode (usrc.F90:742-783): constants of the surface-level sensible / latent / sea-ice terms, each the
+    // sub-expression the reference forms; msi restricted to the owned columns for the kernels
+    t.coupled_T = s.coupled_T == 1; t.coupled_S = s.coupled_S == 1;
+    t.cpl_ooa = c->atm_Ooa;
+    t.cpl_dedt_t = c->atm_lvsc * c->atm_eta * c->atm_qdim * (deltat / c->atm_qdim) * c->atm_dqso;   // usrc.F90:743
+    t.cpl_qtz = c->QTnd * c->ice_zeta;
+    t.cpl_ts = -c->QTnd * c->ice_zeta * c->ice_a0;                                                   // usrc.F90:755
+    t.cpl_pq = par[COMB] * par[SALT] * c->QSnd;                                                       // usrc.F90:767
+    t.cpl_zeta = c->ice_zeta; t.cpl_a0 = c->ice_a0; t.cpl_rl = rhodim * c->ice_Lf;
+    t.cpl_dedt_s = c->atm_nus * (deltat / c->atm_qdim) * c->atm_dqso;                               // usrc.F90:766
+    t.msi = nullptr;
+    c->msi_local.assign((size_t)c->blk.n0 * c->blk.m0, 0.0);
+    if (t.coupled_T || t.coupled_S)
+        for (int lj = 0; lj < c->blk.m0; lj++) for (int li = 0; li < c->blk.n0; li++)
+            c->msi_local[(size_t)lj * c->blk.n0 + li] = c->msi[(size_t)(c->blk.i0 + li) + (size_t)s.N * (c->blk.j0 + lj)];
     // tracer mixing (vmix_fun, mix_imp.f:231-562): only the implicit vertical mixing of the shipped parameter set is built
     const bool mix_on = c->vmix_flag >= 1 && c->vmix_dim > 0;
     if (c->vmix_flag >= 1 && (par[MIXP] != 0.0 || par[MKAP] != 0.0 || par[ALPC] != 1.0))

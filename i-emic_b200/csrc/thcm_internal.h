@@ -53,6 +53,13 @@ struct DevTables {
     // (0 when mixing is off), mix_fac = alphaT * SPL1 (tprstb), mix_rho = rho_mixing .and. xes == 0
     double mix_lambda, mix_xes, mix_kvc, mix_fac, mix_dz;
     int mix_temp, mix_salt, mix_rho;
+    // coupled mode (coupled_T / coupled_S = 1, usrc.F90:733-786): surface-level terms of the T and S rows that replace the
+    // restoring term.  msi = sea-ice mask of the owned columns (n0*m0, i fastest); every constant is the sub-expression the
+    // reference forms: cpl_ooa = Ooa, cpl_dedt_t = lvsc*eta*qdim*(deltat/qdim)*dqso, cpl_qtz = QTnd*zeta,
+    // cpl_ts = -QTnd*zeta*a0, cpl_pq = COMB*SALT*QSnd, cpl_rl = rhodim*Lf, cpl_dedt_s = nus*(deltat/qdim)*dqso
+    const double* msi;
+    int coupled_T, coupled_S;
+    double cpl_ooa, cpl_dedt_t, cpl_qtz, cpl_ts, cpl_pq, cpl_zeta, cpl_a0, cpl_rl, cpl_dedt_s;
 };
 
 // ---- local block of the global grid (TRIOS_Domain.C:201-315 decomposition, global indexing kept) ----
@@ -118,6 +125,14 @@ struct thcmb_ctx {
     std::vector<double> x, y, z, xu, yv, zw, ze, zwe, dfzT, dfzW;  // GLOBAL grid, Fortran index = vector index
     std::vector<int> landm;  // GLOBAL (0:N+1,0:M+1,0:L+1) after init's frame rules
     std::vector<double> taux, tauy, tatm, emip, spert, adapted_emip;  // GLOBAL N*M surface fields
+    std::vector<double> qatm, albe, patm, msi, gsi, qsa;              // coupled mode (m_usr, usr.F90; inserts.F90:33-157)
+    // m_atm (atm.F90) / m_ice (ice.F90) values the ocean needs in coupled mode; set_atmos/seaice_parameters (usrc.F90:254-350)
+    double atm_qdim = 0.01, atm_nuq = 0.0, atm_nus = 0.0, atm_eta = 0.0, atm_dqso = 0.0, atm_eo0 = 0.0, atm_albe0 = 0.0,
+           atm_albed = 0.0, atm_lvsc = 0.0, atm_Ooa = 1.0, atm_Os = 1.0;
+    std::vector<double> suno;                                         // shortwave profile (usrc.F90:1228), index j
+    double ice_zeta = 0.0, ice_a0 = -0.0575, ice_Lf = 3.347e+05, ice_Qvar = 0.0, ice_Q0 = 0.0;
+    std::vector<double> msi_local;                                    // msi on the owned columns (n0*m0, i fastest)
+    double* d_msi = nullptr;
     std::vector<double> frc_local;   // owned rows, masked by the rows `boundaries` turns into identity rows
     std::vector<double> frc_raw;     // owned rows, as `forcing` leaves it
     bool frc_masked = false;         // get_forcing_ semantics (boundary.F90 zeroes Frc lazily inside rhs/matrix)
@@ -207,6 +222,13 @@ void build_grid(thcmb_ctx* c);
 void stpnt(thcmb_ctx* c);
 void apply_landmask_rules(thcmb_ctx* c, const int* landm_in, bool fix_inversion);
 void compute_forcing(thcmb_ctx* c);
+void atmos_coef(thcmb_ctx* c);
+void init_surface_fields(thcmb_ctx* c);
+enum SurfaceField { SF_TAUX = 0, SF_TAUY, SF_TATM, SF_EMIP, SF_SPERT, SF_ADAPTED_EMIP, SF_QATM, SF_ALBE, SF_PATM, SF_QSA, SF_MSI,
+                    SF_GSI, SF_COUNT };
+void insert_surface_field(thcmb_ctx* c, int which, const double* f);
+void set_atmos_parameters(thcmb_ctx* c, const double* pars18);
+void set_seaice_parameters(thcmb_ctx* c, const double* pars7);
 void compute_tables(thcmb_ctx* c);
 void vmix_init(thcmb_ctx* c);
 void vmix_set_flags(thcmb_ctx* c, int temp, int salt);

@@ -90,6 +90,8 @@ def load_library(path=None):
         "thcmb_halo_gids": (None, [vp, vp]), "thcmb_local_gids": (None, [vp, vp]),
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
+        "thcmb_insert_field": (None, [vp, i, vp]), "thcmb_set_atmos_parameters": (None, [vp, vp]),
+        "thcmb_set_seaice_parameters": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
         "thcmb_p2p_local_handle": (i, [vp, vp]), "thcmb_p2p_open": (i, [vp, vp]), "thcmb_set_ortho": (None, [vp, i]),
         "thcmb_set_vmix_fix": (None, [vp, i]), "thcmb_get_vmix_flags": (None, [vp, vp]),
@@ -233,6 +235,31 @@ class THCM:
         f = np.empty(self.ndim)
         self.L_.thcmb_get_forcing(self.ctx, _np_ptr(f))
         return f
+
+    # ---- coupled mode (coupled_T / coupled_S = 1): what Ocean::synchronize feeds THCM (Ocean.C:1451-1560, THCM.C:1336-1568)
+    SURFACE_FIELDS = ("taux", "tauy", "atmosphere_t", "emip", "emip_pert", "adapted_emip", "atmosphere_q", "atmosphere_a",
+                      "atmosphere_p", "seaice_q", "seaice_m", "seaice_g")
+
+    def insertSurfaceField(self, name, field):
+        """m_inserts::insert_<name> (inserts.F90) with the GLOBAL [M, N] field; takes effect at the next parameter change."""
+        f = np.ascontiguousarray(field, dtype=np.float64).reshape(-1)
+        if f.size != self.settings.N * self.settings.M:
+            raise ValueError("surface fields are global N*M arrays")
+        self.L_.thcmb_insert_field(self.ctx, self.SURFACE_FIELDS.index(name), _np_ptr(f))
+
+    def setAtmosphereParameters(self, pars18):
+        """set_atmos_parameters (usrc.F90:254-310): the 18 doubles of Atmosphere::CommPars; re-runs forcing + lin."""
+        p = np.ascontiguousarray(pars18, dtype=np.float64)
+        if p.size != 18:
+            raise ValueError("Atmosphere::CommPars has 18 members")
+        self.L_.thcmb_set_atmos_parameters(self.ctx, _np_ptr(p))
+
+    def setSeaIceParameters(self, pars7):
+        """set_seaice_parameters (usrc.F90:313-350): the 7 doubles of SeaIce::CommPars; re-runs forcing + lin."""
+        p = np.ascontiguousarray(pars7, dtype=np.float64)
+        if p.size != 7:
+            raise ValueError("SeaIce::CommPars has 7 members")
+        self.L_.thcmb_set_seaice_parameters(self.ctx, _np_ptr(p))
 
     def getMassDiagonal(self):
         """coB of fillcolB (assemble.F90:18-54), THCM::evaluateB."""
@@ -542,6 +569,24 @@ class FortranABI:
         f = np.empty(self.ndim)
         self.L_.get_forcing_(_np_ptr(f))
         return f
+
+    def insert(self, name, field):
+        """m_inserts::insert_<name> (THCM.C:85-98): local n*m surface field."""
+        f = np.ascontiguousarray(field, dtype=np.float64).reshape(-1)
+        assert f.size == self.n * self.m
+        fn = getattr(self.L_, "__m_inserts_MOD_insert_" + name)
+        fn.restype = None; fn.argtypes = [C.c_void_p]
+        fn(_np_ptr(f))
+
+    def set_atmos_parameters(self, pars18):
+        p = np.ascontiguousarray(pars18, dtype=np.float64); assert p.size == 18
+        self.L_.set_atmos_parameters_.restype = None; self.L_.set_atmos_parameters_.argtypes = [C.c_void_p]
+        self.L_.set_atmos_parameters_(_np_ptr(p))
+
+    def set_seaice_parameters(self, pars7):
+        p = np.ascontiguousarray(pars7, dtype=np.float64); assert p.size == 7
+        self.L_.set_seaice_parameters_.restype = None; self.L_.set_seaice_parameters_.argtypes = [C.c_void_p]
+        self.L_.set_seaice_parameters_(_np_ptr(p))
 
     def average_block(self):
         """m_scaling::average_block on the Jacobian of the last matrix_ call (THCM.C:1798); (6,6) [row, col]."""

@@ -67,11 +67,27 @@ void setsres_(int* sres);
 void set_landmask_(int* landm, int* periodic, int* reinit);
 /* replaces get_forcing, src/ocean/forcing.F90:220-233 */
 void get_forcing_(double* frc);
-/* replace m_inserts::insert_{taux,tauy,atmosphere_t,emip}, src/ocean/inserts.F90 (no recompute until next setparcs) */
+/* replace m_inserts::insert_*, src/ocean/inserts.F90:11-281 (THCM.C:85-98): n*m surface fields, i fastest; no recompute
+ * until the next setparcs / set_*_parameters.  emip / adapted_emip / emip_pert are masked by the surface land mask
+ * (inserts.F90:179,198,217); atmosphere_q / _a / _p and seaice_g are ignored unless the matching coupling flag is on
+ * (inserts.F90:45,66,87,145) */
 void __m_inserts_MOD_insert_taux(double* f);
 void __m_inserts_MOD_insert_tauy(double* f);
 void __m_inserts_MOD_insert_atmosphere_t(double* f);
+void __m_inserts_MOD_insert_atmosphere_q(double* f);
+void __m_inserts_MOD_insert_atmosphere_a(double* f);
+void __m_inserts_MOD_insert_atmosphere_p(double* f);
+void __m_inserts_MOD_insert_seaice_q(double* f);
+void __m_inserts_MOD_insert_seaice_m(double* f);
+void __m_inserts_MOD_insert_seaice_g(double* f);
 void __m_inserts_MOD_insert_emip(double* f);
+void __m_inserts_MOD_insert_adapted_emip(double* f);
+void __m_inserts_MOD_insert_emip_pert(double* f);
+/* replace set_atmos_parameters / set_seaice_parameters, src/ocean/usrc.F90:254-350 (Ocean.C:48-49, 1486, 1507): pars points
+ * to Atmosphere::CommPars (18 doubles: tdim qdim nuq eta dqso dqsi dqdt Eo0 Ei0 Cs t0o t0i a0 da tauf tauc comb albf) /
+ * SeaIce::CommPars (7 doubles: zeta a0 Lf s0 rhoo Qvar Q0); both re-run forcing + lin */
+void set_atmos_parameters_(void* pars);
+void set_seaice_parameters_(void* pars);
 /* replaces m_mix::set_vmix_fix, src/ocean/mix.F90:52-59 */
 void __m_mix_MOD_set_vmix_fix(int* fix);
 /* replace m_scaling::average_block / compute (src/ocean/scaling.F90:29-105; THCM.C:106-107, 1798-1807): the local average
@@ -132,6 +148,13 @@ void thcmb_local_gids(const thcmb_ctx* c, int* gids); /* global id of each owned
 /* parameters (setparcs/getparcs); set recomputes forcing and the linear tables */
 void thcmb_set_par(thcmb_ctx* c, int idx, double val);
 double thcmb_get_par(const thcmb_ctx* c, int idx);
+/* coupled mode (coupled_T / coupled_S = 1; BASELINE configs[2]: the ocean block of the coupled model): surface fields on
+ * the GLOBAL N*M grid (every rank passes the same field), `which` = 0 taux, 1 tauy, 2 atmosphere_t, 3 emip, 4 emip_pert,
+ * 5 adapted_emip, 6 atmosphere_q, 7 atmosphere_a, 8 atmosphere_p, 9 seaice_q, 10 seaice_m, 11 seaice_g (inserts.F90);
+ * the two parameter setters follow usrc.F90:254-350 and recompute forcing and the linear tables */
+void thcmb_insert_field(thcmb_ctx* c, int which, const double* field_global);
+void thcmb_set_atmos_parameters(thcmb_ctx* c, const double* pars18);
+void thcmb_set_seaice_parameters(thcmb_ctx* c, const double* pars7);
 void thcmb_get_forcing(thcmb_ctx* c, double* frc_host);
 void thcmb_get_cob(thcmb_ctx* c, double* cob_host);
 

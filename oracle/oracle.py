@@ -58,7 +58,8 @@ def lib():
                                 ("oracle_average_block", None, [vp, vp]), ("oracle_compute_scaling", i, [vp, vp, vp, vp]),
                                 ("oracle_intcond_scaling", i, [vp, vp, vp]),
                                 ("oracle_set_vmix_fix", None, [vp, i]), ("oracle_vmix_fun", None, [vp, vp, vp]),
-                                ("oracle_vmix_flags", None, [vp, vp])]:
+                                ("oracle_vmix_flags", None, [vp, vp]),
+                                ("oracle_set_atmos_parameters", None, [vp, vp]), ("oracle_set_seaice_parameters", None, [vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -168,6 +169,26 @@ class OracleTHCM:
 
     def bad_columns(self):
         return self.L_.oracle_bad_columns(self.h)
+
+    FIELDS = ("taux", "tauy", "tatm", "emip", "spert", "adapted_emip", "qatm", "albe", "patm", "qsa", "msi", "gsi")
+
+    def set_field(self, name, f):
+        """m_inserts::insert_* (inserts.F90): surface field [M, N] (i fastest); no recompute until the next setpar."""
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        assert f.size == self.n * self.m
+        self.L_.oracle_set_field(self.h, self.FIELDS.index(name), _p(f))
+
+    def set_atmos_parameters(self, pars18):
+        """usrc.F90:254-310 with the 18 doubles of Atmosphere::CommPars; re-runs forcing + lin."""
+        p = np.ascontiguousarray(pars18, dtype=np.float64)
+        assert p.size == 18
+        self.L_.oracle_set_atmos_parameters(self.h, _p(p))
+
+    def set_seaice_parameters(self, pars7):
+        """usrc.F90:313-350 with the 7 doubles of SeaIce::CommPars; re-runs forcing + lin."""
+        p = np.ascontiguousarray(pars7, dtype=np.float64)
+        assert p.size == 7
+        self.L_.oracle_set_seaice_parameters(self.h, _p(p))
 
     def forcing(self):
         f = np.empty(self.ndim)

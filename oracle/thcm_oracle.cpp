@@ -1653,11 +1653,39 @@ void oracle_get_grid(void* h, double* x, double* y, double* z, double* xu, doubl
     std::memcpy(z, o->z.data(), sizeof(double) * (o->l + 1)); std::memcpy(zw, o->zw.data(), sizeof(double) * (o->l + 1));
     std::memcpy(dfzT, o->dfzT.data(), sizeof(double) * (o->l + 1)); std::memcpy(dfzW, o->dfzW.data(), sizeof(double) * (o->l + 1));
 }
-// surface fields (inserts.F90): which = 0 taux,1 tauy,2 tatm,3 emip,4 spert
+// surface fields (inserts.F90:11-281): which = 0 taux, 1 tauy, 2 tatm (atmosphere_t), 3 emip, 4 spert (emip_pert),
+// 5 adapted_emip, 6 qatm (atmosphere_q), 7 albe (atmosphere_a), 8 patm (atmosphere_p), 9 qsa (seaice_q), 10 msi (seaice_m),
+// 11 gsi (seaice_g).  The E-P fields are masked by the surface land mask (inserts.F90:179,198,217); q / a / p / g are only
+// taken when the matching coupling flag is on (inserts.F90:45,66,87,145).  No recompute until the next setpar.
 void oracle_set_field(void* h, int which, const double* f) {
     Oracle* o = (Oracle*)h;
-    std::vector<double>* dst[] = {&o->taux, &o->tauy, &o->tatm, &o->emip, &o->spert};
-    std::memcpy(dst[which]->data(), f, sizeof(double) * o->n * o->m);
+    std::vector<double>* dst[] = {&o->taux, &o->tauy, &o->tatm, &o->emip, &o->spert, &o->adapted_emip,
+                                  &o->qatm, &o->albe, &o->patm, &o->qsa, &o->msi, &o->gsi};
+    if (which == 6 && !(o->coupled_T == 1 || o->coupled_S == 1)) return;
+    if (which == 7 && o->coupled_T != 1) return;
+    if ((which == 8 || which == 11) && o->coupled_S != 1) return;
+    const bool masked = which >= 3 && which <= 5;
+    size_t pos = 0;
+    for (int j = 1; j <= o->m; j++) for (int i = 1; i <= o->n; i++, pos++)
+        o->f2(*dst[which], i, j) = masked ? f[pos] * (1 - o->lm(i, j, o->l)) : f[pos];
+}
+// usrc.F90:254-310: pars = the 18 doubles of Atmosphere::CommPars (tdim qdim nuq eta dqso dqsi dqdt Eo0 Ei0 Cs t0o t0i a0 da
+// tauf tauc comb albf); nus and lvsc are frozen at the COMB / SALT / TEMP values of the moment of the call
+void oracle_set_atmos_parameters(void* h, const double* pars) {
+    Oracle* o = (Oracle*)h;
+    o->qdim = pars[1]; o->nuq = pars[2]; o->eta = pars[3]; o->dqso = pars[4]; o->eo0 = pars[7];
+    o->albe0 = pars[12]; o->albed = pars[13];
+    o->nus = o->par[COMB] * o->par[SALT] * o->eta * o->qdim * o->QSnd;
+    o->lvsc = o->par[COMB] * o->par[TEMP] * rhodim * lv * o->QTnd;
+    o->forcing();
+    o->lin();
+}
+// usrc.F90:313-350: pars = the 7 doubles of SeaIce::CommPars (zeta a0 Lf s0 rhoo Qvar Q0)
+void oracle_set_seaice_parameters(void* h, const double* pars) {
+    Oracle* o = (Oracle*)h;
+    o->zeta = pars[0]; o->a0 = pars[1]; o->Lf = pars[2]; o->Qvar = pars[5]; o->Q0 = pars[6];
+    o->forcing();
+    o->lin();
 }
 
 // maximal graph (THCM.C:2300-2580): call with col == nullptr to get nnz

@@ -108,3 +108,39 @@ def smooth_state(s, value=1.234):  # test_ocean.C:141
 def apply_pars(obj, pars, setter="setpar"):
     for k, v in pars.items():
         getattr(obj, setter)(PAR_INDEX[k], v)
+
+
+# ---- coupled mode (BASELINE configs[2]: the ocean block of the coupled ocean + atmosphere + sea-ice model) ----
+def coupled_inputs(s, seed=7):
+    """Seeded stand-ins for what Ocean::synchronize hands THCM in a coupled run (Ocean.C:1451-1560): the atmosphere's
+    temperature / humidity / albedo / precipitation, the sea-ice heat flux / mask / salt-flux correction on the GLOBAL
+    surface grid, and the two CommPars structs (AtmosLocal.H / SeaIce.H defaults order of magnitude)."""
+    rng = np.random.default_rng(seed)
+    n, m = s.N, s.M
+    yy = np.linspace(-1.0, 1.0, m)[:, None] * np.ones((1, n))
+    fields = {
+        "tatm": 0.3 * np.cos(1.3 * yy) + 0.05 * rng.standard_normal((m, n)),
+        "qatm": 0.2 * rng.standard_normal((m, n)),
+        "albe": rng.random((m, n)),
+        "patm": 0.1 * rng.standard_normal((m, n)),
+        "qsa": 0.5 * rng.standard_normal((m, n)),
+        "msi": (rng.random((m, n)) < 0.3).astype(np.float64),   # 0 / 1 sea-ice mask, ~30 % ice covered
+        "gsi": 0.01 * rng.standard_normal((m, n)),
+        "emip": rng.standard_normal((m, n)),
+        "adapted_emip": rng.standard_normal((m, n)),
+        "spert": rng.standard_normal((m, n)),
+    }
+    # Atmosphere::CommPars: tdim qdim nuq eta dqso dqsi dqdt Eo0 Ei0 Cs t0o t0i a0 da tauf tauc comb albf
+    atmos = np.array([1.0, 0.01, 5.9e-9 * 1e9, 4.87e-2, 5.0e-4, 5.3e-4, 6.4e-4, 2.0e-3, 9.0e-4, 1.1e-2, 15.0, -5.0, 0.3, 0.5,
+                      4.7, 4.7, 1.0, 0.1])
+    # SeaIce::CommPars: zeta a0 Lf s0 rhoo Qvar Q0
+    seaice = np.array([7.3e-3 * 1e3, -0.0575, 3.347e5, 35.0, 1.024e3, 8.9, -100.0 * 1e-2])
+    return fields, atmos, seaice
+
+
+def apply_coupled(obj, fields, atmos, seaice):
+    """obj: OracleTHCM / EmuTHCM (set_field, set_atmos_parameters, set_seaice_parameters)."""
+    for k, f in fields.items():
+        obj.set_field(k, f)
+    obj.set_atmos_parameters(atmos)
+    obj.set_seaice_parameters(seaice)

@@ -36,7 +36,8 @@ def lib():
                                 ("emu_jacobian", None, [vp, vp, vp, vp]), ("emu_crs", ll, [vp, vp, vp, vp, vp, vp]),
                                 ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp]),
                                 ("emu_check_tiles", ll, [vp, vp, vp]), ("emu_fast_tiles", ll, [vp, vp]),
-                                ("emu_vmix_control", None, [vp, i, i]), ("emu_set_vmix_fix", None, [vp, i])]:
+                                ("emu_vmix_control", None, [vp, i, i]), ("emu_set_vmix_fix", None, [vp, i]),
+                                ("emu_set_field", None, [vp, i, vp]), ("emu_set_atmos", None, [vp, vp]), ("emu_set_seaice", None, [vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -67,6 +68,20 @@ class EmuTHCM:
 
     def getpar(self, idx):
         return self.L_.emu_get_par(self.h, idx)
+
+    FIELDS = ("taux", "tauy", "tatm", "emip", "spert", "adapted_emip", "qatm", "albe", "patm", "qsa", "msi", "gsi")
+
+    def set_field(self, name, f):
+        f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
+        self.L_.emu_set_field(self.h, self.FIELDS.index(name), _p(f))
+
+    def set_atmos_parameters(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64); assert p.size == 18
+        self.L_.emu_set_atmos(self.h, _p(p))
+
+    def set_seaice_parameters(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64); assert p.size == 7
+        self.L_.emu_set_seaice(self.h, _p(p))
 
     def block(self):
         out = np.zeros(9, dtype=np.int32)

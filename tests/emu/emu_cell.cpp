@@ -29,7 +29,7 @@ AsmArgs make_args(Emu* e, const double* un, const double* halo) {
     const Block& b = c->blk;
     AsmArgs a;
     a.b = DevBlock{b.N, b.M, b.L, b.i0, b.j0, b.n0, b.m0, b.periodic, b.wrap_x, b.halo_w, b.halo_e, b.halo_s, b.halo_n, b.hk, b.ncell()};
-    a.t = c->tab; a.t.jt = c->jt_host.data(); a.t.kt = c->kt_host.data();
+    a.t = c->tab; a.t.jt = c->jt_host.data(); a.t.kt = c->kt_host.data(); a.t.msi = c->msi_local.data();
     a.un = un; a.halo = halo; a.nbmask = e->nbmask.data(); a.surf = e->surf.data(); a.uvlive = e->uvlive.data();
     a.frc = c->frc_local.data(); a.rowptr = c->rowptr_host.data();
     a.val = nullptr; a.blockcnt = nullptr; a.begA = nullptr; a.jcoA = nullptr; a.coA = nullptr; a.out = nullptr; a.sign = 1.0;
@@ -105,9 +105,7 @@ void* emu_create(const thcmb_settings* s, const int* landm) {
     thcmb_ctx* c = &e->c;
     c->s = *s;
     if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) { delete e; return nullptr; }
-    size_t nm = (size_t)s->N * s->M;
-    for (auto* f : {&c->taux, &c->tauy, &c->tatm, &c->emip, &c->spert, &c->adapted_emip}) f->assign(nm, 0.0);
-    build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false); vmix_init(c);
+    build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false); vmix_init(c); init_surface_fields(c);
     build_static_host(c, e->nbmask, e->surf, e->uvlive, e->send_idx, e->recv_slot);
     compute_forcing(c); compute_tables(c); compute_cob(c);
     return e;
@@ -117,6 +115,10 @@ void emu_destroy(void* h) { delete (Emu*)h; }
 void emu_vmix_control(void* h, int temp, int salt) { thcmb_ctx* c = &((Emu*)h)->c; if (c->vmix_flag >= 2 && c->vmix_fix == 0) { vmix_set_flags(c, temp, salt); compute_tables(c); } }
 void emu_set_vmix_fix(void* h, int fix) { ((Emu*)h)->c.vmix_fix = fix; }
 void emu_set_par(void* h, int idx, double v) { thcmb_ctx* c = &((Emu*)h)->c; c->par[idx] = v; compute_forcing(c); compute_tables(c); compute_cob(c); }
+// m_inserts / set_atmos_parameters / set_seaice_parameters (coupled mode)
+void emu_set_field(void* h, int which, const double* f) { insert_surface_field(&((Emu*)h)->c, which, f); }
+void emu_set_atmos(void* h, const double* p) { thcmb_ctx* c = &((Emu*)h)->c; set_atmos_parameters(c, p); compute_forcing(c); compute_tables(c); compute_cob(c); }
+void emu_set_seaice(void* h, const double* p) { thcmb_ctx* c = &((Emu*)h)->c; set_seaice_parameters(c, p); compute_forcing(c); compute_tables(c); compute_cob(c); }
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

@@ -205,3 +205,45 @@ def test_decomp2d_matches_reference_rule():
     # remainders go to the first ranks (TRIOS_Domain.C:267-273)
     b3 = blocks(10, 7, 2, 3)
     assert sum(b["n0"] * b["m0"] for b in b3) == 70
+
+
+# ---- coupled mode (coupled_T / coupled_S = 1, usrc.F90:742-783, forcing.F90:66-164, inserts.F90) ----
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "box_np"])
+@pytest.mark.parametrize("flags", [dict(coupled_T=1, coupled_S=1), dict(coupled_T=1, coupled_S=0), dict(coupled_T=0, coupled_S=1, SRES=0)])
+def test_coupled_mode_bit_exact(name, flags):
+    s, landm, o, e = setup(name, pars=dict(PARS, SUNP=1.0), **flags)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    cases.apply_coupled(e, fields, atmos, seaice)
+    x = cases.random_state(s, landm, scale=0.1)
+    fo = o.forcing()
+    assert np.array_equal(fo, e.forcing(masked=False))
+    assert np.count_nonzero(fo.reshape(-1, 6)[:, 4:]) > 0
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    bo, jo, co, cob = o.matrix(x)
+    be, je, ce = e.crs(x)
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0                        # the T,S / S,T centre entries lie inside the maximal graph
+    assert np.array_equal(vo, e.jacobian(x))
+    # the coupling really changes the operator: the sea-ice mask puts TT,SS / SS,TT entries on the surface level
+    s2, landm2, o2, e2 = setup(name, pars=dict(PARS, SUNP=1.0))
+    assert not np.array_equal(o2.jacobian_graph(x)[0], vo)
+    # a later parameter change keeps nus / lvsc frozen (usrc.F90:297-304) and re-runs forcing + lin
+    for obj in (o, e):
+        obj.setpar(P["COMB"], 0.5)
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+
+
+def test_insert_masks_the_freshwater_fields():
+    # inserts.F90:179,198,217: emip / adapted_emip / emip_pert are multiplied by (1 - landm(i,j,l)) on the way in
+    s, landm, o, e = setup("natl8", pars=dict(PARS, HMTP=0.3, SPER=0.2), its=0, SRES=0)
+    fields, _, _ = cases.coupled_inputs(s)
+    for k in ("emip", "adapted_emip", "spert", "tatm", "qatm", "msi"):
+        o.set_field(k, fields[k]); e.set_field(k, fields[k])
+    o.setpar(P["SALT"], 1.0); e.setpar(P["SALT"], 1.0)
+    x = cases.random_state(s, landm)
+    o.rhs(x)
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))
+    assert np.array_equal(o.rhs(x), e.rhs(x))

@@ -205,6 +205,74 @@ def test_fortran_abi_drop_in(gpu, name):
     f.finalize()
 
 
+ORACLE_TO_INSERT = {"tatm": "atmosphere_t", "qatm": "atmosphere_q", "albe": "atmosphere_a", "patm": "atmosphere_p", "qsa": "seaice_q",
+                    "msi": "seaice_m", "gsi": "seaice_g", "emip": "emip", "adapted_emip": "adapted_emip", "spert": "emip_pert"}
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p33", "global4deg"])
+@pytest.mark.parametrize("flags", [dict(coupled_T=1, coupled_S=1), dict(coupled_T=1, coupled_S=0), dict(coupled_T=0, coupled_S=1, SRES=0)])
+def test_coupled_mode_bit_exact(gpu, name, flags, monkeypatch):
+    """BASELINE configs[2]: the ocean block of the coupled model (coupled_T / coupled_S = 1, usrc.F90:742-783,
+    forcing.F90:66-164) with seeded atmosphere / sea-ice fields and CommPars: residual, graph-order Jacobian (TMA kernels and
+    the per-position kernel), Fortran-order CRS and forcing bit-exact against the oracle."""
+    s, landm, o, t = setup(gpu, name, pars=dict(PARS, SUNP=1.0), **flags)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    for k, f in fields.items():
+        t.insertSurfaceField(ORACLE_TO_INSERT[k], f)
+    t.setAtmosphereParameters(atmos)
+    t.setSeaIceParameters(seaice)
+    x = cases.random_state(s, landm, scale=0.1)
+    xd = dev(x)
+    assert np.array_equal(t.getForcing(), o.forcing())
+    B = o.rhs(x)
+    out = t.new_vector()
+    t.rhs_fortran_sign(xd, out)
+    assert np.array_equal(out.cpu().numpy(), B)
+    t.evaluate(xd, None, True)
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0 and np.array_equal(t.jacobian_values_host(), vo)
+    bo, jo, cf, cob = o.matrix(x)
+    beg, jco, coA = t.jacobian_crs(xd)
+    assert np.array_equal(beg.cpu().numpy(), bo) and np.array_equal(jco.cpu().numpy(), jo) and np.array_equal(coA.cpu().numpy(), cf)
+    t.close()
+    monkeypatch.setenv("THCM_ASM_PIPE", "0")
+    s, landm, _, t0 = setup(gpu, name, pars=dict(PARS, SUNP=1.0), **flags)
+    for k, f in fields.items():
+        t0.insertSurfaceField(ORACLE_TO_INSERT[k], f)
+    t0.setAtmosphereParameters(atmos)
+    t0.setSeaIceParameters(seaice)
+    t0.evaluate(xd, None, True)
+    assert np.array_equal(t0.jacobian_values_host(), vo)
+    t0.close()
+
+
+def test_coupled_mode_through_the_fortran_symbols(gpu):
+    """The same through the B1 symbols Ocean.C / THCM.C bind: m_inserts::insert_*, set_atmos_parameters_, set_seaice_parameters_."""
+    from oracle.oracle import OracleTHCM
+    s, landm = CASES["natl8"](coupled_T=1, coupled_S=1)
+    o = OracleTHCM(s, landm)
+    f = gpu.FortranABI()
+    f.global_initialize(s)
+    f.init(s, landm)
+    for k, v in dict(PARS, SUNP=1.0).items():
+        o.setpar(P[k], v)
+        f.setparcs(k, v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    for k, fld in fields.items():
+        f.insert(ORACLE_TO_INSERT[k], fld)
+    f.set_atmos_parameters(atmos)
+    f.set_seaice_parameters(seaice)
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(f.rhs(x), o.rhs(x))
+    beg, jco, co, cob = f.matrix(x)
+    bo, jo, cf, cobo = o.matrix(x)
+    assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf) and np.array_equal(cob, cobo)
+    assert np.array_equal(f.get_forcing(), o.forcing())
+    f.finalize()
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
 def test_spmv_and_vector_kernels(gpu, name):
     from oracle.oracle import spmv, matavec
