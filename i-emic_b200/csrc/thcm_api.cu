@@ -774,6 +774,63 @@ void __m_global_MOD_initialize(int* N, int* M, int* L, double* xmin, double* xma
 }
 void __m_global_MOD_get_landm(int* landm) { memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size()); }
 void __m_global_MOD_finalize(void) { g_landm_global.clear(); g_have_global = false; }
+/* m_global (global.F90:215-608): the global-domain arrays THCM.C reads on the root before it scatters them */
+void __m_global_MOD_get_current_landm(int* landm) { memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size()); }
+void __m_global_MOD_set_landm(int* landm) {   // global.F90:349-381, incl. the land-inversion fix
+    if (!g_have_global) fatal("m_global::set_landm before m_global::initialize");
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    memcpy(g_landm_global.data(), landm, sizeof(int) * g_landm_global.size());
+    auto LMg = [&](int i, int j, int k) -> int& { return g_landm_global[(size_t)i + (size_t)(n + 2) * (j + (size_t)(m + 2) * k)]; };
+    for (int i = 1; i <= n; i++) for (int j = 1; j <= m; j++) for (int k = l; k >= 2; k--)
+        if (LMg(i, j, k) == LAND && LMg(i, j, k - 1) == OCEAN) LMg(i, j, k - 1) = LAND;
+}
+void __m_global_MOD_set_maskfile(const char* maskfile) {   // global.F90:215-224 + the topofit of the next get_landm
+    if (!g_have_global) fatal("m_global::set_maskfile before m_global::initialize");
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    std::string p = maskfile ? maskfile : "";
+    std::vector<int> lm;
+    if (!read_mask_file(p.c_str(), n, m, l, lm)) {
+        const char* dd = getenv("THCM_DATA_DIR");
+        std::string p2 = std::string(dd ? dd : ".") + "/mkmask/" + p;
+        if (!read_mask_file(p2.c_str(), n, m, l, lm)) fatal("cannot read land mask " + p + " / " + p2);
+    }
+    __m_global_MOD_set_landm(lm.data());
+}
+static void need_no_datafile(bool needs_file, const char* what) {
+    if (needs_file) fatal(std::string(what) + ": this option reads a data file (Levitus / Trenberth) that does not ship with the reference; "
+                          "provide the field through m_inserts instead");
+}
+void __m_global_MOD_get_windfield(double* taux, double* tauy) {   // global.F90:425-463
+    need_no_datafile(g_set.iza < 2, "m_global::get_windfield (iza < 2)");
+    const size_t nm = (size_t)g_set.N * g_set.M;
+    for (size_t q = 0; q < nm; q++) { taux[q] = 0.0; tauy[q] = 0.0; }
+}
+void __m_global_MOD_get_temforcing(double* tatm) {                // global.F90:465-506
+    need_no_datafile(g_set.coupled_T == 0 && g_set.ite == 0 && g_set.TRES != 0, "m_global::get_temforcing (ite = 0, TRES = 1)");
+    for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) tatm[q] = 0.0;
+}
+void __m_global_MOD_get_salforcing(double* emip) {                // global.F90:534-560
+    need_no_datafile(g_set.its == 0 && g_set.coupled_S == 0 && g_set.SRES != 0, "m_global::get_salforcing (its = 0, SRES = 1)");
+    for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) emip[q] = 0.0;
+}
+void __m_global_MOD_get_internal_temforcing(double*) { need_no_datafile(true, "m_global::get_internal_temforcing"); }
+void __m_global_MOD_get_internal_salforcing(double*) { need_no_datafile(true, "m_global::get_internal_salforcing"); }
+void __m_global_MOD_get_spert(double* spert) {                    // global.F90:587-608 (rd_spertm = 0)
+    for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) spert[q] = (double)g_set.SRES;
+}
+/* global grid arrays pushed by THCM.C (global.F90:241-293).  The library builds the same arrays itself (grid.F90 formulas,
+ * build_grid); a caller-provided array is only checked against them once the model exists. */
+static void check_grid(const char* name, const std::vector<double>& mine, int first, int n, const double* a) {
+    for (int i = 0; i < n && first + i < (int)mine.size(); i++)
+        if (std::fabs(mine[first + i] - a[i]) > 1e-12 * (1.0 + std::fabs(a[i])))
+            fatal(std::string("set_global_") + name + ": the caller's grid differs from grid.F90's");
+}
+void set_global_x(int* n, double* a) { if (g_ctx) check_grid("x", g_ctx->x, 1, *n, a); }
+void set_global_y(int* n, double* a) { if (g_ctx) check_grid("y", g_ctx->y, 1, *n, a); }
+void set_global_z(int* n, double* a) { if (g_ctx) check_grid("z", g_ctx->z, 1, *n, a); }
+void set_global_xu(int* n, double* a) { if (g_ctx) check_grid("xu", g_ctx->xu, 0, *n, a); }
+void set_global_yv(int* n, double* a) { if (g_ctx) check_grid("yv", g_ctx->yv, 0, *n, a); }
+void set_global_zw(int* n, double* a) { if (g_ctx) check_grid("zw", g_ctx->zw, 0, *n, a); }
 
 void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, double* ymin, double* ymax, double* alphaT, double* alphaS,
            int* ih, int* vmix, int* tap, int* rho_mixing, int* coriolis_on, int* periodic, int* landm, double* taux, double* tauy,
@@ -806,10 +863,11 @@ void __m_mat_MOD_get_array_sizes(int* nrows, int* nnz) {  // mat.F90:56-68
     *nrows = G()->blk.ndim();
     *nnz = G()->blk.ndim() * (NUN * NP + 1);
 }
-void __m_mat_MOD_set_pointers(int* nrows, int* nnz, int* begA, int* jcoA, double* coA, double* coB, int*, int*, double*) {
+void __m_mat_MOD_set_pointers(int* nrows, int* nnz, int* begA, int* jcoA, double* coA, double* coB, int* begF, int* jcoF, double* coF) {
     (void)nrows; (void)nnz;
     thcmb_ctx* c = G();
     c->begA = begA; c->jcoA = jcoA; c->coA = coA; c->coB = coB;
+    c->begF = begF; c->jcoF = jcoF; c->coF = coF;
 }
 void rhs_(double* un, double* B) {
     thcmb_ctx* c = G();
@@ -880,6 +938,44 @@ void __m_inserts_MOD_insert_emip_pert(double* f) { insert_surface_field(G(), SF_
 void set_atmos_parameters_(void* pars) { thcmb_set_atmos_parameters(G(), (const double*)pars); }
 void set_seaice_parameters_(void* pars) { thcmb_set_seaice_parameters(G(), (const double*)pars); }
 void __m_mix_MOD_set_vmix_fix(int* fix) { G()->vmix_fix = *fix; }
+/* m_usr::set_internal_forcing (usr.F90:267-300; THCM.C:594), m_thcm_utils::get_landm / loadbal_weights (thcm_utils.F90:259, 325) */
+void __m_usr_MOD_set_internal_forcing(double* temp, double* salt) { set_internal_forcing(G(), temp, salt); }
+void __m_thcm_utils_MOD_get_landm(int* landm) { thcmb_ctx* c = G(); memcpy(landm, c->landm.data(), sizeof(int) * c->landm.size()); }
+void __m_thcm_utils_MOD_loadbal_weights(double* weights, double*, double*, double*) { loadbal_weights(G(), weights); }
+/* m_probe (probe.F90; THCM.C:1568-1763): surface diagnostics of the coupled model, n*m fields, host state vector */
+void __m_probe_MOD_get_atmosphere_t(double* f) { probe_get_field(G(), SF_TATM, f); }
+void __m_probe_MOD_get_atmosphere_q(double* f) { probe_get_field(G(), SF_QATM, f); }
+void __m_probe_MOD_get_atmosphere_p(double* f) { probe_get_field(G(), SF_PATM, f); }
+void __m_probe_MOD_get_emip(double* f) { probe_get_field(G(), SF_EMIP, f); }
+void __m_probe_MOD_get_adapted_emip(double* f) { probe_get_field(G(), SF_ADAPTED_EMIP, f); }
+void __m_probe_MOD_get_emip_pert(double* f) { probe_get_field(G(), SF_SPERT, f); }
+void __m_probe_MOD_get_taux(double* f) { probe_get_field(G(), SF_TAUX, f); }
+void __m_probe_MOD_get_tauy(double* f) { probe_get_field(G(), SF_TAUY, f); }
+void __m_probe_MOD_get_suno(double* f) { probe_get_suno(G(), f); }
+void __m_probe_MOD_compute_evap(double* evap, double* un) { probe_compute_evap(G(), un, evap); }
+void __m_probe_MOD_get_salflux(double* un, double* salflux, double* scorr, double* qsoaflux, double* qsosflux) {
+    probe_get_salflux(G(), un, salflux, scorr, qsoaflux, qsosflux);
+}
+void __m_probe_MOD_get_temflux(double* un, double* totflux, double* swflux, double* shflux, double* lhflux, double* siflux, double* simask) {
+    probe_get_temflux(G(), un, totflux, swflux, shflux, lhflux, siflux, simask);
+}
+void __m_probe_MOD_get_derivatives(double* un, double* dftdm, double* dfsdq, double* dfsdm, double* dfsdg) {
+    probe_get_derivatives(G(), un, dftdm, dfsdq, dfsdm, dfsdg);
+}
+/* m_integrals (integrals.F90:17-88; THCM.C:2133, 2155) */
+void __m_integrals_MOD_salt_advection(double* un, double* check) { integrals_salt_advection(G(), un, check); }
+void __m_integrals_MOD_salt_diffusion(double* un, double* check) { integrals_salt_diffusion(G(), un, check); }
+/* forcing.F90:235-280 (THCM.C:848); usrc.F90:201-251, 421-431 (Ocean.C:889, 1610; THCM.C:1974); inout.F90:20 (Ocean.C:1877) */
+void get_stochastic_forcing_(void) { thcmb_ctx* c = G(); stochastic_forcing(c, c->begF, c->jcoF, c->coF); refresh_params(c); }
+void getdeps_(double* Ooa, double* Os, double* nus, double* eta, double* lvsc, double* qdim, double* pqsnd) {
+    double o[7]; get_deps(G(), o);
+    *Ooa = o[0]; *Os = o[1]; *nus = o[2]; *eta = o[3]; *lvsc = o[4]; *qdim = o[5]; *pqsnd = o[6];
+}
+void get_parameters_(double* r0dim, double* udim, double* hdim) { get_dim_parameters(G(), r0dim, udim, hdim); }
+void get_nondimensionalization_parameters_(double* out) { for (int i = 0; i < NP; i++) out[i] = 0.0; }
+void writeparams_(void) { write_params(G()); }
+void write_data_(double* u, int* ofile, int* lab) { write_data(G(), u, *ofile, lab); }
+void write_levitus_(const char*) { fprintf(stderr, "thcm_b200: write_levitus is a debugging dump of Levitus fields the library never reads; nothing written\n"); }
 /* m_scaling (scaling.F90:29-105) on the Jacobian of the last matrix_ call, m_thcm_utils::intcond_scaling (thcm_utils.F90:285-309) */
 void __m_scaling_MOD_average_block(double* db) { average_block(G(), db); }
 void __m_scaling_MOD_compute(double* db, double* rowscales, double* colscales) { scaling_compute(G(), db, rowscales, colscales); }

@@ -255,8 +255,15 @@ void compute_forcing(thcmb_ctx* c) {
                                              gamma * par[HMTP] * (F2(c->adapted_emip, gi, gj) - adapted_salcor) +
                                              par[SPER] * (1 - s.SRES + s.SRES * par[BIOT]) * (F2(c->spert, gi, gj) - spertcor);
         }
-        // forcing.F90:199-209: the w-row forcing is built from internal_temp/internal_salt, which are identically
-        // zero unless Levitus data files are read (none ship with the reference) => Frc(w) = 0.
+    }
+    // forcing.F90:199-209: the w-row forcing from internal_temp / internal_salt -- identically zero unless the caller
+    // provided them (m_usr::set_internal_forcing; the Levitus files the reference would read do not ship with it)
+    if (c->internal_set) {
+        auto F3 = [&](const std::vector<double>& f, int i, int j, int k) { return f[(size_t)(i - 1) + (size_t)n * ((j - 1) + (size_t)m * (k - 1))]; };
+        for (int k = 1; k <= l - 1; k++) for (int gj = b.j0 + 1; gj <= b.j0 + b.m0; gj++) for (int gi = b.i0 + 1; gi <= b.i0 + b.n0; gi++)
+            c->frc_raw[row(gi, gj, k, WW)] = -par[COMB] * (1 - LM(c, gi, gj, k)) * par[RAYL] *
+                                             (par[LAMB] * (F3(c->internal_salt, gi, gj, k) + F3(c->internal_salt, gi, gj, k + 1)) / 2. -
+                                              (F3(c->internal_temp, gi, gj, k) + F3(c->internal_temp, gi, gj, k + 1)) / 2.);
     }
     c->frc_local = c->frc_raw;
     for (int k = 1; k <= l; k++) for (int gj = b.j0 + 1; gj <= b.j0 + b.m0; gj++) for (int gi = b.i0 + 1; gi <= b.i0 + b.n0; gi++)
@@ -310,6 +317,13 @@ void set_seaice_parameters(thcmb_ctx* c, const double* p) {
     c->ice_zeta = p[0]; c->ice_a0 = p[1]; c->ice_Lf = p[2]; c->ice_Qvar = p[5]; c->ice_Q0 = p[6];
     if (p[3] != s0) fprintf(stderr, "thcm_b200: WARNING conflicting reference salinity s0\n");
     if (p[4] != rhodim) fprintf(stderr, "thcm_b200: WARNING conflicting sea water density rhodim\n");
+}
+// m_usr::set_internal_forcing (usr.F90:267-300): N*M*L fields, i fastest; takes effect at the next forcing
+void set_internal_forcing(thcmb_ctx* c, const double* temp, const double* salt) {
+    const size_t tot = (size_t)c->s.N * c->s.M * c->s.L;
+    c->internal_temp.assign(temp, temp + tot);
+    c->internal_salt.assign(salt, salt + tot);
+    c->internal_set = true;
 }
 // allocation of the surface fields of m_usr (usr.F90 allocate_usr) + atmos_coef, between stpnt and forcing (usrc.F90:118-131)
 void init_surface_fields(thcmb_ctx* c) {

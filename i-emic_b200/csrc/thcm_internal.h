@@ -131,6 +131,8 @@ struct thcmb_ctx {
            atm_albed = 0.0, atm_lvsc = 0.0, atm_Ooa = 1.0, atm_Os = 1.0;
     std::vector<double> suno;                                         // shortwave profile (usrc.F90:1228), index j
     double ice_zeta = 0.0, ice_a0 = -0.0575, ice_Lf = 3.347e+05, ice_Qvar = 0.0, ice_Q0 = 0.0;
+    std::vector<double> internal_temp, internal_salt;                 // m_usr::set_internal_forcing (usr.F90:267-300), N*M*L
+    bool internal_set = false;
     std::vector<double> msi_local;                                    // msi on the owned columns (n0*m0, i fastest)
     double* d_msi = nullptr;
     std::vector<double> frc_local;   // owned rows, masked by the rows `boundaries` turns into identity rows
@@ -207,9 +209,11 @@ struct thcmb_ctx {
     std::vector<int> prof_kid;
     // borrowed host CRS pointers (m_mat::set_pointers)
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
+    int *begF = nullptr, *jcoF = nullptr; double *coF = nullptr;   // get_stochastic_forcing (forcing.F90:235-280)
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
-    int fused_cgs2 = 1;             // DGKS: first update + second projection in one sweep over the basis (THCM_FUSED_CGS2=0: separate)
+    int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (THCM_FUSED_CGS2=1); off until
+                                    // it has been measured on the GPU (single rank first: the multi-rank tail is shared with multi_dot)
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 
@@ -229,6 +233,23 @@ enum SurfaceField { SF_TAUX = 0, SF_TAUY, SF_TATM, SF_EMIP, SF_SPERT, SF_ADAPTED
 void insert_surface_field(thcmb_ctx* c, int which, const double* f);
 void set_atmos_parameters(thcmb_ctx* c, const double* pars18);
 void set_seaice_parameters(thcmb_ctx* c, const double* pars7);
+void set_internal_forcing(thcmb_ctx* c, const double* temp, const double* salt);
+// diagnostics / output symbols of the B1 boundary (thcm_probe.cpp; probe.F90, integrals.F90, forcing.F90:235, usrc.F90:201-251)
+bool probe_get_field(const thcmb_ctx* c, int which, double* out);
+void probe_get_suno(const thcmb_ctx* c, double* out);
+void probe_compute_evap(const thcmb_ctx* c, const double* un, double* evap);
+void probe_get_salflux(const thcmb_ctx* c, const double* un, double* salflux, double* correction, double* qsoaflux, double* qsosflux);
+void probe_get_temflux(const thcmb_ctx* c, const double* un, double* totflux, double* swflux, double* shflux, double* lhflux,
+                       double* siflux, double* simask);
+void probe_get_derivatives(thcmb_ctx* c, const double* un, double* dftdm, double* dfsdq, double* dfsdm, double* dfsdg);
+void integrals_salt_advection(const thcmb_ctx* c, const double* un, double* check);
+void integrals_salt_diffusion(const thcmb_ctx* c, const double* un, double* check);
+void stochastic_forcing(thcmb_ctx* c, int* begF, int* jcoF, double* coF);
+void get_deps(const thcmb_ctx* c, double* out7);
+void get_dim_parameters(const thcmb_ctx* c, double* r0, double* u0, double* h0);
+void loadbal_weights(const thcmb_ctx* c, double* array);
+void write_params(const thcmb_ctx* c);
+void write_data(const thcmb_ctx* c, const double* u, int ofile, int* lab);
 void compute_tables(thcmb_ctx* c);
 void vmix_init(thcmb_ctx* c);
 void vmix_set_flags(thcmb_ctx* c, int temp, int salt);

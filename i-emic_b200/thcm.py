@@ -588,6 +588,69 @@ class FortranABI:
         self.L_.set_seaice_parameters_.restype = None; self.L_.set_seaice_parameters_.argtypes = [C.c_void_p]
         self.L_.set_seaice_parameters_(_np_ptr(p))
 
+    # ---- diagnostics / setup symbols (thcm_probe.cpp; THCM.C:136-170, Ocean.C:42-49) ----
+    def _call(self, name, *args):
+        fn = getattr(self.L_, name)
+        fn.restype = None; fn.argtypes = [C.c_void_p] * len(args)
+        fn(*args)
+
+    def probe(self, name):
+        """m_probe::get_<name> for atmosphere_t/q/p, emip, adapted_emip, emip_pert, taux, tauy, suno: [m, n]."""
+        out = np.full((self.m, self.n), np.nan)
+        self._call("__m_probe_MOD_get_" + name, _np_ptr(out))
+        return out
+
+    def compute_evap(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64); out = np.empty((self.m, self.n))
+        self._call("__m_probe_MOD_compute_evap", _np_ptr(out), _np_ptr(un))
+        return out
+
+    def get_salflux(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        sf, qa, qs = (np.empty((self.m, self.n)) for _ in range(3)); corr = np.zeros(1)
+        self._call("__m_probe_MOD_get_salflux", _np_ptr(un), _np_ptr(sf), _np_ptr(corr), _np_ptr(qa), _np_ptr(qs))
+        return sf, corr[0], qa, qs
+
+    def get_temflux(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        f = [np.zeros((self.m, self.n)) for _ in range(6)]
+        self._call("__m_probe_MOD_get_temflux", _np_ptr(un), *[_np_ptr(a) for a in f])
+        return dict(zip(("totflux", "swflux", "shflux", "lhflux", "siflux", "simask"), f))
+
+    def get_derivatives(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        f = [np.zeros((self.m, self.n)) for _ in range(4)]
+        self._call("__m_probe_MOD_get_derivatives", _np_ptr(un), *[_np_ptr(a) for a in f])
+        return tuple(f)
+
+    def salt_integrals(self, un):
+        """m_integrals::salt_advection / salt_diffusion (THCM.C:2133, 2155): the two per-cell integrands."""
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        a, d = np.zeros(self.ndim // 6), np.zeros(self.ndim // 6)
+        self._call("__m_integrals_MOD_salt_advection", _np_ptr(un), _np_ptr(a))
+        self._call("__m_integrals_MOD_salt_diffusion", _np_ptr(un), _np_ptr(d))
+        return a, d
+
+    def get_stochastic_forcing(self):
+        self.L_.get_stochastic_forcing_.restype = None; self.L_.get_stochastic_forcing_.argtypes = []
+        self.L_.get_stochastic_forcing_()
+        return self.begF.copy(), self.jcoF.copy(), self.coF.copy()
+
+    def set_internal_forcing(self, temp, salt):
+        t = np.ascontiguousarray(temp, dtype=np.float64).reshape(-1); s_ = np.ascontiguousarray(salt, dtype=np.float64).reshape(-1)
+        self._call("__m_usr_MOD_set_internal_forcing", _np_ptr(t), _np_ptr(s_))
+
+    def getdeps(self):
+        v = [C.c_double() for _ in range(7)]
+        fn = self.L_.getdeps_; fn.restype = None; fn.argtypes = [C.POINTER(C.c_double)] * 7
+        fn(*[C.byref(x) for x in v])
+        return np.array([x.value for x in v])
+
+    def get_landm(self):
+        out = np.empty((self.l + 2, self.m + 2, self.n + 2), dtype=np.int32)
+        self._call("__m_thcm_utils_MOD_get_landm", _np_ptr(out))
+        return out
+
     def average_block(self):
         """m_scaling::average_block on the Jacobian of the last matrix_ call (THCM.C:1798); (6,6) [row, col]."""
         db = np.zeros(36)

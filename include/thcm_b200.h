@@ -90,6 +90,62 @@ void set_atmos_parameters_(void* pars);
 void set_seaice_parameters_(void* pars);
 /* replaces m_mix::set_vmix_fix, src/ocean/mix.F90:52-59 */
 void __m_mix_MOD_set_vmix_fix(int* fix);
+
+/* ---- setup / diagnostics symbols THCM.C and Ocean.C bind besides the hot path (host code, parameter-change or output
+ * frequency).  They exist so that the reference links against this library without an unresolved symbol. ---- */
+/* m_global (src/ocean/global.F90:215-608; THCM.C:86-102): global-domain mask and forcing arrays read on the root.  Options
+ * that read a Levitus / Trenberth data file (iza < 2, ite = 0 or its = 0 with restoring, internal T/S) fail loudly: those files
+ * do not ship with the reference -- feed the fields through m_inserts instead */
+void __m_global_MOD_set_maskfile(const char* maskfile);
+void __m_global_MOD_get_current_landm(int* landm);
+void __m_global_MOD_set_landm(int* landm);
+void __m_global_MOD_get_windfield(double* taux, double* tauy);
+void __m_global_MOD_get_temforcing(double* tatm);
+void __m_global_MOD_get_salforcing(double* emip);
+void __m_global_MOD_get_internal_temforcing(double* temp);
+void __m_global_MOD_get_internal_salforcing(double* salt);
+void __m_global_MOD_get_spert(double* spert);
+/* global.F90:241-293 (THCM.C:51-56): the caller's global grid arrays; checked against the library's own grid.F90 arrays */
+void set_global_x(int* n, double* a);
+void set_global_y(int* n, double* a);
+void set_global_z(int* n, double* a);
+void set_global_xu(int* n, double* a);
+void set_global_yv(int* n, double* a);
+void set_global_zw(int* n, double* a);
+/* m_usr::set_internal_forcing (src/ocean/usr.F90:267-300; THCM.C:594): n*m*l internal T / S fields for the w-row forcing */
+void __m_usr_MOD_set_internal_forcing(double* temp, double* salt);
+/* m_thcm_utils::get_landm / loadbal_weights (src/ocean/thcm_utils.F90:259-277, 325-353) */
+void __m_thcm_utils_MOD_get_landm(int* landm);
+void __m_thcm_utils_MOD_loadbal_weights(double* weights, double* fac_ntrphys, double* fac_consmix, double* fac_convadj);
+/* m_probe (src/ocean/probe.F90; THCM.C:136-170, 1568-1763): n*m surface diagnostics of the coupled model; `un` / `sol` is the
+ * HOST state vector */
+void __m_probe_MOD_get_atmosphere_t(double* f);
+void __m_probe_MOD_get_atmosphere_q(double* f);
+void __m_probe_MOD_get_atmosphere_p(double* f);
+void __m_probe_MOD_get_emip(double* f);
+void __m_probe_MOD_get_adapted_emip(double* f);
+void __m_probe_MOD_get_emip_pert(double* f);
+void __m_probe_MOD_get_taux(double* f);
+void __m_probe_MOD_get_tauy(double* f);
+void __m_probe_MOD_get_suno(double* f);
+void __m_probe_MOD_compute_evap(double* evap, double* un);
+void __m_probe_MOD_get_salflux(double* un, double* salflux, double* scorr, double* qsoaflux, double* qsosflux);
+void __m_probe_MOD_get_temflux(double* un, double* totflux, double* swflux, double* shflux, double* lhflux, double* siflux,
+                               double* simask);
+void __m_probe_MOD_get_derivatives(double* un, double* dftdm, double* dfsdq, double* dfsdm, double* dfsdg);
+/* m_integrals (src/ocean/integrals.F90:17-88; THCM.C:2133, 2155): per-cell salt advection / diffusion integrands (n*m*l) */
+void __m_integrals_MOD_salt_advection(double* un, double* check);
+void __m_integrals_MOD_salt_diffusion(double* un, double* check);
+/* get_stochastic_forcing (src/ocean/forcing.F90:235-280; THCM.C:848): fills begF / jcoF / coF of set_pointers */
+void get_stochastic_forcing_(void);
+/* getdeps / get_parameters / get_nondimensionalization_parameters (src/ocean/usrc.F90:201-251; Ocean.C:889, 1610) */
+void getdeps_(double* Ooa, double* Os, double* nus, double* eta, double* lvsc, double* qdim, double* pqsnd);
+void get_parameters_(double* r0dim, double* udim, double* hdim);
+void get_nondimensionalization_parameters_(double* out27);
+/* writeparams (usrc.F90:421-431 -> fort.7), write_data (src/ocean/inout.F90:20-93 -> fort.3; Ocean.C:1877), write_levitus */
+void writeparams_(void);
+void write_data_(double* u, int* ofile, int* lab);
+void write_levitus_(const char* filename);
 /* replace m_scaling::average_block / compute (src/ocean/scaling.F90:29-105; THCM.C:106-107, 1798-1807): the local average
  * 6x6 diagonal block of the Jacobian of the last matrix_ call over the OCEAN cells, db(nun,nun) column-major; and the THCM
  * row / column scaling vectors built from the (globally averaged) block */

@@ -59,7 +59,10 @@ def lib():
                                 ("oracle_intcond_scaling", i, [vp, vp, vp]),
                                 ("oracle_set_vmix_fix", None, [vp, i]), ("oracle_vmix_fun", None, [vp, vp, vp]),
                                 ("oracle_vmix_flags", None, [vp, vp]),
-                                ("oracle_set_atmos_parameters", None, [vp, vp]), ("oracle_set_seaice_parameters", None, [vp, vp])]:
+                                ("oracle_set_atmos_parameters", None, [vp, vp]), ("oracle_set_seaice_parameters", None, [vp, vp]),
+                                ("oracle_salt_advection", None, [vp, vp, vp]), ("oracle_salt_diffusion", None, [vp, vp, vp]),
+                                ("oracle_stochastic_forcing", None, [vp, vp, vp, vp]), ("oracle_set_internal_forcing", None, [vp, vp, vp]),
+                                ("oracle_get_coupling_state", None, [vp, vp, vp]), ("oracle_get_field", None, [vp, i, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -177,6 +180,45 @@ class OracleTHCM:
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
         assert f.size == self.n * self.m
         self.L_.oracle_set_field(self.h, self.FIELDS.index(name), _p(f))
+
+    def get_field(self, name):
+        f = np.empty((self.m, self.n))
+        self.L_.oracle_get_field(self.h, self.FIELDS.index(name), _p(f))
+        return f
+
+    def coupling_state(self):
+        """Constants of m_usr / m_atm / m_ice the surface diagnostics of probe.F90 use, and suno(1..m)."""
+        v = np.empty(17); suno = np.empty(self.m)
+        self.L_.oracle_get_coupling_state(self.h, _p(v), _p(suno))
+        names = ("QTnd", "QSnd", "Ooa", "Os", "nus", "lvsc", "qdim", "eta", "dqso", "eo0", "albe0", "albed", "zeta", "a0", "Lf", "Qvar", "Q0")
+        d = dict(zip(names, v.tolist()))
+        d["suno"] = suno
+        return d
+
+    def salt_advection(self, un):
+        """m_integrals::salt_advection (integrals.F90:17-51): per-cell integrand [l, m, n]; skipped cells stay 0."""
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        out = np.zeros(self.n * self.m * self.l)
+        self.L_.oracle_salt_advection(self.h, _p(un), _p(out))
+        return out
+
+    def salt_diffusion(self, un):
+        """m_integrals::salt_diffusion (integrals.F90:53-88)."""
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        out = np.zeros(self.n * self.m * self.l)
+        self.L_.oracle_salt_diffusion(self.h, _p(un), _p(out))
+        return out
+
+    def stochastic_forcing(self):
+        """get_stochastic_forcing (forcing.F90:235-280): (begF, jcoF, coF), 1-based."""
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(self.n * self.m, dtype=np.int32); co = np.zeros(self.n * self.m)
+        self.L_.oracle_stochastic_forcing(self.h, _p(beg), _p(jco), _p(co))
+        return beg, jco, co
+
+    def set_internal_forcing(self, temp, salt):
+        t = np.ascontiguousarray(temp, dtype=np.float64).reshape(-1); s_ = np.ascontiguousarray(salt, dtype=np.float64).reshape(-1)
+        assert t.size == s_.size == self.n * self.m * self.l
+        self.L_.oracle_set_internal_forcing(self.h, _p(t), _p(s_))
 
     def set_atmos_parameters(self, pars18):
         """usrc.F90:254-310 with the 18 doubles of Atmosphere::CommPars; re-runs forcing + lin."""

@@ -1507,6 +1507,65 @@ struct Oracle {
         fillcolA();
     }
 
+    // ---------------- integrals.F90:17-88 ----------------
+    void salt_advection(const double* un, double* check) {
+        Fields F(n, m, l);
+        usol(un, F.u, F.v, F.w, F.p, F.t, F.s);
+        Arr3 &u = F.u, &v = F.v, &w = F.w, &s = F.s;
+        size_t pos = 0;
+        for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++, pos++) {
+            if (lm(i, j, l) != OCEAN) continue;
+            check[pos] = (u(i, j, k) + u(i, j - 1, k)) * (s(i + 1, j, k) + s(i, j, k)) / (4 * dx) -
+                         (u(i - 1, j, k) + u(i - 1, j - 1, k)) * (s(i, j, k) + s(i - 1, j, k)) / (4 * dx) +
+                         (v(i, j, k) + v(i - 1, j, k)) * (s(i, j + 1, k) + s(i, j, k)) * std::cos(yv[j]) / (4 * dy) -
+                         (v(i, j - 1, k) + v(i - 1, j - 1, k)) * (s(i, j, k) + s(i, j - 1, k)) * std::cos(yv[j - 1]) / (4 * dy) +
+                         w(i, j, k) * (s(i, j, k + 1) + s(i, j, k)) * std::cos(y[j]) / (2 * dz * dfzW[k]) -
+                         w(i, j, k - 1) * (s(i, j, k) + s(i, j, k - 1)) * std::cos(y[j]) / (2 * dz * dfzW[k - 1]);
+        }
+    }
+    void salt_diffusion(const double* un, double* check) {
+        Fields F(n, m, l);
+        usol(un, F.u, F.v, F.w, F.p, F.t, F.s);
+        Arr3& s = F.s;
+        size_t pos = 0;
+        for (int k = 1; k <= l; k++) {
+            double h1 = 1. / (dfzT[k] * dfzW[k]), h2 = 1. / (dfzT[k] * dfzW[k - 1]);
+            for (int j = 1; j <= m; j++) {
+                double cay = std::cos(y[j]), c1 = std::cos(yv[j]), c2 = std::cos(yv[j - 1]);
+                for (int i = 1; i <= n; i++, pos++) {
+                    if (lm(i, j, k) != OCEAN) continue;
+                    check[pos] = std::cos(y[j]) * dfzT[k] *
+                                 ((s(i + 1, j, k) + s(i - 1, j, k) - 2 * s(i, j, k)) / (dx * dx * cay * cay) +
+                                  (c1 * s(i, j + 1, k) + c2 * s(i, j - 1, k) - (c1 + c2) * s(i, j, k)) / (dy * dy * cay) +
+                                  (h1 * s(i, j, k + 1) + h2 * s(i, j, k - 1) - (h1 + h2) * s(i, j, k)) / (dz * dz));
+                }
+            }
+        }
+    }
+    // ---------------- forcing.F90:235-280 ----------------
+    void get_stochastic_forcing(int* begF, int* jcoF, double* coF) {
+        double oldpar = par[SPER];
+        par[SPER] = 0.0;
+        forcing();
+        int v = 1, prev_row = 0;
+        for (int i = 0; i <= ndim; i++) begF[i] = 0;
+        for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+            if (coupled_S != 1) {
+                int row = find_row2(i, j, l, SS);
+                if (prev_row > row) { fprintf(stderr, "Forcing ordered in the wrong way\n"); abort(); }
+                jcoF[v - 1] = j;
+                coF[v - 1] = Frc[row - 1];
+                v = v + 1;
+                begF[row] = v;
+                prev_row = row;
+            }
+        }
+        v = 1;
+        for (int i = 0; i <= ndim; i++) { if (begF[i] == 0) begF[i] = v; else v = begF[i]; }
+        par[SPER] = oldpar;
+        forcing();
+    }
+
     // ---------------- usrc.F90:523-603 ----------------
     void rhs(const double* un, double* B) {
         std::vector<double> Au(ndim), mix(ndim, 0.0);
@@ -1668,6 +1727,30 @@ void oracle_set_field(void* h, int which, const double* f) {
     size_t pos = 0;
     for (int j = 1; j <= o->m; j++) for (int i = 1; i <= o->n; i++, pos++)
         o->f2(*dst[which], i, j) = masked ? f[pos] * (1 - o->lm(i, j, o->l)) : f[pos];
+}
+void oracle_salt_advection(void* h, const double* un, double* check) { ((Oracle*)h)->salt_advection(un, check); }
+void oracle_salt_diffusion(void* h, const double* un, double* check) { ((Oracle*)h)->salt_diffusion(un, check); }
+void oracle_stochastic_forcing(void* h, int* begF, int* jcoF, double* coF) { ((Oracle*)h)->get_stochastic_forcing(begF, jcoF, coF); }
+// usr.F90:267-300: n*m*l internal temperature / salinity fields (w-row forcing, forcing.F90:199-209)
+void oracle_set_internal_forcing(void* h, const double* temp, const double* salt) {
+    Oracle* o = (Oracle*)h;
+    std::memcpy(o->internal_temp.data(), temp, sizeof(double) * o->internal_temp.size());
+    std::memcpy(o->internal_salt.data(), salt, sizeof(double) * o->internal_salt.size());
+}
+// model constants the numpy restatement of probe.F90 (oracle/probe_oracle.py) needs: QTnd QSnd Ooa Os nus lvsc qdim eta dqso
+// eo0 albe0 albed zeta a0 Lf Qvar Q0, then suno(1..m)
+void oracle_get_coupling_state(void* h, double* out17, double* suno) {
+    Oracle* o = (Oracle*)h;
+    double v[17] = {o->QTnd, o->QSnd, o->Ooa, o->Os, o->nus, o->lvsc, o->qdim, o->eta, o->dqso, o->eo0, o->albe0, o->albed, o->zeta,
+                    o->a0, o->Lf, o->Qvar, o->Q0};
+    std::memcpy(out17, v, sizeof(v));
+    for (int j = 1; j <= o->m; j++) suno[j - 1] = o->suno[j];
+}
+void oracle_get_field(void* h, int which, double* f) {
+    Oracle* o = (Oracle*)h;
+    std::vector<double>* src[] = {&o->taux, &o->tauy, &o->tatm, &o->emip, &o->spert, &o->adapted_emip,
+                                  &o->qatm, &o->albe, &o->patm, &o->qsa, &o->msi, &o->gsi};
+    std::memcpy(f, src[which]->data(), sizeof(double) * o->n * o->m);
 }
 // usrc.F90:254-310: pars = the 18 doubles of Atmosphere::CommPars (tdim qdim nuq eta dqso dqsi dqdt Eo0 Ei0 Cs t0o t0i a0 da
 // tauf tauc comb albf); nus and lvsc are frozen at the COMB / SALT / TEMP values of the moment of the call

@@ -14,7 +14,7 @@ _lib = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libthcm_emu.so")
-    srcs = [os.path.join(_HERE, "emu_cell.cpp"), os.path.join(_CSRC, "thcm_host.cpp")]
+    srcs = [os.path.join(_HERE, "emu_cell.cpp"), os.path.join(_CSRC, "thcm_host.cpp"), os.path.join(_CSRC, "thcm_probe.cpp")]
     deps = srcs + [os.path.join(_CSRC, f) for f in ("thcm_cell.cuh", "thcm_internal.h", "thcm_slots.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
@@ -37,7 +37,13 @@ def lib():
                                 ("emu_rhs", None, [vp, vp, vp, vp]), ("emu_check_staging", ll, [vp, vp, vp]),
                                 ("emu_check_tiles", ll, [vp, vp, vp]), ("emu_fast_tiles", ll, [vp, vp]),
                                 ("emu_vmix_control", None, [vp, i, i]), ("emu_set_vmix_fix", None, [vp, i]),
-                                ("emu_set_field", None, [vp, i, vp]), ("emu_set_atmos", None, [vp, vp]), ("emu_set_seaice", None, [vp, vp])]:
+                                ("emu_set_field", None, [vp, i, vp]), ("emu_set_atmos", None, [vp, vp]), ("emu_set_seaice", None, [vp, vp]),
+                                ("emu_set_internal_forcing", None, [vp, vp, vp]), ("emu_probe_field", i, [vp, i, vp]),
+                                ("emu_probe_suno", None, [vp, vp]), ("emu_compute_evap", None, [vp, vp, vp]),
+                                ("emu_salflux", None, [vp, vp, vp, vp, vp, vp]), ("emu_temflux", None, [vp, vp, vp]),
+                                ("emu_derivatives", None, [vp, vp, vp]), ("emu_salt_advection", None, [vp, vp, vp]),
+                                ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
+                                ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -78,6 +84,65 @@ class EmuTHCM:
     def set_atmos_parameters(self, p):
         p = np.ascontiguousarray(p, dtype=np.float64); assert p.size == 18
         self.L_.emu_set_atmos(self.h, _p(p))
+
+    # ---- host diagnostics of the B1 boundary (thcm_probe.cpp); nm = (M, N) of the single-block domain ----
+    def _nm(self):
+        b = self.block()
+        return b["m0"], b["n0"]
+
+    def set_internal_forcing(self, t, s_):
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(-1); s_ = np.ascontiguousarray(s_, dtype=np.float64).reshape(-1)
+        self.L_.emu_set_internal_forcing(self.h, _p(t), _p(s_))
+
+    def probe_field(self, name):
+        out = np.full(self._nm(), np.nan)
+        ok = self.L_.emu_probe_field(self.h, self.FIELDS.index(name), _p(out))
+        return out if ok else None
+
+    def suno(self):
+        out = np.empty(self._nm()); self.L_.emu_probe_suno(self.h, _p(out)); return out
+
+    def compute_evap(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64); out = np.empty(self._nm())
+        self.L_.emu_compute_evap(self.h, _p(un), _p(out)); return out
+
+    def salflux(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        sf, qa, qs = np.empty(self._nm()), np.empty(self._nm()), np.empty(self._nm()); corr = np.zeros(1)
+        self.L_.emu_salflux(self.h, _p(un), _p(sf), _p(corr), _p(qa), _p(qs))
+        return sf, corr[0], qa, qs
+
+    def temflux(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        six = np.zeros((6,) + self._nm())
+        self.L_.emu_temflux(self.h, _p(un), _p(six))
+        return dict(zip(("totflux", "swflux", "shflux", "lhflux", "siflux", "simask"), six))
+
+    def derivatives(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        four = np.zeros((4,) + self._nm())
+        self.L_.emu_derivatives(self.h, _p(un), _p(four))
+        return tuple(four)
+
+    def salt_advection(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64); out = np.zeros(self.ndim // 6)
+        self.L_.emu_salt_advection(self.h, _p(un), _p(out)); return out
+
+    def salt_diffusion(self, un):
+        un = np.ascontiguousarray(un, dtype=np.float64); out = np.zeros(self.ndim // 6)
+        self.L_.emu_salt_diffusion(self.h, _p(un), _p(out)); return out
+
+    def stochastic_forcing(self):
+        m, n = self._nm()
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(n * m, dtype=np.int32); co = np.zeros(n * m)
+        self.L_.emu_stochastic_forcing(self.h, _p(beg), _p(jco), _p(co))
+        return beg, jco, co
+
+    def getdeps(self):
+        out = np.empty(7); self.L_.emu_getdeps(self.h, _p(out)); return out
+
+    def loadbal_weights(self):
+        out = np.empty(self._nm()); self.L_.emu_loadbal(self.h, _p(out)); return out
 
     def set_seaice_parameters(self, p):
         p = np.ascontiguousarray(p, dtype=np.float64); assert p.size == 7

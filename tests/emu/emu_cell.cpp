@@ -119,6 +119,25 @@ void emu_set_par(void* h, int idx, double v) { thcmb_ctx* c = &((Emu*)h)->c; c->
 void emu_set_field(void* h, int which, const double* f) { insert_surface_field(&((Emu*)h)->c, which, f); }
 void emu_set_atmos(void* h, const double* p) { thcmb_ctx* c = &((Emu*)h)->c; set_atmos_parameters(c, p); compute_forcing(c); compute_tables(c); compute_cob(c); }
 void emu_set_seaice(void* h, const double* p) { thcmb_ctx* c = &((Emu*)h)->c; set_seaice_parameters(c, p); compute_forcing(c); compute_tables(c); compute_cob(c); }
+// host diagnostics of the B1 boundary (thcm_probe.cpp)
+void emu_set_internal_forcing(void* h, const double* t, const double* s_) { thcmb_ctx* c = &((Emu*)h)->c; set_internal_forcing(c, t, s_); }
+int emu_probe_field(void* h, int which, double* out) { return probe_get_field(&((Emu*)h)->c, which, out) ? 1 : 0; }
+void emu_probe_suno(void* h, double* out) { probe_get_suno(&((Emu*)h)->c, out); }
+void emu_compute_evap(void* h, const double* un, double* out) { probe_compute_evap(&((Emu*)h)->c, un, out); }
+void emu_salflux(void* h, const double* un, double* sf, double* corr, double* qa, double* qs) { probe_get_salflux(&((Emu*)h)->c, un, sf, corr, qa, qs); }
+void emu_temflux(void* h, const double* un, double* six) {
+    thcmb_ctx* c = &((Emu*)h)->c; size_t nm = (size_t)c->s.N * c->s.M;
+    probe_get_temflux(c, un, six, six + nm, six + 2 * nm, six + 3 * nm, six + 4 * nm, six + 5 * nm);
+}
+void emu_derivatives(void* h, const double* un, double* four) {
+    thcmb_ctx* c = &((Emu*)h)->c; size_t nm = (size_t)c->s.N * c->s.M;
+    probe_get_derivatives(c, un, four, four + nm, four + 2 * nm, four + 3 * nm);
+}
+void emu_salt_advection(void* h, const double* un, double* out) { integrals_salt_advection(&((Emu*)h)->c, un, out); }
+void emu_salt_diffusion(void* h, const double* un, double* out) { integrals_salt_diffusion(&((Emu*)h)->c, un, out); }
+void emu_stochastic_forcing(void* h, int* beg, int* jco, double* co) { thcmb_ctx* c = &((Emu*)h)->c; stochastic_forcing(c, beg, jco, co); }
+void emu_getdeps(void* h, double* out7) { get_deps(&((Emu*)h)->c, out7); }
+void emu_loadbal(void* h, double* w) { loadbal_weights(&((Emu*)h)->c, w); }
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

@@ -273,6 +273,71 @@ def test_coupled_mode_through_the_fortran_symbols(gpu):
     f.finalize()
 
 
+def test_diagnostic_symbols_of_the_fortran_boundary(gpu):
+    """m_probe / m_integrals / get_stochastic_forcing / set_internal_forcing / getdeps / m_thcm_utils::get_landm through the
+    symbols THCM.C binds (host code of the library, checked against the oracle; tests/test_probe_host.py covers them on CPU)."""
+    from oracle.oracle import OracleTHCM
+    from oracle import probe_oracle as po
+    s, landm = CASES["natl8"](coupled_T=1, coupled_S=1)
+    o = OracleTHCM(s, landm)
+    f = gpu.FortranABI()
+    f.global_initialize(s)
+    f.init(s, landm)
+    for k, v in dict(PARS, SUNP=1.0, SPER=0.3).items():
+        o.setpar(P[k], v)
+        f.setparcs(k, v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    for k, fld in fields.items():
+        f.insert(ORACLE_TO_INSERT[k], fld)
+    f.set_atmos_parameters(atmos)
+    f.set_seaice_parameters(seaice)
+    x = cases.random_state(s, landm, scale=0.2)
+
+    def close(a, b, tol=1e-12):
+        return np.abs(np.asarray(a) - np.asarray(b)).max() <= tol * (np.abs(np.asarray(b)).max() + 1e-300)
+    adv, dif = f.salt_integrals(x)
+    assert np.array_equal(adv, o.salt_advection(x)) and np.array_equal(dif, o.salt_diffusion(x))
+    assert close(f.compute_evap(x), po.compute_evap(o, x, True))
+    sf, corr, qa, qs = f.get_salflux(x)
+    sfo, corro, qao, qso = po.get_salflux(o, x, True, s.SRES)
+    assert close(sf, sfo) and abs(corr - corro) <= 1e-12 * abs(corro) and close(qa, qao) and close(qs, qso)
+    tf, tfo = f.get_temflux(x), po.get_temflux(o, x, True, s.TRES)
+    for k in tfo:
+        assert close(tf[k], tfo[k]), k
+    for a, b in zip(f.get_derivatives(x), po.get_derivatives(o, x, True, True)):
+        assert close(a, b)
+    cs = o.coupling_state()
+    assert np.array_equal(f.getdeps()[:6], [cs["Ooa"], cs["Os"], cs["nus"], cs["eta"], cs["lvsc"], cs["qdim"]])
+    assert np.array_equal(f.probe("atmosphere_t"), o.get_field("tatm")) and np.array_equal(f.probe("suno")[:, 0], cs["suno"])
+    assert np.array_equal(f.get_landm(), o.landm())
+    # internal T / S forcing of the w rows + residual after the next parameter change
+    rng = np.random.default_rng(5)
+    t3, s3 = rng.standard_normal((s.L, s.M, s.N)), rng.standard_normal((s.L, s.M, s.N))
+    o.set_internal_forcing(t3, s3)
+    f.set_internal_forcing(t3, s3)
+    o.setpar(P["COMB"], 0.7)
+    f.setparcs("COMB", 0.7)
+    assert np.array_equal(f.rhs(x), o.rhs(x))
+    assert np.array_equal(f.get_forcing(), o.forcing())
+    f.finalize()
+    # get_stochastic_forcing needs the ocean-only salinity forcing (coupled_S = 0)
+    s2, landm2 = CASES["natl8"](SRES=0)
+    o2 = OracleTHCM(s2, landm2)
+    f2 = gpu.FortranABI()
+    f2.global_initialize(s2)
+    f2.init(s2, landm2)
+    for k, v in dict(PARS, SPER=0.3).items():
+        o2.setpar(P[k], v)
+        f2.setparcs(k, v)
+    bo, jo, co = o2.stochastic_forcing()
+    bf, jf, cf = f2.get_stochastic_forcing()
+    nm = s2.N * s2.M
+    assert np.array_equal(bf, bo) and np.array_equal(jf[:nm], jo) and np.array_equal(cf[:nm], co)
+    assert np.array_equal(f2.rhs(x), o2.rhs(x))     # the forcing is restored afterwards (forcing.F90:277-278)
+    f2.finalize()
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
 def test_spmv_and_vector_kernels(gpu, name):
     from oracle.oracle import spmv, matavec

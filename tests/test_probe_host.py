@@ -1,0 +1,110 @@
+"""CPU tests of the host-side diagnostics / setup symbols of the B1 boundary (i-emic_b200/csrc/thcm_probe.cpp compiled into
+tests/emu): m_probe, m_integrals, get_stochastic_forcing, set_internal_forcing, getdeps, loadbal_weights against the oracle
+(oracle/thcm_oracle.cpp for the routines that need usol / forcing, oracle/probe_oracle.py = numpy restatement of probe.F90)."""
+import numpy as np
+import pytest
+
+import cases
+from cases import PAR_INDEX as P
+from oracle.oracle import OracleTHCM
+from oracle import probe_oracle as po
+from emu.emu import EmuTHCM
+
+PARS = dict(cases.DEFAULT_PARS, NLES=1.0, SUNP=1.0)
+CASES = {"natl8": cases.natl8, "gateway16": cases.gateway16,
+         "box_p": lambda **kw: cases.box(7, 6, 5, True, seed=3, land_frac=0.3, **kw),
+         "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw)}
+
+
+def setup(name, coupled=True, **kw):
+    if coupled:
+        kw = dict(kw, coupled_T=1, coupled_S=1)
+    s, landm = CASES[name](**kw)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v); e.setpar(P[k], v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    cases.apply_coupled(e, fields, atmos, seaice)
+    return s, landm, o, e
+
+
+def close(a, b, tol=1e-13):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-300)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_salt_integrals_bit_exact(name):
+    s, landm, o, e = setup(name, coupled=False)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    assert np.array_equal(o.salt_advection(x), e.salt_advection(x))
+    assert np.array_equal(o.salt_diffusion(x), e.salt_diffusion(x))
+    assert np.abs(o.salt_advection(x)).max() > 0
+    # THCM::integralChecks (THCM.C:2133-2140) / test_ocean.C:247-252: the flux-form integrand telescopes -- on the constraint
+    # manifold (no flow through walls, lid and bottom) its plain sum over the cells vanishes
+    xc = cases.consistent_state(s, landm, scale=0.1)
+    adv = e.salt_advection(xc)
+    assert np.abs(adv).sum() > 1e-3 and abs(adv.sum()) < 1e-12 * np.abs(adv).sum() * adv.size
+
+
+@pytest.mark.parametrize("name", ["natl8", "box_p"])
+@pytest.mark.parametrize("coupled", [True, False])
+def test_surface_probes_match_probe_F90(name, coupled):
+    s, landm, o, e = setup(name, coupled=coupled, SRES=0 if not coupled else 1)
+    x = cases.random_state(s, landm, scale=0.2)
+    cs = o.coupling_state()
+    assert np.array_equal(e.getdeps(), [cs["Ooa"], cs["Os"], cs["nus"], cs["eta"], cs["lvsc"], cs["qdim"], o.getpar(P["COMB"]) * o.getpar(P["SALT"]) * cs["QSnd"]])
+    assert np.array_equal(e.suno(), np.repeat(cs["suno"][:, None], s.N, axis=1))
+    assert close(e.compute_evap(x), po.compute_evap(o, x, coupled))
+    sf, corr, qa, qs = e.salflux(x)
+    sfo, corro, qao, qso = po.get_salflux(o, x, coupled, s.SRES)
+    assert close(sf, sfo, 1e-12) and abs(corr - corro) <= 1e-12 * (abs(corro) + 1e-300) and close(qa, qao) and close(qs, qso)
+    tf = e.temflux(x)
+    tfo = po.get_temflux(o, x, coupled, s.TRES)
+    for k in tfo:
+        assert close(tf[k], tfo[k]), k
+    d = e.derivatives(x)
+    do = po.get_derivatives(o, x, coupled, coupled)
+    for a, b in zip(d, do):
+        assert close(a, b)
+    if coupled:
+        assert np.abs(d[0]).max() > 0 and np.abs(d[2]).max() > 0 and np.all(d[3][landm[s.L, 1:-1, 1:-1] == 0] == -1.0)
+    # plain getters (probe.F90:11-175, 440-490): emip comes back masked, q / p only in coupled mode
+    land = landm[s.L, 1:s.M + 1, 1:s.N + 1]
+    assert np.array_equal(e.probe_field("tatm"), o.get_field("tatm"))
+    assert np.array_equal(e.probe_field("emip"), o.get_field("emip") * (1 - land))
+    assert np.array_equal(e.probe_field("taux"), o.get_field("taux"))
+    if coupled:
+        assert np.array_equal(e.probe_field("qatm"), o.get_field("qatm")) and np.array_equal(e.probe_field("patm"), o.get_field("patm"))
+    else:
+        assert e.probe_field("qatm") is None and e.probe_field("patm") is None
+
+
+@pytest.mark.parametrize("name,flags", [("natl8", dict(SRES=0)), ("box_p", dict()), ("box_np", dict(SRES=0, its=0))])
+def test_stochastic_forcing_and_internal_forcing(name, flags):
+    s, landm, o, e = setup(name, coupled=False, **flags)
+    for obj in (o, e):
+        obj.setpar(P["SPER"], 0.3)
+    bo, jo, co = o.stochastic_forcing()
+    be, je, ce = e.stochastic_forcing()
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
+    assert bo[-1] == s.N * s.M + 1 and np.count_nonzero(co) > 0
+    assert o.getpar(P["SPER"]) == e.getpar(P["SPER"]) == 0.3
+    # m_usr::set_internal_forcing (usr.F90:267-300) -> w-row forcing (forcing.F90:199-209), effective at the next setpar
+    rng = np.random.default_rng(5)
+    t3, s3 = rng.standard_normal((s.L, s.M, s.N)), rng.standard_normal((s.L, s.M, s.N))
+    o.set_internal_forcing(t3, s3); e.set_internal_forcing(t3, s3)
+    for obj in (o, e):
+        obj.setpar(P["COMB"], 0.7)
+    fo = o.forcing()
+    assert np.array_equal(fo, e.forcing(masked=False))
+    assert np.count_nonzero(fo.reshape(-1, 6)[:, 2]) > 0
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+
+
+def test_loadbal_weights_count_ocean_cells():
+    s, landm, o, e = setup("natl8", coupled=False)
+    w = e.loadbal_weights()
+    assert np.array_equal(w, (landm[:, 1:-1, 1:-1] == 0).sum(axis=0) / s.L)   # thcm_utils.F90:335-351 (no extra mixing weights)
