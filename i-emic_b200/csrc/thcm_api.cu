@@ -50,6 +50,7 @@ void upload_params(thcmb_ctx* c) {
     upload(c->d_jrec, c->jrec_host);
     upload(c->d_krec, c->krec_host);
     upload(c->d_msi, c->msi_local);
+    upload(c->d_cob, c->cob_local);
 }
 
 void refresh_params(thcmb_ctx* c) {  // forcing + lin (usrc.F90:178-179)
@@ -175,7 +176,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter, (void*)c->d_bcell, (void*)c->d_brows,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
-                    (void*)c->d_krec, (void*)c->d_msi})
+                    (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -213,6 +214,18 @@ void thcmb_get_forcing(thcmb_ctx* c, double* frc) {
 }
 void thcmb_get_cob(thcmb_ctx* c, double* cob) { memcpy(cob, c->cob_local.data(), sizeof(double) * c->cob_local.size()); }
 
+/* theta time stepping (ThetaModel.H:87-165): d_F holds F(u_{n+1}) on entry and the theta-method residual on return; the Jacobian
+ * variant adds -M / (theta dt) to the diagonal of the stored Jacobian (call after thcmb_jacobian_dev, before the solve) */
+int thcmb_theta_rhs_dev(thcmb_ctx* c, double theta, double dt, const double* d_state, const double* d_old_state, const double* d_old_rhs,
+                        double* d_F) {
+    if (!(dt > 0.0)) fatal("thcmb_theta_rhs_dev: the time step must be positive");
+    return theta_rhs(c, c->blk.ndim(), theta, dt, d_state, d_old_state, d_old_rhs, c->d_cob, d_F);
+}
+int thcmb_theta_jacobian_dev(thcmb_ctx* c, double theta, double dt) {
+    if (theta == 0.0) return 0;                                     // ThetaModel.H:126-127
+    if (!(dt > 0.0)) fatal("thcmb_theta_jacobian_dev: the time step must be positive");
+    return theta_jacobian(c, theta, dt, c->d_cob);
+}
 int thcmb_nccl_unique_id(void* id128) { return nccl_unique_id(id128); }
 int thcmb_nccl_init(thcmb_ctx* c, const void* id128) { return nccl_init(c, id128); }
 int thcmb_p2p_local_handle(thcmb_ctx* c, void* handle64) { return p2p_local_handle(c, handle64); }

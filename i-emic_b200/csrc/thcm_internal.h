@@ -154,6 +154,7 @@ struct thcmb_ctx {
     int asm_pipe = 1;               // Jacobian kernel: 1 block per tile with TMA staging (default), 0 block per tile with
                                     // per-position loads, 2 / 3 persistent TMA-pipelined kernel at 2 / 3 CTAs per SM
     double* d_frc = nullptr;        // owned rows (masked)
+    double* d_cob = nullptr;        // mass diagonal coB of the owned rows (theta stepping)
     int *d_rowptr = nullptr, *d_col = nullptr;  // static graph, local column ids
     double* d_val = nullptr;        // Jacobian values in graph order
     long long gnnz = 0;
@@ -296,6 +297,9 @@ int axpy_negdev(thcmb_ctx* c, int n, const double* d_h, const double* x, double*
 int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, double* d_nrm);   // x /= sqrt(*d_nrm2)
 int copy(thcmb_ctx* c, int n, const double* x, double* y);
 int fill(thcmb_ctx* c, int n, double a, double* x);
+int theta_rhs(thcmb_ctx* c, int n, double theta, double dt, const double* state, const double* old_state, const double* old_rhs,
+              const double* d_cob, double* F);
+int theta_jacobian(thcmb_ctx* c, double theta, double dt, const double* d_cob);
 int build_blockdiag(thcmb_ctx* c);
 int average_block(thcmb_ctx* c, double* db36);
 bool scaling_compute(const thcmb_ctx* c, const double* db36, double* row_scaling, double* col_scaling);

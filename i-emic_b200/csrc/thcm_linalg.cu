@@ -415,6 +415,50 @@ int fill(thcmb_ctx* c, int n, double a, double* x) {
 }
 
 // ---------------------------------------------------------------------------
+// Theta time stepping (src/transient/ThetaModel.H:87-165): the implicit step reuses residual, Jacobian and solver and adds
+//   rhs_theta = M (u_n - u_{n+1}) + dt (1 - theta) F(u_n) + dt theta F(u_{n+1})      (one fused elementwise kernel)
+//   J_theta   = J - M / (theta dt)   on the diagonal of the stored graph Jacobian     (one thread per row)
+// with the diagonal mass matrix M = coB (assemble.F90:18-54).  Operation order follows the Epetra Update calls.
+// ---------------------------------------------------------------------------
+__global__ void theta_rhs_kernel(int n, double dt, double theta, const double* __restrict__ state, const double* __restrict__ old_state,
+                                 const double* __restrict__ old_rhs, const double* __restrict__ cob, double* __restrict__ F) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double xdot = -1.0 * state[i] + 1.0 * old_state[i];                    // ThetaModel.H:103-104
+        const double bx = cob[i] * xdot;                                             // applyMassMat
+        const double f = (dt * (1 - theta)) * old_rhs[i] + (dt * theta) * F[i];      // :108-109
+        F[i] = 1.0 * bx + 1.0 * f;                                                   // :112
+    }
+}
+__global__ void theta_jac_kernel(int nrow, double dt, double theta, const int* __restrict__ rp, const int* __restrict__ col,
+                                 const double* __restrict__ cob, double* __restrict__ val, int* __restrict__ missing) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    const double value = -cob[r] / dt / theta;                                       // ThetaModel.H:139
+    bool found = false;
+    for (int q = rp[r]; q < rp[r + 1]; q++)
+        if (col[q] == r) { val[q] = val[q] + value; found = true; break; }           // SumIntoGlobalValues on the diagonal
+    if (!found) atomicAdd(missing, 1);
+}
+int theta_rhs(thcmb_ctx* c, int n, double theta, double dt, const double* state, const double* old_state, const double* old_rhs,
+              const double* d_cob, double* F) {
+    ProfScope prof_(c, KID_AXPBY);
+    theta_rhs_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, dt, theta, state, old_state, old_rhs, d_cob, F); c->launches++; return 0;
+}
+int theta_jacobian(thcmb_ctx* c, double theta, double dt, const double* d_cob) {
+    if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
+    const int nrow = c->blk.ndim();
+    THCM_CUDA(cudaMemsetAsync(c->d_flags + 4, 0, sizeof(int), c->stream));
+    { ProfScope prof_(c, KID_AXPBY);
+      theta_jac_kernel<<<(nrow + 255) / 256, 256, 0, c->stream>>>(nrow, dt, theta, c->d_rowptr, c->d_col, d_cob, c->d_val, c->d_flags + 4); }
+    c->launches++;
+    int missing = 0;
+    THCM_CUDA(cudaMemcpyAsync(&missing, c->d_flags + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    if (missing) fatal("theta_jacobian: a row of the maximal graph has no diagonal entry");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Batched (classical) Gram-Schmidt pass, the orthogonalisation Belos uses on the reference's production path
 // (Ocean.C:977-1024: "Orthogonalization" = "DGKS"): ALL projections h = V^T w of an iteration in ONE reduction kernel
 // (+ w.w), then ONE update kernel w -= V h.  Per iteration this is 2-4 dependent global reductions instead of the i+2

@@ -90,6 +90,7 @@ def load_library(path=None):
         "thcmb_halo_gids": (None, [vp, vp]), "thcmb_local_gids": (None, [vp, vp]),
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
+        "thcmb_theta_rhs_dev": (i, [vp, d, d, vp, vp, vp, vp]), "thcmb_theta_jacobian_dev": (i, [vp, d, d]),
         "thcmb_insert_field": (None, [vp, i, vp]), "thcmb_set_atmos_parameters": (None, [vp, vp]),
         "thcmb_set_seaice_parameters": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
@@ -486,6 +487,52 @@ class Ocean:
         self.last_solve = res
         self.last_history = hist
         return res.status
+
+
+class ThetaOcean(Ocean):
+    """src/transient/ThetaModel.H:18-165 over the Ocean mirror: the implicit theta step
+    M u_n + dt theta F(u_{n+1}) + dt (1 - theta) F(u_n) - M u_{n+1} = 0 with J_theta = J - M / (theta dt)."""
+
+    def __init__(self, settings, landm, theta=1.0, comm=None, solver_params=None):
+        super().__init__(settings, landm, comm, solver_params)
+        if theta < 0 or theta > 1:
+            raise ValueError(f"ThetaModel: incorrect theta {theta}")   # ThetaModel.H:93-97
+        self.theta_ = float(theta)
+        self.timestep_ = 1.0e-3
+        self.oldState_ = self.thcm.new_vector()
+        self.oldRhs_ = self.thcm.new_vector()
+
+    def initStep(self, timestep):   # ThetaModel.H:65-75
+        self.timestep_ = float(timestep)
+        self.oldState_.copy_(self.state_)
+        Ocean.computeRHS(self)
+        self.oldRhs_.copy_(self.rhs_)
+
+    def setState(self, state):      # ThetaModel.H:77-81
+        if state is not self.state_:
+            self.state_.copy_(state)
+
+    def computeRHS(self):           # ThetaModel.H:87-113
+        Ocean.computeRHS(self)
+        t = self.thcm
+        t._pre()
+        t.L_.thcmb_theta_rhs_dev(t.ctx, self.theta_, self.timestep_, _dev_ptr(self.state_), _dev_ptr(self.oldState_),
+                                 _dev_ptr(self.oldRhs_), _dev_ptr(self.rhs_))
+        t.sync()
+
+    def computeJacobian(self):      # ThetaModel.H:118-149
+        Ocean.computeJacobian(self)
+        t = self.thcm
+        t.L_.thcmb_theta_jacobian_dev(t.ctx, self.theta_, self.timestep_)
+
+    def solve(self, rhs=None):      # ThetaModel.H:153-165: J_theta x = b / (theta dt)
+        if self.theta_ == 0.0:
+            raise ValueError("theta = 0 divides by the mass matrix, which is singular for THCM (w and p rows)")
+        b = (self.rhs_ if rhs is None else rhs).clone()
+        t = self.thcm
+        t._pre()
+        t.L_.thcmb_scale(t.ctx, t.ndim, 1.0 / self.timestep_ / self.theta_, _dev_ptr(b))
+        return Ocean.solve(self, b)
 
 
 class FortranABI:

@@ -244,6 +244,13 @@ int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y);
 int thcmb_csr_spmv_dev(thcmb_ctx* c, int nrow, const int* d_rowptr, const int* d_col, const double* d_val,
                        const double* d_x, double* d_y);
 
+/* Theta time stepping, src/transient/ThetaModel.H:87-165.  rhs: d_F holds F(u_{n+1}) on entry and
+ * M (u_n - u_{n+1}) + dt (1-theta) F(u_n) + dt theta F(u_{n+1}) on return (M = the mass diagonal coB); jacobian: adds
+ * -M / (theta dt) to the diagonal of the stored Jacobian (no-op for theta = 0, like the reference) */
+int thcmb_theta_rhs_dev(thcmb_ctx* c, double theta, double dt, const double* d_state, const double* d_old_state,
+                        const double* d_old_rhs, double* d_F);
+int thcmb_theta_jacobian_dev(thcmb_ctx* c, double theta, double dt);
+
 /* vector kernels (Epetra_MultiVector::Dot/Norm2/Update/Scale as used by GMRESSolver.H / IDRSolver.H);
  * dot/nrm2 all-reduce over ranks and return on the host */
 double thcmb_dot(thcmb_ctx* c, int n, const double* d_x, const double* d_y);

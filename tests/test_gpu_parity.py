@@ -273,6 +273,48 @@ def test_coupled_mode_through_the_fortran_symbols(gpu):
     f.finalize()
 
 
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_theta_stepping_operator(gpu, theta):
+    """src/transient/ThetaModel.H:87-165 on the device: rhs_theta = M (u_n - u_{n+1}) + dt (1-theta) F(u_n) + dt theta F(u_{n+1}),
+    J_theta = J - M / (theta dt) on the diagonal, and one implicit step solved with the in-library FGMRES."""
+    from oracle.oracle import OracleTHCM, spmv
+    s, landm = CASES["natl8"]()
+    o = OracleTHCM(s, landm)
+    m = gpu.ThetaOcean(s, landm, theta=theta, solver_params=dict(tol=1e-10, maxit=400, restart=400, precon=1))
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        m.setPar(k, v)
+    dt = 0.05
+    x0 = cases.consistent_state(s, landm, scale=0.05, seed=3)
+    x1 = cases.consistent_state(s, landm, scale=0.05, seed=4)
+    m.setState(dev(x0))
+    m.initStep(dt)
+    m.setState(dev(x1))
+    m.computeRHS()
+    F0, F1 = -o.rhs(x0), -o.rhs(x1)
+    _, _, _, cob = o.matrix(x1)
+    ref = cob * (-1.0 * x1 + 1.0 * x0) + ((dt * (1 - theta)) * F0 + (dt * theta) * F1)
+    got = m.getRHS().cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-15 * np.abs(ref).max() + 1e-300
+    m.computeJacobian()
+    vo, _ = o.jacobian_graph(x1)
+    rowptr, col = o.graph()
+    v = np.random.default_rng(1).standard_normal(o.ndim)
+    y = m.thcm.new_vector()
+    m.applyMatrix(dev(v), y)
+    yo = spmv(rowptr, col, vo, v) + (-cob / dt / theta) * v
+    assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
+    # one Newton iteration of the implicit step: J_theta dx = rhs_theta / (theta dt) (ThetaModel.H:153-165)
+    # (block-diagonal preconditioning need not converge on the pressure-singular operator: GMRES only has to reduce the TRUE
+    # residual of the shifted system, which checks that solve() scaled the right-hand side and used J_theta)
+    m.solve()
+    dx = m.getSolution().cpu().numpy()
+    b = ref / dt / theta
+    r = spmv(rowptr, col, vo, dx) + (-cob / dt / theta) * dx - b
+    assert np.linalg.norm(r) < 0.9 * np.linalg.norm(b)
+    m.thcm.close()
+
+
 def test_diagnostic_symbols_of_the_fortran_boundary(gpu):
     """m_probe / m_integrals / get_stochastic_forcing / set_internal_forcing / getdeps / m_thcm_utils::get_landm through the
     symbols THCM.C binds (host code of the library, checked against the oracle; tests/test_probe_host.py covers them on CPU)."""
