@@ -97,7 +97,7 @@ __device__ __forceinline__ void stage_inputs(const AsmArgs& a, const TileGeom& g
     }
 }
 
-template <int R, int MODE>
+template <int R, int MODE, bool CPL>
 __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const TileGeom& g, int lane, uint32_t nb_in, double sm) {
     constexpr int NSV = MODE == MODE_RHS ? SV_NRHS : SV_NJAC;
     const DevBlock& b = a.b;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void do_row(const AsmArgs& a, Smem<MODE>& sh, const T
         cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) |
               (c.k == b.L ? 32 : 0);
         if (!((nb >> 4) & 1u)) {
-            eval_row<R, MODE != MODE_RHS>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
+            eval_row<R, MODE != MODE_RHS, CPL>(E, a.t, b, c, sm, tile, SmemTabs<NSV>{&sh.in});
             if constexpr (MODE != MODE_RHS && (R == TT || R == SS)) vmix_jac<R>(E, a.t, c, nb, tile, SmemTabs<NSV>{&sh.in});   // usrc.F90:489-508
         }
     }
@@ -228,7 +228,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, int byt
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
 
-template <int MODE>
+template <int MODE, bool CPL>
 __global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(const AsmArgs a) {
     constexpr int NT = 32 * mode_warps(MODE);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,20 +250,20 @@ __global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(co
     __syncthreads();
     if constexpr (MODE == MODE_JAC_CRS) {
         switch (warp) {
-        case 0: do_row<1, MODE>(a, sh, g, lane, nb, sm); break;
-        case 1: do_row<2, MODE>(a, sh, g, lane, nb, sm); break;
-        case 2: do_row<3, MODE>(a, sh, g, lane, nb, sm); break;
-        case 3: do_row<4, MODE>(a, sh, g, lane, nb, sm); break;
-        case 4: do_row<5, MODE>(a, sh, g, lane, nb, sm); break;
-        default: do_row<6, MODE>(a, sh, g, lane, nb, sm); break;
+        case 0: do_row<1, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 1: do_row<2, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 2: do_row<3, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 3: do_row<4, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 4: do_row<5, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        default: do_row<6, MODE, CPL>(a, sh, g, lane, nb, sm); break;
         }
     } else {   // 5 warps: u | v | w + p | T | S
         switch (warp) {
-        case 0: do_row<1, MODE>(a, sh, g, lane, nb, sm); break;
-        case 1: do_row<2, MODE>(a, sh, g, lane, nb, sm); break;
-        case 2: do_row<3, MODE>(a, sh, g, lane, nb, sm); do_row<4, MODE>(a, sh, g, lane, nb, sm); break;
-        case 3: do_row<5, MODE>(a, sh, g, lane, nb, sm); break;
-        default: do_row<6, MODE>(a, sh, g, lane, nb, sm); break;
+        case 0: do_row<1, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 1: do_row<2, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 2: do_row<3, MODE, CPL>(a, sh, g, lane, nb, sm); do_row<4, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        case 3: do_row<5, MODE, CPL>(a, sh, g, lane, nb, sm); break;
+        default: do_row<6, MODE, CPL>(a, sh, g, lane, nb, sm); break;
         }
     }
     if constexpr (MODE == MODE_JAC_GRAPH || MODE == MODE_JAC_COUNT) {
@@ -389,12 +389,12 @@ template <class ST> struct PipeTabs {
     __device__ __forceinline__ double kt(int tb) const { return st->tk[tb]; }
 };
 
-template <int R, class ST>
+template <int R, bool CPL, class ST>
 __device__ __forceinline__ void pipe_eval(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, uint32_t nb, double sm,
                                           double* E) {
     if (lane < g.ncell && !((nb >> 4) & 1u)) {
         Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
-        eval_row<R, true>(E, a.t, a.b, c, sm, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
+        eval_row<R, true, CPL>(E, a.t, a.b, c, sm, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
         if constexpr (R == TT || R == SS) vmix_jac<R>(E, a.t, c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});   // usrc.F90:489-508
     }
 }
@@ -454,8 +454,8 @@ __device__ __forceinline__ void pipe_consumer(const AsmArgs& a, PipeSmem& sh, in
         const int g0 = st.desc.g0, tot = st.desc.tot;
         double EA[NA], EB[NB];
         PROG(1)
-        pipe_eval<RA>(a, st, g, lane, nb, sm, EA);
-        if constexpr (RB != RA) pipe_eval<RB>(a, st, g, lane, nb, sm, EB);
+        pipe_eval<RA, true>(a, st, g, lane, nb, sm, EA);
+        if constexpr (RB != RA) pipe_eval<RB, true>(a, st, g, lane, nb, sm, EB);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.bar_empty[s]);          // the stage may be refilled
         PROG(2)
@@ -630,24 +630,24 @@ template <int GROUP> struct alignas(16) TmaSmem {
 
 __device__ __forceinline__ constexpr int diag_pos(int R) { return ROW_OFF[R - 1] + interior_pos(R, slot_of(R, 5, R)); }
 
-template <int GROUP, int RA, int RB>
+template <int GROUP, int RA, int RB, bool CPL>
 __device__ __forceinline__ void tma_rows(const AsmArgs& a, TmaSmem<GROUP>& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
     using G = RowGroup<GROUP>;
     constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
     const uint32_t nb = sh.st.desc.nbmask[lane];
     const double sm = (double)((sh.st.desc.surfbits >> lane) & 1u);
     double EA[NA], EB[NB];
-    pipe_eval<RA>(a, sh.st, g, lane, nb, sm, EA);
+    pipe_eval<RA, CPL>(a, sh.st, g, lane, nb, sm, EA);
     pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
     pipe_emit<RA, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EA);
     if constexpr (RB != RA) {
-        pipe_eval<RB>(a, sh.st, g, lane, nb, sm, EB);
+        pipe_eval<RB, CPL>(a, sh.st, g, lane, nb, sm, EB);
         pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
         pipe_emit<RB, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EB);
     }
 }
 
-template <int GROUP, int BLOCKS_PER_SM>
+template <int GROUP, int BLOCKS_PER_SM, bool CPL>
 __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
     using G = RowGroup<GROUP>;
     constexpr int NT = 32 * G::NWARP;
@@ -717,13 +717,13 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
         __syncthreads();
         if constexpr (GROUP == 0) {
             switch (warp) {
-            case 0: tma_rows<0, 1, 1>(a, sh, g, lane, open_ocean, interior); break;
-            case 1: tma_rows<0, 2, 2>(a, sh, g, lane, open_ocean, interior); break;
-            default: tma_rows<0, 3, 4>(a, sh, g, lane, open_ocean, interior); break;
+            case 0: tma_rows<0, 1, 1, CPL>(a, sh, g, lane, open_ocean, interior); break;
+            case 1: tma_rows<0, 2, 2, CPL>(a, sh, g, lane, open_ocean, interior); break;
+            default: tma_rows<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, interior); break;
             }
         } else {
-            if (warp == 0) tma_rows<1, 5, 5>(a, sh, g, lane, open_ocean, interior);
-            else tma_rows<1, 6, 6>(a, sh, g, lane, open_ocean, interior);
+            if (warp == 0) tma_rows<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, interior);
+            else tma_rows<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, interior);
         }
     }
     if (fast) {
@@ -750,17 +750,19 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     }
 }
 
-template <int GROUP, int BLOCKS_PER_SM> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
+template <int GROUP, int BLOCKS_PER_SM, bool CPL> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<GROUP>)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<GROUP>)));
         attr_set = true;
     }
-    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(TmaSmem<GROUP>), c->stream>>>(a);
+    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(TmaSmem<GROUP>), c->stream>>>(a);
 }
+// coupled mode only touches the T | S rows (group B); group A is the same kernel either way
 template <int BA, int BB> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
-    launch_jac_tma_group<0, BA>(c, a);
-    launch_jac_tma_group<1, BB>(c, a);
+    launch_jac_tma_group<0, BA, false>(c, a);
+    if (a.t.coupled_T || a.t.coupled_S) launch_jac_tma_group<1, BB, true>(c, a);
+    else launch_jac_tma_group<1, BB, false>(c, a);
     c->launches++;   // two kernels per assembly
 }
 
@@ -802,13 +804,17 @@ int scan_block_counts(thcmb_ctx* c) {
     return 0;
 }
 
-template <int MODE> static void launch_mode(thcmb_ctx* c, const AsmArgs& a, int nblk) {
+template <int MODE, bool CPL> static void launch_mode_t(thcmb_ctx* c, const AsmArgs& a, int nblk) {
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_assemble_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<MODE>)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_assemble_kernel<MODE, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem<MODE>)));
         attr_set = true;
     }
-    thcm_assemble_kernel<MODE><<<nblk, 32 * mode_warps(MODE), sizeof(Smem<MODE>), c->stream>>>(a);
+    thcm_assemble_kernel<MODE, CPL><<<nblk, 32 * mode_warps(MODE), sizeof(Smem<MODE>), c->stream>>>(a);
+}
+template <int MODE> static void launch_mode(thcmb_ctx* c, const AsmArgs& a, int nblk) {
+    if (a.t.coupled_T || a.t.coupled_S) launch_mode_t<MODE, true>(c, a, nblk);
+    else launch_mode_t<MODE, false>(c, a, nblk);
 }
 
 int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA) {

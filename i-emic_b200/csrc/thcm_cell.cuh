@@ -266,7 +266,9 @@ template <int R, int LOC, int COL> THCM_HD double& entref(double* E) {
 // ---------------------------------------------------------------------------
 // row evaluation: An = Al (lin, usrc.F90:690-785) + nonlinear atoms (usrc.F90:842-882 | 950-1007)
 // ---------------------------------------------------------------------------
-template <int R, bool JAC, class Tile, class Tabs>
+// CPL: compile the coupled-mode terms in (the uncoupled kernels carry none of that code: their instruction streams are
+// instruction-cache bound)
+template <int R, bool JAC, bool CPL, class Tile, class Tabs>
 THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const Cell& c, double sm, const Tile& tile, const Tabs& tabs) {
     const int gi = c.gi, gj = c.gj, k = c.k, N = blk.N, M = blk.M, L = blk.L;
     const int a = 0;  // (the accessors below keep the call shape of the global-memory versions)
@@ -398,9 +400,13 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
         // restoring term TRES*bi*tc | SRES*bi*sc, or -- coupled to an external atmosphere / sea ice (usrc.F90:742-783) -- the
         // sensible + latent heat flux and sea-ice terms of the surface level (tc = sc = 1 and mc = msi at k = l, else 0, so
         // the lower levels only add exact zeros); TT,SS / SS,TT centre entries below
-        const bool cpl = (R == TT ? t.coupled_T : t.coupled_S) && k == L;
-        const double mc = cpl ? THCM_LDG(t.msi + (size_t)c.lj * blk.n0 + c.li) : 0.0;
-        if (cpl) {
+        bool cpl = false;
+        double mc = 0.0;
+        if constexpr (CPL) {
+            cpl = (R == TT ? t.coupled_T : t.coupled_S) && k == L;
+            if (cpl) mc = THCM_LDG(t.msi + (size_t)c.lj * blk.n0 + c.li);
+        }
+        if (CPL && cpl) {
             if constexpr (R == TT) l5 = l5 + t.cpl_ooa + t.cpl_dedt_t + mc * (t.cpl_qtz - t.cpl_ooa - t.cpl_dedt_t);
             else l5 = l5 - mc * t.cpl_pq * t.cpl_zeta * t.cpl_a0 / t.cpl_rl;
         } else {
@@ -421,7 +427,7 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
         ENT(4, R) = l4 + y4; ENT(6, R) = l6 + y6;
         ENT(5, R) = l5 + x5 + y5 + z5;
         ENT(14, R) = l14 + z14; ENT(23, R) = l23 + z23;
-        if (cpl) {
+        if (CPL && cpl) {
             if constexpr (R == TT) {
                 ENT(5, SS) = t.cpl_ts * mc;                                  // Al(TT,SS) = -QTnd*zeta*a0*mc (usrc.F90:755)
             } else {

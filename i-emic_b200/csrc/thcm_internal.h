@@ -213,8 +213,9 @@ struct thcmb_ctx {
     int *begF = nullptr, *jcoF = nullptr; double *coF = nullptr;   // get_stochastic_forcing (forcing.F90:235-280)
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
-    int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (THCM_FUSED_CGS2=1); off until
-                                    // it has been measured on the GPU (single rank first: the multi-rank tail is shared with multi_dot)
+    int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
+                                    // iteration instead of four; measured 82.5 -> 79.0 ms per Newton step at 1 degree, r01c).  On by
+                                    // default on one rank; THCM_FUSED_CGS2=0|1 overrides (multi-rank: not yet measured, off)
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 

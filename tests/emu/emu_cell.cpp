@@ -46,7 +46,7 @@ void cell_row(const AsmArgs& a, int cell, double* E, Cell& c, int& cls, uint32_t
     double sm = (double)(int)(int8_t)a.surf[lj * b.n0 + li];
     cls = (c.gi == 1 ? 1 : 0) | (c.gi == b.N ? 2 : 0) | (c.gj == 1 ? 4 : 0) | (c.gj == b.M ? 8 : 0) | (c.k == 1 ? 16 : 0) | (c.k == b.L ? 32 : 0);
     if (!((nb >> 4) & 1u)) {
-        eval_row<R, JAC>(E, a.t, a.b, c, sm, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
+        eval_row<R, JAC, true>(E, a.t, a.b, c, sm, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
         if constexpr (JAC && (R == TT || R == SS)) vmix_jac<R>(E, a.t, c, nb, DirectTile{a, c.gi, c.gj, c.k}, DirectTabs{a.t, c.gj, c.k});
     }
     boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);

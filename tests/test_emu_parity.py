@@ -247,3 +247,35 @@ def test_insert_masks_the_freshwater_fields():
     o.rhs(x)
     assert np.array_equal(o.forcing(), e.forcing(masked=True))
     assert np.array_equal(o.rhs(x), e.rhs(x))
+
+
+@pytest.mark.parametrize("name", ["gateway16", "box_np"])
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_coupled_mode_on_decomposed_blocks(name, nranks):
+    """Coupled mode on the 2-D decomposition: every rank holds the GLOBAL surface fields, restricts msi to its columns and
+    must reproduce the owned rows of the 1-rank residual, Jacobian and forcing."""
+    flags = dict(coupled_T=1, coupled_S=1)
+    s, landm, o, _ = setup(name, pars=dict(PARS, SUNP=1.0), **flags)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    fo = o.forcing()            # as `forcing` leaves it (before rhs zeroes the identity rows)
+    B = o.rhs(x)
+    vo, _ = o.jacobian_graph(x)
+    ro, _ = o.graph()
+    for rank in range(nranks):
+        sr, _ = CASES[name](rank=rank, nranks=nranks, **flags)
+        e = EmuTHCM(sr, landm)
+        for k, v in dict(PARS, SUNP=1.0).items():
+            e.setpar(P[k], v)
+        cases.apply_coupled(e, fields, atmos, seaice)
+        gid = e.local_gids()
+        hg = e.halo_gids()
+        halo = np.where(hg >= 0, x[np.maximum(hg, 0)], np.nan)
+        xl = x[gid]
+        assert np.array_equal(e.forcing(masked=False), fo[gid])
+        assert np.array_equal(e.rhs(xl, halo), B[gid])
+        rp, _ = e.graph()
+        val = e.jacobian(xl, halo)
+        idx = np.concatenate([np.arange(ro[g], ro[g + 1]) for g in gid])
+        assert np.array_equal(val, vo[idx])
