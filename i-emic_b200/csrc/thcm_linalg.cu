@@ -667,6 +667,108 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_axpy_dot_kernel(int n, Ve
     multi_tail((int)gridDim.x, nv, partial, counter, out, pa, ep);
 }
 
+// Variant 2 of the fused first update + second projection (THCM_FUSED_CGS2=2): L2-tiled instead of parked in shared memory.
+// A block walks over tiles of 256 double2 elements.  Phase A: thread t owns element t of the tile, streams the nv basis values
+// of that element from HBM (8 independent 16-byte loads in flight), forms w' = w - V h1, stores it to global memory and into a
+// 4 KB shared tile.  Phase B: warp q' takes the basis vectors q = q', q'+8, ... and re-reads THEIR 4 KB rows of the same tile --
+// now L2 hits, the rows were touched microseconds ago and the live tiles of all resident blocks (2 per SM x nv x 4 KB ~ 60 MB at
+// nv = 50) fit the 126 MB L2 -- against the shared w' tile; the per-lane partial sums of a vector stay in ONE register across
+// all tiles.  HBM sees the basis once; no nv-sized register arrays, no nv x 2 KB shared parking, 16 warps per SM.
+constexpr int F2_THREADS = 256;
+constexpr int F2_VPW = MD_MAXV / (F2_THREADS / 32);   // basis vectors per warp (8)
+__global__ void __launch_bounds__(F2_THREADS, 2) fused2_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h1, double* __restrict__ w,
+                                                                        double* partial, unsigned int* counter, double* out,
+                                                                        const P2PArgs pa, const RedEpilogue ep) {
+    constexpr int NW = F2_THREADS / 32;
+    __shared__ double hs[MD_MAXV];
+    __shared__ double2 wt[2][F2_THREADS];
+    __shared__ double wred[NW];
+    __shared__ bool last;
+    const int nv = vl.nv, n2 = n >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = threadIdx.x; q < nv; q += F2_THREADS) hs[q] = h1[q];
+    __syncthreads();
+    double acc[F2_VPW];
+#pragma unroll
+    for (int j = 0; j < F2_VPW; j++) acc[j] = 0.0;
+    double wwacc = 0.0;
+    double2* w2 = reinterpret_cast<double2*>(w);
+    const int ntiles = (n2 + F2_THREADS - 1) / F2_THREADS;
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int base = tile * F2_THREADS;
+        // ---- phase A: w' = w - V h1 on this thread's element (q order = the order of multi_axpy) ----
+        const int i = base + threadIdx.x;
+        const bool valid = i < n2;
+        double2 wi = valid ? w2[i] : make_double2(0.0, 0.0);
+        for (int c0 = 0; c0 < nv; c0 += MD_CHUNK) {
+            double2 vv[MD_CHUNK];
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++)
+                vv[q] = (valid && c0 + q < nv) ? reinterpret_cast<const double2*>(vl.v[c0 + q])[i] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++)
+                if (c0 + q < nv) { wi.x = wi.x - hs[c0 + q] * vv[q].x; wi.y = wi.y - hs[c0 + q] * vv[q].y; }
+        }
+        if (valid) w2[i] = wi;
+        wt[buf][threadIdx.x] = wi;
+        wwacc += wi.x * wi.x; wwacc += wi.y * wi.y;
+        __syncthreads();   // the tile is complete; also: every warp has left phase B of tile - 1, whose buffer tile + 1 will overwrite
+        // ---- phase B: h2[q] += V_q[tile] . w'[tile] for this warp's vectors (L2 hits) ----
+#pragma unroll
+        for (int j = 0; j < F2_VPW; j++) {
+            const int q = warp + NW * j;
+            if (q < nv) {
+                const double2* vq = reinterpret_cast<const double2*>(vl.v[q]) + base;
+                double2 v[F2_THREADS / 32];
+#pragma unroll
+                for (int r = 0; r < F2_THREADS / 32; r++) {
+                    const int e = lane + 32 * r;
+                    v[r] = (base + e < n2) ? vq[e] : make_double2(0.0, 0.0);
+                }
+                double a = acc[j];
+#pragma unroll
+                for (int r = 0; r < F2_THREADS / 32; r++) {
+                    const double2 wv = wt[buf][lane + 32 * r];
+                    a += wv.x * v[r].x; a += wv.y * v[r].y;
+                }
+                acc[j] = a;
+            }
+        }
+    }
+    // per-block results: one (warp, j) pair per vector, lanes summed by a shuffle tree; w'.w' over the whole block
+    constexpr int stride = MD_MAXV + 1;
+#pragma unroll
+    for (int j = 0; j < F2_VPW; j++) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int q = warp + NW * j;
+        if (lane == 0 && q < nv) partial[(size_t)blockIdx.x * stride + q] = v;
+    }
+    {
+        double v = wwacc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wred[warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int ww = 0; ww < NW; ww++) v += wred[ww];
+        partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, ep);
+}
+
 // w -= sum_q h[q] v_q  (applied in q order);  skipped when *skip == 0
 __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, VecList vl, const double* __restrict__ h, const int* __restrict__ skip,
                                                           double* __restrict__ w) {
@@ -805,6 +907,14 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
     const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out};
+    if (c->fused_cgs2 == 2) {
+        ProfScope prof_(c, KID_MULTIAXPY);
+        const int ntiles = ((n >> 1) + F2_THREADS - 1) / F2_THREADS;
+        const int grid = std::max(1, std::min(std::min(ntiles, NSM * 2), MD_BLOCKS));
+        fused2_axpy_dot_kernel<<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        c->launches++;
+        return 0;
+    }
     { ProfScope prof_(c, KID_MULTIAXPY);
       if (nv <= 16) launch_fused<16>(c, n, vl, d_h1, w, d_out, ep);
       else if (nv <= 32) launch_fused<32>(c, n, vl, d_h1, w, d_out, ep);
