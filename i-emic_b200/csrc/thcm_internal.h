@@ -214,8 +214,9 @@ struct thcmb_ctx {
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
     int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
-                                    // iteration instead of four; measured 82.5 -> 79.0 ms per Newton step at 1 degree, r01c).  On by
-                                    // default on one rank; THCM_FUSED_CGS2=0|1 overrides (multi-rank: not yet measured, off)
+                                    // iteration instead of four).  0 separate kernels, 1 basis values parked in shared memory, 2 L2-tiled
+                                    // (default on one rank; measured at 1 degree, r01d: 82.5 / 78.7 / 76.2 ms per Newton step).
+                                    // THCM_FUSED_CGS2 overrides; multi-rank runs default to 0 until measured
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 

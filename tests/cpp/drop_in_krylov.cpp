@@ -85,7 +85,8 @@ int main(int argc, char** argv) {
     for (int i = 0; i < n; i++) {
         const int cell = i / 6, ci = cell % N, cj = (cell / N) % M, ck = cell / (N * M);
         const bool land = landm[(size_t)(ci + 1) + (size_t)(N + 2) * ((cj + 1) + (size_t)(M + 2) * (ck + 1))] != 0;
-        x[(size_t)i] = land ? 0.0 : 0.05 * std::sin(1.0 + 0.37 * (double)i);
+        // exactly representable arithmetic only (numpy's SIMD sin and glibc's differ in the last bit)
+        x[(size_t)i] = land ? 0.0 : 0.05 * ((double)((i * 37) % 101) / 101.0 - 0.5);
     }
     ocean.getState('V')->fromHost(x.data());
     ocean.computeRHS();

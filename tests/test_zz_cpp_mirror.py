@@ -74,7 +74,7 @@ def test_reference_krylov_templates_run_on_the_device():
     n = d["n"]
     assert n == o.ndim
     land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
-    x = np.where(land, 0.0, 0.05 * np.sin(1.0 + 0.37 * np.arange(n)))
+    x = np.where(land, 0.0, 0.05 * (((np.arange(n) * 37) % 101) / 101.0 - 0.5))   # the program's state, exact arithmetic only
     assert np.array_equal(np.array(d["rhs"]), -o.rhs(x))
     # reference GMRES template over device kernels vs the in-library GMRES
     href, hlib = np.array(d["hist_ref"])[1:], np.array(d["hist_lib"])
