@@ -61,11 +61,11 @@ static void print_vec(const char* name, const std::vector<double>& v, bool last 
 
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: drop_in_krylov <mask_natl8 file>\n"); return 2; }
-    const double PI = 3.14159265358979323846, D2R = PI / 180.0;
+    const double PI = 3.14159265358979323846;   // THCMdefs.H:19; degrees are converted as value * PI_ / 180.0 (THCM.C:203-206)
     // test/ocean/ocean_params.xml: 8 x 8 x 4 North Atlantic box, non-periodic
     int N = 8, M = 8, L = 4, periodic = 0, itopo = 0, flat = 0, rd_mask = 1, TRES = 1, SRES = 1, iza = 2, ite = 1, its = 1, rd_spertm = 0,
         cT = 0, cS = 0, ftype = 0;
-    double xmin = 286 * D2R, xmax = 350 * D2R, ymin = 10 * D2R, ymax = 74 * D2R, hdim = 4000.0, qz = 1.0;
+    double xmin = 286 * PI / 180.0, xmax = 350 * PI / 180.0, ymin = 10 * PI / 180.0, ymax = 74 * PI / 180.0, hdim = 4000.0, qz = 1.0;
     __m_global_MOD_initialize(&N, &M, &L, &xmin, &xmax, &ymin, &ymax, &hdim, &qz, &periodic, &itopo, &flat, &rd_mask, &TRES, &SRES, &iza,
                               &ite, &its, &rd_spertm, &cT, &cS, &ftype, argv[1], "", "", "", "");
     std::vector<int> landm((size_t)(N + 2) * (M + 2) * (L + 2));
