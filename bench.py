@@ -231,8 +231,9 @@ def main():
     for k, v in PARS.items():
         t.setParameter(k, v)
     t.set_ortho(a.ortho)
-    config["gmres_orthogonalisation"] = ("batched Gram-Schmidt + DGKS criterion (Belos 'DGKS', Ocean.C:977-1024)" if a.ortho == "dgks"
-                                         else "modified Gram-Schmidt (GMRESSolver.H:177-181)")
+    config["gmres_orthogonalisation"] = ("batched Gram-Schmidt + DGKS criterion (Belos 'DGKS', Ocean.C:977-1024); on one GPU the first "
+                                         "update and the second projection share one sweep over the basis (3 basis reads per iteration)"
+                                         if a.ortho == "dgks" else "modified Gram-Schmidt (GMRESSolver.H:177-181)")
     xg = cases.consistent_state(s, landm, scale=0.05)
     x_local = xg[t.local_gids()]
     xd = torch.from_numpy(x_local).cuda()

@@ -907,7 +907,9 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
     const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out};
-    if (c->fused_cgs2 == 2) {
+    // measured (profiles/ncu_full_r01d_fused_cgs2_summary.json): at nv = 11 the shared-memory kernel <16> needs 0.17 ms, the L2-tiled one
+    // 0.21 ms; averaged over nv = 1..50 it is 0.47 vs 0.40 ms (the <32..64> instantiations park up to 131 KB per block)
+    if (c->fused_cgs2 == 2 && nv > 16) {
         ProfScope prof_(c, KID_MULTIAXPY);
         const int ntiles = ((n >> 1) + F2_THREADS - 1) / F2_THREADS;
         const int grid = std::max(1, std::min(std::min(ntiles, NSM * 2), MD_BLOCKS));
