@@ -1,0 +1,69 @@
+"""BASELINE.json configs as parity cases at their FULL size where the oracle finishes in seconds: configs[1] = the synthetic
+2-degree global grid 180x76x16 (Jacobian assembly + SpMV sweep).  configs[0] (4 degree, real mask) is `global4deg` in
+test_emu_parity.py / test_gpu_parity.py, configs[2] the coupled-mode tests there, configs[3] (1 degree) the property test
+`test_full_size_properties_1deg`; configs[4] (0.5 degree, 8 GPUs) is a bench configuration (`bench.py --grid 720 304 32`)."""
+import numpy as np
+import pytest
+
+import cases
+from cases import PAR_INDEX as P
+
+PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
+
+
+@pytest.fixture(scope="module")
+def two_degree():
+    from oracle.oracle import OracleTHCM
+    s, landm = cases.global_synth(180, 76, 16)
+    o = OracleTHCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+    x = cases.random_state(s, landm, scale=0.1)
+    B = o.rhs(x)
+    val, missing = o.jacobian_graph(x)
+    assert missing == 0
+    return s, landm, o, x, B, val
+
+
+def test_two_degree_device_functions_bit_exact(two_degree):
+    """The library's device functions (compiled for the host) against the oracle on the full 2-degree grid."""
+    from emu.emu import EmuTHCM
+    s, landm, o, x, B, val = two_degree
+    e = EmuTHCM(s, landm)
+    for k, v in PARS.items():
+        e.setpar(P[k], v)
+    assert np.array_equal(e.rhs(x), B)
+    assert np.array_equal(e.jacobian(x), val)
+    assert e.check_tiles(x) == 0
+    rp, col = e.graph()
+    ro, co = o.graph()
+    assert np.array_equal(rp, ro) and np.array_equal(col, co)
+    assert 22_000_000 < len(col) <= 104 * s.N * s.M * s.L           # ~104 entries per cell before edge clipping
+
+
+@pytest.mark.gpu
+def test_two_degree_assembly_and_spmv_sweep(two_degree):
+    """configs[1] on the B200 through the C ABI: residual and Jacobian bit-exact, a sweep of SpMVs within 1e-13 (2-norm)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import spmv
+    s, landm, o, x, B, val = two_degree
+    t = iemic_b200.THCM(s, landm)
+    for k, v in PARS.items():
+        t.setParameter(k, v)
+    xd = torch.from_numpy(x).cuda()
+    F = t.new_vector()
+    t.evaluate(xd, F, True)
+    assert np.array_equal(F.cpu().numpy(), -B)
+    assert np.array_equal(t.jacobian_values_host(), val)
+    rowptr, col = o.graph()
+    rng = np.random.default_rng(2)
+    y = t.new_vector()
+    for _ in range(4):
+        v = rng.standard_normal(t.ndim)
+        t.applyMatrix(torch.from_numpy(v).cuda(), y)
+        yo = spmv(rowptr, col, val, v)
+        assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
+    t.close()
