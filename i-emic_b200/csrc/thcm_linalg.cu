@@ -676,9 +676,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_axpy_dot_kernel(int n, Ve
 // all tiles.  HBM sees the basis once; no nv-sized register arrays, no nv x 2 KB shared parking, 16 warps per SM.
 constexpr int F2_THREADS = 256;
 constexpr int F2_VPW = MD_MAXV / (F2_THREADS / 32);   // basis vectors per warp (8)
-__global__ void __launch_bounds__(F2_THREADS, 2) fused2_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h1, double* __restrict__ w,
-                                                                        double* partial, unsigned int* counter, double* out,
-                                                                        const P2PArgs pa, const RedEpilogue ep) {
+// BPS: resident blocks per SM the register budget is bounded for, CHUNK: independent basis loads per thread in phase A
+template <int BPS, int CHUNK>
+__global__ void __launch_bounds__(F2_THREADS, BPS) fused2_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h1, double* __restrict__ w,
+                                                                          double* partial, unsigned int* counter, double* out,
+                                                                          const P2PArgs pa, const RedEpilogue ep) {
     constexpr int NW = F2_THREADS / 32;
     __shared__ double hs[MD_MAXV];
     __shared__ double2 wt[2][F2_THREADS];
@@ -701,13 +703,13 @@ __global__ void __launch_bounds__(F2_THREADS, 2) fused2_axpy_dot_kernel(int n, V
         const int i = base + threadIdx.x;
         const bool valid = i < n2;
         double2 wi = valid ? w2[i] : make_double2(0.0, 0.0);
-        for (int c0 = 0; c0 < nv; c0 += MD_CHUNK) {
-            double2 vv[MD_CHUNK];
+        for (int c0 = 0; c0 < nv; c0 += CHUNK) {
+            double2 vv[CHUNK];
 #pragma unroll
-            for (int q = 0; q < MD_CHUNK; q++)
+            for (int q = 0; q < CHUNK; q++)
                 vv[q] = (valid && c0 + q < nv) ? reinterpret_cast<const double2*>(vl.v[c0 + q])[i] : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int q = 0; q < MD_CHUNK; q++)
+            for (int q = 0; q < CHUNK; q++)
                 if (c0 + q < nv) { wi.x = wi.x - hs[c0 + q] * vv[q].x; wi.y = wi.y - hs[c0 + q] * vv[q].y; }
         }
         if (valid) w2[i] = wi;
@@ -912,8 +914,14 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     if (c->fused_cgs2 == 2 && nv > 16) {
         ProfScope prof_(c, KID_MULTIAXPY);
         const int ntiles = ((n >> 1) + F2_THREADS - 1) / F2_THREADS;
-        const int grid = std::max(1, std::min(std::min(ntiles, NSM * 2), MD_BLOCKS));
-        fused2_axpy_dot_kernel<<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        // resident blocks per SM x independent phase-A loads per thread, measured at 1 degree (Newton step, profiles/bench_r01g_*):
+        // 2 x 8 (92 registers) 75.6 ms, 3 x 4 (78 registers) 74.5 ms, 4 x 4 (64 registers) 77.5 ms.  THCM_FUSED2_BPS overrides.
+        // The live tiles stay below the L2 size: BPS x 148 x nv x 4 KB = 89 MB at nv = 50
+        static const int bps = [] { const char* e = getenv("THCM_FUSED2_BPS"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
+        const int grid = std::max(1, std::min(std::min(ntiles, NSM * bps), MD_BLOCKS));
+        if (bps == 2) fused2_axpy_dot_kernel<2, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        else if (bps == 3) fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        else fused2_axpy_dot_kernel<4, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
         c->launches++;
         return 0;
     }
