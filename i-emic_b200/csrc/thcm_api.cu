@@ -53,10 +53,17 @@ void upload_params(thcmb_ctx* c) {
     upload(c->d_cob, c->cob_local);
 }
 
+// mass diagonal of the rows THCM::evaluate replaces (integral condition, pressure Dirichlet rows) = 0 (THCM.C:1220-1240)
+void zero_cob_of_fixed_rows(thcmb_ctx* c) {
+    if (c->ic_on && c->ic_lrow >= 0) c->cob_local[(size_t)c->ic_lrow] = 0.0;
+    if (c->pfix_on) for (int q = 0; q < 2; q++) if (c->pfix_lrow[q] >= 0) c->cob_local[(size_t)c->pfix_lrow[q]] = 0.0;
+}
+
 void refresh_params(thcmb_ctx* c) {  // forcing + lin (usrc.F90:178-179)
     compute_forcing(c);
     compute_tables(c);
     compute_cob(c);
+    zero_cob_of_fixed_rows(c);
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     upload_params(c);
 }
@@ -177,7 +184,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter, (void*)c->d_bcell, (void*)c->d_brows,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
-                    (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob})
+                    (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -269,6 +276,56 @@ double thcmb_intcond_coeff(const thcmb_ctx* c, double* coeff) {
     for (int q = 0; q < len; q++) { coeff[ind[q] - 1] = val[q]; vol += std::fabs(val[q]); }
     return vol;
 }
+/* The row replacements THCM::evaluate makes above the Fortran core.  Local row of a global cell (0-based i, j, k) or -1. */
+static int local_row_of(const thcmb_ctx* c, int gi, int gj, int k, int XX) {
+    const Block& b = c->blk;
+    const int li = gi - b.i0, lj = gj - b.j0;
+    if (li < 0 || li >= b.n0 || lj < 0 || lj >= b.m0) return -1;
+    return NUN * ((k * b.m0 + lj) * b.n0 + li) + XX - 1;
+}
+static void refresh_fix_rows(thcmb_ctx* c) {
+    compute_cob(c);
+    zero_cob_of_fixed_rows(c);
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    upload(c->d_cob, c->cob_local);
+}
+/* THCM.C:653-697: the salinity integral condition replaces the S row of cell (Nic, Mic, L-1) (0-based; -1 = N-1 / M-1); only
+ * with SRES = 0, and the cell's surface point must be ocean.  sign = "Salinity Integral Sign" (+-1, default -1) */
+void thcmb_enable_intcond(thcmb_ctx* c, int Nic, int Mic, int sign) {
+    const thcmb_settings& s = c->s;
+    if (s.SRES != 0) fatal("the salinity integral condition needs SRES = 0 (Restoring Salinity Profile = 0)");
+    if (sign != 1 && sign != -1) fatal("Salinity Integral Sign must be +1 or -1");     // THCM.C:261
+    if (Nic < 0) Nic = s.N - 1;
+    if (Mic < 0) Mic = s.M - 1;
+    if (Nic >= s.N || Mic >= s.M) fatal("Integral row coordinates outside the domain");
+    if (c->landm[(size_t)(Nic + 1) + (size_t)(s.N + 2) * ((Mic + 1) + (size_t)(s.M + 2) * s.L)] != 0)
+        fatal("Integral row coordinates (" + std::to_string(Nic) + "," + std::to_string(Mic) + ") give a land point! Please give better coordinates");
+    c->ic_on = true; c->ic_sign = sign;
+    c->ic_grow = NUN * (((s.L - 1) * s.M + Mic) * s.N + Nic) + SS - 1;
+    c->ic_lrow = local_row_of(c, Nic, Mic, s.L - 1, SS);
+    std::vector<double> coeff((size_t)c->blk.ndim());
+    thcmb_intcond_coeff(c, coeff.data());
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    upload(c->d_iccoeff, coeff);
+    refresh_fix_rows(c);
+}
+/* THCM::setIntCondCorrection (THCM.C:2078-2097): the salinity integral of d_vec becomes the target of the condition */
+double thcmb_set_intcond_correction(thcmb_ctx* c, const double* d_vec) {
+    if (!c->ic_on) fatal("setIntCondCorrection: the integral condition is not enabled");
+    c->ic_correction = thcmb_dot(c, c->blk.ndim(), c->d_iccoeff, d_vec);
+    return c->ic_correction;
+}
+/* "Fix Pressure Points" (THCM.C:749-757, 2258-2296): Dirichlet rows for the pressure of the cells (N-1, M-1, L-1) and (N-2, M-1, L-1) */
+void thcmb_fix_pressure_points(thcmb_ctx* c, int on) {
+    const thcmb_settings& s = c->s;
+    c->pfix_on = on != 0;
+    for (int q = 0; q < 2; q++) {
+        c->pfix_grow[q] = NUN * (((s.L - 1) * s.M + (s.M - 1)) * s.N + (s.N - 1 - q)) + PP - 1;
+        c->pfix_lrow[q] = local_row_of(c, s.N - 1 - q, s.M - 1, s.L - 1, PP);
+    }
+    refresh_fix_rows(c);
+}
+int thcmb_intcond_row(const thcmb_ctx* c) { return c->ic_on ? c->ic_grow : -1; }
 void thcmb_set_vmix_fix(thcmb_ctx* c, int fix) { c->vmix_fix = fix; }   /* m_mix::set_vmix_fix, mix.F90:52-59 */
 void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4) { out4[0] = c->vmix_flag; out4[1] = c->vmix_temp; out4[2] = c->vmix_salt; out4[3] = c->vmix_fix; }
 
@@ -294,13 +351,15 @@ int thcmb_residual_dev(thcmb_ctx* c, const double* d_un, double* d_F) {
     c->frc_masked = true;
     vmix_control(c, d_un);
     halo_exchange(c, d_un);
-    return launch_assembly(c, MODE_RHS | 0x100, d_un, d_F, nullptr, nullptr, nullptr);
+    launch_assembly(c, MODE_RHS | 0x100, d_un, d_F, nullptr, nullptr, nullptr);
+    return fix_residual_rows(c, d_un, d_F);   // integral condition / pressure Dirichlet rows (THCM.C:1013-1041), no-op unless enabled
 }
 int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un) {
     c->frc_masked = true;
     vmix_control(c, d_un);
     halo_exchange(c, d_un);
-    return launch_assembly(c, MODE_JAC_GRAPH, d_un, nullptr, nullptr, nullptr, nullptr);
+    launch_assembly(c, MODE_JAC_GRAPH, d_un, nullptr, nullptr, nullptr, nullptr);
+    return fix_jacobian_rows(c);              // THCM.C:1164-1172, no-op unless enabled
 }
 const double* thcmb_jacobian_values(const thcmb_ctx* c) { return c->d_val; }
 const int* thcmb_graph_rowptr_dev(const thcmb_ctx* c) { return c->d_rowptr; }
@@ -325,10 +384,12 @@ int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y) {
         halo_exchange(c, d_x, false);
         spmv_part(c, 0, d_x, d_y);
         halo_wait(c);
-        return spmv_part(c, 1, d_x, d_y);
+        spmv_part(c, 1, d_x, d_y);
+        return fix_spmv_rows(c, d_x, d_y);
     }
     halo_exchange(c, d_x);
-    return spmv(c, c->blk.ndim(), c->d_rowptr, c->d_col, c->d_val, d_x, c->d_halo, c->blk.ndim(), d_y);
+    spmv(c, c->blk.ndim(), c->d_rowptr, c->d_col, c->d_val, d_x, c->d_halo, c->blk.ndim(), d_y);
+    return fix_spmv_rows(c, d_x, d_y);        // the dense integral-condition row: one more dot product, only when enabled
 }
 int thcmb_csr_spmv_dev(thcmb_ctx* c, int nrow, const int* d_rowptr, const int* d_col, const double* d_val, const double* d_x, double* d_y) {
     return spmv(c, nrow, d_rowptr, d_col, d_val, d_x, d_x, 0x7fffffff, d_y);

@@ -211,6 +211,12 @@ struct thcmb_ctx {
     // borrowed host CRS pointers (m_mat::set_pointers)
     int *begA = nullptr, *jcoA = nullptr; double *coA = nullptr, *coB = nullptr;
     int *begF = nullptr, *jcoF = nullptr; double *coF = nullptr;   // get_stochastic_forcing (forcing.F90:235-280)
+    // row replacements of THCM::evaluate (THCM.C:1013-1041, 1164-1172): salinity integral condition (SRES = 0), pressure Dirichlet rows
+    bool ic_on = false, pfix_on = false;
+    int ic_sign = -1, ic_grow = -1, ic_lrow = -1;   // "Salinity Integral Sign", global row (rowintcon_), local row or -1 when not owned
+    double ic_correction = 0.0;                      // THCM::setIntCondCorrection (THCM.C:2078-2097)
+    double* d_iccoeff = nullptr;                     // intcondCoeff_ on the owned rows
+    int pfix_grow[2] = {-1, -1}, pfix_lrow[2] = {-1, -1};
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
     int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
@@ -302,6 +308,9 @@ int fill(thcmb_ctx* c, int n, double a, double* x);
 int theta_rhs(thcmb_ctx* c, int n, double theta, double dt, const double* state, const double* old_state, const double* old_rhs,
               const double* d_cob, double* F);
 int theta_jacobian(thcmb_ctx* c, double theta, double dt, const double* d_cob);
+int fix_residual_rows(thcmb_ctx* c, const double* d_un, double* d_F);
+int fix_spmv_rows(thcmb_ctx* c, const double* d_x, double* d_y);
+int fix_jacobian_rows(thcmb_ctx* c);
 int build_blockdiag(thcmb_ctx* c);
 int average_block(thcmb_ctx* c, double* db36);
 bool scaling_compute(const thcmb_ctx* c, const double* db36, double* row_scaling, double* col_scaling);

@@ -415,6 +415,55 @@ int fill(thcmb_ctx* c, int n, double a, double* x) {
 }
 
 // ---------------------------------------------------------------------------
+// Row replacements THCM::evaluate applies on top of the Fortran assembly (THCM.C:1013-1041, 1164-1172, 2180-2296): the salinity
+// integral condition row (SRES = 0: F_row = sign (c.x - correction), J_row = sign c^T, a DENSE row that is not part of the
+// static graph -- its product is a dot product) and the two pressure Dirichlet rows ("Fix Pressure Points": identity rows).
+// rows3 = {integral row, pfix1, pfix2} as LOCAL row ids, -1 = not owned / off.
+// ---------------------------------------------------------------------------
+struct FixRows { int ic, p1, p2; };
+__global__ void fix_residual_rows_kernel(FixRows r, double sign, const double* __restrict__ cx, double correction, double* __restrict__ F) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (r.ic >= 0) F[r.ic] = sign * (*cx - correction);
+    if (r.p1 >= 0) F[r.p1] = 0.0;
+    if (r.p2 >= 0) F[r.p2] = 0.0;
+}
+__global__ void fix_spmv_rows_kernel(FixRows r, double sign, const double* __restrict__ cx, const double* __restrict__ x, double* __restrict__ y) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (r.ic >= 0) y[r.ic] = sign * (*cx);
+    (void)x;   // the pressure rows are identity rows of the stored matrix already
+}
+__global__ void fix_jacobian_rows_kernel(FixRows r, const int* __restrict__ rp, const int* __restrict__ col, double* __restrict__ val) {
+    const int rows[3] = {r.ic, r.p1, r.p2};
+    const int which = blockIdx.x;
+    const int row = rows[which];
+    if (row < 0) return;
+    for (int q = rp[row] + threadIdx.x; q < rp[row + 1]; q += blockDim.x)
+        val[q] = (which > 0 && col[q] == row) ? 1.0 : 0.0;   // integral row: the sparse part is empty (the dense part lives in the SpMV)
+}
+int fix_residual_rows(thcmb_ctx* c, const double* d_un, double* d_F) {
+    if (!c->ic_on && !c->pfix_on) return 0;
+    if (c->ic_on) dot_dev(c, c->blk.ndim(), c->d_iccoeff, d_un, c->d_scalars + 4010);
+    fix_residual_rows_kernel<<<1, 32, 0, c->stream>>>(FixRows{c->ic_on ? c->ic_lrow : -1, c->pfix_on ? c->pfix_lrow[0] : -1, c->pfix_on ? c->pfix_lrow[1] : -1},
+                                                      (double)c->ic_sign, c->d_scalars + 4010, c->ic_correction, d_F);
+    c->launches++;
+    return 0;
+}
+int fix_spmv_rows(thcmb_ctx* c, const double* d_x, double* d_y) {
+    if (!c->ic_on) return 0;
+    dot_dev(c, c->blk.ndim(), c->d_iccoeff, d_x, c->d_scalars + 4010);
+    fix_spmv_rows_kernel<<<1, 32, 0, c->stream>>>(FixRows{c->ic_lrow, -1, -1}, (double)c->ic_sign, c->d_scalars + 4010, d_x, d_y);
+    c->launches++;
+    return 0;
+}
+int fix_jacobian_rows(thcmb_ctx* c) {
+    if (!c->ic_on && !c->pfix_on) return 0;
+    fix_jacobian_rows_kernel<<<3, 32, 0, c->stream>>>(FixRows{c->ic_on ? c->ic_lrow : -1, c->pfix_on ? c->pfix_lrow[0] : -1, c->pfix_on ? c->pfix_lrow[1] : -1},
+                                                      c->d_rowptr, c->d_col, c->d_val);
+    c->launches++;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // Theta time stepping (src/transient/ThetaModel.H:87-165): the implicit step reuses residual, Jacobian and solver and adds
 //   rhs_theta = M (u_n - u_{n+1}) + dt (1 - theta) F(u_n) + dt theta F(u_{n+1})      (one fused elementwise kernel)
 //   J_theta   = J - M / (theta dt)   on the diagonal of the stored graph Jacobian     (one thread per row)

@@ -91,6 +91,8 @@ def load_library(path=None):
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
         "thcmb_theta_rhs_dev": (i, [vp, d, d, vp, vp, vp, vp]), "thcmb_theta_jacobian_dev": (i, [vp, d, d]),
+        "thcmb_enable_intcond": (None, [vp, i, i, i]), "thcmb_set_intcond_correction": (d, [vp, vp]),
+        "thcmb_fix_pressure_points": (None, [vp, i]), "thcmb_intcond_row": (i, [vp]),
         "thcmb_insert_field": (None, [vp, i, vp]), "thcmb_set_atmos_parameters": (None, [vp, vp]),
         "thcmb_set_seaice_parameters": (None, [vp, vp]),
         "thcmb_nccl_unique_id": (i, [vp]), "thcmb_nccl_init": (i, [vp, vp]),
@@ -384,6 +386,20 @@ class THCM:
         coeff = np.empty(self.ndim)
         vol = self.L_.thcmb_intcond_coeff(self.ctx, _np_ptr(coeff))
         return coeff, vol
+
+    def enableIntegralCondition(self, Nic=-1, Mic=-1, sign=-1):
+        """The salinity integral condition of THCM::evaluate (SRES = 0; THCM.C:653-697, 1013-1026, 2180-2256); returns the global row."""
+        self.L_.thcmb_enable_intcond(self.ctx, int(Nic), int(Mic), int(sign))
+        return self.L_.thcmb_intcond_row(self.ctx)
+
+    def setIntCondCorrection(self, vec):
+        """THCM::setIntCondCorrection (THCM.C:2078-2097)."""
+        self._pre()
+        return self.L_.thcmb_set_intcond_correction(self.ctx, _dev_ptr(vec))
+
+    def fixPressurePoints(self, on=True):
+        """"Fix Pressure Points" (THCM.C:749-757, 2258-2296)."""
+        self.L_.thcmb_fix_pressure_points(self.ctx, 1 if on else 0)
 
     def set_vmix_fix(self, fix):
         """m_mix::set_vmix_fix (THCM.C:2639-2647): 0 lets the next rhs / matrix call re-decide the Mixing = 2 partition."""

@@ -299,6 +299,17 @@ int thcmb_recompute_scaling(thcmb_ctx* c, double* row_scaling, double* col_scali
 /* THCM::getIntCondCoeff (THCM.C:2608-2637): integral-condition coefficients on the owned S rows; returns the local volume */
 double thcmb_intcond_coeff(const thcmb_ctx* c, double* coeff);
 void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4);
+/* The row replacements THCM::evaluate makes above the Fortran core (THCM.C:653-697, 1013-1041, 1164-1172, 2180-2296).
+ * thcmb_enable_intcond: with SRES = 0 the S row of cell (Nic, Mic, L-1) (0-based, -1 = N-1 / M-1; "Integral row coordinate
+ * i / j") becomes the salinity integral condition: F_row = sign (c.x - correction), J_row = sign c^T (c = thcmb_intcond_coeff,
+ * sign = "Salinity Integral Sign").  The row is dense: it is not stored in the graph, thcmb_spmv_dev adds it as one fused
+ * dot product + all-reduce.  thcmb_set_intcond_correction = THCM::setIntCondCorrection (returns the correction);
+ * thcmb_fix_pressure_points = "Fix Pressure Points" (identity rows for p of the cells (N-1, M-1, L-1), (N-2, M-1, L-1)).
+ * All three also zero the mass diagonal of the replaced rows.  thcmb_intcond_row: global row id (0-based) or -1 */
+void thcmb_enable_intcond(thcmb_ctx* c, int Nic, int Mic, int sign);
+double thcmb_set_intcond_correction(thcmb_ctx* c, const double* d_vec);
+void thcmb_fix_pressure_points(thcmb_ctx* c, int on);
+int thcmb_intcond_row(const thcmb_ctx* c);
 /* the same step with the state already in HBM (bench.py "value") */
 int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double tol, int maxit, int restart,
                           int precon_kind, double* fnorm, thcmb_krylov_result* res);

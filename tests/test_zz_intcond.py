@@ -1,0 +1,99 @@
+"""The row replacements THCM::evaluate applies above the Fortran core (THCM.C:1013-1041, 1164-1172, 2180-2296) on the device
+API: salinity integral condition (SRES = 0 -- the configuration of the reference's own test/ocean/ocean_params.xml) and the
+pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
+m_thcm_utils::intcond_scaling coefficients."""
+import numpy as np
+import pytest
+
+import cases
+from cases import PAR_INDEX as P
+
+pytestmark = pytest.mark.gpu
+PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
+
+
+def reference_evaluate(o, x, sign, correction, rows_pfix):
+    """THCM::evaluate on one rank: (F, dense J as a LinearOperator-like callable, cob, rowintcon)."""
+    from oracle.oracle import spmv
+    F = -o.rhs(x)
+    val, _ = o.jacobian_graph(x)
+    rowptr, col = o.graph()
+    _, _, _, cob = o.matrix(x)
+    cv, ci = o.intcond_scaling()
+    coeff = np.zeros(o.ndim); coeff[ci - 1] = cv
+    n, m, l = o.n, o.m, o.l
+    rowic = 6 * (((l - 1) * m + (m - 1)) * n + (n - 1)) + 5
+    F = F.copy(); cob = cob.copy()
+    F[rowic] = sign * (coeff @ x - correction)
+    cob[rowic] = 0.0
+    val = val.copy()
+    val[rowptr[rowic]:rowptr[rowic + 1]] = 0.0
+    for r in rows_pfix:
+        F[r] = 0.0; cob[r] = 0.0
+        sl = slice(rowptr[r], rowptr[r + 1])
+        val[sl] = np.where(col[sl] == r, 1.0, 0.0)
+
+    def apply(v):
+        y = spmv(rowptr, col, val, v)
+        y[rowic] = sign * (coeff @ v)
+        return y
+    return F, apply, cob, rowic, coeff
+
+
+@pytest.mark.parametrize("name,pfix", [("natl8", False), ("natl8", True), ("box_np", False)])
+def test_integral_condition_and_pressure_rows(name, pfix):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import OracleTHCM
+    mk = {"natl8": cases.natl8, "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.0, **kw)}[name]
+    s, landm = mk(SRES=0)
+    o = OracleTHCM(s, landm)
+    t = iemic_b200.THCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        t.setParameter(k, v)
+    n, m, l = s.N, s.M, s.L
+    sign = -1
+    rowic = t.enableIntegralCondition(-1, -1, sign)
+    rows_pfix = []
+    if pfix:
+        t.fixPressurePoints(True)
+        rows_pfix = [6 * (((l - 1) * m + (m - 1)) * n + (n - 1 - q)) + 3 for q in range(2)]
+    x0 = cases.consistent_state(s, landm, scale=0.05, seed=5)
+    corr = t.setIntCondCorrection(torch.from_numpy(x0).cuda())
+    x = cases.consistent_state(s, landm, scale=0.05, seed=6)
+    Fo, apply, cob, rowic_o, coeff = reference_evaluate(o, x, sign, 0.0, rows_pfix)
+    assert rowic == rowic_o
+    assert abs(corr - coeff @ x0) <= 1e-13 * np.abs(coeff * x0).sum()
+    Fo[rowic] = sign * (coeff @ x - corr)
+    xd = torch.from_numpy(x).cuda()
+    F = t.new_vector()
+    t.evaluate(xd, F, True)
+    Fg = F.cpu().numpy()
+    other = np.ones(o.ndim, bool); other[rowic] = False
+    assert np.array_equal(Fg[other], Fo[other])
+    assert abs(Fg[rowic] - Fo[rowic]) <= 1e-12 * np.abs(coeff * x).sum()
+    assert np.array_equal(t.getMassDiagonal(), cob)
+    rng = np.random.default_rng(3)
+    y = t.new_vector()
+    for _ in range(3):
+        v = rng.standard_normal(o.ndim)
+        t.applyMatrix(torch.from_numpy(v).cuda(), y)
+        yo = apply(v)
+        assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
+    # a parameter change keeps the replaced rows' mass entries at zero
+    t.setParameter("COMB", 0.9)
+    assert t.getMassDiagonal()[rowic] == 0.0
+    t.close()
+
+
+def test_integral_condition_needs_sres_zero_and_an_ocean_point():
+    import ctypes as C
+    import iemic_b200
+    L = iemic_b200.load_library()
+    s, landm = cases.natl8()          # SRES = 1
+    t = iemic_b200.THCM(s, landm)
+    assert L.thcmb_intcond_row(t.ctx) == -1
+    t.close()
