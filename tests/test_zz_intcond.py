@@ -8,7 +8,13 @@ import pytest
 import cases
 from cases import PAR_INDEX as P
 
-pytestmark = pytest.mark.gpu
+import os
+
+# Written after the GPU budget of round 1 was spent: the device code is compiled and reviewed but has not run
+# on a B200 yet.  THCM_RUN_UNVERIFIED=1 enables the tests; the first GPU pass of the next round does that and removes the gate.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("THCM_RUN_UNVERIFIED") != "1",
+                                 reason="not yet run on a GPU (written after the round's GPU budget was spent); set THCM_RUN_UNVERIFIED=1")]
 PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
 
 
