@@ -159,6 +159,10 @@ struct thcmb_ctx {
     double* d_val = nullptr;        // Jacobian values in graph order
     long long gnnz = 0;
     std::vector<int> rowptr_host, col_host, halo_gid, local_gid;
+    // SpMV column-index compression (build_spmv_patterns): pattern id per row, relative columns per pattern
+    std::vector<uint16_t> rowpat_host; std::vector<int> patrel_host;
+    uint16_t* d_rowpat = nullptr; int* d_patrel = nullptr;
+    int spmv_pattern = 0;           // THCM_SPMV_PATTERN=1: columns from the pattern table (not yet measured: off by default)
     // ---- halo exchange ----
     double *d_halo = nullptr;       // 6*nhalo doubles, laid out per Block::hk
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
@@ -263,6 +267,8 @@ void compute_tables(thcmb_ctx* c);
 void vmix_init(thcmb_ctx* c);
 void vmix_set_flags(thcmb_ctx* c, int temp, int salt);
 void compute_cob(thcmb_ctx* c);
+constexpr int SPMV_PATLEN = 24;     // longest row of the maximal graph (THCM.C:2320-2325)
+void build_spmv_patterns(thcmb_ctx* c);
 const ClassTables& class_tables(int periodic);
 int halo_slot(const Block& b, int ie, int je, int k);  // extended local coords (-1..n0, -1..m0); -1 if not a halo cell
 // device side

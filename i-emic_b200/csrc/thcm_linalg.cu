@@ -23,12 +23,16 @@ constexpr int SPMV_THREADS = 256;
 // loop exposes one memory latency per iteration and leaves the kernel latency-bound at full occupancy).
 // SEL: 0 every row; 1 rows of cells NOT flagged in `bcell` (interior rows: no halo column -- they run while the halo is
 // still in flight); 2 the rows listed in `rowlist` (rows of the boundary cells, after the halo has arrived)
-template <int LANES, int UNROLL, int SEL = 0>
+// PAT: column ids come from the pattern table (build_spmv_patterns): col = 6*cell + patrel[rowpat[row]][position]; rows with
+// rowpat = 0xFFFF (halo columns) read the explicit col array.  2 bytes per row instead of 4 bytes per entry.
+template <int LANES, int UNROLL, int SEL = 0, bool PAT = false>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
                                                                  const double* __restrict__ val, const double* __restrict__ x,
                                                                  const double* __restrict__ halo, int nlocal, double* __restrict__ y,
                                                                  const unsigned char* __restrict__ bcell = nullptr,
-                                                                 const int* __restrict__ rowlist = nullptr) {
+                                                                 const int* __restrict__ rowlist = nullptr,
+                                                                 const unsigned short* __restrict__ rowpat = nullptr,
+                                                                 const int* __restrict__ patrel = nullptr) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
     // the loop bound is warp-uniform and rows that do not take part stay in the body with an empty range: the full-mask
@@ -41,11 +45,20 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
         if constexpr (SEL == 2) row = act ? __ldg(rowlist + r0) : 0;
         const int b = act ? __ldg(rp + row) : 0, e = act ? __ldg(rp + row + 1) : 0;
         int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
+        int pat = 0xFFFF;
+        if constexpr (PAT) pat = act ? (int)__ldg(rowpat + row) : 0xFFFF;
+        const int cbase = NUN * (row / NUN);
+        const int* prel = patrel + (size_t)(pat == 0xFFFF ? 0 : pat) * SPMV_PATLEN;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int q = b + sub + u * LANES;
             const bool ok = q < e;
-            cc[u] = ok ? __ldg(col + q) : -1;
+            if constexpr (PAT) {
+                static_assert(!PAT || LANES * UNROLL <= SPMV_PATLEN, "pattern rows are at most SPMV_PATLEN long");
+                cc[u] = ok ? (pat != 0xFFFF ? cbase + __ldg(prel + sub + u * LANES) : __ldg(col + q)) : -1;
+            } else {
+                cc[u] = ok ? __ldg(col + q) : -1;
+            }
             vv[u] = ok ? __ldg(val + q) : 0.0;
         }
 #pragma unroll
@@ -96,6 +109,12 @@ int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* va
         long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
         return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 64));
     };
+    if (c->spmv_pattern && col == c->d_col && c->d_rowpat && c->d_patrel) {   // the context's own graph: pattern-compressed columns
+        spmv_csr_kernel<4, 6, 0, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
+                                                                                    c->d_rowpat, c->d_patrel);
+        c->launches++;
+        return 0;
+    }
     switch (spmv_variant()) {
     case 0: spmv_csr_kernel<8, 1><<<grid_for(8), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
     case 2: spmv_csr_kernel<4, 6><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;

@@ -43,7 +43,8 @@ def lib():
                                 ("emu_salflux", None, [vp, vp, vp, vp, vp, vp]), ("emu_temflux", None, [vp, vp, vp]),
                                 ("emu_derivatives", None, [vp, vp, vp]), ("emu_salt_advection", None, [vp, vp, vp]),
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
-                                ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp])]:
+                                ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
+                                ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -137,6 +138,14 @@ class EmuTHCM:
         beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(n * m, dtype=np.int32); co = np.zeros(n * m)
         self.L_.emu_stochastic_forcing(self.h, _p(beg), _p(jco), _p(co))
         return beg, jco, co
+
+    def spmv_patterns(self):
+        """(rowpat uint16[ndim], patrel int32[npat, 24]) of build_spmv_patterns."""
+        npat = C.c_int()
+        self.L_.emu_spmv_pattern_sizes(self.h, C.byref(npat))
+        rowpat = np.zeros(self.ndim, dtype=np.uint16); patrel = np.zeros((max(npat.value, 1), 24), dtype=np.int32)
+        self.L_.emu_spmv_patterns(self.h, _p(rowpat), _p(patrel))
+        return rowpat, patrel[:npat.value]
 
     def getdeps(self):
         out = np.empty(7); self.L_.emu_getdeps(self.h, _p(out)); return out

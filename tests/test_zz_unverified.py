@@ -1,7 +1,12 @@
-"""The row replacements THCM::evaluate applies above the Fortran core (THCM.C:1013-1041, 1164-1172, 2180-2296) on the device
+"""Device code written after the GPU budget of round 1 was spent: compiled and reviewed, host parts verified on the CPU, not yet
+run on a B200 (gated by THCM_RUN_UNVERIFIED=1, see below).
+
+(1) The row replacements THCM::evaluate applies above the Fortran core (THCM.C:1013-1041, 1164-1172, 2180-2296) on the device
 API: salinity integral condition (SRES = 0 -- the configuration of the reference's own test/ocean/ocean_params.xml) and the
 pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
-m_thcm_utils::intcond_scaling coefficients."""
+m_thcm_utils::intcond_scaling coefficients.
+(2) The SpMV with pattern-compressed column indices (THCM_SPMV_PATTERN=1; the host dictionary is verified in
+tests/test_emu_parity.py::test_spmv_column_patterns_reproduce_the_graph)."""
 import numpy as np
 import pytest
 
@@ -102,4 +107,34 @@ def test_integral_condition_needs_sres_zero_and_an_ocean_point():
     s, landm = cases.natl8()          # SRES = 1
     t = iemic_b200.THCM(s, landm)
     assert L.thcmb_intcond_row(t.ctx) == -1
+    t.close()
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
+def test_spmv_with_pattern_compressed_columns(name, monkeypatch):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import OracleTHCM, spmv
+    mk = {"natl8": cases.natl8, "gateway16": cases.gateway16, "global4deg": cases.global4deg,
+          "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw)}[name]
+    monkeypatch.setenv("THCM_SPMV_PATTERN", "1")
+    s, landm = mk()
+    o = OracleTHCM(s, landm)
+    t = iemic_b200.THCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        t.setParameter(k, v)
+    x = cases.random_state(s, landm, scale=0.2)
+    t.evaluate(torch.from_numpy(x).cuda(), None, True)
+    val, _ = o.jacobian_graph(x)
+    rowptr, col = o.graph()
+    rng = np.random.default_rng(4)
+    y = t.new_vector()
+    for _ in range(3):
+        v = rng.standard_normal(o.ndim)
+        t.applyMatrix(torch.from_numpy(v).cuda(), y)
+        yo = spmv(rowptr, col, val, v)
+        assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
     t.close()
