@@ -308,7 +308,9 @@ def main():
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     ncell_loc, ndim_loc, nnz_loc = t.ndim // 6, t.ndim, t.nnz
     alg_bytes = {  # algorithmic bytes per launch
-        "spmv_csr": nnz_loc * 12 + ndim_loc * 20,
+        # bytes actually streamed by the format being timed (SURVEY 8d accounting rule): explicit CRS = values + column ids +
+        # row pointers + x + y; with THCM_SPMV_PATTERN=1 the column ids shrink to a 2-byte pattern id per row
+        "spmv_csr": (nnz_loc * 8 + ndim_loc * 22) if os.environ.get("THCM_SPMV_PATTERN") == "1" else (nnz_loc * 12 + ndim_loc * 20),
         "thcm_assemble<JAC_GRAPH>": ncell_loc * 49 + 8 * nnz_loc,
         "thcm_assemble<RHS>": ncell_loc * 145,
         "mgs_step": 32 * ndim_loc, "dot": 16 * ndim_loc,
