@@ -251,7 +251,7 @@ void set_internal_forcing(thcmb_ctx* c, const double* temp, const double* salt);
 bool probe_get_field(const thcmb_ctx* c, int which, double* out);
 void probe_get_suno(const thcmb_ctx* c, double* out);
 void probe_compute_evap(const thcmb_ctx* c, const double* un, double* evap);
-void probe_get_salflux(const thcmb_ctx* c, const double* un, double* salflux, double* correction, double* qsoaflux, double* qsosflux);
+void probe_get_salflux(thcmb_ctx* c, const double* un, double* salflux, double* correction, double* qsoaflux, double* qsosflux);
 void probe_get_temflux(const thcmb_ctx* c, const double* un, double* totflux, double* swflux, double* shflux, double* lhflux,
                        double* siflux, double* simask);
 void probe_get_derivatives(thcmb_ctx* c, const double* un, double* dftdm, double* dfsdq, double* dfsdm, double* dfsdg);

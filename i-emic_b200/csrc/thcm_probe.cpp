@@ -115,7 +115,7 @@ void probe_compute_evap(const thcmb_ctx* c, const double* un, double* evap) {
             evap[pos] = c->atm_eo0 + c->atm_eta * c->atm_qdim * (((deltat / c->atm_qdim) * c->atm_dqso * un[frow(c, i, j, s.L, TT)] - F2c(c->qatm, c, i, j)));
 }
 // m_probe::get_salflux (probe.F90:177-245)
-void probe_get_salflux(const thcmb_ctx* c, const double* un, double* salflux, double* correction, double* qsoaflux, double* qsosflux) {
+void probe_get_salflux(thcmb_ctx* c, const double* un, double* salflux, double* correction, double* qsoaflux, double* qsosflux) {
     need_single_rank(c, "get_salflux");
     const thcmb_settings& s = c->s;
     const double* par = c->par;
@@ -123,6 +123,9 @@ void probe_get_salflux(const thcmb_ctx* c, const double* un, double* salflux, do
     const double gamma = par[COMB] * par[SALT];
     std::fill(salflux, salflux + (size_t)n * m, 0.0);
     const double pQSnd = par[COMB] * par[SALT] * c->QSnd;
+    // side effect of the reference kept: the module variable nus is overwritten WITHOUT the eta*qdim factor (probe.F90:224), which
+    // the next `lin` then uses until set_atmos_parameters / get_derivatives restore it
+    c->atm_nus = par[COMB] * par[SALT] * c->QSnd;
     size_t pos = 0;
     for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++, pos++) {
         const double T = un[frow(c, i, j, l, TT)], S = un[frow(c, i, j, l, SS)];
