@@ -893,6 +893,8 @@ void __m_global_MOD_get_salforcing(double* emip) {                // global.F90:
 }
 void __m_global_MOD_get_internal_temforcing(double*) { need_no_datafile(true, "m_global::get_internal_temforcing"); }
 void __m_global_MOD_get_internal_salforcing(double*) { need_no_datafile(true, "m_global::get_internal_salforcing"); }
+/* declared by THCM.C:170 but defined nowhere in the reference's Fortran (and never called): present so that nothing is unresolved */
+void __m_global_MOD_get_land_temp(double*) { fatal("m_global::get_land_temp is declared by THCM.C but not implemented by the reference"); }
 void __m_global_MOD_get_spert(double* spert) {                    // global.F90:587-608 (rd_spertm = 0)
     for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) spert[q] = (double)g_set.SRES;
 }

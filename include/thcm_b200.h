@@ -105,6 +105,7 @@ void __m_global_MOD_get_salforcing(double* emip);
 void __m_global_MOD_get_internal_temforcing(double* temp);
 void __m_global_MOD_get_internal_salforcing(double* salt);
 void __m_global_MOD_get_spert(double* spert);
+void __m_global_MOD_get_land_temp(double* land);   /* THCM.C:170 declares it; the reference's Fortran never defines it: fails loudly */
 /* global.F90:241-293 (THCM.C:51-56): the caller's global grid arrays; checked against the library's own grid.F90 arrays */
 void set_global_x(int* n, double* a);
 void set_global_y(int* n, double* a);
