@@ -46,6 +46,21 @@ def test_every_symbol_the_reference_binds_is_exported():
     assert not sorted(names - declared), sorted(names - declared)
     L = ctypes.CDLL(iemic_b200.lib_path())
     assert not [n for n in names if not hasattr(L, n)]
+    # ... with the same number of arguments as the reference's declaration
+    def nargs(a):
+        a = a.strip()
+        return 0 if a in ("", "void") else a.count(",") + 1
+    blk = re.sub(r"//[^\n]*", "", blk)
+    oc = re.sub(r"//[^\n]*", "", oc)
+    refsig = {m.group(1) + "_": nargs(m.group(2)) for m in re.finditer(r"_SUBROUTINE_\((\w+)\)\s*\(([^;]*?)\)\s*;", blk, re.S)}
+    refsig.update({f"__{m.group(1)}_MOD_{m.group(2)}": nargs(m.group(3))
+                   for m in re.finditer(r"_MODULE_SUBROUTINE_\(\s*(\w+)\s*,\s*(\w+)\s*\)\s*\(([^;]*?)\)\s*;", blk, re.S)})
+    refsig.update({m.group(1): nargs(m.group(2)) for m in re.finditer(r"void (set_global_\w+)\(([^;]*?)\)\s*;", blk, re.S)})
+    refsig.update({m.group(1) + "_": nargs(m.group(2)) for m in re.finditer(r'extern "C" _SUBROUTINE_\((\w+)\)\s*\(([^;]*?)\)\s*;', oc, re.S)})
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "thcm_b200.h")).read(), flags=re.S)
+    ours = {m.group(1): nargs(m.group(2)) for m in re.finditer(r"\b(\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S)}
+    assert len(refsig) >= 74
+    assert not [(k, v, ours.get(k)) for k, v in refsig.items() if ours.get(k) != v]
 
 
 def test_python_binding_signatures_cover_the_device_api():
