@@ -44,7 +44,8 @@ def lib():
                                 ("emu_derivatives", None, [vp, vp, vp]), ("emu_salt_advection", None, [vp, vp, vp]),
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
                                 ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
-                                ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp])]:
+                                ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp]),
+                                ("emu_grid", None, [vp] * 9)]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -138,6 +139,12 @@ class EmuTHCM:
         beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(n * m, dtype=np.int32); co = np.zeros(n * m)
         self.L_.emu_stochastic_forcing(self.h, _p(beg), _p(jco), _p(co))
         return beg, jco, co
+
+    def grid(self, N, M, L):
+        a = dict(x=np.empty(N), xu=np.empty(N + 1), y=np.empty(M), yv=np.empty(M + 1), z=np.empty(L), zw=np.empty(L + 1),
+                 dfzT=np.empty(L), dfzW=np.empty(L + 1))
+        self.L_.emu_grid(self.h, *[_p(a[k]) for k in ("x", "xu", "y", "yv", "z", "zw", "dfzT", "dfzW")])
+        return a
 
     def spmv_patterns(self):
         """(rowpat uint16[ndim], patrel int32[npat, 24]) of build_spmv_patterns."""

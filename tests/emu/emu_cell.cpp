@@ -145,6 +145,16 @@ void emu_spmv_patterns(void* h, unsigned short* rowpat, int* patrel) {
     memcpy(rowpat, c->rowpat_host.data(), sizeof(uint16_t) * c->rowpat_host.size());
     memcpy(patrel, c->patrel_host.data(), sizeof(int) * c->patrel_host.size());
 }
+// the library's grid arrays (build_grid = grid.F90): x(1..N), xu(0..N), y(1..M), yv(0..M), z(1..L), zw(0..L), dfzT(1..L), dfzW(0..L)
+void emu_grid(void* h, double* x, double* xu, double* y, double* yv, double* z, double* zw, double* dfzT, double* dfzW) {
+    thcmb_ctx* c = &((Emu*)h)->c; const int N = c->s.N, M = c->s.M, L = c->s.L;
+    for (int i = 1; i <= N; i++) x[i - 1] = c->x[i];
+    for (int i = 0; i <= N; i++) xu[i] = c->xu[i];
+    for (int j = 1; j <= M; j++) y[j - 1] = c->y[j];
+    for (int j = 0; j <= M; j++) yv[j] = c->yv[j];
+    for (int k = 1; k <= L; k++) { z[k - 1] = c->z[k]; dfzT[k - 1] = c->dfzT[k]; }
+    for (int k = 0; k <= L; k++) { zw[k] = c->zw[k]; dfzW[k] = c->dfzW[k]; }
+}
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

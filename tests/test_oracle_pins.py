@@ -262,3 +262,25 @@ def test_fd_jacobian_with_mixing(name):
     assert np.linalg.norm(J @ v - fd) < 1e-5 * np.linalg.norm(fd)
     val, missing = o.jacobian_graph(x)
     assert missing == 0      # the mixing entries (T,S at k-1, k, k+1) lie inside the maximal graph
+
+
+@pytest.mark.parametrize("qz", [1, 2])
+def test_grid_matches_the_reference_golden_arrays(qz):
+    """GOLDEN PIN (reference-produced data): test/domain/domain_values.hdf5 holds x, xu, y, yv, z, zw of the 16 x 16 x 8 grid for
+    qz = 1, 2 (src/tests/test_domain.C:40-133, tolerance 1e-15).  Pins grid.F90 / fz / dfdz -- both the oracle's
+    restatement and the library's build_grid -- against arrays the reference itself wrote."""
+    import os
+    from emu.emu import EmuTHCM
+    gold = np.fromfile(os.path.join(cases.ROOT, "tests", "golden", f"domain_values_qz{qz}.f64"), dtype="<f8")
+    gx, gxu, gy, gyv, gz, gzw = np.split(gold, np.cumsum([16, 17, 16, 17, 8]))
+    s = cases.Settings.from_degrees(16, 16, 8, 286, 350, 10, 74, periodic=False, hdim=4000.0, qz=float(qz))
+    landm = cases.all_ocean_mask(16, 16, 8, periodic=False)
+    g = OracleTHCM(s, landm).grid()          # Fortran-indexed arrays: x(0:n), y(0:m+1), z(0:l), xu(0:n), yv(0:m), zw(0:l)
+    tol = 1e-15
+    assert np.abs(g["x"][1:] - gx).max() <= tol and np.abs(g["xu"] - gxu).max() <= tol
+    assert np.abs(g["y"][1:17] - gy).max() <= tol and np.abs(g["yv"] - gyv).max() <= tol
+    assert np.abs(g["z"][1:] - gz).max() <= tol and np.abs(g["zw"] - gzw).max() <= tol
+    e = EmuTHCM(s, landm).grid(16, 16, 8)    # the library's own build_grid
+    for k, ref in (("x", gx), ("xu", gxu), ("y", gy), ("yv", gyv), ("z", gz), ("zw", gzw)):
+        assert np.abs(e[k] - ref).max() <= tol, k
+    assert np.array_equal(e["dfzT"], g["dfzT"][1:]) and np.array_equal(e["dfzW"], g["dfzW"])
