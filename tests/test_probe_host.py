@@ -108,3 +108,45 @@ def test_loadbal_weights_count_ocean_cells():
     s, landm, o, e = setup("natl8", coupled=False)
     w = e.loadbal_weights()
     assert np.array_equal(w, (landm[:, 1:-1, 1:-1] == 0).sum(axis=0) / s.L)   # thcm_utils.F90:335-351 (no extra mixing weights)
+
+
+def test_wind_forcing_round_trip_like_the_reference_test():
+    """src/tests/test_ocean.C:346-380 (TEST(Ocean, WindForcing)): with "Wind Forcing Type" = 3 the inserted wind stress survives the
+    parameter change and the Jacobian computation, and comes back unchanged."""
+    s, landm = cases.natl8(iza=3)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    rng = np.random.default_rng(11)
+    taux, tauy = rng.uniform(-1, 1, (s.M, s.N)), rng.uniform(-1, 1, (s.M, s.N))
+    for obj in (o, e):
+        obj.set_field("taux", taux); obj.set_field("tauy", tauy)
+        obj.setpar(P["COMB"], 0.2)
+    x = cases.smooth_state(s)                       # getState('V')->PutScalar(1.234)
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    tx, ty = e.probe_field("taux"), e.probe_field("tauy")
+    assert np.linalg.norm(tx) >= 1e-2 and np.linalg.norm(tx - taux) <= 1e-7
+    assert np.linalg.norm(ty) >= 1e-2 and np.linalg.norm(ty - tauy) <= 1e-7
+    # ... and it is what drives the u, v rows of the forcing (forcing.F90:40-45)
+    f = e.forcing(masked=False).reshape(s.L, s.M, s.N, 6)
+    sigma = 0.2 * o.getpar(P["WIND"]) * o.getpar(P["AL_T"])
+    assert np.array_equal(f[s.L - 1, : s.M - 1, :, 0], (sigma * taux)[: s.M - 1])
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))     # after matrix(): identity rows zeroed (boundary.F90)
+
+
+def test_salt_and_temperature_forcing_round_trip_like_the_reference_test():
+    """src/tests/test_ocean.C:383-416 (TEST(Ocean, SaltTempForcing)): "Levitus T" = "Levitus S" = 2 (fields set externally): emip comes
+    back zero on the land mask, tatm unchanged, after a parameter change and a Jacobian computation."""
+    s, landm = cases.natl8(ite=2, its=2)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    rng = np.random.default_rng(12)
+    emip, tatm = rng.uniform(-1, 1, (s.M, s.N)), rng.uniform(-1, 1, (s.M, s.N))
+    for obj in (o, e):
+        obj.set_field("emip", emip); obj.set_field("tatm", tatm)
+        obj.setpar(P["COMB"], 0.05)
+    x = cases.smooth_state(s)
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    land = landm[s.L, 1:s.M + 1, 1:s.N + 1]
+    em, ta = e.probe_field("emip"), e.probe_field("tatm")
+    assert np.linalg.norm(ta) >= 1e-2 and np.linalg.norm(ta - tatm) <= 1e-7
+    assert np.linalg.norm(em) >= 1e-2 and np.array_equal(em, emip * (1 - land))
+    assert np.array_equal(o.forcing(), e.forcing(masked=False))
+    assert np.array_equal(o.rhs(x), e.rhs(x))
