@@ -608,6 +608,12 @@ class FortranABI:
         self._set_pointers(C.byref(nrows), C.byref(capi), _np_ptr(self.begA), _np_ptr(self.jcoA), _np_ptr(self.coA),
                                          _np_ptr(self.coB), _np_ptr(self.begF), _np_ptr(self.jcoF), _np_ptr(self.coF))
 
+    def set_landmask(self, landm, periodic, reinit=1):
+        """set_landmask_ (usrc.F90:353-418; THCM.C:1357)."""
+        lm = np.ascontiguousarray(landm, dtype=np.int32)
+        assert lm.shape == (self.l + 2, self.m + 2, self.n + 2)
+        self.L_.set_landmask_(_np_ptr(lm), C.byref(C.c_int(int(periodic))), C.byref(C.c_int(int(reinit))))
+
     def setparcs(self, idx, val):
         self.L_.setparcs_(C.byref(C.c_int(par_index(idx))), C.byref(C.c_double(val)))
 

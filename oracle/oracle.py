@@ -62,7 +62,8 @@ def lib():
                                 ("oracle_set_atmos_parameters", None, [vp, vp]), ("oracle_set_seaice_parameters", None, [vp, vp]),
                                 ("oracle_salt_advection", None, [vp, vp, vp]), ("oracle_salt_diffusion", None, [vp, vp, vp]),
                                 ("oracle_stochastic_forcing", None, [vp, vp, vp, vp]), ("oracle_set_internal_forcing", None, [vp, vp, vp]),
-                                ("oracle_get_coupling_state", None, [vp, vp, vp]), ("oracle_get_field", None, [vp, i, vp])]:
+                                ("oracle_get_coupling_state", None, [vp, vp, vp]), ("oracle_get_field", None, [vp, i, vp]),
+                                ("oracle_set_landmask", None, [vp, vp, i, i])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -180,6 +181,14 @@ class OracleTHCM:
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
         assert f.size == self.n * self.m
         self.L_.oracle_set_field(self.h, self.FIELDS.index(name), _p(f))
+
+    def set_landmask(self, landm, periodic=None, reinit=1):
+        """SUBROUTINE set_landmask (usrc.F90:353-418)."""
+        lm = np.ascontiguousarray(landm, dtype=np.int32)
+        assert lm.shape == (self.l + 2, self.m + 2, self.n + 2)
+        if periodic is not None:
+            self.periodic = int(periodic)
+        self.L_.oracle_set_landmask(self.h, _p(lm), self.periodic, int(reinit))
 
     def get_field(self, name):
         f = np.empty((self.m, self.n))

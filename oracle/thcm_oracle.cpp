@@ -1728,6 +1728,13 @@ void oracle_set_field(void* h, int which, const double* f) {
     for (int j = 1; j <= o->m; j++) for (int i = 1; i <= o->n; i++, pos++)
         o->f2(*dst[which], i, j) = masked ? f[pos] * (1 - o->lm(i, j, o->l)) : f[pos];
 }
+// usrc.F90:353-418: new land mask (land-inversion fix, dummy frame), optionally re-running vmix_init + forcing + lin
+void oracle_set_landmask(void* h, const int* landm, int periodic, int reinit) {
+    Oracle* o = (Oracle*)h;
+    o->periodic = periodic != 0;
+    o->set_landmask_raw(landm, true);
+    if (reinit == 1) { o->vmix_init(); o->forcing(); o->lin(); }
+}
 void oracle_salt_advection(void* h, const double* un, double* check) { ((Oracle*)h)->salt_advection(un, check); }
 void oracle_salt_diffusion(void* h, const double* un, double* check) { ((Oracle*)h)->salt_diffusion(un, check); }
 void oracle_stochastic_forcing(void* h, int* begF, int* jcoF, double* coF) { ((Oracle*)h)->get_stochastic_forcing(begF, jcoF, coF); }

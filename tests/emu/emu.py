@@ -45,7 +45,7 @@ def lib():
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
                                 ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
                                 ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp]),
-                                ("emu_grid", None, [vp] * 9)]:
+                                ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -139,6 +139,11 @@ class EmuTHCM:
         beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(n * m, dtype=np.int32); co = np.zeros(n * m)
         self.L_.emu_stochastic_forcing(self.h, _p(beg), _p(jco), _p(co))
         return beg, jco, co
+
+    def set_landmask(self, landm, periodic, reinit=1):
+        lm = np.ascontiguousarray(landm, dtype=np.int32)
+        self.L_.emu_set_landmask(self.h, _p(lm), int(periodic), int(reinit))
+        self.nnz = self.L_.emu_gnnz(self.h)
 
     def grid(self, N, M, L):
         a = dict(x=np.empty(N), xu=np.empty(N + 1), y=np.empty(M), yv=np.empty(M + 1), z=np.empty(L), zw=np.empty(L + 1),

@@ -155,6 +155,17 @@ void emu_grid(void* h, double* x, double* xu, double* y, double* yv, double* z, 
     for (int k = 1; k <= L; k++) { z[k - 1] = c->z[k]; dfzT[k - 1] = c->dfzT[k]; }
     for (int k = 0; k <= L; k++) { zw[k] = c->zw[k]; dfzW[k] = c->dfzW[k]; }
 }
+// set_landmask_ (usrc.F90:353-418) exactly as thcm_api.cu runs it on the host side: mask rules with the inversion fix, static data, then
+// either the re-initialisation (vmix_init + forcing + lin) or just the mass diagonal
+void emu_set_landmask(void* h, const int* landm, int periodic, int reinit) {
+    Emu* e = (Emu*)h; thcmb_ctx* c = &e->c;
+    c->s.periodic = periodic; c->blk.periodic = periodic; c->blk.wrap_x = (periodic && c->blk.npN == 1) ? 1 : 0;
+    apply_landmask_rules(c, landm, true);
+    c->peers.clear(); c->send_dst_host.clear(); c->send_peer_host.clear();
+    build_static_host(c, e->nbmask, e->surf, e->uvlive, e->send_idx, e->recv_slot);
+    if (reinit == 1) { vmix_init(c); compute_forcing(c); compute_tables(c); compute_cob(c); }
+    else compute_cob(c);
+}
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

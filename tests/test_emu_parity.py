@@ -309,3 +309,36 @@ def test_spmv_column_patterns_reproduce_the_graph(name, nranks):
             got = (6 * (sub // 6)[:, None] + patrel[rowpat[sub]])[pos < lens[sub][:, None]]
             expect = col[idx]
         assert np.array_equal(got, expect)
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p"])
+@pytest.mark.parametrize("vmix", [0, 1])
+def test_set_landmask_rebuilds_everything(name, vmix):
+    """SUBROUTINE set_landmask (usrc.F90:353-418; THCM::setLandMask, the mask fixing of Ocean.C:496-566): a new mask with extra land
+    -- one cell placed so that the land-inversion fix has to act -- and reinit = 1: residual, Jacobian, forcing and mass
+    diagonal afterwards equal a fresh oracle's, bit for bit."""
+    s, landm, o, e = setup(name, vmix=vmix)
+    n, m, l = s.N, s.M, s.L
+    new = landm.copy()
+    ocean = np.argwhere(new[1:l + 1, 1:m + 1, 1:n + 1] == 0)
+    rng = np.random.default_rng(9)
+    for k, j, i in ocean[rng.choice(len(ocean), size=max(3, len(ocean) // 20), replace=False)]:
+        new[k + 1, j + 1, i + 1] = 1                      # LAND somewhere in the column: everything below must follow
+    for obj in (o, e):
+        obj.set_landmask(new, s.periodic, 1)
+    fixed = o.landm()
+    assert (fixed[1:l + 1, 1:m + 1, 1:n + 1] != new[1:l + 1, 1:m + 1, 1:n + 1]).any()   # the inversion fix acted
+    x = cases.random_state(s, fixed, scale=0.2, zero_on_land=False)
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert e.check_tiles(x) == 0
+    bo, jo, co, cob = o.matrix(x)
+    be, je, ce = e.crs(x)
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    assert np.array_equal(cob, e.cob())
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))
+    # and a fresh model on the fixed mask agrees with the re-masked one
+    o2 = OracleTHCM(s, fixed)
+    for k, v in PARS.items():
+        o2.setpar(P[k], v)
+    assert np.array_equal(o2.rhs(x), e.rhs(x))

@@ -138,3 +138,37 @@ def test_spmv_with_pattern_compressed_columns(name, monkeypatch):
         yo = spmv(rowptr, col, val, v)
         assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
     t.close()
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16"])
+def test_set_landmask_through_the_fortran_symbol(name):
+    """set_landmask_ (usrc.F90:353-418) on the device path: the static per-cell data, tile descriptors and forcing are rebuilt; the
+    host part is verified on the CPU (tests/test_emu_parity.py::test_set_landmask_rebuilds_everything)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import OracleTHCM
+    s, landm = {"natl8": cases.natl8, "gateway16": cases.gateway16}[name]()
+    o = OracleTHCM(s, landm)
+    f = iemic_b200.FortranABI()
+    f.global_initialize(s)
+    f.init(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        f.setparcs(k, v)
+    n, m, l = s.N, s.M, s.L
+    new = landm.copy()
+    ocean = np.argwhere(new[1:l + 1, 1:m + 1, 1:n + 1] == 0)
+    rng = np.random.default_rng(9)
+    for k, j, i in ocean[rng.choice(len(ocean), size=max(3, len(ocean) // 20), replace=False)]:
+        new[k + 1, j + 1, i + 1] = 1
+    o.set_landmask(new, s.periodic, 1)
+    f.set_landmask(new, s.periodic, 1)
+    x = cases.random_state(s, o.landm(), scale=0.2, zero_on_land=False)
+    assert np.array_equal(f.rhs(x), o.rhs(x))
+    beg, jco, co, cob = f.matrix(x)
+    bo, jo, cf, cobo = o.matrix(x)
+    assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf) and np.array_equal(cob, cobo)
+    assert np.array_equal(f.get_forcing(), o.forcing())
+    f.finalize()
