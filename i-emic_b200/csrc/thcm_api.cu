@@ -22,7 +22,12 @@ extern "C" {
 __attribute__((weak)) void thcm_throw_error_(char* msg) { fprintf(stderr, "%s\n", msg); abort(); }
 __attribute__((weak)) void timer_start_(const char*) {}
 __attribute__((weak)) void timer_stop_(const char*) {}
-__attribute__((weak)) void thcm_forcing_integral_(double*, double*, int*, double* out) { *out = 0.0; }
+// standalone default of the callback of forcing.F90:452-464: the one-rank integral over the sub-domain of the global instance
+// (the reference's definition, THCM.C:2653-2686, sums the ranks' real cells with MPI instead)
+void thcm_forcing_integral_default(double* field, double* y, int* landm, double* out);
+__attribute__((weak)) void thcm_forcing_integral_(double* field, double* y, int* landm, double* out) {
+    thcm_forcing_integral_default(field, y, landm, out);
+}
 }
 
 namespace {
@@ -803,6 +808,17 @@ static thcmb_ctx* g_ctx = nullptr;
 static int *g_dbeg = nullptr, *g_djco = nullptr; static double* g_dco = nullptr;
 
 static thcmb_ctx* G() { if (!g_ctx) fatal("THCM not initialised: call init_ first"); return g_ctx; }
+static int g_dims[3] = {0, 0, 0};   // n, m, l of the instance init_ is creating / has created
+void thcm_forcing_integral_default(double* field, double* y, int* landm, double* out) {
+    const int n = g_dims[0], m = g_dims[1], l = g_dims[2];
+    double lf = 0.0, ls = 0.0;
+    for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+        const int land = landm[(size_t)i + (size_t)(n + 2) * (j + (size_t)(m + 2) * l)];
+        lf = field[(size_t)(i - 1) + (size_t)n * (j - 1)] * std::cos(y[j - 1]) * (1 - land) + lf;
+        ls = std::cos(y[j - 1]) * (1 - land) + ls;
+    }
+    *out = lf / ls;
+}
 
 // reads a land mask in the format of topo.F90:41-64 (per level k=0..l+1: one header line, rows j=m+1..0 of n+2 digits)
 static bool read_mask_file(const char* path, int n, int m, int l, std::vector<int>& out) {
@@ -920,14 +936,25 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     thcmb_settings s = g_set;
     // the library sees the caller's (sub)domain as its whole world, like the Fortran it replaces.  NOTE: temfun/salfun
     // use the GLOBAL ymin/ymax of m_global (forcing.F90:424-449); on a single rank they coincide with the local ones.
+    // The caller's sub-domain (under MPI: one block of Decomp2D incl. its ghost layers, THCM.C:566-611) with its own bounds; the
+    // global latitude bounds of m_global stay available to temfun / salfun (forcing.F90:418-449)
     s.N = *n; s.M = *m; s.L = *l; s.xmin = *xmin; s.xmax = *xmax;
-    if (!g_have_global) { s.ymin = *ymin; s.ymax = *ymax; }
-    if (g_have_global && (s.ymin != *ymin || s.ymax != *ymax))
-        fatal("init_: sub-domain bounds differ from the global ones; multi-rank runs must use the thcmb_* API (DESIGN.md)");
+    if (g_have_global && (g_set.ymin != *ymin || g_set.ymax != *ymax)) { s.ymin_glob = g_set.ymin; s.ymax_glob = g_set.ymax; }
+    s.ymin = *ymin; s.ymax = *ymax;
+    // one process per GPU under MPI: the local rank picks the device (THCM_DEVICE overrides)
+    {
+        int dev = 0, ndev = 0;
+        for (const char* v : {"THCM_DEVICE", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID"})
+            if (const char* e = getenv(v)) { dev = atoi(e); break; }
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) dev %= ndev;
+        s.device = dev;
+    }
+    g_dims[0] = s.N; g_dims[1] = s.M; g_dims[2] = s.L;
     s.alphaT = *alphaT; s.alphaS = *alphaS; s.ih = *ih; s.vmix = *vmix; s.tap = *tap; s.rho_mixing = *rho_mixing;
     s.coriolis_on = *coriolis_on; s.periodic = *periodic; s.rank = 0; s.nranks = 1;
     if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }  // THCM is a singleton that replaces the previous instance (THCM.H:76-84)
     g_ctx = thcmb_create(&s, landm);
+    g_ctx->use_integral_callback = true;
     size_t nm = (size_t)s.N * s.M;
     memcpy(g_ctx->taux.data(), taux, sizeof(double) * nm); memcpy(g_ctx->tauy.data(), tauy, sizeof(double) * nm);
     memcpy(g_ctx->tatm.data(), tatm, sizeof(double) * nm); memcpy(g_ctx->emip.data(), emip, sizeof(double) * nm);

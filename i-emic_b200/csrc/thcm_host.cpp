@@ -12,6 +12,7 @@
 #include "thcm_cell.cuh"
 
 extern "C" void thcm_throw_error_(char* msg);
+extern "C" void thcm_forcing_integral_(double* field, double* y, int* landm, double* out);
 
 namespace thcm {
 
@@ -171,21 +172,31 @@ static double wfun(double yy, int v1) {
                0.5 * (1 - std::tanh(10 * (PI / 2 - std::fabs(yy))));
     return 0.0;
 }
+// temfun / salfun use the GLOBAL latitude bounds of m_global, also on a sub-domain (forcing.F90:418-449)
+static inline double glob_ymin(const thcmb_ctx* c) { return (c->s.ymin_glob == 0.0 && c->s.ymax_glob == 0.0) ? c->s.ymin : c->s.ymin_glob; }
+static inline double glob_ymax(const thcmb_ctx* c) { return (c->s.ymin_glob == 0.0 && c->s.ymax_glob == 0.0) ? c->s.ymax : c->s.ymax_glob; }
 static double temfun(const thcmb_ctx* c, double yy) {
     const thcmb_settings& s = c->s;
-    if (s.forcing_type == 2) return std::cos(PI * (yy - s.ymin) / (s.ymax - s.ymin));
-    return std::cos(PI * yy / s.ymax) + c->par[CMPR] * std::sin(PI * yy / s.ymax);
+    const double ymin = glob_ymin(c), ymax = glob_ymax(c);
+    if (s.forcing_type == 2) return std::cos(PI * (yy - ymin) / (ymax - ymin));
+    return std::cos(PI * yy / ymax) + c->par[CMPR] * std::sin(PI * yy / ymax);
 }
 static double salfun(const thcmb_ctx* c, double yy) {
     const thcmb_settings& s = c->s;
-    if (s.forcing_type == 2) return std::cos(PI * (yy - s.ymin) / (s.ymax - s.ymin));
-    if (s.forcing_type == 1) return (std::cos(PI * yy / s.ymax) + c->par[FPER] * yy / s.ymax) / std::cos(yy);
-    return std::cos(PI * yy / s.ymax) + c->par[FPER] * yy / s.ymax;
+    const double ymin = glob_ymin(c), ymax = glob_ymax(c);
+    if (s.forcing_type == 2) return std::cos(PI * (yy - ymin) / (ymax - ymin));
+    if (s.forcing_type == 1) return (std::cos(PI * yy / ymax) + c->par[FPER] * yy / ymax) / std::cos(yy);
+    return std::cos(PI * yy / ymax) + c->par[FPER] * yy / ymax;
 }
 // forcing.F90:452-464 -> THCM.C:2653-2686.  Every rank holds the global surface fields and mask, so the
 // global integral is evaluated redundantly in the reference's 1-rank summation order (no collective).
 static double qint(thcmb_ctx* c, const std::vector<double>& f) {
     int n = c->s.N, m = c->s.M, l = c->s.L;
+    if (c->use_integral_callback) {   // created through init_: like the Fortran, let the C++ side form the (MPI-summed) integral
+        double cor = 0.0;
+        thcm_forcing_integral_(const_cast<double*>(f.data()), c->y.data() + 1, c->landm.data(), &cor);
+        return cor;
+    }
     double lf = 0.0, ls = 0.0;
     for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
         lf = f[(size_t)(i - 1) + (size_t)n * (j - 1)] * std::cos(c->y[j]) * (1 - LM(c, i, j, l)) + lf;

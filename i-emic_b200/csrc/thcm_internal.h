@@ -137,6 +137,7 @@ struct thcmb_ctx {
     double* d_msi = nullptr;
     std::vector<double> frc_local;   // owned rows, masked by the rows `boundaries` turns into identity rows
     std::vector<double> frc_raw;     // owned rows, as `forcing` leaves it
+    bool use_integral_callback = false;   // qint goes through thcm_forcing_integral_ (THCM.C:2653): contexts created by init_
     bool frc_masked = false;         // get_forcing_ semantics (boundary.F90 zeroes Frc lazily inside rhs/matrix)
     std::vector<double> cob_local;
     std::vector<double> jt_host, kt_host;

@@ -35,7 +35,8 @@ class Settings(C.Structure):
                 ("TRES", C.c_int), ("SRES", C.c_int), ("iza", C.c_int), ("ite", C.c_int), ("its", C.c_int),
                 ("coupled_T", C.c_int), ("coupled_S", C.c_int), ("forcing_type", C.c_int),
                 ("alphaT", C.c_double), ("alphaS", C.c_double),
-                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
+                ("ymin_glob", C.c_double), ("ymax_glob", C.c_double)]
 
     PI = 3.14159265358979323846  # THCMdefs.H:19
 

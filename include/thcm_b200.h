@@ -181,6 +181,9 @@ typedef struct thcmb_settings {
     int rank, nranks;
     /* CUDA device ordinal to use */
     int device;
+    /* latitude bounds of the GLOBAL domain when this context is one sub-domain of an MPI-decomposed run that calls the
+     * Fortran symbols per rank (temfun / salfun use m_global's ymin, ymax, forcing.F90:418-449); both 0 = same as ymin, ymax */
+    double ymin_glob, ymax_glob;
 } thcmb_settings;
 
 void thcmb_default_settings(thcmb_settings* s);

@@ -97,7 +97,8 @@ class OracleTHCM:
     def __init__(self, s, landm):
         """s: any object with the thcmb_settings fields (iemic_b200.Settings); landm int32[L+2,M+2,N+2]."""
         self.L_ = lib()
-        os_ = OracleSettings(hdim=s.hdim, qz=s.qz, alphaT=s.alphaT, alphaS=s.alphaS, ymin_glob=s.ymin, ymax_glob=s.ymax,
+        yg = (s.ymin_glob, s.ymax_glob) if (getattr(s, "ymin_glob", 0.0) or getattr(s, "ymax_glob", 0.0)) else (s.ymin, s.ymax)
+        os_ = OracleSettings(hdim=s.hdim, qz=s.qz, alphaT=s.alphaT, alphaS=s.alphaS, ymin_glob=yg[0], ymax_glob=yg[1],
                              periodic=s.periodic, ih=s.ih, vmix=s.vmix, tap=s.tap, rho_mixing=s.rho_mixing,
                              coriolis_on=s.coriolis_on, TRES=s.TRES, SRES=s.SRES, iza=s.iza, ite=s.ite, its=s.its,
                              coupled_T=s.coupled_T, coupled_S=s.coupled_S, forcing_type=s.forcing_type)

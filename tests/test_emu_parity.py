@@ -342,3 +342,28 @@ def test_set_landmask_rebuilds_everything(name, vmix):
     for k, v in PARS.items():
         o2.setpar(P[k], v)
     assert np.array_equal(o2.rhs(x), e.rhs(x))
+
+
+@pytest.mark.parametrize("forcing_type,TRES,SRES", [(0, 1, 1), (2, 1, 1), (1, 0, 0), (0, 0, 1)])
+def test_sub_domain_with_global_latitude_bounds(forcing_type, TRES, SRES):
+    """What one MPI rank of the reference hands the Fortran symbols (THCM.C:566-611): a sub-domain with its OWN bounds, while the
+    idealised forcing profiles keep using the GLOBAL latitude bounds of m_global (forcing.F90:418-449)."""
+    rad = np.pi / 180.0
+    s, landm = cases.box(6, 5, 4, False, seed=8, land_frac=0.25, forcing_type=forcing_type, TRES=TRES, SRES=SRES)
+    s.xmin, s.xmax, s.ymin, s.ymax = 300 * rad, 340 * rad, 22 * rad, 54 * rad      # the block
+    s.ymin_glob, s.ymax_glob = 10 * rad, 74 * rad                                  # the domain it belongs to
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    for k, v in dict(PARS, CMPR=0.3, FPER=0.2).items():
+        o.setpar(P[k], v)
+        e.setpar(P[k], v)
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(o.forcing(), e.forcing(masked=False))
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    # the profiles really are the global ones: a model that believes the block is the whole domain gets another forcing
+    s2, _ = cases.box(6, 5, 4, False, seed=8, land_frac=0.25, forcing_type=forcing_type, TRES=TRES, SRES=SRES)
+    s2.xmin, s2.xmax, s2.ymin, s2.ymax = s.xmin, s.xmax, s.ymin, s.ymax
+    e2 = EmuTHCM(s2, landm)
+    for k, v in dict(PARS, CMPR=0.3, FPER=0.2).items():
+        e2.setpar(P[k], v)
+    assert not np.array_equal(e2.forcing(masked=False), e.forcing(masked=False))

@@ -172,3 +172,35 @@ def test_set_landmask_through_the_fortran_symbol(name):
     assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf) and np.array_equal(cob, cobo)
     assert np.array_equal(f.get_forcing(), o.forcing())
     f.finalize()
+
+
+def test_fortran_symbols_on_a_sub_domain_of_an_mpi_run():
+    """init_ with the bounds of ONE Decomp2D block while m_global holds the global domain (THCM.C:328-338, 566-611): the idealised
+    forcing uses the global latitude bounds, the flux correction goes through the thcm_forcing_integral_ callback (here the library's
+    one-rank default).  Host logic verified on the CPU: test_emu_parity.py::test_sub_domain_with_global_latitude_bounds."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import copy
+    import iemic_b200
+    from oracle.oracle import OracleTHCM
+    rad = np.pi / 180.0
+    s, landm = cases.box(6, 5, 4, False, seed=8, land_frac=0.25, TRES=0, SRES=0)
+    s.xmin, s.xmax, s.ymin, s.ymax = 300 * rad, 340 * rad, 22 * rad, 54 * rad
+    sg = copy.copy(s)
+    sg.ymin, sg.ymax = 10 * rad, 74 * rad
+    s.ymin_glob, s.ymax_glob = sg.ymin, sg.ymax
+    o = OracleTHCM(s, landm)
+    f = iemic_b200.FortranABI()
+    f.global_initialize(sg)          # m_global: the whole domain
+    f.init(s, landm)                 # usrc init: this rank's block
+    for k, v in dict(PARS, CMPR=0.3, FPER=0.2).items():
+        o.setpar(P[k], v)
+        f.setparcs(k, v)
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(f.rhs(x), o.rhs(x))
+    beg, jco, co, cob = f.matrix(x)
+    bo, jo, cf, cobo = o.matrix(x)
+    assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf)
+    assert np.array_equal(f.get_forcing(), o.forcing())
+    f.finalize()
