@@ -63,7 +63,7 @@ def lib():
                                 ("oracle_salt_advection", None, [vp, vp, vp]), ("oracle_salt_diffusion", None, [vp, vp, vp]),
                                 ("oracle_stochastic_forcing", None, [vp, vp, vp, vp]), ("oracle_set_internal_forcing", None, [vp, vp, vp]),
                                 ("oracle_get_coupling_state", None, [vp, vp, vp]), ("oracle_get_field", None, [vp, i, vp]),
-                                ("oracle_set_landmask", None, [vp, vp, i, i])]:
+                                ("oracle_set_landmask", None, [vp, vp, i, i]), ("oracle_setsres", None, [vp, i])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -190,6 +190,10 @@ class OracleTHCM:
         if periodic is not None:
             self.periodic = int(periodic)
         self.L_.oracle_set_landmask(self.h, _p(lm), self.periodic, int(reinit))
+
+    def setsres(self, sres):
+        """SUBROUTINE setsres (usrc.F90:434-446): THCM.C:1059-1070 brackets matrix_ with it for the mask test."""
+        self.L_.oracle_setsres(self.h, int(sres))
 
     def get_field(self, name):
         f = np.empty((self.m, self.n))

@@ -1735,6 +1735,8 @@ void oracle_set_landmask(void* h, const int* landm, int periodic, int reinit) {
     o->set_landmask_raw(landm, true);
     if (reinit == 1) { o->vmix_init(); o->forcing(); o->lin(); }
 }
+// usrc.F90:434-446
+void oracle_setsres(void* h, int sres) { Oracle* o = (Oracle*)h; o->SRES = sres; o->forcing(); o->lin(); }
 void oracle_salt_advection(void* h, const double* un, double* check) { ((Oracle*)h)->salt_advection(un, check); }
 void oracle_salt_diffusion(void* h, const double* un, double* check) { ((Oracle*)h)->salt_diffusion(un, check); }
 void oracle_stochastic_forcing(void* h, int* begF, int* jcoF, double* coF) { ((Oracle*)h)->get_stochastic_forcing(begF, jcoF, coF); }

@@ -45,7 +45,7 @@ def lib():
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
                                 ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
                                 ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp]),
-                                ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i])]:
+                                ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i]), ("emu_setsres", None, [vp, i])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -144,6 +144,9 @@ class EmuTHCM:
         lm = np.ascontiguousarray(landm, dtype=np.int32)
         self.L_.emu_set_landmask(self.h, _p(lm), int(periodic), int(reinit))
         self.nnz = self.L_.emu_gnnz(self.h)
+
+    def setsres(self, sres):
+        self.L_.emu_setsres(self.h, int(sres))
 
     def grid(self, N, M, L):
         a = dict(x=np.empty(N), xu=np.empty(N + 1), y=np.empty(M), yv=np.empty(M + 1), z=np.empty(L), zw=np.empty(L + 1),

@@ -167,6 +167,7 @@ void emu_set_landmask(void* h, const int* landm, int periodic, int reinit) {
     if (reinit == 1) { vmix_init(c); compute_forcing(c); compute_tables(c); compute_cob(c); }
     else compute_cob(c);
 }
+void emu_setsres(void* h, int sres) { thcmb_ctx* c = &((Emu*)h)->c; c->s.SRES = sres; compute_forcing(c); compute_tables(c); compute_cob(c); }   // setsres_
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

@@ -367,3 +367,21 @@ def test_sub_domain_with_global_latitude_bounds(forcing_type, TRES, SRES):
     for k, v in dict(PARS, CMPR=0.3, FPER=0.2).items():
         e2.setpar(P[k], v)
     assert not np.array_equal(e2.forcing(masked=False), e.forcing(masked=False))
+
+
+def test_setsres_toggles_the_restoring_terms_like_thcm_evaluate():
+    """SUBROUTINE setsres (usrc.F90:434-446) re-runs forcing + lin with the other restoring flag and back again, the way
+    THCM::evaluate brackets matrix_ for its mask test (THCM.C:1059-1070)."""
+    s, landm, o, e = setup("natl8", SRES=0)
+    x = cases.random_state(s, landm, scale=0.1)
+    B0 = o.rhs(x)
+    assert np.array_equal(B0, e.rhs(x))
+    for obj in (o, e):
+        obj.setsres(1)
+    vo, _ = o.jacobian_graph(x)
+    assert np.array_equal(vo, e.jacobian(x))
+    assert np.array_equal(o.forcing(), e.forcing(masked=True))
+    for obj in (o, e):
+        obj.setsres(0)
+    assert np.array_equal(o.rhs(x), e.rhs(x)) and np.array_equal(o.rhs(x), B0)
+    assert not np.array_equal(o.jacobian_graph(x)[0], vo)        # the restoring term sits on the S diagonal of the surface cells
