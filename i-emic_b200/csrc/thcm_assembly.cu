@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdio>
+#include <type_traits>
 #include "thcm_cell.cuh"
 
 namespace thcm {
@@ -627,37 +628,70 @@ template <int GROUP> struct alignas(16) TmaSmem {
     int cstart[TI + 2];
     unsigned long long bar;
 };
+// THCM_ASM_PIPE=5 (candidate, not yet measured): the output staging `v` ALIASES the input stage -- the staged records are dead once
+// every warp has evaluated its rows -- so a block needs 17 / 11 KB instead of 28 / 20 KB of shared memory and, with the register
+// budget bounded for it, 10 / 13 instead of 8 / 11 blocks fit an SM (the kernels are latency bound: DESIGN.md section 3.1)
+template <int GROUP> struct alignas(16) TmaSmemAlias {
+    union alignas(16) U {
+        Stage<RowGroup<GROUP>::LINES> st;
+        double v[TI * RowGroup<GROUP>::VS];
+        __device__ U() {}
+    } u;
+    int cstart[TI + 2];
+    unsigned long long bar;
+};
+template <int G> __device__ __forceinline__ Stage<RowGroup<G>::LINES>& smem_stage(TmaSmem<G>& s) { return s.st; }
+template <int G> __device__ __forceinline__ double* smem_out(TmaSmem<G>& s) { return s.v; }
+template <int G> __device__ __forceinline__ Stage<RowGroup<G>::LINES>& smem_stage(TmaSmemAlias<G>& s) { return s.u.st; }
+template <int G> __device__ __forceinline__ double* smem_out(TmaSmemAlias<G>& s) { return s.u.v; }
 
 __device__ __forceinline__ constexpr int diag_pos(int R) { return ROW_OFF[R - 1] + interior_pos(R, slot_of(R, 5, R)); }
 
-template <int GROUP, int RA, int RB, bool CPL>
-__device__ __forceinline__ void tma_rows(const AsmArgs& a, TmaSmem<GROUP>& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
+template <int GROUP, int RA, int RB, bool CPL, bool ALIAS, class SH>
+__device__ __forceinline__ void tma_rows(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
     using G = RowGroup<GROUP>;
     constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
-    const uint32_t nb = sh.st.desc.nbmask[lane];
-    const double sm = (double)((sh.st.desc.surfbits >> lane) & 1u);
+    auto& st = smem_stage<GROUP>(sh);
+    double* v = smem_out<GROUP>(sh);
+    const uint32_t nb = st.desc.nbmask[lane];
+    const double sm = (double)((st.desc.surfbits >> lane) & 1u);
     double EA[NA], EB[NB];
-    pipe_eval<RA, CPL>(a, sh.st, g, lane, nb, sm, EA);
-    pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-    pipe_emit<RA, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EA);
-    if constexpr (RB != RA) {
-        pipe_eval<RB, CPL>(a, sh.st, g, lane, nb, sm, EB);
-        pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-        pipe_emit<RB, G::ROW0, G::VS>(a, sh.v, g, lane, interior, EB);
+    if constexpr (!ALIAS) {
+        pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
+        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+        pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
+        if constexpr (RB != RA) {
+            pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
+            pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+            pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
+        }
+    } else {
+        // every row of the block is evaluated (the last read of the stage) before the first entry is written over it
+        pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
+        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+        if constexpr (RB != RA) {
+            pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
+            pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+        }
+        __syncthreads();
+        pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
+        if constexpr (RB != RA) pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
     }
 }
 
-template <int GROUP, int BLOCKS_PER_SM, bool CPL>
+template <int GROUP, int BLOCKS_PER_SM, bool CPL, bool ALIAS = false>
 __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
     using G = RowGroup<GROUP>;
     constexpr int NT = 32 * G::NWARP;
     constexpr int SEG0 = ROW_OFF[G::ROW0 - 1];   // first entry of the group inside an interior cell record
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TmaSmem<GROUP>& sh = *reinterpret_cast<TmaSmem<GROUP>*>(smem_raw);
+    using SH = typename std::conditional<ALIAS, TmaSmemAlias<GROUP>, TmaSmem<GROUP>>::type;
+    SH& sh = *reinterpret_cast<SH*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     using ST = Stage<G::LINES>;
-    ST& st = sh.st;
+    ST& st = smem_stage<GROUP>(sh);
+    double* const vout = smem_out<GROUP>(sh);
     const TileGeom g = tile_geom_of(a.b, tile);
     const int w = g.ncell + 2;
     // the loads go out before anything is known about the tile (one latency exposure): per staged grid line one
@@ -693,14 +727,15 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
     if (all_land && interior && fast) {
         // identity rows only: zeros with a one on the diagonal of every row of the group
-        double2* v2 = reinterpret_cast<double2*>(sh.v);
+        if constexpr (ALIAS) __syncthreads();   // every thread has read the descriptor flags before the stage is overwritten
+        double2* v2 = reinterpret_cast<double2*>(vout);
         for (int i = threadIdx.x; i < g.ncell * (G::VS / 2); i += NT) v2[i] = make_double2(0.0, 0.0);
         __syncthreads();
         constexpr int NR = G::ROW1 - G::ROW0 + 1;
         for (int i = threadIdx.x; i < g.ncell * NR; i += NT) {
             const int cell = i / NR, r = G::ROW0 + (i - cell * NR);
             const int dp = r == 1 ? diag_pos(1) : r == 2 ? diag_pos(2) : r == 3 ? diag_pos(3) : r == 4 ? diag_pos(4) : r == 5 ? diag_pos(5) : diag_pos(6);
-            sh.v[cell * G::VS + dp - SEG0] = 1.0;
+            vout[cell * G::VS + dp - SEG0] = 1.0;
         }
     } else {
         // usol in place: no-slip zeroing of u,v, lid / bottom / ghost-column rule of w (descriptor bits)
@@ -717,13 +752,13 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
         __syncthreads();
         if constexpr (GROUP == 0) {
             switch (warp) {
-            case 0: tma_rows<0, 1, 1, CPL>(a, sh, g, lane, open_ocean, interior); break;
-            case 1: tma_rows<0, 2, 2, CPL>(a, sh, g, lane, open_ocean, interior); break;
-            default: tma_rows<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, interior); break;
+            case 0: tma_rows<0, 1, 1, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
+            case 1: tma_rows<0, 2, 2, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
+            default: tma_rows<0, 3, 4, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
             }
         } else {
-            if (warp == 0) tma_rows<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, interior);
-            else tma_rows<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, interior);
+            if (warp == 0) tma_rows<1, 5, 5, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior);
+            else tma_rows<1, 6, 6, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior);
         }
     }
     if (fast) {
@@ -731,7 +766,7 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
         if (threadIdx.x < g.ncell) {
-            bulk_store(a.val + g0 + (size_t)threadIdx.x * NSLOT_TOTAL + SEG0, sh.v + threadIdx.x * G::VS, G::LEN * (int)sizeof(double));
+            bulk_store(a.val + g0 + (size_t)threadIdx.x * NSLOT_TOTAL + SEG0, vout + threadIdx.x * G::VS, G::LEN * (int)sizeof(double));
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         }
@@ -745,18 +780,26 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
         for (int q = threadIdx.x; q < g.ncell * G::LEN; q += NT) {
             const int cl = q / G::LEN, e = q - cl * G::LEN;
             const int lo = sh.cstart[cl], hi = __ldg(a.rowptr + NUN * (g.cell0 + cl) + G::ROW1);
-            if (e < hi - lo) a.val[lo + e] = sh.v[cl * G::VS + e];
+            if (e < hi - lo) a.val[lo + e] = vout[cl * G::VS + e];
         }
     }
 }
 
-template <int GROUP, int BLOCKS_PER_SM, bool CPL> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
+template <int GROUP, int BLOCKS_PER_SM, bool CPL, bool ALIAS = false> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
+    using SH = typename std::conditional<ALIAS, TmaSmemAlias<GROUP>, TmaSmem<GROUP>>::type;
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem<GROUP>)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SH)));
         attr_set = true;
     }
-    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(TmaSmem<GROUP>), c->stream>>>(a);
+    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL, ALIAS><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(SH), c->stream>>>(a);
+}
+// candidate (THCM_ASM_PIPE=5): aliased staging, register budget for 10 / 13 blocks per SM; uncoupled kernels only
+static void launch_jac_tma_alias(thcmb_ctx* c, const AsmArgs& a) {
+    launch_jac_tma_group<0, 10, false, true>(c, a);
+    if (a.t.coupled_T || a.t.coupled_S) launch_jac_tma_group<1, 11, true, false>(c, a);
+    else launch_jac_tma_group<1, 13, false, true>(c, a);
+    c->launches++;
 }
 // coupled mode only touches the T | S rows (group B); group A is the same kernel either way
 template <int BA, int BB> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
@@ -837,6 +880,7 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     case MODE_JAC_GRAPH:
         if (c->asm_pipe == 1) launch_jac_tma<8, 11>(c, a);
         else if (c->asm_pipe == 4) launch_jac_tma<6, 8>(c, a);
+        else if (c->asm_pipe == 5) launch_jac_tma_alias(c, a);
         else if (c->asm_pipe >= 2) launch_jac_pipe(c, a);
         else launch_mode<MODE_JAC_GRAPH>(c, a, nblk);
         break;

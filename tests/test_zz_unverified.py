@@ -5,6 +5,7 @@ run on a B200 (gated by THCM_RUN_UNVERIFIED=1, see below).
 API: salinity integral condition (SRES = 0 -- the configuration of the reference's own test/ocean/ocean_params.xml) and the
 pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
 m_thcm_utils::intcond_scaling coefficients.
+(3) The Jacobian kernels with the output staging aliased onto the input stage (THCM_ASM_PIPE=5; more blocks per SM).
 (2) The SpMV with pattern-compressed column indices (THCM_SPMV_PATTERN=1; the host dictionary is verified in
 tests/test_emu_parity.py::test_spmv_column_patterns_reproduce_the_graph)."""
 import numpy as np
@@ -204,3 +205,31 @@ def test_fortran_symbols_on_a_sub_domain_of_an_mpi_run():
     assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf)
     assert np.array_equal(f.get_forcing(), o.forcing())
     f.finalize()
+
+
+@pytest.mark.parametrize("name", ["global4deg", "box_p33", "box_np", "gateway16", "box_tiny"])
+def test_jacobian_kernels_with_aliased_staging(name, monkeypatch):
+    """THCM_ASM_PIPE=5: same arithmetic as the default TMA kernels, shared memory reused between the staged records and the output
+    staging (one more block barrier), register budget for 10 / 13 blocks per SM: values must stay bit-exact."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import OracleTHCM
+    mk = {"global4deg": cases.global4deg, "gateway16": cases.gateway16,
+          "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw),
+          "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
+          "box_tiny": lambda **kw: cases.box(3, 2, 2, True, seed=5, land_frac=0.2, **kw)}[name]
+    monkeypatch.setenv("THCM_ASM_PIPE", "5")
+    s, landm = mk()
+    o = OracleTHCM(s, landm)
+    t = iemic_b200.THCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        t.setParameter(k, v)
+    for seed in (1, 2):
+        x = cases.random_state(s, landm, scale=0.3, zero_on_land=False, seed=seed)
+        t.evaluate(torch.from_numpy(x).cuda(), None, True)
+        vo, missing = o.jacobian_graph(x)
+        assert missing == 0 and np.array_equal(t.jacobian_values_host(), vo)
+    t.close()
