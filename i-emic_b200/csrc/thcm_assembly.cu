@@ -656,27 +656,38 @@ __device__ __forceinline__ void tma_rows(const AsmArgs& a, SH& sh, const TileGeo
     const uint32_t nb = st.desc.nbmask[lane];
     const double sm = (double)((st.desc.surfbits >> lane) & 1u);
     double EA[NA], EB[NB];
-    if constexpr (!ALIAS) {
-        pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
-        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-        pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
-        if constexpr (RB != RA) {
-            pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
-            pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-            pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
-        }
-    } else {
-        // every row of the block is evaluated (the last read of the stage) before the first entry is written over it
-        pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
-        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-        if constexpr (RB != RA) {
-            pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
-            pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-        }
-        __syncthreads();
-        pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
-        if constexpr (RB != RA) pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
+    static_assert(!ALIAS, "the aliased kernels use tma_rows_eval / tma_rows_emit");
+    pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
+    pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+    pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
+    if constexpr (RB != RA) {
+        pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
+        pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+        pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
     }
+}
+// aliased staging (THCM_ASM_PIPE=5): evaluation and emission are separate calls so that the block barrier between the last read of
+// the stage and the first write over it sits in the kernel's common path (not inside the per-warp switch).  EA / EB are sized for the
+// longest rows (u: 24, p: 11)
+constexpr int ALIAS_NA = 24, ALIAS_NB = 11;
+template <int GROUP, int RA, int RB, bool CPL, class SH>
+__device__ __forceinline__ void tma_rows_eval(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool open_ocean, double* EA, double* EB) {
+    auto& st = smem_stage<GROUP>(sh);
+    const uint32_t nb = st.desc.nbmask[lane];
+    const double sm = (double)((st.desc.surfbits >> lane) & 1u);
+    pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
+    pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
+    if constexpr (RB != RA) {
+        pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
+        pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
+    }
+}
+template <int GROUP, int RA, int RB, class SH>
+__device__ __forceinline__ void tma_rows_emit(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool interior, const double* EA, const double* EB) {
+    using G = RowGroup<GROUP>;
+    double* v = smem_out<GROUP>(sh);
+    pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
+    if constexpr (RB != RA) pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
 }
 
 template <int GROUP, int BLOCKS_PER_SM, bool CPL, bool ALIAS = false>
@@ -750,15 +761,40 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
             }
         }
         __syncthreads();
-        if constexpr (GROUP == 0) {
-            switch (warp) {
-            case 0: tma_rows<0, 1, 1, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
-            case 1: tma_rows<0, 2, 2, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
-            default: tma_rows<0, 3, 4, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior); break;
+        if constexpr (!ALIAS) {
+            if constexpr (GROUP == 0) {
+                switch (warp) {
+                case 0: tma_rows<0, 1, 1, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
+                case 1: tma_rows<0, 2, 2, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
+                default: tma_rows<0, 3, 4, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
+                }
+            } else {
+                if (warp == 0) tma_rows<1, 5, 5, CPL, false>(a, sh, g, lane, open_ocean, interior);
+                else tma_rows<1, 6, 6, CPL, false>(a, sh, g, lane, open_ocean, interior);
             }
         } else {
-            if (warp == 0) tma_rows<1, 5, 5, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior);
-            else tma_rows<1, 6, 6, CPL, ALIAS>(a, sh, g, lane, open_ocean, interior);
+            double EA[ALIAS_NA], EB[ALIAS_NB];
+            if constexpr (GROUP == 0) {
+                switch (warp) {
+                case 0: tma_rows_eval<0, 1, 1, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
+                case 1: tma_rows_eval<0, 2, 2, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
+                default: tma_rows_eval<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
+                }
+            } else {
+                if (warp == 0) tma_rows_eval<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, EA, EB);
+                else tma_rows_eval<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, EA, EB);
+            }
+            __syncthreads();   // every row of the block has been evaluated: the staged records may be overwritten
+            if constexpr (GROUP == 0) {
+                switch (warp) {
+                case 0: tma_rows_emit<0, 1, 1>(a, sh, g, lane, interior, EA, EB); break;
+                case 1: tma_rows_emit<0, 2, 2>(a, sh, g, lane, interior, EA, EB); break;
+                default: tma_rows_emit<0, 3, 4>(a, sh, g, lane, interior, EA, EB); break;
+                }
+            } else {
+                if (warp == 0) tma_rows_emit<1, 5, 5>(a, sh, g, lane, interior, EA, EB);
+                else tma_rows_emit<1, 6, 6>(a, sh, g, lane, interior, EA, EB);
+            }
         }
     }
     if (fast) {
