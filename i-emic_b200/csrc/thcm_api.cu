@@ -914,19 +914,30 @@ void __m_global_MOD_get_land_temp(double*) { fatal("m_global::get_land_temp is d
 void __m_global_MOD_get_spert(double* spert) {                    // global.F90:587-608 (rd_spertm = 0)
     for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) spert[q] = (double)g_set.SRES;
 }
-/* global grid arrays pushed by THCM.C (global.F90:241-293).  The library builds the same arrays itself (grid.F90 formulas,
- * build_grid); a caller-provided array is only checked against them once the model exists. */
-static void check_grid(const char* name, const std::vector<double>& mine, int first, int n, const double* a) {
-    for (int i = 0; i < n && first + i < (int)mine.size(); i++)
-        if (std::fabs(mine[first + i] - a[i]) > 1e-12 * (1.0 + std::fabs(a[i])))
-            fatal(std::string("set_global_") + name + ": the caller's grid differs from grid.F90's");
+/* global grid arrays pushed by THCM.C right after m_global::initialize (THCM.C:340-354; global.F90:241-293).  The library builds the
+ * same arrays itself (grid.F90 formulas, build_grid); the caller's copies are kept and compared with them when init_ creates a model
+ * that spans the whole domain (under MPI the sub-domain grids differ by construction). */
+static std::vector<double> g_grid_in[6];   // x, y, z, xu, yv, zw as handed in
+static void keep_grid(int which, int n, const double* a) { g_grid_in[which].assign(a, a + (n > 0 ? n : 0)); }
+void set_global_x(int* n, double* a) { keep_grid(0, *n, a); }
+void set_global_y(int* n, double* a) { keep_grid(1, *n, a); }
+void set_global_z(int* n, double* a) { keep_grid(2, *n, a); }
+void set_global_xu(int* n, double* a) { keep_grid(3, *n, a); }
+void set_global_yv(int* n, double* a) { keep_grid(4, *n, a); }
+void set_global_zw(int* n, double* a) { keep_grid(5, *n, a); }
+static void check_global_grid(const thcmb_ctx* c) {
+    // THCM.C hands x(1..N), y(1..M), z(1..L), xu(0..N), yv(0..M), zw(0..L)
+    const std::vector<double>* mine[6] = {&c->x, &c->y, &c->z, &c->xu, &c->yv, &c->zw};
+    const int first[6] = {1, 1, 1, 0, 0, 0};
+    const int count[6] = {c->s.N, c->s.M, c->s.L, c->s.N + 1, c->s.M + 1, c->s.L + 1};
+    const char* name[6] = {"x", "y", "z", "xu", "yv", "zw"};
+    for (int w = 0; w < 6; w++) {
+        if ((int)g_grid_in[w].size() != count[w]) continue;     // not provided (or another layout): nothing to compare
+        for (int i = 0; i < count[w]; i++)
+            if (std::fabs((*mine[w])[first[w] + i] - g_grid_in[w][i]) > 1e-12 * (1.0 + std::fabs(g_grid_in[w][i])))
+                fatal(std::string("set_global_") + name[w] + ": the caller's grid differs from grid.F90's");
+    }
 }
-void set_global_x(int* n, double* a) { if (g_ctx) check_grid("x", g_ctx->x, 1, *n, a); }
-void set_global_y(int* n, double* a) { if (g_ctx) check_grid("y", g_ctx->y, 1, *n, a); }
-void set_global_z(int* n, double* a) { if (g_ctx) check_grid("z", g_ctx->z, 1, *n, a); }
-void set_global_xu(int* n, double* a) { if (g_ctx) check_grid("xu", g_ctx->xu, 0, *n, a); }
-void set_global_yv(int* n, double* a) { if (g_ctx) check_grid("yv", g_ctx->yv, 0, *n, a); }
-void set_global_zw(int* n, double* a) { if (g_ctx) check_grid("zw", g_ctx->zw, 0, *n, a); }
 
 void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, double* ymin, double* ymax, double* alphaT, double* alphaS,
            int* ih, int* vmix, int* tap, int* rho_mixing, int* coriolis_on, int* periodic, int* landm, double* taux, double* tauy,
@@ -955,6 +966,8 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }  // THCM is a singleton that replaces the previous instance (THCM.H:76-84)
     g_ctx = thcmb_create(&s, landm);
     g_ctx->use_integral_callback = true;
+    if (g_have_global && s.N == g_set.N && s.M == g_set.M && s.L == g_set.L && s.ymin == g_set.ymin && s.ymax == g_set.ymax && s.xmin == g_set.xmin)
+        check_global_grid(g_ctx);   // the model spans the whole domain: the caller's global grid must be grid.F90's
     size_t nm = (size_t)s.N * s.M;
     memcpy(g_ctx->taux.data(), taux, sizeof(double) * nm); memcpy(g_ctx->tauy.data(), tauy, sizeof(double) * nm);
     memcpy(g_ctx->tatm.data(), tatm, sizeof(double) * nm); memcpy(g_ctx->emip.data(), emip, sizeof(double) * nm);
