@@ -202,6 +202,9 @@ def test_decomp2d_matches_reference_rule():
     assert {(b["npN"], b["npM"]) for b in b2} == {(2, 1)} and {(b["n0"], b["m0"]) for b in b2} == {(180, 152)}
     b4 = blocks(360, 152, 2, 4)
     assert {(b["npN"], b["npM"]) for b in b4} == {(4, 1)} and {(b["n0"], b["m0"]) for b in b4} == {(90, 152)}
+    # BASELINE configs[4]: 0.5 degree on 8 GPUs = 4 x 2 blocks of 180 x 152 columns (0.88 M cells per GPU at L = 32)
+    b05 = blocks(720, 304, 2, 8)
+    assert {(b["npN"], b["npM"]) for b in b05} == {(4, 2)} and {(b["n0"], b["m0"]) for b in b05} == {(180, 152)}
     # remainders go to the first ranks (TRIOS_Domain.C:267-273)
     b3 = blocks(10, 7, 2, 3)
     assert sum(b["n0"] * b["m0"] for b in b3) == 70
