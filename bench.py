@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=list(GRID))
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling (BASELINE configs[4]): the grid grows with the GPU count -- 1: 360x152x24, 2: 510x214x24, "
+                         "4: 720x304x24 (1.31 M cells per GPU each), 8: 720x304x32 (the 0.5-degree grid, 0.88 M cells per GPU)")
     ap.add_argument("--gmres-iters", type=int, default=50)
     ap.add_argument("--precon", type=int, default=1)
     ap.add_argument("--ortho", default="dgks", choices=["mgs", "dgks"],
@@ -185,6 +188,9 @@ def reference_run(n, m, l, iters, steps, warmup, max_workers=None):
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     a = parse()
+    if a.weak:
+        a.grid = list({1: (360, 152, 24), 2: (510, 214, 24), 4: (720, 304, 24), 8: (720, 304, 32)}.get(a.gpus, tuple(a.grid)))
+    scaling = "weak" if a.weak else "strong"
     n, m, l = a.grid
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +204,7 @@ def main():
             return 0
         r = reference_run(n, m, l, iters, a.steps, a.warmup)
         line = {"impl": "reference", "metric": "newton_step_seconds", "value": r["value"], "unit": "s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": r["value"] * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "warmup": a.warmup, "ms_per_step": r["value"] * 1e3, "higher_is_better": False, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": "s", "cores": r["cores"], "kind": "port", "sample": r["sample"], "stages_s": r["stages_s"]},
                 "e2e": {"value": r["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -347,7 +353,7 @@ def main():
             "alg_bytes_per_launch": kernels[dom].get("alg_bytes"), "avg_launch_ms": kernels[dom]["avg_ms"],
             "share_of_step": kernels[dom]["share_of_step"]}
     line = {"metric": "newton_step_seconds", "value": step_ms * 1e-3, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": step_ms, "higher_is_better": False, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": ms_e2e / a.steps * 1e-3, "unit": "s", "h2d_bytes_per_step": 8 * t.ndim, "d2h_bytes_per_step": 8 * t.ndim + 8,
                     "wall_ms_per_step": wall_e2e / a.steps},
@@ -355,7 +361,8 @@ def main():
             "spmv_hbm_gbs": kernels.get("spmv_csr", {}).get("gbs"), "spmv_frac_of_peak": kernels.get("spmv_csr", {}).get("frac_of_peak"),
             "assembly_ms": kernels.get("thcm_assemble<JAC_GRAPH>", {}).get("avg_ms"), "residual_ms": kernels.get("thcm_assemble<RHS>", {}).get("avg_ms"),
             "spmv_ms": kernels.get("spmv_csr", {}).get("avg_ms"), "gmres": {"iters": res.iters, "resid": res.resid, "fnorm": fnorm},
-            "wall_ms_per_step": wall / a.steps, "ndim_global": 6 * n * m * l, "nnz_local": int(nnz_loc)}
+            "wall_ms_per_step": wall / a.steps, "ndim_global": 6 * n * m * l, "nnz_local": int(nnz_loc),
+            "ns_per_cell_per_gpu": step_ms * 1e6 / (n * m * l / max(a.gpus, 1))}
     # north-star target: FP64 Jacobian assembly + SpMV as a fraction of the HBM roofline (algorithmic bytes of both / time of both)
     ka, ks = kernels.get("thcm_assemble<JAC_GRAPH>"), kernels.get("spmv_csr")
     if ka and ks:
