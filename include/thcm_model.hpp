@@ -171,7 +171,8 @@ public:
         rowScaling.resize((size_t)ndim()); colScaling.resize((size_t)ndim());
         return thcmb_recompute_scaling(c_, rowScaling.data(), colScaling.data(), nullptr);
     }
-    double getIntCondCoeff(std::vector<double>& coeff) { coeff.resize((size_t)ndim() / 6); return thcmb_intcond_coeff(c_, coeff.data()); }
+    // coefficients on ALL owned unknowns (non-zero on the S rows of ocean cells), like the Epetra vector intcondCoeff_; returns the volume
+    double getIntCondCoeff(std::vector<double>& coeff) { coeff.resize((size_t)ndim()); return thcmb_intcond_coeff(c_, coeff.data()); }
     void fixMixing(int value) { thcmb_set_vmix_fix(c_, value); }
     // coupling setters (THCM.C:1395-1560 -> m_inserts); `which` as in thcmb_insert_field
     void setSurfaceField(int which, const std::vector<double>& fieldGlobal) { thcmb_insert_field(c_, which, fieldGlobal.data()); }

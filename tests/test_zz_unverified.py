@@ -233,3 +233,19 @@ def test_jacobian_kernels_with_aliased_staging(name, monkeypatch):
         vo, missing = o.jacobian_graph(x)
         assert missing == 0 and np.array_equal(t.jacobian_values_host(), vo)
     t.close()
+
+
+def test_reference_ocean_tests_over_the_cpp_mirror():
+    """tests/cpp/test_ocean_mirror.cpp: the reference's src/tests/test_ocean.C (Initialization, MassMat, ComputeJacobian + the integral
+    condition of its SRES = 0 configuration) re-stated over include/thcm_model.hpp; every EXPECT must hold."""
+    import os
+    import subprocess
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    exe = os.path.join(cases.ROOT, "tests", "cpp", "_bin", "test_ocean_mirror")
+    if not os.path.exists(exe):
+        pytest.fail(exe + " is missing: build it with `make -C tests/cpp`")
+    r = subprocess.run([exe, os.path.join(cases.MASKS, "mask_natl8")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "0 failed" in r.stdout
