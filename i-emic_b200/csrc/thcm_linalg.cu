@@ -985,9 +985,11 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
         // resident blocks per SM x independent phase-A loads per thread, measured at 1 degree (Newton step, profiles/bench_r01g_*):
         // 2 x 8 (92 registers) 75.6 ms, 3 x 4 (78 registers) 74.5 ms, 4 x 4 (64 registers) 77.5 ms.  THCM_FUSED2_BPS overrides.
         // The live tiles stay below the L2 size: BPS x 148 x nv x 4 KB = 89 MB at nv = 50
-        static const int bps = [] { const char* e = getenv("THCM_FUSED2_BPS"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
-        const int grid = std::max(1, std::min(std::min(ntiles, NSM * bps), MD_BLOCKS));
-        if (bps == 2) fused2_axpy_dot_kernel<2, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        // THCM_FUSED2_BPS=38: 3 blocks x 8 loads (candidate, not yet measured: +50 % bytes in flight per SM at <= 85 registers)
+        static const int bps = [] { const char* e = getenv("THCM_FUSED2_BPS"); int v = e ? atoi(e) : 3; return v == 38 ? 38 : (v < 2 ? 2 : (v > 4 ? 4 : v)); }();
+        const int grid = std::max(1, std::min(std::min(ntiles, NSM * (bps == 38 ? 3 : bps)), MD_BLOCKS));
+        if (bps == 38) fused2_axpy_dot_kernel<3, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        else if (bps == 2) fused2_axpy_dot_kernel<2, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
         else if (bps == 3) fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
         else fused2_axpy_dot_kernel<4, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
         c->launches++;
