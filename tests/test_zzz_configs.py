@@ -2,6 +2,8 @@
 2-degree global grid 180x76x16 (Jacobian assembly + SpMV sweep).  configs[0] (4 degree, real mask) is `global4deg` in
 test_emu_parity.py / test_gpu_parity.py, configs[2] the coupled-mode tests there, configs[3] (1 degree) the property test
 `test_full_size_properties_1deg`; configs[4] (0.5 degree, 8 GPUs) is a bench configuration (`bench.py --grid 720 304 32`)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -67,3 +69,21 @@ def test_two_degree_assembly_and_spmv_sweep(two_degree):
         yo = spmv(rowptr, col, val, v)
         assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
     t.close()
+
+
+@pytest.mark.skipif(os.environ.get("THCM_SLOW_TESTS") != "1", reason="needs ~40 GB of RAM and ~3 min (the oracle's dense Al/An at 1 degree); set THCM_SLOW_TESTS=1")
+def test_one_degree_device_functions_bit_exact():
+    """BASELINE configs[3] at FULL size (360 x 152 x 24, 7.88 M unknowns, 134.9 M graph entries): the library's device functions
+    (compiled for the host) against the oracle, residual and Jacobian bit for bit.  Last run: round 1 (r01h), both True."""
+    from emu.emu import EmuTHCM
+    from oracle.oracle import OracleTHCM
+    s, landm = cases.global_synth(360, 152, 24)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+        e.setpar(P[k], v)
+    x = cases.random_state(s, landm, scale=0.1)
+    assert np.array_equal(e.rhs(x), o.rhs(x))
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0 and len(vo) == 134866080
+    assert np.array_equal(e.jacobian(x), vo)
