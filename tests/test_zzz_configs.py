@@ -72,16 +72,23 @@ def test_two_degree_assembly_and_spmv_sweep(two_degree):
 
 
 @pytest.mark.skipif(os.environ.get("THCM_SLOW_TESTS") != "1", reason="needs ~40 GB of RAM and ~3 min (the oracle's dense Al/An at 1 degree); set THCM_SLOW_TESTS=1")
-def test_one_degree_device_functions_bit_exact():
+@pytest.mark.parametrize("variant", ["plain", "mixing+coupled"])
+def test_one_degree_device_functions_bit_exact(variant):
     """BASELINE configs[3] at FULL size (360 x 152 x 24, 7.88 M unknowns, 134.9 M graph entries): the library's device functions
-    (compiled for the host) against the oracle, residual and Jacobian bit for bit.  Last run: round 1 (r01h), both True."""
+    (compiled for the host) against the oracle, residual and Jacobian bit for bit -- plain, and with Mixing = 1 plus the coupled
+    ocean block (configs[2]'s terms).  Last run: round 1 (r01h), all True."""
     from emu.emu import EmuTHCM
     from oracle.oracle import OracleTHCM
-    s, landm = cases.global_synth(360, 152, 24)
+    flags = dict(vmix=1, coupled_T=1, coupled_S=1) if variant != "plain" else {}
+    s, landm = cases.global_synth(360, 152, 24, **flags)
     o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
-    for k, v in PARS.items():
+    for k, v in dict(PARS, SUNP=1.0).items():
         o.setpar(P[k], v)
         e.setpar(P[k], v)
+    if flags:
+        fields, atmos, seaice = cases.coupled_inputs(s)
+        cases.apply_coupled(o, fields, atmos, seaice)
+        cases.apply_coupled(e, fields, atmos, seaice)
     x = cases.random_state(s, landm, scale=0.1)
     assert np.array_equal(e.rhs(x), o.rhs(x))
     vo, missing = o.jacobian_graph(x)
