@@ -94,3 +94,23 @@ def test_one_degree_device_functions_bit_exact(variant):
     vo, missing = o.jacobian_graph(x)
     assert missing == 0 and len(vo) == 134866080
     assert np.array_equal(e.jacobian(x), vo)
+
+
+def test_two_degree_device_functions_with_mixing_and_coupling():
+    """The same 2-degree grid with Mixing = 2 (vmix_control decides the partition) and the coupled ocean block: bit-exact."""
+    from emu.emu import EmuTHCM
+    from oracle.oracle import OracleTHCM
+    s, landm = cases.global_synth(180, 76, 16, vmix=2, coupled_T=1, coupled_S=1)
+    o, e = OracleTHCM(s, landm), EmuTHCM(s, landm)
+    for k, v in dict(PARS, NLES=0.0, SUNP=1.0).items():
+        o.setpar(P[k], v)
+        e.setpar(P[k], v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    cases.apply_coupled(o, fields, atmos, seaice)
+    cases.apply_coupled(e, fields, atmos, seaice)
+    x = cases.random_state(s, landm, scale=0.1)
+    e.vmix_control(x)
+    assert np.array_equal(e.rhs(x), o.rhs(x))
+    vo, missing = o.jacobian_graph(x)
+    assert missing == 0 and np.array_equal(e.jacobian(x), vo)
+    assert np.abs(o.vmix_fun(x)).max() > 0
