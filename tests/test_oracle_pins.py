@@ -284,3 +284,39 @@ def test_grid_matches_the_reference_golden_arrays(qz):
     for k, ref in (("x", gx), ("xu", gxu), ("y", gy), ("yv", gyv), ("z", gz), ("zw", gzw)):
         assert np.abs(e[k] - ref).max() <= tol, k
     assert np.array_equal(e["dfzT"], g["dfzT"][1:]) and np.array_equal(e["dfzW"], g["dfzW"])
+
+
+def test_newton_from_the_reference_state_converges_quadratically():
+    """JACOBIAN PIN against reference-produced data.  Starting at the converged state the reference ships (|F| = 1.8e-4, its continuation
+    stops at 1e-2), Newton with the restated F and J -- mixing (Mixing = 2) and its forward-difference block included -- converges
+    QUADRATICALLY, 1.8e-4 -> 1e-9 -> 6e-15, to a root 2e-5 away from the reference's state in u, v, w, T, S (reft_ocean.C checks norms to 1e-3).
+    Quadratic convergence needs J to be the derivative of F; landing next to the stored state needs both to be the reference's.
+    The pressure has null modes (the linear systems are solved with a 1e-7 shift on the p rows, which does not touch F)."""
+    import scipy.sparse.linalg as spla
+    from emu.emu import EmuTHCM
+    s, mask, pars, state = reft_case()
+    _, _, o = make((s, mask), pars)
+    n = o.ndim
+    rp, col = o.graph()
+    prow = np.zeros(n); prow[3::6] = 1.0
+    x = state.copy()
+    hist = []
+    for it in range(4):
+        F = -o.rhs(x)
+        hist.append(np.linalg.norm(F))
+        if hist[-1] < 1e-13:
+            break
+        val, missing = o.jacobian_graph(x)
+        assert missing == 0
+        J = (sp.csr_matrix((val, col, rp), shape=(n, n)) + sp.diags(1e-7 * prow)).tocsc()
+        x = x + spla.splu(J).solve(-F)
+    assert hist[0] < 2e-4 and hist[1] < 1e-8 and hist[2] < 1e-13, hist          # quadratic: e -> ~3e4 * e^2
+    noP = lambda v: np.delete(v.reshape(-1, 6), 3, axis=1)
+    assert np.linalg.norm(noP(x - state)) < 1e-4 * np.linalg.norm(noP(state))
+    # the library's device functions (compiled for the host) give the same F and J at the root, bit for bit
+    e = EmuTHCM(s, mask)
+    for k, v in pars.items():
+        e.setpar(P[k], v)
+    e.vmix_control(x)
+    assert np.array_equal(e.rhs(x), o.rhs(x))
+    assert np.array_equal(e.jacobian(x), o.jacobian_graph(x)[0])
