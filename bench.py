@@ -313,10 +313,23 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     ncell_loc, ndim_loc, nnz_loc = t.ndim // 6, t.ndim, t.nnz
+    spmv_nnz, spmv_rows_streamed = nnz_loc, ndim_loc
+    if os.environ.get("THCM_SPMV_SKIP_LAND") == "1":
+        # identity rows of LAND cells are not streamed (y = x): count the entries of the other rows ("a land-compressed
+        # format would legitimately move fewer bytes; report both")
+        import numpy as _np
+        rp_, _ = t.graph()
+        cellg = t.local_gids()[::6] // 6
+        ci, cj, ck = cellg % n, (cellg // n) % m, cellg // (n * m)
+        land = landm[ck + 1, cj + 1, ci + 1] != 0
+        lens = _np.diff(rp_).reshape(-1, 6).sum(axis=1)
+        spmv_nnz, spmv_rows_streamed = int(lens[~land].sum()), int(6 * (~land).sum())
+        config["spmv"] = f"identity rows of LAND cells not streamed: {spmv_nnz} of {nnz_loc} entries, graph-equivalent bytes {nnz_loc * 12 + ndim_loc * 20}"
     alg_bytes = {  # algorithmic bytes per launch
         # bytes actually streamed by the format being timed (SURVEY 8d accounting rule): explicit CRS = values + column ids +
         # row pointers + x + y; with THCM_SPMV_PATTERN=1 the column ids shrink to a 2-byte pattern id per row
-        "spmv_csr": (nnz_loc * 8 + ndim_loc * 22) if os.environ.get("THCM_SPMV_PATTERN") == "1" else (nnz_loc * 12 + ndim_loc * 20),
+        "spmv_csr": ((spmv_nnz * 8 + spmv_rows_streamed * 6 + ndim_loc * 16) if os.environ.get("THCM_SPMV_PATTERN") == "1"
+                     else (spmv_nnz * 12 + spmv_rows_streamed * 4 + ndim_loc * 16)) + (ndim_loc // 6 if spmv_rows_streamed != ndim_loc else 0),
         "thcm_assemble<JAC_GRAPH>": ncell_loc * 49 + 8 * nnz_loc,
         "thcm_assemble<RHS>": ncell_loc * 145,
         "mgs_step": 32 * ndim_loc, "dot": 16 * ndim_loc,

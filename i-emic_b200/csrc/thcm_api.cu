@@ -82,6 +82,11 @@ void build_static(thcmb_ctx* c) {
     upload(c->d_tdesc, tdesc);
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_rowpat, c->rowpat_host); upload(c->d_patrel, c->patrel_host);
+    {   // LAND cells: identity rows of the Jacobian whatever the state (bit 4 of the neighbour mask = centre not OCEAN)
+        std::vector<uint8_t> landcell(nbmask.size());
+        for (size_t q = 0; q < nbmask.size(); q++) landcell[q] = (uint8_t)((nbmask[q] >> 4) & 1u);
+        upload(c->d_landcell, landcell);
+    }
     upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
     upload(c->d_send_dst, c->send_dst_host); upload(c->d_send_peer, c->send_peer_host);
     {   // boundary cells (a stencil neighbour lies in the halo) and their rows, for the SpMV split around the exchange
@@ -164,6 +169,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
     if (const char* e = getenv("THCM_SPMV_PATTERN")) c->spmv_pattern = atoi(e);
+    if (const char* e = getenv("THCM_SPMV_SKIP_LAND")) c->spmv_skip_land = atoi(e);
     c->fused_cgs2 = s->nranks == 1 ? 2 : 0;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
     if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
@@ -192,7 +198,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff, (void*)c->d_rowpat, (void*)c->d_patrel,
-                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls})
+                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);

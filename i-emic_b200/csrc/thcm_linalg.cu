@@ -25,14 +25,17 @@ constexpr int SPMV_THREADS = 256;
 // still in flight); 2 the rows listed in `rowlist` (rows of the boundary cells, after the halo has arrived)
 // PAT: column ids come from the pattern table (build_spmv_patterns): col = 6*cell + patrel[rowpat[row]][position]; rows with
 // rowpat = 0xFFFF (halo columns) read the explicit col array.  2 bytes per row instead of 4 bytes per entry.
-template <int LANES, int UNROLL, int SEL = 0, bool PAT = false>
+// LSKIP: rows of LAND cells are identity rows whatever the state (boundary.F90:381-386; explicit zeros elsewhere in the maximal graph):
+// y = x for them without touching their values or column ids (landcell = one byte per owned cell).  Bit-identical to the full product.
+template <int LANES, int UNROLL, int SEL = 0, bool PAT = false, bool LSKIP = false>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
                                                                  const double* __restrict__ val, const double* __restrict__ x,
                                                                  const double* __restrict__ halo, int nlocal, double* __restrict__ y,
                                                                  const unsigned char* __restrict__ bcell = nullptr,
                                                                  const int* __restrict__ rowlist = nullptr,
                                                                  const unsigned short* __restrict__ rowpat = nullptr,
-                                                                 const int* __restrict__ patrel = nullptr) {
+                                                                 const int* __restrict__ patrel = nullptr,
+                                                                 const unsigned char* __restrict__ landcell = nullptr) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
     // the loop bound is warp-uniform and rows that do not take part stay in the body with an empty range: the full-mask
@@ -43,7 +46,10 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
         int row = act ? r0 : 0;
         if constexpr (SEL == 1) act = act && __ldg(bcell + row / NUN) == 0;
         if constexpr (SEL == 2) row = act ? __ldg(rowlist + r0) : 0;
-        const int b = act ? __ldg(rp + row) : 0, e = act ? __ldg(rp + row + 1) : 0;
+        bool land = false;
+        if constexpr (LSKIP) land = act && __ldg(landcell + row / NUN) != 0;
+        const bool ld = act && !land;
+        const int b = ld ? __ldg(rp + row) : 0, e = ld ? __ldg(rp + row + 1) : 0;
         int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
         int pat = 0xFFFF;
         if constexpr (PAT) pat = act ? (int)__ldg(rowpat + row) : 0xFFFF;
@@ -74,6 +80,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
+        if constexpr (LSKIP) { if (sub == 0 && land) s = __ldg(x + row); }
         if (sub == 0 && act) y[row] = s;
     }
 }
@@ -109,6 +116,16 @@ int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* va
         long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
         return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 64));
     };
+    if (c->spmv_skip_land && col == c->d_col && c->d_landcell) {   // the context's own graph: identity rows of LAND cells are not streamed
+        if (c->spmv_pattern && c->d_rowpat && c->d_patrel)
+            spmv_csr_kernel<4, 6, 0, true, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
+                                                                                              c->d_rowpat, c->d_patrel, c->d_landcell);
+        else
+            spmv_csr_kernel<4, 6, 0, false, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
+                                                                                               nullptr, nullptr, c->d_landcell);
+        c->launches++;
+        return 0;
+    }
     if (c->spmv_pattern && col == c->d_col && c->d_rowpat && c->d_patrel) {   // the context's own graph: pattern-compressed columns
         spmv_csr_kernel<4, 6, 0, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
                                                                                     c->d_rowpat, c->d_patrel);

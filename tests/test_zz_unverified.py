@@ -6,6 +6,7 @@ API: salinity integral condition (SRES = 0 -- the configuration of the reference
 pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
 m_thcm_utils::intcond_scaling coefficients.
 (3) The Jacobian kernels with the output staging aliased onto the input stage (THCM_ASM_PIPE=5; more blocks per SM).
+(4) The SpMV that does not stream the identity rows of LAND cells (THCM_SPMV_SKIP_LAND=1).
 (2) The SpMV with pattern-compressed column indices (THCM_SPMV_PATTERN=1; the host dictionary is verified in
 tests/test_emu_parity.py::test_spmv_column_patterns_reproduce_the_graph)."""
 import numpy as np
@@ -109,6 +110,40 @@ def test_integral_condition_needs_sres_zero_and_an_ocean_point():
     t = iemic_b200.THCM(s, landm)
     assert L.thcmb_intcond_row(t.ctx) == -1
     t.close()
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
+@pytest.mark.parametrize("pattern", ["0", "1"])
+def test_spmv_skipping_land_rows(name, pattern, monkeypatch):
+    """THCM_SPMV_SKIP_LAND=1: y = x on the identity rows of LAND cells without streaming them -- bit-identical to the full product
+    (1.0 * x + 0.0 * ... = x), alone and combined with the pattern-compressed columns."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    mk = {"natl8": cases.natl8, "gateway16": cases.gateway16, "global4deg": cases.global4deg,
+          "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw)}[name]
+    s, landm = mk()
+    x = cases.random_state(s, landm, scale=0.2)
+    rng = np.random.default_rng(4)
+    vs = [rng.standard_normal(6 * s.N * s.M * s.L) for _ in range(3)]
+    out = {}
+    for skip in ("0", "1"):
+        monkeypatch.setenv("THCM_SPMV_SKIP_LAND", skip)
+        monkeypatch.setenv("THCM_SPMV_PATTERN", pattern if skip == "1" else "0")
+        t = iemic_b200.THCM(s, landm)
+        for k, v in PARS.items():
+            t.setParameter(k, v)
+        t.evaluate(torch.from_numpy(x).cuda(), None, True)
+        y = t.new_vector()
+        res = []
+        for v in vs:
+            t.applyMatrix(torch.from_numpy(v).cuda(), y)
+            res.append(y.cpu().numpy().copy())
+        out[skip] = res
+        t.close()
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
