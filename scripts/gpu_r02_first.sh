@@ -1,5 +1,5 @@
-# First GPU call of the next round (1 GPU, ~6 min): everything that was written after round 1's GPU budget was spent, then the
-# captures the next optimisation steps need.  Usage: gpurun --timeout 600 -- 'bash scripts/gpu_r02_first.sh'
+# First GPU call of the next round (1 GPU, ~12 min worst case: steps are individually bounded; split into two calls if the budget is tight): everything that was written after round 1's GPU budget was spent, then the
+# captures the next optimisation steps need.  Usage: gpurun --timeout 900 -- 'bash scripts/gpu_r02_first.sh'
 TAG=${1:-r02a}
 # 1. the gated tests (integral condition / pressure rows, pattern-compressed SpMV) + the whole suite
 THCM_RUN_UNVERIFIED=1 timeout 240 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo rc=$? >> gpurun_out/pytest_gpu_$TAG.log; tail -8 gpurun_out/pytest_gpu_$TAG.log
