@@ -821,6 +821,12 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
     }
     c->nsend_cells = (int)send_idx.size(); c->nrecv_cells = (int)recv_slot.size();
     build_spmv_patterns(c);
+    // cell compaction maps (groundwork for the ocean-only Krylov space): ocean cells of the block in cell order,
+    // and the inverse map (compact index or -1 for LAND)
+    c->ocell_host.clear();
+    c->ccell_host.assign((size_t)b.ncell(), -1);
+    for (int cell = 0; cell < b.ncell(); cell++)
+        if (!((nbmask[(size_t)cell] >> 4) & 1u)) { c->ccell_host[(size_t)cell] = (int)c->ocell_host.size(); c->ocell_host.push_back(cell); }
 }
 
 // Column-index compression for the SpMV: the static maximal graph only depends on a row's unknown and on the boundary class /

@@ -163,6 +163,7 @@ struct thcmb_ctx {
     // SpMV column-index compression (build_spmv_patterns): pattern id per row, relative columns per pattern
     std::vector<uint16_t> rowpat_host; std::vector<int> patrel_host;
     uint16_t* d_rowpat = nullptr; int* d_patrel = nullptr;
+    std::vector<int> ocell_host, ccell_host;   // ocean cells of the block (cell order) and the inverse map (-1 = LAND)
     uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows)
     int spmv_skip_land = 0;         // THCM_SPMV_SKIP_LAND=1: y = x on the rows of LAND cells without streaming them (not yet measured: off)
     int spmv_pattern = 0;           // THCM_SPMV_PATTERN=1: columns from the pattern table (not yet measured: off by default)

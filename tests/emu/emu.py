@@ -46,7 +46,8 @@ def lib():
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
                                 ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
                                 ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp]),
-                                ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i]), ("emu_setsres", None, [vp, i])]:
+                                ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i]), ("emu_setsres", None, [vp, i]),
+                                ("emu_ocean_cells", i, [vp]), ("emu_cell_maps", None, [vp, vp, vp])]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
@@ -145,6 +146,13 @@ class EmuTHCM:
         lm = np.ascontiguousarray(landm, dtype=np.int32)
         self.L_.emu_set_landmask(self.h, _p(lm), int(periodic), int(reinit))
         self.nnz = self.L_.emu_gnnz(self.h)
+
+    def cell_maps(self):
+        """(ocell[n_ocean], ccell[ncell]): ocean cells of the block in cell order and the inverse map (-1 = LAND)."""
+        no = self.L_.emu_ocean_cells(self.h)
+        ocell = np.zeros(no, dtype=np.int32); ccell = np.zeros(self.ndim // 6, dtype=np.int32)
+        self.L_.emu_cell_maps(self.h, _p(ocell), _p(ccell))
+        return ocell, ccell
 
     def setsres(self, sres):
         self.L_.emu_setsres(self.h, int(sres))

@@ -168,6 +168,13 @@ void emu_set_landmask(void* h, const int* landm, int periodic, int reinit) {
     else compute_cob(c);
 }
 void emu_setsres(void* h, int sres) { thcmb_ctx* c = &((Emu*)h)->c; c->s.SRES = sres; compute_forcing(c); compute_tables(c); compute_cob(c); }   // setsres_
+// cell compaction maps: number of ocean cells, then ocell[n_ocean] and ccell[ncell]
+int emu_ocean_cells(void* h) { return (int)((Emu*)h)->c.ocell_host.size(); }
+void emu_cell_maps(void* h, int* ocell, int* ccell) {
+    thcmb_ctx* c = &((Emu*)h)->c;
+    memcpy(ocell, c->ocell_host.data(), sizeof(int) * c->ocell_host.size());
+    memcpy(ccell, c->ccell_host.data(), sizeof(int) * c->ccell_host.size());
+}
 double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }

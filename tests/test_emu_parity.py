@@ -4,6 +4,7 @@ mass diagonal, forcing -- on one block and on every block of 2/4/8-rank decompos
 state (which checks the decomposition, the static graph with halo columns and the halo plan without a GPU)."""
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 import cases
 from cases import PAR_INDEX as P
@@ -388,3 +389,38 @@ def test_setsres_toggles_the_restoring_terms_like_thcm_evaluate():
         obj.setsres(0)
     assert np.array_equal(o.rhs(x), e.rhs(x)) and np.array_equal(o.rhs(x), B0)
     assert not np.array_equal(o.jacobian_graph(x)[0], vo)        # the restoring term sits on the S diagonal of the surface cells
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg"])
+def test_ocean_only_krylov_space_is_exact(name):
+    """Design validation for the cell-compacted Krylov space: rows of LAND cells are identity rows and the Newton
+    right-hand side vanishes there, so GMRES on the system restricted to the ocean cells (the library's cell maps) is the SAME iteration:
+    the reference's own GMRES template gives the same residual history and, scattered back, the same solution."""
+    from oracle.oracle import kref_gmres, spmv
+    s, landm, o, e = setup(name)
+    x = cases.consistent_state(s, landm, scale=0.05)
+    val, _ = o.jacobian_graph(x)
+    rp, col = o.graph()
+    b = o.rhs(x)
+    n = o.ndim
+    ocell, ccell = e.cell_maps()
+    land = landm[1:-1, 1:-1, 1:-1].reshape(-1) != 0
+    assert np.array_equal(ccell >= 0, ~land) and np.array_equal(ocell, np.nonzero(~land)[0])
+    assert np.all(b.reshape(-1, 6)[land] == 0.0)                                  # F is masked by (1 - landm) (usrc.F90:580-591)
+    J = sp.csr_matrix((val, col, rp), shape=(n, n))
+    orow = (6 * ocell[:, None] + np.arange(6)[None, :]).reshape(-1)
+    Jl = J[np.repeat(land, 6)]
+    assert (Jl != sp.identity(n, format="csr")[np.repeat(land, 6)]).nnz == 0      # LAND rows: exactly the identity
+    assert abs(J[orow][:, np.repeat(land, 6)]).sum() == 0.0                        # no ocean row couples to a LAND unknown (boundary.F90)
+    Jc = J[orow][:, orow].tocsr()
+    Jc.sort_indices()
+    tol, maxit, restart = 1e-10, 40, 40
+    kf = kref_gmres(rp, col, val, b, np.zeros(n), tol=tol, maxit=maxit, restart=restart, prec_kind=0)
+    kc = kref_gmres(Jc.indptr.astype(np.int32), Jc.indices.astype(np.int32), Jc.data, b[orow], np.zeros(len(orow)), tol=tol, maxit=maxit,
+                    restart=restart, prec_kind=0)
+    k = min(len(kf["hist"]), len(kc["hist"]))
+    assert k > 10 and abs(kf["iters"] - kc["iters"]) <= 1
+    assert np.abs(kf["hist"][:k] - kc["hist"][:k]).max() <= 1e-12
+    xs = np.zeros(n); xs[orow] = kc["x"]
+    assert np.linalg.norm(xs - kf["x"]) <= 1e-10 * np.linalg.norm(kf["x"])
+    assert len(orow) < n and (name != "global4deg" or len(orow) < 0.55 * n)        # 51.5 % of the unknowns on the real 4-degree mask
