@@ -314,7 +314,8 @@ def main():
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     ncell_loc, ndim_loc, nnz_loc = t.ndim // 6, t.ndim, t.nnz
     spmv_nnz, spmv_rows_streamed = nnz_loc, ndim_loc
-    if os.environ.get("THCM_SPMV_SKIP_LAND") == "1":
+    kry_compact = os.environ.get("THCM_KRYLOV_COMPACT") == "1" and a.gpus == 1
+    if os.environ.get("THCM_SPMV_SKIP_LAND") == "1" or kry_compact:
         # identity rows of LAND cells are not streamed (y = x): count the entries of the other rows ("a land-compressed
         # format would legitimately move fewer bytes; report both")
         import numpy as _np
@@ -325,18 +326,22 @@ def main():
         lens = _np.diff(rp_).reshape(-1, 6).sum(axis=1)
         spmv_nnz, spmv_rows_streamed = int(lens[~land].sum()), int(6 * (~land).sum())
         config["spmv"] = f"identity rows of LAND cells not streamed: {spmv_nnz} of {nnz_loc} entries, graph-equivalent bytes {nnz_loc * 12 + ndim_loc * 20}"
+    nk = ndim_loc          # length of the Krylov vectors
+    if kry_compact:
+        nk = spmv_rows_streamed
+        config["krylov"] = f"ocean-only Krylov space: vectors of {nk} of {ndim_loc} unknowns (LAND rows are identity rows, b = 0 there)"
     alg_bytes = {  # algorithmic bytes per launch
         # bytes actually streamed by the format being timed (SURVEY 8d accounting rule): explicit CRS = values + column ids +
         # row pointers + x + y; with THCM_SPMV_PATTERN=1 the column ids shrink to a 2-byte pattern id per row
         "spmv_csr": ((spmv_nnz * 8 + spmv_rows_streamed * 6 + ndim_loc * 16) if os.environ.get("THCM_SPMV_PATTERN") == "1"
-                     else (spmv_nnz * 12 + spmv_rows_streamed * 4 + ndim_loc * 16)) + (ndim_loc // 6 if spmv_rows_streamed != ndim_loc else 0),
+                     else (spmv_nnz * 12 + spmv_rows_streamed * 4 + (nk if kry_compact else ndim_loc) * 16)) + (ndim_loc // 6 if spmv_rows_streamed != ndim_loc else 0),
         "thcm_assemble<JAC_GRAPH>": ncell_loc * 49 + 8 * nnz_loc,
         "thcm_assemble<RHS>": ncell_loc * 145,
-        "mgs_step": 32 * ndim_loc, "dot": 16 * ndim_loc,
+        "mgs_step": 32 * nk, "dot": 16 * nk,
         # batched Gram-Schmidt: a pass over nv basis vectors + w; nv averages (iters+1)/2 over a cycle
-        "multi_dot": int(8 * ndim_loc * ((iters + 1) / 2 * (1 + 1 / 8) + 0)), "multi_axpy": int(8 * ndim_loc * ((iters + 1) / 2 + 2)), "axpby": 24 * ndim_loc, "axpy_negdev": 24 * ndim_loc,
-        "scale_invsqrt": 16 * ndim_loc, "copy": 16 * ndim_loc, "fill": 8 * ndim_loc,
-        "blockdiag_apply": (36 + 12) * 8 * ncell_loc, "blockdiag_build": ncell_loc * 36 * 8 + 12 * nnz_loc,
+        "multi_dot": int(8 * nk * ((iters + 1) / 2 * (1 + 1 / 8) + 0)), "multi_axpy": int(8 * nk * ((iters + 1) / 2 + 2)), "axpby": 24 * nk, "axpy_negdev": 24 * nk,
+        "scale_invsqrt": 16 * nk, "copy": 16 * nk, "fill": 8 * nk,
+        "blockdiag_apply": (36 + 12) * 8 * (nk // 6), "blockdiag_build": ncell_loc * 36 * 8 + 12 * nnz_loc,
     }
     step_ms = ms / a.steps
     kernels = {}

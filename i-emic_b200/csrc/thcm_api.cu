@@ -82,6 +82,7 @@ void build_static(thcmb_ctx* c) {
     upload(c->d_tdesc, tdesc);
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_rowpat, c->rowpat_host); upload(c->d_patrel, c->patrel_host);
+    upload(c->d_ocell, c->ocell_host); upload(c->d_ccell, c->ccell_host); c->n_ocell = (int)c->ocell_host.size();
     {   // LAND cells: identity rows of the Jacobian whatever the state (bit 4 of the neighbour mask = centre not OCEAN)
         std::vector<uint8_t> landcell(nbmask.size());
         for (size_t q = 0; q < nbmask.size(); q++) landcell[q] = (uint8_t)((nbmask[q] >> 4) & 1u);
@@ -170,6 +171,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
     if (const char* e = getenv("THCM_SPMV_PATTERN")) c->spmv_pattern = atoi(e);
     if (const char* e = getenv("THCM_SPMV_SKIP_LAND")) c->spmv_skip_land = atoi(e);
+    if (const char* e = getenv("THCM_KRYLOV_COMPACT")) c->krylov_compact = atoi(e);
     c->fused_cgs2 = s->nranks == 1 ? 2 : 0;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
     if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
@@ -198,7 +200,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff, (void*)c->d_rowpat, (void*)c->d_patrel,
-                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell})
+                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -502,14 +504,31 @@ static void app_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESS
 
 int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags, double* hist,
                 int hist_cap, thcmb_krylov_result* res) {
-    const int n = c->blk.ndim();
+    int n = c->blk.ndim();
     const bool prec = flags & 1, flexible = flags & 4, batched = flags & 8;
     const int m = restart;
     long long n_reorth = 0;
     if (batched && m > 63) fatal("batched (DGKS) orthogonalisation supports GMRES restart <= 63");
     if (m + 2 > 4000) fatal("GMRES restart too large for the device scalar buffer");
-    auto applyA = [&](const double* v, double* out) { thcmb_spmv_dev(c, v, out); };
-    auto applyM = [&](const double* v, double* out) { thcmb_apply_precon_dev(c, v, out); };
+    // Ocean-only Krylov space (THCM_KRYLOV_COMPACT=1, one rank, no integral-condition row): valid when b and the initial guess vanish on
+    // LAND cells, which is checked; the caller's vectors are gathered once and the solution is scattered back at the end
+    double* const d_x_full = d_x;
+    bool compact = c->krylov_compact && c->blk.nranks == 1 && !c->ic_on && c->n_ocell > 0 && c->n_ocell < c->blk.ncell();
+    if (compact && (land_nonzero(c, d_b) != 0 || land_nonzero(c, d_x) != 0)) compact = false;
+    if (compact) {
+        double* bc = pool_vec(c, 2 * (size_t)m + 3);
+        double* xc = pool_vec(c, 2 * (size_t)m + 4);
+        gather_cells(c, d_b, bc);
+        gather_cells(c, d_x, xc);
+        d_b = bc; d_x = xc;
+        n = c->n_ocell * NUN;
+    }
+    auto applyA = [&](const double* v, double* out) { if (compact) spmv_compact(c, v, out); else thcmb_spmv_dev(c, v, out); };
+    auto applyM = [&](const double* v, double* out) {
+        if (!compact) thcmb_apply_precon_dev(c, v, out);
+        else if (c->precon_kind == 1) apply_blockdiag_compact(c, v, out);
+        else copy(c, n, v, out);
+    };
     long long n_matvec = 0;
     int nh = 0;
     auto push = [&](double r) { if (hist && nh < hist_cap) hist[nh] = r; nh++; };
@@ -651,6 +670,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
             if (converged || resid < tol) { status = 0; break; }
         }
     }
+    if (compact) scatter_cells(c, d_x, d_x_full);
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     if (res) { res->status = status; res->iters = iter; res->resid = resid; res->nhist = std::min(nh, hist_cap); res->n_matvec = n_matvec; }
     return status;

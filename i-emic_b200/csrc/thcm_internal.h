@@ -164,6 +164,8 @@ struct thcmb_ctx {
     std::vector<uint16_t> rowpat_host; std::vector<int> patrel_host;
     uint16_t* d_rowpat = nullptr; int* d_patrel = nullptr;
     std::vector<int> ocell_host, ccell_host;   // ocean cells of the block (cell order) and the inverse map (-1 = LAND)
+    int *d_ocell = nullptr, *d_ccell = nullptr; int n_ocell = 0;
+    int krylov_compact = 0;          // THCM_KRYLOV_COMPACT=1: GMRES on the ocean cells only (one rank; candidate, not yet measured)
     uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows)
     int spmv_skip_land = 0;         // THCM_SPMV_SKIP_LAND=1: y = x on the rows of LAND cells without streaming them (not yet measured: off)
     int spmv_pattern = 0;           // THCM_SPMV_PATTERN=1: columns from the pattern table (not yet measured: off by default)
@@ -326,6 +328,11 @@ int average_block(thcmb_ctx* c, double* db36);
 bool scaling_compute(const thcmb_ctx* c, const double* db36, double* row_scaling, double* col_scaling);
 int intcond_scaling(const thcmb_ctx* c, double* val, int* ind);
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
+int gather_cells(thcmb_ctx* c, const double* in, double* out);
+int scatter_cells(thcmb_ctx* c, const double* in, double* out);
+int land_nonzero(thcmb_ctx* c, const double* x);
+int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);
+int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y);
 double* pool_vec(thcmb_ctx* c, size_t idx);
 }  // namespace thcm
 

@@ -1304,6 +1304,120 @@ int build_blockdiag(thcmb_ctx* c) {
     c->launches++;
     return 0;
 }
+// ---------------------------------------------------------------------------
+// Ocean-only (cell-compacted) Krylov space, THCM_KRYLOV_COMPACT=1 (candidate, one rank): rows of LAND cells are
+// identity rows and the Newton right-hand side vanishes there, so every Krylov vector is zero on LAND -- GMRES runs on vectors that
+// hold the OCEAN cells only (51.5 % of the length at 1 degree).  ocell[ci] = full cell of compact cell ci, ccell[cell] = compact
+// index or -1.  The compact SpMV reads the rows of the ocean cells from the SAME graph-order value / column arrays and maps a
+// column to its compact position through ccell (columns on LAND carry exact zeros and are skipped).
+// ---------------------------------------------------------------------------
+__global__ void gather_cells_kernel(int nc, const int* __restrict__ ocell, const double* __restrict__ in, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc * NUN; i += gridDim.x * blockDim.x) {
+        const int ci = i / NUN, v = i - ci * NUN;
+        out[i] = in[(size_t)__ldg(ocell + ci) * NUN + v];
+    }
+}
+__global__ void scatter_cells_kernel(int ncell, const int* __restrict__ ccell, const double* __restrict__ in, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell * NUN; i += gridDim.x * blockDim.x) {
+        const int cell = i / NUN, v = i - cell * NUN;
+        const int ci = __ldg(ccell + cell);
+        out[i] = ci >= 0 ? in[(size_t)ci * NUN + v] : 0.0;     // identity rows: x = b = 0 on LAND
+    }
+}
+// number of non-zero entries of x on LAND cells (the compact space is only valid when there are none)
+__global__ void land_nonzero_kernel(int ncell, const int* __restrict__ ccell, const double* __restrict__ x, int* count) {
+    int local = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell * NUN; i += gridDim.x * blockDim.x)
+        if (__ldg(ccell + i / NUN) < 0 && x[i] != 0.0) local++;
+    if (local) atomicAdd(count, local);
+}
+template <int LANES, int UNROLL>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ ccell,
+                                                                     const int* __restrict__ rp, const int* __restrict__ col,
+                                                                     const double* __restrict__ val, const double* __restrict__ xc,
+                                                                     double* __restrict__ yc) {
+    const int sub = threadIdx.x & (LANES - 1);
+    constexpr int rows_per_block = SPMV_THREADS / LANES;
+    for (int base = blockIdx.x * rows_per_block; base < nrow_c; base += gridDim.x * rows_per_block) {
+        const int i = base + (threadIdx.x / LANES);
+        const bool act = i < nrow_c;
+        int row = 0;
+        if (act) { const int ci = i / NUN; row = __ldg(ocell + ci) * NUN + (i - ci * NUN); }
+        const int b = act ? __ldg(rp + row) : 0, e = act ? __ldg(rp + row + 1) : 0;
+        int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int q = b + sub + u * LANES;
+            const bool ok = q < e;
+            cc[u] = ok ? __ldg(col + q) : -1;
+            vv[u] = ok ? __ldg(val + q) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            double xv = 0.0;
+            if (cc[u] >= 0) {
+                const int cell = cc[u] / NUN, ci = __ldg(ccell + cell);
+                if (ci >= 0) xv = __ldg(xc + (size_t)ci * NUN + (cc[u] - cell * NUN));
+            }
+            xx[u] = xv;
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) s += vv[u] * xx[u];
+        for (int q = b + sub + UNROLL * LANES; q < e; q += LANES) {
+            const int cidx = __ldg(col + q), cell = cidx / NUN, ci = __ldg(ccell + cell);
+            if (ci >= 0) s += __ldg(val + q) * __ldg(xc + (size_t)ci * NUN + (cidx - cell * NUN));
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
+        if (sub == 0 && act) yc[i] = s;
+    }
+}
+__global__ void blockdiag_apply_compact_kernel(int nc, const int* __restrict__ ocell, const double* __restrict__ minv,
+                                               const double* __restrict__ x, double* __restrict__ y) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc * NUN) return;
+    int ci = t / NUN, r = t - ci * NUN;
+    const double* M = minv + (size_t)__ldg(ocell + ci) * 36 + r * NUN;
+    const double* xc = x + (size_t)ci * NUN;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < NUN; q++) s += M[q] * xc[q];
+    y[t] = s;
+}
+int gather_cells(thcmb_ctx* c, const double* in, double* out) {
+    ProfScope prof_(c, KID_COPY);
+    gather_cells_kernel<<<ew_grid(c->n_ocell * NUN), 256, 0, c->stream>>>(c->n_ocell, c->d_ocell, in, out); c->launches++; return 0;
+}
+int scatter_cells(thcmb_ctx* c, const double* in, double* out) {
+    ProfScope prof_(c, KID_COPY);
+    scatter_cells_kernel<<<ew_grid(c->blk.ndim()), 256, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, in, out); c->launches++; return 0;
+}
+int land_nonzero(thcmb_ctx* c, const double* x) {
+    if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
+    THCM_CUDA(cudaMemsetAsync(c->d_flags + 5, 0, sizeof(int), c->stream));
+    land_nonzero_kernel<<<ew_grid(c->blk.ndim()), 256, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, x, c->d_flags + 5); c->launches++;
+    int cnt = 0;
+    THCM_CUDA(cudaMemcpyAsync(&cnt, c->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    return cnt;
+}
+int spmv_compact(thcmb_ctx* c, const double* xc, double* yc) {
+    ProfScope prof_(c, KID_SPMV);
+    const int nrow_c = c->n_ocell * NUN, rows_per_block = SPMV_THREADS / 4;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)nrow_c + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
+    spmv_compact_kernel<4, 6><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_ccell, c->d_rowptr, c->d_col, c->d_val, xc, yc);
+    c->launches++;
+    return 0;
+}
+int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y) {
+    ProfScope prof_(c, KID_PRECON_APPLY);
+    const int n = c->n_ocell * NUN;
+    blockdiag_apply_compact_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->n_ocell, c->d_ocell, c->d_minv, x, y);
+    c->launches++;
+    return 0;
+}
+
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y) {
     int n = c->blk.ndim();
     ProfScope prof_(c, KID_PRECON_APPLY);

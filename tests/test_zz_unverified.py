@@ -6,6 +6,7 @@ API: salinity integral condition (SRES = 0 -- the configuration of the reference
 pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
 m_thcm_utils::intcond_scaling coefficients.
 (3) The Jacobian kernels with the output staging aliased onto the input stage (THCM_ASM_PIPE=5; more blocks per SM).
+(5) GMRES on the ocean-only (cell-compacted) Krylov space (THCM_KRYLOV_COMPACT=1).
 (4) The SpMV that does not stream the identity rows of LAND cells (THCM_SPMV_SKIP_LAND=1).
 (2) The SpMV with pattern-compressed column indices (THCM_SPMV_PATTERN=1; the host dictionary is verified in
 tests/test_emu_parity.py::test_spmv_column_patterns_reproduce_the_graph)."""
@@ -284,3 +285,49 @@ def test_reference_ocean_tests_over_the_cpp_mirror():
     r = subprocess.run([exe, os.path.join(cases.MASKS, "mask_natl8")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "0 failed" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg"])
+@pytest.mark.parametrize("ortho", ["mgs", "dgks"])
+def test_gmres_on_the_ocean_only_krylov_space(name, ortho, monkeypatch):
+    """THCM_KRYLOV_COMPACT=1: the Krylov vectors hold the ocean cells only (LAND rows are identity rows and b vanishes there): same
+    residual history (1e-10) and iteration count as the full-length solve, same solution, zero on LAND; a right-hand side that does
+    not vanish on LAND falls back to the full space.  The reduction itself is validated on the CPU
+    (tests/test_emu_parity.py::test_ocean_only_krylov_space_is_exact)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from oracle.oracle import OracleTHCM
+    mk = {"natl8": cases.natl8, "gateway16": cases.gateway16, "global4deg": cases.global4deg}[name]
+    s, landm = mk()
+    o = OracleTHCM(s, landm)
+    for k, v in PARS.items():
+        o.setpar(P[k], v)
+    x = cases.consistent_state(s, landm, scale=0.05)
+    b = o.rhs(x)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("THCM_KRYLOV_COMPACT", mode)
+        t = iemic_b200.THCM(s, landm)
+        for k, v in PARS.items():
+            t.setParameter(k, v)
+        t.evaluate(torch.from_numpy(x).cuda(), None, True)
+        t.buildPreconditioner(1)
+        sol = t.new_vector()
+        res, hist = t.gmres(torch.from_numpy(b).cuda(), sol, tol=1e-9, maxit=40, restart=40, ortho=ortho)
+        out[mode] = (res.iters, np.array(hist), sol.cpu().numpy().copy())
+        if mode == "1":     # a right-hand side with LAND entries must not use the compact space (and still give the full answer)
+            b2 = b.copy(); b2[:] += 1.0e-3
+            sol2 = t.new_vector()
+            res2, hist2 = t.gmres(torch.from_numpy(b2).cuda(), sol2, tol=1e-9, maxit=10, restart=40, ortho=ortho)
+            land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
+            assert np.allclose(sol2.cpu().numpy()[land], 1.0e-3, rtol=1e-6)      # identity rows: x = b
+        t.close()
+    (i0, h0, s0), (i1, h1, s1) = out["0"], out["1"]
+    k = min(len(h0), len(h1))
+    assert abs(i0 - i1) <= 1 and k > 5
+    assert np.abs(h0[:k] - h1[:k]).max() <= 1e-10
+    assert np.linalg.norm(s0 - s1) <= 1e-9 * np.linalg.norm(s0)
+    land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
+    assert np.all(s1[land] == 0.0)
