@@ -424,3 +424,32 @@ def test_ocean_only_krylov_space_is_exact(name):
     xs = np.zeros(n); xs[orow] = kc["x"]
     assert np.linalg.norm(xs - kf["x"]) <= 1e-10 * np.linalg.norm(kf["x"])
     assert len(orow) < n and (name != "global4deg" or len(orow) < 0.55 * n)        # 51.5 % of the unknowns on the real 4-degree mask
+
+
+@pytest.mark.parametrize("name", ["gateway16", "global4deg", "box_p"])
+def test_compact_spmv_index_maps(name):
+    """The index arithmetic of spmv_compact_kernel / gather_cells / scatter_cells (thcm_linalg.cu), replayed in numpy on the library's
+    cell maps and graph: compact row i -> full row 6*ocell[i/6] + i%6, full column c -> 6*ccell[c/6] + c%6 (skipped on LAND)."""
+    s, landm, o, e = setup(name)
+    x = cases.consistent_state(s, landm, scale=0.05)
+    val, _ = o.jacobian_graph(x)
+    rp, col = e.graph()
+    ocell, ccell = e.cell_maps()
+    n = e.ndim
+    rng = np.random.default_rng(2)
+    xf = rng.standard_normal(n)
+    xf.reshape(-1, 6)[ccell < 0] = 0.0                       # a vector of the compact space: zero on LAND
+    xc = xf.reshape(-1, 6)[ocell].reshape(-1)                # gather_cells
+    yc = np.zeros(6 * len(ocell))
+    for i in range(0, 6 * len(ocell), max(1, len(ocell) // 400)):
+        ci, r = divmod(i, 6)
+        row = 6 * ocell[ci] + r
+        c = col[rp[row]:rp[row + 1]]
+        cc = ccell[c // 6]
+        keep = cc >= 0
+        yc[i] = np.sum(val[rp[row]:rp[row + 1]][keep] * xc[6 * cc[keep] + c[keep] % 6])
+        full = np.sum(val[rp[row]:rp[row + 1]] * xf[c])
+        assert abs(yc[i] - full) <= 1e-13 * (abs(full) + 1e-300) + 1e-300
+    back = np.zeros(n)                                       # scatter_cells
+    back.reshape(-1, 6)[ccell >= 0] = xc.reshape(-1, 6)[ccell[ccell >= 0]]
+    assert np.array_equal(back, xf)
