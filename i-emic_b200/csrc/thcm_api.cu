@@ -131,13 +131,17 @@ void stage_end(thcmb_ctx* c, const char* label) {  // device time under the refe
 }  // namespace
 
 namespace thcm {
+// slot `idx` of the Krylov vector pool, allocated on first use (a solve with restart = 400 that converges in 30 iterations
+// touches 30 slots, not 800)
 double* pool_vec(thcmb_ctx* c, size_t idx) {
-    while (c->krylov_pool.size() <= idx) {
-        double* p = nullptr;
-        THCM_CUDA(cudaMalloc(&p, sizeof(double) * (size_t)c->blk.ndim()));
-        c->krylov_pool.push_back(p);
-    }
+    if (c->krylov_pool.size() <= idx) c->krylov_pool.resize(idx + 1, nullptr);
+    if (!c->krylov_pool[idx]) THCM_CUDA(cudaMalloc(&c->krylov_pool[idx], sizeof(double) * (size_t)c->blk.ndim()));
     return c->krylov_pool[idx];
+}
+// dedicated work vectors that must never alias a pool slot: 0 = dx of thcmb_newton_step, 1 / 2 = compact b / x of thcmb_gmres
+double* work_vec(thcmb_ctx* c, int which) {
+    if (!c->d_work[which]) THCM_CUDA(cudaMalloc(&c->d_work[which], sizeof(double) * (size_t)c->blk.ndim()));
+    return c->d_work[which];
 }
 }  // namespace thcm
 
@@ -202,7 +206,8 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff, (void*)c->d_rowpat, (void*)c->d_patrel,
                     (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell})
         if (p) cudaFree(p);
-    for (double* p : c->krylov_pool) cudaFree(p);
+    for (double* p : c->krylov_pool) if (p) cudaFree(p);
+    for (double* p : c->d_work) if (p) cudaFree(p);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (auto e : c->ev_slot) cudaEventDestroy(e);
@@ -516,8 +521,8 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
     bool compact = c->krylov_compact && c->blk.nranks == 1 && !c->ic_on && c->n_ocell > 0 && c->n_ocell < c->blk.ncell();
     if (compact && (land_nonzero(c, d_b) != 0 || land_nonzero(c, d_x) != 0)) compact = false;
     if (compact) {
-        double* bc = pool_vec(c, 2 * (size_t)m + 3);
-        double* xc = pool_vec(c, 2 * (size_t)m + 4);
+        double* bc = work_vec(c, 1);
+        double* xc = work_vec(c, 2);
         gather_cells(c, d_b, bc);
         gather_cells(c, d_x, xc);
         d_b = bc; d_x = xc;
@@ -793,7 +798,7 @@ int thcmb_newton_step_dev(thcmb_ctx* c, const double* d_un, double* d_dx, double
 int thcmb_newton_step(thcmb_ctx* c, const double* un_host, double* dx_host, double tol, int maxit, int restart, int precon_kind,
                       double* fnorm, thcmb_krylov_result* res) {
     const int n = c->blk.ndim();
-    double* d_dx = pool_vec(c, 2 + (size_t)(restart + 1) + (size_t)restart + 1);
+    double* d_dx = work_vec(c, 0);
     THCM_CUDA(cudaMemcpyAsync(c->d_un, un_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     int rc = thcmb_newton_step_dev(c, c->d_un, d_dx, tol, maxit, restart, precon_kind, fnorm, res);
     THCM_CUDA(cudaMemcpyAsync(dx_host, d_dx, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -989,7 +994,11 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     g_dims[0] = s.N; g_dims[1] = s.M; g_dims[2] = s.L;
     s.alphaT = *alphaT; s.alphaS = *alphaS; s.ih = *ih; s.vmix = *vmix; s.tap = *tap; s.rho_mixing = *rho_mixing;
     s.coriolis_on = *coriolis_on; s.periodic = *periodic; s.rank = 0; s.nranks = 1;
-    if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }  // THCM is a singleton that replaces the previous instance (THCM.H:76-84)
+    if (g_ctx) {   // THCM is a singleton that replaces the previous instance (THCM.H:76-84); the CRS staging buffers were sized for it
+        thcmb_destroy(g_ctx); g_ctx = nullptr;
+        for (void* p : {(void*)g_dbeg, (void*)g_djco, (void*)g_dco}) if (p) cudaFree(p);
+        g_dbeg = g_djco = nullptr; g_dco = nullptr;
+    }
     g_ctx = thcmb_create(&s, landm);
     g_ctx->use_integral_callback = true;
     if (g_have_global && s.N == g_set.N && s.M == g_set.M && s.L == g_set.L && s.ymin == g_set.ymin && s.ymax == g_set.ymax && s.xmin == g_set.xmin)
@@ -1064,7 +1073,11 @@ void set_landmask_(int* landm, int* periodic, int* reinit) {
     build_static(c);
     if (g_dbeg) { cudaFree(g_dbeg); cudaFree(g_djco); cudaFree(g_dco); g_dbeg = g_djco = nullptr; g_dco = nullptr; }
     if (*reinit == 1) { vmix_init(c); refresh_params(c); }   // usrc.F90:410-415
-    else { compute_cob(c); }
+    else {   // no re-initialisation of forcing / lin asked: the mass diagonal and the rows `boundaries` masks in Frc still follow the mask
+        compute_cob(c); zero_cob_of_fixed_rows(c);
+        mask_forcing_rows(c);
+        upload(c->d_cob, c->cob_local); upload(c->d_frc, c->frc_local);
+    }
 }
 void get_forcing_(double* frc) { thcmb_get_forcing(G(), frc); }
 /* m_inserts (inserts.F90:11-281; THCM.C:85-98): n*m surface fields, i fastest; no recompute until the next setparcs */

@@ -278,10 +278,19 @@ void compute_forcing(thcmb_ctx* c) {
                                               (F3(c->internal_temp, gi, gj, k) + F3(c->internal_temp, gi, gj, k + 1)) / 2.);
     }
     c->frc_local = c->frc_raw;
+    mask_forcing_rows(c);
+    c->frc_masked = false;
+}
+
+// boundary.F90 writes Frc(row) = 0 for every row it turns into an identity row, inside each rhs / matrix call and on top of what
+// earlier calls zeroed (the zeros are cumulative until `forcing` refills Frc): applied to frc_local as it stands
+void mask_forcing_rows(thcmb_ctx* c) {
+    const Block& b = c->blk;
+    const int l = c->s.L;
+    auto row = [&](int gi, int gj, int k, int XX) { return (size_t)NUN * (((size_t)(k - 1) * b.m0 + (gj - 1 - b.j0)) * b.n0 + (gi - 1 - b.i0)) + XX - 1; };
     for (int k = 1; k <= l; k++) for (int gj = b.j0 + 1; gj <= b.j0 + b.m0; gj++) for (int gi = b.i0 + 1; gi <= b.i0 + b.n0; gi++)
         for (int XX = 1; XX <= NUN; XX++)
             if (frc_row_zeroed(c, gi, gj, k, XX)) c->frc_local[row(gi, gj, k, XX)] = 0.0;
-    c->frc_masked = false;
 }
 
 // usrc.F90:1200-1240: the members of m_atm the ocean reads (Ooa, Os, suno); nus and lvsc wait for set_atmos_parameters

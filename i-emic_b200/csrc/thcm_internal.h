@@ -209,7 +209,8 @@ struct thcmb_ctx {
     int n_asm_blocks = 0;
     double* d_minv = nullptr;       // block-diagonal inverse, 36 per cell
     int precon_kind = 0;
-    std::vector<double*> krylov_pool;  // device vectors reused across solves
+    std::vector<double*> krylov_pool;  // device vectors reused across solves (slots allocated on first use)
+    double* d_work[3] = {nullptr, nullptr, nullptr};   // dx of thcmb_newton_step, compact b / x of thcmb_gmres: never pool slots
     long long launches = 0;
     std::map<std::string, double> stage_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -245,6 +246,7 @@ void build_grid(thcmb_ctx* c);
 void stpnt(thcmb_ctx* c);
 void apply_landmask_rules(thcmb_ctx* c, const int* landm_in, bool fix_inversion);
 void compute_forcing(thcmb_ctx* c);
+void mask_forcing_rows(thcmb_ctx* c);
 void atmos_coef(thcmb_ctx* c);
 void init_surface_fields(thcmb_ctx* c);
 enum SurfaceField { SF_TAUX = 0, SF_TAUY, SF_TATM, SF_EMIP, SF_SPERT, SF_ADAPTED_EMIP, SF_QATM, SF_ALBE, SF_PATM, SF_QSA, SF_MSI,
@@ -334,6 +336,7 @@ int land_nonzero(thcmb_ctx* c, const double* x);
 int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);
 int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y);
 double* pool_vec(thcmb_ctx* c, size_t idx);
+double* work_vec(thcmb_ctx* c, int which);
 }  // namespace thcm
 
 namespace thcm {

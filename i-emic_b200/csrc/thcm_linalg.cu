@@ -313,8 +313,12 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int n, const doub
     finish_reduction(s, partial, counter, out, pa);
 }
 
-__global__ void axpby_kernel(int n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i] + b * y[i];
+// y = a x + b y with the BLAS / Epetra_MultiVector::Update convention: an operand whose scalar is zero is NOT read (b = 0 makes this a
+// scaled copy into possibly uninitialised memory; 0 * NaN would poison it).  x and y may alias (scale in place), hence no __restrict__.
+__global__ void axpby_kernel(int n, double a, const double* x, double b, double* y) {
+    if (b == 0.0)      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i];
+    else if (a == 0.0) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = b * y[i];
+    else               for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = a * x[i] + b * y[i];
 }
 __global__ void axpy_negdev_kernel(int n, const double* __restrict__ h, const double* __restrict__ x, double* __restrict__ y) {
     const double a = -(*h);
@@ -1069,7 +1073,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
     if (!last) return;
     // every block's stores were performed at the neighbours (its system fence completed) before it bumped the counter this
     // block has just read: the flags can follow with a device-scope fence only -- system fences cost ~5 us each here
-    __threadfence();
+    // (the flag store to a PEER must be ordered after them at system scope in the PTX memory model: one fence, one thread group)
+    __threadfence_system();
     const int par = (int)(seq & 1ull);
     if (threadIdx.x < hp.n) {
         const int q = threadIdx.x;
@@ -1386,10 +1391,12 @@ __global__ void blockdiag_apply_compact_kernel(int nc, const int* __restrict__ o
     y[t] = s;
 }
 int gather_cells(thcmb_ctx* c, const double* in, double* out) {
+    if (in == out) fatal("gather_cells: in-place gather is not supported");
     ProfScope prof_(c, KID_COPY);
     gather_cells_kernel<<<ew_grid(c->n_ocell * NUN), 256, 0, c->stream>>>(c->n_ocell, c->d_ocell, in, out); c->launches++; return 0;
 }
 int scatter_cells(thcmb_ctx* c, const double* in, double* out) {
+    if (in == out) fatal("scatter_cells: in-place scatter is not supported");
     ProfScope prof_(c, KID_COPY);
     scatter_cells_kernel<<<ew_grid(c->blk.ndim()), 256, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, in, out); c->launches++; return 0;
 }

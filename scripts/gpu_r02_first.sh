@@ -2,7 +2,7 @@
 # captures the next optimisation steps need.  Usage: gpurun --timeout 900 -- 'bash scripts/gpu_r02_first.sh'
 TAG=${1:-r02a}
 # 1. the gated tests (integral condition / pressure rows, pattern-compressed SpMV) + the whole suite
-THCM_RUN_UNVERIFIED=1 timeout 240 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo rc=$? >> gpurun_out/pytest_gpu_$TAG.log; tail -8 gpurun_out/pytest_gpu_$TAG.log
+THCM_RUN_UNVERIFIED=1 timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo rc=$? >> gpurun_out/pytest_gpu_$TAG.log; tail -8 gpurun_out/pytest_gpu_$TAG.log
 # 2. A/B of the candidates on the same box: pattern SpMV, fused CGS2 occupancy
 for v in "" "THCM_KRYLOV_COMPACT=1" "THCM_SPMV_SKIP_LAND=1" "THCM_SPMV_PATTERN=1" "THCM_ASM_PIPE=5" "THCM_FUSED2_BPS=38" "THCM_FUSED2_BPS=2" ; do
   name=$(echo "${v:-default}" | tr '=' '_')
