@@ -314,7 +314,7 @@ def main():
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     ncell_loc, ndim_loc, nnz_loc = t.ndim // 6, t.ndim, t.nnz
     spmv_nnz, spmv_rows_streamed = nnz_loc, ndim_loc
-    kry_compact = os.environ.get("THCM_KRYLOV_COMPACT") == "1" and a.gpus == 1
+    kry_compact = os.environ.get("THCM_KRYLOV_COMPACT", "1") != "0"
     if os.environ.get("THCM_SPMV_SKIP_LAND") == "1" or kry_compact:
         # identity rows of LAND cells are not streamed (y = x): count the entries of the other rows ("a land-compressed
         # format would legitimately move fewer bytes; report both")

@@ -83,6 +83,8 @@ void build_static(thcmb_ctx* c) {
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
     upload(c->d_rowpat, c->rowpat_host); upload(c->d_patrel, c->patrel_host);
     upload(c->d_ocell, c->ocell_host); upload(c->d_ccell, c->ccell_host); c->n_ocell = (int)c->ocell_host.size();
+    upload(c->d_colc, c->colc_host); upload(c->d_send_cidx, c->send_cidx_host);
+    std::vector<int>().swap(c->colc_host);   // as large as the graph's column array: the device copy is the one that is used
     {   // LAND cells: identity rows of the Jacobian whatever the state (bit 4 of the neighbour mask = centre not OCEAN)
         std::vector<uint8_t> landcell(nbmask.size());
         for (size_t q = 0; q < nbmask.size(); q++) landcell[q] = (uint8_t)((nbmask[q] >> 4) & 1u);
@@ -176,7 +178,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     if (const char* e = getenv("THCM_SPMV_PATTERN")) c->spmv_pattern = atoi(e);
     if (const char* e = getenv("THCM_SPMV_SKIP_LAND")) c->spmv_skip_land = atoi(e);
     if (const char* e = getenv("THCM_KRYLOV_COMPACT")) c->krylov_compact = atoi(e);
-    c->fused_cgs2 = s->nranks == 1 ? 2 : 0;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
+    c->fused_cgs2 = 2;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
     if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));
@@ -204,7 +206,8 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff, (void*)c->d_rowpat, (void*)c->d_patrel,
-                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell})
+                    (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell, (void*)c->d_colc, (void*)c->d_send_cidx,
+                    (void*)c->d_iccoeff_c})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) if (p) cudaFree(p);
     for (double* p : c->d_work) if (p) cudaFree(p);
@@ -328,6 +331,9 @@ void thcmb_enable_intcond(thcmb_ctx* c, int Nic, int Mic, int sign) {
     thcmb_intcond_coeff(c, coeff.data());
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     upload(c->d_iccoeff, coeff);
+    if (c->d_iccoeff_c) { cudaFree(c->d_iccoeff_c); c->d_iccoeff_c = nullptr; }
+    THCM_CUDA(cudaMalloc(&c->d_iccoeff_c, sizeof(double) * (size_t)std::max(NUN * c->n_ocell, 1)));
+    if (c->n_ocell > 0) gather_cells(c, c->d_iccoeff, c->d_iccoeff_c);
     refresh_fix_rows(c);
 }
 /* THCM::setIntCondCorrection (THCM.C:2078-2097): the salinity integral of d_vec becomes the target of the condition */
@@ -515,11 +521,13 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
     long long n_reorth = 0;
     if (batched && m > 63) fatal("batched (DGKS) orthogonalisation supports GMRES restart <= 63");
     if (m + 2 > 4000) fatal("GMRES restart too large for the device scalar buffer");
-    // Ocean-only Krylov space (THCM_KRYLOV_COMPACT=1, one rank, no integral-condition row): valid when b and the initial guess vanish on
-    // LAND cells, which is checked; the caller's vectors are gathered once and the solution is scattered back at the end
+    // Ocean-only Krylov space (default; THCM_KRYLOV_COMPACT=0 or flag 16 switch it off): rows of LAND cells are identity rows, so when b
+    // and the initial guess vanish on LAND -- checked, over all ranks -- every Krylov vector does; the caller's vectors are gathered once
+    // and the solution is scattered back at the end
     double* const d_x_full = d_x;
-    bool compact = c->krylov_compact && c->blk.nranks == 1 && !c->ic_on && c->n_ocell > 0 && c->n_ocell < c->blk.ncell();
-    if (compact && (land_nonzero(c, d_b) != 0 || land_nonzero(c, d_x) != 0)) compact = false;
+    // (every rank takes the same branch: the test is global; a rank without LAND cells simply keeps all of its cells)
+    bool compact = compact_possible(c) && !(flags & 16);
+    if (compact && (land_nonzero_global(c, d_b) != 0.0 || land_nonzero_global(c, d_x) != 0.0)) compact = false;
     if (compact) {
         double* bc = work_vec(c, 1);
         double* xc = work_vec(c, 2);

@@ -836,6 +836,23 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
     c->ccell_host.assign((size_t)b.ncell(), -1);
     for (int cell = 0; cell < b.ncell(); cell++)
         if (!((nbmask[(size_t)cell] >> 4) & 1u)) { c->ccell_host[(size_t)cell] = (int)c->ocell_host.size(); c->ocell_host.push_back(cell); }
+    // column ids of the ocean-only (cell-compacted) space, stored at the SAME offsets as the graph's column array: compact position of
+    // an owned ocean column, -1 for a column on LAND (its value is an exact zero and x = 0 there), nc6 + halo offset for a halo column
+    // (halo cells keep their slots; a neighbour pushes zeros for its LAND cells).  Entries of LAND rows are never read.
+    const int nc6 = NUN * (int)c->ocell_host.size(), nd = b.ndim();
+    c->colc_host.assign(c->col_host.size(), -1);
+    for (size_t ci = 0; ci < c->ocell_host.size(); ci++)
+        for (int r = 0; r < NUN; r++) {
+            const int row = NUN * c->ocell_host[ci] + r;
+            for (int q = c->rowptr_host[row]; q < c->rowptr_host[row + 1]; q++) {
+                const int id = c->col_host[q];
+                if (id >= nd) c->colc_host[q] = nc6 + (id - nd);
+                else { const int cc = c->ccell_host[(size_t)(id / NUN)]; c->colc_host[q] = cc < 0 ? -1 : NUN * cc + id % NUN; }
+            }
+        }
+    // compact source of every cell of the send lists (-1 = LAND: a zero record is pushed)
+    c->send_cidx_host.resize(send_idx.size());
+    for (size_t q = 0; q < send_idx.size(); q++) c->send_cidx_host[q] = c->ccell_host[(size_t)send_idx[q]];
 }
 
 // Column-index compression for the SpMV: the static maximal graph only depends on a row's unknown and on the boundary class /

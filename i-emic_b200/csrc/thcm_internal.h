@@ -165,7 +165,13 @@ struct thcmb_ctx {
     uint16_t* d_rowpat = nullptr; int* d_patrel = nullptr;
     std::vector<int> ocell_host, ccell_host;   // ocean cells of the block (cell order) and the inverse map (-1 = LAND)
     int *d_ocell = nullptr, *d_ccell = nullptr; int n_ocell = 0;
-    int krylov_compact = 0;          // THCM_KRYLOV_COMPACT=1: GMRES on the ocean cells only (one rank; candidate, not yet measured)
+    std::vector<int> colc_host, send_cidx_host;   // compact column ids (graph offsets), compact source cell of the send lists
+    int *d_colc = nullptr, *d_send_cidx = nullptr;
+    double* d_iccoeff_c = nullptr;   // integral-condition coefficients gathered to the ocean cells
+    void* d_peer_ll = nullptr;       // device array [2][npeers]: the neighbours' LL halo buffers (compact SpMV), per parity
+    void* d_halo_ll[2] = {nullptr, nullptr};   // my LL halo buffers (inside the IPC-shared allocation)
+    unsigned long long halo_ll_seq = 0;
+    int krylov_compact = 1;          // GMRES on the ocean cells only (THCM_KRYLOV_COMPACT=0 switches it off)
     uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows)
     int spmv_skip_land = 0;         // THCM_SPMV_SKIP_LAND=1: y = x on the rows of LAND cells without streaming them (not yet measured: off)
     int spmv_pattern = 0;           // THCM_SPMV_PATTERN=1: columns from the pattern table (not yet measured: off by default)
@@ -332,8 +338,9 @@ int intcond_scaling(const thcmb_ctx* c, double* val, int* ind);
 int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
 int gather_cells(thcmb_ctx* c, const double* in, double* out);
 int scatter_cells(thcmb_ctx* c, const double* in, double* out);
-int land_nonzero(thcmb_ctx* c, const double* x);
-int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);
+int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);   // incl. the LL halo push on more than one rank and the integral row
+bool compact_possible(const thcmb_ctx* c);
+double land_nonzero_global(thcmb_ctx* c, const double* x);
 int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y);
 double* pool_vec(thcmb_ctx* c, size_t idx);
 double* work_vec(thcmb_ctx* c, int which);

@@ -196,18 +196,36 @@ constexpr size_t P2P_HALOFLAG_OFFSET = (P2P_MAILBOX_BYTES + 255) / 256 * 256;
 constexpr size_t P2P_HALO_OFFSET = P2P_HALOFLAG_OFFSET + 256;
 static_assert(2 * P2P_MAX_RANKS * sizeof(unsigned long long) <= 256, "halo flag area");
 static inline size_t p2p_halo_bytes(const thcmb_ctx* c) { return ((size_t)NUN * std::max(c->blk.nhalo_cells(), 1) * sizeof(double) + 255) / 256 * 256; }
+// ... and, behind the two plain halo buffers, two halo buffers in LL format (one 16-byte slot per double: data + flags) for the halo
+// exchange that is fused into the compact SpMV -- the reader polls the slot it needs, no fence, no flag round trip, no wait kernel
+static inline size_t p2p_ll_bytes(const thcmb_ctx* c) { return 2 * p2p_halo_bytes(c); }
+static inline size_t p2p_ll_offset(const thcmb_ctx* c, int b) { return P2P_HALO_OFFSET + 2 * p2p_halo_bytes(c) + (size_t)b * p2p_ll_bytes(c); }
+static inline size_t p2p_total_bytes(const thcmb_ctx* c) { return p2p_ll_offset(c, 2); }
 
 __device__ __forceinline__ void ll_store(P2PSlot* dst, double v, unsigned int flag) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(dst), "r"((unsigned int)b), "r"(flag),
                  "r"((unsigned int)(b >> 32)), "r"(flag) : "memory");
 }
+// A peer that never arrives (a rank that died or left the SPMD sequence) must not hang the node silently: every poll loop is bounded
+// (~2^27 polls of >= 0.5 us: more than a minute, against exchanges that take microseconds), then reports and traps -- the host sees a
+// CUDA error at its next call and fails through thcm_throw_error_.
+constexpr unsigned int P2P_SPIN_LIMIT = 1u << 27;
+__device__ __noinline__ void p2p_timeout(const void* slot, unsigned int want, unsigned int got) {
+    printf("thcm_b200: timed out waiting for a peer GPU (slot %p, expected flag %u, last seen %u): a rank left the SPMD sequence\n", slot, want, got);
+    __trap();
+}
 __device__ __forceinline__ double ll_wait(const P2PSlot* src, unsigned int flag) {
-    unsigned int lo, f0, hi, f1;
+    unsigned int lo, f0, hi, f1, spins = 0;
     do {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+        if (++spins > P2P_SPIN_LIMIT) p2p_timeout(src, flag, f0);
     } while (f0 != flag || f1 != flag);
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+__device__ __forceinline__ void flag_wait(volatile unsigned long long* f, unsigned long long seq) {
+    unsigned int spins = 0;
+    while (*f != seq) if (++spins > P2P_SPIN_LIMIT) p2p_timeout((const void*)f, (unsigned int)seq, (unsigned int)*f);
 }
 
 // optional epilogue of a reduction (DGKS, thcmb_gmres): flag = (result < 0.5 * *ww_old), *final_out = result
@@ -358,7 +376,7 @@ int p2p_local_handle(thcmb_ctx* c, void* handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (c->blk.nranks > P2P_MAX_RANKS) return -1;
     if (!c->d_mailbox) {
-        const size_t bytes = P2P_HALO_OFFSET + 2 * p2p_halo_bytes(c);
+        const size_t bytes = p2p_total_bytes(c);
         THCM_CUDA(cudaMalloc(&c->d_mailbox, bytes));
         THCM_CUDA(cudaMemset(c->d_mailbox, 0, bytes));
         THCM_CUDA(cudaDeviceSynchronize());
@@ -393,14 +411,22 @@ int p2p_open(thcmb_ctx* c, const void* handles_all) {
         if (c->d_halo) cudaFree(c->d_halo);
         c->d_halo = c->d_halo_p2p[0];
         std::vector<double*> ph(2 * std::max<size_t>(c->peers.size(), 1), nullptr);
+        std::vector<void*> pl(2 * std::max<size_t>(c->peers.size(), 1), nullptr);
         for (size_t q = 0; q < c->peers.size(); q++) {
             thcmb_ctx tmp; tmp.blk = Block();
             if (!decomp2d(c->blk.nranks, c->peers[q].rank, c->blk.N, c->blk.M, c->blk.L, c->blk.periodic, tmp.blk)) fatal("halo push: bad peer block");
             const size_t pb = p2p_halo_bytes(&tmp);
-            for (int b = 0; b < 2; b++) ph[b * c->peers.size() + q] = (double*)((char*)ptrs[c->peers[q].rank] + P2P_HALO_OFFSET + b * pb);
+            for (int b = 0; b < 2; b++) {
+                ph[b * c->peers.size() + q] = (double*)((char*)ptrs[c->peers[q].rank] + P2P_HALO_OFFSET + b * pb);
+                pl[b * c->peers.size() + q] = (void*)((char*)ptrs[c->peers[q].rank] + p2p_ll_offset(&tmp, b));
+            }
         }
         THCM_CUDA(cudaMalloc(&c->d_peer_halo, sizeof(double*) * ph.size()));
         THCM_CUDA(cudaMemcpy(c->d_peer_halo, ph.data(), sizeof(double*) * ph.size(), cudaMemcpyHostToDevice));
+        THCM_CUDA(cudaMalloc(&c->d_peer_ll, sizeof(void*) * pl.size()));
+        THCM_CUDA(cudaMemcpy(c->d_peer_ll, pl.data(), sizeof(void*) * pl.size(), cudaMemcpyHostToDevice));
+        for (int b = 0; b < 2; b++) c->d_halo_ll[b] = (char*)c->d_mailbox + p2p_ll_offset(c, b);
+        c->halo_ll_seq = 0;
         THCM_CUDA(cudaMalloc(&c->d_halo_counter, sizeof(unsigned int)));
         THCM_CUDA(cudaMemset(c->d_halo_counter, 0, sizeof(unsigned int)));
         c->halo_seq = 0;
@@ -414,6 +440,8 @@ void p2p_close(thcmb_ctx* c) {
     c->p2p_peer_ptrs.clear();
     if (c->d_peer_mailboxes) cudaFree(c->d_peer_mailboxes);
     if (c->d_peer_halo) cudaFree(c->d_peer_halo);
+    if (c->d_peer_ll) cudaFree(c->d_peer_ll);
+    c->d_peer_ll = nullptr; c->d_halo_ll[0] = c->d_halo_ll[1] = nullptr;
     if (c->d_p2p_seq) cudaFree(c->d_p2p_seq);
     c->d_p2p_seq = nullptr;
     if (c->halo_p2p) c->d_halo = nullptr;   // lived inside the mailbox allocation
@@ -1084,7 +1112,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
         }
         if (wait && hp.recv[q]) {
             volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[q];
-            while (*f != seq) { }
+            flag_wait(f, seq);
         }
     }
     if (wait) __threadfence_system();
@@ -1095,7 +1123,7 @@ __global__ void halo_wait_kernel(HaloPeers hp, char* my_base, unsigned long long
     const int par = (int)(seq & 1ull);
     if (threadIdx.x < hp.n && hp.recv[threadIdx.x]) {
         volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[threadIdx.x];
-        while (*f != seq) { }
+        flag_wait(f, seq);
     }
     __threadfence_system();
 }
@@ -1329,18 +1357,37 @@ __global__ void scatter_cells_kernel(int ncell, const int* __restrict__ ccell, c
         out[i] = ci >= 0 ? in[(size_t)ci * NUN + v] : 0.0;     // identity rows: x = b = 0 on LAND
     }
 }
-// number of non-zero entries of x on LAND cells (the compact space is only valid when there are none)
-__global__ void land_nonzero_kernel(int ncell, const int* __restrict__ ccell, const double* __restrict__ x, int* count) {
-    int local = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncell * NUN; i += gridDim.x * blockDim.x)
-        if (__ldg(ccell + i / NUN) < 0 && x[i] != 0.0) local++;
-    if (local) atomicAdd(count, local);
+// number of non-zero entries of x on LAND cells, summed over the ranks (the compact space is only valid when there are none, and
+// every rank must take the same decision): an ordinary reduction kernel with the fused all-reduce
+__global__ void __launch_bounds__(RED_THREADS) land_nonzero_kernel(int ncell, const int* __restrict__ ccell, const double* __restrict__ x,
+                                                                   double* partial, unsigned int* counter, double* out, const P2PArgs pa) {
+    double v = 0.0;
+    for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < ncell * NUN; i += gridDim.x * RED_THREADS)
+        if (__ldg(ccell + i / NUN) < 0 && x[i] != 0.0) v += 1.0;
+    double s = block_sum(v);
+    finish_reduction(s, partial, counter, out, pa);
 }
-template <int LANES, int UNROLL>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ ccell,
-                                                                     const int* __restrict__ rp, const int* __restrict__ col,
-                                                                     const double* __restrict__ val, const double* __restrict__ xc,
-                                                                     double* __restrict__ yc) {
+// Halo exchange of the compact SpMV: every boundary cell's six values go straight into the neighbour's LL halo buffer, each as one
+// 16-byte {lo, flag, hi, flag} store (zeros for LAND cells).  Fire and forget: no fence, no counter, no wait -- the consumer is the
+// neighbour's SpMV kernel, which polls exactly the slots its rows reference.
+__global__ void __launch_bounds__(256) halo_push_ll_kernel(int ncells, const int* __restrict__ cidx, const int* __restrict__ dst_slot,
+                                                            const int* __restrict__ peer, const double* __restrict__ xc,
+                                                            P2PSlot* const* peer_ll, unsigned int flag) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncells * NUN; t += gridDim.x * blockDim.x) {
+        const int q = t / NUN, v = t - q * NUN;
+        const int ci = __ldg(cidx + q);
+        const double val = ci >= 0 ? xc[(size_t)NUN * ci + v] : 0.0;
+        ll_store(peer_ll[__ldg(peer + q)] + (size_t)NUN * __ldg(dst_slot + q) + v, val, flag);
+    }
+}
+// y_c = J x_c on the rows of the ocean cells.  Values and row pointers are the graph's own arrays (row = 6 ocell[ci] + r), the column
+// ids come from the compact column array stored at the same offsets: < 0 LAND column (skipped), < nlocal_c owned, else an LL halo slot
+// that is polled until the neighbour's push of THIS exchange (flag) has landed -- interior rows never wait.
+template <int LANES, int UNROLL, bool HALO>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ rp,
+                                                                     const int* __restrict__ colc, const double* __restrict__ val,
+                                                                     const double* __restrict__ xc, int nlocal_c, const P2PSlot* halo_ll,
+                                                                     unsigned int flag, double* __restrict__ yc) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
     for (int base = blockIdx.x * rows_per_block; base < nrow_c; base += gridDim.x * rows_per_block) {
@@ -1354,24 +1401,26 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, 
         for (int u = 0; u < UNROLL; u++) {
             const int q = b + sub + u * LANES;
             const bool ok = q < e;
-            cc[u] = ok ? __ldg(col + q) : -1;
+            cc[u] = ok ? __ldg(colc + q) : -1;
             vv[u] = ok ? __ldg(val + q) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             double xv = 0.0;
             if (cc[u] >= 0) {
-                const int cell = cc[u] / NUN, ci = __ldg(ccell + cell);
-                if (ci >= 0) xv = __ldg(xc + (size_t)ci * NUN + (cc[u] - cell * NUN));
+                if (!HALO || cc[u] < nlocal_c) xv = __ldg(xc + cc[u]);
+                else xv = ll_wait(halo_ll + (cc[u] - nlocal_c), flag);
             }
             xx[u] = xv;
         }
         double s = 0.0;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) s += vv[u] * xx[u];
-        for (int q = b + sub + UNROLL * LANES; q < e; q += LANES) {
-            const int cidx = __ldg(col + q), cell = cidx / NUN, ci = __ldg(ccell + cell);
-            if (ci >= 0) s += __ldg(val + q) * __ldg(xc + (size_t)ci * NUN + (cidx - cell * NUN));
+        for (int q = b + sub + UNROLL * LANES; q < e; q += LANES) {   // rows longer than UNROLL*LANES (not in the THCM graph)
+            const int cidx = __ldg(colc + q);
+            if (cidx < 0) continue;
+            const double xv = (!HALO || cidx < nlocal_c) ? __ldg(xc + cidx) : ll_wait(halo_ll + (cidx - nlocal_c), flag);
+            s += __ldg(val + q) * xv;
         }
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, LANES);
@@ -1400,21 +1449,49 @@ int scatter_cells(thcmb_ctx* c, const double* in, double* out) {
     ProfScope prof_(c, KID_COPY);
     scatter_cells_kernel<<<ew_grid(c->blk.ndim()), 256, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, in, out); c->launches++; return 0;
 }
-int land_nonzero(thcmb_ctx* c, const double* x) {
-    if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
-    THCM_CUDA(cudaMemsetAsync(c->d_flags + 5, 0, sizeof(int), c->stream));
-    land_nonzero_kernel<<<ew_grid(c->blk.ndim()), 256, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, x, c->d_flags + 5); c->launches++;
-    int cnt = 0;
-    THCM_CUDA(cudaMemcpyAsync(&cnt, c->d_flags + 5, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+// the ocean-only Krylov space needs the LL halo exchange on more than one rank
+bool compact_possible(const thcmb_ctx* c) {
+    return c->krylov_compact && c->d_colc && (c->blk.nranks == 1 || (c->p2p_on && c->halo_p2p && c->d_peer_ll));
+}
+double land_nonzero_global(thcmb_ctx* c, const double* x) {
+    double* d = c->d_scalars + 4020;
+    land_nonzero_kernel<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->blk.ncell(), c->d_ccell, x, c->d_partial, c->d_counter, d, p2p_args(c));
+    c->launches++;
+    if (!c->p2p_on) allreduce_dev(c, d, 1);
+    double cnt = 0.0;
+    THCM_CUDA(cudaMemcpyAsync(&cnt, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     return cnt;
 }
 int spmv_compact(thcmb_ctx* c, const double* xc, double* yc) {
-    ProfScope prof_(c, KID_SPMV);
     const int nrow_c = c->n_ocell * NUN, rows_per_block = SPMV_THREADS / 4;
     const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)nrow_c + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
-    spmv_compact_kernel<4, 6><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_ccell, c->d_rowptr, c->d_col, c->d_val, xc, yc);
+    if (c->blk.nranks > 1) {
+        if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 8 neighbours");
+        const unsigned long long seq = ++c->halo_ll_seq;
+        const int par = (int)(seq & 1ull);
+        if (c->nsend_cells > 0) {
+            ProfScope prof_(c, KID_HALO_PACK);
+            const int pgrid = std::max(1, std::min(ew_grid(c->nsend_cells * NUN), NSM));
+            halo_push_ll_kernel<<<pgrid, 256, 0, c->stream>>>(c->nsend_cells, c->d_send_cidx, c->d_send_dst, c->d_send_peer, xc,
+                                                              (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size(), (unsigned int)seq);
+            c->launches++;
+        }
+        ProfScope prof_(c, KID_SPMV);
+        spmv_compact_kernel<4, 6, true><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                              (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
+    } else {
+        ProfScope prof_(c, KID_SPMV);
+        spmv_compact_kernel<4, 6, false><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                               nullptr, 0u, yc);
+    }
     c->launches++;
+    if (c->ic_on) {   // the dense integral-condition row (THCM.C:2180-2229) on the compact vectors
+        dot_dev(c, nrow_c, c->d_iccoeff_c, xc, c->d_scalars + 4010);
+        const int crow = c->ic_lrow >= 0 ? NUN * c->ccell_host[(size_t)(c->ic_lrow / NUN)] + c->ic_lrow % NUN : -1;
+        fix_spmv_rows_kernel<<<1, 32, 0, c->stream>>>(FixRows{crow, -1, -1}, (double)c->ic_sign, c->d_scalars + 4010, xc, yc);
+        c->launches++;
+    }
     return 0;
 }
 int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y) {

@@ -349,12 +349,13 @@ class THCM:
         self.L_.thcmb_apply_precon_dev(self.ctx, _dev_ptr(v), _dev_ptr(out))
         self.sync()
 
-    def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096, ortho="mgs"):
-        """GMRESSolver::solve (src/gmressolver/GMRESSolver.H:81-255).  Returns (KrylovResult, history)."""
+    def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096, ortho="mgs", full_space=False):
+        """GMRESSolver::solve (src/gmressolver/GMRESSolver.H:81-255).  Returns (KrylovResult, history).  By default the Krylov vectors
+        hold the ocean cells only when b and x vanish on LAND (identity rows); full_space=True keeps full-length vectors."""
         self._pre()
         hist = np.zeros(hist_cap)
         res = KrylovResult()
-        flags = (1 if prec else 0) | (4 if flexible else 0) | (8 if ortho == "dgks" else 0)
+        flags = (1 if prec else 0) | (4 if flexible else 0) | (8 if ortho == "dgks" else 0) | (16 if full_space else 0)
         self.L_.thcmb_gmres(self.ctx, _dev_ptr(b), _dev_ptr(x), tol, maxit, restart, flags, _np_ptr(hist), hist_cap, C.byref(res))
         return res, hist[:res.nhist].copy()
 

@@ -276,7 +276,7 @@ typedef struct thcmb_krylov_result {
 
 /* Restarted right-preconditioned (F)GMRES with modified Gram-Schmidt and Givens rotations: the algorithm of
  * src/gmressolver/GMRESSolver.H:81-255 (minimiser scheme 'B').  d_b, d_x on device; hist (host, may be NULL)
- * receives the scaled residual after every inner iteration.  flags: bit0 precondition, bit2 flexible,
+ * receives the scaled residual after every inner iteration.  flags: bit0 precondition, bit2 flexible, bit4 (16) full-length Krylov vectors (no ocean-only compaction),
  * bit3 batched Gram-Schmidt with the DGKS criterion (the orthogonalisation Belos uses on the reference's production path,
  * Ocean.C:977-1024) instead of the template's modified Gram-Schmidt: 2-4 global reductions per iteration instead of i+2. */
 int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int maxit, int restart, int flags,

@@ -1,15 +1,14 @@
-"""Device code written after the GPU budget of round 1 was spent: compiled and reviewed, host parts verified on the CPU, not yet
-run on a B200 (gated by THCM_RUN_UNVERIFIED=1, see below).
+"""GPU tests of the parts of the path that sit around the core kernels (first run on a B200 in round 2: profiles/r02/pytest_gpu_r02a_ungated.log):
 
 (1) The row replacements THCM::evaluate applies above the Fortran core (THCM.C:1013-1041, 1164-1172, 2180-2296) on the device
 API: salinity integral condition (SRES = 0 -- the configuration of the reference's own test/ocean/ocean_params.xml) and the
 pressure Dirichlet rows.  Checked against a numpy restatement built on the oracle's residual, Jacobian and
 m_thcm_utils::intcond_scaling coefficients.
-(3) The Jacobian kernels with the output staging aliased onto the input stage (THCM_ASM_PIPE=5; more blocks per SM).
-(5) GMRES on the ocean-only (cell-compacted) Krylov space (THCM_KRYLOV_COMPACT=1).
-(4) The SpMV that does not stream the identity rows of LAND cells (THCM_SPMV_SKIP_LAND=1).
-(2) The SpMV with pattern-compressed column indices (THCM_SPMV_PATTERN=1; the host dictionary is verified in
-tests/test_emu_parity.py::test_spmv_column_patterns_reproduce_the_graph)."""
+(2) set_landmask_ and init_ on an MPI sub-domain through the Fortran symbols.
+(3) GMRES on the ocean-only (cell-compacted) Krylov space (the default) against the full-length solve; the Newton step through host
+buffers against the device-resident one.
+(4) The SpMV that does not stream the identity rows of LAND cells.
+(5) The reference's own src/tests/test_ocean.C restated over the C++ mirror."""
 import numpy as np
 import pytest
 
@@ -18,11 +17,7 @@ from cases import PAR_INDEX as P
 
 import os
 
-# Written after the GPU budget of round 1 was spent: the device code is compiled and reviewed but has not run
-# on a B200 yet.  THCM_RUN_UNVERIFIED=1 enables the tests; the first GPU pass of the next round does that and removes the gate.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("THCM_RUN_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU (written after the round's GPU budget was spent); set THCM_RUN_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
 
 
@@ -331,3 +326,31 @@ def test_gmres_on_the_ocean_only_krylov_space(name, ortho, monkeypatch):
     assert np.linalg.norm(s0 - s1) <= 1e-9 * np.linalg.norm(s0)
     land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
     assert np.all(s1[land] == 0.0)
+
+
+@pytest.mark.parametrize("name", ["gateway16", "global4deg"])
+@pytest.mark.parametrize("compact", ["0", "1"])
+def test_newton_step_from_host_buffers_equals_the_device_resident_step(name, compact, monkeypatch):
+    """thcmb_newton_step (H2D state, step, D2H update) must return the dx of thcmb_newton_step_dev bit for bit -- in particular on the
+    ocean-only Krylov space, whose gather / scatter buffers must not alias the update (round-1 advisor finding)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    monkeypatch.setenv("THCM_KRYLOV_COMPACT", compact)
+    s, landm = {"gateway16": cases.gateway16, "global4deg": cases.global4deg}[name]()
+    t = iemic_b200.THCM(s, landm)
+    for k, v in PARS.items():
+        t.setParameter(k, v)
+    t.set_ortho("dgks")
+    x = cases.consistent_state(s, landm, scale=0.05)
+    dx_dev = t.new_vector()
+    res_d, fn_d = t.newton_step_dev(torch.from_numpy(x).cuda(), dx_dev, tol=1e-8, maxit=24, restart=25, precon=1)
+    dx_host = np.full(t.ndim, np.nan)
+    res_h, fn_h = t.newton_step(x, dx_host, tol=1e-8, maxit=24, restart=25, precon=1)
+    assert fn_d == fn_h and res_d.iters == res_h.iters and res_d.resid == res_h.resid
+    assert np.array_equal(dx_host, dx_dev.cpu().numpy())
+    assert np.linalg.norm(dx_host) > 0
+    land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
+    assert np.all(dx_host[land] == 0.0)
+    t.close()

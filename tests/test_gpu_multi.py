@@ -56,6 +56,9 @@ def worker(rank, world, port, name, outdir):
     # batched DGKS orthogonalisation (multi_dot with the fused LL all-reduce over peer memory)
     sol2 = t.new_vector()
     res2, hist2 = t.gmres(F, sol2, tol=1e-8, maxit=30, restart=15, ortho="dgks")
+    # the same solve on full-length vectors (the default above ran on the ocean cells only, halo through the LL slots)
+    sol3 = t.new_vector()
+    res3, hist3 = t.gmres(F, sol3, tol=1e-8, maxit=30, restart=15, ortho="dgks", full_space=True)
     # back-to-back operator applications with no reduction in between: the two alternating halo buffers of the P2P push
     y2, y3 = t.new_vector(), t.new_vector()
     for _ in range(5):
@@ -63,7 +66,7 @@ def worker(rank, world, port, name, outdir):
         t.applyMatrix(y2, y3)
     np.savez(os.path.join(outdir, f"r{rank}.npz"), gid=gid, F=F.cpu().numpy(), val=val, rp=rp, col=col, hg=t.halo_gids(),
              y=y.cpu().numpy(), nrm=nrm, hist=hist, sol=sol.cpu().numpy(), iters=res.iters, hist2=hist2, iters2=res2.iters,
-             y3=y3.cpu().numpy())
+             y3=y3.cpu().numpy(), hist3=hist3, iters3=res3.iters, sol2=sol2.cpu().numpy(), sol3=sol3.cpu().numpy())
     t.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -76,7 +79,7 @@ def test_multi_gpu_reproduces_global_answer(name, tmp_path):
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    world = 2 if ngpu < 4 else 4
+    world = int(os.environ.get("THCM_TEST_WORLD", "0")) or (8 if ngpu >= 8 else 4 if ngpu >= 4 else 2)
     mp.spawn(worker, args=(world, free_port(), name, str(tmp_path)), nprocs=world, join=True)
     s, landm = CASES[name]()
     o = OracleTHCM(s, landm)
@@ -103,6 +106,7 @@ def test_multi_gpu_reproduces_global_answer(name, tmp_path):
     seen = np.zeros(o.ndim, int)
     y_all = np.zeros(o.ndim)
     y3_all = np.zeros(o.ndim)
+    sol2_all = np.zeros(o.ndim); sol3_all = np.zeros(o.ndim)
     for r in range(world):
         d = np.load(tmp_path / f"r{r}.npz")
         gid = d["gid"]
@@ -119,7 +123,12 @@ def test_multi_gpu_reproduces_global_answer(name, tmp_path):
         assert abs(int(d["iters2"]) - res1d.iters) <= 1
         assert np.abs(d["hist2"][:k] - hist1d[:k]).max() <= 1e-10
         y3_all[gid] = d["y3"]
+        # ocean-only Krylov space (default) against full-length vectors on the same ranks
+        k = min(len(d["hist2"]), len(d["hist3"]))
+        assert abs(int(d["iters2"]) - int(d["iters3"])) <= 1 and np.abs(d["hist2"][:k] - d["hist3"][:k]).max() <= 1e-10
+        sol2_all[gid] = d["sol2"]; sol3_all[gid] = d["sol3"]
     assert np.all(seen == 1)
+    assert np.linalg.norm(sol2_all - sol3_all) <= 1e-9 * np.linalg.norm(sol3_all) and np.linalg.norm(sol3_all) > 0
     assert np.linalg.norm(y3_all - y3o) <= 1e-12 * np.linalg.norm(y3o)
     assert np.linalg.norm(y_all - yo) <= 1e-13 * np.linalg.norm(yo)
     t1.close()
