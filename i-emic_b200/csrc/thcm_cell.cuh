@@ -9,6 +9,7 @@
 #pragma once
 #include "thcm_internal.h"
 #include "thcm_slots.h"
+#include "thcm_tanh.h"
 #ifdef __CUDACC__
 #define THCM_HD __host__ __device__ __forceinline__
 #else
@@ -457,13 +458,14 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
 //   mix_T    = (Ftimp(k) - Ftimp(k-1)) / (dz * dfzT(k))                                            (mix_imp.f:517-524)
 // a function of T,S in the cell and its two vertical neighbours only.  tt / ss = T, S at k-1, k, k+1 as usol leaves them;
 // oc[3] = isoc (OCEAN or PERIO) of the three cells.  Operation order follows the reference statement by statement.
-// The only transcendental is tanh: the host tests (tests/emu) run this very code with glibc's tanh and are bit-exact
-// against the oracle; on the device CUDA's tanh may differ in the last bit (see DESIGN.md for the tolerance).
+// The only transcendental is tanh, taken from thcm_tanh.h: one specified algorithm (fdlibm's tanh through expm1, plain IEEE operations)
+// on the device, in the host emulation (tests/emu) and in the oracle, so the term AND its forward-difference Jacobian block (one ulp of
+// tanh is amplified by 1 / eps = 1e8 there) are bit-exact against the oracle on the B200.
 // ---------------------------------------------------------------------------
 struct MixTabs { double dfzT, dfzW, dfzWm; int k; };
 THCM_HD double mix_tprstb(double grad, double fac) {   // mix_imp.f:837-857
     double a = -grad * fac;
-    double th = tanh(a * a * a);
+    double th = fd_tanh(a * a * a);
     return th > 0.0 ? th : 0.0;
 }
 // var = 4: temperature row, 5: salinity row

@@ -25,7 +25,7 @@ def build(force=False):
     """Compiles the oracles (gcc only; the reference Krylov templates only when /root/reference exists)."""
     so = os.path.join(_HERE, "libthcm_oracle.so")
     src = os.path.join(_HERE, "thcm_oracle.cpp")
-    need = force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src)
+    need = force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "fdlibm_tanh.h")))
     kso = os.path.join(_HERE, "_ref", "libkrylov_ref.so")
     ksrc = os.path.join(_HERE, "krylov_ref.cpp")
     if os.path.isdir("/root/reference/src/gmressolver") and (force or not os.path.exists(kso) or os.path.getmtime(kso) < os.path.getmtime(ksrc)):

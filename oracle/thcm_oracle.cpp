@@ -40,8 +40,14 @@
 #include <vector>
 #include <algorithm>
 #include <string>
+#include "fdlibm_tanh.h"
 
 namespace {
+
+// tanh of the mixing tapers (mix_imp.f:675-727, 837-857): 1 = the specified fdlibm algorithm (fdlibm_tanh.h; what the device path
+// implements too), 0 = the platform libm (what a build of the reference on THIS machine would call)
+int g_tanh_impl = 1;
+inline double mix_tanh(double x) { return g_tanh_impl ? oracle_tanh(x) : std::tanh(x); }
 
 // par.F90:14-81
 constexpr double PI = 3.14159265358979323846;
@@ -1235,7 +1241,7 @@ struct Oracle {
     inline double tprstb(double grad, double spl) const {
         double fac = alphaT * spl;
         double a = -grad * fac;
-        return std::max(std::tanh(a * a * a), 0.0);
+        return std::max(mix_tanh(a * a * a), 0.0);
     }
     // mix_imp.f:675-727
     void tprslp(double drdh, double& drdz, double spl, double& slp, double& tpr) const {
@@ -1246,7 +1252,7 @@ struct Oracle {
         double delta = (r0dim / hdim) * spl;
         double sd = width * delta;
         if (tap == 1) { tpr = absslp > delta ? (delta / absslp) * (delta / absslp) : 1.0; }
-        else if (tap == 2) { tpr = 0.5 * (1.0 - std::tanh((absslp - delta) / sd)); }
+        else if (tap == 2) { tpr = 0.5 * (1.0 - mix_tanh((absslp - delta) / sd)); }
         else if (tap == 3) {
             if (absslp < delta - sd && drdz < 0.0) tpr = 1.0;
             else if (absslp >= delta - sd && absslp < delta && drdz < 0.0) { double dum = (absslp - (delta - sd)) / sd; tpr = 1.0 - 3.0 * (dum * dum) + 2.0 * (dum * dum * dum); }
@@ -1657,6 +1663,9 @@ Graph maximal_graph(int N, int M, int L, bool perio) {
 // C ABI for ctypes (tests / bench only)
 // =============================================================================
 extern "C" {
+
+void oracle_set_tanh(int impl) { g_tanh_impl = impl; }
+double oracle_tanh_value(double x) { return oracle_tanh(x); }
 
 struct oracle_settings {
     double hdim, qz, alphaT, alphaS, ymin_glob, ymax_glob;

@@ -15,7 +15,7 @@ _lib = None
 def build(force=False):
     so = os.path.join(_HERE, "libthcm_emu.so")
     srcs = [os.path.join(_HERE, "emu_cell.cpp"), os.path.join(_CSRC, "thcm_host.cpp"), os.path.join(_CSRC, "thcm_probe.cpp")]
-    deps = srcs + [os.path.join(_CSRC, f) for f in ("thcm_cell.cuh", "thcm_internal.h", "thcm_slots.h")] + \
+    deps = srcs + [os.path.join(_CSRC, f) for f in ("thcm_cell.cuh", "thcm_internal.h", "thcm_slots.h", "thcm_tanh.h")] + \
         [os.path.join(_ROOT, "include", "thcm_b200.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"

@@ -101,6 +101,8 @@ void rhs_row(const AsmArgs& a, int cell, double* out) {
 
 extern "C" {
 
+double emu_tanh(double x) { return thcm::fd_tanh(x); }   // the device path's tanh (thcm_tanh.h), compiled for the host
+
 void* emu_create(const thcmb_settings* s, const int* landm) {
     Emu* e = new Emu();
     thcmb_ctx* c = &e->c;

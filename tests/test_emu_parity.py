@@ -84,7 +84,7 @@ def test_model_flags(name, flags):
 @pytest.mark.parametrize("vmix,rho_mixing,xes", [(1, 0, 1.0), (1, 1, 0.0), (2, 0, 0.0)])
 def test_tracer_mixing_bit_exact(name, vmix, rho_mixing, xes):
     """Mixing = 1, 2 (mix_imp.f: implicit vertical mixing / convective adjustment + its forward-difference Jacobian): the
-    device functions, compiled for the host with glibc's tanh, against the oracle's whole-field vmix_fun / vmix_jac."""
+    device functions, compiled for the host (tanh = thcm_tanh.h, the oracle's = oracle/fdlibm_tanh.h: the same specified algorithm), against the oracle's whole-field vmix_fun / vmix_jac."""
     s, landm, o, e = setup(name, pars=dict(cases.DEFAULT_PARS, NLES=xes), vmix=vmix, rho_mixing=rho_mixing)
     x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
     e.vmix_control(x)

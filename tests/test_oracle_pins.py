@@ -320,3 +320,49 @@ def test_newton_from_the_reference_state_converges_quadratically():
     e.vmix_control(x)
     assert np.array_equal(e.rhs(x), o.rhs(x))
     assert np.array_equal(e.jacobian(x), o.jacobian_graph(x)[0])
+
+
+def test_specified_tanh_of_the_mixing_taper():
+    """tprstb's tanh (mix_imp.f:837-857) is the platform libm's in the reference; the device path and the oracle both use ONE specified
+    algorithm instead (fdlibm's tanh through expm1: i-emic_b200/csrc/thcm_tanh.h, oracle/fdlibm_tanh.h -- written independently).
+    Pins: (i) the two restatements agree bit for bit; (ii) against this machine's libm they differ in < 0.1 % of the arguments and by
+    <= 3 ulp (glibc's tanh IS this algorithm, in an FMA-contracted multiarch build here); (iii) the oracle with the platform tanh and
+    with the specified one gives the same residual to 1e-12 of the row scale and the same Jacobian except the forward-difference block
+    (1 / eps = 1e8 amplification: <= 1e-6) -- the spread two builds of the reference itself would show."""
+    import ctypes as C
+    import cases
+    from cases import PAR_INDEX as P
+    from oracle.oracle import OracleTHCM, lib
+    sys_path_emu = os.path.join(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path_emu)
+    from emu import emu
+    L, E = lib(), emu.lib()
+    L.oracle_tanh_value.restype = C.c_double; L.oracle_tanh_value.argtypes = [C.c_double]
+    E.emu_tanh.restype = C.c_double; E.emu_tanh.argtypes = [C.c_double]
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([rng.uniform(-1, 1, 40000) * 2.0 ** rng.integers(-60, 6, 40000),
+                         np.array([0.0, -0.0, 1e-320, 0.5 * np.log(2), 1.5 * np.log(2), 1.0, -1.0, 22.0, -22.0, 21.999, 700.0, np.inf, -np.inf])])
+    a = np.array([L.oracle_tanh_value(float(x)) for x in xs])
+    b = np.array([E.emu_tanh(float(x)) for x in xs])
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    import math
+    ref = np.array([math.tanh(float(x)) for x in xs])      # the platform libm (numpy's own SIMD tanh is yet another algorithm)
+    ulp = np.abs(a.view(np.int64) - ref.view(np.int64))
+    assert ulp.max() <= 3 and (ulp > 0).mean() < 1e-3
+    # the platform tanh against the specified one, through the oracle
+    s, landm = cases.gateway16(vmix=1)
+    o = OracleTHCM(s, landm)
+    for k, v in dict(cases.DEFAULT_PARS, NLES=1.0).items():
+        o.setpar(P[k], v)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    try:
+        L.oracle_set_tanh(1)
+        B1 = o.rhs(x); v1, _ = o.jacobian_graph(x)
+        L.oracle_set_tanh(0)
+        B0 = o.rhs(x); v0, _ = o.jacobian_graph(x)
+    finally:
+        L.oracle_set_tanh(1)
+    scale = np.abs(B1).reshape(-1, 6).max(axis=0) + 1e-300
+    assert (np.abs(B1 - B0).reshape(-1, 6) / scale).max() <= 1e-12
+    assert np.abs(v1 - v0).max() <= 1e-6 * np.abs(v1).max()
