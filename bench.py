@@ -232,7 +232,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = dist.group.WORLD
-    s, landm = cases.global_synth(n, m, l, rank=rank, nranks=world, device=local_rank)
+    balance = 0 if os.environ.get("THCM_BALANCE", "1") == "0" else 1
+    s, landm = cases.global_synth(n, m, l, rank=rank, nranks=world, device=local_rank, balance=balance)
+    config["decomposition"] = ("Decomp2D rank grid, cut lines placed by ocean-cell count (thcmb_settings.balance = 1)" if balance and world > 1
+                               else "Decomp2D, uniform cut lines (TRIOS_Domain.C:258-273)")
     t = iemic_b200.THCM(s, landm, comm)
     for k, v in PARS.items():
         t.setParameter(k, v)

@@ -157,13 +157,14 @@ void thcmb_default_settings(thcmb_settings* s) {
     s->TRES = 1; s->SRES = 1; s->iza = 2; s->ite = 1; s->its = 1; s->coupled_T = 0; s->coupled_S = 0; s->forcing_type = 0;
     s->alphaT = 1.0e-04; s->alphaS = 7.6e-04;               // usr.F90:143-144
     s->rank = 0; s->nranks = 1; s->device = 0;
+    s->balance = 0;                                         // the reference's uniform cut lines
 }
 
 thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     require_device(s->device);
     thcmb_ctx* c = new thcmb_ctx();
     c->s = *s; c->device = s->device;
-    if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) fatal("domain decomposition produced an empty block");
+    if (!setup_block(c, landm_global)) fatal("domain decomposition produced an empty block");
     THCM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     THCM_CUDA(cudaEventCreate(&c->ev0)); THCM_CUDA(cudaEventCreate(&c->ev1));
     for (auto& e : c->ev_slot) THCM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -573,9 +574,18 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
             //      column of H copied to pinned host slot `slot` (async).  MGS follows GMRESSolver.H:177-187 statement by
             //      statement; batched = classical Gram-Schmidt with the DGKS criterion (Belos "DGKS", Ocean.C:977-1024).
             constexpr int S = 80, HSLOT = 256;   // batched dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] ||w||^2, [3S+1] ||w||
+            // fused head (compact space, block-diagonal preconditioner, flexible, batched): the orthogonalisation works in a buffer of
+            // its own (wbuf); the next step's first kernel turns it into V[i+1] = w / ||w|| AND Z[i+1] = M^-1 V[i+1] AND pushes the halo of
+            // Z[i+1] -- scale_invsqrt + blockdiag_apply + halo push in one launch.  V[i+1] of the LAST step of a cycle is never formed:
+            // nothing reads it (the update uses Z[0..i], GMRESSolver.H:293-313).
+            const bool fuse_head = batched && compact && prec && flexible && c->precon_kind == 1 && c->d_minv && !getenv("THCM_NO_FUSED_HEAD");
+            double* const wbuf = fuse_head ? work_vec(c, 3) : nullptr;
             auto enqueue = [&](int i, int slot) {
-                double* w = V(i + 1);
-                if (prec) {
+                double* w = fuse_head ? wbuf : V(i + 1);
+                if (fuse_head && i > 0) {
+                    const unsigned long long seq = scale_precon_push(c, wbuf, c->d_scalars + 3 * S, V(i), Z(i), nullptr);
+                    spmv_compact_rows(c, Z(i), w, seq);
+                } else if (prec) {
                     double* z = flexible ? Z(i) : tmp;
                     applyM(V(i), z);
                     applyA(z, w);
@@ -598,14 +608,14 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     std::vector<double*> vp(nv);
                     for (int k = 0; k < nv; k++) vp[k] = V(k);
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
-                    THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));
+                    const bool fused_cgs2 = (c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0;
+                    if (!fused_cgs2) THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));   // h2 of a skipped second pass
                     multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
-                    if ((c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0) {
+                    if (fused_cgs2) {
                         // CGS2 with the basis read three times instead of four: w' = w - V h1 and h2 = V^T w', w'.w' in ONE sweep
                         // (+ all-reduce + DGKS decision); the second update only when the decision asks for it.  h2 lands in
                         // dh[2S..] and is used by the host only when the flag is set.
                         fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S);
-                        THCM_CUDA(cudaMemcpyAsync(dh + S, dh + 2 * S + nv, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // ww_new
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
                     } else if (c->p2p_on || c->blk.nranks == 1) {
                         // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
@@ -620,7 +630,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                         multi_axpy_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w);
                         dot_dev(c, n, w, w, dh + 3 * S);
                     }
-                    scale_invsqrt_dev(c, n, dh + 3 * S, w, dh + 3 * S + 1);
+                    if (!fuse_head) scale_invsqrt_dev(c, n, dh + 3 * S, w, dh + 3 * S + 1);
                     THCM_CUDA(cudaMemcpyAsync(hs, dh, sizeof(double) * (3 * S + 2), cudaMemcpyDeviceToHost, c->stream));
                     THCM_CUDA(cudaMemcpyAsync(hs + 3 * S + 2, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
                     THCM_CUDA(cudaEventRecord(c->ev_slot[slot], c->stream));
@@ -637,7 +647,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     THCM_CUDA(cudaEventSynchronize(c->ev_slot[slot]));
                     const bool second = *reinterpret_cast<const int*>(hs + 3 * S + 2) != 0;
                     for (int k = 0; k <= i; k++) H[k][i] = hs[k] + (second ? hs[2 * S + k] : 0.0);
-                    H[i + 1][i] = hs[3 * S + 1];
+                    H[i + 1][i] = fuse_head ? std::sqrt(hs[3 * S]) : hs[3 * S + 1];   // (IEEE sqrt: the same bits on host and device)
                     if (second) n_reorth++;
                 }
                 space = i;

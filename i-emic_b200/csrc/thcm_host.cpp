@@ -43,7 +43,7 @@ static constexpr double rhoa = 1.25, ce = 1.3e-03, ch = 0.94 * ce, cpa = 1000., 
 // remainders to the first ranks.  Ghost layers are NOT added here: kernels index globally and use a
 // width-1 halo buffer instead of the reference's 2 overlapping layers (multi-GPU).
 // ---------------------------------------------------------------------------------------------
-bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b) {
+bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b, const Cuts* cuts) {
     int t1 = nprocs, t2 = 1, npM = t1, npN = t2;
     double r, r_min = 100;
     while (t1 > 0) {
@@ -62,6 +62,13 @@ bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b) 
     if (b.pidN < remN) b.n0++;
     b.j0 += std::min(remM, b.pidM);
     b.i0 += std::min(remN, b.pidN);
+    b.cuts = nullptr;
+    if (cuts && cuts->npM == npM && cuts->npN == npN) {   // ocean-weighted cut lines (same rank grid, same rank -> (pidN, pidM) map)
+        b.cuts = cuts;
+        b.j0 = cuts->jc[b.pidM]; b.m0 = cuts->jc[b.pidM + 1] - b.j0;
+        const int* ic = cuts->ic.data() + (size_t)b.pidM * (npN + 1);
+        b.i0 = ic[b.pidN]; b.n0 = ic[b.pidN + 1] - b.i0;
+    }
     b.wrap_x = (periodic && npN == 1) ? 1 : 0;
     b.halo_w = (b.pidN > 0 || (periodic && npN > 1)) ? 1 : 0;
     b.halo_e = (b.pidN < npN - 1 || (periodic && npN > 1)) ? 1 : 0;
@@ -69,6 +76,53 @@ bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b) 
     b.halo_n = b.pidM < npM - 1 ? 1 : 0;
     b.hk = (b.halo_s + b.halo_n) * (b.n0 + b.halo_w + b.halo_e) + (b.halo_w + b.halo_e) * b.m0;
     return b.n0 > 0 && b.m0 > 0;
+}
+
+// prefix-balanced cuts of a weight sequence into `parts` pieces of at least `minw` entries each
+static std::vector<int> balanced_cuts(const std::vector<double>& w, int parts, int minw) {
+    const int len = (int)w.size();
+    std::vector<double> cum(len + 1, 0.0);
+    for (int q = 0; q < len; q++) cum[q + 1] = cum[q] + w[q];
+    std::vector<int> cut(parts + 1, 0);
+    cut[parts] = len;
+    for (int p = 1; p < parts; p++) {
+        const double target = cum[len] * p / parts;
+        const int lo = cut[p - 1] + minw, hi = len - (parts - p) * minw;
+        int best = lo;
+        for (int k = lo; k <= hi; k++) if (std::fabs(cum[k] - target) < std::fabs(cum[best] - target)) best = k;
+        cut[p] = best;
+    }
+    return cut;
+}
+// Ocean-weighted cut lines on the reference's npN x npM rank grid: an OCEAN cell weighs 1 (assembly, SpMV and every Krylov vector
+// operation), a LAND cell 0.05 (its tile is skipped by the assembly kernels, its rows are never streamed).  Deterministic in the global
+// mask, so every rank computes the same cuts.
+void compute_cuts(const int* landm, int N, int M, int L, int nprocs, Cuts& cuts) {
+    Block tmp;
+    decomp2d(nprocs, 0, N, M, L, 0, tmp);
+    const int npN = tmp.npN, npM = tmp.npM;
+    cuts = Cuts();
+    if (N < 2 * npN || M < 2 * npM) return;   // too small to move a cut: uniform
+    std::vector<double> w((size_t)N * M, 0.0);
+    for (int k = 1; k <= L; k++) for (int j = 1; j <= M; j++) for (int i = 1; i <= N; i++)
+        w[(size_t)(j - 1) * N + (i - 1)] += landm[(size_t)i + (size_t)(N + 2) * (j + (size_t)(M + 2) * k)] == OCEAN ? 1.0 : 0.05;
+    std::vector<double> rowsum(M, 0.0);
+    for (int j = 0; j < M; j++) for (int i = 0; i < N; i++) rowsum[j] += w[(size_t)j * N + i];
+    cuts.npN = npN; cuts.npM = npM;
+    cuts.jc = balanced_cuts(rowsum, npM, 2);
+    cuts.ic.assign((size_t)npM * (npN + 1), 0);
+    for (int pm = 0; pm < npM; pm++) {
+        std::vector<double> colsum(N, 0.0);
+        for (int j = cuts.jc[pm]; j < cuts.jc[pm + 1]; j++) for (int i = 0; i < N; i++) colsum[i] += w[(size_t)j * N + i];
+        const std::vector<int> ic = balanced_cuts(colsum, npN, 2);
+        for (int pn = 0; pn <= npN; pn++) cuts.ic[(size_t)pm * (npN + 1) + pn] = ic[pn];
+    }
+}
+bool setup_block(thcmb_ctx* c, const int* landm_global) {
+    const thcmb_settings& s = c->s;
+    c->cuts = Cuts();
+    if (s.balance && s.nranks > 1) compute_cuts(landm_global, s.N, s.M, s.L, s.nranks, c->cuts);
+    return decomp2d(s.nranks, s.rank, s.N, s.M, s.L, s.periodic, c->blk, c->cuts.npM ? &c->cuts : nullptr);
 }
 
 int halo_slot(const Block& b, int ie, int je, int k) {
@@ -585,6 +639,13 @@ static int owner_of(const Block& me, int gi, int gj) {
         int cut = rem * (base + 1);
         return g < cut ? g / (base + 1) : rem + (g - cut) / base;
     };
+    if (me.cuts) {
+        const Cuts& cu = *me.cuts;
+        int pm = 0; while (pm + 1 < cu.npM && gj >= cu.jc[pm + 1]) pm++;
+        const int* ic = cu.ic.data() + (size_t)pm * (cu.npN + 1);
+        int pn = 0; while (pn + 1 < cu.npN && gi >= ic[pn + 1]) pn++;
+        return pm * cu.npN + pn;
+    }
     int pn = find(gi, me.N, me.npN), pm = find(gj, me.M, me.npM);
     return pm * me.npN + pn;
 }
@@ -814,7 +875,7 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
             for (size_t q = 0; q < hslot.size(); q++)
                 if (owner_of(b, hgi[q], hgj[q]) == p) recv_slot.push_back(hslot[q]);
             Block pb;
-            decomp2d(b.nranks, p, N, M, L, b.periodic, pb);
+            decomp2d(b.nranks, p, N, M, L, b.periodic, pb, b.cuts);
             std::vector<int> pgi, pgj, pk, pslot;
             halo_cells(pb, pgi, pgj, pk, pslot);
             for (size_t q = 0; q < pslot.size(); q++)

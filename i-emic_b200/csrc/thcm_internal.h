@@ -62,8 +62,16 @@ struct DevTables {
     double cpl_ooa, cpl_dedt_t, cpl_qtz, cpl_ts, cpl_pq, cpl_zeta, cpl_a0, cpl_rl, cpl_dedt_s;
 };
 
+// Cut lines of the lon x lat block partition.  The reference cuts the index ranges uniformly (TRIOS_Domain.C:258-273) and notes load
+// balancing as "not implemented" (TRIOS_Domain.C:384-392); with LAND = identity rows that costs up to 1.6x at 8 ranks on a global mask
+// (the slowest rank owns 1.6x the mean number of OCEAN cells).  thcmb_settings.balance = 1 keeps the reference's npN x npM rank grid and
+// rectangular blocks but places the cuts by ocean-cell count: latitude cuts jc[0..npM] first, then longitude cuts per latitude band,
+// ic[pm * (npN + 1) + 0..npN].  Empty (npM == 0) = the reference's uniform cuts.
+struct Cuts { int npN = 0, npM = 0; std::vector<int> jc, ic; };
+
 // ---- local block of the global grid (TRIOS_Domain.C:201-315 decomposition, global indexing kept) ----
 struct Block {
+    const Cuts* cuts = nullptr;   // non-uniform cut lines (owned by the context), nullptr = uniform
     int N, M, L;        // global sizes
     int i0, j0;         // 0-based global offset of the first owned cell
     int n0, m0;         // owned cells in x, y (full depth L)
@@ -116,6 +124,7 @@ struct Timer {
 
 struct thcmb_ctx {
     thcmb_settings s;
+    thcm::Cuts cuts;
     thcm::Block blk;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -216,7 +225,7 @@ struct thcmb_ctx {
     double* d_minv = nullptr;       // block-diagonal inverse, 36 per cell
     int precon_kind = 0;
     std::vector<double*> krylov_pool;  // device vectors reused across solves (slots allocated on first use)
-    double* d_work[3] = {nullptr, nullptr, nullptr};   // dx of thcmb_newton_step, compact b / x of thcmb_gmres: never pool slots
+    double* d_work[4] = {nullptr, nullptr, nullptr, nullptr};   // dx of thcmb_newton_step, compact b / x and the Arnoldi work vector of thcmb_gmres: never pool slots
     long long launches = 0;
     std::map<std::string, double> stage_ms;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -247,7 +256,9 @@ namespace thcm {
 // host side (thcm_host.cpp)
 void set_error(const std::string& msg);
 void fatal(const std::string& msg);
-bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b);
+bool decomp2d(int nprocs, int pid, int N, int M, int L, int periodic, Block& b, const Cuts* cuts = nullptr);
+void compute_cuts(const int* landm_global, int N, int M, int L, int nprocs, Cuts& cuts);
+bool setup_block(thcmb_ctx* c, const int* landm_global);   // cuts (when settings.balance) + decomp2d for the context's rank
 void build_grid(thcmb_ctx* c);
 void stpnt(thcmb_ctx* c);
 void apply_landmask_rules(thcmb_ctx* c, const int* landm_in, bool fix_inversion);
@@ -339,6 +350,8 @@ int apply_blockdiag(thcmb_ctx* c, const double* x, double* y);
 int gather_cells(thcmb_ctx* c, const double* in, double* out);
 int scatter_cells(thcmb_ctx* c, const double* in, double* out);
 int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);   // incl. the LL halo push on more than one rank and the integral row
+int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long long seq);   // the SpMV alone: the halo of exchange `seq` was pushed by the caller
+unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out);
 bool compact_possible(const thcmb_ctx* c);
 double land_nonzero_global(thcmb_ctx* c, const double* x);
 int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y);

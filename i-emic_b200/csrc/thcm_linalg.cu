@@ -414,7 +414,7 @@ int p2p_open(thcmb_ctx* c, const void* handles_all) {
         std::vector<void*> pl(2 * std::max<size_t>(c->peers.size(), 1), nullptr);
         for (size_t q = 0; q < c->peers.size(); q++) {
             thcmb_ctx tmp; tmp.blk = Block();
-            if (!decomp2d(c->blk.nranks, c->peers[q].rank, c->blk.N, c->blk.M, c->blk.L, c->blk.periodic, tmp.blk)) fatal("halo push: bad peer block");
+            if (!decomp2d(c->blk.nranks, c->peers[q].rank, c->blk.N, c->blk.M, c->blk.L, c->blk.periodic, tmp.blk, c->blk.cuts)) fatal("halo push: bad peer block");
             const size_t pb = p2p_halo_bytes(&tmp);
             for (int b = 0; b < 2; b++) {
                 ph[b * c->peers.size() + q] = (double*)((char*)ptrs[c->peers[q].rank] + P2P_HALO_OFFSET + b * pb);
@@ -1081,7 +1081,7 @@ __global__ void halo_unpack_kernel(int ncells, const int* __restrict__ slot, con
 // last block to finish publishes a sequence flag in every neighbour's mailbox and waits for theirs, so the halo is complete
 // when the kernel ends.  Two halo buffers alternate by the parity of the sequence number: a neighbour that runs ahead
 // writes exchange s+1 into the other buffer while this rank still reads exchange s.
-constexpr int HALO_MAX_PEERS = 8;
+constexpr int HALO_MAX_PEERS = 16;   // per-band longitude cuts: a north / south edge can touch several blocks
 struct HaloPeers { int n; int rank[HALO_MAX_PEERS]; unsigned char send[HALO_MAX_PEERS], recv[HALO_MAX_PEERS]; };
 __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* __restrict__ idx, const int* __restrict__ dst_slot,
                                                          const int* __restrict__ peer, const double* __restrict__ x, double* const* peer_halo,
@@ -1190,7 +1190,7 @@ int halo_wait(thcmb_ctx* c) {
 int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
     if (c->blk.nranks == 1) return 0;
     if (c->halo_p2p) {
-        if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 8 neighbours");
+        if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 16 neighbours");
         if ((((uintptr_t)d_x) & 15) != 0) fatal("halo push: vector must be 16-byte aligned");
         HaloPeers hp = halo_peers(c);
         const unsigned long long seq = ++c->halo_seq;
@@ -1439,6 +1439,75 @@ __global__ void blockdiag_apply_compact_kernel(int nc, const int* __restrict__ o
     for (int q = 0; q < NUN; q++) s += M[q] * xc[q];
     y[t] = s;
 }
+// Head of an Arnoldi step in ONE kernel (compact space, 6x6 block-diagonal preconditioner, flexible GMRES):
+//   v = w / sqrt(nrm2)   (GMRESSolver.H:185-186, the tail of the previous step),   z = M^-1 v   (:160-164),
+//   and the halo of z pushed into the neighbours' LL buffers for the SpMV that follows.
+// w is only read (the orthogonalisation works in a buffer of its own), so the blocks that push -- they recompute z for the cells of the
+// send lists, ~2 % of the block -- need no ordering against the blocks that sweep the vector.  Replaces scale_invsqrt +
+// blockdiag_apply + halo_push: three launches and one pass over the vector less per iteration.
+constexpr int SPP_CELLS = 32, SPP_THREADS = SPP_CELLS * NUN;
+__global__ void __launch_bounds__(SPP_THREADS) scale_precon_push_kernel(int nc, const int* __restrict__ ocell, const double* __restrict__ minv,
+                                                                        const double* __restrict__ nrm2, const double* __restrict__ w,
+                                                                        double* __restrict__ v, double* __restrict__ z, double* nrm_out,
+                                                                        int main_blocks, int nsend, const int* __restrict__ cidx,
+                                                                        const int* __restrict__ dst_slot, const int* __restrict__ peer,
+                                                                        P2PSlot* const* peer_ll, unsigned int flag) {
+    __shared__ double sv[SPP_THREADS];
+    const double nrm = sqrt(*nrm2);
+    const double a = 1.0 / nrm;
+    const int r = threadIdx.x % NUN, lc = threadIdx.x / NUN;
+    if ((int)blockIdx.x < main_blocks) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
+        for (int c0 = blockIdx.x * SPP_CELLS; c0 < nc; c0 += main_blocks * SPP_CELLS) {
+            const int t = c0 * NUN + threadIdx.x;
+            const bool ok = t < nc * NUN;
+            const double vi = ok ? a * w[t] : 0.0;
+            sv[threadIdx.x] = vi;
+            __syncthreads();
+            if (ok) {
+                const double* M = minv + (size_t)__ldg(ocell + c0 + lc) * 36 + r * NUN;
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < NUN; q++) s += M[q] * sv[lc * NUN + q];
+                v[t] = vi;
+                z[t] = s;
+            }
+            __syncthreads();
+        }
+    } else {
+        const int pb = blockIdx.x - main_blocks, npb = gridDim.x - main_blocks;
+        for (int q0 = pb * SPP_CELLS; q0 < nsend; q0 += npb * SPP_CELLS) {
+            const int q = q0 + lc;
+            if (q < nsend) {
+                const int ci = __ldg(cidx + q);
+                double s = 0.0;
+                if (ci >= 0) {
+                    const double* M = minv + (size_t)__ldg(ocell + ci) * 36 + r * NUN;
+#pragma unroll
+                    for (int k = 0; k < NUN; k++) s += M[k] * (a * w[(size_t)NUN * ci + k]);
+                }
+                ll_store(peer_ll[__ldg(peer + q)] + (size_t)NUN * __ldg(dst_slot + q) + r, s, flag);
+            }
+        }
+    }
+}
+unsigned long long ll_exchange_begin(thcmb_ctx* c);
+// returns the sequence number of the exchange it started (0 on one rank); the caller hands it to spmv_compact_rows
+unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out) {
+    const unsigned long long seq = ll_exchange_begin(c);
+    const int nc = c->n_ocell;
+    const int main_blocks = std::max(1, std::min((nc + SPP_CELLS - 1) / SPP_CELLS, NSM * 8));
+    const bool push = c->blk.nranks > 1 && c->nsend_cells > 0;
+    const int push_blocks = push ? std::max(1, std::min((c->nsend_cells + SPP_CELLS - 1) / SPP_CELLS, NSM)) : 0;
+    const int par = (int)(seq & 1ull);
+    ProfScope prof_(c, KID_PRECON_APPLY);
+    scale_precon_push_kernel<<<main_blocks + push_blocks, SPP_THREADS, 0, c->stream>>>(
+        nc, c->d_ocell, c->d_minv, d_nrm2, w, v, z, d_nrm_out, main_blocks, push ? c->nsend_cells : 0, c->d_send_cidx, c->d_send_dst,
+        c->d_send_peer, push ? (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size() : nullptr, (unsigned int)seq);
+    c->launches++;
+    return seq;
+}
+
 int gather_cells(thcmb_ctx* c, const double* in, double* out) {
     if (in == out) fatal("gather_cells: in-place gather is not supported");
     ProfScope prof_(c, KID_COPY);
@@ -1463,20 +1532,31 @@ double land_nonzero_global(thcmb_ctx* c, const double* x) {
     THCM_CUDA(cudaStreamSynchronize(c->stream));
     return cnt;
 }
+// One exchange of the LL halo = one sequence number; the push may come from halo_push_ll_kernel or from the kernel that produced
+// the vector (scale_precon_push_kernel), the consumer is always the compact SpMV of the same sequence number.
+unsigned long long ll_exchange_begin(thcmb_ctx* c) {
+    if (c->blk.nranks <= 1) return 0ull;
+    if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 16 neighbours");
+    return ++c->halo_ll_seq;
+}
+int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long long seq);
 int spmv_compact(thcmb_ctx* c, const double* xc, double* yc) {
+    const unsigned long long seq = ll_exchange_begin(c);
+    if (c->blk.nranks > 1 && c->nsend_cells > 0) {
+        const int par = (int)(seq & 1ull);
+        ProfScope prof_(c, KID_HALO_PACK);
+        const int pgrid = std::max(1, std::min(ew_grid(c->nsend_cells * NUN), NSM));
+        halo_push_ll_kernel<<<pgrid, 256, 0, c->stream>>>(c->nsend_cells, c->d_send_cidx, c->d_send_dst, c->d_send_peer, xc,
+                                                          (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size(), (unsigned int)seq);
+        c->launches++;
+    }
+    return spmv_compact_rows(c, xc, yc, seq);
+}
+int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long long seq) {
     const int nrow_c = c->n_ocell * NUN, rows_per_block = SPMV_THREADS / 4;
     const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)nrow_c + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
     if (c->blk.nranks > 1) {
-        if ((int)c->peers.size() > HALO_MAX_PEERS) fatal("halo push: more than 8 neighbours");
-        const unsigned long long seq = ++c->halo_ll_seq;
         const int par = (int)(seq & 1ull);
-        if (c->nsend_cells > 0) {
-            ProfScope prof_(c, KID_HALO_PACK);
-            const int pgrid = std::max(1, std::min(ew_grid(c->nsend_cells * NUN), NSM));
-            halo_push_ll_kernel<<<pgrid, 256, 0, c->stream>>>(c->nsend_cells, c->d_send_cidx, c->d_send_dst, c->d_send_peer, xc,
-                                                              (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size(), (unsigned int)seq);
-            c->launches++;
-        }
         ProfScope prof_(c, KID_SPMV);
         spmv_compact_kernel<4, 6, true><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
                                                                               (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);

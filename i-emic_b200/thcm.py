@@ -36,7 +36,7 @@ class Settings(C.Structure):
                 ("coupled_T", C.c_int), ("coupled_S", C.c_int), ("forcing_type", C.c_int),
                 ("alphaT", C.c_double), ("alphaS", C.c_double),
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
-                ("ymin_glob", C.c_double), ("ymax_glob", C.c_double)]
+                ("ymin_glob", C.c_double), ("ymax_glob", C.c_double), ("balance", C.c_int)]
 
     PI = 3.14159265358979323846  # THCMdefs.H:19
 

@@ -184,6 +184,10 @@ typedef struct thcmb_settings {
     /* latitude bounds of the GLOBAL domain when this context is one sub-domain of an MPI-decomposed run that calls the
      * Fortran symbols per rank (temfun / salfun use m_global's ymin, ymax, forcing.F90:418-449); both 0 = same as ymin, ymax */
     double ymin_glob, ymax_glob;
+    /* 0: the reference's uniform cut lines (TRIOS_Domain.C:258-273); 1: same rank grid and rectangular blocks, cut lines placed by
+     * OCEAN-cell count (the reference's "load balancing: not implemented", TRIOS_Domain.C:384-392) -- LAND cells are identity rows and
+     * cost almost nothing, so uniform cuts leave the slowest of 8 ranks with 1.6x the mean work on a global mask */
+    int balance;
 } thcmb_settings;
 
 void thcmb_default_settings(thcmb_settings* s);

@@ -18,7 +18,6 @@ if what == "asm":
         t.buildPreconditioner(1)
         t.applyPrecon(y, F)
 else:
-    t.newton_step_dev(x, dx, tol=0.0, maxit=29, restart=30, precon=1)
-    t.newton_step_dev(x, dx, tol=0.0, maxit=29, restart=30, precon=1)
+    t.newton_step_dev(x, dx, tol=0.0, maxit=49, restart=50, precon=1)
 torch.cuda.synchronize()
 print("done")

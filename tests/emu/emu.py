@@ -181,6 +181,17 @@ class EmuTHCM:
         p = np.ascontiguousarray(p, dtype=np.float64); assert p.size == 7
         self.L_.emu_set_seaice(self.h, _p(p))
 
+    @staticmethod
+    def block_only(s, landm):
+        """(i0, j0, n0, m0, npN, npM) of rank s.rank without building a model."""
+        out = np.zeros(6, dtype=np.int32)
+        lm = np.ascontiguousarray(landm, dtype=np.int32)
+        L = lib()
+        L.emu_block_only.restype = C.c_int
+        L.emu_block_only.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        assert L.emu_block_only(C.byref(s), _p(lm), _p(out)) == 0
+        return tuple(out.tolist())
+
     def block(self):
         out = np.zeros(9, dtype=np.int32)
         self.L_.emu_block(self.h, _p(out))

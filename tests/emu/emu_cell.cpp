@@ -107,7 +107,7 @@ void* emu_create(const thcmb_settings* s, const int* landm) {
     Emu* e = new Emu();
     thcmb_ctx* c = &e->c;
     c->s = *s;
-    if (!decomp2d(s->nranks, s->rank, s->N, s->M, s->L, s->periodic, c->blk)) { delete e; return nullptr; }
+    if (!setup_block(c, landm)) { delete e; return nullptr; }
     build_grid(c); stpnt(c); apply_landmask_rules(c, landm, false); vmix_init(c); init_surface_fields(c);
     build_static_host(c, e->nbmask, e->surf, e->uvlive, e->send_idx, e->recv_slot);
     compute_forcing(c); compute_tables(c); compute_cob(c);
@@ -181,6 +181,13 @@ double emu_get_par(void* h, int idx) { return ((Emu*)h)->c.par[idx]; }
 int emu_ndim(void* h) { return ((Emu*)h)->c.blk.ndim(); }
 long long emu_gnnz(void* h) { return ((Emu*)h)->c.gnnz; }
 int emu_halo_size(void* h) { return NUN * ((Emu*)h)->c.blk.nhalo_cells(); }
+// the block of settings->rank alone (decomposition incl. ocean-weighted cut lines), without building a model
+int emu_block_only(const thcmb_settings* s, const int* landm, int* out) {
+    thcmb_ctx c; c.s = *s;
+    if (!setup_block(&c, landm)) return -1;
+    const Block& b = c.blk; int v[] = {b.i0, b.j0, b.n0, b.m0, b.npN, b.npM}; memcpy(out, v, sizeof(v));
+    return 0;
+}
 void emu_block(void* h, int* out) { const Block& b = ((Emu*)h)->c.blk; int v[] = {b.i0, b.j0, b.n0, b.m0, b.npN, b.npM, b.pidN, b.pidM, b.hk}; memcpy(out, v, sizeof(v)); }
 void emu_graph(void* h, int* rowptr, int* col) {
     thcmb_ctx* c = &((Emu*)h)->c;

@@ -110,7 +110,8 @@ def test_mixing_partition_follows_the_fields():
 
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "box_np", "box_p_open"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):
+@pytest.mark.parametrize("balance", [0, 1])
+def test_decomposed_blocks_reproduce_the_global_answer(name, nranks, balance):
     """Every rank's block, with its halo filled from the global state, must give exactly the owned rows of the 1-rank
     answer (the multi-GPU path reproduces the global result on any GPU count)."""
     s, landm, o, _ = setup(name)
@@ -121,7 +122,7 @@ def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):
     bo, jo, co, cob = o.matrix(x)
     seen = np.zeros(o.ndim, int)
     for rank in range(nranks):
-        sr, _ = CASES[name](rank=rank, nranks=nranks)
+        sr, _ = CASES[name](rank=rank, nranks=nranks, balance=balance)   # 1: ocean-weighted cut lines instead of the reference's uniform ones
         e = EmuTHCM(sr, landm)
         for k, v in PARS.items():
             e.setpar(P[k], v)
@@ -159,12 +160,13 @@ def test_decomposed_blocks_reproduce_the_global_answer(name, nranks):
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 @pytest.mark.parametrize("name", ["gateway16", "box_np", "global4deg"])
-def test_halo_plan_is_consistent(name, nranks):
+@pytest.mark.parametrize("balance", [0, 1])
+def test_halo_plan_is_consistent(name, nranks, balance):
     """What rank p packs for rank q is exactly what q unpacks, slot by slot (global ids match)."""
     _, landm = CASES[name]()
     emus = []
     for rank in range(nranks):
-        sr, _ = CASES[name](rank=rank, nranks=nranks)
+        sr, _ = CASES[name](rank=rank, nranks=nranks, balance=balance)
         emus.append(EmuTHCM(sr, landm))
     plans = [e.plan() for e in emus]
     for p, e in enumerate(emus):
@@ -186,6 +188,26 @@ def test_halo_plan_is_consistent(name, nranks):
         used = np.unique(np.nonzero(hg[:, 0] >= 0)[0])
         assert set(used).issubset(set(recv.tolist()))
         assert len(set(recv.tolist())) == len(recv)
+
+
+def test_ocean_weighted_cut_lines_balance_the_global_grids():
+    """thcmb_settings.balance = 1: same rank grid as the reference's Decomp2D, rectangular blocks that tile the domain, cut lines
+    placed by OCEAN-cell count.  On the synthetic 1-degree mask the slowest of 8 ranks owns 1.62x the mean number of ocean cells with
+    the reference's uniform cuts and <= 1.05x with the weighted ones."""
+    s0, landm = cases.global_synth(360, 152, 24)
+    ocean = (landm[1:-1, 1:-1, 1:-1] == 0)
+    for nranks, worst_uniform in ((2, 1.15), (4, 1.29), (8, 1.60)):
+        out = {}
+        for balance in (0, 1):
+            cnt, cover = [], np.zeros((152, 360), int)
+            for r in range(nranks):
+                s, _ = cases.global_synth(360, 152, 24, rank=r, nranks=nranks, balance=balance)
+                i0, j0, n0, m0, npN, npM = EmuTHCM.block_only(s, landm)
+                cover[j0:j0 + m0, i0:i0 + n0] += 1
+                cnt.append(ocean[:, j0:j0 + m0, i0:i0 + n0].sum())
+            assert np.all(cover == 1)
+            out[balance] = max(cnt) / np.mean(cnt)
+        assert out[0] >= worst_uniform and out[1] <= 1.05, out
 
 
 def test_decomp2d_matches_reference_rule():

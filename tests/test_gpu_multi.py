@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
 
 PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
 CASES = {"gateway16": cases.gateway16, "global4deg": cases.global4deg,
+         "global4deg_balanced": lambda **kw: cases.global4deg(balance=1, **kw),     # ocean-weighted cut lines
+         "gateway16_balanced": lambda **kw: cases.gateway16(balance=1, **kw),
          "box_np": lambda **kw: cases.box(12, 10, 4, False, seed=2, land_frac=0.3, **kw)}
 
 

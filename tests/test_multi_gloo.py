@@ -16,7 +16,7 @@ import cases
 from cases import PAR_INDEX as P
 
 PARS = dict(cases.DEFAULT_PARS, NLES=1.0)
-CASES = {"gateway16": cases.gateway16, "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
+CASES = {"gateway16": cases.gateway16, "gateway16_balanced": lambda **kw: cases.gateway16(balance=1, **kw), "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
          "box_p": lambda **kw: cases.box(9, 8, 3, True, seed=7, land_frac=0.25, **kw)}
 
 
@@ -70,7 +70,7 @@ def worker(rank, world, port, name, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("gateway16", 2), ("box_np", 2), ("box_p", 2), ("gateway16", 4)])
+@pytest.mark.parametrize("name,world", [("gateway16", 2), ("box_np", 2), ("box_p", 2), ("gateway16", 4), ("gateway16_balanced", 4)])
 def test_two_rank_gloo_matches_global_oracle(name, world, tmp_path):
     from oracle.oracle import OracleTHCM
     port = free_port()
