@@ -80,8 +80,13 @@ void build_static(thcmb_ctx* c) {
     std::vector<TileDesc> tdesc;
     build_tile_descs(c, nbmask, surf, uvlive, tdesc);
     upload(c->d_tdesc, tdesc);
+    {   // tiles the Jacobian kernels revisit on every assembly: all but the all-LAND ones (state-independent identity rows)
+        std::vector<int> active;
+        for (size_t q = 0; q < tdesc.size(); q++) if (!(tdesc[q].flags & 4u)) active.push_back((int)q);
+        upload(c->d_active_tiles, active); c->n_active_tiles = (int)active.size();
+        c->land_tiles_written = false;   // d_val is rebuilt below
+    }
     upload(c->d_rowptr, c->rowptr_host); upload(c->d_col, c->col_host);
-    upload(c->d_rowpat, c->rowpat_host); upload(c->d_patrel, c->patrel_host);
     upload(c->d_ocell, c->ocell_host); upload(c->d_ccell, c->ccell_host); c->n_ocell = (int)c->ocell_host.size();
     upload(c->d_colc, c->colc_host); upload(c->d_send_cidx, c->send_cidx_host);
     std::vector<int>().swap(c->colc_host);   // as large as the graph's column array: the device copy is the one that is used
@@ -92,20 +97,6 @@ void build_static(thcmb_ctx* c) {
     }
     upload(c->d_send_idx, send_idx); upload(c->d_recv_slot, recv_slot);
     upload(c->d_send_dst, c->send_dst_host); upload(c->d_send_peer, c->send_peer_host);
-    {   // boundary cells (a stencil neighbour lies in the halo) and their rows, for the SpMV split around the exchange
-        const Block& b = c->blk;
-        std::vector<unsigned char> bcell((size_t)std::max(b.ncell(), 1), 0);
-        std::vector<int> brows;
-        for (int k = 0; k < b.L; k++) for (int lj = 0; lj < b.m0; lj++) for (int li = 0; li < b.n0; li++) {
-            const bool edge = (b.halo_w && li == 0) || (b.halo_e && li == b.n0 - 1) || (b.halo_s && lj == 0) || (b.halo_n && lj == b.m0 - 1);
-            if (!edge) continue;
-            const int cell = (k * b.m0 + lj) * b.n0 + li;
-            bcell[cell] = 1;
-            for (int r = 0; r < NUN; r++) brows.push_back(NUN * cell + r);
-        }
-        c->n_brows = (int)brows.size();
-        upload(c->d_bcell, bcell); upload(c->d_brows, brows);
-    }
     if (c->d_val) cudaFree(c->d_val);
     THCM_CUDA(cudaMalloc(&c->d_val, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
     THCM_CUDA(cudaMemset(c->d_val, 0, sizeof(double) * (size_t)std::max<long long>(c->gnnz, 1)));
@@ -175,9 +166,6 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     init_surface_fields(c);   // allocate_usr + atmos_coef (usrc.F90:118-134)
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
-    if (const char* e = getenv("THCM_SPMV_OVERLAP")) c->spmv_overlap = atoi(e);
-    if (const char* e = getenv("THCM_SPMV_PATTERN")) c->spmv_pattern = atoi(e);
-    if (const char* e = getenv("THCM_SPMV_SKIP_LAND")) c->spmv_skip_land = atoi(e);
     if (const char* e = getenv("THCM_KRYLOV_COMPACT")) c->krylov_compact = atoi(e);
     c->fused_cgs2 = 2;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
     if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
@@ -203,12 +191,12 @@ void thcmb_destroy(thcmb_ctx* c) {
     nccl_destroy(c);
     for (void* p : {(void*)c->d_jt, (void*)c->d_kt, (void*)c->d_nbmask, (void*)c->d_surf, (void*)c->d_uvlive, (void*)c->d_frc,
                     (void*)c->d_rowptr, (void*)c->d_col, (void*)c->d_val, (void*)(c->halo_p2p ? nullptr : c->d_halo), (void*)c->d_sendbuf,
-                    (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter, (void*)c->d_bcell, (void*)c->d_brows,
+                    (void*)c->d_recvbuf, (void*)c->d_send_dst, (void*)c->d_send_peer, (void*)c->d_halo_counter,
                     (void*)c->d_send_idx, (void*)c->d_recv_slot, (void*)c->d_un, (void*)c->d_tmp, (void*)c->d_partial,
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
-                    (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff, (void*)c->d_rowpat, (void*)c->d_patrel,
+                    (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff,
                     (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell, (void*)c->d_colc, (void*)c->d_send_cidx,
-                    (void*)c->d_iccoeff_c})
+                    (void*)c->d_iccoeff_c, (void*)c->d_active_tiles})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) if (p) cudaFree(p);
     for (double* p : c->d_work) if (p) cudaFree(p);
@@ -407,14 +395,6 @@ long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, 
 }
 
 int thcmb_spmv_dev(thcmb_ctx* c, const double* d_x, double* d_y) {
-    if (c->halo_p2p && c->blk.nranks > 1 && c->spmv_overlap) {
-        // push my boundary cells to the neighbours, run the rows that need no halo while theirs arrive, then the rest
-        halo_exchange(c, d_x, false);
-        spmv_part(c, 0, d_x, d_y);
-        halo_wait(c);
-        spmv_part(c, 1, d_x, d_y);
-        return fix_spmv_rows(c, d_x, d_y);
-    }
     halo_exchange(c, d_x);
     spmv(c, c->blk.ndim(), c->d_rowptr, c->d_col, c->d_val, d_x, c->d_halo, c->blk.ndim(), d_y);
     return fix_spmv_rows(c, d_x, d_y);        // the dense integral-condition row: one more dot product, only when enabled
@@ -474,35 +454,6 @@ double thcmb_last_stage_ms(const thcmb_ctx* c, const char* label) {
 // The MGS chain runs without host syncs: every projection coefficient stays in device memory and is
 // consumed by the next fused (axpy + dot) kernel; one small D2H per iteration brings column i of H.
 // =============================================================================
-// Optional L2 residency hint (THCM_L2_PERSIST=1): pins the vector that an MGS chain rewrites i+2 times in the persisting
-// part of the 126 MB L2, so that only the basis vectors stream from HBM.
-static void l2_persist(thcmb_ctx* c, const void* base, size_t bytes) {
-    static int enabled = -1;
-    static size_t max_win = 0;
-    if (enabled < 0) {
-        const char* e = getenv("THCM_L2_PERSIST");
-        enabled = (e && atoi(e) != 0) ? 1 : 0;
-        if (enabled) {
-            cudaDeviceProp p; int dev = 0;
-            cudaGetDevice(&dev); cudaGetDeviceProperties(&p, dev);
-            size_t want = std::min<size_t>((size_t)p.persistingL2CacheMaxSize, (size_t)96 << 20);
-            if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) enabled = 0;
-            max_win = std::min<size_t>(want, (size_t)p.accessPolicyMaxWindowSize);
-            fprintf(stderr, "thcm_b200: L2 persistence %s (persisting max %zu MB, window max %zu MB)\n", enabled ? "on" : "off",
-                    (size_t)p.persistingL2CacheMaxSize >> 20, (size_t)p.accessPolicyMaxWindowSize >> 20);
-        }
-    }
-    if (!enabled) return;
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    attr.accessPolicyWindow.num_bytes = base ? std::min(bytes, max_win) : 0;
-    attr.accessPolicyWindow.hitRatio = base ? (float)std::min(1.0, (double)max_win / (double)std::max<size_t>(bytes, 1)) : 0.f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-}
-
 static void gen_rot(double& dx, double& dy, double& cs, double& sn) {  // GMRESSolver.H:258-279
     if (dy == 0.0) { cs = 1.0; sn = 0.0; }
     else if (std::abs(dy) > std::abs(dx)) { double t = dx / dy; sn = 1.0 / sqrt(1.0 + t * t); cs = t * sn; }
@@ -595,13 +546,11 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                 double* hs = c->h_scalars + (size_t)slot * HSLOT;
                 if (!batched) {
                     // dh[k] = H[k][i], dh[i+1] = ||w||^2, dh[i+2] = ||w||
-                    l2_persist(c, w, (size_t)n * sizeof(double));   // w is re-read and re-written by every kernel of the chain
                     dot_dev(c, n, w, V(0), dh + 0);
                     for (int k = 0; k < i; k++) mgs_step_dev(c, n, dh + k, V(k), V(k + 1), w, dh + k + 1);
                     axpy_negdev(c, n, dh + i, V(i), w);
                     dot_dev(c, n, w, w, dh + i + 1);
                     scale_invsqrt_dev(c, n, dh + i + 1, w, dh + i + 2);  // V[i+1] = w / ||w||
-                    l2_persist(c, nullptr, 0);
                     THCM_CUDA(cudaMemcpyAsync(c->h_scalars, dh, sizeof(double) * (i + 3), cudaMemcpyDeviceToHost, c->stream));
                 } else {
                     const int nv = i + 1;

@@ -302,25 +302,12 @@ __global__ void __launch_bounds__(32 * mode_warps(MODE)) thcm_assemble_kernel(co
 
 
 // =============================================================================
-// Persistent, TMA-pipelined Jacobian kernel (MODE_JAC_GRAPH).
-//
-// One CTA = 5 consumer warps (row types u | v | w+p | T | S for the 32 cells of a tile) + a loader warp + a storer
-// warp, looping over tiles; no __syncthreads in the steady state, all hand-offs go through mbarriers:
-//   loader  : per tile, cp.async.bulk (TMA) of the 9 grid lines of raw 48-byte state records (1 run per line, 2-3 at
-//             the periodic seam / block edges), the tile descriptor (neighbour masks, usol liveness bits) and the j / k
-//             table records into stage s; waits for the bytes (mbarrier complete_tx), applies usol's no-slip / lid
-//             zeroing in place from the descriptor bits, then signals `ready[s]`.  Runs one tile ahead of the consumers.
-//   consumer: waits `ready[s]`, evaluates its row(s) from shared memory into registers, releases the stage (`empty[s]`),
-//             applies `boundaries` + the drop threshold, waits until the previous tile's values have left the output
-//             staging (`outempty`), writes its entries at their final graph offsets, signals `outfull`.
-//   storer  : waits `outfull`, sends the tile out with one 832-byte TMA bulk store per cell, signals `outempty` when
-//             the TMA unit has read the staging.
-// Clipped tiles (k = 1 / k = L planes, non-periodic edges) leave through a coalesced generic copy by the consumers.
+// TMA staging helpers of the Jacobian kernels: grid lines of raw 48-byte state records, the tile descriptor and the j / k table
+// records arrive by cp.async.bulk into one Stage, completion through an mbarrier.
+// (A persistent, warp-specialised variant -- loader warp, five consumer warps, storer warp, double-buffered stages -- was built and
+// measured in round 1: 2x SLOWER than one block per tile, instruction-fetch bound with five row-type instruction streams per CTA;
+// removed in round 2)
 // =============================================================================
-constexpr int PIPE_NSTAGE = 2;
-constexpr int PIPE_CONS = 5;
-constexpr int PIPE_THREADS = 32 * (PIPE_CONS + 2);
-
 // LINES: bit r set = grid line r = (dk+1)*3 + (dj+1) of the 3x3 neighbourhood is staged (compacted in bit order)
 constexpr __host__ __device__ int popc9(int m) { int c = 0; for (int i = 0; i < 9; i++) c += (m >> i) & 1; return c; }
 template <int LINES> struct alignas(16) Stage {
@@ -331,25 +318,6 @@ template <int LINES> struct alignas(16) Stage {
     double tj[J_COUNT][JREC];
     double tk[K_COUNT];
 };
-using PipeStage = Stage<0x1ff>;
-static_assert(sizeof(PipeStage) % 16 == 0 && offsetof(PipeStage, desc) % 16 == 0 && offsetof(PipeStage, tj) % 16 == 0 &&
-              offsetof(PipeStage, tk) % 16 == 0, "bulk-copy destinations must be 16-byte aligned");
-struct alignas(16) PipeSmem {
-    PipeStage st[PIPE_NSTAGE];
-    double v[TI * VSTRIDE];
-    int cstart[TI + 2];
-    int outinfo[4];                // g0, ncell, fast
-    unsigned long long bar_raw[PIPE_NSTAGE], bar_ready[PIPE_NSTAGE], bar_empty[PIPE_NSTAGE], bar_outfull, bar_outempty;
-#ifdef THCM_PIPE_DEBUG
-    volatile int prog[8][32];
-#endif
-};
-#ifdef THCM_PIPE_DEBUG
-#define PROG(pt) sh.prog[threadIdx.x >> 5][lane] = (pt);
-#else
-#define PROG(pt)
-#endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -368,7 +336,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity, int tag = 
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
         if ((++polls & 255u) == 0 && clock64() - t0 > (tag == 4 ? 1000000000ll : (tag == 1 || tag == 3) ? 2000000000ll : 4000000000ll)) {           // a lost hand-off must fail loudly, never hang the GPU
-            if ((threadIdx.x & 31) == 0) printf("thcm_jac_pipe: block %d warp %d stuck at wait %d (parity %u)\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
+            if ((threadIdx.x & 31) == 0) printf("thcm_jac_tma: block %d warp %d stuck at wait %d (parity %u)\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
             __trap();
         }
     }
@@ -437,170 +405,6 @@ __device__ __forceinline__ void pipe_emit(const AsmArgs& a, double* v, const Til
     }
 }
 
-template <int RA, int RB>
-__device__ __forceinline__ void pipe_consumer(const AsmArgs& a, PipeSmem& sh, int lane) {
-    constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
-        const int s = it % PIPE_NSTAGE;
-        const uint32_t n = it / PIPE_NSTAGE;
-        PipeStage& st = sh.st[s];
-        const TileGeom g = tile_geom_of(a.b, tile);
-        mbar_wait(&sh.bar_ready[s], n & 1, 1);
-        const uint32_t nb = st.desc.nbmask[lane];
-        const double sm = (double)((st.desc.surfbits >> lane) & 1u);
-        const bool fast = (st.desc.flags & 1u) != 0, open_ocean = (st.desc.flags & 2u) != 0;
-        // every cell of the tile away from the domain faces: graph positions are compile-time constants
-        const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
-        const int g0 = st.desc.g0, tot = st.desc.tot;
-        double EA[NA], EB[NB];
-        PROG(1)
-        pipe_eval<RA, true>(a, st, g, lane, nb, sm, EA);
-        if constexpr (RB != RA) pipe_eval<RB, true>(a, st, g, lane, nb, sm, EB);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.bar_empty[s]);          // the stage may be refilled
-        PROG(2)
-        pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-        if constexpr (RB != RA) pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-        PROG(3)
-        if (it >= 1) mbar_wait(&sh.bar_outempty, (it - 1) & 1, 2); // previous tile has left the output staging
-        pipe_emit<RA>(a, sh.v, g, lane, interior, EA);
-        PROG(4)
-        if constexpr (RB != RA) pipe_emit<RB>(a, sh.v, g, lane, interior, EB);
-        PROG(5)
-        if (fast) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // STS visible to the TMA unit
-        } else {
-            // clipped / unaligned tile: coalesced generic copy by the consumer warps
-            if (threadIdx.x <= g.ncell) sh.cstart[threadIdx.x] = __ldg(a.rowptr + NUN * (g.cell0 + threadIdx.x)) - g0;
-            PROG(6)
-            __syncwarp();
-            PROG(7)
-            asm volatile("bar.sync 1, %0;\n" ::"n"(32 * PIPE_CONS) : "memory");
-            PROG(8)
-            double* gdst = a.val + g0;
-            for (int q = threadIdx.x; q < tot; q += 32 * PIPE_CONS) {
-                int cl = min(q / NSLOT_TOTAL, g.ncell - 1);
-                while (q < sh.cstart[cl]) cl--;
-                while (q >= sh.cstart[cl + 1]) cl++;
-                gdst[q] = sh.v[cl * VSTRIDE + (q - sh.cstart[cl])];
-            }
-        }
-        PROG(fast ? 10 : 9)
-        if (RA == 1 && lane == 0) { sh.outinfo[0] = g0; sh.outinfo[1] = g.ncell; sh.outinfo[2] = fast ? 1 : 0; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.bar_outfull);
-    }
-}
-
-template <int CTAS_PER_SM>
-__global__ void __launch_bounds__(PIPE_THREADS, CTAS_PER_SM) thcm_jac_pipe_kernel(const AsmArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PipeSmem& sh = *reinterpret_cast<PipeSmem*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PIPE_NSTAGE; s++) { mbar_init(&sh.bar_raw[s], 1); mbar_init(&sh.bar_ready[s], 1); mbar_init(&sh.bar_empty[s], PIPE_CONS); }
-        mbar_init(&sh.bar_outfull, PIPE_CONS); mbar_init(&sh.bar_outempty, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == PIPE_CONS) {
-        // ---------------- loader ----------------
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
-            const int s = it % PIPE_NSTAGE;
-            const uint32_t n = it / PIPE_NSTAGE;
-            PipeStage& st = sh.st[s];
-            if (n >= 1) mbar_wait(&sh.bar_empty[s], (n - 1) & 1, 3);
-            const TileGeom g = tile_geom_of(a.b, tile);
-            const int w = g.ncell + 2;
-            if (lane == 0)
-                mbar_expect_tx(&sh.bar_raw[s], (uint32_t)(9 * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
-            __syncwarp();
-            if (lane < 9) {
-                LineSeg seg[3];
-                const int ns = line_plan(a.b, g, lane, seg);
-#pragma unroll
-                for (int q = 0; q < 3; q++)
-                    if (q < ns)
-                        bulk_load(&st.rec[lane][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
-                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar_raw[s]);
-            } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar_raw[s]);
-            else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar_raw[s]);
-            else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar_raw[s]);
-            mbar_wait(&sh.bar_raw[s], n & 1, 4);
-            // usol in place: no-slip zeroing of u,v, lid / bottom / ghost-column rule of w (descriptor bits)
-            for (int p = lane; p < 9 * TW; p += 32) {
-                const int r = p / TW, x = p - r * TW;
-                if (x < w) {
-                    if (!((st.desc.uvbits[r] >> x) & 1ull)) *reinterpret_cast<double2*>(&st.rec[r][x][0]) = make_double2(0.0, 0.0);
-                    if (!((st.desc.wbits[r] >> x) & 1ull)) st.rec[r][x][2] = 0.0;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.bar_ready[s]);
-        }
-    } else if (warp == PIPE_CONS + 1) {
-        // ---------------- storer ----------------
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.ntile; tile += gridDim.x, it++) {
-#ifdef THCM_PIPE_DEBUG
-            {
-                uint32_t done = 0; const long long t0 = clock64();
-                while (!done) {
-                    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                                 : "=r"(done) : "r"(smem_u32(&sh.bar_outfull)), "r"((uint32_t)(it & 1)) : "memory");
-                    if (!done && clock64() - t0 > 1000000000ll) {
-                        if (lane == 0) for (int w = 0; w < 5; w++) {
-                            int mn = 99, mx = -1, l0 = sh.prog[w][0];
-                            for (int l = 0; l < 32; l++) { int v = sh.prog[w][l]; mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
-                            printf("blk %d it %d warp %d prog lane0 %d min %d max %d\n", blockIdx.x, it, w, l0, mn, mx);
-                        }
-                        __trap();
-                    }
-                }
-            }
-#else
-            mbar_wait(&sh.bar_outfull, it & 1, 5);
-#endif
-            const int g0 = sh.outinfo[0], ncell = sh.outinfo[1], fast = sh.outinfo[2];
-            if (fast && lane < ncell) {
-                bulk_store(a.val + g0 + (size_t)lane * NSLOT_TOTAL, sh.v + lane * VSTRIDE, NSLOT_TOTAL * (int)sizeof(double));
-                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.bar_outempty);
-        }
-        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
-    } else {
-        switch (warp) {
-        case 0: pipe_consumer<1, 1>(a, sh, lane); break;
-        case 1: pipe_consumer<2, 2>(a, sh, lane); break;
-        case 2: pipe_consumer<3, 4>(a, sh, lane); break;
-        case 3: pipe_consumer<5, 5>(a, sh, lane); break;
-        default: pipe_consumer<6, 6>(a, sh, lane); break;
-        }
-    }
-}
-
-template <int CTAS_PER_SM> static void launch_jac_pipe_t(thcmb_ctx* c, const AsmArgs& a) {
-    static int grid_per_dev = 0;
-    if (!grid_per_dev) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_pipe_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem)));
-        int nsm = 0, occ = 0;
-        THCM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-        THCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, thcm_jac_pipe_kernel<CTAS_PER_SM>, PIPE_THREADS, sizeof(PipeSmem)));
-        if (occ < 1) fatal("pipelined assembly kernel does not fit on this device");
-        grid_per_dev = nsm * std::min(occ, CTAS_PER_SM);
-    }
-    int grid = std::min(grid_per_dev, a.ntile);
-    thcm_jac_pipe_kernel<CTAS_PER_SM><<<grid, PIPE_THREADS, sizeof(PipeSmem), c->stream>>>(a);
-}
-static void launch_jac_pipe(thcmb_ctx* c, const AsmArgs& a) {
-    if (c->asm_pipe == 3) launch_jac_pipe_t<3>(c, a); else launch_jac_pipe_t<2>(c, a);
-}
-
 // =============================================================================
 // One-block-per-tile Jacobian kernel with TMA staging (MODE_JAC_GRAPH default).  Same three phases as
 // thcm_assemble_kernel, but
@@ -628,26 +432,12 @@ template <int GROUP> struct alignas(16) TmaSmem {
     int cstart[TI + 2];
     unsigned long long bar;
 };
-// THCM_ASM_PIPE=5 (candidate, not yet measured): the output staging `v` ALIASES the input stage -- the staged records are dead once
-// every warp has evaluated its rows -- so a block needs 17 / 11 KB instead of 28 / 20 KB of shared memory and, with the register
-// budget bounded for it, 10 / 13 instead of 8 / 11 blocks fit an SM (the kernels are latency bound: DESIGN.md section 3.1)
-template <int GROUP> struct alignas(16) TmaSmemAlias {
-    union alignas(16) U {
-        Stage<RowGroup<GROUP>::LINES> st;
-        double v[TI * RowGroup<GROUP>::VS];
-        __device__ U() {}
-    } u;
-    int cstart[TI + 2];
-    unsigned long long bar;
-};
 template <int G> __device__ __forceinline__ Stage<RowGroup<G>::LINES>& smem_stage(TmaSmem<G>& s) { return s.st; }
 template <int G> __device__ __forceinline__ double* smem_out(TmaSmem<G>& s) { return s.v; }
-template <int G> __device__ __forceinline__ Stage<RowGroup<G>::LINES>& smem_stage(TmaSmemAlias<G>& s) { return s.u.st; }
-template <int G> __device__ __forceinline__ double* smem_out(TmaSmemAlias<G>& s) { return s.u.v; }
 
 __device__ __forceinline__ constexpr int diag_pos(int R) { return ROW_OFF[R - 1] + interior_pos(R, slot_of(R, 5, R)); }
 
-template <int GROUP, int RA, int RB, bool CPL, bool ALIAS, class SH>
+template <int GROUP, int RA, int RB, bool CPL, class SH>
 __device__ __forceinline__ void tma_rows(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool open_ocean, bool interior) {
     using G = RowGroup<GROUP>;
     constexpr int NA = RowSlots<RA>::N, NB = RowSlots<RB>::N;
@@ -656,7 +446,6 @@ __device__ __forceinline__ void tma_rows(const AsmArgs& a, SH& sh, const TileGeo
     const uint32_t nb = st.desc.nbmask[lane];
     const double sm = (double)((st.desc.surfbits >> lane) & 1u);
     double EA[NA], EB[NB];
-    static_assert(!ALIAS, "the aliased kernels use tma_rows_eval / tma_rows_emit");
     pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
     pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
     pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
@@ -666,40 +455,16 @@ __device__ __forceinline__ void tma_rows(const AsmArgs& a, SH& sh, const TileGeo
         pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
     }
 }
-// aliased staging (THCM_ASM_PIPE=5): evaluation and emission are separate calls so that the block barrier between the last read of
-// the stage and the first write over it sits in the kernel's common path (not inside the per-warp switch).  EA / EB are sized for the
-// longest rows (u: 24, p: 11)
-constexpr int ALIAS_NA = 24, ALIAS_NB = 11;
-template <int GROUP, int RA, int RB, bool CPL, class SH>
-__device__ __forceinline__ void tma_rows_eval(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool open_ocean, double* EA, double* EB) {
-    auto& st = smem_stage<GROUP>(sh);
-    const uint32_t nb = st.desc.nbmask[lane];
-    const double sm = (double)((st.desc.surfbits >> lane) & 1u);
-    pipe_eval<RA, CPL>(a, st, g, lane, nb, sm, EA);
-    pipe_finish<RA>(a, g, lane, nb, open_ocean, EA);
-    if constexpr (RB != RA) {
-        pipe_eval<RB, CPL>(a, st, g, lane, nb, sm, EB);
-        pipe_finish<RB>(a, g, lane, nb, open_ocean, EB);
-    }
-}
-template <int GROUP, int RA, int RB, class SH>
-__device__ __forceinline__ void tma_rows_emit(const AsmArgs& a, SH& sh, const TileGeom& g, int lane, bool interior, const double* EA, const double* EB) {
-    using G = RowGroup<GROUP>;
-    double* v = smem_out<GROUP>(sh);
-    pipe_emit<RA, G::ROW0, G::VS>(a, v, g, lane, interior, EA);
-    if constexpr (RB != RA) pipe_emit<RB, G::ROW0, G::VS>(a, v, g, lane, interior, EB);
-}
-
-template <int GROUP, int BLOCKS_PER_SM, bool CPL, bool ALIAS = false>
+template <int GROUP, int BLOCKS_PER_SM, bool CPL>
 __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) thcm_jac_tma_kernel(const AsmArgs a) {
     using G = RowGroup<GROUP>;
     constexpr int NT = 32 * G::NWARP;
     constexpr int SEG0 = ROW_OFF[G::ROW0 - 1];   // first entry of the group inside an interior cell record
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SH = typename std::conditional<ALIAS, TmaSmemAlias<GROUP>, TmaSmem<GROUP>>::type;
+    using SH = TmaSmem<GROUP>;
     SH& sh = *reinterpret_cast<SH*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
+    const int tile = a.tile_list ? a.tile_list[blockIdx.x] : (int)blockIdx.x;
     using ST = Stage<G::LINES>;
     ST& st = smem_stage<GROUP>(sh);
     double* const vout = smem_out<GROUP>(sh);
@@ -738,7 +503,6 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
     if (all_land && interior && fast) {
         // identity rows only: zeros with a one on the diagonal of every row of the group
-        if constexpr (ALIAS) __syncthreads();   // every thread has read the descriptor flags before the stage is overwritten
         double2* v2 = reinterpret_cast<double2*>(vout);
         for (int i = threadIdx.x; i < g.ncell * (G::VS / 2); i += NT) v2[i] = make_double2(0.0, 0.0);
         __syncthreads();
@@ -761,40 +525,15 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
             }
         }
         __syncthreads();
-        if constexpr (!ALIAS) {
-            if constexpr (GROUP == 0) {
-                switch (warp) {
-                case 0: tma_rows<0, 1, 1, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
-                case 1: tma_rows<0, 2, 2, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
-                default: tma_rows<0, 3, 4, CPL, false>(a, sh, g, lane, open_ocean, interior); break;
-                }
-            } else {
-                if (warp == 0) tma_rows<1, 5, 5, CPL, false>(a, sh, g, lane, open_ocean, interior);
-                else tma_rows<1, 6, 6, CPL, false>(a, sh, g, lane, open_ocean, interior);
+        if constexpr (GROUP == 0) {
+            switch (warp) {
+            case 0: tma_rows<0, 1, 1, CPL>(a, sh, g, lane, open_ocean, interior); break;
+            case 1: tma_rows<0, 2, 2, CPL>(a, sh, g, lane, open_ocean, interior); break;
+            default: tma_rows<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, interior); break;
             }
         } else {
-            double EA[ALIAS_NA], EB[ALIAS_NB];
-            if constexpr (GROUP == 0) {
-                switch (warp) {
-                case 0: tma_rows_eval<0, 1, 1, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
-                case 1: tma_rows_eval<0, 2, 2, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
-                default: tma_rows_eval<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, EA, EB); break;
-                }
-            } else {
-                if (warp == 0) tma_rows_eval<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, EA, EB);
-                else tma_rows_eval<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, EA, EB);
-            }
-            __syncthreads();   // every row of the block has been evaluated: the staged records may be overwritten
-            if constexpr (GROUP == 0) {
-                switch (warp) {
-                case 0: tma_rows_emit<0, 1, 1>(a, sh, g, lane, interior, EA, EB); break;
-                case 1: tma_rows_emit<0, 2, 2>(a, sh, g, lane, interior, EA, EB); break;
-                default: tma_rows_emit<0, 3, 4>(a, sh, g, lane, interior, EA, EB); break;
-                }
-            } else {
-                if (warp == 0) tma_rows_emit<1, 5, 5>(a, sh, g, lane, interior, EA, EB);
-                else tma_rows_emit<1, 6, 6>(a, sh, g, lane, interior, EA, EB);
-            }
+            if (warp == 0) tma_rows<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, interior);
+            else tma_rows<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, interior);
         }
     }
     if (fast) {
@@ -821,27 +560,26 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     }
 }
 
-template <int GROUP, int BLOCKS_PER_SM, bool CPL, bool ALIAS = false> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a) {
-    using SH = typename std::conditional<ALIAS, TmaSmemAlias<GROUP>, TmaSmem<GROUP>>::type;
+template <int GROUP, int BLOCKS_PER_SM, bool CPL> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
+    using SH = TmaSmem<GROUP>;
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SH)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SH)));
         attr_set = true;
     }
-    thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL, ALIAS><<<a.ntile, 32 * RowGroup<GROUP>::NWARP, sizeof(SH), c->stream>>>(a);
+    if (nblocks > 0) thcm_jac_tma_kernel<GROUP, BLOCKS_PER_SM, CPL><<<nblocks, 32 * RowGroup<GROUP>::NWARP, sizeof(SH), c->stream>>>(a);
 }
-// candidate (THCM_ASM_PIPE=5): aliased staging, register budget for 10 / 13 blocks per SM; uncoupled kernels only
-static void launch_jac_tma_alias(thcmb_ctx* c, const AsmArgs& a) {
-    launch_jac_tma_group<0, 10, false, true>(c, a);
-    if (a.t.coupled_T || a.t.coupled_S) launch_jac_tma_group<1, 11, true, false>(c, a);
-    else launch_jac_tma_group<1, 13, false, true>(c, a);
-    c->launches++;
-}
-// coupled mode only touches the T | S rows (group B); group A is the same kernel either way
-template <int BA, int BB> static void launch_jac_tma(thcmb_ctx* c, const AsmArgs& a) {
-    launch_jac_tma_group<0, BA, false>(c, a);
-    if (a.t.coupled_T || a.t.coupled_S) launch_jac_tma_group<1, BB, true>(c, a);
-    else launch_jac_tma_group<1, BB, false>(c, a);
+// coupled mode only touches the T | S rows (group B); group A is the same kernel either way.
+// Tiles whose cells are all LAND hold identity rows whatever the state (boundary.F90:381-386): they are written by the FIRST assembly
+// after the static data were built and skipped afterwards (the blocks then walk the list of the other tiles): a third of the tiles of a
+// global mask, with their loads, barriers and 832-byte-per-cell stores.
+template <int BA, int BB> static void launch_jac_tma(thcmb_ctx* c, AsmArgs a) {
+    int nblocks = a.ntile;
+    if (c->land_tiles_written && c->d_active_tiles) { a.tile_list = c->d_active_tiles; nblocks = c->n_active_tiles; }
+    launch_jac_tma_group<0, BA, false>(c, a, nblocks);
+    if (a.t.coupled_T || a.t.coupled_S) launch_jac_tma_group<1, BB, true>(c, a, nblocks);
+    else launch_jac_tma_group<1, BB, false>(c, a, nblocks);
+    c->land_tiles_written = true;
     c->launches++;   // two kernels per assembly
 }
 
@@ -905,7 +643,7 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     a.un = d_un; a.halo = c->d_halo; a.nbmask = c->d_nbmask; a.surf = c->d_surf; a.uvlive = c->d_uvlive; a.frc = c->d_frc;
     a.rowptr = c->d_rowptr; a.val = c->d_val; a.blockcnt = c->d_blockcnt; a.begA = d_begA; a.jcoA = d_jcoA; a.coA = d_coA;
     a.out = d_out; a.sign = 1.0;
-    a.tdesc = c->d_tdesc; a.jrec = c->d_jrec; a.krec = c->d_krec; a.ntile = c->n_asm_blocks;
+    a.tdesc = c->d_tdesc; a.jrec = c->d_jrec; a.krec = c->d_krec; a.ntile = c->n_asm_blocks; a.tile_list = nullptr;
     int nblk = c->n_asm_blocks;
     static const int kid_of_mode[4] = {KID_ASM_RHS, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS};
     ProfScope prof_(c, kid_of_mode[mode & 3]);
@@ -915,10 +653,7 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
         launch_mode<MODE_RHS>(c, a, nblk); break;
     case MODE_JAC_GRAPH:
         if (c->asm_pipe == 1) launch_jac_tma<8, 11>(c, a);
-        else if (c->asm_pipe == 4) launch_jac_tma<6, 8>(c, a);
-        else if (c->asm_pipe == 5) launch_jac_tma_alias(c, a);
-        else if (c->asm_pipe >= 2) launch_jac_pipe(c, a);
-        else launch_mode<MODE_JAC_GRAPH>(c, a, nblk);
+        else { launch_mode<MODE_JAC_GRAPH>(c, a, nblk); c->land_tiles_written = true; }   // THCM_ASM_PIPE=0: per-position loads, every tile
         break;
     case MODE_JAC_COUNT: launch_mode<MODE_JAC_COUNT>(c, a, nblk); break;
     case MODE_JAC_CRS: launch_mode<MODE_JAC_CRS>(c, a, nblk); break;

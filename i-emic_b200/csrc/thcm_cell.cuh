@@ -45,6 +45,7 @@ struct AsmArgs {
     const TileDesc* tdesc;   // pipelined kernel: per-tile descriptors, per-j / per-k table records
     const double* jrec; const double* krec;
     int ntile;
+    const int* tile_list;    // Jacobian kernels: tiles to work on (nullptr = all tiles in order)
 };
 
 // ---------------------------------------------------------------------------

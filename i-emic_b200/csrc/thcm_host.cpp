@@ -890,7 +890,6 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
         }
     }
     c->nsend_cells = (int)send_idx.size(); c->nrecv_cells = (int)recv_slot.size();
-    build_spmv_patterns(c);
     // cell compaction maps (groundwork for the ocean-only Krylov space): ocean cells of the block in cell order,
     // and the inverse map (compact index or -1 for LAND)
     c->ocell_host.clear();
@@ -916,34 +915,6 @@ void build_static_host(thcmb_ctx* c, std::vector<uint32_t>& nbmask, std::vector<
     for (size_t q = 0; q < send_idx.size(); q++) c->send_cidx_host[q] = c->ccell_host[(size_t)send_idx[q]];
 }
 
-// Column-index compression for the SpMV: the static maximal graph only depends on a row's unknown and on the boundary class /
-// periodic seam of its cell, so `col[q] - 6*cell` takes a few hundred distinct sequences ("patterns") over the whole grid.
-// rowpat[row] = pattern id, patrel[id*SPMV_PATLEN + q] = relative column; rows that reference a halo column keep the explicit
-// col array (id 0xFFFF).  Built from the graph itself, so it cannot disagree with it; with it the kernel reads 2 bytes per ROW
-// instead of 4 bytes per ENTRY of column information (546 MB -> 16 MB at 1 degree).
-void build_spmv_patterns(thcmb_ctx* c) {
-    const int n = c->blk.ndim();
-    c->rowpat_host.assign((size_t)n, (uint16_t)0xFFFF);
-    c->patrel_host.clear();
-    std::map<std::vector<int>, int> dict;
-    std::vector<int> key;
-    for (int row = 0; row < n; row++) {
-        const int b = c->rowptr_host[row], e = c->rowptr_host[row + 1], base = NUN * (row / NUN);
-        if (e - b > SPMV_PATLEN) continue;
-        key.clear();
-        bool halo = false;
-        for (int q = b; q < e; q++) { if (c->col_host[q] >= n) { halo = true; break; } key.push_back(c->col_host[q] - base); }
-        if (halo) continue;
-        auto it = dict.find(key);
-        if (it == dict.end()) {
-            if (dict.size() >= 0xFFFE) continue;   // dictionary full: the row keeps its explicit columns
-            it = dict.emplace(key, (int)dict.size()).first;
-            c->patrel_host.resize(dict.size() * SPMV_PATLEN, 0);
-            for (size_t q = 0; q < key.size(); q++) c->patrel_host[(size_t)it->second * SPMV_PATLEN + q] = key[q];
-        }
-        c->rowpat_host[(size_t)row] = (uint16_t)it->second;
-    }
-}
 
 }  // namespace thcm
 

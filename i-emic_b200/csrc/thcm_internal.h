@@ -162,16 +162,15 @@ struct thcmb_ctx {
     std::vector<double> jrec_host, krec_host;
     unsigned int* d_tilectr = nullptr;
     int asm_pipe = 1;               // Jacobian kernel: 1 block per tile with TMA staging (default), 0 block per tile with
-                                    // per-position loads, 2 / 3 persistent TMA-pipelined kernel at 2 / 3 CTAs per SM
+                                    // per-position loads (THCM_ASM_PIPE=0; the kernel family of the residual and of the Fortran-order CRS)
+    int* d_active_tiles = nullptr; int n_active_tiles = 0;   // tiles with at least one non-LAND cell
+    bool land_tiles_written = false;                          // the identity rows of the all-LAND tiles are in d_val
     double* d_frc = nullptr;        // owned rows (masked)
     double* d_cob = nullptr;        // mass diagonal coB of the owned rows (theta stepping)
     int *d_rowptr = nullptr, *d_col = nullptr;  // static graph, local column ids
     double* d_val = nullptr;        // Jacobian values in graph order
     long long gnnz = 0;
     std::vector<int> rowptr_host, col_host, halo_gid, local_gid;
-    // SpMV column-index compression (build_spmv_patterns): pattern id per row, relative columns per pattern
-    std::vector<uint16_t> rowpat_host; std::vector<int> patrel_host;
-    uint16_t* d_rowpat = nullptr; int* d_patrel = nullptr;
     std::vector<int> ocell_host, ccell_host;   // ocean cells of the block (cell order) and the inverse map (-1 = LAND)
     int *d_ocell = nullptr, *d_ccell = nullptr; int n_ocell = 0;
     std::vector<int> colc_host, send_cidx_host;   // compact column ids (graph offsets), compact source cell of the send lists
@@ -181,9 +180,7 @@ struct thcmb_ctx {
     void* d_halo_ll[2] = {nullptr, nullptr};   // my LL halo buffers (inside the IPC-shared allocation)
     unsigned long long halo_ll_seq = 0;
     int krylov_compact = 1;          // GMRES on the ocean cells only (THCM_KRYLOV_COMPACT=0 switches it off)
-    uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows)
-    int spmv_skip_land = 0;         // THCM_SPMV_SKIP_LAND=1: y = x on the rows of LAND cells without streaming them (not yet measured: off)
-    int spmv_pattern = 0;           // THCM_SPMV_PATTERN=1: columns from the pattern table (not yet measured: off by default)
+    uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows; the SpMV answers y = x for them without streaming the row)
     // ---- halo exchange ----
     double *d_halo = nullptr;       // 6*nhalo doubles, laid out per Block::hk
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
@@ -198,9 +195,6 @@ struct thcmb_ctx {
     double** d_peer_halo = nullptr;  // device array [2][npeers]: peer halo buffer base per parity
     unsigned long long halo_seq = 0;
     unsigned int* d_halo_counter = nullptr;
-    unsigned char* d_bcell = nullptr;   // per owned cell: 1 if a row of the cell can reference a halo column
-    int* d_brows = nullptr; int n_brows = 0;   // rows of those cells
-    int spmv_overlap = 0;               // 1: split the SpMV around the halo exchange (measured slower at 8 GPUs: two small kernels more)
     struct Peer { int rank; int send_off, send_cnt, recv_off, recv_cnt; };
     std::vector<Peer> peers;
     int nsend_cells = 0, nrecv_cells = 0;
@@ -292,8 +286,6 @@ void compute_tables(thcmb_ctx* c);
 void vmix_init(thcmb_ctx* c);
 void vmix_set_flags(thcmb_ctx* c, int temp, int salt);
 void compute_cob(thcmb_ctx* c);
-constexpr int SPMV_PATLEN = 24;     // longest row of the maximal graph (THCM.C:2320-2325)
-void build_spmv_patterns(thcmb_ctx* c);
 const ClassTables& class_tables(int periodic);
 int halo_slot(const Block& b, int ie, int je, int k);  // extended local coords (-1..n0, -1..m0); -1 if not a halo cell
 // device side
@@ -305,9 +297,7 @@ int asm_block_count(const Block& b);
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y);
 int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait = true);
-int halo_wait(thcmb_ctx* c);
 int field_sumsq(thcmb_ctx* c, const double* d_un, double* h_out2);   // global sum of squares of the T and S fields
-int spmv_part(thcmb_ctx* c, int part, const double* x, double* y);
 // vector kernels (device-scalar flavours keep the Krylov inner loops free of host syncs)
 int dot_dev(thcmb_ctx* c, int n, const double* x, const double* y, double* d_out);
 int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);

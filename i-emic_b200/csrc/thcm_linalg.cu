@@ -21,50 +21,33 @@ constexpr int SPMV_THREADS = 256;
 // LANES lanes share a row; every lane first issues its first UNROLL (col, val) loads -- predicated, independent --
 // then the x gathers, then the products: all loads of a row are in flight together (rows are short, so a plain
 // loop exposes one memory latency per iteration and leaves the kernel latency-bound at full occupancy).
-// SEL: 0 every row; 1 rows of cells NOT flagged in `bcell` (interior rows: no halo column -- they run while the halo is
-// still in flight); 2 the rows listed in `rowlist` (rows of the boundary cells, after the halo has arrived)
-// PAT: column ids come from the pattern table (build_spmv_patterns): col = 6*cell + patrel[rowpat[row]][position]; rows with
-// rowpat = 0xFFFF (halo columns) read the explicit col array.  2 bytes per row instead of 4 bytes per entry.
+// 4 lanes x 6 entries measured best on the B200 (r01: 8x1, 8x3, 4x3, 16x2, 2x12 were the alternatives).
 // LSKIP: rows of LAND cells are identity rows whatever the state (boundary.F90:381-386; explicit zeros elsewhere in the maximal graph):
-// y = x for them without touching their values or column ids (landcell = one byte per owned cell).  Bit-identical to the full product.
-template <int LANES, int UNROLL, int SEL = 0, bool PAT = false, bool LSKIP = false>
+// y = x for them without touching their values or column ids (landcell = one byte per owned cell).  Bit-identical to the full product
+// (r02a on the 1-degree grid: 0.265 ms instead of 0.352 ms).
+template <int LANES, int UNROLL, bool LSKIP>
 __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const int* __restrict__ rp, const int* __restrict__ col,
                                                                  const double* __restrict__ val, const double* __restrict__ x,
                                                                  const double* __restrict__ halo, int nlocal, double* __restrict__ y,
-                                                                 const unsigned char* __restrict__ bcell = nullptr,
-                                                                 const int* __restrict__ rowlist = nullptr,
-                                                                 const unsigned short* __restrict__ rowpat = nullptr,
-                                                                 const int* __restrict__ patrel = nullptr,
-                                                                 const unsigned char* __restrict__ landcell = nullptr) {
+                                                                 const unsigned char* __restrict__ landcell) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
     // the loop bound is warp-uniform and rows that do not take part stay in the body with an empty range: the full-mask
     // shuffles below must be reached by every lane of the warp
     for (int base = blockIdx.x * rows_per_block; base < nrow; base += gridDim.x * rows_per_block) {
         const int r0 = base + (threadIdx.x / LANES);
-        bool act = r0 < nrow;
-        int row = act ? r0 : 0;
-        if constexpr (SEL == 1) act = act && __ldg(bcell + row / NUN) == 0;
-        if constexpr (SEL == 2) row = act ? __ldg(rowlist + r0) : 0;
+        const bool act = r0 < nrow;
+        const int row = act ? r0 : 0;
         bool land = false;
         if constexpr (LSKIP) land = act && __ldg(landcell + row / NUN) != 0;
         const bool ld = act && !land;
         const int b = ld ? __ldg(rp + row) : 0, e = ld ? __ldg(rp + row + 1) : 0;
         int cc[UNROLL]; double vv[UNROLL], xx[UNROLL];
-        int pat = 0xFFFF;
-        if constexpr (PAT) pat = act ? (int)__ldg(rowpat + row) : 0xFFFF;
-        const int cbase = NUN * (row / NUN);
-        const int* prel = patrel + (size_t)(pat == 0xFFFF ? 0 : pat) * SPMV_PATLEN;
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int q = b + sub + u * LANES;
             const bool ok = q < e;
-            if constexpr (PAT) {
-                static_assert(!PAT || LANES * UNROLL <= SPMV_PATLEN, "pattern rows are at most SPMV_PATLEN long");
-                cc[u] = ok ? (pat != 0xFFFF ? cbase + __ldg(prel + sub + u * LANES) : __ldg(col + q)) : -1;
-            } else {
-                cc[u] = ok ? __ldg(col + q) : -1;
-            }
+            cc[u] = ok ? __ldg(col + q) : -1;
             vv[u] = ok ? __ldg(val + q) : 0.0;
         }
 #pragma unroll
@@ -85,61 +68,15 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_csr_kernel(int nrow, const 
     }
 }
 
-static int spmv_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("THCM_SPMV_VARIANT"); v = e ? atoi(e) : 2; }   // 2 = 4 lanes x 6 entries: best on B200 (profiles/)
-    return v;
-}
-
-// operator application split around the halo exchange (multi-GPU): interior rows, then -- after the wait -- boundary rows
-int spmv_part(thcmb_ctx* c, int part, const double* x, double* y) {
-    ProfScope prof_(c, KID_SPMV);
-    const int n = c->blk.ndim();
-    if (part == 0) {
-        const int rows_per_block = SPMV_THREADS / 4;
-        const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)n + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
-        spmv_csr_kernel<4, 6, 1><<<grid, SPMV_THREADS, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, c->d_halo, n, y, c->d_bcell, nullptr);
-    } else if (c->n_brows > 0) {
-        const int rows_per_block = SPMV_THREADS / 4;
-        const int grid = std::max(1, (c->n_brows + rows_per_block - 1) / rows_per_block);
-        spmv_csr_kernel<4, 6, 2><<<grid, SPMV_THREADS, 0, c->stream>>>(c->n_brows, c->d_rowptr, c->d_col, c->d_val, x, c->d_halo, n, y, nullptr, c->d_brows);
-    }
-    c->launches++;
-    return 0;
-}
-
 int spmv(thcmb_ctx* c, int nrow, const int* rp, const int* col, const double* val, const double* x, const double* halo,
          int nlocal, double* y) {
     ProfScope prof_(c, KID_SPMV);
-    auto grid_for = [&](int lanes) {
-        const int rows_per_block = SPMV_THREADS / lanes;
-        long long want = ((long long)nrow + rows_per_block - 1) / rows_per_block;
-        return (int)std::max<long long>(1, std::min<long long>(want, (long long)NSM * 64));
-    };
-    if (c->spmv_skip_land && col == c->d_col && c->d_landcell) {   // the context's own graph: identity rows of LAND cells are not streamed
-        if (c->spmv_pattern && c->d_rowpat && c->d_patrel)
-            spmv_csr_kernel<4, 6, 0, true, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
-                                                                                              c->d_rowpat, c->d_patrel, c->d_landcell);
-        else
-            spmv_csr_kernel<4, 6, 0, false, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
-                                                                                               nullptr, nullptr, c->d_landcell);
-        c->launches++;
-        return 0;
-    }
-    if (c->spmv_pattern && col == c->d_col && c->d_rowpat && c->d_patrel) {   // the context's own graph: pattern-compressed columns
-        spmv_csr_kernel<4, 6, 0, true><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr, nullptr,
-                                                                                    c->d_rowpat, c->d_patrel);
-        c->launches++;
-        return 0;
-    }
-    switch (spmv_variant()) {
-    case 0: spmv_csr_kernel<8, 1><<<grid_for(8), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    case 2: spmv_csr_kernel<4, 6><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    case 3: spmv_csr_kernel<4, 3><<<grid_for(4), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    case 4: spmv_csr_kernel<16, 2><<<grid_for(16), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    case 5: spmv_csr_kernel<2, 12><<<grid_for(2), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    default: spmv_csr_kernel<8, 3><<<grid_for(8), SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y); break;
-    }
+    const int rows_per_block = SPMV_THREADS / 4;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(((long long)nrow + rows_per_block - 1) / rows_per_block, (long long)NSM * 64));
+    if (col == c->d_col && c->d_landcell)   // the context's own graph: identity rows of LAND cells are not streamed
+        spmv_csr_kernel<4, 6, true><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, c->d_landcell);
+    else
+        spmv_csr_kernel<4, 6, false><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow, rp, col, val, x, halo, nlocal, y, nullptr);
     c->launches++;
     return 0;
 }
@@ -1031,16 +968,11 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     if (c->fused_cgs2 == 2 && nv > 16) {
         ProfScope prof_(c, KID_MULTIAXPY);
         const int ntiles = ((n >> 1) + F2_THREADS - 1) / F2_THREADS;
-        // resident blocks per SM x independent phase-A loads per thread, measured at 1 degree (Newton step, profiles/bench_r01g_*):
-        // 2 x 8 (92 registers) 75.6 ms, 3 x 4 (78 registers) 74.5 ms, 4 x 4 (64 registers) 77.5 ms.  THCM_FUSED2_BPS overrides.
-        // The live tiles stay below the L2 size: BPS x 148 x nv x 4 KB = 89 MB at nv = 50
-        // THCM_FUSED2_BPS=38: 3 blocks x 8 loads (candidate, not yet measured: +50 % bytes in flight per SM at <= 85 registers)
-        static const int bps = [] { const char* e = getenv("THCM_FUSED2_BPS"); int v = e ? atoi(e) : 3; return v == 38 ? 38 : (v < 2 ? 2 : (v > 4 ? 4 : v)); }();
-        const int grid = std::max(1, std::min(std::min(ntiles, NSM * (bps == 38 ? 3 : bps)), MD_BLOCKS));
-        if (bps == 38) fused2_axpy_dot_kernel<3, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
-        else if (bps == 2) fused2_axpy_dot_kernel<2, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
-        else if (bps == 3) fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
-        else fused2_axpy_dot_kernel<4, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        // resident blocks per SM x independent phase-A loads per thread, measured at 1 degree (Newton step, profiles/bench_r01g_*,
+        // profiles/r02/bench_r02a_THCM_FUSED2_BPS_*): 2 x 8 (92 registers) 75.6 ms, 3 x 4 (78 registers) 74.5 ms = kept, 4 x 4 (64
+        // registers) 77.5 ms, 3 x 8 74.3 ms (within noise).  The live tiles stay below the L2 size: 3 x 148 x nv x 4 KB = 89 MB at nv = 50
+        const int grid = std::max(1, std::min(std::min(ntiles, NSM * 3), MD_BLOCKS));
+        fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
         c->launches++;
         return 0;
     }
@@ -1118,16 +1050,6 @@ __global__ void __launch_bounds__(256) halo_push_kernel(int ncells, const int* _
     if (wait) __threadfence_system();
     if (threadIdx.x == 0) *counter = 0u;
 }
-// second half of a split exchange: the neighbours' flags of exchange `seq` (the operator's interior rows ran meanwhile)
-__global__ void halo_wait_kernel(HaloPeers hp, char* my_base, unsigned long long seq) {
-    const int par = (int)(seq & 1ull);
-    if (threadIdx.x < hp.n && hp.recv[threadIdx.x]) {
-        volatile unsigned long long* f = (volatile unsigned long long*)(my_base + P2P_HALOFLAG_OFFSET) + par * P2P_MAX_RANKS + hp.rank[threadIdx.x];
-        flag_wait(f, seq);
-    }
-    __threadfence_system();
-}
-
 struct Id128 { char b[128]; };  // ncclUniqueId (nccl.h: struct { char internal[128]; }), passed by value
 struct NcclApi {
     void* lib = nullptr;
@@ -1180,12 +1102,6 @@ static HaloPeers halo_peers(const thcmb_ctx* c) {
     HaloPeers hp; hp.n = (int)c->peers.size();
     for (int q = 0; q < hp.n; q++) { hp.rank[q] = c->peers[q].rank; hp.send[q] = c->peers[q].send_cnt > 0; hp.recv[q] = c->peers[q].recv_cnt > 0; }
     return hp;
-}
-int halo_wait(thcmb_ctx* c) {
-    ProfScope prof_(c, KID_HALO_UNPACK);
-    halo_wait_kernel<<<1, 32, 0, c->stream>>>(halo_peers(c), (char*)c->d_mailbox, c->halo_seq);
-    c->launches++;
-    return 0;
 }
 int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
     if (c->blk.nranks == 1) return 0;

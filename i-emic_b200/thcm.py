@@ -349,6 +349,12 @@ class THCM:
         self.L_.thcmb_apply_precon_dev(self.ctx, _dev_ptr(v), _dev_ptr(out))
         self.sync()
 
+    def csr_spmv(self, rowptr, col, val, x, y):
+        """y = A x for a CSR matrix in device memory (int32 rowptr / col, float64 val): the plain kernel that streams every row."""
+        self._pre()
+        self.L_.thcmb_csr_spmv_dev(self.ctx, rowptr.numel() - 1, _dev_ptr(rowptr), _dev_ptr(col), _dev_ptr(val), _dev_ptr(x), _dev_ptr(y))
+        self.sync()
+
     def gmres(self, b, x, tol=1e-4, maxit=500, restart=400, prec=True, flexible=True, hist_cap=4096, ortho="mgs", full_space=False):
         """GMRESSolver::solve (src/gmressolver/GMRESSolver.H:81-255).  Returns (KrylovResult, history).  By default the Krylov vectors
         hold the ocean cells only when b and x vanish on LAND (identity rows); full_space=True keeps full-length vectors."""

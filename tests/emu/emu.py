@@ -45,7 +45,6 @@ def lib():
                                 ("emu_derivatives", None, [vp, vp, vp]), ("emu_salt_advection", None, [vp, vp, vp]),
                                 ("emu_salt_diffusion", None, [vp, vp, vp]), ("emu_stochastic_forcing", None, [vp, vp, vp, vp]),
                                 ("emu_getdeps", None, [vp, vp]), ("emu_loadbal", None, [vp, vp]),
-                                ("emu_spmv_pattern_sizes", None, [vp, vp]), ("emu_spmv_patterns", None, [vp, vp, vp]),
                                 ("emu_grid", None, [vp] * 9), ("emu_set_landmask", None, [vp, vp, i, i]), ("emu_setsres", None, [vp, i]),
                                 ("emu_ocean_cells", i, [vp]), ("emu_cell_maps", None, [vp, vp, vp])]:
             fn = getattr(L, name)
@@ -162,14 +161,6 @@ class EmuTHCM:
                  dfzT=np.empty(L), dfzW=np.empty(L + 1))
         self.L_.emu_grid(self.h, *[_p(a[k]) for k in ("x", "xu", "y", "yv", "z", "zw", "dfzT", "dfzW")])
         return a
-
-    def spmv_patterns(self):
-        """(rowpat uint16[ndim], patrel int32[npat, 24]) of build_spmv_patterns."""
-        npat = C.c_int()
-        self.L_.emu_spmv_pattern_sizes(self.h, C.byref(npat))
-        rowpat = np.zeros(self.ndim, dtype=np.uint16); patrel = np.zeros((max(npat.value, 1), 24), dtype=np.int32)
-        self.L_.emu_spmv_patterns(self.h, _p(rowpat), _p(patrel))
-        return rowpat, patrel[:npat.value]
 
     def getdeps(self):
         out = np.empty(7); self.L_.emu_getdeps(self.h, _p(out)); return out

@@ -141,13 +141,6 @@ void emu_salt_diffusion(void* h, const double* un, double* out) { integrals_salt
 void emu_stochastic_forcing(void* h, int* beg, int* jco, double* co) { thcmb_ctx* c = &((Emu*)h)->c; stochastic_forcing(c, beg, jco, co); }
 void emu_getdeps(void* h, double* out7) { get_deps(&((Emu*)h)->c, out7); }
 void emu_loadbal(void* h, double* w) { loadbal_weights(&((Emu*)h)->c, w); }
-// SpMV column patterns (build_spmv_patterns): sizes, then the arrays
-void emu_spmv_pattern_sizes(void* h, int* npat) { *npat = (int)(((Emu*)h)->c.patrel_host.size() / SPMV_PATLEN); }
-void emu_spmv_patterns(void* h, unsigned short* rowpat, int* patrel) {
-    thcmb_ctx* c = &((Emu*)h)->c;
-    memcpy(rowpat, c->rowpat_host.data(), sizeof(uint16_t) * c->rowpat_host.size());
-    memcpy(patrel, c->patrel_host.data(), sizeof(int) * c->patrel_host.size());
-}
 // the library's grid arrays (build_grid = grid.F90): x(1..N), xu(0..N), y(1..M), yv(0..M), z(1..L), zw(0..L), dfzT(1..L), dfzW(0..L)
 void emu_grid(void* h, double* x, double* xu, double* y, double* yv, double* z, double* zw, double* dfzT, double* dfzW) {
     thcmb_ctx* c = &((Emu*)h)->c; const int N = c->s.N, M = c->s.M, L = c->s.L;

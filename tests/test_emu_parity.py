@@ -307,36 +307,6 @@ def test_coupled_mode_on_decomposed_blocks(name, nranks):
         assert np.array_equal(val, vo[idx])
 
 
-@pytest.mark.parametrize("name,nranks", [("global4deg", 1), ("gateway16", 1), ("box_np", 1), ("box_tiny", 1), ("global4deg", 4), ("box_p", 2)])
-def test_spmv_column_patterns_reproduce_the_graph(name, nranks):
-    """build_spmv_patterns: col[q] == 6*cell + patrel[rowpat[row]][q - rowptr[row]] for every compressed row; only rows with a halo
-    column keep explicit indices; the dictionary stays small (row type x boundary class x seam)."""
-    for rank in range(nranks):
-        sr, landm = CASES[name](rank=rank, nranks=nranks)
-        e = EmuTHCM(sr, landm)
-        rp, col = e.graph()
-        rowpat, patrel = e.spmv_patterns()
-        n = e.ndim
-        lens = np.diff(rp)
-        comp = rowpat != 0xFFFF
-        has_halo = np.add.reduceat((col >= n).astype(np.int64), rp[:-1]) > 0
-        assert np.array_equal(~comp, has_halo)               # exactly the rows with halo columns stay explicit
-        assert nranks > 1 or comp.all()
-        assert len(patrel) <= 6 * 64 * 3
-        rows = np.nonzero(comp)[0]
-        pos = np.arange(24)[None, :]
-        cand = 6 * (rows // 6)[:, None] + patrel[rowpat[rows]]
-        mask = pos < lens[rows][:, None]
-        expect = np.concatenate([col[rp[r]:rp[r + 1]] for r in rows]) if len(rows) < 50000 else None
-        got = cand[mask]
-        if expect is None:
-            idx = np.concatenate([np.arange(rp[r], rp[r + 1]) for r in rows[:: max(1, len(rows) // 20000)]])
-            sub = rows[:: max(1, len(rows) // 20000)]
-            got = (6 * (sub // 6)[:, None] + patrel[rowpat[sub]])[pos < lens[sub][:, None]]
-            expect = col[idx]
-        assert np.array_equal(got, expect)
-
-
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p"])
 @pytest.mark.parametrize("vmix", [0, 1])
 def test_set_landmask_rebuilds_everything(name, vmix):

@@ -109,10 +109,9 @@ def test_integral_condition_needs_sres_zero_and_an_ocean_point():
 
 
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
-@pytest.mark.parametrize("pattern", ["0", "1"])
-def test_spmv_skipping_land_rows(name, pattern, monkeypatch):
-    """THCM_SPMV_SKIP_LAND=1: y = x on the identity rows of LAND cells without streaming them -- bit-identical to the full product
-    (1.0 * x + 0.0 * ... = x), alone and combined with the pattern-compressed columns."""
+def test_spmv_skipping_land_rows(name):
+    """The SpMV answers y = x on the identity rows of LAND cells without streaming them: it must equal the full CSR product over the
+    graph arrays (thcmb_csr_spmv_dev on the same device arrays streams every row) bit for bit -- 1.0 * x + 0.0 * ... = x."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
@@ -122,53 +121,19 @@ def test_spmv_skipping_land_rows(name, pattern, monkeypatch):
     s, landm = mk()
     x = cases.random_state(s, landm, scale=0.2)
     rng = np.random.default_rng(4)
-    vs = [rng.standard_normal(6 * s.N * s.M * s.L) for _ in range(3)]
-    out = {}
-    for skip in ("0", "1"):
-        monkeypatch.setenv("THCM_SPMV_SKIP_LAND", skip)
-        monkeypatch.setenv("THCM_SPMV_PATTERN", pattern if skip == "1" else "0")
-        t = iemic_b200.THCM(s, landm)
-        for k, v in PARS.items():
-            t.setParameter(k, v)
-        t.evaluate(torch.from_numpy(x).cuda(), None, True)
-        y = t.new_vector()
-        res = []
-        for v in vs:
-            t.applyMatrix(torch.from_numpy(v).cuda(), y)
-            res.append(y.cpu().numpy().copy())
-        out[skip] = res
-        t.close()
-    for a, b in zip(out["0"], out["1"]):
-        assert np.array_equal(a, b)
-
-
-@pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg", "box_p33"])
-def test_spmv_with_pattern_compressed_columns(name, monkeypatch):
-    torch = pytest.importorskip("torch")
-    if not torch.cuda.is_available():
-        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
-    import iemic_b200
-    from oracle.oracle import OracleTHCM, spmv
-    mk = {"natl8": cases.natl8, "gateway16": cases.gateway16, "global4deg": cases.global4deg,
-          "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw)}[name]
-    monkeypatch.setenv("THCM_SPMV_PATTERN", "1")
-    s, landm = mk()
-    o = OracleTHCM(s, landm)
     t = iemic_b200.THCM(s, landm)
     for k, v in PARS.items():
-        o.setpar(P[k], v)
         t.setParameter(k, v)
-    x = cases.random_state(s, landm, scale=0.2)
     t.evaluate(torch.from_numpy(x).cuda(), None, True)
-    val, _ = o.jacobian_graph(x)
-    rowptr, col = o.graph()
-    rng = np.random.default_rng(4)
-    y = t.new_vector()
+    rp, col = t.graph()
+    rpd, cold = torch.from_numpy(rp).cuda(), torch.from_numpy(col).cuda()
+    vald = torch.from_numpy(t.jacobian_values_host()).cuda()
+    y, y_full = t.new_vector(), t.new_vector()
     for _ in range(3):
-        v = rng.standard_normal(o.ndim)
-        t.applyMatrix(torch.from_numpy(v).cuda(), y)
-        yo = spmv(rowptr, col, val, v)
-        assert np.linalg.norm(y.cpu().numpy() - yo) <= 1e-13 * np.linalg.norm(yo)
+        v = torch.from_numpy(rng.standard_normal(t.ndim)).cuda()
+        t.applyMatrix(v, y)
+        t.csr_spmv(rpd, cold, vald, v, y_full)
+        assert np.array_equal(y.cpu().numpy(), y_full.cpu().numpy())
     t.close()
 
 
@@ -236,34 +201,6 @@ def test_fortran_symbols_on_a_sub_domain_of_an_mpi_run():
     assert np.array_equal(beg, bo) and np.array_equal(jco, jo) and np.array_equal(co, cf)
     assert np.array_equal(f.get_forcing(), o.forcing())
     f.finalize()
-
-
-@pytest.mark.parametrize("name", ["global4deg", "box_p33", "box_np", "gateway16", "box_tiny"])
-def test_jacobian_kernels_with_aliased_staging(name, monkeypatch):
-    """THCM_ASM_PIPE=5: same arithmetic as the default TMA kernels, shared memory reused between the staged records and the output
-    staging (one more block barrier), register budget for 10 / 13 blocks per SM: values must stay bit-exact."""
-    torch = pytest.importorskip("torch")
-    if not torch.cuda.is_available():
-        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
-    import iemic_b200
-    from oracle.oracle import OracleTHCM
-    mk = {"global4deg": cases.global4deg, "gateway16": cases.gateway16,
-          "box_p33": lambda **kw: cases.box(33, 5, 3, True, seed=6, land_frac=0.2, **kw),
-          "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw),
-          "box_tiny": lambda **kw: cases.box(3, 2, 2, True, seed=5, land_frac=0.2, **kw)}[name]
-    monkeypatch.setenv("THCM_ASM_PIPE", "5")
-    s, landm = mk()
-    o = OracleTHCM(s, landm)
-    t = iemic_b200.THCM(s, landm)
-    for k, v in PARS.items():
-        o.setpar(P[k], v)
-        t.setParameter(k, v)
-    for seed in (1, 2):
-        x = cases.random_state(s, landm, scale=0.3, zero_on_land=False, seed=seed)
-        t.evaluate(torch.from_numpy(x).cuda(), None, True)
-        vo, missing = o.jacobian_graph(x)
-        assert missing == 0 and np.array_equal(t.jacobian_values_host(), vo)
-    t.close()
 
 
 def test_reference_ocean_tests_over_the_cpp_mirror():

@@ -82,14 +82,14 @@ def test_residual_and_jacobian_bit_exact(gpu, name, state):
 
 
 @pytest.mark.parametrize("name", ["global4deg", "box_p33", "box_np", "gateway16", "box_tiny"])
-@pytest.mark.parametrize("variant", ["0", "1", "4", "2", "3"])
+@pytest.mark.parametrize("variant", ["0", "1"])
 def test_jacobian_kernel_variants_bit_exact(gpu, name, variant, monkeypatch):
-    """Every Jacobian kernel -- one block per tile with per-position loads (THCM_ASM_PIPE=0), with TMA staging at 5 / 4
-    blocks per SM (1, the default / 4) and the persistent TMA-pipelined one at 2 / 3 CTAs per SM -- must give the oracle's
-    values bit for bit, repeatedly (the pipelined kernel recycles its stages)."""
+    """Both Jacobian kernel families -- one block per tile with per-position loads (THCM_ASM_PIPE=0) and the TMA-staged row-group
+    pair (1, the default) -- must give the oracle's values bit for bit, repeatedly: from the second assembly on the default kernels
+    skip the all-LAND tiles, whose identity rows the first assembly wrote (the states below are non-zero on LAND on purpose)."""
     monkeypatch.setenv("THCM_ASM_PIPE", variant)
     s, landm, o, t = setup(gpu, name)
-    for seed in (1, 2):
+    for seed in (1, 2, 3):
         x = cases.random_state(s, landm, scale=0.3, zero_on_land=False, seed=seed)
         t.evaluate(dev(x), None, True)
         vo, missing = o.jacobian_graph(x)
