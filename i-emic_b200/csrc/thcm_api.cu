@@ -216,6 +216,7 @@ void thcmb_get_graph(const thcmb_ctx* c, int* rowptr, int* col) {
     memcpy(rowptr, c->rowptr_host.data(), sizeof(int) * c->rowptr_host.size());
     memcpy(col, c->col_host.data(), sizeof(int) * c->col_host.size());
 }
+void thcmb_tile_counts(const thcmb_ctx* c, int* ntiles, int* nactive) { *ntiles = c->n_asm_blocks; *nactive = c->n_active_tiles; }
 int thcmb_halo_size(const thcmb_ctx* c) { return NUN * c->blk.nhalo_cells(); }
 void thcmb_halo_gids(const thcmb_ctx* c, int* gids) { memcpy(gids, c->halo_gid.data(), sizeof(int) * c->halo_gid.size()); }
 void thcmb_local_gids(const thcmb_ctx* c, int* gids) { memcpy(gids, c->local_gid.data(), sizeof(int) * c->local_gid.size()); }

@@ -103,7 +103,7 @@ def load_library(path=None):
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
-        "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
+        "thcmb_tile_counts": (None, [vp, vp, vp]), "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
         "thcmb_dot": (d, [vp, i, vp, vp]), "thcmb_nrm2": (d, [vp, i, vp]), "thcmb_axpby": (i, [vp, i, d, vp, d, vp]),
         "thcmb_scale": (i, [vp, i, d, vp]), "thcmb_build_precon": (i, [vp, i]), "thcmb_apply_precon_dev": (i, [vp, vp, vp]),
         "thcmb_gmres": (i, [vp, vp, vp, d, i, i, i, vp, i, C.POINTER(KrylovResult)]),
@@ -444,6 +444,12 @@ class THCM:
                 out[self.L_.thcmb_kernel_name(kid).decode()] = (n.value, ms.value)
         return out
 
+    def tile_counts(self):
+        """(tiles of 32 cells in this rank's block, tiles the Jacobian kernels revisit on every assembly = not all-LAND)."""
+        a, b = C.c_int(), C.c_int()
+        self.L_.thcmb_tile_counts(self.ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def launch_count(self):
         return self.L_.thcmb_launch_count(self.ctx)
 
@@ -635,6 +641,18 @@ class FortranABI:
         B = np.empty_like(un)
         self.L_.rhs_(_np_ptr(un), _np_ptr(B))
         return B
+
+    def rhs_inplace(self, un):
+        """rhs_ into a reused caller-owned buffer (what THCM.C:1001 does every call): returns that buffer."""
+        if getattr(self, "_B", None) is None or self._B.shape != un.shape:
+            self._B = np.empty_like(un)
+        self.L_.rhs_(_np_ptr(un), _np_ptr(self._B))
+        return self._B
+
+    def matrix_inplace(self, un):
+        """matrix_ into the buffers handed to set_pointers (THCM.C:1066), no copies on the Python side: returns the entry count."""
+        self.L_.matrix_(_np_ptr(un))
+        return int(self.begA[self.ndim] - 1)
 
     def matrix(self, un):
         un = np.ascontiguousarray(un, dtype=np.float64)

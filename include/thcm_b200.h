@@ -202,6 +202,9 @@ const char* thcmb_last_error(void);
 void thcmb_local_block(const thcmb_ctx* c, int* i0, int* j0, int* n0, int* m0, int* npN, int* npM);
 int thcmb_ndim_local(const thcmb_ctx* c);  /* 6*n0*m0*L owned unknowns */
 long long thcmb_graph_nnz(const thcmb_ctx* c);
+/* tiles of 32 cells of this rank's block, and how many of them hold at least one non-LAND cell (the Jacobian kernels write the identity
+ * rows of the all-LAND tiles once and revisit only the others) */
+void thcmb_tile_counts(const thcmb_ctx* c, int* ntiles, int* nactive);
 /* static maximal graph of the owned rows (THCM.C:2300-2580): 0-based CSR, columns sorted ascending by global id;
  * col[] holds LOCAL column ids: < ndim_local owned, >= ndim_local halo slot (see thcmb_halo_gids) */
 void thcmb_get_graph(const thcmb_ctx* c, int* rowptr, int* col);
