@@ -971,8 +971,16 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
         // resident blocks per SM x independent phase-A loads per thread, measured at 1 degree (Newton step, profiles/bench_r01g_*,
         // profiles/r02/bench_r02a_THCM_FUSED2_BPS_*): 2 x 8 (92 registers) 75.6 ms, 3 x 4 (78 registers) 74.5 ms = kept, 4 x 4 (64
         // registers) 77.5 ms, 3 x 8 74.3 ms (within noise).  The live tiles stay below the L2 size: 3 x 148 x nv x 4 KB = 89 MB at nv = 50
-        const int grid = std::max(1, std::min(std::min(ntiles, NSM * 3), MD_BLOCKS));
-        fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        // Above ~32 vectors the live tiles of 3 blocks per SM (444 x nv x 4 KB) no longer stay in the L2: ncu at nv = 49 (profiles/r02/
+        // ncu_full_r02f_summary.json) shows 2.42 GB of DRAM traffic for 1.69 GB of algorithmic bytes -- phase B re-reads from HBM.  Two
+        // blocks per SM (296 x nv x 4 KB = 59 MB at nv = 50) with 8 loads in flight per thread keep phase B in the L2.
+        if (nv > 32) {
+            const int grid = std::max(1, std::min(std::min(ntiles, NSM * 2), MD_BLOCKS));
+            fused2_axpy_dot_kernel<2, 8><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        } else {
+            const int grid = std::max(1, std::min(std::min(ntiles, NSM * 3), MD_BLOCKS));
+            fused2_axpy_dot_kernel<3, 4><<<grid, F2_THREADS, 0, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
+        }
         c->launches++;
         return 0;
     }
@@ -1145,34 +1153,47 @@ int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
 // of the stored Jacobian, invert it with partial pivoting (w and p rows have no diagonal entry on
 // ocean cells, spf.F90:176,340), fall back to the identity when a block is numerically singular.
 // ---------------------------------------------------------------------------
-__global__ void blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col, const double* __restrict__ val,
-                                       double* __restrict__ minv) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= ncell) return;
-    double A[NUN][NUN], B[NUN][NUN];
-    for (int r = 0; r < NUN; r++) for (int q = 0; q < NUN; q++) { A[r][q] = 0.0; B[r][q] = r == q ? 1.0 : 0.0; }
-    for (int r = 0; r < NUN; r++) {
-        int row = NUN * cell + r;
-        for (int q = rp[row]; q < rp[row + 1]; q++) {
-            int cc = col[q] - NUN * cell;
-            if (cc >= 0 && cc < NUN) A[r][cc] = val[q];
+// 32 cells per block: one thread per ROW gathers the row's in-cell entries into shared memory (six times the parallelism of a thread
+// per cell, loops of 7..24 instead of 104 entries), one thread per cell inverts its block, all threads store the inverses coalesced.
+constexpr int BDB_CELLS = 32, BDB_THREADS = BDB_CELLS * NUN;
+__global__ void __launch_bounds__(BDB_THREADS) blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col,
+                                                                      const double* __restrict__ val, double* __restrict__ minv) {
+    __shared__ double sA[BDB_CELLS][NUN * NUN + 1];     // (+1: the per-cell inversion walks the rows of 32 different blocks at once)
+    const int cell0 = blockIdx.x * BDB_CELLS;
+    const int lc = threadIdx.x / NUN, r = threadIdx.x - lc * NUN;
+    const int cell_r = cell0 + lc;
+#pragma unroll
+    for (int q = 0; q < NUN; q++) sA[lc][r * NUN + q] = 0.0;
+    if (cell_r < ncell) {
+        const int row = NUN * cell_r + r;
+        for (int q = __ldg(rp + row); q < __ldg(rp + row + 1); q++) {
+            const int cc = __ldg(col + q) - NUN * cell_r;
+            if (cc >= 0 && cc < NUN) sA[lc][r * NUN + cc] = __ldg(val + q);
         }
     }
-    bool singular = false;
-    for (int p = 0; p < NUN; p++) {
-        int piv = p; double best = fabs(A[p][p]);
-        for (int r = p + 1; r < NUN; r++) if (fabs(A[r][p]) > best) { best = fabs(A[r][p]); piv = r; }
-        if (best < 1e-14) { singular = true; break; }
-        if (piv != p) for (int q = 0; q < NUN; q++) { double t = A[p][q]; A[p][q] = A[piv][q]; A[piv][q] = t; t = B[p][q]; B[p][q] = B[piv][q]; B[piv][q] = t; }
-        double d = 1.0 / A[p][p];
-        for (int q = 0; q < NUN; q++) { A[p][q] *= d; B[p][q] *= d; }
-        for (int r = 0; r < NUN; r++) if (r != p) {
-            double f = A[r][p];
-            if (f != 0.0) for (int q = 0; q < NUN; q++) { A[r][q] -= f * A[p][q]; B[r][q] -= f * B[p][q]; }
+    __syncthreads();
+    if (threadIdx.x < BDB_CELLS && cell0 + (int)threadIdx.x < ncell) {
+        const int c = threadIdx.x;
+        double A[NUN][NUN], B[NUN][NUN];
+        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) { A[i][q] = sA[c][i * NUN + q]; B[i][q] = i == q ? 1.0 : 0.0; }
+        bool singular = false;
+        for (int p = 0; p < NUN; p++) {
+            int piv = p; double best = fabs(A[p][p]);
+            for (int i = p + 1; i < NUN; i++) if (fabs(A[i][p]) > best) { best = fabs(A[i][p]); piv = i; }
+            if (best < 1e-14) { singular = true; break; }
+            if (piv != p) for (int q = 0; q < NUN; q++) { double t = A[p][q]; A[p][q] = A[piv][q]; A[piv][q] = t; t = B[p][q]; B[p][q] = B[piv][q]; B[piv][q] = t; }
+            double d = 1.0 / A[p][p];
+            for (int q = 0; q < NUN; q++) { A[p][q] *= d; B[p][q] *= d; }
+            for (int i = 0; i < NUN; i++) if (i != p) {
+                double f = A[i][p];
+                if (f != 0.0) for (int q = 0; q < NUN; q++) { A[i][q] -= f * A[p][q]; B[i][q] -= f * B[p][q]; }
+            }
         }
+        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) sA[c][i * NUN + q] = singular ? (i == q ? 1.0 : 0.0) : B[i][q];
     }
-    for (int r = 0; r < NUN; r++) for (int q = 0; q < NUN; q++)
-        minv[(size_t)cell * 36 + r * NUN + q] = singular ? (r == q ? 1.0 : 0.0) : B[r][q];
+    __syncthreads();
+    const int nloc = min(BDB_CELLS, ncell - cell0) * NUN * NUN;
+    for (int i = threadIdx.x; i < nloc; i += BDB_THREADS) minv[(size_t)cell0 * NUN * NUN + i] = sA[i / (NUN * NUN)][i % (NUN * NUN)];
 }
 __global__ void blockdiag_apply_kernel(int ncell, const double* __restrict__ minv, const double* __restrict__ x, double* __restrict__ y) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1249,7 +1270,7 @@ int build_blockdiag(thcmb_ctx* c) {
     int ncell = c->blk.ncell();
     if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));
     ProfScope prof_(c, KID_PRECON_BUILD);
-    blockdiag_build_kernel<<<(ncell + 127) / 128, 128, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_minv);
+    blockdiag_build_kernel<<<std::max(1, (ncell + BDB_CELLS - 1) / BDB_CELLS), BDB_THREADS, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_minv);
     c->launches++;
     return 0;
 }

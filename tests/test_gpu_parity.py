@@ -493,6 +493,39 @@ def test_idrs_history_matches_reference_templates(gpu, name, prec):
     t.close()
 
 
+@pytest.mark.parametrize("variant", ["plain", "mixing_coupled"])
+def test_one_degree_bit_exact_against_the_host_twin(gpu, variant):
+    """The HEADLINE size (BASELINE configs[3], 360x152x24: 7.88 M unknowns, 134.9 M graph entries) on the GPU against the host twin of the
+    device functions (tests/emu: thcm_cell.cuh compiled for the host), residual and every Jacobian value bit for bit -- plain, and with
+    Mixing = 1 plus the coupled ocean block.  The twin itself equals the oracle's dense Al / An path at this size bit for bit
+    (tests/test_zzz_configs.py::test_one_degree_device_functions_bit_exact, 40 GB on the CPU; log under profiles/)."""
+    from emu.emu import EmuTHCM
+    flags = dict(vmix=1, coupled_T=1, coupled_S=1) if variant == "mixing_coupled" else {}
+    pars = dict(PARS, SUNP=1.0) if variant == "mixing_coupled" else PARS
+    s, landm = cases.global_synth(360, 152, 24, **flags)
+    t = gpu.THCM(s, landm)
+    e = EmuTHCM(s, landm)
+    for k, v in pars.items():
+        t.setParameter(k, v)
+        e.setpar(P[k], v)
+    if variant == "mixing_coupled":
+        fields, atmos, seaice = cases.coupled_inputs(s)
+        cases.apply_coupled(e, fields, atmos, seaice)
+        for k, f in fields.items():
+            t.insertSurfaceField(ORACLE_TO_INSERT[k], f)
+        t.setAtmosphereParameters(atmos)
+        t.setSeaIceParameters(seaice)
+    for seed, on_land in ((20261017, True), (5, False)):       # the second assembly skips the all-LAND tiles: their rows must still be right
+        x = cases.consistent_state(s, landm, scale=0.05, seed=seed) if on_land else cases.random_state(s, landm, scale=0.05, zero_on_land=False, seed=seed)
+        xd = dev(x)
+        out = t.new_vector()
+        t.rhs_fortran_sign(xd, out)
+        assert np.array_equal(out.cpu().numpy(), e.rhs(x))
+        t.evaluate(xd, None, True)
+        assert np.array_equal(t.jacobian_values_host(), e.jacobian(x))
+    t.close()
+
+
 def test_full_size_properties_1deg(gpu):
     """BASELINE config 4 (360x152x24): properties that do not need the oracle -- identity rows, FD consistency of J with F
     along a random direction, salt conservation of the S columns, SpMV linearity, CRS == graph product."""
