@@ -7,4 +7,4 @@ sm_100a; there is no CPU fallback -- loading fails loudly when the extension is 
 from .params import PAR_INDEX, PAR_NAMES, par_index            # noqa: F401
 from .masks import read_mask, write_mask, synthetic_global_mask, all_ocean_mask  # noqa: F401
 from .thcm import (Settings, THCM, Ocean, lib, lib_path, load_library, KrylovResult,  # noqa: F401
-                   FortranABI, ThetaOcean)
+                   FortranABI, ThetaOcean, last_error)

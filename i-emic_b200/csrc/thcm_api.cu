@@ -472,8 +472,14 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
     const bool prec = flags & 1, flexible = flags & 4, batched = flags & 8;
     const int m = restart;
     long long n_reorth = 0;
-    if (batched && m > 63) fatal("batched (DGKS) orthogonalisation supports GMRES restart <= 63");
-    if (m + 2 > 4000) fatal("GMRES restart too large for the device scalar buffer");
+    // argument errors of the handle API are reported, not fatal (thcmb_last_error); the Fortran symbols keep the reference's abort semantics.
+    // Batched orthogonalisation works through the basis in chunks of 64 vectors, so the reference's 500 Krylov vectors
+    // (run/ocean/solver_params.xml) are fine; the limit is the pinned scalar buffer (two pipelined slots of 3 (m + 2) + 8 doubles)
+    if (m < 1 || (batched ? 2 * (3 * (m + 18) + 8) > 3800 : m + 3 > 3800)) {
+        set_error("thcmb_gmres: restart length " + std::to_string(m) + " outside the supported range (1 .. " + (batched ? "600" : "3796") + ")");
+        if (res) { res->status = -1; res->iters = 0; res->resid = 0.0; res->nhist = 0; res->n_matvec = 0; }
+        return -1;
+    }
     // Ocean-only Krylov space (default; THCM_KRYLOV_COMPACT=0 or flag 16 switch it off): rows of LAND cells are identity rows, so when b
     // and the initial guess vanish on LAND -- checked, over all ranks -- every Krylov vector does; the caller's vectors are gathered once
     // and the solution is scattered back at the end
@@ -525,7 +531,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
             // ---- one Arnoldi step on the device: w = A M^-1 v_i, orthogonalised against V[0..i], V[i+1] = w / ||w||, and the
             //      column of H copied to pinned host slot `slot` (async).  MGS follows GMRESSolver.H:177-187 statement by
             //      statement; batched = classical Gram-Schmidt with the DGKS criterion (Belos "DGKS", Ocean.C:977-1024).
-            constexpr int S = 80, HSLOT = 256;   // batched dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] ||w||^2, [3S+1] ||w||
+            const int S = std::max(80, (m + 2 + 15) / 16 * 16), HSLOT = 3 * S + 8;   // batched dh layout: [0,S) h1 + ww_old, [S,2S) ww_new, [2S,3S) h2, [3S] ||w||^2, [3S+1] ||w||
             // fused head (compact space, block-diagonal preconditioner, flexible, batched): the orthogonalisation works in a buffer of
             // its own (wbuf); the next step's first kernel turns it into V[i+1] = w / ||w|| AND Z[i+1] = M^-1 V[i+1] AND pushes the halo of
             // Z[i+1] -- scale_invsqrt + blockdiag_apply + halo push in one launch.  V[i+1] of the LAST step of a cycle is never formed:
@@ -558,7 +564,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     std::vector<double*> vp(nv);
                     for (int k = 0; k < nv; k++) vp[k] = V(k);
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
-                    const bool fused_cgs2 = (c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0;
+                    const bool fused_cgs2 = (c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0 && nv <= 64;   // (one kernel holds up to 64 basis pointers)
                     if (!fused_cgs2) THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));   // h2 of a skipped second pass
                     multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
                     if (fused_cgs2) {

@@ -908,7 +908,12 @@ static P2PArgs p2p_vec_args(thcmb_ctx* c) {
 }
 
 int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out) {
-    if (nv > MD_MAXV) fatal("multi_dot: too many vectors (GMRES restart must be <= 63 with batched orthogonalisation)");
+    if (nv > MD_MAXV) {
+        // more basis vectors than one kernel takes: chunks of MD_MAXV in increasing order -- every chunk leaves w.w behind its last
+        // projection, the next chunk overwrites that slot with its first projection, the last chunk's lands at d_out[nv]
+        for (int q0 = 0; q0 < nv; q0 += MD_MAXV) multi_dot_dev(c, n, std::min(MD_MAXV, nv - q0), vecs + q0, w, d_skip, d_out + q0);
+        return 0;
+    }
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
@@ -920,6 +925,10 @@ int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double
     return c->p2p_on ? 0 : allreduce_dev(c, d_out, nv + 1);
 }
 int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w) {
+    if (nv > MD_MAXV) {
+        for (int q0 = 0; q0 < nv; q0 += MD_MAXV) multi_axpy_dev(c, n, std::min(MD_MAXV, nv - q0), vecs + q0, d_h + q0, d_skip, w);
+        return 0;
+    }
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     ProfScope prof_(c, KID_MULTIAXPY);
@@ -929,6 +938,11 @@ int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const doubl
 }
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
                        const double* d_ww_old, int* d_flag_out, double* d_final_out) {
+    if (nv > MD_MAXV) {   // all but the last chunk only update; the last one also takes the norm of the fully updated vector
+        const int last0 = (nv - 1) / MD_MAXV * MD_MAXV;
+        multi_axpy_dev(c, n, last0, vecs, d_h, d_skip, w);
+        return multi_axpy_dot_dev(c, n, nv - last0, vecs + last0, d_h + last0, d_skip, w, d_ww, d_ww_old, d_flag_out, d_final_out);
+    }
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     { ProfScope prof_(c, KID_MULTIAXPY);
@@ -1153,29 +1167,33 @@ int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
 // of the stored Jacobian, invert it with partial pivoting (w and p rows have no diagonal entry on
 // ocean cells, spf.F90:176,340), fall back to the identity when a block is numerically singular.
 // ---------------------------------------------------------------------------
-// 32 cells per block: one thread per ROW gathers the row's in-cell entries into shared memory (six times the parallelism of a thread
-// per cell, loops of 7..24 instead of 104 entries), one thread per cell inverts its block, all threads store the inverses coalesced.
-constexpr int BDB_CELLS = 32, BDB_THREADS = BDB_CELLS * NUN;
-__global__ void __launch_bounds__(BDB_THREADS) blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col,
-                                                                      const double* __restrict__ val, double* __restrict__ minv) {
-    __shared__ double sA[BDB_CELLS][NUN * NUN + 1];     // (+1: the per-cell inversion walks the rows of 32 different blocks at once)
+// 128 cells per block.  Gather: the 6 x 128 rows of the block are walked by all threads (thread t takes rows t, t + 128, ...: consecutive
+// threads read consecutive rows), each row's in-cell entries go to shared memory; rows of LAND cells are identity rows and are not read at
+// all (half of a global grid).  Inversion: one thread per cell, every thread busy.  Store: coalesced from shared memory.
+constexpr int BDB_CELLS = 128;
+__global__ void __launch_bounds__(BDB_CELLS) blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col,
+                                                                    const double* __restrict__ val, const unsigned char* __restrict__ landcell,
+                                                                    double* __restrict__ minv) {
+    extern __shared__ double sA[];                      // [BDB_CELLS][37] (+1: the inversion walks the rows of 128 different blocks at once)
+    constexpr int LD = NUN * NUN + 1;
     const int cell0 = blockIdx.x * BDB_CELLS;
-    const int lc = threadIdx.x / NUN, r = threadIdx.x - lc * NUN;
-    const int cell_r = cell0 + lc;
-#pragma unroll
-    for (int q = 0; q < NUN; q++) sA[lc][r * NUN + q] = 0.0;
-    if (cell_r < ncell) {
-        const int row = NUN * cell_r + r;
+    for (int i = threadIdx.x; i < BDB_CELLS * LD; i += BDB_CELLS) sA[i] = 0.0;
+    __syncthreads();
+    for (int lr = threadIdx.x; lr < BDB_CELLS * NUN; lr += BDB_CELLS) {
+        const int lc = lr / NUN, r = lr - lc * NUN, cell = cell0 + lc;
+        if (cell >= ncell) continue;
+        if (landcell && __ldg(landcell + cell)) { sA[lc * LD + r * NUN + r] = 1.0; continue; }
+        const int row = NUN * cell + r;
         for (int q = __ldg(rp + row); q < __ldg(rp + row + 1); q++) {
-            const int cc = __ldg(col + q) - NUN * cell_r;
-            if (cc >= 0 && cc < NUN) sA[lc][r * NUN + cc] = __ldg(val + q);
+            const int cc = __ldg(col + q) - NUN * cell;
+            if (cc >= 0 && cc < NUN) sA[lc * LD + r * NUN + cc] = __ldg(val + q);
         }
     }
     __syncthreads();
-    if (threadIdx.x < BDB_CELLS && cell0 + (int)threadIdx.x < ncell) {
-        const int c = threadIdx.x;
+    const int c = threadIdx.x;
+    if (cell0 + c < ncell && !(landcell && __ldg(landcell + cell0 + c))) {
         double A[NUN][NUN], B[NUN][NUN];
-        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) { A[i][q] = sA[c][i * NUN + q]; B[i][q] = i == q ? 1.0 : 0.0; }
+        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) { A[i][q] = sA[c * LD + i * NUN + q]; B[i][q] = i == q ? 1.0 : 0.0; }
         bool singular = false;
         for (int p = 0; p < NUN; p++) {
             int piv = p; double best = fabs(A[p][p]);
@@ -1189,11 +1207,11 @@ __global__ void __launch_bounds__(BDB_THREADS) blockdiag_build_kernel(int ncell,
                 if (f != 0.0) for (int q = 0; q < NUN; q++) { A[i][q] -= f * A[p][q]; B[i][q] -= f * B[p][q]; }
             }
         }
-        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) sA[c][i * NUN + q] = singular ? (i == q ? 1.0 : 0.0) : B[i][q];
+        for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) sA[c * LD + i * NUN + q] = singular ? (i == q ? 1.0 : 0.0) : B[i][q];
     }
     __syncthreads();
     const int nloc = min(BDB_CELLS, ncell - cell0) * NUN * NUN;
-    for (int i = threadIdx.x; i < nloc; i += BDB_THREADS) minv[(size_t)cell0 * NUN * NUN + i] = sA[i / (NUN * NUN)][i % (NUN * NUN)];
+    for (int i = threadIdx.x; i < nloc; i += BDB_CELLS) minv[(size_t)cell0 * NUN * NUN + i] = sA[(i / (NUN * NUN)) * LD + i % (NUN * NUN)];
 }
 __global__ void blockdiag_apply_kernel(int ncell, const double* __restrict__ minv, const double* __restrict__ x, double* __restrict__ y) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1270,7 +1288,9 @@ int build_blockdiag(thcmb_ctx* c) {
     int ncell = c->blk.ncell();
     if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));
     ProfScope prof_(c, KID_PRECON_BUILD);
-    blockdiag_build_kernel<<<std::max(1, (ncell + BDB_CELLS - 1) / BDB_CELLS), BDB_THREADS, 0, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val, c->d_minv);
+    const size_t smem = sizeof(double) * BDB_CELLS * (NUN * NUN + 1);
+    blockdiag_build_kernel<<<std::max(1, (ncell + BDB_CELLS - 1) / BDB_CELLS), BDB_CELLS, smem, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val,
+                                                                                                            c->d_landcell, c->d_minv);
     c->launches++;
     return 0;
 }

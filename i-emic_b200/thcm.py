@@ -71,6 +71,11 @@ class KrylovResult(C.Structure):
 _lib = None
 
 
+def last_error():
+    """The message of the last argument / runtime error the handle API reported (thcmb_last_error)."""
+    return load_library().thcmb_last_error().decode()
+
+
 def load_library(path=None):
     """Loads libthcm_b200.so.  Fails loudly when it has not been built (there is no fallback)."""
     global _lib

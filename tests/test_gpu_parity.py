@@ -493,6 +493,33 @@ def test_idrs_history_matches_reference_templates(gpu, name, prec):
     t.close()
 
 
+def test_batched_gmres_with_the_reference_restart_length(gpu):
+    """run/ocean/solver_params.xml asks for 500 Krylov vectors and no restart: the batched (DGKS) orthogonalisation works through a basis
+    of more than 64 vectors in chunks -- same history as the template's modified Gram-Schmidt (1e-10), on the ocean-only space and on
+    full-length vectors; an unusable restart length is reported through thcmb_last_error, not by aborting the process."""
+    s, landm, o, t = setup(gpu, "natl8")
+    x = cases.consistent_state(s, landm, scale=0.1)
+    F = t.new_vector()
+    t.evaluate(dev(x), F, True)
+    t.buildPreconditioner(1)
+    out = {}
+    for key, kw in (("mgs", dict(ortho="mgs")), ("dgks", dict(ortho="dgks")), ("dgks_full", dict(ortho="dgks", full_space=True))):
+        sol = t.new_vector()
+        res, hist = t.gmres(F, sol, tol=1e-13, maxit=149, restart=500, **kw)
+        out[key] = (res.iters, hist, sol.cpu().numpy())
+    it0, h0, s0 = out["mgs"]
+    assert it0 > 70                                     # the chunked path (> 64 basis vectors) really ran
+    for key in ("dgks", "dgks_full"):
+        it1, h1, s1 = out[key]
+        k = min(len(h0), len(h1))
+        assert abs(it0 - it1) <= 1 and np.abs(h0[:k] - h1[:k]).max() <= 1e-10
+        assert np.linalg.norm(s0 - s1) <= 1e-8 * np.linalg.norm(s0)
+    sol = t.new_vector()
+    res, hist = t.gmres(F, sol, tol=1e-8, maxit=10, restart=5000, ortho="dgks")
+    assert res.status == -1 and "restart length" in gpu.last_error()
+    t.close()
+
+
 @pytest.mark.parametrize("variant", ["plain", "mixing_coupled"])
 def test_one_degree_bit_exact_against_the_host_twin(gpu, variant):
     """The HEADLINE size (BASELINE configs[3], 360x152x24: 7.88 M unknowns, 134.9 M graph entries) on the GPU against the host twin of the
