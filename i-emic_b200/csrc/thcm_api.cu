@@ -14,6 +14,7 @@
 #include <fstream>
 #include <memory>
 #include "thcm_internal.h"
+#include "thcm_slots.h"
 
 using namespace thcm;
 
@@ -110,6 +111,15 @@ void build_static(thcmb_ctx* c) {
     THCM_CUDA(cudaMalloc(&c->d_sendbuf, sizeof(double) * NUN * (size_t)std::max(c->nsend_cells, 1)));
     THCM_CUDA(cudaMalloc(&c->d_recvbuf, sizeof(double) * NUN * (size_t)std::max(c->nrecv_cells, 1)));
     upload_class_tables(class_tables(c->blk.periodic));
+    {   // where the 6x6 in-cell block sits inside the sorted graph rows, per boundary class (block-diagonal preconditioner)
+        const ClassTables& ct = class_tables(c->blk.periodic);
+        std::vector<signed char> cpos((size_t)NCLASS * NUN * NUN, (signed char)-1);
+        for (int cls = 0; cls < NCLASS; cls++) for (int R = 1; R <= NUN; R++) for (int C = 1; C <= NUN; C++) {
+            const int sl = slot_of(R, 5, C);
+            if (sl >= 0) cpos[((size_t)cls * NUN + (R - 1)) * NUN + (C - 1)] = (signed char)ct.pos[cls][ROW_OFF[R - 1] + sl];
+        }
+        upload(c->d_cpos, cpos);
+    }
 }
 
 void stage_begin(thcmb_ctx* c) { THCM_CUDA(cudaEventRecord(c->ev0, c->stream)); }
@@ -196,7 +206,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff,
                     (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell, (void*)c->d_colc, (void*)c->d_send_cidx,
-                    (void*)c->d_iccoeff_c, (void*)c->d_active_tiles})
+                    (void*)c->d_iccoeff_c, (void*)c->d_active_tiles, (void*)c->d_cpos})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) if (p) cudaFree(p);
     for (double* p : c->d_work) if (p) cudaFree(p);

@@ -560,6 +560,124 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
     }
 }
 
+// =============================================================================
+// Matrix-free residual with TMA staging (MODE_RHS default since round 2; the per-position kernel thcm_assemble_kernel<RHS> needed
+// ~240 instructions per warp for its staging and ran at 7 % of the HBM roofline).  Same prologue as the Jacobian kernels: the six
+// grid lines the rows read arrive as cp.async.bulk runs of raw 48-byte records together with the tile descriptor and the table
+// records.  The records STAY raw -- matAvec multiplies the raw unknowns (matetc.F90:160-164) -- and the accessor applies usol's
+// no-slip / lid rules (usrc.F90:1014-1121) from the descriptor's bit masks when an atom reads u, v or w.  Five warps = five row
+// types (u | v | w + p | T | S), no output staging: every lane owns one cell and writes its rows.  Tiles that are entirely LAND
+// are not visited (B = 0 there, usrc.F90:580-591: the output is zeroed first and the blocks walk the list of the other tiles).
+// =============================================================================
+constexpr int RHS_LINES = 0xBE;   // union of the row groups' lines
+struct alignas(16) RhsSmem {
+    Stage<RHS_LINES> st;
+    unsigned long long bar;
+};
+template <class ST> struct RhsTile {
+    const ST* st; int lane;
+    __device__ __forceinline__ double operator()(int sv, int di, int dj, int dk) const {
+        const int r = (dk + 1) * 3 + (dj + 1), x = lane + 1 + di;
+        if (sv >= SV_RAW) return st->rec[ST::slot(r)][x][sv - SV_RAW];
+        const double v = st->rec[ST::slot(r)][x][sv <= SV_W ? sv : sv + 1];   // u v w . T S
+        if (sv <= SV_V) return ((st->desc.uvbits[r] >> x) & 1ull) ? v : 0.0;
+        if (sv == SV_W) return ((st->desc.wbits[r] >> x) & 1ull) ? v : 0.0;
+        return v;
+    }
+};
+template <int R, bool CPL, class ST>
+__device__ __forceinline__ void rhs_row(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, bool open_ocean) {
+    if (lane >= g.ncell) return;
+    const DevBlock& b = a.b;
+    const uint32_t nb = st.desc.nbmask[lane];
+    const double sm = (double)((st.desc.surfbits >> lane) & 1u);
+    const int cell = g.cell0 + lane;
+    const Cell c{g.gi0 + lane, g.gj, g.k, cell % b.n0, g.lj};
+    const RhsTile<ST> tile{&st, lane};
+    const PipeTabs<ST> tabs{&st};
+    double E[RowSlots<R>::N];
+    if (!((nb >> 4) & 1u)) eval_row<R, false, CPL>(E, a.t, b, c, sm, tile, tabs);
+    if (!open_ocean) boundaries<R>(E, nb, c.gi < b.N, c.gj < b.M);
+#pragma unroll
+    for (int q = 0; q < RowSlots<R>::N; q++) E[q] = fabs(E[q]) > DROP_TOL ? E[q] : 0.0;   // fillcolA's threshold (assemble.F90:115)
+    // matAvec (matetc.F90:160-164): v2 = coA*v1(jcoA) + v2 in CRS order = slot order
+    double s = 0.0;
+    static_for<0, RowSlots<R>::N>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        constexpr int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
+        const int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
+        const bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
+        if (E[q] != 0.0 && inside) s = E[q] * tile(SV_RAW + col - 1, loc_di(loc), loc_dj(loc), loc_dk(loc)) + s;
+    });
+    const int row = NUN * cell + R - 1;
+    double mixv = 0.0;
+    if constexpr (R == TT || R == SS) mixv = vmix_rhs<R>(a.t, c, nb, tile, tabs);   // vmix_fun, usrc.F90:551-571
+    double B = -s - mixv + a.frc[row] - 0.0;                                          // usrc.F90:576
+    B = B * (((nb >> 4) & 1u) ? 0.0 : 1.0);                                           // usrc.F90:580-591
+    a.out[row] = a.sign * B;
+}
+template <bool CPL>
+__global__ void __launch_bounds__(160) thcm_rhs_tma_kernel(const AsmArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RhsSmem& sh = *reinterpret_cast<RhsSmem*>(smem_raw);
+    using ST = Stage<RHS_LINES>;
+    ST& st = sh.st;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = a.tile_list ? a.tile_list[blockIdx.x] : (int)blockIdx.x;
+    const TileGeom g = tile_geom_of(a.b, tile);
+    const int w = g.ncell + 2;
+    if (threadIdx.x == 0) {
+        mbar_init(&sh.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            mbar_expect_tx(&sh.bar, (uint32_t)(ST::NL * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
+        __syncwarp();
+        if (lane < 9) {
+            if ((RHS_LINES >> lane) & 1) {
+                LineSeg seg[3];
+                const int ns = line_plan(a.b, g, lane, seg);
+#pragma unroll
+                for (int q = 0; q < 3; q++)
+                    if (q < ns)
+                        bulk_load(&st.rec[ST::slot(lane)][seg[q].x0][0], (seg[q].halo ? a.halo : a.un) + (size_t)NUN * seg[q].idx,
+                                  (uint32_t)(seg[q].n * NUN * sizeof(double)), &sh.bar);
+            }
+        } else if (lane == 9) bulk_load(&st.desc, a.tdesc + tile, sizeof(TileDesc), &sh.bar);
+        else if (lane == 10) bulk_load(st.tj, a.jrec + (size_t)g.gj * J_COUNT * JREC, sizeof(st.tj), &sh.bar);
+        else if (lane == 11) bulk_load(st.tk, a.krec + (size_t)g.k * K_COUNT, sizeof(st.tk), &sh.bar);
+        mbar_wait(&sh.bar, 0, 4);   // one warp polls, the others sleep at the barrier
+    }
+    __syncthreads();
+    const bool open_ocean = (st.desc.flags & 2u) != 0;
+    switch (warp) {
+    case 0: rhs_row<1, CPL>(a, st, g, lane, open_ocean); break;
+    case 1: rhs_row<2, CPL>(a, st, g, lane, open_ocean); break;
+    case 2: rhs_row<3, CPL>(a, st, g, lane, open_ocean); rhs_row<4, CPL>(a, st, g, lane, open_ocean); break;
+    case 3: rhs_row<5, CPL>(a, st, g, lane, open_ocean); break;
+    default: rhs_row<6, CPL>(a, st, g, lane, open_ocean); break;
+    }
+}
+template <bool CPL> static void launch_rhs_tma_t(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        THCM_CUDA(cudaFuncSetAttribute(thcm_rhs_tma_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem)));
+        attr_set = true;
+    }
+    if (nblocks > 0) thcm_rhs_tma_kernel<CPL><<<nblocks, 160, sizeof(RhsSmem), c->stream>>>(a);
+}
+static void launch_rhs_tma(thcmb_ctx* c, AsmArgs a) {
+    int nblocks = a.ntile;
+    if (c->d_active_tiles && c->n_active_tiles < a.ntile) {   // B = 0 on the all-LAND tiles: zero everything once, visit the other tiles
+        THCM_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * (size_t)NUN * a.b.ncell, c->stream));
+        a.tile_list = c->d_active_tiles; nblocks = c->n_active_tiles;
+    }
+    if (a.t.coupled_T || a.t.coupled_S) launch_rhs_tma_t<true>(c, a, nblocks);
+    else launch_rhs_tma_t<false>(c, a, nblocks);
+}
+
 template <int GROUP, int BLOCKS_PER_SM, bool CPL> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
     using SH = TmaSmem<GROUP>;
     static bool attr_set = false;
@@ -650,7 +768,9 @@ int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, i
     switch (mode & 0xff) {
     case MODE_RHS:
         a.sign = (mode & 0x100) ? -1.0 : 1.0;
-        launch_mode<MODE_RHS>(c, a, nblk); break;
+        if (c->asm_pipe == 1) launch_rhs_tma(c, a);
+        else launch_mode<MODE_RHS>(c, a, nblk);   // THCM_ASM_PIPE=0: per-position loads
+        break;
     case MODE_JAC_GRAPH:
         if (c->asm_pipe == 1) launch_jac_tma<8, 11>(c, a);
         else { launch_mode<MODE_JAC_GRAPH>(c, a, nblk); c->land_tiles_written = true; }   // THCM_ASM_PIPE=0: per-position loads, every tile

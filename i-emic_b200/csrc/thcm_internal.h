@@ -180,6 +180,7 @@ struct thcmb_ctx {
     void* d_halo_ll[2] = {nullptr, nullptr};   // my LL halo buffers (inside the IPC-shared allocation)
     unsigned long long halo_ll_seq = 0;
     int krylov_compact = 1;          // GMRES on the ocean cells only (THCM_KRYLOV_COMPACT=0 switches it off)
+    signed char* d_cpos = nullptr;   // [64 classes][6 rows][6 cols]: position of the in-cell entry inside its sorted graph row, -1 = none
     uint8_t* d_landcell = nullptr;   // per owned cell: 1 = LAND (identity rows; the SpMV answers y = x for them without streaming the row)
     // ---- halo exchange ----
     double *d_halo = nullptr;       // 6*nhalo doubles, laid out per Block::hk

@@ -1168,30 +1168,40 @@ int halo_exchange(thcmb_ctx* c, const double* d_x, bool wait) {
 // ocean cells, spf.F90:176,340), fall back to the identity when a block is numerically singular.
 // ---------------------------------------------------------------------------
 // 128 cells per block.  Gather: the 6 x 128 rows of the block are walked by all threads (thread t takes rows t, t + 128, ...: consecutive
-// threads read consecutive rows), each row's in-cell entries go to shared memory; rows of LAND cells are identity rows and are not read at
-// all (half of a global grid).  Inversion: one thread per cell, every thread busy.  Store: coalesced from shared memory.
+// threads read consecutive rows); the in-cell entries of a row are its stencil-centre slots, whose positions inside the sorted graph row
+// only depend on the cell's boundary class (host-built table cpos[class][row][col], -1 = no such entry): one row-pointer load and at most
+// six value loads per row, no column ids, no search.  Rows of LAND cells are identity rows and are not read at all (half of a global
+// grid).  Inversion: one thread per cell, every thread busy.  Store: coalesced from shared memory.
 constexpr int BDB_CELLS = 128;
-__global__ void __launch_bounds__(BDB_CELLS) blockdiag_build_kernel(int ncell, const int* __restrict__ rp, const int* __restrict__ col,
-                                                                    const double* __restrict__ val, const unsigned char* __restrict__ landcell,
-                                                                    double* __restrict__ minv) {
+__global__ void __launch_bounds__(BDB_CELLS) blockdiag_build_kernel(DevBlock b, const int* __restrict__ rp, const double* __restrict__ val,
+                                                                    const signed char* __restrict__ cpos,
+                                                                    const unsigned char* __restrict__ landcell, double* __restrict__ minv) {
     extern __shared__ double sA[];                      // [BDB_CELLS][37] (+1: the inversion walks the rows of 128 different blocks at once)
     constexpr int LD = NUN * NUN + 1;
+    const int ncell = b.ncell;
     const int cell0 = blockIdx.x * BDB_CELLS;
-    for (int i = threadIdx.x; i < BDB_CELLS * LD; i += BDB_CELLS) sA[i] = 0.0;
-    __syncthreads();
     for (int lr = threadIdx.x; lr < BDB_CELLS * NUN; lr += BDB_CELLS) {
         const int lc = lr / NUN, r = lr - lc * NUN, cell = cell0 + lc;
-        if (cell >= ncell) continue;
-        if (landcell && __ldg(landcell + cell)) { sA[lc * LD + r * NUN + r] = 1.0; continue; }
-        const int row = NUN * cell + r;
-        for (int q = __ldg(rp + row); q < __ldg(rp + row + 1); q++) {
-            const int cc = __ldg(col + q) - NUN * cell;
-            if (cc >= 0 && cc < NUN) sA[lc * LD + r * NUN + cc] = __ldg(val + q);
+        double* dst = sA + lc * LD + r * NUN;
+        if (cell >= ncell || __ldg(landcell + cell)) {
+#pragma unroll
+            for (int q = 0; q < NUN; q++) dst[q] = q == r ? 1.0 : 0.0;
+            continue;
         }
+        const int li = cell % b.n0, rest = cell / b.n0, lj = rest % b.m0, k0 = rest / b.m0;
+        const int gi = b.i0 + li + 1, gj = b.j0 + lj + 1, k = k0 + 1;
+        const int cls = (gi == 1 ? 1 : 0) | (gi == b.N ? 2 : 0) | (gj == 1 ? 4 : 0) | (gj == b.M ? 8 : 0) | (k == 1 ? 16 : 0) | (k == b.L ? 32 : 0);
+        const signed char* cp = cpos + cls * (NUN * NUN) + r * NUN;
+        const int base = __ldg(rp + NUN * cell + r);
+        double v[NUN];
+#pragma unroll
+        for (int q = 0; q < NUN; q++) { const int pq = cp[q]; v[q] = pq >= 0 ? __ldg(val + base + pq) : 0.0; }
+#pragma unroll
+        for (int q = 0; q < NUN; q++) dst[q] = v[q];
     }
     __syncthreads();
     const int c = threadIdx.x;
-    if (cell0 + c < ncell && !(landcell && __ldg(landcell + cell0 + c))) {
+    if (cell0 + c < ncell && !__ldg(landcell + cell0 + c)) {
         double A[NUN][NUN], B[NUN][NUN];
         for (int i = 0; i < NUN; i++) for (int q = 0; q < NUN; q++) { A[i][q] = sA[c * LD + i * NUN + q]; B[i][q] = i == q ? 1.0 : 0.0; }
         bool singular = false;
@@ -1289,8 +1299,8 @@ int build_blockdiag(thcmb_ctx* c) {
     if (!c->d_minv) THCM_CUDA(cudaMalloc(&c->d_minv, sizeof(double) * 36 * (size_t)ncell));
     ProfScope prof_(c, KID_PRECON_BUILD);
     const size_t smem = sizeof(double) * BDB_CELLS * (NUN * NUN + 1);
-    blockdiag_build_kernel<<<std::max(1, (ncell + BDB_CELLS - 1) / BDB_CELLS), BDB_CELLS, smem, c->stream>>>(ncell, c->d_rowptr, c->d_col, c->d_val,
-                                                                                                            c->d_landcell, c->d_minv);
+    blockdiag_build_kernel<<<std::max(1, (ncell + BDB_CELLS - 1) / BDB_CELLS), BDB_CELLS, smem, c->stream>>>(dev_block(c->blk), c->d_rowptr, c->d_val,
+                                                                                                            c->d_cpos, c->d_landcell, c->d_minv);
     c->launches++;
     return 0;
 }
