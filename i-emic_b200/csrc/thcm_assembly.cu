@@ -586,7 +586,7 @@ template <class ST> struct RhsTile {
     }
 };
 template <int R, bool CPL, class ST>
-__device__ __forceinline__ void rhs_row(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, bool open_ocean) {
+__device__ __forceinline__ void rhs_row(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, bool open_ocean, bool interior) {
     if (lane >= g.ncell) return;
     const DevBlock& b = a.b;
     const uint32_t nb = st.desc.nbmask[lane];
@@ -602,13 +602,21 @@ __device__ __forceinline__ void rhs_row(const AsmArgs& a, const ST& st, const Ti
     for (int q = 0; q < RowSlots<R>::N; q++) E[q] = fabs(E[q]) > DROP_TOL ? E[q] : 0.0;   // fillcolA's threshold (assemble.F90:115)
     // matAvec (matetc.F90:160-164): v2 = coA*v1(jcoA) + v2 in CRS order = slot order
     double s = 0.0;
-    static_for<0, RowSlots<R>::N>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        constexpr int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
-        const int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
-        const bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
-        if (E[q] != 0.0 && inside) s = E[q] * tile(SV_RAW + col - 1, loc_di(loc), loc_dj(loc), loc_dk(loc)) + s;
-    });
+    if (interior) {   // tile-uniform: every neighbour of every cell of the tile lies inside the domain
+        static_for<0, RowSlots<R>::N>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
+            if (E[q] != 0.0) s = E[q] * tile(SV_RAW + col - 1, loc_di(loc), loc_dj(loc), loc_dk(loc)) + s;
+        });
+    } else {
+        static_for<0, RowSlots<R>::N>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr int loc = row_slots(R)[q].loc, col = row_slots(R)[q].col;
+            const int gi2 = c.gi + loc_di(loc), gj2 = c.gj + loc_dj(loc), k2 = c.k + loc_dk(loc);
+            const bool inside = gj2 >= 1 && gj2 <= b.M && k2 >= 1 && k2 <= b.L && (b.periodic || (gi2 >= 1 && gi2 <= b.N));
+            if (E[q] != 0.0 && inside) s = E[q] * tile(SV_RAW + col - 1, loc_di(loc), loc_dj(loc), loc_dk(loc)) + s;
+        });
+    }
     const int row = NUN * cell + R - 1;
     double mixv = 0.0;
     if constexpr (R == TT || R == SS) mixv = vmix_rhs<R>(a.t, c, nb, tile, tabs);   // vmix_fun, usrc.F90:551-571
@@ -652,12 +660,13 @@ __global__ void __launch_bounds__(160) thcm_rhs_tma_kernel(const AsmArgs a) {
     }
     __syncthreads();
     const bool open_ocean = (st.desc.flags & 2u) != 0;
+    const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
     switch (warp) {
-    case 0: rhs_row<1, CPL>(a, st, g, lane, open_ocean); break;
-    case 1: rhs_row<2, CPL>(a, st, g, lane, open_ocean); break;
-    case 2: rhs_row<3, CPL>(a, st, g, lane, open_ocean); rhs_row<4, CPL>(a, st, g, lane, open_ocean); break;
-    case 3: rhs_row<5, CPL>(a, st, g, lane, open_ocean); break;
-    default: rhs_row<6, CPL>(a, st, g, lane, open_ocean); break;
+    case 0: rhs_row<1, CPL>(a, st, g, lane, open_ocean, interior); break;
+    case 1: rhs_row<2, CPL>(a, st, g, lane, open_ocean, interior); break;
+    case 2: rhs_row<3, CPL>(a, st, g, lane, open_ocean, interior); rhs_row<4, CPL>(a, st, g, lane, open_ocean, interior); break;
+    case 3: rhs_row<5, CPL>(a, st, g, lane, open_ocean, interior); break;
+    default: rhs_row<6, CPL>(a, st, g, lane, open_ocean, interior); break;
     }
 }
 template <bool CPL> static void launch_rhs_tma_t(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
