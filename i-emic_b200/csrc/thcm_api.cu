@@ -548,10 +548,20 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
             // nothing reads it (the update uses Z[0..i], GMRESSolver.H:293-313).
             const bool fuse_head = batched && compact && prec && flexible && c->precon_kind == 1 && c->d_minv && !getenv("THCM_NO_FUSED_HEAD");
             double* const wbuf = fuse_head ? work_vec(c, 3) : nullptr;
+            // ... and the second Gram-Schmidt update moves into that kernel too, its norm taken from Pythagoras (RedEpilogue::flag2_out):
+            // two all-reduces and four kernels per iteration instead of three and five
+            const bool cgs2_kernel = (c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0;
+            const bool pyth_norm = fuse_head && cgs2_kernel && !getenv("THCM_EXPLICIT_NORM");
             auto enqueue = [&](int i, int slot) {
                 double* w = fuse_head ? wbuf : V(i + 1);
                 if (fuse_head && i > 0) {
-                    const unsigned long long seq = scale_precon_push(c, wbuf, c->d_scalars + 3 * S, V(i), Z(i), nullptr);
+                    // the previous step's second update (against V[0..i-1], coefficients h2 in dh[2S..], DGKS flag d_flags[0]) rides
+                    // in this kernel unless the explicit path took it (d_flags[1])
+                    std::vector<double*> vprev(i);
+                    for (int k = 0; k < i; k++) vprev[k] = V(k);
+                    const bool pyth = pyth_norm && i <= 64;
+                    const unsigned long long seq = scale_precon_push(c, wbuf, c->d_scalars + 3 * S, V(i), Z(i), nullptr, i, vprev.data(),
+                                                                     c->d_scalars + 2 * S, pyth ? c->d_flags : nullptr, c->d_flags + 1);
                     spmv_compact_rows(c, Z(i), w, seq);
                 } else if (prec) {
                     double* z = flexible ? Z(i) : tmp;
@@ -574,15 +584,17 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                     std::vector<double*> vp(nv);
                     for (int k = 0; k < nv; k++) vp[k] = V(k);
                     if (!c->d_flags) { THCM_CUDA(cudaMalloc(&c->d_flags, sizeof(int) * 8)); THCM_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int) * 8, c->stream)); }
-                    const bool fused_cgs2 = (c->p2p_on || c->blk.nranks == 1) && c->fused_cgs2 && (n & 1) == 0 && nv <= 64;   // (one kernel holds up to 64 basis pointers)
+                    const bool fused_cgs2 = cgs2_kernel && nv <= 64;   // (one kernel holds up to 64 basis pointers)
                     if (!fused_cgs2) THCM_CUDA(cudaMemsetAsync(dh + 2 * S, 0, sizeof(double) * S, c->stream));   // h2 of a skipped second pass
                     multi_dot_dev(c, n, nv, vp.data(), w, nullptr, dh);
                     if (fused_cgs2) {
                         // CGS2 with the basis read three times instead of four: w' = w - V h1 and h2 = V^T w', w'.w' in ONE sweep
                         // (+ all-reduce + DGKS decision); the second update only when the decision asks for it.  h2 lands in
                         // dh[2S..] and is used by the host only when the flag is set.
-                        fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S);
-                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
+                        const bool pyth = pyth_norm && nv <= 64;
+                        fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S, pyth ? c->d_flags + 1 : nullptr);
+                        // explicit second update + norm: always without the Pythagorean shortcut, else only when its guard tripped
+                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, pyth ? c->d_flags + 1 : c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
                     } else if (c->p2p_on || c->blk.nranks == 1) {
                         // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh, nullptr, w, dh + S, dh + nv, c->d_flags, dh + 3 * S);

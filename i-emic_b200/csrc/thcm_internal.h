@@ -307,7 +307,7 @@ int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const doubl
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
                        const double* d_ww_old, int* d_flag_out, double* d_final_out);
 int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out);
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int* d_flag2_out = nullptr);
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);
 int mgs_step_dev(thcmb_ctx* c, int n, const double* d_hk, const double* vk, const double* vnext, double* w, double* d_out);
 int nccl_unique_id(void* id128);
@@ -342,7 +342,8 @@ int gather_cells(thcmb_ctx* c, const double* in, double* out);
 int scatter_cells(thcmb_ctx* c, const double* in, double* out);
 int spmv_compact(thcmb_ctx* c, const double* xc, double* yc);   // incl. the LL halo push on more than one rank and the integral row
 int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long long seq);   // the SpMV alone: the halo of exchange `seq` was pushed by the caller
-unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out);
+unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out,
+                                     int nv, double* const* vecs, const double* d_h2, const int* d_flag, const int* d_flag2);
 bool compact_possible(const thcmb_ctx* c);
 double land_nonzero_global(thcmb_ctx* c, const double* x);
 int apply_blockdiag_compact(thcmb_ctx* c, const double* x, double* y);

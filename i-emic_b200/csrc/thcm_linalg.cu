@@ -166,13 +166,18 @@ __device__ __forceinline__ void flag_wait(volatile unsigned long long* f, unsign
 }
 
 // optional epilogue of a reduction (DGKS, thcmb_gmres): flag = (result < 0.5 * *ww_old), *final_out = result
-struct RedEpilogue { const double* ww_old; int* flag_out; double* final_out; };
+// flag2_out (batched tails only, multi_tail): the norm of the vector AFTER the second update is taken from Pythagoras,
+//   ||w' - V h2||^2 = ||w'||^2 - ||h2||^2   (V orthonormal, h2 = V^T w'),
+// both terms being in hand (all-reduced) right here -- the second update then needs no reduction of its own and moves into the
+// head kernel of the next Arnoldi step.  Guard: when the difference cancels below 1 % of ||w'||^2 the explicit update + norm
+// kernel runs instead (*flag2_out = 1).
+struct RedEpilogue { const double* ww_old; int* flag_out; double* final_out; int* flag2_out; };
 __device__ __forceinline__ void red_epilogue(double tot, const RedEpilogue ep) {
     if (ep.flag_out) *ep.flag_out = (tot < 0.5 * (*ep.ww_old)) ? 1 : 0;
     if (ep.final_out) *ep.final_out = tot;
 }
 __device__ __forceinline__ void finish_reduction(double blocksum, double* partial, unsigned int* counter, double* out, const P2PArgs pa,
-                                                 const RedEpilogue ep = RedEpilogue{nullptr, nullptr, nullptr}) {
+                                                 const RedEpilogue ep = RedEpilogue{nullptr, nullptr, nullptr, nullptr}) {
     __shared__ bool last;
     __shared__ double peer_val[P2P_MAX_RANKS];
     if (threadIdx.x == 0) {
@@ -578,6 +583,20 @@ __device__ __forceinline__ void multi_tail(int nslices, int nv, const double* pa
     } else {
         for (int q = threadIdx.x; q <= nv; q += nthreads) { out[q] = mine[q]; if (q == nv) red_epilogue(mine[q], ep); }
     }
+    if (ep.flag2_out) {
+        __syncthreads();   // out[0..nv] and the DGKS flag were written by threads of this block
+        if (threadIdx.x == 0) {
+            int f2 = 0;
+            if (*ep.flag_out) {
+                const double wwn = out[nv];
+                double s2 = 0.0;
+                for (int q = 0; q < nv; q++) s2 += out[q] * out[q];
+                const double r = wwn - s2;
+                if (r > 0.01 * wwn) *ep.final_out = r; else f2 = 1;
+            }
+            *ep.flag2_out = f2;
+        }
+    }
 }
 
 // grid = (slices, chunks): block (x, y) accumulates the projections of chunk y (8 basis vectors, + w.w for chunk 0)
@@ -638,7 +657,7 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(int n, VecList v
     }
     __syncthreads();
     if (!last) return;
-    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, RedEpilogue{nullptr, nullptr, nullptr});
+    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, RedEpilogue{nullptr, nullptr, nullptr, nullptr});
 }
 
 // Fused first update + second projection of classical Gram-Schmidt with re-orthogonalisation (CGS2 / DGKS):
@@ -948,7 +967,7 @@ int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     { ProfScope prof_(c, KID_MULTIAXPY);
       const int grid = std::min(ew_grid(n), RED_BLOCKS);
       multi_axpy_dot_kernel<<<grid, RED_THREADS, 0, c->stream>>>(n, vl, d_h, d_skip, w, c->d_partial, c->d_counter, d_ww, p2p_args(c),
-                                                                 RedEpilogue{d_ww_old, d_flag_out, d_final_out}); }
+                                                                 RedEpilogue{d_ww_old, d_flag_out, d_final_out, nullptr}); }
     c->launches++;
     if (!c->p2p_on && c->blk.nranks > 1) fatal("multi_axpy_dot needs the P2P mailboxes on multi-GPU runs (THCM_P2P=1)");
     return 0;
@@ -969,14 +988,14 @@ static void launch_fused(thcmb_ctx* c, int n, const VecList& vl, const double* d
     fused_axpy_dot_kernel<NVCAP><<<grid, FUSED_THREADS, smem, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
 }
 int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out) {
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int* d_flag2_out) {
     if (nv > MD_MAXV) fatal("fused_axpy_dot: too many vectors");
     if (n & 1) fatal("fused_axpy_dot: vector length must be even (6 unknowns per cell)");
     if (!c->p2p_on && c->blk.nranks > 1) fatal("fused_axpy_dot needs the P2P mailboxes on multi-GPU runs (THCM_P2P=1)");
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
-    const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out};
+    const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out, d_flag2_out};
     // measured (profiles/ncu_full_r01d_fused_cgs2_summary.json): at nv = 11 the shared-memory kernel <16> needs 0.17 ms, the L2-tiled one
     // 0.21 ms; averaged over nv = 1..50 it is 0.47 vs 0.40 ms (the <32..64> instantiations park up to 131 KB per block)
     if (c->fused_cgs2 == 2 && nv > 16) {
@@ -1406,29 +1425,52 @@ __global__ void blockdiag_apply_compact_kernel(int nc, const int* __restrict__ o
     for (int q = 0; q < NUN; q++) s += M[q] * xc[q];
     y[t] = s;
 }
-// Head of an Arnoldi step in ONE kernel (compact space, 6x6 block-diagonal preconditioner, flexible GMRES):
-//   v = w / sqrt(nrm2)   (GMRESSolver.H:185-186, the tail of the previous step),   z = M^-1 v   (:160-164),
+// Head of an Arnoldi step in ONE kernel (compact space, 6x6 block-diagonal preconditioner, flexible GMRES, batched orthogonalisation):
+//   w'' = w' - V h2      the SECOND Gram-Schmidt update of the previous step, when its DGKS flag asked for it (its norm is known from
+//                        Pythagoras, RedEpilogue::flag2_out; the rare explicit path has done the update already: *flag2 = 1),
+//   v = w'' / ||w''||    (GMRESSolver.H:185-186),    z = M^-1 v    (:160-164),
 //   and the halo of z pushed into the neighbours' LL buffers for the SpMV that follows.
-// w is only read (the orthogonalisation works in a buffer of its own), so the blocks that push -- they recompute z for the cells of the
-// send lists, ~2 % of the block -- need no ordering against the blocks that sweep the vector.  Replaces scale_invsqrt +
-// blockdiag_apply + halo_push: three launches and one pass over the vector less per iteration.
+// w is only read (the orthogonalisation works in a buffer of its own), so the blocks that push -- the FIRST blocks of the grid: their
+// stores travel while the others sweep the vector; they recompute z for the cells of the send lists, ~2 % of the block -- need no
+// ordering against the sweeping blocks.  Replaces multi_axpy_dot (+ its all-reduce) + scale_invsqrt + blockdiag_apply + halo_push:
+// four launches, one reduction and two passes over the vector less per iteration.
 constexpr int SPP_CELLS = 32, SPP_THREADS = SPP_CELLS * NUN;
 __global__ void __launch_bounds__(SPP_THREADS) scale_precon_push_kernel(int nc, const int* __restrict__ ocell, const double* __restrict__ minv,
                                                                         const double* __restrict__ nrm2, const double* __restrict__ w,
                                                                         double* __restrict__ v, double* __restrict__ z, double* nrm_out,
-                                                                        int main_blocks, int nsend, const int* __restrict__ cidx,
+                                                                        VecList vl, const double* __restrict__ h2, const int* __restrict__ flag,
+                                                                        const int* __restrict__ flag2,
+                                                                        int push_blocks, int nsend, const int* __restrict__ cidx,
                                                                         const int* __restrict__ dst_slot, const int* __restrict__ peer,
-                                                                        P2PSlot* const* peer_ll, unsigned int flag) {
+                                                                        P2PSlot* const* peer_ll, unsigned int llflag) {
     __shared__ double sv[SPP_THREADS];
+    __shared__ double hs[MD_MAXV];
     const double nrm = sqrt(*nrm2);
     const double a = 1.0 / nrm;
+    const bool upd = flag != nullptr && *flag != 0 && *flag2 == 0;
+    const int nv = upd ? vl.nv : 0;
+    for (int q = threadIdx.x; q < nv; q += SPP_THREADS) hs[q] = h2[q];
+    __syncthreads();
     const int r = threadIdx.x % NUN, lc = threadIdx.x / NUN;
-    if ((int)blockIdx.x < main_blocks) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
-        for (int c0 = blockIdx.x * SPP_CELLS; c0 < nc; c0 += main_blocks * SPP_CELLS) {
+    // w''[t] for one unknown: the update in the order of multi_axpy (q ascending), eight basis loads in flight
+    auto updated = [&](size_t t) {
+        double wi = w[t];
+        for (int c0 = 0; c0 < nv; c0 += MD_CHUNK) {
+            double vv[MD_CHUNK];
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) vv[q] = (c0 + q < nv) ? vl.v[c0 + q][t] : 0.0;
+#pragma unroll
+            for (int q = 0; q < MD_CHUNK; q++) if (c0 + q < nv) wi = wi - hs[c0 + q] * vv[q];
+        }
+        return wi;
+    };
+    if ((int)blockIdx.x >= push_blocks) {
+        const int mb = blockIdx.x - push_blocks, main_blocks = gridDim.x - push_blocks;
+        if (mb == 0 && threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
+        for (int c0 = mb * SPP_CELLS; c0 < nc; c0 += main_blocks * SPP_CELLS) {
             const int t = c0 * NUN + threadIdx.x;
             const bool ok = t < nc * NUN;
-            const double vi = ok ? a * w[t] : 0.0;
+            const double vi = ok ? a * updated((size_t)t) : 0.0;
             sv[threadIdx.x] = vi;
             __syncthreads();
             if (ok) {
@@ -1442,35 +1484,43 @@ __global__ void __launch_bounds__(SPP_THREADS) scale_precon_push_kernel(int nc, 
             __syncthreads();
         }
     } else {
-        const int pb = blockIdx.x - main_blocks, npb = gridDim.x - main_blocks;
-        for (int q0 = pb * SPP_CELLS; q0 < nsend; q0 += npb * SPP_CELLS) {
+        for (int q0 = blockIdx.x * SPP_CELLS; q0 < nsend; q0 += push_blocks * SPP_CELLS) {
             const int q = q0 + lc;
+            const int ci = q < nsend ? __ldg(cidx + q) : -1;
+            sv[threadIdx.x] = ci >= 0 ? a * updated((size_t)NUN * ci + r) : 0.0;
+            __syncthreads();
             if (q < nsend) {
-                const int ci = __ldg(cidx + q);
                 double s = 0.0;
                 if (ci >= 0) {
                     const double* M = minv + (size_t)__ldg(ocell + ci) * 36 + r * NUN;
 #pragma unroll
-                    for (int k = 0; k < NUN; k++) s += M[k] * (a * w[(size_t)NUN * ci + k]);
+                    for (int k = 0; k < NUN; k++) s += M[k] * sv[lc * NUN + k];
                 }
-                ll_store(peer_ll[__ldg(peer + q)] + (size_t)NUN * __ldg(dst_slot + q) + r, s, flag);
+                ll_store(peer_ll[__ldg(peer + q)] + (size_t)NUN * __ldg(dst_slot + q) + r, s, llflag);
             }
+            __syncthreads();
         }
     }
 }
 unsigned long long ll_exchange_begin(thcmb_ctx* c);
-// returns the sequence number of the exchange it started (0 on one rank); the caller hands it to spmv_compact_rows
-unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out) {
+// returns the sequence number of the exchange it started (0 on one rank); the caller hands it to spmv_compact_rows.
+// nv / vecs / d_h2 / d_flag / d_flag2: the pending second update (nullptr flag = none)
+unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double* d_nrm2, double* v, double* z, double* d_nrm_out,
+                                     int nv, double* const* vecs, const double* d_h2, const int* d_flag, const int* d_flag2) {
     const unsigned long long seq = ll_exchange_begin(c);
     const int nc = c->n_ocell;
+    if (nv > MD_MAXV) fatal("scale_precon_push: the fused second update takes at most 64 basis vectors");
+    VecList vl; vl.nv = d_flag ? nv : 0;
+    for (int q = 0; q < vl.nv; q++) vl.v[q] = vecs[q];
     const int main_blocks = std::max(1, std::min((nc + SPP_CELLS - 1) / SPP_CELLS, NSM * 8));
     const bool push = c->blk.nranks > 1 && c->nsend_cells > 0;
     const int push_blocks = push ? std::max(1, std::min((c->nsend_cells + SPP_CELLS - 1) / SPP_CELLS, NSM)) : 0;
     const int par = (int)(seq & 1ull);
     ProfScope prof_(c, KID_PRECON_APPLY);
     scale_precon_push_kernel<<<main_blocks + push_blocks, SPP_THREADS, 0, c->stream>>>(
-        nc, c->d_ocell, c->d_minv, d_nrm2, w, v, z, d_nrm_out, main_blocks, push ? c->nsend_cells : 0, c->d_send_cidx, c->d_send_dst,
-        c->d_send_peer, push ? (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size() : nullptr, (unsigned int)seq);
+        nc, c->d_ocell, c->d_minv, d_nrm2, w, v, z, d_nrm_out, vl, d_h2, d_flag, d_flag2, push_blocks, push ? c->nsend_cells : 0,
+        c->d_send_cidx, c->d_send_dst, c->d_send_peer, push ? (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size() : nullptr,
+        (unsigned int)seq);
     c->launches++;
     return seq;
 }
