@@ -357,6 +357,16 @@ void thcmb_set_vmix_fix(thcmb_ctx* c, int fix) { c->vmix_fix = fix; }   /* m_mix
 void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4) { out4[0] = c->vmix_flag; out4[1] = c->vmix_temp; out4[2] = c->vmix_salt; out4[3] = c->vmix_fix; }
 
 int thcmb_halo_exchange(thcmb_ctx* c, const double* d_x) { return halo_exchange(c, d_x); }
+/* Ocean::getBlock(Atmosphere / SeaIce) (Ocean.C:1603-1810): the ocean block's coupling to the other models (host code at coupling
+ * frequency: surface points only) */
+int thcmb_ocean_block_atmosphere(thcmb_ctx* c, double albed, const double* pdist, const int* colT, const int* colQ, const int* colA,
+                                 const int* colP, int* beg, int* jco, double* co) {
+    return ocean_block_atmosphere(c, albed, pdist, colT, colQ, colA, colP, beg, jco, co);
+}
+int thcmb_ocean_block_seaice(thcmb_ctx* c, const double* un_host, const int* colQ, const int* colM, const int* colG, int* beg, int* jco,
+                             double* co) {
+    return ocean_block_seaice(c, un_host, colQ, colM, colG, beg, jco, co);
+}
 
 // vmix_control (mix_imp.f:139-169), called from rhs / matrix when Mixing = 2 and the partition is not fixed
 // (usrc.F90:496, 558): which of the T and S fields are non-zero decides whether their mixing terms are on

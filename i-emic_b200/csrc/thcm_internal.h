@@ -279,6 +279,9 @@ void integrals_salt_advection(const thcmb_ctx* c, const double* un, double* chec
 void integrals_salt_diffusion(const thcmb_ctx* c, const double* un, double* check);
 void stochastic_forcing(thcmb_ctx* c, int* begF, int* jcoF, double* coF);
 void get_deps(const thcmb_ctx* c, double* out7);
+int ocean_block_atmosphere(thcmb_ctx* c, double albed, const double* pdist, const int* colT, const int* colQ, const int* colA,
+                           const int* colP, int* beg, int* jco, double* co);
+int ocean_block_seaice(thcmb_ctx* c, const double* un, const int* colQ, const int* colM, const int* colG, int* beg, int* jco, double* co);
 void get_dim_parameters(const thcmb_ctx* c, double* r0, double* u0, double* h0);
 void loadbal_weights(const thcmb_ctx* c, double* array);
 void write_params(const thcmb_ctx* c);

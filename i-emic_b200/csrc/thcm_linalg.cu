@@ -1509,7 +1509,7 @@ unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double
                                      int nv, double* const* vecs, const double* d_h2, const int* d_flag, const int* d_flag2) {
     const unsigned long long seq = ll_exchange_begin(c);
     const int nc = c->n_ocell;
-    if (nv > MD_MAXV) fatal("scale_precon_push: the fused second update takes at most 64 basis vectors");
+    if (d_flag && nv > MD_MAXV) fatal("scale_precon_push: the fused second update takes at most 64 basis vectors");
     VecList vl; vl.nv = d_flag ? nv : 0;
     for (int q = 0; q < vl.nv; q++) vl.v[q] = vecs[q];
     const int main_blocks = std::max(1, std::min((nc + SPP_CELLS - 1) / SPP_CELLS, NSM * 8));

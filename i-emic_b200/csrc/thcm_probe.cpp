@@ -282,6 +282,70 @@ void get_deps(const thcmb_ctx* c, double* out7) {
     out7[0] = c->atm_Ooa; out7[1] = c->atm_Os; out7[2] = c->atm_nus; out7[3] = c->atm_eta; out7[4] = c->atm_lvsc; out7[5] = c->atm_qdim;
     out7[6] = c->par[COMB] * c->par[SALT] * c->QSnd;
 }
+// Ocean::getBlock(Atmosphere) (Ocean.C:1603-1730): the dependence of the ocean rows on the atmosphere's unknowns as a CRS block over
+// ALL 6 N M L ocean rows in FIND_ROW2 order (0-based beg[ndim + 1]); only the surface T rows (coupled_T: columns T, A, Q in that order)
+// and the surface S rows (coupled_S, the integral-condition row excepted: columns Q and, when the atmosphere carries the auxiliary
+// precipitation unknown, P) of OCEAN surface points hold entries.  "Negating as the Jacobian is taken negative": the entries are
+// d F_ocean / d x_atmos for the C++-sign residual F = A u - Frc.  col*: the atmosphere's interface_row(i, j, XX) per surface point
+// (n*m, i fastest; colP < 0 = no auxiliary row), pdist = Atmosphere::getPdist (NULL = 1), albed = Atmosphere::CommPars::da.
+int ocean_block_atmosphere(thcmb_ctx* c, double albed, const double* pdist, const int* colT, const int* colQ, const int* colA,
+                           const int* colP, int* beg, int* jco, double* co) {
+    need_single_rank(c, "Ocean::getBlock(Atmosphere)");
+    const thcmb_settings& s = c->s;
+    const int n = s.N, m = s.M, l = s.L;
+    double dep[7]; get_deps(c, dep);
+    const double Ooa = dep[0], nus = dep[2], eta = dep[3], lvsc = dep[4], qdim = dep[5];
+    const double comb = c->par[COMB], sunp = c->par[SUNP];
+    const int rowIntCon = c->ic_on ? c->ic_grow : -1;
+    int el = 0;
+    size_t row = 0;
+    for (int k = 0; k < l; k++) for (int j = 0; j < m; j++) for (int i = 0; i < n; i++) {
+        const size_t sr = (size_t)j * n + i;
+        const double M = c->msi[sr], S = c->suno[j + 1], Pd = pdist ? pdist[sr] : 1.0;
+        for (int xx = UU; xx <= SS; xx++, row++) {
+            beg[row] = el;
+            if (k != l - 1 || LMc(c, i + 1, j + 1, l) != OCEAN) continue;
+            if (xx == TT && s.coupled_T) {
+                co[el] = -(Ooa * (1.0 - M)); jco[el++] = colT[sr];
+                co[el] = -(-comb * sunp * S * albed * (1.0 - M)); jco[el++] = colA[sr];
+                co[el] = -(lvsc * eta * qdim * (1.0 - M)); jco[el++] = colQ[sr];
+            } else if (xx == SS && s.coupled_S && (int)row != rowIntCon) {
+                co[el] = -(-nus * (1.0 - M)); jco[el++] = colQ[sr];
+                if (colP && colP[sr] >= 0) { co[el] = -(-nus * Pd * (1.0 - M)); jco[el++] = colP[sr]; }
+            }
+        }
+    }
+    beg[row] = el;
+    return el;
+}
+// Ocean::getBlock(SeaIce) (Ocean.C:1733-1810): likewise for the sea-ice unknowns Q (heat flux), M (mask), G (integral correction), from
+// m_probe::get_derivatives at the HOST state un (THCM::getDerivatives).  Surface T rows: column M; surface S rows: columns Q, M, G.
+int ocean_block_seaice(thcmb_ctx* c, const double* un, const int* colQ, const int* colM, const int* colG, int* beg, int* jco, double* co) {
+    need_single_rank(c, "Ocean::getBlock(SeaIce)");
+    const thcmb_settings& s = c->s;
+    const int n = s.N, m = s.M, l = s.L;
+    const size_t nm = (size_t)n * m;
+    std::vector<double> dftdm(nm), dfsdq(nm), dfsdm(nm), dfsdg(nm);
+    probe_get_derivatives(c, un, dftdm.data(), dfsdq.data(), dfsdm.data(), dfsdg.data());
+    const int rowIntCon = c->ic_on ? c->ic_grow : -1;
+    int el = 0;
+    size_t row = 0;
+    for (int k = 0; k < l; k++) for (int j = 0; j < m; j++) for (int i = 0; i < n; i++) {
+        const size_t sr = (size_t)j * n + i;
+        for (int xx = UU; xx <= SS; xx++, row++) {
+            beg[row] = el;
+            if (k != l - 1 || LMc(c, i + 1, j + 1, l) != OCEAN) continue;
+            if (xx == TT && s.coupled_T) { co[el] = -dftdm[sr]; jco[el++] = colM[sr]; }
+            else if (xx == SS && s.coupled_S && (int)row != rowIntCon) {
+                co[el] = -dfsdq[sr]; jco[el++] = colQ[sr];
+                co[el] = -dfsdm[sr]; jco[el++] = colM[sr];
+                co[el] = -dfsdg[sr]; jco[el++] = colG[sr];
+            }
+        }
+    }
+    beg[row] = el;
+    return el;
+}
 void get_dim_parameters(const thcmb_ctx* c, double* r0, double* u0, double* h0) { *r0 = r0dim; *u0 = udim; *h0 = c->s.hdim; }
 
 // m_thcm_utils::loadbal_weights (thcm_utils.F90:325-353): OCEAN cells per water column / l.  The vmix_counts terms are the

@@ -108,7 +108,9 @@ def load_library(path=None):
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
         "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
-        "thcmb_tile_counts": (None, [vp, vp, vp]), "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
+        "thcmb_tile_counts": (None, [vp, vp, vp]),
+        "thcmb_ocean_block_atmosphere": (i, [vp, d, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "thcmb_ocean_block_seaice": (i, [vp, vp, vp, vp, vp, vp, vp, vp]), "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),
         "thcmb_dot": (d, [vp, i, vp, vp]), "thcmb_nrm2": (d, [vp, i, vp]), "thcmb_axpby": (i, [vp, i, d, vp, d, vp]),
         "thcmb_scale": (i, [vp, i, d, vp]), "thcmb_build_precon": (i, [vp, i]), "thcmb_apply_precon_dev": (i, [vp, vp, vp]),
         "thcmb_gmres": (i, [vp, vp, vp, d, i, i, i, vp, i, C.POINTER(KrylovResult)]),
@@ -269,6 +271,26 @@ class THCM:
         if p.size != 7:
             raise ValueError("SeaIce::CommPars has 7 members")
         self.L_.thcmb_set_seaice_parameters(self.ctx, _np_ptr(p))
+
+    def oceanBlockAtmosphere(self, albed, pdist, colT, colQ, colA, colP):
+        """Ocean::getBlock(Atmosphere) (Ocean.C:1603-1730): d F_ocean / d x_atmosphere as (beg, jco, co), CRS over all ocean rows."""
+        n, m = self.settings.N, self.settings.M
+        cols = [np.ascontiguousarray(c, dtype=np.int32).reshape(-1) for c in (colT, colQ, colA, colP)]
+        pd = None if pdist is None else np.ascontiguousarray(pdist, dtype=np.float64).reshape(-1)
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(6 * n * m, dtype=np.int32); co = np.zeros(6 * n * m)
+        f = self.L_.thcmb_ocean_block_atmosphere
+        nnz = f(self.ctx, float(albed), None if pd is None else _np_ptr(pd), *[_np_ptr(c) for c in cols], _np_ptr(beg), _np_ptr(jco), _np_ptr(co))
+        return beg, jco[:nnz].copy(), co[:nnz].copy()
+
+    def oceanBlockSeaIce(self, state_host, colQ, colM, colG):
+        """Ocean::getBlock(SeaIce) (Ocean.C:1733-1810) at the host state (THCM::getDerivatives)."""
+        n, m = self.settings.N, self.settings.M
+        cols = [np.ascontiguousarray(c, dtype=np.int32).reshape(-1) for c in (colQ, colM, colG)]
+        un = np.ascontiguousarray(state_host, dtype=np.float64)
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(6 * n * m, dtype=np.int32); co = np.zeros(6 * n * m)
+        f = self.L_.thcmb_ocean_block_seaice
+        nnz = f(self.ctx, _np_ptr(un), *[_np_ptr(c) for c in cols], _np_ptr(beg), _np_ptr(jco), _np_ptr(co))
+        return beg, jco[:nnz].copy(), co[:nnz].copy()
 
     def getMassDiagonal(self):
         """coB of fillcolB (assemble.F90:18-54), THCM::evaluateB."""
@@ -511,6 +533,19 @@ class Ocean:
     def applyPrecon(self, v, out):
         self.buildPreconditioner()
         self.thcm.applyPrecon(v, out)
+
+    def getBlock(self, other):
+        """Ocean::getBlock(std::shared_ptr<Atmosphere>) / getBlock(std::shared_ptr<SeaIce>) (Ocean.C:1603-1810): the coupling block of the
+        coupled model's Jacobian, (beg, jco, co).  `other` stands for the other model: .kind "atmosphere" | "seaice" and
+        .interface_row(i, j, XX) (1-based unknown XX, 0-based row, -1 = none); an atmosphere also gives .da (CommPars::da) and .pdist."""
+        s = self.thcm.settings
+        ii, jj = np.meshgrid(np.arange(s.N), np.arange(s.M))
+        rows = lambda XX: np.array([other.interface_row(int(i), int(j), XX) for i, j in zip(ii.ravel(), jj.ravel())], dtype=np.int32)  # noqa: E731
+        if other.kind == "atmosphere":     # ATMOS_TT_ 1, ATMOS_QQ_ 2, ATMOS_AA_ 3, ATMOS_PP_ 4 (AtmosphereDefinitions.H:27-33)
+            return self.thcm.oceanBlockAtmosphere(other.da, getattr(other, "pdist", None), rows(1), rows(2), rows(3), rows(4))
+        if other.kind == "seaice":         # SEAICE_QQ_ 2, SEAICE_MM_ 3, SEAICE_GG_ 5 (SeaIceDefinitions.H:19-24)
+            return self.thcm.oceanBlockSeaIce(self.state_.cpu().numpy(), rows(2), rows(3), rows(5))
+        raise ValueError("getBlock: unknown model kind " + str(other.kind))
 
     def solve(self, rhs=None):  # Ocean.C:1070-1147: sol_ = J^{-1} rhs with preconditioned FGMRES, zero initial guess
         b = self.rhs_ if rhs is None else rhs

@@ -192,6 +192,16 @@ typedef struct thcmb_settings {
 
 void thcmb_default_settings(thcmb_settings* s);
 
+/* Ocean::getBlock(std::shared_ptr<Atmosphere>) / getBlock(std::shared_ptr<SeaIce>) (Ocean.C:1603-1730, 1733-1810): the coupling blocks
+ * d F_ocean / d x_atmosphere and d F_ocean / d x_seaice of the coupled model's Jacobian, CRS over all 6 N M L ocean rows in FIND_ROW2
+ * order (0-based beg[ndim + 1]; at most 3 entries per surface T / S row: allocate 3 * 2 * N * M).  The column ids are the other model's
+ * interface_row(i, j, XX) per surface point (N*M ints, i fastest; colP: -1 where the atmosphere has no auxiliary precipitation row).
+ * One rank (the reference all-gathers the surface fields for these blocks too).  Return the number of entries. */
+int thcmb_ocean_block_atmosphere(thcmb_ctx* c, double albed, const double* pdist, const int* colT, const int* colQ, const int* colA,
+                                 const int* colP, int* beg, int* jco, double* co);
+int thcmb_ocean_block_seaice(thcmb_ctx* c, const double* un_host, const int* colQ, const int* colM, const int* colG, int* beg, int* jco,
+                             double* co);
+
 /* landm_global: (N+2)(M+2)(L+2) ints, i fastest, values OCEAN 0 / LAND 1 / WATER 2 / PERIO 3 (par.F90:78-81).
  * Every rank passes the same global mask (replaces the bcast+import of THCM.C:378-565). Returns NULL on error. */
 thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global);

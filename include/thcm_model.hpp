@@ -256,6 +256,39 @@ public:
         return lastSolve_.status;
     }
     const thcmb_krylov_result& lastSolve() const { return lastSolve_; }
+
+    // Utils::CRSMat of the reference (src/utils/Utils.H): beg / jco / co, 0-based
+    struct CRSMat { std::vector<int> beg, jco; std::vector<double> co; };
+    // Ocean::getBlock(std::shared_ptr<Atmosphere>) (Ocean.C:1603-1730): d F_ocean / d x_atmosphere.  AtmosLike: interface_row(i, j, XX)
+    // (Atmosphere.C:1746-1763), commParsDa() (Atmosphere::CommPars::da), pdist() (n*m doubles or nullptr).  N, M: the global surface grid
+    template <class AtmosLike> CRSMat getBlockAtmosphere(AtmosLike& atmos, int N, int M) {
+        std::vector<int> cT((size_t)N * M), cQ(cT.size()), cA(cT.size()), cP(cT.size());
+        for (int j = 0; j < M; j++) for (int i = 0; i < N; i++) {
+            const size_t sr = (size_t)j * N + i;
+            cT[sr] = atmos.interface_row(i, j, 1); cQ[sr] = atmos.interface_row(i, j, 2);     // ATMOS_TT_, ATMOS_QQ_
+            cA[sr] = atmos.interface_row(i, j, 3); cP[sr] = atmos.interface_row(i, j, 4);     // ATMOS_AA_, ATMOS_PP_
+        }
+        CRSMat b;
+        b.beg.resize((size_t)thcmb_ndim_local(context()) + 1); b.jco.resize(6 * cT.size()); b.co.resize(6 * cT.size());
+        const int nnz = thcmb_ocean_block_atmosphere(context(), atmos.commParsDa(), atmos.pdist(), cT.data(), cQ.data(), cA.data(), cP.data(),
+                                                     b.beg.data(), b.jco.data(), b.co.data());
+        b.jco.resize((size_t)nnz); b.co.resize((size_t)nnz);
+        return b;
+    }
+    // Ocean::getBlock(std::shared_ptr<SeaIce>) (Ocean.C:1733-1810): d F_ocean / d x_seaice at the current state
+    template <class SeaIceLike> CRSMat getBlockSeaIce(SeaIceLike& seaice, int N, int M) {
+        std::vector<int> cQ((size_t)N * M), cM(cQ.size()), cG(cQ.size());
+        for (int j = 0; j < M; j++) for (int i = 0; i < N; i++) {
+            const size_t sr = (size_t)j * N + i;
+            cQ[sr] = seaice.interface_row(i, j, 2); cM[sr] = seaice.interface_row(i, j, 3); cG[sr] = seaice.interface_row(i, j, 5);   // SEAICE_QQ_, _MM_, _GG_
+        }
+        const std::vector<double> un = state_->toHost();
+        CRSMat b;
+        b.beg.resize(un.size() + 1); b.jco.resize(6 * cQ.size()); b.co.resize(6 * cQ.size());
+        const int nnz = thcmb_ocean_block_seaice(context(), un.data(), cQ.data(), cM.data(), cG.data(), b.beg.data(), b.jco.data(), b.co.data());
+        b.jco.resize((size_t)nnz); b.co.resize((size_t)nnz);
+        return b;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

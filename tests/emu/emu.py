@@ -162,6 +162,30 @@ class EmuTHCM:
         self.L_.emu_grid(self.h, *[_p(a[k]) for k in ("x", "xu", "y", "yv", "z", "zw", "dfzT", "dfzW")])
         return a
 
+    def ocean_block_atmosphere(self, albed, pdist, colT, colQ, colA, colP):
+        """Ocean::getBlock(Atmosphere) (Ocean.C:1603-1730): (beg, jco, co) over all ocean rows."""
+        m, n = self._nm()
+        cap = 6 * n * m
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(cap, dtype=np.int32); co = np.zeros(cap)
+        a = [np.ascontiguousarray(c, dtype=np.int32) for c in (colT, colQ, colA, colP)]
+        pd = np.ascontiguousarray(pdist, dtype=np.float64)
+        f = self.L_.emu_ocean_block_atmosphere
+        f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 8
+        nnz = f(self.h, float(albed), _p(pd), *[_p(x) for x in a], _p(beg), _p(jco), _p(co))
+        return beg, jco[:nnz].copy(), co[:nnz].copy()
+
+    def ocean_block_seaice(self, un, colQ, colM, colG):
+        """Ocean::getBlock(SeaIce) (Ocean.C:1733-1810)."""
+        m, n = self._nm()
+        cap = 6 * n * m
+        beg = np.zeros(self.ndim + 1, dtype=np.int32); jco = np.zeros(cap, dtype=np.int32); co = np.zeros(cap)
+        a = [np.ascontiguousarray(c, dtype=np.int32) for c in (colQ, colM, colG)]
+        un = np.ascontiguousarray(un, dtype=np.float64)
+        f = self.L_.emu_ocean_block_seaice
+        f.restype = C.c_int; f.argtypes = [C.c_void_p] * 8
+        nnz = f(self.h, _p(un), *[_p(x) for x in a], _p(beg), _p(jco), _p(co))
+        return beg, jco[:nnz].copy(), co[:nnz].copy()
+
     def getdeps(self):
         out = np.empty(7); self.L_.emu_getdeps(self.h, _p(out)); return out
 

@@ -139,6 +139,13 @@ void emu_derivatives(void* h, const double* un, double* four) {
 void emu_salt_advection(void* h, const double* un, double* out) { integrals_salt_advection(&((Emu*)h)->c, un, out); }
 void emu_salt_diffusion(void* h, const double* un, double* out) { integrals_salt_diffusion(&((Emu*)h)->c, un, out); }
 void emu_stochastic_forcing(void* h, int* beg, int* jco, double* co) { thcmb_ctx* c = &((Emu*)h)->c; stochastic_forcing(c, beg, jco, co); }
+int emu_ocean_block_atmosphere(void* h, double albed, const double* pdist, const int* colT, const int* colQ, const int* colA, const int* colP,
+                               int* beg, int* jco, double* co) {
+    return ocean_block_atmosphere(&((Emu*)h)->c, albed, pdist, colT, colQ, colA, colP, beg, jco, co);
+}
+int emu_ocean_block_seaice(void* h, const double* un, const int* colQ, const int* colM, const int* colG, int* beg, int* jco, double* co) {
+    return ocean_block_seaice(&((Emu*)h)->c, un, colQ, colM, colG, beg, jco, co);
+}
 void emu_getdeps(void* h, double* out7) { get_deps(&((Emu*)h)->c, out7); }
 void emu_loadbal(void* h, double* w) { loadbal_weights(&((Emu*)h)->c, w); }
 // the library's grid arrays (build_grid = grid.F90): x(1..N), xu(0..N), y(1..M), yv(0..M), z(1..L), zw(0..L), dfzT(1..L), dfzW(0..L)

@@ -291,3 +291,59 @@ def test_newton_step_from_host_buffers_equals_the_device_resident_step(name, com
     land = np.repeat((landm[1:-1, 1:-1, 1:-1] != 0).reshape(-1), 6)
     assert np.all(dx_host[land] == 0.0)
     t.close()
+
+
+def test_ocean_coupling_blocks_through_the_model_mirror():
+    """Ocean::getBlock(Atmosphere) / getBlock(SeaIce) (Ocean.C:1603-1810) through the Python mirror of the Model API, against finite
+    differences of the CUDA residual with respect to the atmosphere temperature / the sea-ice mask at one surface point (the residual is
+    affine in both; the full finite-difference check of every column runs on the CPU: tests/test_probe_host.py)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    s, landm = cases.natl8(coupled_T=1, coupled_S=1)
+    oc = iemic_b200.Ocean(s, landm)
+    t = oc.thcm
+    for k, v in dict(PARS, SUNP=1.0).items():
+        oc.setPar(k, v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    fields["msi"] = np.random.default_rng(12).random(fields["msi"].shape)
+    names = {"tatm": "atmosphere_t", "qatm": "atmosphere_q", "albe": "atmosphere_a", "patm": "atmosphere_p", "qsa": "seaice_q",
+             "msi": "seaice_m", "gsi": "seaice_g", "emip": "emip", "adapted_emip": "adapted_emip", "spert": "emip_pert"}
+    for k, f in fields.items():
+        t.insertSurfaceField(names[k], f)
+    t.setAtmosphereParameters(atmos)
+    t.setSeaIceParameters(seaice)
+    n, m, l = s.N, s.M, s.L
+    x = cases.random_state(s, landm, scale=0.2)
+    oc.getState().copy_(torch.from_numpy(x))
+
+    class Atmos:
+        kind, da, pdist = "atmosphere", atmos[13], None
+        @staticmethod
+        def interface_row(i, j, XX):
+            return 3 * (j * n + i) + XX - 1 if XX <= 3 else 3 * n * m
+
+    class Ice:
+        kind = "seaice"
+        @staticmethod
+        def interface_row(i, j, XX):
+            return 4 * (j * n + i) + XX - 1
+
+    import scipy.sparse as sp
+    beg, jco, co = oc.getBlock(Atmos)
+    A = sp.csr_matrix((co, jco, beg), shape=(t.ndim, 3 * n * m + 1)).tocsc()
+    beg, jco, co = oc.getBlock(Ice)
+    B = sp.csr_matrix((co, jco, beg), shape=(t.ndim, 4 * n * m + 4)).tocsc()
+    j, i = np.argwhere(landm[l, 1:-1, 1:-1] == 0)[7]
+    oc.computeRHS()
+    F0 = oc.getRHS("C").cpu().numpy()
+    for field, mat, col in (("tatm", A, 3 * (j * n + i)), ("msi", B, 4 * (j * n + i) + 2)):
+        f = fields[field].copy(); f[j, i] += 1e-3
+        t.insertSurfaceField(names[field], f); oc.setPar("COMB", PARS["COMB"])
+        oc.computeRHS()
+        want = (oc.getRHS("C").cpu().numpy() - F0) / 1e-3
+        t.insertSurfaceField(names[field], fields[field]); oc.setPar("COMB", PARS["COMB"])
+        got = mat[:, col].toarray().ravel()
+        assert np.abs(got).max() > 0 and np.abs(got - want).max() <= 1e-9 * max(np.abs(mat).max(), 1.0), field
+    t.close()

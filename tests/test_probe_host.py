@@ -150,3 +150,64 @@ def test_salt_and_temperature_forcing_round_trip_like_the_reference_test():
     assert np.linalg.norm(em) >= 1e-2 and np.array_equal(em, emip * (1 - land))
     assert np.array_equal(o.forcing(), e.forcing(masked=False))
     assert np.array_equal(o.rhs(x), e.rhs(x))
+
+
+@pytest.mark.parametrize("name", ["natl8", "box_np"])
+def test_ocean_coupling_blocks_are_the_derivatives_of_the_residual(name):
+    """Ocean::getBlock(Atmosphere) / getBlock(SeaIce) (Ocean.C:1603-1810, SURVEY 8f N4: the ocean's side of the coupled Jacobian) against
+    finite differences of the library's own residual with respect to the fields the other models hand in -- the residual is affine in
+    every one of them, so the quotient is exact up to rounding.  F = -B (THCM.C:1011)."""
+    import scipy.sparse as sp
+    mk = {"natl8": cases.natl8, "box_np": lambda **kw: cases.box(6, 7, 4, False, seed=2, land_frac=0.3, **kw)}[name]
+    s, landm = mk(coupled_T=1, coupled_S=1)
+    e = EmuTHCM(s, landm)
+    for k, v in dict(cases.DEFAULT_PARS, NLES=1.0, SUNP=1.0).items():
+        e.setpar(P[k], v)
+    fields, atmos, seaice = cases.coupled_inputs(s)
+    rng = np.random.default_rng(12)
+    fields["msi"] = rng.random(fields["msi"].shape)           # a fractional mask exercises the (1 - M) factors
+    cases.apply_coupled(e, fields, atmos, seaice)
+    n, m = s.N, s.M
+    x = cases.random_state(s, landm, scale=0.2)
+    sr = np.arange(n * m)
+    colT, colQ, colA = 3 * sr, 3 * sr + 1, 3 * sr + 2         # FIND_ROW_ATMOS0 with dof = 3 on the surface level
+    colP = np.full(n * m, 3 * n * m)                          # the auxiliary precipitation row (dim - aux)
+    pdist = 0.5 + rng.random((m, n))
+    F0 = -e.rhs(x)
+
+    def refresh():
+        e.setpar(P["COMB"], cases.DEFAULT_PARS["COMB"])       # forcing + lin are re-run at the next parameter change (inserts.F90)
+
+    def fd_column(field, pattern, delta=1e-3):
+        f = fields[field].copy()
+        e.set_field(field, f + delta * pattern); refresh()
+        col = (-e.rhs(x) - F0) / delta
+        e.set_field(field, f); refresh()
+        return col
+
+    beg, jco, co = e.ocean_block_atmosphere(atmos[13], pdist, colT, colQ, colA, colP)
+    A = sp.csr_matrix((co, jco, beg), shape=(e.ndim, 3 * n * m + 1)).tocsc()
+    surf_ocean = np.argwhere(landm[s.L, 1:-1, 1:-1] == 0)
+    assert len(surf_ocean) > 3 and A.nnz > 0
+    scale = np.abs(A).max()
+    for j, i in surf_ocean[rng.choice(len(surf_ocean), size=4, replace=False)]:
+        unit = np.zeros((m, n)); unit[j, i] = 1.0
+        for field, col in (("tatm", colT), ("qatm", colQ), ("albe", colA)):
+            want = fd_column(field, unit)
+            got = A[:, col[j * n + i]].toarray().ravel()
+            assert np.abs(got - want).max() <= 1e-9 * scale, (field, i, j)
+    # P is the atmosphere's nondimensional global precipitation anomaly: the field it hands the ocean is
+    # pdist * (Po0 + eta * qdim * P) (AtmosLocal.C:1117-1124), hence the eta * qdim inside nus (usrc.F90:266)
+    want = fd_column("patm", atmos[3] * atmos[1] * pdist)
+    assert np.abs(A[:, 3 * n * m].toarray().ravel() - want).max() <= 1e-9 * scale
+
+    beg, jco, co = e.ocean_block_seaice(x, 4 * sr + 1, 4 * sr + 2, 4 * sr + 3)
+    B = sp.csr_matrix((co, jco, beg), shape=(e.ndim, 4 * n * m)).tocsc()
+    scale = np.abs(B).max()
+    assert B.nnz > 0
+    for j, i in surf_ocean[rng.choice(len(surf_ocean), size=4, replace=False)]:
+        unit = np.zeros((m, n)); unit[j, i] = 1.0
+        for field, off in (("qsa", 1), ("msi", 2), ("gsi", 3)):
+            want = fd_column(field, unit)
+            got = B[:, 4 * (j * n + i) + off].toarray().ravel()
+            assert np.abs(got - want).max() <= 1e-9 * max(scale, 1.0), (field, i, j)
