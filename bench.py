@@ -337,7 +337,8 @@ def main():
         "decomposition": ("Decomp2D rank grid, cut lines placed by ocean-cell count (thcmb_settings.balance = 1)" if balance and world > 1
                           else "Decomp2D, uniform cut lines (TRIOS_Domain.C:258-273)"),
         "orthogonalisation": ("batched classical Gram-Schmidt + DGKS criterion (Belos 'DGKS', Ocean.C:977-1024): first update and second projection "
-                              "share one sweep over the basis" if a.ortho == "dgks" else "modified Gram-Schmidt (GMRESSolver.H:177-181)"),
+                              "share one sweep over the basis; the second update rides in the head kernel of the next Arnoldi step with its norm from "
+                              "Pythagoras (two all-reduces per iteration)" if a.ortho == "dgks" else "modified Gram-Schmidt (GMRESSolver.H:177-181)"),
         "krylov_space": "ocean cells only (LAND rows are identity rows, b = 0 there)" if kry_compact else "full-length vectors",
         "l2": "working set (Jacobian 1.6 GB + Krylov basis) >> 126 MB L2; no flush needed"}
     t = iemic_b200.THCM(s, landm, comm)
@@ -436,6 +437,7 @@ def main():
     nnz_active = int(nnz_loc * ntile_active / max(ntile_all, 1))     # entries of the tiles the Jacobian kernels revisit (tiles are 32 cells)
     nk = 6 * ncell_ocean if kry_compact else ndim_loc      # length of the Krylov vectors
     nvavg = (iters + 1) / 2                                 # basis vectors of an orthogonalisation pass, averaged over a cycle
+    pyth_head = kry_compact and a.ortho == "dgks" and a.precon == 1 and not os.environ.get("THCM_EXPLICIT_NORM") and not os.environ.get("THCM_NO_FUSED_HEAD")
     alg_bytes = {  # ALGORITHMIC bytes per launch of the format being timed (minimum compulsory traffic)
         # compact SpMV: values + compact column ids of the ocean rows, row pointers, cell map, x and y once
         "spmv_csr": (nnz_ocean * 12 + 6 * ncell_ocean * 4 + ncell_ocean * 4 + nk * 16) if kry_compact else (nnz_ocean * 12 + 6 * ncell_ocean * 4 + ncell_loc + ndim_loc * 16),
@@ -443,16 +445,20 @@ def main():
         "thcm_assemble<RHS>": ncell_loc * 145,
         "mgs_step": 32 * nk, "dot": 16 * nk,
         "multi_dot": int(8 * nk * (nvavg + 1)),             # nv basis vectors + w, each once
-        "multi_axpy": int(8 * nk * (nvavg + 2)),            # nv basis vectors + w read + w written
+        "multi_axpy": int(8 * nk * (nvavg + 2)),            # first update + second projection: nv basis vectors + w read + w written
+        "second_update": 0,                                 # the explicit second update + norm: launched every iteration, leaves at once unless
+                                                            # the guard of the Pythagorean norm tripped (then 8 nk (nv + 2))
         "axpby": 24 * nk, "axpy_negdev": 24 * nk, "scale_invsqrt": 16 * nk, "copy": 16 * nk, "fill": 8 * nk,
-        # head of an Arnoldi step: w in, v and z out, 36 doubles of the block inverse per cell
-        "blockdiag_apply": (24 * 6 + 36 * 8) * (nk // 6), "blockdiag_build": ncell_loc * 36 * 8 + 12 * nnz_loc,
+        # head of an Arnoldi step: w in, v and z out, 36 doubles of the block inverse per cell -- plus, whenever the DGKS criterion asked
+        # for it (every iteration of this benchmark: counted), the second Gram-Schmidt update against the nv basis vectors
+        "blockdiag_apply": (24 * 6 + 36 * 8) * (nk // 6) + (int(8 * nk * nvavg) if pyth_head else 0),
+        "blockdiag_build": ncell_ocean * (36 * 8 + 6 * 4) + ncell_loc * 36 * 8 + ncell_loc,   # in-cell entries + row pointers of the ocean rows, inverses out
     }
     graph_equiv = {"spmv_csr": nnz_loc * 12 + ndim_loc * 20, "thcm_assemble<JAC_GRAPH>": ncell_loc * 49 + 8 * nnz_loc,
                    "multi_dot": int(8 * ndim_loc * (nvavg + 1)), "multi_axpy": int(8 * ndim_loc * (nvavg + 2))}
     symbol = {"spmv_csr": "spmv_compact_kernel" if kry_compact else "spmv_csr_kernel", "multi_dot": "multi_dot_kernel",
-              "multi_axpy": "fused2_axpy_dot_kernel", "thcm_assemble<JAC_GRAPH>": "thcm_jac_tma_kernel", "thcm_assemble<RHS>": "thcm_assemble_kernel",
-              "blockdiag_apply": "scale_precon_push_kernel", "blockdiag_build": "blockdiag_build_kernel"}
+              "multi_axpy": "fused2_axpy_dot_kernel", "thcm_assemble<JAC_GRAPH>": "thcm_jac_tma_kernel", "thcm_assemble<RHS>": "thcm_rhs_tma_kernel",
+              "blockdiag_apply": "scale_precon_push_kernel", "blockdiag_build": "blockdiag_build_kernel", "second_update": "multi_axpy_dot_kernel"}
     step_ms = ms / a.steps
     kernels = {}
     for name, (cnt, tot) in prof.items():

@@ -604,7 +604,8 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                         const bool pyth = pyth_norm && nv <= 64;
                         fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S, pyth ? c->d_flags + 1 : nullptr);
                         // explicit second update + norm: always without the Pythagorean shortcut, else only when its guard tripped
-                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, pyth ? c->d_flags + 1 : c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr);
+                        multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, pyth ? c->d_flags + 1 : c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr,
+                                           KID_SECOND_UPDATE);
                     } else if (c->p2p_on || c->blk.nranks == 1) {
                         // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh, nullptr, w, dh + S, dh + nv, c->d_flags, dh + 3 * S);
@@ -820,7 +821,7 @@ void thcmb_profile(thcmb_ctx* c, int on) {
 }
 static const char* kKernelNames[KID_COUNT] = {"thcm_assemble<RHS>", "thcm_assemble<JAC_GRAPH>", "thcm_assemble<JAC_COUNT>",
     "thcm_assemble<JAC_CRS>", "scan_counts", "spmv_csr", "dot", "mgs_step", "axpby", "axpy_negdev", "scale_invsqrt", "copy", "fill",
-    "blockdiag_build", "blockdiag_apply", "halo_pack", "halo_unpack", "multi_dot", "multi_axpy"};
+    "blockdiag_build", "blockdiag_apply", "halo_pack", "halo_unpack", "multi_dot", "multi_axpy", "second_update"};
 int thcmb_kernel_count(void) { return KID_COUNT; }
 const char* thcmb_kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? kKernelNames[kid] : ""; }
 int thcmb_profile_report(thcmb_ctx* c, int kid, int* count, double* total_ms) {
@@ -994,7 +995,11 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
         int dev = 0, ndev = 0;
         for (const char* v : {"THCM_DEVICE", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID"})
             if (const char* e = getenv(v)) { dev = atoi(e); break; }
-        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) dev %= ndev;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && dev >= ndev) {
+            fprintf(stderr, "thcm_b200: local rank %d but only %d CUDA device(s) on this node: ranks share devices (device %d); set THCM_DEVICE "
+                            "or start one rank per GPU\n", dev, ndev, dev % ndev);
+            dev %= ndev;
+        }
         s.device = dev;
     }
     g_dims[0] = s.N; g_dims[1] = s.M; g_dims[2] = s.L;

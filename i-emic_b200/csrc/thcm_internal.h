@@ -240,10 +240,9 @@ struct thcmb_ctx {
     int pfix_grow[2] = {-1, -1}, pfix_lrow[2] = {-1, -1};
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
     bool vmix_has_ocean = false;
-    int fused_cgs2 = 0;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
-                                    // iteration instead of four).  0 separate kernels, 1 basis values parked in shared memory, 2 L2-tiled
-                                    // (default on one rank; measured at 1 degree, r01d: 82.5 / 78.7 / 76.2 ms per Newton step).
-                                    // THCM_FUSED_CGS2 overrides; multi-rank runs default to 0 until measured
+    int fused_cgs2 = 2;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
+                                    // iteration instead of four).  0 separate kernels, 1 basis values parked in shared memory, 2 parked
+                                    // for nv <= 16 and L2-tiled above (default on any rank count).  THCM_FUSED_CGS2 overrides
     int gmres_ortho = 0;            // thcmb_newton_step: 0 modified Gram-Schmidt (GMRESSolver.H), 1 batched DGKS (Belos)
 };
 
@@ -308,7 +307,7 @@ int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
 int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out);
 int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w);
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out);
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid = -1);
 int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
                        const double* d_ww_old, int* d_flag_out, double* d_final_out, int* d_flag2_out = nullptr);
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);
@@ -357,7 +356,7 @@ double* work_vec(thcmb_ctx* c, int which);
 namespace thcm {
 enum KernelId { KID_ASM_RHS = 0, KID_ASM_JAC, KID_ASM_COUNT, KID_ASM_CRS, KID_SCAN, KID_SPMV, KID_DOT, KID_MGS, KID_AXPBY,
                 KID_AXPY_DEV, KID_SCALE, KID_COPY, KID_FILL, KID_PRECON_BUILD, KID_PRECON_APPLY, KID_HALO_PACK, KID_HALO_UNPACK,
-                KID_MULTIDOT, KID_MULTIAXPY, KID_COUNT };
+                KID_MULTIDOT, KID_MULTIAXPY, KID_SECOND_UPDATE, KID_COUNT };
 struct ProfScope {   // records an event pair around one kernel launch when profiling is on
     thcmb_ctx* c; bool on;
     ProfScope(thcmb_ctx* c_, int kid) : c(c_), on(c_->prof_on && c_->prof_kid.size() < 60000) {

@@ -956,15 +956,15 @@ int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const doubl
     return 0;
 }
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out) {
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid) {
     if (nv > MD_MAXV) {   // all but the last chunk only update; the last one also takes the norm of the fully updated vector
         const int last0 = (nv - 1) / MD_MAXV * MD_MAXV;
         multi_axpy_dev(c, n, last0, vecs, d_h, d_skip, w);
-        return multi_axpy_dot_dev(c, n, nv - last0, vecs + last0, d_h + last0, d_skip, w, d_ww, d_ww_old, d_flag_out, d_final_out);
+        return multi_axpy_dot_dev(c, n, nv - last0, vecs + last0, d_h + last0, d_skip, w, d_ww, d_ww_old, d_flag_out, d_final_out, kid);
     }
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
-    { ProfScope prof_(c, KID_MULTIAXPY);
+    { ProfScope prof_(c, kid >= 0 ? kid : KID_MULTIAXPY);
       const int grid = std::min(ew_grid(n), RED_BLOCKS);
       multi_axpy_dot_kernel<<<grid, RED_THREADS, 0, c->stream>>>(n, vl, d_h, d_skip, w, c->d_partial, c->d_counter, d_ww, p2p_args(c),
                                                                  RedEpilogue{d_ww_old, d_flag_out, d_final_out, nullptr}); }

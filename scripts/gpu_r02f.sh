@@ -10,7 +10,7 @@ for l in open('gpurun_out/bench_${TAG}.json'):
         print({k: (v.get('launches_per_step'), round(v['avg_ms'], 4), round(v.get('frac_of_peak', 0), 3), round(v.get('graph_equivalent_frac_of_peak', 0), 3)) for k, v in d['kernels'].items()})
 PY
 ( time python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err; tail -4 gpurun_out/bench_${TAG}_reference.err; cut -c1-400 gpurun_out/bench_${TAG}_reference.json
-timeout 420 python -m pytest tests -q -m gpu -p no:cacheprovider -x > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo rc=$? >> gpurun_out/pytest_gpu_$TAG.log; tail -4 gpurun_out/pytest_gpu_$TAG.log
+timeout 120 python __graft_entry__.py --smoke > gpurun_out/smoke_$TAG.log 2>&1; tail -1 gpurun_out/smoke_$TAG.log
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-b1 > gpurun_out/ncu_bench_$TAG.log 2>&1
 mkdir -p /tmp/ncu
 cap() { # name, kernel regex, skip, count, workload
@@ -18,7 +18,7 @@ cap() { # name, kernel regex, skip, count, workload
   ncu -i /tmp/ncu/$1.ncu-rep --page raw --csv > gpurun_out/ncu_raw_$1_$TAG.csv 2>/dev/null
   ls -la /tmp/ncu/$1.ncu-rep | awk '{print $5}'
 }
-cap asm "jac_tma|thcm_assemble|blockdiag_build|spmv_csr" 4 6 asm
+cap asm "jac_tma|thcm_assemble|rhs_tma|blockdiag_build|spmv_csr" 5 7 asm
 cap krylov25 "multi_dot|fused|multi_axpy_dot|spmv_compact|scale_precon" 118 8 krylov
 cap krylov50 "multi_dot|fused|multi_axpy_dot|spmv_compact|scale_precon" 238 5 krylov
 ncu -i /tmp/ncu/asm.ncu-rep --page source --csv --kernel-name regex:jac_tma 2>/dev/null | head -c 3000000 > gpurun_out/ncu_source_jac_$TAG.csv
