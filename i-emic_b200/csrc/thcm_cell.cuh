@@ -453,10 +453,12 @@ THCM_HD void eval_row(double* E, const DevTables& t, const DevBlock& blk, const 
 }
 
 // ---------------------------------------------------------------------------
-// Tracer mixing (mix_imp.f) with the shipped parameters (MIXP = MKAP = 0, ALPC = 1: no neutral physics, no GM, no
-// "consistent" mixing): what remains of vmix_fun is the implicit vertical mixing / convective adjustment
-//   Ftimp(k) = -tprstb(-drhodzt(k), SPL1) * P_VC * dtdzt(k)            on the top face of cell k   (mix_imp.f:489-492)
-//   mix_T    = (Ftimp(k) - Ftimp(k-1)) / (dz * dfzT(k))                                            (mix_imp.f:517-524)
+// Tracer mixing (mix_imp.f) without neutral physics and GM (MIXP = MKAP = 0; the reference's own THCM::evaluate cannot insert their
+// entries: they fall outside the maximal graph).  What remains of vmix_fun are the two vertical schemes
+//   Ftimp(k) = -tprstb(-drhodzt(k), SPL1) * P_VC * dtdzt(k)            implicit mixing / convective adjustment (mix_imp.f:489-492)
+//   Ftzt(k)  =  tprstb( drhodzt(k), SPL1) * eps * dtdzt(k) / (drhodzt(k) - 1e-20), eps = (1 - ALPC) * ENER * PE_V
+//                                                                      "consistent" vertical mixing, ALPC != 1 (mix_imp.f:478-487)
+//   mix_T    = (Ftzt(k) - Ftzt(k-1)) / (dz * dfzT(k)) + (Ftimp(k) - Ftimp(k-1)) / (dz * dfzT(k))   (mix_imp.f:511-524)
 // a function of T,S in the cell and its two vertical neighbours only.  tt / ss = T, S at k-1, k, k+1 as usol leaves them;
 // oc[3] = isoc (OCEAN or PERIO) of the three cells.  Operation order follows the reference statement by statement.
 // The only transcendental is tanh, taken from thcm_tanh.h: one specified algorithm (fdlibm's tanh through expm1, plain IEEE operations)
@@ -477,21 +479,28 @@ THCM_HD double vmix_value(const DevTables& t, int var, const double* tt, const d
 #pragma unroll
     for (int q = 0; q < 3; q++)
         rho[q] = t.mix_lambda * ss[q] - tt[q] - t.mix_xes * (alpt1 * tt[q] + alpt2 * tt[q] * tt[q] - alpt3 * tt[q] * tt[q] * tt[q]);
-    double Ft[2], Fs[2];   // [0]: face k-1 (below), [1]: face k (above)
+    double Ft[2], Fs[2];   // implicit mixing flux Ftimp / Fsimp; [0]: face k-1 (below), [1]: face k (above)
+    double Gt[2], Gs[2];   // explicit vertical flux Ftzt / Fszt of the "consistent" vertical mixing (ALPC != 1)
 #pragma unroll
     for (int f = 0; f < 2; f++) {
-        if (f == 0 && mt.k == 1) { Ft[0] = 0.0; Fs[0] = 0.0; continue; }       // Ftimp(:,:,0) is never set
+        Gt[f] = 0.0; Gs[f] = 0.0;
+        if (f == 0 && mt.k == 1) { Ft[0] = 0.0; Fs[0] = 0.0; continue; }       // Ftimp(:,:,0), Ftzt(:,:,0) are never set
         const double dzw = t.mix_dz * (f == 0 ? mt.dfzWm : mt.dfzW);
         const double io = oc[f + 1] * oc[f];
         const double drho = io * (rho[f + 1] - rho[f]) / dzw;
         const double dtz = io * (tt[f + 1] - tt[f]) / dzw;
         const double dsz = io * (ss[f + 1] - ss[f]) / dzw;
+        if (t.mix_eps != 0.0) {   // mix_imp.f:478-487: Ftzt = Ftzt + tprstb(drhodzt, SPL1) * eps * dtdzt / (drhodzt - epsln)
+            Gt[f] = Gt[f] + mix_tprstb(drho, t.mix_fac) * t.mix_eps * dtz / (drho - 1.0e-20);
+            Gs[f] = Gs[f] + mix_tprstb(drho, t.mix_fac) * t.mix_eps * dsz / (drho - 1.0e-20);
+        }
         if (t.mix_kvc != 0.0) {
             Ft[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dtz);
             Fs[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dsz);
         } else { Ft[f] = 0.0; Fs[f] = 0.0; }
     }
-    double mix = 0.0;   // the zonal, meridional and explicit vertical differences are exact zeros with these parameters
+    double mix = 0.0;   // the zonal and meridional differences are exact zeros without neutral physics / GM (refused, thcm_host.cpp)
+    mix = ((var == 4 ? Gt[1] : Gs[1]) - (var == 4 ? Gt[0] : Gs[0])) / (t.mix_dz * mt.dfzT) + mix;   // mix_imp.f:511-513, 541-543
     if (var == 4) {
         if (t.mix_rho) mix = ((Ft[1] - Ft[0]) - (Fs[1] - Fs[0]) * t.mix_lambda) / (2.0 * t.mix_dz * mt.dfzT) + mix;
         else mix = (Ft[1] - Ft[0]) / (t.mix_dz * mt.dfzT) + mix;

@@ -551,12 +551,14 @@ void compute_tables(thcmb_ctx* c) {
     if (t.coupled_T || t.coupled_S)
         for (int lj = 0; lj < c->blk.m0; lj++) for (int li = 0; li < c->blk.n0; li++)
             c->msi_local[(size_t)lj * c->blk.n0 + li] = c->msi[(size_t)(c->blk.i0 + li) + (size_t)s.N * (c->blk.j0 + lj)];
-    // tracer mixing (vmix_fun, mix_imp.f:231-562): only the implicit vertical mixing of the shipped parameter set is built
+    // tracer mixing (vmix_fun, mix_imp.f:231-562): the vertical schemes (implicit mixing / convective adjustment, consistent vertical
+    // mixing).  Neutral physics and GM put T,S entries on all 27 stencil positions; the reference's own C++ layer cannot take them
+    // (they are outside the maximal graph of THCM.C:2320-2549, ReplaceGlobalValues fails with "value excluded", THCM.C:1095-1104).
     const bool mix_on = c->vmix_flag >= 1 && c->vmix_dim > 0;
-    if (c->vmix_flag >= 1 && (par[MIXP] != 0.0 || par[MKAP] != 0.0 || par[ALPC] != 1.0))
-        fatal("Mixing >= 1 with MIXP != 0 (neutral physics), MKAP != 0 (Gent-McWilliams) or ALPC != 1 (consistent vertical mixing) "
-              "is not implemented on the B200 path; the shipped defaults (implicit vertical mixing / convective adjustment) are");
-    t.mix_lambda = lambda; t.mix_xes = xes; t.mix_kvc = par[P_VC]; t.mix_fac = s.alphaT * par[SPL1]; t.mix_dz = dz;
+    if (c->vmix_flag >= 1 && (par[MIXP] != 0.0 || par[MKAP] != 0.0))
+        fatal("Mixing >= 1 with MIXP != 0 (neutral physics) or MKAP != 0 (Gent-McWilliams): their Jacobian entries fall outside the "
+              "maximal matrix graph of THCM.C:2320-2549, so the reference's THCM::evaluate cannot assemble them either; not built");
+    t.mix_lambda = lambda; t.mix_xes = xes; t.mix_kvc = par[P_VC]; t.mix_eps = (1.0 - par[ALPC]) * par[ENER] * par[PE_V]; t.mix_fac = s.alphaT * par[SPL1]; t.mix_dz = dz;
     t.mix_temp = mix_on ? c->vmix_temp : 0; t.mix_salt = mix_on ? c->vmix_salt : 0;
     t.mix_rho = (s.rho_mixing && xes == 0.0) ? 1 : 0;
 }

@@ -51,7 +51,7 @@ struct DevTables {
     double epsr, dyi, cWT, cWS, c2, c3, tdzi2;
     // tracer mixing (mix_imp.f): implicit vertical mixing / convective adjustment.  mix_temp / mix_salt = vmix_temp / vmix_salt
     // (0 when mixing is off), mix_fac = alphaT * SPL1 (tprstb), mix_rho = rho_mixing .and. xes == 0
-    double mix_lambda, mix_xes, mix_kvc, mix_fac, mix_dz;
+    double mix_lambda, mix_xes, mix_kvc, mix_eps, mix_fac, mix_dz;   // mix_eps = (1 - ALPC) * ENER * PE_V (consistent vertical mixing)
     int mix_temp, mix_salt, mix_rho;
     // coupled mode (coupled_T / coupled_S = 1, usrc.F90:733-786): surface-level terms of the T and S rows that replace the
     // restoring term.  msi = sea-ice mask of the owned columns (n0*m0, i fastest); every constant is the sub-expression the

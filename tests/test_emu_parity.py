@@ -96,6 +96,42 @@ def test_tracer_mixing_bit_exact(name, vmix, rho_mixing, xes):
     assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
 
 
+@pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "global4deg"])
+@pytest.mark.parametrize("alpc,pvc,rho_mixing,xes", [(0.5, None, 0, 1.0), (0.0, 0.0, 0, 0.0), (0.7, None, 1, 0.0)])
+def test_consistent_vertical_mixing_bit_exact(name, alpc, pvc, rho_mixing, xes):
+    """ALPC != 1 ("consistent" vertical mixing, mix_imp.f:478-487: Ftzt = tprstb(drhodzt) * eps * dtdzt / (drhodzt - 1e-20) with
+    eps = (1 - ALPC) * ENER * PE_V), alone (P_VC = 0) and together with the implicit mixing: residual, every Jacobian value incl. the
+    forward-difference block, CRS pattern / order / values against the oracle's whole-field vmix_fun / vmix_jac."""
+    pars = dict(cases.DEFAULT_PARS, NLES=xes, ALPC=alpc)
+    if pvc is not None:
+        pars["P_VC"] = pvc
+    s, landm, o, e = setup(name, pars=pars, vmix=1, rho_mixing=rho_mixing)
+    x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
+    ref = OracleTHCM(s, landm)                      # the same run with ALPC = 1: the new term must actually be live
+    for k, v in dict(pars, ALPC=1.0).items():
+        ref.setpar(P[k], v)
+    assert np.abs(o.vmix_fun(x) - ref.vmix_fun(x)).max() > 0
+    assert np.array_equal(o.rhs(x), e.rhs(x))
+    assert np.array_equal(o.jacobian_graph(x)[0], e.jacobian(x))
+    bo, jo, co, _ = o.matrix(x)
+    be, je, ce = e.crs(x)
+    assert np.array_equal(bo, be) and np.array_equal(jo, je) and np.array_equal(co, ce)
+
+
+def test_neutral_physics_leaves_the_reference_graph():
+    """Why MIXP / MKAP != 0 stay refused: with neutral physics or GM the forward-difference block of vmix_jac has T,S entries on
+    stencil positions outside the maximal graph of THCM.C:2320-2549 -- THCM::evaluate's ReplaceGlobalValues (THCM.C:1095-1104) fails on
+    them, so the reference's own hot path cannot run these modes either; with the vertical schemes every entry is inside."""
+    s, landm = cases.natl8(vmix=1)
+    x = cases.random_state(s, landm, scale=0.3)
+    for pars, outside in [(dict(ALPC=0.5), False), (dict(MIXP=0.5), True), (dict(MKAP=0.5), True)]:
+        o = OracleTHCM(s, landm)
+        for k, v in dict(cases.DEFAULT_PARS, **pars).items():
+            o.setpar(P[k], v)
+        _, missing = o.jacobian_graph(x)
+        assert (missing > 0) == outside, (pars, missing)
+
+
 def test_mixing_partition_follows_the_fields():
     """Mixing = 2 (vmix_control, mix_imp.f:139-169): a zero temperature field switches the temperature mixing off, and --
     because the reference only re-partitions when the TEMPERATURE flag is set (:163) -- leaves the pair count at zero."""

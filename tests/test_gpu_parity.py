@@ -98,12 +98,14 @@ def test_jacobian_kernel_variants_bit_exact(gpu, name, variant, monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "box_p", "global4deg"])
-@pytest.mark.parametrize("vmix,rho_mixing,xes", [(1, 0, 1.0), (1, 1, 0.0), (2, 0, 0.0)])
-def test_tracer_mixing(gpu, name, vmix, rho_mixing, xes):
+@pytest.mark.parametrize("vmix,rho_mixing,xes,extra", [(1, 0, 1.0, {}), (1, 1, 0.0, {}), (2, 0, 0.0, {}), (1, 0, 1.0, {"ALPC": 0.5}),
+                                                       (1, 1, 0.0, {"ALPC": 0.0, "P_VC": 0.0})])
+def test_tracer_mixing(gpu, name, vmix, rho_mixing, xes, extra):
     """Mixing = 1, 2 on the device: bit-exact against the oracle, the forward-difference mixing block of the Jacobian included -- both
     sides evaluate tprstb's tanh (mix_imp.f:837-857) with the same specified algorithm (thcm_tanh.h / oracle/fdlibm_tanh.h), so the
-    1 / eps = 1e8 amplification of vmix_jac (mix_imp.f:729-815) has nothing to amplify."""
-    s, landm, o, t = setup(gpu, name, pars=dict(cases.DEFAULT_PARS, NLES=xes), vmix=vmix, rho_mixing=rho_mixing)
+    1 / eps = 1e8 amplification of vmix_jac (mix_imp.f:729-815) has nothing to amplify.  `extra`: ALPC != 1 switches the "consistent"
+    vertical mixing on (mix_imp.f:478-487), with and without the implicit scheme (P_VC = 0)."""
+    s, landm, o, t = setup(gpu, name, pars=dict(cases.DEFAULT_PARS, NLES=xes, **extra), vmix=vmix, rho_mixing=rho_mixing)
     x = cases.random_state(s, landm, scale=0.3, zero_on_land=False)
     xd = dev(x)
     B = o.rhs(x)
