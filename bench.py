@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--ortho", default="dgks", choices=["mgs", "dgks"],
                     help="GMRES orthogonalisation: mgs = src/gmressolver template, dgks = batched Gram-Schmidt as Belos uses in Ocean::solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mixing", action="store_true", help="skip the Mixing = 1 timing (second instance, same grid and state)")
     ap.add_argument("--no-b1", action="store_true", help="skip the timing of the B1 Fortran-symbol boundary (rhs_ + matrix_ with host buffers)")
     return ap.parse_args()
 
@@ -525,6 +526,11 @@ def main():
                                       "graph_equivalent_gbs": gb_g, "graph_equivalent_frac_of_peak": gb_g / peak,
                                       "graph_equivalent_frac_of_nominal_8TBs": gb_g / 8000.0}
     t.close()
+    if a.gpus == 1 and not a.no_mixing:
+        try:
+            line["mixing1"] = mixing_timing(n, m, l, xg, iters, a, peak)
+        except Exception as ex:
+            line["mixing1"] = {"failed": str(ex)}
     if a.gpus == 1 and not a.no_b1 and [n, m, l] == list(GRID):
         try:
             line["e2e_b1"] = b1_boundary_timing(s, landm, x_local)
@@ -542,6 +548,49 @@ def main():
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
+
+
+def mixing_timing(n, m, l, xg, iters, a, peak):
+    """The same grid, state and parameters with Mixing = 1 (the default of the reference's run configurations: implicit vertical mixing /
+    convective adjustment, mix_imp.f:489-492, whose forward-difference Jacobian block costs six extra evaluations of the mixing term per
+    T / S row, mix_imp.f:729-815): device time of the residual kernel, the Jacobian pair and the whole fixed-work Newton step."""
+    import torch
+    import cases
+    import iemic_b200
+    s, landm = cases.global_synth(n, m, l, vmix=1)
+    t = iemic_b200.THCM(s, landm, None)
+    for k, v in PARS.items():
+        t.setParameter(k, v)
+    t.set_ortho(a.ortho)
+    xd = torch.from_numpy(xg).cuda()
+    dx, F = t.new_vector(), t.new_vector()
+    for _ in range(3):
+        t.newton_step_dev(xd, dx, tol=0.0, maxit=iters - 1, restart=iters, precon=a.precon)
+    torch.cuda.synchronize(); t.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(t.stream)
+    for _ in range(a.steps):
+        res, _ = t.newton_step_dev(xd, dx, tol=0.0, maxit=iters - 1, restart=iters, precon=a.precon)
+    e1.record(t.stream)
+    torch.cuda.synchronize(); t.sync()
+    step_ms = e0.elapsed_time(e1) / a.steps
+    t.profile(True)
+    for _ in range(10):
+        t.evaluate(xd, F, True)
+    prof = t.profile_report()
+    t.profile(False)
+    ncell = t.ndim // 6
+    ntile_all, ntile_active = t.tile_counts()
+    jac_bytes = int(ncell * ntile_active / max(ntile_all, 1)) * 49 + 8 * int(t.nnz * ntile_active / max(ntile_all, 1))
+    out = {"what": "Mixing = 1 (implicit vertical mixing / convective adjustment + forward-difference Jacobian block), same grid, state, parameters",
+           "ms_per_step": step_ms, "gmres": {"iters": res.iters, "resid": res.resid}, "vmix_flags": t.vmix_flags()}
+    for key, name, nbytes in (("residual", "thcm_assemble<RHS>", ncell * 145), ("jacobian", "thcm_assemble<JAC_GRAPH>", jac_bytes)):
+        if name in prof:
+            cnt, tot = prof[name]
+            out[key + "_ms"] = tot / cnt
+            out[key + "_frac_of_peak"] = nbytes / (tot / cnt * 1e-3) / 1e9 / peak
+    t.close()
+    return out
 
 
 def b1_boundary_timing(s, landm, x):

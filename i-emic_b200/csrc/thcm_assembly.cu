@@ -569,9 +569,11 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
 // types (u | v | w + p | T | S), no output staging: every lane owns one cell and writes its rows.  Tiles that are entirely LAND
 // are not visited (B = 0 there, usrc.F90:580-591: the output is zeroed first and the blocks walk the list of the other tiles).
 // =============================================================================
-constexpr int RHS_LINES = 0xBE;   // union of the row groups' lines
-struct alignas(16) RhsSmem {
-    Stage<RHS_LINES> st;
+// The residual runs as the same two row-group kernels as the Jacobian (u | v | w+p and T | S): with all five instruction streams in one
+// kernel the top stall was no_instruction (ncu r02m: 6.2 per issue) -- the unrolled row evaluations of several co-resident blocks do not
+// fit the instruction cache -- and 70 registers x 160 threads capped the SM at 5 blocks.
+template <int GROUP> struct alignas(16) RhsSmem {
+    Stage<RowGroup<GROUP>::LINES> st;
     unsigned long long bar;
 };
 template <class ST> struct RhsTile {
@@ -624,11 +626,12 @@ __device__ __forceinline__ void rhs_row(const AsmArgs& a, const ST& st, const Ti
     B = B * (((nb >> 4) & 1u) ? 0.0 : 1.0);                                           // usrc.F90:580-591
     a.out[row] = a.sign * B;
 }
-template <bool CPL>
-__global__ void __launch_bounds__(160) thcm_rhs_tma_kernel(const AsmArgs a) {
+template <int GROUP, bool CPL>
+__global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP) thcm_rhs_tma_kernel(const AsmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RhsSmem& sh = *reinterpret_cast<RhsSmem*>(smem_raw);
-    using ST = Stage<RHS_LINES>;
+    using G = RowGroup<GROUP>;
+    RhsSmem<GROUP>& sh = *reinterpret_cast<RhsSmem<GROUP>*>(smem_raw);
+    using ST = Stage<G::LINES>;
     ST& st = sh.st;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = a.tile_list ? a.tile_list[blockIdx.x] : (int)blockIdx.x;
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(160) thcm_rhs_tma_kernel(const AsmArgs a) {
             mbar_expect_tx(&sh.bar, (uint32_t)(ST::NL * w * NUN * sizeof(double) + sizeof(TileDesc) + sizeof(st.tj) + sizeof(st.tk)));
         __syncwarp();
         if (lane < 9) {
-            if ((RHS_LINES >> lane) & 1) {
+            if ((G::LINES >> lane) & 1) {
                 LineSeg seg[3];
                 const int ns = line_plan(a.b, g, lane, seg);
 #pragma unroll
@@ -661,21 +664,24 @@ __global__ void __launch_bounds__(160) thcm_rhs_tma_kernel(const AsmArgs a) {
     __syncthreads();
     const bool open_ocean = (st.desc.flags & 2u) != 0;
     const bool interior = g.gi0 > 1 && g.gi0 + g.ncell - 1 < a.b.N && g.gj > 1 && g.gj < a.b.M && g.k > 1 && g.k < a.b.L;
-    switch (warp) {
-    case 0: rhs_row<1, CPL>(a, st, g, lane, open_ocean, interior); break;
-    case 1: rhs_row<2, CPL>(a, st, g, lane, open_ocean, interior); break;
-    case 2: rhs_row<3, CPL>(a, st, g, lane, open_ocean, interior); rhs_row<4, CPL>(a, st, g, lane, open_ocean, interior); break;
-    case 3: rhs_row<5, CPL>(a, st, g, lane, open_ocean, interior); break;
-    default: rhs_row<6, CPL>(a, st, g, lane, open_ocean, interior); break;
+    if constexpr (GROUP == 0) {
+        switch (warp) {
+        case 0: rhs_row<1, CPL>(a, st, g, lane, open_ocean, interior); break;
+        case 1: rhs_row<2, CPL>(a, st, g, lane, open_ocean, interior); break;
+        default: rhs_row<3, CPL>(a, st, g, lane, open_ocean, interior); rhs_row<4, CPL>(a, st, g, lane, open_ocean, interior); break;
+        }
+    } else {
+        if (warp == 0) rhs_row<5, CPL>(a, st, g, lane, open_ocean, interior);
+        else rhs_row<6, CPL>(a, st, g, lane, open_ocean, interior);
     }
 }
-template <bool CPL> static void launch_rhs_tma_t(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
+template <int GROUP, bool CPL> static void launch_rhs_tma_t(thcmb_ctx* c, const AsmArgs& a, int nblocks) {
     static bool attr_set = false;
     if (!attr_set) {
-        THCM_CUDA(cudaFuncSetAttribute(thcm_rhs_tma_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem)));
+        THCM_CUDA(cudaFuncSetAttribute(thcm_rhs_tma_kernel<GROUP, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RhsSmem<GROUP>)));
         attr_set = true;
     }
-    if (nblocks > 0) thcm_rhs_tma_kernel<CPL><<<nblocks, 160, sizeof(RhsSmem), c->stream>>>(a);
+    if (nblocks > 0) thcm_rhs_tma_kernel<GROUP, CPL><<<nblocks, 32 * RowGroup<GROUP>::NWARP, sizeof(RhsSmem<GROUP>), c->stream>>>(a);
 }
 static void launch_rhs_tma(thcmb_ctx* c, AsmArgs a) {
     int nblocks = a.ntile;
@@ -683,8 +689,10 @@ static void launch_rhs_tma(thcmb_ctx* c, AsmArgs a) {
         THCM_CUDA(cudaMemsetAsync(a.out, 0, sizeof(double) * (size_t)NUN * a.b.ncell, c->stream));
         a.tile_list = c->d_active_tiles; nblocks = c->n_active_tiles;
     }
-    if (a.t.coupled_T || a.t.coupled_S) launch_rhs_tma_t<true>(c, a, nblocks);
-    else launch_rhs_tma_t<false>(c, a, nblocks);
+    launch_rhs_tma_t<0, false>(c, a, nblocks);   // coupled mode only touches the T | S rows
+    if (a.t.coupled_T || a.t.coupled_S) launch_rhs_tma_t<1, true>(c, a, nblocks);
+    else launch_rhs_tma_t<1, false>(c, a, nblocks);
+    c->launches++;   // two kernels per residual
 }
 
 template <int GROUP, int BLOCKS_PER_SM, bool CPL> static void launch_jac_tma_group(thcmb_ctx* c, const AsmArgs& a, int nblocks) {

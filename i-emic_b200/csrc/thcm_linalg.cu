@@ -938,7 +938,15 @@ int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double
     if (!c->d_mdpartial) THCM_CUDA(cudaMalloc(&c->d_mdpartial, sizeof(double) * (size_t)MD_BLOCKS * (MD_MAXV + 1)));
     { ProfScope prof_(c, KID_MULTIDOT);
       const int nchunk = std::max(1, (nv + MD_CHUNK - 1) / MD_CHUNK);
-      const int slices = std::max(NSM / 2, MD_BLOCKS / nchunk);
+      // ONE wave: slices x chunks = what the SMs hold at once (76 registers x 256 threads: 3 blocks per SM -- the 592 blocks of the
+      // r02m build ran as 444 + a 148-block tail at a third of the occupancy, ~8 % of the kernel)
+      static int resident = 0;
+      if (!resident) {
+          int occ = 0;
+          THCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, multi_dot_kernel, RED_THREADS, 0));
+          resident = std::min(MD_BLOCKS, NSM * std::max(occ, 1));
+      }
+      const int slices = std::max(32, resident / nchunk);
       multi_dot_kernel<<<dim3(slices, nchunk), RED_THREADS, 0, c->stream>>>(n, vl, w, d_skip, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c)); }
     c->launches++;
     return c->p2p_on ? 0 : allreduce_dev(c, d_out, nv + 1);
