@@ -844,6 +844,23 @@ static bool g_have_global = false;
 static std::vector<int> g_landm_global;
 static thcmb_ctx* g_ctx = nullptr;
 static int *g_dbeg = nullptr, *g_djco = nullptr; static double* g_dco = nullptr;
+// The caller's CRS arrays live from set_pointers to finalize_ (THCM.C:619-638 allocates them once, THCM::~THCM calls finalize_ before it
+// deletes them, THCM.C:798-812): the prefix that actually travels (begA, and jcoA / coA up to 1.25 x the entry count) is page-locked so
+// that matrix_'s device-to-host copies run at PCIe speed instead of through the driver's pageable staging (0.95 GB per Jacobian at 1
+// degree).  Released by set_pointers, init_ and finalize_; THCM_PIN_CRS=0 keeps the buffers pageable.
+static struct PinnedPrefix { void* p = nullptr; size_t bytes = 0, cap = 0; } g_pin[3];
+static void unpin_crs() {
+    for (auto& e : g_pin) { if (e.p) { cudaHostUnregister(e.p); cudaGetLastError(); } e = PinnedPrefix{}; }
+}
+static void pin_prefix(int which, void* p, size_t bytes, size_t cap_bytes) {
+    static const bool on = !(getenv("THCM_PIN_CRS") && atoi(getenv("THCM_PIN_CRS")) == 0);
+    PinnedPrefix& e = g_pin[which];
+    if (!on || !p || (e.p == p && e.bytes >= bytes)) return;
+    if (e.p) { cudaHostUnregister(e.p); cudaGetLastError(); e = PinnedPrefix{}; }
+    const size_t want = std::min(cap_bytes, bytes + bytes / 4);
+    if (cudaHostRegister(p, want, cudaHostRegisterDefault) == cudaSuccess) { e.p = p; e.bytes = want; e.cap = cap_bytes; }
+    else cudaGetLastError();   // (locked-memory limit, exotic allocator ...): the copy simply stays pageable
+}
 
 static thcmb_ctx* G() { if (!g_ctx) fatal("THCM not initialised: call init_ first"); return g_ctx; }
 static int g_dims[3] = {0, 0, 0};   // n, m, l of the instance init_ is creating / has created
@@ -1007,6 +1024,7 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     s.coriolis_on = *coriolis_on; s.periodic = *periodic; s.rank = 0; s.nranks = 1;
     if (g_ctx) {   // THCM is a singleton that replaces the previous instance (THCM.H:76-84); the CRS staging buffers were sized for it
         thcmb_destroy(g_ctx); g_ctx = nullptr;
+        unpin_crs();
         for (void* p : {(void*)g_dbeg, (void*)g_djco, (void*)g_dco}) if (p) cudaFree(p);
         g_dbeg = g_djco = nullptr; g_dco = nullptr;
     }
@@ -1021,6 +1039,7 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     refresh_params(g_ctx);
 }
 void finalize_(void) {
+    unpin_crs();
     if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }
     for (void* p : {(void*)g_dbeg, (void*)g_djco, (void*)g_dco}) if (p) cudaFree(p);
     g_dbeg = g_djco = nullptr; g_dco = nullptr;
@@ -1030,8 +1049,10 @@ void __m_mat_MOD_get_array_sizes(int* nrows, int* nnz) {  // mat.F90:56-68
     *nnz = G()->blk.ndim() * (NUN * NP + 1);
 }
 void __m_mat_MOD_set_pointers(int* nrows, int* nnz, int* begA, int* jcoA, double* coA, double* coB, int* begF, int* jcoF, double* coF) {
-    (void)nrows; (void)nnz;
+    (void)nrows;
     thcmb_ctx* c = G();
+    unpin_crs();
+    c->crs_cap = nnz ? (long long)*nnz : 0;
     c->begA = begA; c->jcoA = jcoA; c->coA = coA; c->coB = coB;
     c->begF = begF; c->jcoF = jcoF; c->coF = coF;
 }
@@ -1067,6 +1088,11 @@ void matrix_(double* un) {
     stage_begin(c);
     long long nnz = thcmb_jacobian_crs_dev(c, c->d_un, g_dbeg, g_djco, g_dco);
     stage_end(c, "nlin_jac+boundaries+fillcolA");
+    if (c->crs_cap > 0 && nnz > c->crs_cap) fatal("matrix_: the Jacobian holds more entries than the arrays handed to set_pointers");
+    const size_t cap = c->crs_cap > 0 ? (size_t)c->crs_cap : (size_t)nnz;
+    pin_prefix(0, c->begA, sizeof(int) * (size_t)(n + 1), sizeof(int) * (size_t)(n + 1));
+    pin_prefix(1, c->jcoA, sizeof(int) * (size_t)nnz, sizeof(int) * cap);
+    pin_prefix(2, c->coA, sizeof(double) * (size_t)nnz, sizeof(double) * cap);
     THCM_CUDA(cudaMemcpyAsync(c->begA, g_dbeg, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, c->stream));
     THCM_CUDA(cudaMemcpyAsync(c->jcoA, g_djco, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));
     THCM_CUDA(cudaMemcpyAsync(c->coA, g_dco, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, c->stream));

@@ -471,44 +471,57 @@ THCM_HD double mix_tprstb(double grad, double fac) {   // mix_imp.f:837-857
     double th = fd_tanh(a * a * a);
     return th > 0.0 ? th : 0.0;
 }
+// the four vertical fluxes through ONE cell face, between the cell below (lo) and the cell above (hi) it: implicit mixing Ftimp / Fsimp
+// and consistent mixing Ftzt / Fszt.  io = isoc(lo) * isoc(hi), dzw = dz * dfzW(face).  One taper evaluation per scheme and face
+// (the reference evaluates tprstb twice with the same argument, for T and for S: the same bits).
+struct MixFace { double Ft, Fs, Gt, Gs; };
+THCM_HD double mix_rho_of(const DevTables& t, double tt, double ss) {
+    constexpr double alpt1 = 2.93, alpt2 = 8.3e-02, alpt3 = 6.6e-04;   // usr.F90:151-153
+    return t.mix_lambda * ss - tt - t.mix_xes * (alpt1 * tt + alpt2 * tt * tt - alpt3 * tt * tt * tt);
+}
+THCM_HD MixFace mix_face(const DevTables& t, double t_lo, double t_hi, double s_lo, double s_hi, double io, double dzw) {
+    const double drho = io * (mix_rho_of(t, t_hi, s_hi) - mix_rho_of(t, t_lo, s_lo)) / dzw;
+    const double dtz = io * (t_hi - t_lo) / dzw;
+    const double dsz = io * (s_hi - s_lo) / dzw;
+    MixFace F{0.0, 0.0, 0.0, 0.0};
+    if (t.mix_eps != 0.0) {   // mix_imp.f:478-487: Ftzt = Ftzt + tprstb(drhodzt, SPL1) * eps * dtdzt / (drhodzt - epsln)
+        const double tp = mix_tprstb(drho, t.mix_fac);
+        F.Gt = F.Gt + tp * t.mix_eps * dtz / (drho - 1.0e-20);
+        F.Gs = F.Gs + tp * t.mix_eps * dsz / (drho - 1.0e-20);
+    }
+    if (t.mix_kvc != 0.0) {   // mix_imp.f:489-492
+        const double tp = mix_tprstb(-drho, t.mix_fac);
+        F.Ft = -(tp * t.mix_kvc * dtz);
+        F.Fs = -(tp * t.mix_kvc * dsz);
+    }
+    return F;
+}
+// divergence of the fluxes of the faces below (F0) and above (F1) a cell (mix_imp.f:495-560); var = 4: temperature row, 5: salinity row.
+// The zonal and meridional differences are exact zeros without neutral physics / GM (refused, thcm_host.cpp).
+THCM_HD double mix_combine(const DevTables& t, int var, const MixFace& F0, const MixFace& F1, double dfzT) {
+    double mix = 0.0;
+    mix = ((var == 4 ? F1.Gt : F1.Gs) - (var == 4 ? F0.Gt : F0.Gs)) / (t.mix_dz * dfzT) + mix;   // mix_imp.f:511-513, 541-543
+    if (var == 4) {
+        if (t.mix_rho) mix = ((F1.Ft - F0.Ft) - (F1.Fs - F0.Fs) * t.mix_lambda) / (2.0 * t.mix_dz * dfzT) + mix;
+        else mix = (F1.Ft - F0.Ft) / (t.mix_dz * dfzT) + mix;
+    } else {
+        if (t.mix_rho) mix = ((F1.Fs - F0.Fs) - (F1.Ft - F0.Ft) / t.mix_lambda) / (2.0 * t.mix_dz * dfzT) + mix;
+        else mix = (F1.Fs - F0.Fs) / (t.mix_dz * dfzT) + mix;
+    }
+    return mix;
+}
+// face below cell k: Ftimp(:,:,0) and Ftzt(:,:,0) are never set (k = 1)
+THCM_HD MixFace mix_face_below(const DevTables& t, const double* tt, const double* ss, const double* oc, const MixTabs& mt) {
+    if (mt.k == 1) return MixFace{0.0, 0.0, 0.0, 0.0};
+    return mix_face(t, tt[0], tt[1], ss[0], ss[1], oc[1] * oc[0], t.mix_dz * mt.dfzWm);
+}
+THCM_HD MixFace mix_face_above(const DevTables& t, const double* tt, const double* ss, const double* oc, const MixTabs& mt) {
+    return mix_face(t, tt[1], tt[2], ss[1], ss[2], oc[2] * oc[1], t.mix_dz * mt.dfzW);
+}
 // var = 4: temperature row, 5: salinity row
 THCM_HD double vmix_value(const DevTables& t, int var, const double* tt, const double* ss, const double* oc, const MixTabs& mt) {
     if (!(var == 4 ? t.mix_temp : t.mix_salt)) return 0.0;
-    constexpr double alpt1 = 2.93, alpt2 = 8.3e-02, alpt3 = 6.6e-04;   // usr.F90:151-153
-    double rho[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++)
-        rho[q] = t.mix_lambda * ss[q] - tt[q] - t.mix_xes * (alpt1 * tt[q] + alpt2 * tt[q] * tt[q] - alpt3 * tt[q] * tt[q] * tt[q]);
-    double Ft[2], Fs[2];   // implicit mixing flux Ftimp / Fsimp; [0]: face k-1 (below), [1]: face k (above)
-    double Gt[2], Gs[2];   // explicit vertical flux Ftzt / Fszt of the "consistent" vertical mixing (ALPC != 1)
-#pragma unroll
-    for (int f = 0; f < 2; f++) {
-        Gt[f] = 0.0; Gs[f] = 0.0;
-        if (f == 0 && mt.k == 1) { Ft[0] = 0.0; Fs[0] = 0.0; continue; }       // Ftimp(:,:,0), Ftzt(:,:,0) are never set
-        const double dzw = t.mix_dz * (f == 0 ? mt.dfzWm : mt.dfzW);
-        const double io = oc[f + 1] * oc[f];
-        const double drho = io * (rho[f + 1] - rho[f]) / dzw;
-        const double dtz = io * (tt[f + 1] - tt[f]) / dzw;
-        const double dsz = io * (ss[f + 1] - ss[f]) / dzw;
-        if (t.mix_eps != 0.0) {   // mix_imp.f:478-487: Ftzt = Ftzt + tprstb(drhodzt, SPL1) * eps * dtdzt / (drhodzt - epsln)
-            Gt[f] = Gt[f] + mix_tprstb(drho, t.mix_fac) * t.mix_eps * dtz / (drho - 1.0e-20);
-            Gs[f] = Gs[f] + mix_tprstb(drho, t.mix_fac) * t.mix_eps * dsz / (drho - 1.0e-20);
-        }
-        if (t.mix_kvc != 0.0) {
-            Ft[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dtz);
-            Fs[f] = -(mix_tprstb(-drho, t.mix_fac) * t.mix_kvc * dsz);
-        } else { Ft[f] = 0.0; Fs[f] = 0.0; }
-    }
-    double mix = 0.0;   // the zonal and meridional differences are exact zeros without neutral physics / GM (refused, thcm_host.cpp)
-    mix = ((var == 4 ? Gt[1] : Gs[1]) - (var == 4 ? Gt[0] : Gs[0])) / (t.mix_dz * mt.dfzT) + mix;   // mix_imp.f:511-513, 541-543
-    if (var == 4) {
-        if (t.mix_rho) mix = ((Ft[1] - Ft[0]) - (Fs[1] - Fs[0]) * t.mix_lambda) / (2.0 * t.mix_dz * mt.dfzT) + mix;
-        else mix = (Ft[1] - Ft[0]) / (t.mix_dz * mt.dfzT) + mix;
-    } else {
-        if (t.mix_rho) mix = ((Fs[1] - Fs[0]) - (Ft[1] - Ft[0]) / t.mix_lambda) / (2.0 * t.mix_dz * mt.dfzT) + mix;
-        else mix = (Fs[1] - Fs[0]) / (t.mix_dz * mt.dfzT) + mix;
-    }
-    return mix;
+    return mix_combine(t, var, mix_face_below(t, tt, ss, oc, mt), mix_face_above(t, tt, ss, oc, mt), mt.dfzT);
 }
 // gathers the column and evaluates the mixing term of row R (TT or SS) of one cell; nb = the cell's neighbour mask
 template <int R, class Tile, class Tabs>
@@ -522,23 +535,29 @@ THCM_HD double vmix_rhs(const DevTables& t, const Cell& c, uint32_t nb, const Ti
     const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
     return vmix_value(t, R == TT ? 4 : 5, tt, ss, oc, mt);
 }
-// one column pair of the forward-difference block: T and S of the cell at vertical offset Q-1 (stencil position LOC)
+// one column pair of the forward-difference block: T and S of the cell at vertical offset Q-1 (stencil position LOC).  A perturbation of
+// the cell below (Q = 0) moves only the face below, one of the cell above (Q = 2) only the face above: the other face keeps the bits of
+// the unperturbed evaluation (F0 / F1), so only the faces that change are re-evaluated -- 10 taper evaluations per row instead of 28.
 template <int R, int LOC, int Q>
-THCM_HD void vmix_fd_one(double* E, const DevTables& t, int var, double f0, const double* tt, const double* ss, const double* oc,
-                         const MixTabs& mt) {
+THCM_HD void vmix_fd_one(double* E, const DevTables& t, int var, double f0, const MixFace& F0, const MixFace& F1, const double* tt,
+                         const double* ss, const double* oc, const MixTabs& mt) {
     const double eps = 1.0e-08;
     // the neighbour is a column only if it is an OCEAN cell of the domain (k-1 >= 1, k+1 <= L: the frame is LAND)
     if (oc[Q] == 0.0) return;
     if (t.mix_temp) {
         double tp[3] = {tt[0], tt[1], tt[2]};
         tp[Q] = tt[Q] + eps;
-        const double d = vmix_value(t, var, tp, ss, oc, mt) - f0;
+        const MixFace A = Q == 2 ? F0 : mix_face_below(t, tp, ss, oc, mt);
+        const MixFace B = Q == 0 ? F1 : mix_face_above(t, tp, ss, oc, mt);
+        const double d = mix_combine(t, var, A, B, mt.dfzT) - f0;
         entref<R, LOC, TT>(E) = entref<R, LOC, TT>(E) + d / eps;
     }
     if (t.mix_salt) {
         double sp[3] = {ss[0], ss[1], ss[2]};
         sp[Q] = ss[Q] + eps;
-        const double d = vmix_value(t, var, tt, sp, oc, mt) - f0;
+        const MixFace A = Q == 2 ? F0 : mix_face_below(t, tt, sp, oc, mt);
+        const MixFace B = Q == 0 ? F1 : mix_face_above(t, tt, sp, oc, mt);
+        const double d = mix_combine(t, var, A, B, mt.dfzT) - f0;
         entref<R, LOC, SS>(E) = entref<R, LOC, SS>(E) + d / eps;
     }
 }
@@ -556,10 +575,11 @@ THCM_HD void vmix_jac(double* E, const DevTables& t, const Cell& c, uint32_t nb,
     oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
     const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
     constexpr int var = R == TT ? 4 : 5;
-    const double f0 = vmix_value(t, var, tt, ss, oc, mt);
-    vmix_fd_one<R, 14, 0>(E, t, var, f0, tt, ss, oc, mt);
-    vmix_fd_one<R, 5, 1>(E, t, var, f0, tt, ss, oc, mt);
-    vmix_fd_one<R, 23, 2>(E, t, var, f0, tt, ss, oc, mt);
+    const MixFace F0 = mix_face_below(t, tt, ss, oc, mt), F1 = mix_face_above(t, tt, ss, oc, mt);
+    const double f0 = mix_combine(t, var, F0, F1, mt.dfzT);
+    vmix_fd_one<R, 14, 0>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
+    vmix_fd_one<R, 5, 1>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
+    vmix_fd_one<R, 23, 2>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
 }
 
 // ---------------------------------------------------------------------------

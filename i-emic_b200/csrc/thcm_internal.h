@@ -239,6 +239,7 @@ struct thcmb_ctx {
     double* d_iccoeff = nullptr;                     // intcondCoeff_ on the owned rows
     int pfix_grow[2] = {-1, -1}, pfix_lrow[2] = {-1, -1};
     int vmix_fix = 1, vmix_flag = 0, vmix_temp = 0, vmix_salt = 0, vmix_dim = 0;   // mix_imp.f:61-169
+    long long crs_cap = 0;   // entries the caller's jcoA / coA hold (set_pointers' nnz argument)
     bool vmix_has_ocean = false;
     int fused_cgs2 = 2;             // DGKS: first update + second projection in one sweep over the basis (three reads of the basis per
                                     // iteration instead of four).  0 separate kernels, 1 basis values parked in shared memory, 2 parked

@@ -22,6 +22,14 @@
 #endif
 #endif
 
+// The tanh itself is NOT inlined on the device: the mixing Jacobian calls it ten times per tracer row, and ten inlined copies of these
+// branches (two FP64 divisions each) in every unrolled row evaluation pushed the assembly kernels out of the instruction cache.
+#ifdef __CUDACC__
+#define THCM_TANH_FN static __host__ __device__ __noinline__
+#else
+#define THCM_TANH_FN inline
+#endif
+
 namespace thcm {
 
 THCM_HD uint32_t f64_hi(double x) {
@@ -115,7 +123,7 @@ THCM_HD double fd_expm1(double x) {
 }
 
 // tanh(x): |x| < 2^-55 -> x (1 + x); |x| < 1 -> -t / (t + 2), t = expm1(-2|x|); |x| < 22 -> 1 - 2 / (t + 2), t = expm1(2|x|); else 1 - tiny
-THCM_HD double fd_tanh(double x) {
+THCM_TANH_FN double fd_tanh(double x) {
     const double one = 1.0, two = 2.0, tiny = 1.0e-300;
     double t, z;
     const uint32_t jx = f64_hi(x), ix = jx & 0x7fffffffu;

@@ -607,6 +607,7 @@ class ThetaOcean(Ocean):
 
 class FortranABI:
     """The gfortran symbols of the B1 boundary (THCM.C:49-176) bound with host numpy buffers."""
+    _owner = None
 
     def __init__(self):
         L = load_library()
@@ -648,6 +649,7 @@ class FortranABI:
         a = [i(n), i(m), i(l), i(n * m * l), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.alphaT), d(s.alphaS), i(s.ih), i(s.vmix),
              i(s.tap), i(s.rho_mixing), i(s.coriolis_on), i(s.periodic)]
         self.L_.init_(*[C.byref(x) for x in a], _np_ptr(landm), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z), _np_ptr(z))
+        FortranABI._owner = id(self)   # the library holds ONE instance per process (THCM.H:76-84): the last init_ owns it
         nrows, nnz = i(), i()
         self._get_array_sizes(C.byref(nrows), C.byref(nnz))
         self.ndim = nrows.value
@@ -807,3 +809,11 @@ class FortranABI:
 
     def finalize(self):
         self.L_.finalize_()
+        FortranABI._owner = None
+
+    def __del__(self):   # the library page-locks the CRS arrays of set_pointers until finalize_: never let them go while registered
+        if FortranABI._owner == id(self):
+            try:
+                self.finalize()
+            except Exception:
+                pass
