@@ -418,6 +418,11 @@ def main():
     prof_full = t.profile_report()
     t.profile(False)
 
+    if os.environ.get("THCM_BENCH_RANK_TABLES"):   # per-rank kernel tables (load-balance diagnosis on multi-GPU boxes)
+        os.makedirs(os.environ["THCM_BENCH_RANK_TABLES"], exist_ok=True)
+        with open(os.path.join(os.environ["THCM_BENCH_RANK_TABLES"], f"kernels_g{world}_rank{rank}.json"), "w") as fh:
+            json.dump({"rank": rank, "ms_per_step": ms / a.steps, "ocean_cells": int(t.n_ocean_cells()) if hasattr(t, "n_ocean_cells") else None,
+                       "ndim": int(t.ndim), "nnz": int(t.nnz), "kernels": {k: [c_, tot / c_] for k, (c_, tot) in prof.items()}}, fh)
     if rank != 0:
         return 0
     peaks = {}
