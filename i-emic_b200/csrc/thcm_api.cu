@@ -400,6 +400,10 @@ int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un) {
 }
 const double* thcmb_jacobian_values(const thcmb_ctx* c) { return c->d_val; }
 const int* thcmb_graph_rowptr_dev(const thcmb_ctx* c) { return c->d_rowptr; }
+int thcmb_scatter_values_dev(thcmb_ctx* c, long long n, const int* d_slot, const double* d_in, double* d_out) {
+    if (n < 0 || (n > 0 && (!d_slot || !d_in || !d_out))) { set_error("thcmb_scatter_values_dev: null argument"); return -1; }
+    return scatter_slots(c, n, d_slot, d_in, d_out);
+}
 const int* thcmb_graph_col_dev(const thcmb_ctx* c) { return c->d_col; }
 
 long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, int* d_jcoA, double* d_coA) {
@@ -1038,6 +1042,7 @@ void init_(int* n, int* m, int* l, int* nmlglob, double* xmin, double* xmax, dou
     memcpy(g_ctx->spert.data(), spert, sizeof(double) * nm);
     refresh_params(g_ctx);
 }
+thcmb_ctx* thcmb_fortran_context(void) { return g_ctx; }   // the instance behind the Fortran symbols (nullptr before init_)
 void finalize_(void) {
     unpin_crs();
     if (g_ctx) { thcmb_destroy(g_ctx); g_ctx = nullptr; }

@@ -294,6 +294,7 @@ const ClassTables& class_tables(int periodic);
 int halo_slot(const Block& b, int ie, int je, int k);  // extended local coords (-1..n0, -1..m0); -1 if not a halo cell
 // device side
 void upload_class_tables(const ClassTables& t);
+int scatter_slots(thcmb_ctx* c, long long n, const int* d_slot, const double* d_in, double* d_out);
 int launch_assembly(thcmb_ctx* c, int mode, const double* d_un, double* d_out, int* d_begA, int* d_jcoA, double* d_coA);
 enum { MODE_RHS = 0, MODE_JAC_GRAPH = 1, MODE_JAC_COUNT = 2, MODE_JAC_CRS = 3 };
 int scan_block_counts(thcmb_ctx* c);

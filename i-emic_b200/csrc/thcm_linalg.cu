@@ -423,6 +423,17 @@ int fill(thcmb_ctx* c, int n, double a, double* x) {
     ProfScope prof_(c, KID_FILL);
     fill_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, a, x); c->launches++; return 0;
 }
+// out[slot[e]] = in[e]: the stored Jacobian values (graph order) into the value layout of a caller's matrix object (Epetra bridge,
+// include/thcm_epetra_bridge.hpp); slot is a permutation, so every position of `out` is written exactly once
+__global__ void scatter_slots_kernel(long long n, const int* __restrict__ slot, const double* __restrict__ in, double* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) out[slot[e]] = in[e];
+}
+int scatter_slots(thcmb_ctx* c, long long n, const int* d_slot, const double* d_in, double* d_out) {
+    ProfScope prof_(c, KID_COPY);
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)NSM * 32);
+    if (n > 0) scatter_slots_kernel<<<grid, 256, 0, c->stream>>>(n, d_slot, d_in, d_out);
+    c->launches++; return 0;
+}
 
 // ---------------------------------------------------------------------------
 // Row replacements THCM::evaluate applies on top of the Fortran assembly (THCM.C:1013-1041, 1164-1172, 2180-2296): the salinity

@@ -107,7 +107,7 @@ def load_library(path=None):
         "thcmb_recompute_scaling": (i, [vp, vp, vp, vp]), "thcmb_intcond_coeff": (d, [vp, vp]),
         "thcmb_halo_exchange": (i, [vp, vp]), "thcmb_residual_dev": (i, [vp, vp, vp]), "thcmb_rhs_dev": (i, [vp, vp, vp]),
         "thcmb_jacobian_dev": (i, [vp, vp]), "thcmb_jacobian_values": (vp, [vp]), "thcmb_graph_rowptr_dev": (vp, [vp]),
-        "thcmb_graph_col_dev": (vp, [vp]), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
+        "thcmb_graph_col_dev": (vp, [vp]), "thcmb_scatter_values_dev": (i, [vp, ll, vp, vp, vp]), "thcmb_fortran_context": (vp, []), "thcmb_jacobian_crs_dev": (ll, [vp, vp, vp, vp, vp]),
         "thcmb_tile_counts": (None, [vp, vp, vp]),
         "thcmb_ocean_block_atmosphere": (i, [vp, d, vp, vp, vp, vp, vp, vp, vp, vp]),
         "thcmb_ocean_block_seaice": (i, [vp, vp, vp, vp, vp, vp, vp, vp]), "thcmb_spmv_dev": (i, [vp, vp, vp]), "thcmb_csr_spmv_dev": (i, [vp, i, vp, vp, vp, vp, vp]),

@@ -207,6 +207,9 @@ int thcmb_ocean_block_seaice(thcmb_ctx* c, const double* un_host, const int* col
 thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global);
 void thcmb_destroy(thcmb_ctx* c);
 const char* thcmb_last_error(void);
+/* The ONE instance behind the Fortran symbols of B1 (created by init_, replaced by the next init_, gone after finalize_; NULL outside):
+ * lets code that keeps calling the Fortran symbols use the device API on the same model (include/thcm_epetra_bridge.hpp) */
+thcmb_ctx* thcmb_fortran_context(void);
 
 /* decomposition queries (TRIOS_Domain.H:114-247 subset) */
 void thcmb_local_block(const thcmb_ctx* c, int* i0, int* j0, int* n0, int* m0, int* npN, int* npM);
@@ -257,6 +260,9 @@ int thcmb_jacobian_dev(thcmb_ctx* c, const double* d_un);
 const double* thcmb_jacobian_values(const thcmb_ctx* c);   /* device pointer, graph order */
 const int* thcmb_graph_rowptr_dev(const thcmb_ctx* c);
 const int* thcmb_graph_col_dev(const thcmb_ctx* c);
+/* out[slot[e]] = in[e], e < n, on the context's stream: the stored values (graph order) into the value layout of the caller's
+ * matrix object -- what replaces the ReplaceGlobalValues loop of THCM.C:1082-1104 (include/thcm_epetra_bridge.hpp) */
+int thcmb_scatter_values_dev(thcmb_ctx* c, long long n, const int* d_slot, const double* d_in, double* d_out);
 /* Fortran-order thresholded CRS on the device (count -> scan -> fill); returns nnz, arrays 1-based like matrix_ */
 long long thcmb_jacobian_crs_dev(thcmb_ctx* c, const double* d_un, int* d_begA, int* d_jcoA, double* d_coA);
 /* y = J x on the stored Jacobian (Ocean::applyMatrix, Ocean.C:1369-1374), with halo exchange when nranks>1 */
