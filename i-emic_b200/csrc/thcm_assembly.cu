@@ -358,13 +358,43 @@ template <class ST> struct PipeTabs {
     __device__ __forceinline__ double kt(int tb) const { return st->tk[tb]; }
 };
 
-template <int R, bool CPL, class ST>
+// the ten face evaluations of the mixing Jacobian of a tile in shared memory: face f of the cell of `lane` at mx[f * TI + lane]
+struct SharedFaces {
+    const MixFace* mx; int lane;
+    __device__ __forceinline__ MixFace operator()(int f) const { return mx[f * TI + lane]; }
+};
+// T | S row group with tracer mixing: the two warps of a tile (T row, S row) need the SAME ten face evaluations per cell; warp 0
+// computes the faces {0, 2, 3, 4, 5} (base below + the temperature perturbations), warp 1 {1, 6, 7, 8, 9} (base above + the salinity
+// perturbations) -- five taper evaluations per thread instead of ten.  The caller separates this from the readers by a block barrier.
+template <class ST>
+__device__ __forceinline__ void mix_faces_to_shared(const AsmArgs& a, const ST& st, const TileGeom& g, int warp, int lane, uint32_t nb,
+                                                    MixFace* mx) {
+    if (lane >= g.ncell || ((nb >> 4) & 1u)) return;      // rows of OCEAN cells only (vmix_el_1/2)
+    const Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
+    double tt[3], ss[3], oc[3];
+    const MixTabs mt = mix_column(c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st}, tt, ss, oc);
+#pragma unroll
+    for (int q = 0; q < MIX_NFACE / 2; q++) {
+        const int f = warp == 0 ? (q == 0 ? 0 : q + 1) : (q == 0 ? 1 : q + 5);
+        if (mix_face_needed(a.t, f, oc)) mx[f * TI + lane] = mix_face_eval(a.t, f, tt, ss, oc, mt);
+    }
+}
+// SHARED_MIX: the mixing Jacobian takes its face evaluations from shared memory (mx; nullptr = mixing is off) instead of computing all
+// ten per thread
+template <int R, bool CPL, bool SHARED_MIX = false, class ST>
 __device__ __forceinline__ void pipe_eval(const AsmArgs& a, const ST& st, const TileGeom& g, int lane, uint32_t nb, double sm,
-                                          double* E) {
+                                          double* E, const MixFace* mx = nullptr) {
     if (lane < g.ncell && !((nb >> 4) & 1u)) {
         Cell c{g.gi0 + lane, g.gj, g.k, (g.cell0 + lane) % a.b.n0, g.lj};
         eval_row<R, true, CPL>(E, a.t, a.b, c, sm, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
-        if constexpr (R == TT || R == SS) vmix_jac<R>(E, a.t, c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});   // usrc.F90:489-508
+        if constexpr (R == TT || R == SS) {   // usrc.F90:489-508
+            if constexpr (!SHARED_MIX) vmix_jac<R>(E, a.t, c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st});
+            else if (mx != nullptr && (R == TT ? a.t.mix_temp : a.t.mix_salt)) {
+                double tt[3], ss[3], oc[3];
+                const MixTabs mt = mix_column(c, nb, PipeTile<ST>{&st, lane}, PipeTabs<ST>{&st}, tt, ss, oc);
+                vmix_jac_from_faces<R>(E, a.t, SharedFaces{mx, lane}, oc, mt);
+            }
+        }
     }
 }
 // open_ocean / interior are TILE-uniform (descriptor flag, tile geometry): no warp votes, inactive lanes of a ragged tile
@@ -532,8 +562,22 @@ __global__ void __launch_bounds__(32 * RowGroup<GROUP>::NWARP, BLOCKS_PER_SM) th
             default: tma_rows<0, 3, 4, CPL>(a, sh, g, lane, open_ocean, interior); break;
             }
         } else {
-            if (warp == 0) tma_rows<1, 5, 5, CPL>(a, sh, g, lane, open_ocean, interior);
-            else tma_rows<1, 6, 6, CPL>(a, sh, g, lane, open_ocean, interior);
+            // T | S: the same steps as tma_rows, with the face evaluations of the mixing Jacobian shared between the two warps.  The
+            // exchange area aliases the output staging (10 x 32 x 32 B <= 32 x 42 x 8 B): a barrier after the faces are written, one
+            // more before the first row is staged.  mixing is block-uniform (kernel argument).
+            static_assert(sizeof(MixFace) * MIX_NFACE * TI <= sizeof(double) * TI * G::VS, "the face exchange must fit the output staging");
+            const bool mixing = (a.t.mix_temp | a.t.mix_salt) != 0;
+            MixFace* const mx = mixing ? reinterpret_cast<MixFace*>(vout) : nullptr;
+            const uint32_t nb = st.desc.nbmask[lane];
+            const double sm = (double)((st.desc.surfbits >> lane) & 1u);
+            double E[RowSlots<5>::N];
+            static_assert(RowSlots<5>::N == RowSlots<6>::N, "T and S rows have the same length");
+            if (mixing) { mix_faces_to_shared(a, st, g, warp, lane, nb, mx); __syncthreads(); }
+            if (warp == 0) { pipe_eval<5, CPL, true>(a, st, g, lane, nb, sm, E, mx); pipe_finish<5>(a, g, lane, nb, open_ocean, E); }
+            else { pipe_eval<6, CPL, true>(a, st, g, lane, nb, sm, E, mx); pipe_finish<6>(a, g, lane, nb, open_ocean, E); }
+            if (mixing) __syncthreads();
+            if (warp == 0) pipe_emit<5, G::ROW0, G::VS>(a, vout, g, lane, interior, E);
+            else pipe_emit<6, G::ROW0, G::VS>(a, vout, g, lane, interior, E);
         }
     }
     if (fast) {

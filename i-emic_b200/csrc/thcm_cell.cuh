@@ -535,51 +535,75 @@ THCM_HD double vmix_rhs(const DevTables& t, const Cell& c, uint32_t nb, const Ti
     const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
     return vmix_value(t, R == TT ? 4 : 5, tt, ss, oc, mt);
 }
-// one column pair of the forward-difference block: T and S of the cell at vertical offset Q-1 (stencil position LOC).  A perturbation of
-// the cell below (Q = 0) moves only the face below, one of the cell above (Q = 2) only the face above: the other face keeps the bits of
-// the unperturbed evaluation (F0 / F1), so only the faces that change are re-evaluated -- 10 taper evaluations per row instead of 28.
-template <int R, int LOC, int Q>
-THCM_HD void vmix_fd_one(double* E, const DevTables& t, int var, double f0, const MixFace& F0, const MixFace& F1, const double* tt,
-                         const double* ss, const double* oc, const MixTabs& mt) {
+// vmix_jac (mix_imp.f:729-815): forward differences, eps = 1e-8, of vmix_fun w.r.t. the T,S unknowns of the OCEAN cells among the
+// neighbours -- here k-1, k, k+1 -- added to An(loc, R, TT|SS) for loc = 14, 5, 23 BEFORE `boundaries`.  (The reference perturbs whole
+// colour groups at once; no row meets two columns of a group, so the quotient is the same.)
+// A perturbation of the cell below moves only the face below, one of the cell above only the face above: the other face keeps the bits
+// of the unperturbed evaluation.  So the whole block of a cell -- its T row AND its S row -- is a function of TEN face evaluations:
+//   0 below(base)   2 below(T[k-1]+eps)  3 below(T[k]+eps)  6 below(S[k-1]+eps)  7 below(S[k]+eps)
+//   1 above(base)   4 above(T[k]+eps)    5 above(T[k+1]+eps) 8 above(S[k]+eps)   9 above(S[k+1]+eps)
+// (28 taper evaluations per row when every perturbed state re-evaluates both faces and both tracers).  mix_face_needed says which of
+// them exist for a cell, mix_face_eval computes one, vmix_jac_from_faces turns them into the six entries of row R: the TMA-staged
+// Jacobian kernel lets the T warp and the S warp of a tile compute five faces each and exchange them through shared memory.
+constexpr int MIX_NFACE = 10;
+THCM_HD bool mix_face_needed(const DevTables& t, int f, const double* oc) {
+    if (f < 2) return true;
+    if (f < 6 ? !t.mix_temp : !t.mix_salt) return false;
+    const int g = f < 6 ? f - 2 : f - 6;           // 0: cell below, 1 / 2: this cell (face below / above), 3: cell above
+    return g == 0 ? oc[0] != 0.0 : (g == 3 ? oc[2] != 0.0 : oc[1] != 0.0);
+}
+THCM_HD MixFace mix_face_eval(const DevTables& t, int f, const double* tt, const double* ss, const double* oc, const MixTabs& mt) {
     const double eps = 1.0e-08;
+    double tp[3] = {tt[0], tt[1], tt[2]}, sp[3] = {ss[0], ss[1], ss[2]};
+    if (f >= 2) {
+        const int g = f < 6 ? f - 2 : f - 6;
+        const int q = g == 0 ? 0 : (g == 3 ? 2 : 1);
+        if (f < 6) tp[q] = tt[q] + eps; else sp[q] = ss[q] + eps;
+    }
+    const bool below = f == 0 || f == 2 || f == 3 || f == 6 || f == 7;
+    return below ? mix_face_below(t, tp, sp, oc, mt) : mix_face_above(t, tp, sp, oc, mt);
+}
+// F(f): the face evaluation f of this cell (only the needed ones are read)
+template <int R, class Faces>
+THCM_HD void vmix_jac_from_faces(double* E, const DevTables& t, const Faces& F, const double* oc, const MixTabs& mt) {
+    static_assert(R == TT || R == SS, "mixing acts on the tracer rows");
+    constexpr int var = R == TT ? 4 : 5;
+    const double eps = 1.0e-08;
+    const MixFace F0 = F(0), F1 = F(1);
+    const double f0 = mix_combine(t, var, F0, F1, mt.dfzT);
     // the neighbour is a column only if it is an OCEAN cell of the domain (k-1 >= 1, k+1 <= L: the frame is LAND)
-    if (oc[Q] == 0.0) return;
     if (t.mix_temp) {
-        double tp[3] = {tt[0], tt[1], tt[2]};
-        tp[Q] = tt[Q] + eps;
-        const MixFace A = Q == 2 ? F0 : mix_face_below(t, tp, ss, oc, mt);
-        const MixFace B = Q == 0 ? F1 : mix_face_above(t, tp, ss, oc, mt);
-        const double d = mix_combine(t, var, A, B, mt.dfzT) - f0;
-        entref<R, LOC, TT>(E) = entref<R, LOC, TT>(E) + d / eps;
+        if (oc[0] != 0.0) entref<R, 14, TT>(E) = entref<R, 14, TT>(E) + (mix_combine(t, var, F(2), F1, mt.dfzT) - f0) / eps;
+        if (oc[1] != 0.0) entref<R, 5, TT>(E) = entref<R, 5, TT>(E) + (mix_combine(t, var, F(3), F(4), mt.dfzT) - f0) / eps;
+        if (oc[2] != 0.0) entref<R, 23, TT>(E) = entref<R, 23, TT>(E) + (mix_combine(t, var, F0, F(5), mt.dfzT) - f0) / eps;
     }
     if (t.mix_salt) {
-        double sp[3] = {ss[0], ss[1], ss[2]};
-        sp[Q] = ss[Q] + eps;
-        const MixFace A = Q == 2 ? F0 : mix_face_below(t, tt, sp, oc, mt);
-        const MixFace B = Q == 0 ? F1 : mix_face_above(t, tt, sp, oc, mt);
-        const double d = mix_combine(t, var, A, B, mt.dfzT) - f0;
-        entref<R, LOC, SS>(E) = entref<R, LOC, SS>(E) + d / eps;
+        if (oc[0] != 0.0) entref<R, 14, SS>(E) = entref<R, 14, SS>(E) + (mix_combine(t, var, F(6), F1, mt.dfzT) - f0) / eps;
+        if (oc[1] != 0.0) entref<R, 5, SS>(E) = entref<R, 5, SS>(E) + (mix_combine(t, var, F(7), F(8), mt.dfzT) - f0) / eps;
+        if (oc[2] != 0.0) entref<R, 23, SS>(E) = entref<R, 23, SS>(E) + (mix_combine(t, var, F0, F(9), mt.dfzT) - f0) / eps;
     }
 }
-// vmix_jac (mix_imp.f:729-815): forward differences, eps = 1e-8, of vmix_fun w.r.t. the T,S unknowns of the OCEAN cells
-// among the neighbours -- here k-1, k, k+1 -- added to An(loc, R, TT|SS) for loc = 14, 5, 23 BEFORE `boundaries`.
-// (The reference perturbs whole colour groups at once; no row meets two columns of a group, so the quotient is the same.)
+// the column of a cell as the mixing term sees it
+template <class Tile, class Tabs>
+THCM_HD MixTabs mix_column(const Cell& c, uint32_t nb, const Tile& tile, const Tabs& tabs, double* tt, double* ss, double* oc) {
+#pragma unroll
+    for (int q = 0; q < 3; q++) { tt[q] = tile(SV_T, 0, 0, q - 1); ss[q] = tile(SV_S, 0, 0, q - 1); }
+    oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
+    return MixTabs{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
+}
+struct LocalFaces { const MixFace* f; THCM_HD MixFace operator()(int q) const { return f[q]; } };
+// one thread does everything for its row (per-position kernels, host emulation)
 template <int R, class Tile, class Tabs>
 THCM_HD void vmix_jac(double* E, const DevTables& t, const Cell& c, uint32_t nb, const Tile& tile, const Tabs& tabs) {
     static_assert(R == TT || R == SS, "mixing acts on the tracer rows");
     if (!(R == TT ? t.mix_temp : t.mix_salt)) return;
     if ((nb >> 4) & 1u) return;                      // rows of OCEAN cells only (vmix_el_1/2)
     double tt[3], ss[3], oc[3];
+    const MixTabs mt = mix_column(c, nb, tile, tabs, tt, ss, oc);
+    MixFace F[MIX_NFACE];
 #pragma unroll
-    for (int q = 0; q < 3; q++) { tt[q] = tile(SV_T, 0, 0, q - 1); ss[q] = tile(SV_S, 0, 0, q - 1); }
-    oc[0] = ((nb >> 13) & 1u) ? 0.0 : 1.0; oc[1] = 1.0; oc[2] = ((nb >> 22) & 1u) ? 0.0 : 1.0;
-    const MixTabs mt{tabs.kt(K_DFZT), tabs.kt(K_DFZW), tabs.kt(K_DFZWM), c.k};
-    constexpr int var = R == TT ? 4 : 5;
-    const MixFace F0 = mix_face_below(t, tt, ss, oc, mt), F1 = mix_face_above(t, tt, ss, oc, mt);
-    const double f0 = mix_combine(t, var, F0, F1, mt.dfzT);
-    vmix_fd_one<R, 14, 0>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
-    vmix_fd_one<R, 5, 1>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
-    vmix_fd_one<R, 23, 2>(E, t, var, f0, F0, F1, tt, ss, oc, mt);
+    for (int f = 0; f < MIX_NFACE; f++) if (mix_face_needed(t, f, oc)) F[f] = mix_face_eval(t, f, tt, ss, oc, mt);
+    vmix_jac_from_faces<R>(E, t, LocalFaces{F}, oc, mt);
 }
 
 // ---------------------------------------------------------------------------
