@@ -160,6 +160,18 @@ __device__ __forceinline__ double ll_wait(const P2PSlot* src, unsigned int flag)
     } while (f0 != flag || f1 != flag);
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
+// the same poll without a call inside the loop (a call site keeps every live value of the caller in callee-saved registers or on the
+// stack: the compact SpMV needed 58 instead of 40 registers for its six unrolled polls): returns false after the spin limit, the caller
+// reports once, at a point where nothing is live
+__device__ __forceinline__ bool ll_poll(const P2PSlot* src, unsigned int flag, double& out) {
+    unsigned int lo, f0, hi, f1, spins = 0;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+        if (++spins > P2P_SPIN_LIMIT) return false;
+    } while (f0 != flag || f1 != flag);
+    out = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    return true;
+}
 __device__ __forceinline__ void flag_wait(volatile unsigned long long* f, unsigned long long seq) {
     unsigned int spins = 0;
     while (*f != seq) if (++spins > P2P_SPIN_LIMIT) p2p_timeout((const void*)f, (unsigned int)seq, (unsigned int)*f);
@@ -1388,8 +1400,8 @@ __global__ void __launch_bounds__(256) halo_push_ll_kernel(int ncells, const int
 // y_c = J x_c on the rows of the ocean cells.  Values and row pointers are the graph's own arrays (row = 6 ocell[ci] + r), the column
 // ids come from the compact column array stored at the same offsets: < 0 LAND column (skipped), < nlocal_c owned, else an LL halo slot
 // that is polled until the neighbour's push of THIS exchange (flag) has landed -- interior rows never wait.
-template <int LANES, int UNROLL, bool HALO>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ rp,
+template <int LANES, int UNROLL, bool HALO, int MINB = 6>
+__global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ rp,
                                                                      const int* __restrict__ colc, const double* __restrict__ val,
                                                                      const double* __restrict__ xc, int nlocal_c, const P2PSlot* halo_ll,
                                                                      unsigned int flag, double* __restrict__ yc) {
@@ -1414,9 +1426,11 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, 
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) xx[u] = (cc[u] >= 0 && (!HALO || cc[u] < nlocal_c)) ? __ldg(xc + cc[u]) : 0.0;
         if constexpr (HALO) {
+            bool arrived = true;
 #pragma unroll
             for (int u = 0; u < UNROLL; u++)
-                if (cc[u] >= nlocal_c) xx[u] = ll_wait(halo_ll + (cc[u] - nlocal_c), flag);
+                if (cc[u] >= nlocal_c) arrived = ll_poll(halo_ll + (cc[u] - nlocal_c), flag, xx[u]) && arrived;
+            if (!arrived) p2p_timeout(halo_ll, flag, 0u);
         }
         double s = 0.0;
 #pragma unroll
@@ -1594,8 +1608,13 @@ int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long 
     if (c->blk.nranks > 1) {
         const int par = (int)(seq & 1ull);
         ProfScope prof_(c, KID_SPMV);
-        spmv_compact_kernel<4, 6, true><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
-                                                                              (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
+        static const int bps = getenv("THCM_SPMV_HALO_BPS") ? atoi(getenv("THCM_SPMV_HALO_BPS")) : 6;   // A/B: 6 = 40 registers + 14 spill instructions, 5 = 48 registers
+        if (bps == 5)
+            spmv_compact_kernel<4, 6, true, 5><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                                     (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
+        else
+            spmv_compact_kernel<4, 6, true, 6><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                                     (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
     } else {
         ProfScope prof_(c, KID_SPMV);
         spmv_compact_kernel<4, 6, false><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,

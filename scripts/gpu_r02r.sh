@@ -1,0 +1,12 @@
+# r02r (2 GPUs): A/B of the halo-polling compact SpMV (5 vs 6 resident blocks per SM), multi-rank parity first
+TAG=${1:-r02r}
+THCM_TEST_WORLD=2 timeout 500 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider > gpurun_out/pytest_multi_g2_$TAG.log 2>&1; echo rc=$? >> gpurun_out/pytest_multi_g2_$TAG.log; tail -3 gpurun_out/pytest_multi_g2_$TAG.log
+for bps in 6 5; do
+THCM_SPMV_HALO_BPS=$bps timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_g2_bps$bps.json 2> gpurun_out/bench_${TAG}_g2_bps$bps.err
+python - <<PY
+import json
+for l in open('gpurun_out/bench_${TAG}_g2_bps$bps.json'):
+    if l.startswith('{'):
+        d = json.loads(l); print('bps $bps g2 step_ms', round(d['ms_per_step'], 3), 'resid', d['gmres']['resid'], {k: (v.get('launches_per_step'), round(v['avg_ms'], 4)) for k, v in d['kernels'].items()})
+PY
+done
