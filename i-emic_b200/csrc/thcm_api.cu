@@ -206,7 +206,7 @@ void thcmb_destroy(thcmb_ctx* c) {
                     (void*)c->d_scalars, (void*)c->d_counter, (void*)c->d_blockcnt, (void*)c->d_minv, (void*)c->d_tdesc, (void*)c->d_jrec,
                     (void*)c->d_krec, (void*)c->d_msi, (void*)c->d_cob, (void*)c->d_iccoeff,
                     (void*)c->d_flags, (void*)c->d_mdpartial, (void*)c->d_tilectr, (void*)c->d_cls, (void*)c->d_landcell, (void*)c->d_ocell, (void*)c->d_ccell, (void*)c->d_colc, (void*)c->d_send_cidx,
-                    (void*)c->d_iccoeff_c, (void*)c->d_active_tiles, (void*)c->d_cpos})
+                    (void*)c->d_iccoeff_c, (void*)c->d_active_tiles, (void*)c->d_cpos, (void*)c->d_halo_plain_c})
         if (p) cudaFree(p);
     for (double* p : c->krylov_pool) if (p) cudaFree(p);
     for (double* p : c->d_work) if (p) cudaFree(p);

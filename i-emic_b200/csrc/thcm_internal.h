@@ -178,6 +178,8 @@ struct thcmb_ctx {
     double* d_iccoeff_c = nullptr;   // integral-condition coefficients gathered to the ocean cells
     void* d_peer_ll = nullptr;       // device array [2][npeers]: the neighbours' LL halo buffers (compact SpMV), per parity
     void* d_halo_ll[2] = {nullptr, nullptr};   // my LL halo buffers (inside the IPC-shared allocation)
+    double* d_halo_plain_c = nullptr;            // the LL halo of one exchange landed as plain doubles (compact SpMV after the fused head kernel)
+    unsigned long long halo_landed_seq = 0;      // the exchange d_halo_plain_c holds (0 = none)
     unsigned long long halo_ll_seq = 0;
     int krylov_compact = 1;          // GMRES on the ocean cells only (THCM_KRYLOV_COMPACT=0 switches it off)
     signed char* d_cpos = nullptr;   // [64 classes][6 rows][6 cols]: position of the in-cell entry inside its sorted graph row, -1 = none

@@ -1398,13 +1398,17 @@ __global__ void __launch_bounds__(256) halo_push_ll_kernel(int ncells, const int
     }
 }
 // y_c = J x_c on the rows of the ocean cells.  Values and row pointers are the graph's own arrays (row = 6 ocell[ci] + r), the column
-// ids come from the compact column array stored at the same offsets: < 0 LAND column (skipped), < nlocal_c owned, else an LL halo slot
-// that is polled until the neighbour's push of THIS exchange (flag) has landed -- interior rows never wait.
-template <int LANES, int UNROLL, bool HALO, int MINB = 6>
-__global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ rp,
+// ids come from the compact column array stored at the same offsets: < 0 LAND column (skipped), < nlocal_c owned, else a halo slot.
+// HALO = 0: one rank.  HALO = 1: the slot is an LL slot that is polled until the neighbour's push of THIS exchange (flag) has landed
+// (interior rows never wait).  HALO = 2: the exchange was landed into a plain array by the kernel that ran before (the landing blocks
+// of scale_precon_push_kernel): owned and halo columns are ONE batch of independent gathers, the address chosen by a select.  Measured
+// on 2 GPUs (profiles/r02/bench_r02s_*): 0.103 ms with the halo columns ignored, 0.114 with plain loads issued after the owned gathers,
+// 0.125 with the polls -- the second, dependent round of loads costs as much as the polling itself.
+template <int LANES, int UNROLL, int HALO>
+__global__ void __launch_bounds__(SPMV_THREADS) spmv_compact_kernel(int nrow_c, const int* __restrict__ ocell, const int* __restrict__ rp,
                                                                      const int* __restrict__ colc, const double* __restrict__ val,
                                                                      const double* __restrict__ xc, int nlocal_c, const P2PSlot* halo_ll,
-                                                                     unsigned int flag, double* __restrict__ yc) {
+                                                                     const double* __restrict__ xh, unsigned int flag, double* __restrict__ yc) {
     const int sub = threadIdx.x & (LANES - 1);
     constexpr int rows_per_block = SPMV_THREADS / LANES;
     for (int base = blockIdx.x * rows_per_block; base < nrow_c; base += gridDim.x * rows_per_block) {
@@ -1421,16 +1425,24 @@ __global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_compact_kernel(int nr
             cc[u] = ok ? __ldg(colc + q) : -1;
             vv[u] = ok ? __ldg(val + q) : 0.0;
         }
-        // owned columns first, as independent predicated loads (all gathers of the row in flight together); the few halo columns after
-        // them -- a poll loop inside the gather would serialise it (measured: 0.150 instead of ~0.10 ms on the half-size blocks of 2 GPUs)
+        if constexpr (HALO == 2) {
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) xx[u] = (cc[u] >= 0 && (!HALO || cc[u] < nlocal_c)) ? __ldg(xc + cc[u]) : 0.0;
-        if constexpr (HALO) {
-            bool arrived = true;
+            for (int u = 0; u < UNROLL; u++) {
+                const double* p = cc[u] < nlocal_c ? xc + cc[u] : xh + (cc[u] - nlocal_c);
+                xx[u] = cc[u] >= 0 ? __ldg(p) : 0.0;
+            }
+        } else {
+            // owned columns first, as independent predicated loads (all gathers of the row in flight together); the few halo columns
+            // after them -- a poll loop inside the gather would serialise it
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++)
-                if (cc[u] >= nlocal_c) arrived = ll_poll(halo_ll + (cc[u] - nlocal_c), flag, xx[u]) && arrived;
-            if (!arrived) p2p_timeout(halo_ll, flag, 0u);
+            for (int u = 0; u < UNROLL; u++) xx[u] = (cc[u] >= 0 && (HALO == 0 || cc[u] < nlocal_c)) ? __ldg(xc + cc[u]) : 0.0;
+            if constexpr (HALO == 1) {
+                bool arrived = true;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++)
+                    if (cc[u] >= nlocal_c) arrived = ll_poll(halo_ll + (cc[u] - nlocal_c), flag, xx[u]) && arrived;
+                if (!arrived) p2p_timeout(halo_ll, flag, 0u);
+            }
         }
         double s = 0.0;
 #pragma unroll
@@ -1438,7 +1450,10 @@ __global__ void __launch_bounds__(SPMV_THREADS, MINB) spmv_compact_kernel(int nr
         for (int q = b + sub + UNROLL * LANES; q < e; q += LANES) {   // rows longer than UNROLL*LANES (not in the THCM graph)
             const int cidx = __ldg(colc + q);
             if (cidx < 0) continue;
-            const double xv = (!HALO || cidx < nlocal_c) ? __ldg(xc + cidx) : ll_wait(halo_ll + (cidx - nlocal_c), flag);
+            double xv;
+            if (HALO == 0 || cidx < nlocal_c) xv = __ldg(xc + cidx);
+            else if (HALO == 2) xv = __ldg(xh + (cidx - nlocal_c));
+            else xv = ll_wait(halo_ll + (cidx - nlocal_c), flag);
             s += __ldg(val + q) * xv;
         }
 #pragma unroll
@@ -1475,9 +1490,24 @@ __global__ void __launch_bounds__(SPP_THREADS) scale_precon_push_kernel(int nc, 
                                                                         const int* __restrict__ flag2,
                                                                         int push_blocks, int nsend, const int* __restrict__ cidx,
                                                                         const int* __restrict__ dst_slot, const int* __restrict__ peer,
-                                                                        P2PSlot* const* peer_ll, unsigned int llflag) {
+                                                                        P2PSlot* const* peer_ll, unsigned int llflag,
+                                                                        int land_blocks, int nrecv, const int* __restrict__ recv_slot,
+                                                                        const P2PSlot* my_ll, double* __restrict__ xh) {
     __shared__ double sv[SPP_THREADS];
     __shared__ double hs[MD_MAXV];
+    if ((int)blockIdx.x >= (int)gridDim.x - land_blocks) {
+        // LANDING blocks (the LAST blocks of the grid): the halo the neighbours' pushing blocks -- the FIRST blocks of their head kernel,
+        // which depend on nothing of this rank -- store into my LL buffer is polled here and written to the plain array the SpMV of this
+        // step gathers from.  By the time these blocks are scheduled the data have usually been there for tens of microseconds.
+        const int lb = blockIdx.x - ((int)gridDim.x - land_blocks);
+        for (int q = lb * SPP_CELLS + (int)threadIdx.x / NUN; q < nrecv; q += land_blocks * SPP_CELLS) {
+            const size_t e = (size_t)NUN * __ldg(recv_slot + q) + threadIdx.x % NUN;
+            double val;
+            if (!ll_poll(my_ll + e, llflag, val)) p2p_timeout(my_ll + e, llflag, 0u);
+            xh[e] = val;
+        }
+        return;
+    }
     const double nrm = sqrt(*nrm2);
     const double a = 1.0 / nrm;
     const bool upd = flag != nullptr && *flag != 0 && *flag2 == 0;
@@ -1498,7 +1528,7 @@ __global__ void __launch_bounds__(SPP_THREADS) scale_precon_push_kernel(int nc, 
         return wi;
     };
     if ((int)blockIdx.x >= push_blocks) {
-        const int mb = blockIdx.x - push_blocks, main_blocks = gridDim.x - push_blocks;
+        const int mb = blockIdx.x - push_blocks, main_blocks = gridDim.x - push_blocks - land_blocks;
         if (mb == 0 && threadIdx.x == 0 && nrm_out) *nrm_out = nrm;
         for (int c0 = mb * SPP_CELLS; c0 < nc; c0 += main_blocks * SPP_CELLS) {
             const int t = c0 * NUN + threadIdx.x;
@@ -1549,12 +1579,17 @@ unsigned long long scale_precon_push(thcmb_ctx* c, const double* w, const double
     const bool push = c->blk.nranks > 1 && c->nsend_cells > 0;
     const int push_blocks = push ? std::max(1, std::min((c->nsend_cells + SPP_CELLS - 1) / SPP_CELLS, NSM)) : 0;
     const int par = (int)(seq & 1ull);
+    // the halo of THIS exchange is landed by the last blocks of the same kernel (the SpMV that follows then needs no polling)
+    const bool land = c->blk.nranks > 1 && c->nrecv_cells > 0 && c->d_recv_slot && !getenv("THCM_NO_HALO_LANDING");
+    const int land_blocks = land ? std::max(1, std::min((c->nrecv_cells + SPP_CELLS - 1) / SPP_CELLS, NSM)) : 0;
+    if (land && !c->d_halo_plain_c) THCM_CUDA(cudaMalloc(&c->d_halo_plain_c, sizeof(double) * (size_t)NUN * std::max(c->blk.nhalo_cells(), 1)));
     ProfScope prof_(c, KID_PRECON_APPLY);
-    scale_precon_push_kernel<<<main_blocks + push_blocks, SPP_THREADS, 0, c->stream>>>(
+    scale_precon_push_kernel<<<main_blocks + push_blocks + land_blocks, SPP_THREADS, 0, c->stream>>>(
         nc, c->d_ocell, c->d_minv, d_nrm2, w, v, z, d_nrm_out, vl, d_h2, d_flag, d_flag2, push_blocks, push ? c->nsend_cells : 0,
         c->d_send_cidx, c->d_send_dst, c->d_send_peer, push ? (P2PSlot* const*)c->d_peer_ll + (size_t)par * c->peers.size() : nullptr,
-        (unsigned int)seq);
+        (unsigned int)seq, land_blocks, land ? c->nrecv_cells : 0, c->d_recv_slot, (const P2PSlot*)c->d_halo_ll[par], c->d_halo_plain_c);
     c->launches++;
+    c->halo_landed_seq = land ? seq : 0ull;
     return seq;
 }
 
@@ -1608,17 +1643,16 @@ int spmv_compact_rows(thcmb_ctx* c, const double* xc, double* yc, unsigned long 
     if (c->blk.nranks > 1) {
         const int par = (int)(seq & 1ull);
         ProfScope prof_(c, KID_SPMV);
-        static const int bps = getenv("THCM_SPMV_HALO_BPS") ? atoi(getenv("THCM_SPMV_HALO_BPS")) : 6;   // A/B: 6 = 40 registers + 14 spill instructions, 5 = 48 registers
-        if (bps == 5)
-            spmv_compact_kernel<4, 6, true, 5><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
-                                                                                     (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
+        if (seq != 0ull && c->halo_landed_seq == seq)   // the head kernel of this step landed the exchange
+            spmv_compact_kernel<4, 6, 2><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                               nullptr, c->d_halo_plain_c, 0u, yc);
         else
-            spmv_compact_kernel<4, 6, true, 6><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
-                                                                                     (const P2PSlot*)c->d_halo_ll[par], (unsigned int)seq, yc);
+            spmv_compact_kernel<4, 6, 1><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                               (const P2PSlot*)c->d_halo_ll[par], nullptr, (unsigned int)seq, yc);
     } else {
         ProfScope prof_(c, KID_SPMV);
-        spmv_compact_kernel<4, 6, false><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
-                                                                               nullptr, 0u, yc);
+        spmv_compact_kernel<4, 6, 0><<<grid, SPMV_THREADS, 0, c->stream>>>(nrow_c, c->d_ocell, c->d_rowptr, c->d_colc, c->d_val, xc, nrow_c,
+                                                                           nullptr, nullptr, 0u, yc);
     }
     c->launches++;
     if (c->ic_on) {   // the dense integral-condition row (THCM.C:2180-2229) on the compact vectors
