@@ -609,7 +609,7 @@ int thcmb_gmres(thcmb_ctx* c, const double* d_b, double* d_x, double tol, int ma
                         fused_axpy_dot_dev(c, n, nv, vp.data(), dh, w, dh + 2 * S, dh + nv, c->d_flags, dh + 3 * S, pyth ? c->d_flags + 1 : nullptr);
                         // explicit second update + norm: always without the Pythagorean shortcut, else only when its guard tripped
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh + 2 * S, pyth ? c->d_flags + 1 : c->d_flags, w, dh + 3 * S, nullptr, nullptr, nullptr,
-                                           KID_SECOND_UPDATE);
+                                           KID_SECOND_UPDATE, pyth);
                     } else if (c->p2p_on || c->blk.nranks == 1) {
                         // fused update + norm (+ all-reduce + DGKS decision): two reductions per iteration when no second pass
                         multi_axpy_dot_dev(c, n, nv, vp.data(), dh, nullptr, w, dh + S, dh + nv, c->d_flags, dh + 3 * S);

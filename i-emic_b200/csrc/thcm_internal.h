@@ -311,7 +311,7 @@ int allreduce_dev(thcmb_ctx* c, double* d_buf, int count);
 int multi_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* w, const int* d_skip, double* d_out);
 int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w);
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid = -1);
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid = -1, bool rare_path = false);
 int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h1, double* w, double* d_out,
                        const double* d_ww_old, int* d_flag_out, double* d_final_out, int* d_flag2_out = nullptr);
 int dgks_flag_dev(thcmb_ctx* c, const double* ww_old, const double* ww_new, int* d_flag);

@@ -986,17 +986,19 @@ int multi_axpy_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const doubl
     c->launches++;
     return 0;
 }
+// rare_path: the launch almost always finds its skip flag cleared and leaves (the explicit second update behind the Pythagorean norm):
+// one block per SM keeps what such a launch costs small (6.6 -> ~4 us); when it does run it is slower than the full grid
 int multi_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const double* d_h, const int* d_skip, double* w, double* d_ww,
-                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid) {
+                       const double* d_ww_old, int* d_flag_out, double* d_final_out, int kid, bool rare_path) {
     if (nv > MD_MAXV) {   // all but the last chunk only update; the last one also takes the norm of the fully updated vector
         const int last0 = (nv - 1) / MD_MAXV * MD_MAXV;
         multi_axpy_dev(c, n, last0, vecs, d_h, d_skip, w);
-        return multi_axpy_dot_dev(c, n, nv - last0, vecs + last0, d_h + last0, d_skip, w, d_ww, d_ww_old, d_flag_out, d_final_out, kid);
+        return multi_axpy_dot_dev(c, n, nv - last0, vecs + last0, d_h + last0, d_skip, w, d_ww, d_ww_old, d_flag_out, d_final_out, kid, rare_path);
     }
     VecList vl; vl.nv = nv;
     for (int q = 0; q < nv; q++) vl.v[q] = vecs[q];
     { ProfScope prof_(c, kid >= 0 ? kid : KID_MULTIAXPY);
-      const int grid = std::min(ew_grid(n), RED_BLOCKS);
+      const int grid = rare_path ? std::min(ew_grid(n), NSM) : std::min(ew_grid(n), RED_BLOCKS);
       multi_axpy_dot_kernel<<<grid, RED_THREADS, 0, c->stream>>>(n, vl, d_h, d_skip, w, c->d_partial, c->d_counter, d_ww, p2p_args(c),
                                                                  RedEpilogue{d_ww_old, d_flag_out, d_final_out, nullptr}); }
     c->launches++;
