@@ -22,4 +22,4 @@ PY
 }
 for g in $LIST; do ENVX="" run $g g$g; done
 if [ -n "$WEAK" ]; then ENVX="" run $N g${N}_weak --weak; fi
-if [ "$N" != "1" ]; then ENVX="THCM_BALANCE=0" run $N g${N}_uniform_cuts; fi
+if [ "$N" != "1" ] && [ -n "$5" ]; then ENVX="THCM_BALANCE=0" run $N g${N}_uniform_cuts; fi
