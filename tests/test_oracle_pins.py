@@ -366,3 +366,46 @@ def test_specified_tanh_of_the_mixing_taper():
     scale = np.abs(B1).reshape(-1, 6).max(axis=0) + 1e-300
     assert (np.abs(B1 - B0).reshape(-1, 6) / scale).max() <= 1e-12
     assert np.abs(v1 - v0).max() <= 1e-6 * np.abs(v1).max()
+
+
+def test_transient_run_reproduces_the_reference_golden_norm():
+    """GOLDEN PIN against a number the reference itself produced: src/tests/trns_ocean.C runs ten adaptive implicit theta steps of the
+    ocean model from rest (8 x 8 x 4 North Atlantic box, Mixing = 1, salinity integral condition, test/ocean/test_oceantransient.xml) and
+    asserts || state || = 37.03750142 +- 1e-4 and 30 Newton steps in total.  The same time stepper (tests/transient_twin.py) over the
+    ORACLE's residual and Jacobian reproduces both -- the norm to 1e-8: every term of F (lin, nlin_rhs, boundaries, forcing, vmix_fun,
+    the integral condition, the mass matrix) is pinned at the 1e-9 level, and J well enough to repeat the reference's Newton history."""
+    import transient_twin as tt
+    s, landm = cases.natl8(**tt.SETTINGS)
+    o = OracleTHCM(s, landm)
+    for k, v in tt.PARAMETERS.items():
+        o.setpar(P[k], v)
+    n, m, l, nd = s.N, s.M, s.L, o.ndim
+    rowptr, col = o.graph()
+    cv, ci = o.intcond_scaling()
+    coeff = np.zeros(nd)
+    coeff[ci - 1] = cv
+    rowic = 6 * (((l - 1) * m + (m - 1)) * n + (n - 1)) + 5                  # THCM.C:695
+    sign, correction = -1.0, 0.0                                            # "Salinity Integral Sign"; Ocean.C:145-148 at the zero state
+
+    class Model:
+        mass = o.matrix(np.zeros(nd))[3].copy()
+
+        @staticmethod
+        def F(x):                                                           # THCM.C:1001-1026
+            f = -o.rhs(x)
+            f[rowic] = sign * (coeff @ x - correction)
+            return f
+
+        @staticmethod
+        def J(x):                                                           # THCM.C:1046-1180, 2180-2229
+            import scipy.sparse as sp
+            val = o.jacobian_graph(x)[0].copy()
+            val[rowptr[rowic]:rowptr[rowic + 1]] = 0.0
+            A = sp.csr_matrix((val, col, rowptr), shape=(nd, nd)).tolil()
+            A[rowic, :] = sign * coeff
+            return A.tocsr()
+    Model.mass[rowic] = 0.0
+    log = []
+    x, total, steps = tt.run(Model, log=log)
+    assert steps == 10 and total == tt.GOLDEN_NEWTON_STEPS, log
+    assert abs(np.linalg.norm(x) - tt.GOLDEN_NORM) < 1e-7, np.linalg.norm(x)    # the reference prints 8 decimals and allows 1e-4
