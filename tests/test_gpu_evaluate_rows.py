@@ -347,3 +347,76 @@ def test_ocean_coupling_blocks_through_the_model_mirror():
         got = mat[:, col].toarray().ravel()
         assert np.abs(got).max() > 0 and np.abs(got - want).max() <= 1e-9 * max(np.abs(mat).max(), 1.0), field
     t.close()
+
+
+def test_transient_run_on_the_device_reproduces_the_reference_golden_norm():
+    """The reference's own regression number for the ocean time stepper (src/tests/trns_ocean.C:63-64: || state || = 37.03750142 +- 1e-4,
+    30 Newton steps after ten adaptive theta steps from rest; Mixing = 1, salinity integral condition) through the DEVICE path: the
+    theta residual (theta_rhs_kernel over the CUDA residual), the theta Jacobian (theta_jac_kernel over the CUDA Jacobian values) and the
+    integral-condition row of the ThetaOcean mirror, driven by the restated AdaptiveTransient / Newton loop (tests/transient_twin.py).
+    Only the direct linear solve runs on the host (the solver is not what is pinned here)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import scipy.sparse as sp
+    import iemic_b200
+    import transient_twin as tt
+    s, landm = cases.natl8(**tt.SETTINGS)
+    p = tt.TIMESTEPPER
+    model = iemic_b200.ThetaOcean(s, landm, theta=p["theta"])
+    t = model.thcm
+    for k, v in tt.PARAMETERS.items():
+        t.setParameter(k, v)
+    rowic = t.enableIntegralCondition(-1, -1, -1)
+    assert t.setIntCondCorrection(t.new_vector()) == 0.0                 # Ocean.C:145-148 at the zero state
+    coeff, _ = t.getIntCondCoeff()
+    rowptr, col = t.graph()
+    nd = t.ndim
+    solve = tt.NullSpaceSolver()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()   # noqa: E731
+
+    def theta_rhs(y):
+        model.setState(dev(y))
+        model.computeRHS()
+        return model.getRHS("V").cpu().numpy()
+
+    x = np.zeros(nd)
+    dt, time_, steps, total = p["dt"], 0.0, 0, 0
+    tmax = p["tmax_years"] / (737.2685 / 365.0)
+    while time_ < tmax and steps < p["nsteps"]:
+        model.setState(dev(x))
+        model.initStep(dt)
+        y = x.copy()
+        Fx = theta_rhs(y)
+        converged = False
+        for k in range(p["max_newton"]):
+            model.setState(dev(y))
+            model.computeJacobian()                                       # J - M / (theta dt) on the device
+            val = t.jacobian_values_host()
+            val[rowptr[rowic]:rowptr[rowic + 1]] = 0.0
+            A = sp.csr_matrix((val, col, rowptr), shape=(nd, nd)).tolil()
+            A[rowic, :] = -1.0 * coeff                                    # the dense row the device applies inside its SpMV (THCM.C:2180-2229)
+            dx = solve(A.tocsr(), Fx / (p["theta"] * dt))
+            normdx = np.abs(dx).max()
+            y = y - dx
+            Fx = theta_rhs(y)
+            if normdx < p["newton_tol"] and np.linalg.norm(Fx) < p["newton_tol"]:
+                converged = True
+                break
+            if normdx > 1e2:
+                break
+        if not converged:
+            assert dt > p["dt_min"]
+            dt = max(dt / p["decrease"], p["dt_min"])
+            continue
+        steps += 1
+        time_ += dt
+        x = y
+        if k < p["min_wanted"]:
+            dt = min(dt * p["increase"], p["dt_max"])
+        elif k > p["max_wanted"]:
+            dt = max(dt / p["decrease"], p["dt_min"])
+        total += k
+    assert steps == 10 and total == tt.GOLDEN_NEWTON_STEPS
+    assert abs(np.linalg.norm(x) - tt.GOLDEN_NORM) < 1e-7, np.linalg.norm(x)
+    t.close()
