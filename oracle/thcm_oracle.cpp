@@ -12,7 +12,17 @@
 // arm may load this library.  The product (i-emic_b200/csrc) never links it.
 //
 // PARITY PIN STATUS: the reference cannot be built here (no gfortran / MPI /
-// Trilinos) and ships no golden Jacobian / residual vectors, but it ships ONE
+// Trilinos) and ships no golden Jacobian / residual vectors.  It does hold a
+// GOLDEN NUMBER of its own making for this path: src/tests/trns_ocean.C:63-64
+// asserts || state || = 37.03750142 (+- 1e-4) and 30 Newton steps after ten
+// adaptive implicit theta steps from rest (8 x 8 x 4 box, Mixing = 1, salinity
+// integral condition).  The reference's time stepper restated over THIS
+// oracle's residual and Jacobian (tests/transient_twin.py) gives 37.0375014173
+// and 30 (tests/test_oracle_pins.py, 1e-7): every term of F is pinned at the
+// 1e-9 level by a number the reference produced, and J well enough to repeat
+// its Newton history step for step.  The same run through the CUDA path gives
+// the same number (tests/test_gpu_evaluate_rows.py).
+// It also ships ONE
 // reference-produced vector: the converged state of its regression test
 // (test/ocean/ocean_reference.h5, src/tests/reft_ocean.C:59-89; committed as
 // tests/golden/ocean_reference_state.f64).  That state is a root of the
