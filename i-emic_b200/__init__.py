@@ -8,3 +8,4 @@ from .params import PAR_INDEX, PAR_NAMES, par_index            # noqa: F401
 from .masks import read_mask, write_mask, synthetic_global_mask, all_ocean_mask  # noqa: F401
 from .thcm import (Settings, THCM, Ocean, lib, lib_path, load_library, KrylovResult,  # noqa: F401
                    FortranABI, ThetaOcean, last_error)
+from . import paramlist                                         # noqa: F401

@@ -896,36 +896,95 @@ static bool read_mask_file(const char* path, int n, int m, int l, std::vector<in
     return true;
 }
 
+// m_global keeps what topofit (topo.F90:6-38) needs later: initialize only stores it and clears landm (global.F90:100-160); every
+// get_landm runs topofit -- readmask when "Read Land Mask" is set, else depth3land with the "Topography" case
+static int g_itopo = 1, g_flat = 0, g_rd_mask = 0, g_rd_spertm = 0;
+static std::string g_maskfile, g_spertmaskfile;
+static std::string locate_mkmask(const std::string& file) {   // global.F90 locate_file: the name as given, then mkmask/<name> below the data dir
+    if (std::ifstream(file)) return file;
+    const char* dd = getenv("THCM_DATA_DIR");
+    return std::string(dd ? dd : ".") + "/mkmask/" + file;
+}
+static inline int& LMglob(int i, int j, int k) {
+    return g_landm_global[(size_t)i + (size_t)(g_set.N + 2) * (j + (size_t)(g_set.M + 2) * k)];
+}
+static void fix_land_inversion_and_flatten() {   // topo.F90:94-109 / 287-291
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    for (int i = 1; i <= n; i++) for (int j = 1; j <= m; j++) for (int k = l; k >= 2; k--)
+        if (LMglob(i, j, k) == LAND && LMglob(i, j, k - 1) == OCEAN) LMglob(i, j, k - 1) = LAND;
+    if (g_flat) for (int k = 1; k <= l - 1; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++) LMglob(i, j, k) = LMglob(i, j, l);
+}
+// readmask (topo.F90:41-127)
+static void readmask() {
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    const std::string p = locate_mkmask(g_maskfile);
+    if (!read_mask_file(p.c_str(), n, m, l, g_landm_global)) fatal("failed to read land mask " + g_maskfile + " (tried " + p + ")");
+    fix_land_inversion_and_flatten();
+}
+// depth3land (topo.F90:129-330) without bathymetry data (depth = 0: every cell starts as LAND): the idealised continents of
+// "Topography" 1..4; case 0 fits ETOPO data that does not ship with the reference and stops there too ("cannot find ocean point")
+static void depth3land() {
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    g_landm_global.assign((size_t)(n + 2) * (m + 2) * (l + 2), LAND);
+    auto ocean_interior = [&]() { for (int k = 1; k <= l; k++) for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) LMglob(i, j, k) = OCEAN; };
+    auto land_box = [&](int i0, int i1, int j0, int j1) {   // landm(i0:i1, j0:j1, 1:l) = LAND with Fortran bounds checking left to the caller
+        if (i0 < 1 || i1 > n || j0 < 1 || j1 > m) fatal("depth3land: this Topography case needs a larger grid (topo.F90:252-270)");
+        for (int k = 1; k <= l; k++) for (int j = j0; j <= j1; j++) for (int i = i0; i <= i1; i++) LMglob(i, j, k) = LAND;
+    };
+    switch (g_itopo) {
+    case 1: ocean_interior(); break;                                   // no continents
+    case 2: {                                                          // Miocene: four rectangular continents in longitude / latitude
+        ocean_interior();
+        constexpr double PI = 3.14159265358979323846;                  // par.F90:14
+        const double dx = (g_set.xmax - g_set.xmin) / n, dy = (g_set.ymax - g_set.ymin) / m;
+        const double ph1 = 250 * PI / 180., ph2 = 315 * PI / 180., ph3 = 10 * PI / 180., ph4 = 65. * PI / 180.;
+        const double thd = -60 * PI / 180., thsa = -35 * PI / 180., thn = 10. * PI / 180., tha = 30 * PI / 180.;
+        for (int i = 1; i <= n; i++) {
+            const double x = (i - 0.5) * dx + g_set.xmin;              // grid.F90:28
+            const bool am = x < ph2 && x > ph1, af = x < ph4 && x > ph3;
+            for (int j = 1; j <= m; j++) {
+                const double y = (j - 0.5) * dy + g_set.ymin;          // grid.F90:34
+                const bool land = (am && y < 0. && y > thd) || (af && y < thn && y > thsa) || (am && y < g_set.ymax && y > tha) ||
+                                  (af && y < g_set.ymax && y > tha);
+                if (land) for (int k = 1; k <= l; k++) LMglob(i, j, k) = LAND;
+            }
+        }
+        break;
+    }
+    case 3: ocean_interior(); land_box(18, 20, 1, 16); break;          // single-hemisphere basin
+    case 4: ocean_interior(); land_box(22, 24, 6, m); break;           // double-hemisphere basin
+    default:
+        fatal("m_global::get_landm: \"Topography\" = 0 fits bathymetry data that does not ship with the reference (its depth3land stops "
+              "with 'cannot find ocean point'); use \"Read Land Mask\" or Topography 1..4");
+    }
+    if (g_flat) for (int k = 1; k <= l - 1; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++) LMglob(i, j, k) = LMglob(i, j, l);
+    if (g_set.periodic)
+        for (int k = 0; k <= l + 1; k++) for (int j = 0; j <= m + 1; j++)
+            if (LMglob(1, j, k) == OCEAN && LMglob(n, j, k) == OCEAN) { LMglob(n + 1, j, k) = PERIO; LMglob(0, j, k) = PERIO; }
+}
+
 void __m_global_MOD_initialize(int* N, int* M, int* L, double* xmin, double* xmax, double* ymin, double* ymax, double* hdim,
                                double* qz, int* periodic, int* itopo, int* flat, int* rd_mask, int* TRES, int* SRES, int* iza,
                                int* ite, int* its, int* rd_spertm, int* coupled_T, int* coupled_S, int* forcing_type,
-                               const char* maskfile, const char*, const char*, const char*, const char*) {
+                               const char* maskfile, const char* spertmaskfile, const char*, const char*, const char*) {
     thcmb_default_settings(&g_set);
     g_set.N = *N; g_set.M = *M; g_set.L = *L;
     g_set.xmin = *xmin; g_set.xmax = *xmax; g_set.ymin = *ymin; g_set.ymax = *ymax; g_set.hdim = *hdim; g_set.qz = *qz;
     g_set.periodic = *periodic; g_set.TRES = *TRES; g_set.SRES = *SRES; g_set.iza = *iza; g_set.ite = *ite; g_set.its = *its;
     g_set.coupled_T = *coupled_T; g_set.coupled_S = *coupled_S; g_set.forcing_type = *forcing_type;
-    (void)itopo; (void)rd_spertm;
-    int n = *N, m = *M, l = *L;
-    g_landm_global.assign((size_t)(n + 2) * (m + 2) * (l + 2), OCEAN);
-    if (*rd_mask && maskfile && maskfile[0]) {
-        // the reference resolves mkmask/<file> below its DATA_DIR (global.F90 locate_file); here the caller passes
-        // a path, or sets THCM_DATA_DIR
-        std::string p = maskfile;
-        if (!read_mask_file(p.c_str(), n, m, l, g_landm_global)) {
-            const char* dd = getenv("THCM_DATA_DIR");
-            std::string p2 = std::string(dd ? dd : ".") + "/mkmask/" + maskfile;
-            if (!read_mask_file(p2.c_str(), n, m, l, g_landm_global)) fatal("cannot read land mask " + p + " / " + p2);
-        }
-        // land inversion fix of readmask (topo.F90:94-103)
-        auto LMg = [&](int i, int j, int k) -> int& { return g_landm_global[(size_t)i + (size_t)(n + 2) * (j + (size_t)(m + 2) * k)]; };
-        for (int i = 1; i <= n; i++) for (int j = 1; j <= m; j++) for (int k = l; k >= 2; k--)
-            if (LMg(i, j, k) == LAND && LMg(i, j, k - 1) == OCEAN) LMg(i, j, k - 1) = LAND;
-        if (*flat) for (int k = 1; k <= l - 1; k++) for (int j = 0; j <= m + 1; j++) for (int i = 0; i <= n + 1; i++) LMg(i, j, k) = LMg(i, j, l);
-    }
+    g_itopo = *itopo; g_flat = *flat; g_rd_mask = *rd_mask; g_rd_spertm = *rd_spertm;
+    g_maskfile = maskfile ? maskfile : ""; g_spertmaskfile = spertmaskfile ? spertmaskfile : "";
+    g_landm_global.assign((size_t)(*N + 2) * (*M + 2) * (*L + 2), OCEAN);   // landm = 0 (global.F90:158)
     g_have_global = true;
+    // (the mask of "Read Land Mask" is read right away as well, so that get_current_landm serves it before the first get_landm)
+    if (g_rd_mask && !g_maskfile.empty()) readmask();
 }
-void __m_global_MOD_get_landm(int* landm) { memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size()); }
+void __m_global_MOD_get_landm(int* landm) {   // global.F90:299-318: topofit, then the copy
+    if (!g_have_global) fatal("m_global::get_landm before m_global::initialize");
+    if (g_rd_mask) { if (!g_maskfile.empty()) readmask(); else fatal("failed to read land mask: \"Read Land Mask\" without a \"Land Mask\" file"); }
+    else depth3land();
+    memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size());
+}
 void __m_global_MOD_finalize(void) { g_landm_global.clear(); g_have_global = false; }
 /* m_global (global.F90:215-608): the global-domain arrays THCM.C reads on the root before it scatters them */
 void __m_global_MOD_get_current_landm(int* landm) { memcpy(landm, g_landm_global.data(), sizeof(int) * g_landm_global.size()); }
@@ -940,13 +999,10 @@ void __m_global_MOD_set_landm(int* landm) {   // global.F90:349-381, incl. the l
 void __m_global_MOD_set_maskfile(const char* maskfile) {   // global.F90:215-224 + the topofit of the next get_landm
     if (!g_have_global) fatal("m_global::set_maskfile before m_global::initialize");
     const int n = g_set.N, m = g_set.M, l = g_set.L;
-    std::string p = maskfile ? maskfile : "";
+    g_maskfile = maskfile ? maskfile : "";
     std::vector<int> lm;
-    if (!read_mask_file(p.c_str(), n, m, l, lm)) {
-        const char* dd = getenv("THCM_DATA_DIR");
-        std::string p2 = std::string(dd ? dd : ".") + "/mkmask/" + p;
-        if (!read_mask_file(p2.c_str(), n, m, l, lm)) fatal("cannot read land mask " + p + " / " + p2);
-    }
+    const std::string p = locate_mkmask(g_maskfile);
+    if (!read_mask_file(p.c_str(), n, m, l, lm)) fatal("cannot read land mask " + g_maskfile + " (tried " + p + ")");
     __m_global_MOD_set_landm(lm.data());
 }
 static void need_no_datafile(bool needs_file, const char* what) {
@@ -970,8 +1026,23 @@ void __m_global_MOD_get_internal_temforcing(double*) { need_no_datafile(true, "m
 void __m_global_MOD_get_internal_salforcing(double*) { need_no_datafile(true, "m_global::get_internal_salforcing"); }
 /* declared by THCM.C:170 but defined nowhere in the reference's Fortran (and never called): present so that nothing is unresolved */
 void __m_global_MOD_get_land_temp(double*) { fatal("m_global::get_land_temp is declared by THCM.C but not implemented by the reference"); }
-void __m_global_MOD_get_spert(double* spert) {                    // global.F90:587-608 (rd_spertm = 0)
-    for (size_t q = 0; q < (size_t)g_set.N * g_set.M; q++) spert[q] = (double)g_set.SRES;
+void __m_global_MOD_get_spert(double* spert) {                    // global.F90:587-608
+    const int n = g_set.N, m = g_set.M, l = g_set.L;
+    for (size_t q = 0; q < (size_t)n * m; q++) spert[q] = (double)g_set.SRES;
+    if (!g_rd_spertm) return;
+    // read_spertm (forcing.F90:372-402): rows j = m+1 .. 0 of n+2 digits; spert = (1 - digit) * (1 - landm(i,j,l))
+    std::ifstream f(locate_mkmask(g_spertmaskfile));
+    std::vector<std::string> rows((size_t)m + 2);
+    bool ok = (bool)f;
+    for (int j = m + 1; ok && j >= 0; j--) ok = (bool)std::getline(f, rows[(size_t)j]);
+    if (!ok) {   // the reference prints this warning and goes on with whatever the array held; here: the value without a mask
+        fprintf(stderr, "WARNING: failed to read salinity perturbation mask from file mkmask/%s\n", g_spertmaskfile.c_str());
+        return;
+    }
+    for (int j = 1; j <= m; j++) for (int i = 1; i <= n; i++) {
+        const int dum = i < (int)rows[(size_t)j].size() ? rows[(size_t)j][(size_t)i] - '0' : 0;
+        spert[(size_t)(i - 1) + (size_t)n * (j - 1)] = (double)(1 - dum) * (1 - LMglob(i, j, l));
+    }
 }
 /* global grid arrays pushed by THCM.C right after m_global::initialize (THCM.C:340-354; global.F90:241-293).  The library builds the
  * same arrays itself (grid.F90 formulas, build_grid); the caller's copies are kept and compared with them when init_ creates a model

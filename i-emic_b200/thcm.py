@@ -38,7 +38,7 @@ class Settings(C.Structure):
                 ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int),
                 ("ymin_glob", C.c_double), ("ymax_glob", C.c_double), ("balance", C.c_int)]
 
-    PI = 3.14159265358979323846  # THCMdefs.H:19
+    PI = 3.14159265358979323846  # src/trios/THCMdefs.H:17
 
     @classmethod
     def from_degrees(cls, n, m, l, xmin, xmax, ymin, ymax, periodic=False, hdim=4000.0, qz=1.0, **kw):
@@ -171,6 +171,30 @@ class THCM:
         self.stream = torch.cuda.ExternalStream(self.L_.thcmb_stream(self.ctx), device=self.device)
         if settings.nranks > 1:
             self._init_nccl(comm)
+
+    @classmethod
+    def from_parameter_list(cls, params, comm=None, rank=0, nranks=1, device=0, balance=0, data_dir=None):
+        """THCM::THCM(Teuchos::ParameterList&, comm) (THCM.C:180-795): `params` is the THCM list of the reference's ocean_params.xml (a
+        paramlist.ParameterList, or the path of an XML file whose root or "THCM" sublist it is).  Land mask from "Land Mask" / "Topography",
+        integral condition when "Restoring Salinity Profile" is 0, "Fix Pressure Points", then the "Starting Parameters"."""
+        from . import paramlist as pl
+        if isinstance(params, (str, os.PathLike)):
+            params = pl.read_xml(params)
+        if "THCM" in params and isinstance(params["THCM"], pl.ParameterList):
+            params = params["THCM"]
+        su = pl.thcm_setup(params, rank=rank, nranks=nranks, device=device, balance=balance, data_dir=data_dir)
+        t = cls(su["settings"], su["landm"], comm)
+        t.paramList_ = su["params"]
+        t.scalingType_ = su["scaling"]
+        if su["spert"] is not None:
+            t.insertSurfaceField("emip_pert", su["spert"])        # spert of init_ (THCM.C:566-611); used from the next parameter change on
+        if su["integral_condition"] is not None:
+            t.enableIntegralCondition(*su["integral_condition"])
+        if su["fix_pressure_points"]:
+            t.fixPressurePoints(True)
+        for name, value in su["starting_parameters"]:              # THCM.C:781-792
+            t.setParameter(name, value)
+        return t
 
     def _init_nccl(self, comm):
         import torch.distributed as dist
@@ -484,8 +508,8 @@ class THCM:
 class Ocean:
     """The Model API of the reference (src/utils/Model.H:54-117) as implemented by Ocean (Ocean.C)."""
 
-    def __init__(self, settings, landm, comm=None, solver_params=None):
-        self.thcm = THCM(settings, landm, comm)
+    def __init__(self, settings, landm, comm=None, solver_params=None, thcm=None):
+        self.thcm = thcm if thcm is not None else THCM(settings, landm, comm)
         t = self.thcm
         self.state_ = t.new_vector()
         self.rhs_ = t.new_vector()
@@ -495,6 +519,20 @@ class Ocean:
         self.solver_params = sp
         self.jac_valid = False
         self.precon_valid = False
+
+    @classmethod
+    def from_parameter_list(cls, params, comm=None, **kw):
+        """Ocean::Ocean(comm, Teuchos::ParameterList&) (Ocean.C:71-200): `params` is the reference's ocean list (ocean_params.xml; a
+        paramlist.ParameterList or a path) with its "THCM" sublist and, as the reference's drivers merge it in, the "Belos Solver" sublist
+        (solver_params.xml).  kw: rank, nranks, device, balance, data_dir (THCM.from_parameter_list)."""
+        from . import paramlist as pl
+        if isinstance(params, (str, os.PathLike)):
+            params = pl.read_xml(params)
+        params = pl.validate_parameters_and_set_defaults(params, pl.ocean_default_init_parameters())
+        t = THCM.from_parameter_list(params["THCM"], comm=comm, **kw)
+        o = cls(t.settings, None, comm, solver_params=pl.solver_parameters(params["Belos Solver"]), thcm=t)
+        o.params_ = params
+        return o
 
     def getState(self, mode="V"):
         return self.state_ if mode == "V" else self.state_.clone()
@@ -632,12 +670,31 @@ class FortranABI:
         self._global_initialize.restype = None
         self._global_initialize.argtypes = [ip] * 3 + [dp] * 6 + [ip] * 13 + [C.c_char_p] * 5
 
-    def global_initialize(self, s, maskfile=b""):
+    def global_initialize(self, s, maskfile=b"", itopo=1, flat=False, spertmaskfile=b""):
+        """m_global::initialize (global.F90:65-160, THCM.C:325-337).  maskfile = "Land Mask" with "Read Land Mask" (a path, or a name below
+        $THCM_DATA_DIR/mkmask); without one the next global_get_landm builds the idealised "Topography" case itopo (topo.F90:129-330).
+        spertmaskfile = "Salinity Perturbation Mask" with "Read Salinity Perturbation Mask"."""
         i, d = C.c_int, C.c_double
-        a = [i(s.N), i(s.M), i(s.L), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.hdim), d(s.qz), i(s.periodic), i(0), i(0),
-             i(1 if maskfile else 0), i(s.TRES), i(s.SRES), i(s.iza), i(s.ite), i(s.its), i(0), i(s.coupled_T), i(s.coupled_S),
-             i(s.forcing_type)]
-        self._global_initialize(*[C.byref(x) for x in a], maskfile, b"", b"", b"", b"")
+        self._gdims = (s.N, s.M, s.L)
+        a = [i(s.N), i(s.M), i(s.L), d(s.xmin), d(s.xmax), d(s.ymin), d(s.ymax), d(s.hdim), d(s.qz), i(s.periodic), i(itopo), i(int(flat)),
+             i(1 if maskfile else 0), i(s.TRES), i(s.SRES), i(s.iza), i(s.ite), i(s.its), i(1 if spertmaskfile else 0), i(s.coupled_T),
+             i(s.coupled_S), i(s.forcing_type)]
+        self._global_initialize(*[C.byref(x) for x in a], maskfile, spertmaskfile, b"", b"", b"")
+
+    def global_get_landm(self):
+        """m_global::get_landm (global.F90:299-318): runs topofit -- the mask file or the Topography case -- and returns the GLOBAL
+        mask [l+2, m+2, n+2] THCM.C distributes over the sub-domains (THCM.C:372-400)."""
+        n, m, l = self._gdims
+        out = np.empty((l + 2, m + 2, n + 2), dtype=np.int32)
+        self._call("__m_global_MOD_get_landm", _np_ptr(out))
+        return out
+
+    def global_get_spert(self):
+        """m_global::get_spert (global.F90:587-608): the salinity perturbation mask [m, n] THCM.C hands to init_."""
+        n, m, _ = self._gdims
+        out = np.empty((m, n))
+        self._call("__m_global_MOD_get_spert", _np_ptr(out))
+        return out
 
     def init(self, s, landm):
         """init_ for a single-rank domain (usrc.F90:6-139), followed by get_array_sizes / set_pointers like THCM.C:619-638."""

@@ -29,15 +29,18 @@ extern "C" {
  * ------------------------------------------------------------------------ */
 
 /* replaces m_global::initialize, src/ocean/global.F90:65-157 (THCM.C:331-338).
- * Angles in radians.  File names are accepted but only the mask file is read
- * (data/ in the reference holds nothing else); rd_mask=0 leaves an all-ocean mask. */
+ * Angles in radians.  Stores the settings and clears the mask; of the file names the land mask and the salinity perturbation mask
+ * are used (data/ in the reference holds nothing else).  The mask itself is made by get_landm, like the reference's topofit
+ * (topo.F90:6-38): rd_mask != 0 reads mkmask/<maskfile> (a path, or a name below $THCM_DATA_DIR/mkmask; readmask, topo.F90:41-127),
+ * rd_mask == 0 builds the idealised continents of itopo = 1..4 (depth3land, topo.F90:129-330; itopo = 0 needs bathymetry data
+ * the reference does not ship and fails loudly); flat copies the surface level down. */
 void __m_global_MOD_initialize(int* N, int* M, int* L, double* xmin, double* xmax, double* ymin, double* ymax,
                                double* hdim, double* qz, int* periodic, int* itopo, int* flat, int* rd_mask,
                                int* TRES, int* SRES, int* iza, int* ite, int* its, int* rd_spertm,
                                int* coupled_T, int* coupled_S, int* forcing_type,
                                const char* maskfile, const char* spertmaskfile, const char* windfile,
                                const char* sstfile, const char* sssfile);
-/* replaces m_global::get_landm (THCM.C:389): (N+2)(M+2)(L+2) ints, i fastest */
+/* replaces m_global::get_landm (global.F90:299-318, THCM.C:389): runs topofit, then (N+2)(M+2)(L+2) ints, i fastest */
 void __m_global_MOD_get_landm(int* landm);
 void __m_global_MOD_finalize(void);
 
@@ -104,7 +107,7 @@ void __m_global_MOD_get_temforcing(double* tatm);
 void __m_global_MOD_get_salforcing(double* emip);
 void __m_global_MOD_get_internal_temforcing(double* temp);
 void __m_global_MOD_get_internal_salforcing(double* salt);
-void __m_global_MOD_get_spert(double* spert);
+void __m_global_MOD_get_spert(double* spert);   /* SRES everywhere, or (1 - digit)(1 - landm(i,j,l)) from mkmask/<spertmaskfile> (read_spertm, forcing.F90:372-402) */
 void __m_global_MOD_get_land_temp(double* land);   /* THCM.C:170 declares it; the reference's Fortran never defines it: fails loudly */
 /* global.F90:241-293 (THCM.C:51-56): the caller's global grid arrays; checked against the library's own grid.F90 arrays */
 void set_global_x(int* n, double* a);

@@ -420,3 +420,48 @@ def test_transient_run_on_the_device_reproduces_the_reference_golden_norm():
     assert steps == 10 and total == tt.GOLDEN_NEWTON_STEPS
     assert abs(np.linalg.norm(x) - tt.GOLDEN_NORM) < 1e-7, np.linalg.norm(x)
     t.close()
+
+
+def test_models_built_from_the_reference_parameter_lists(tmp_path):
+    """THCM / Ocean from the reference's Teuchos XML lists (paramlist.py; THCM.C:186-795, Ocean.C:985-1012): the model the constructor
+    builds from tests/golden/params/natl8_integral_condition.xml (mask by file name, Mixing = 1, SRES = 0 -> integral condition,
+    starting parameters) evaluates to the same bits as the hand-built one, and the basin the default run's "Topography" = 1 builds
+    reproduces the stored steady state of that run as a root (tests/test_oracle_pins.py)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    from iemic_b200 import paramlist as pl
+    here = os.path.dirname(os.path.abspath(__file__))
+    os.symlink(os.path.join(here, "golden", "masks"), tmp_path / "mkmask")
+    xml = os.path.join(here, "golden", "params", "natl8_integral_condition.xml")
+    oc = iemic_b200.Ocean.from_parameter_list(xml, data_dir=tmp_path)
+    assert oc.solver_params == dict(tol=1e-6, restart=120, maxit=360, precon=1)
+    s, landm = cases.natl8(vmix=1, SRES=0)
+    t = iemic_b200.THCM(s, landm)
+    rowic = t.enableIntegralCondition(-1, -1, -1)
+    start = pl.read_xml(xml)["THCM"]["Starting Parameters"]
+    for k, v in start.items():
+        t.setParameter(k, v)
+    assert oc.thcm.L_.thcmb_intcond_row(oc.thcm.ctx) == rowic
+    for k in ("Combined Forcing", "SPL1", "Rossby-Number", "Wind Forcing"):
+        assert oc.getPar(k) == t.getParameter(k)
+    x = cases.consistent_state(s, landm, scale=0.05, seed=6)
+    oc.getState("V").copy_(torch.from_numpy(x).cuda())
+    oc.computeRHS()
+    oc.computeJacobian()
+    F = t.new_vector()
+    t.evaluate(torch.from_numpy(x).cuda(), F, True)
+    assert np.array_equal(oc.getRHS("V").cpu().numpy(), F.cpu().numpy())
+    assert np.array_equal(oc.thcm.jacobian_values_host(), t.jacobian_values_host())
+    assert np.array_equal(oc.thcm.getMassDiagonal(), t.getMassDiagonal())
+    t.close(); oc.thcm.close()
+    # the default run: Topography = 1 basin, Forcing Type 2; its stored steady state is a root
+    from test_oracle_pins import DEFAULT_RUN_STATE
+    t2 = iemic_b200.THCM.from_parameter_list(os.path.join(here, "golden", "params", "basin16_topography1.xml"))
+    xs = np.fromfile(DEFAULT_RUN_STATE)
+    F2, F0 = t2.new_vector(), t2.new_vector()
+    t2.evaluate(torch.from_numpy(xs).cuda(), F2, False)
+    t2.evaluate(torch.zeros(t2.ndim, dtype=torch.float64, device="cuda"), F0, False)
+    assert float(F2.norm()) < 1e-10 * float(F0.norm())
+    t2.close()
