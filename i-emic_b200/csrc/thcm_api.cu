@@ -253,6 +253,10 @@ int thcmb_theta_rhs_dev(thcmb_ctx* c, double theta, double dt, const double* d_s
     if (!(dt > 0.0)) fatal("thcmb_theta_rhs_dev: the time step must be positive");
     return theta_rhs(c, c->blk.ndim(), theta, dt, d_state, d_old_state, d_old_rhs, c->d_cob, d_F);
 }
+int thcmb_apply_mass_dev(thcmb_ctx* c, const double* d_v, double* d_out) {
+    if (d_v == d_out) { set_error("thcmb_apply_mass_dev: v and out must be different vectors"); return -1; }
+    return mass_apply(c, c->blk.ndim(), c->d_cob, d_v, d_out);
+}
 int thcmb_theta_jacobian_dev(thcmb_ctx* c, double theta, double dt) {
     if (theta == 0.0) return 0;                                     // ThetaModel.H:126-127
     if (!(dt > 0.0)) fatal("thcmb_theta_jacobian_dev: the time step must be positive");

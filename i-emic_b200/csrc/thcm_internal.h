@@ -333,6 +333,7 @@ int axpy_negdev(thcmb_ctx* c, int n, const double* d_h, const double* x, double*
 int scale_invsqrt_dev(thcmb_ctx* c, int n, const double* d_nrm2, double* x, double* d_nrm);   // x /= sqrt(*d_nrm2)
 int copy(thcmb_ctx* c, int n, const double* x, double* y);
 int fill(thcmb_ctx* c, int n, double a, double* x);
+int mass_apply(thcmb_ctx* c, int n, const double* d_cob, const double* v, double* out);
 int theta_rhs(thcmb_ctx* c, int n, double theta, double dt, const double* state, const double* old_state, const double* old_rhs,
               const double* d_cob, double* F);
 int theta_jacobian(thcmb_ctx* c, double theta, double dt, const double* d_cob);

@@ -521,6 +521,14 @@ __global__ void theta_jac_kernel(int nrow, double dt, double theta, const int* _
         if (col[q] == r) { val[q] = val[q] + value; found = true; break; }           // SumIntoGlobalValues on the diagonal
     if (!found) atomicAdd(missing, 1);
 }
+// out = M v with the diagonal mass matrix (Ocean::applyMassMat, Ocean.C:1448-1457: out.Multiply(1.0, diagB, v, 0.0); `out` is not read)
+__global__ void mass_apply_kernel(int n, const double* __restrict__ cob, const double* __restrict__ v, double* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = cob[i] * v[i];
+}
+int mass_apply(thcmb_ctx* c, int n, const double* d_cob, const double* v, double* out) {
+    ProfScope prof_(c, KID_AXPBY);
+    mass_apply_kernel<<<ew_grid(n), 256, 0, c->stream>>>(n, d_cob, v, out); c->launches++; return 0;
+}
 int theta_rhs(thcmb_ctx* c, int n, double theta, double dt, const double* state, const double* old_state, const double* old_rhs,
               const double* d_cob, double* F) {
     ProfScope prof_(c, KID_AXPBY);

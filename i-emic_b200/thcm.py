@@ -96,7 +96,7 @@ def load_library(path=None):
         "thcmb_halo_gids": (None, [vp, vp]), "thcmb_local_gids": (None, [vp, vp]),
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
-        "thcmb_theta_rhs_dev": (i, [vp, d, d, vp, vp, vp, vp]), "thcmb_theta_jacobian_dev": (i, [vp, d, d]),
+        "thcmb_apply_mass_dev": (i, [vp, vp, vp]), "thcmb_theta_rhs_dev": (i, [vp, d, d, vp, vp, vp, vp]), "thcmb_theta_jacobian_dev": (i, [vp, d, d]),
         "thcmb_enable_intcond": (None, [vp, i, i, i]), "thcmb_set_intcond_correction": (d, [vp, vp]),
         "thcmb_fix_pressure_points": (None, [vp, i]), "thcmb_intcond_row": (i, [vp]),
         "thcmb_insert_field": (None, [vp, i, vp]), "thcmb_set_atmos_parameters": (None, [vp, vp]),
@@ -162,6 +162,7 @@ class THCM:
         self.settings = settings
         landm = np.ascontiguousarray(landm, dtype=np.int32)
         assert landm.shape == (settings.L + 2, settings.M + 2, settings.N + 2), landm.shape
+        self.landm_global = landm
         self.ctx = self.L_.thcmb_create(C.byref(settings), _np_ptr(landm))
         if not self.ctx:
             raise RuntimeError("thcmb_create failed: " + self.L_.thcmb_last_error().decode())
@@ -562,6 +563,31 @@ class Ocean:
 
     def applyMatrix(self, v, out):  # Ocean.C:1369-1374
         self.thcm.applyMatrix(v, out)
+
+    def applyMassMat(self, v, out):  # Ocean.C:1448-1457: out = diag(B) v
+        t = self.thcm
+        t._pre()
+        if t.L_.thcmb_apply_mass_dev(t.ctx, _dev_ptr(v), _dev_ptr(out)) != 0:
+            raise ValueError(last_error())
+        t.sync()
+
+    # ---- the small queries of the Model API (Model.H:82-100, Ocean.H) ----
+    def npar(self):
+        return 30                      # _NPAR_ (THCMdefs.H)
+
+    def int2par(self, ind):
+        from .params import PAR_NAMES
+        return PAR_NAMES[ind]
+
+    def name(self):
+        return "ocean"
+
+    def dof(self):
+        return 6                       # _NUN_
+
+    def getLandMask(self):
+        """The GLOBAL land mask [l+2, m+2, n+2] the model was created with (Ocean::getLandMask's `global_borders`)."""
+        return self.thcm.landm_global.copy()
 
     def buildPreconditioner(self):  # Ocean.C:1377-1391
         if not self.precon_valid:

@@ -280,6 +280,9 @@ int thcmb_csr_spmv_dev(thcmb_ctx* c, int nrow, const int* d_rowptr, const int* d
 int thcmb_theta_rhs_dev(thcmb_ctx* c, double theta, double dt, const double* d_state, const double* d_old_state,
                         const double* d_old_rhs, double* d_F);
 int thcmb_theta_jacobian_dev(thcmb_ctx* c, double theta, double dt);
+/* Ocean::applyMassMat (Ocean.C:1448-1457): d_out = M d_v with the diagonal mass matrix (coB of assemble.F90:18-54; 0 on w, p, LAND and
+ * the replaced rows of thcmb_enable_intcond / thcmb_fix_pressure_points).  d_out is not read; returns -1 when it aliases d_v */
+int thcmb_apply_mass_dev(thcmb_ctx* c, const double* d_v, double* d_out);
 
 /* vector kernels (Epetra_MultiVector::Dot/Norm2/Update/Scale as used by GMRESSolver.H / IDRSolver.H);
  * dot/nrm2 all-reduce over ranks and return on the host */

@@ -232,11 +232,8 @@ public:
     virtual void computeMassMat() { massMat_ = thcm_->evaluateB(); }
     virtual void applyMatrix(const Vector& v, Vector& out) { thcm_->applyMatrix(v, out); }               // Ocean.C:1369-1374
     virtual void applyMassMat(const Vector& v, Vector& out) {                                            // diagonal B
-        if (massMat_.empty()) computeMassMat();
-        std::vector<double> h = v.toHost();
-        for (size_t i = 0; i < h.size(); i++) h[i] = massMat_[i] * h[i];
         out.ensure(v);
-        out.fromHost(h.data());
+        if (thcmb_apply_mass_dev(context(), v.data(), out.data()) != 0) throw std::runtime_error(thcmb_last_error());
     }
     virtual void buildPreconditioner() {                                                                 // Ocean.C:1377-1391
         if (!precInitialized_) { thcmb_build_precon(context(), sp_.precon); precInitialized_ = true; }

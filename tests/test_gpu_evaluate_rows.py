@@ -455,6 +455,15 @@ def test_models_built_from_the_reference_parameter_lists(tmp_path):
     assert np.array_equal(oc.getRHS("V").cpu().numpy(), F.cpu().numpy())
     assert np.array_equal(oc.thcm.jacobian_values_host(), t.jacobian_values_host())
     assert np.array_equal(oc.thcm.getMassDiagonal(), t.getMassDiagonal())
+    # Ocean::applyMassMat (Ocean.C:1448-1457) on the device: out = diag(B) v, the integral-condition row included (B = 0 there)
+    v = torch.from_numpy(np.random.default_rng(2).standard_normal(t.ndim)).cuda()
+    out = torch.full_like(v, float("nan"))
+    oc.applyMassMat(v, out)
+    B = oc.thcm.getMassDiagonal()
+    assert np.array_equal(out.cpu().numpy(), B * v.cpu().numpy()) and B[rowic] == 0.0 and (B != 0).any()
+    with pytest.raises(ValueError):
+        oc.applyMassMat(v, v)
+    assert oc.npar() == 30 and oc.int2par(19) == "Combined Forcing" and oc.dof() == 6 and np.array_equal(oc.getLandMask(), landm)
     t.close(); oc.thcm.close()
     # the default run: Topography = 1 basin, Forcing Type 2; its stored steady state is a root
     from test_oracle_pins import DEFAULT_RUN_STATE
