@@ -21,7 +21,13 @@
 // and 30 (tests/test_oracle_pins.py, 1e-7): every term of F is pinned at the
 // 1e-9 level by a number the reference produced, and J well enough to repeat
 // its Newton history step for step.  The same run through the CUDA path gives
-// the same number (tests/test_gpu_evaluate_rows.py).
+// the same number (tests/test_gpu_evaluate_rows.py).  A second reference-made
+// number, on another configuration (the default run of run/ocean: 16^3 basin
+// without land, Forcing Type 2, restoring salinity): run/ocean/workflow.org:13-21
+// prints norm state 542.3414237 at parameter 1.000006854 (Newton tolerance
+// 1e-2); the exact root of this oracle's F at that parameter has norm
+// 542.3439468, 4.7e-6 relative away (scripts/default_run_steady_state.py,
+// tests/test_oracle_pins.py).
 // It also ships ONE
 // reference-produced vector: the converged state of its regression test
 // (test/ocean/ocean_reference.h5, src/tests/reft_ocean.C:59-89; committed as

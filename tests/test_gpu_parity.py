@@ -144,6 +144,26 @@ def test_reference_converged_state_is_a_root_on_the_device(gpu):
     t.close()
 
 
+def test_default_run_steady_state_is_a_root_on_the_device(gpu):
+    """The steady state of the reference's default run (norm 542.34 = the number run/ocean/workflow.org prints, test_oracle_pins.py) through
+    the CUDA residual: equal to the oracle's bit for bit, i.e. a root to 1e-10 of || F(0) ||."""
+    from test_oracle_pins import default_run_case, DEFAULT_RUN_STATE
+    from oracle.oracle import OracleTHCM
+    s, landm, pars = default_run_case()
+    t = gpu.THCM(s, landm)
+    o = OracleTHCM(s, landm)
+    for k, v in pars.items():
+        t.setParameter(k, v)
+        o.setpar(P[k], v)
+    x = np.fromfile(DEFAULT_RUN_STATE)
+    F = t.new_vector()
+    t.evaluate(dev(x), F, False)
+    Fg = F.cpu().numpy()
+    assert np.array_equal(Fg, -o.rhs(x))
+    assert np.linalg.norm(Fg) < 1e-10 * np.linalg.norm(o.rhs(np.zeros(o.ndim)))
+    t.close()
+
+
 @pytest.mark.parametrize("name", ["natl8", "gateway16", "global4deg"])
 def test_scaling_and_integral_condition(gpu, name):
     """THCM::RecomputeScaling (m_scaling::average_block + compute, scaling.F90) and getIntCondCoeff (thcm_utils.F90:285-309):
@@ -495,10 +515,13 @@ def test_idrs_history_matches_reference_templates(gpu, name, prec):
     t.close()
 
 
-def test_batched_gmres_with_the_reference_restart_length(gpu):
+@pytest.mark.parametrize("cgs2", ["2", "3"])
+def test_batched_gmres_with_the_reference_restart_length(gpu, cgs2, monkeypatch):
     """run/ocean/solver_params.xml asks for 500 Krylov vectors and no restart: the batched (DGKS) orthogonalisation works through a basis
     of more than 64 vectors in chunks -- same history as the template's modified Gram-Schmidt (1e-10), on the ocean-only space and on
-    full-length vectors; an unusable restart length is reported through thcmb_last_error, not by aborting the process."""
+    full-length vectors; an unusable restart length is reported through thcmb_last_error, not by aborting the process.
+    cgs2: the fused first update + second projection as the L2-tiled kernel (2) or the TMA-staged one (3, for 17..52 basis vectors)."""
+    monkeypatch.setenv("THCM_FUSED_CGS2", cgs2)
     s, landm, o, t = setup(gpu, "natl8")
     x = cases.consistent_state(s, landm, scale=0.1)
     F = t.new_vector()
@@ -624,10 +647,13 @@ def test_missing_extension_fails_loudly(gpu, tmp_path):
 
 
 @pytest.mark.parametrize("name", ["natl8", "gateway16"])
-def test_gmres_dgks_mode_matches_mgs_history(gpu, name):
+@pytest.mark.parametrize("cgs2", ["2", "3"])
+def test_gmres_dgks_mode_matches_mgs_history(gpu, name, cgs2, monkeypatch):
     """The batched Gram-Schmidt / DGKS mode (Belos-style, fewer global reductions) against the template's MGS on the GPU
-    and against the reference template itself: same residual history to 1e-10, same iteration count +-1."""
+    and against the reference template itself: same residual history to 1e-10, same iteration count +-1 (cgs2: kernel variant of the
+    fused first update + second projection, THCM_FUSED_CGS2)."""
     from oracle.oracle import kref_gmres
+    monkeypatch.setenv("THCM_FUSED_CGS2", cgs2)
     s, landm, o, t = setup(gpu, name)
     x = cases.consistent_state(s, landm, scale=0.1)
     F = t.new_vector()
