@@ -177,7 +177,7 @@ thcmb_ctx* thcmb_create(const thcmb_settings* s, const int* landm_global) {
     c->n_asm_blocks = asm_block_count(c->blk);
     if (const char* e = getenv("THCM_ASM_PIPE")) c->asm_pipe = atoi(e);
     if (const char* e = getenv("THCM_KRYLOV_COMPACT")) c->krylov_compact = atoi(e);
-    c->fused_cgs2 = 2;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5), 3 = TMA-staged tile
+    c->fused_cgs2 = 2;   // 2 = L2-tiled kernel (76.2 ms per Newton step at 1 degree), 1 = shared-memory parking (78.7), 0 = unfused (82.5)
     if (const char* e = getenv("THCM_FUSED_CGS2")) c->fused_cgs2 = atoi(e);
     THCM_CUDA(cudaMalloc(&c->d_partial, sizeof(double) * 4096));
     THCM_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 4096));

@@ -875,142 +875,10 @@ __global__ void __launch_bounds__(F2_THREADS, BPS) fused2_axpy_dot_kernel(int n,
     multi_tail((int)gridDim.x, nv, partial, counter, out, pa, ep);
 }
 
-// Variant 3 of the fused first update + second projection (THCM_FUSED_CGS2=3): the basis tile staged in SHARED memory by TMA.
-// A block walks over tiles of 128 double2 elements.  One warp issues one cp.async.bulk per basis vector (a 2 KB row of the tile) against
-// an mbarrier: nv x 2 KB in flight per block with no register or instruction cost, several blocks per SM so that one loads while another
-// computes.  Phase A: thread t forms w'[t] = w[t] - sum_q h1[q] V_q[t] from column t of the staged tile (q ascending: the bits of
-// multi_axpy), stores it to global memory and into a 2 KB shared tile.  Phase B: warp q' takes the rows q = q', q'+4, ... of the SAME staged
-// tile against w'.  HBM sees the basis once and nothing is re-read through the L2 (variant 2 reads the tile twice: 204 us at 67 % of
-// the HBM peak for the 1-degree grid at nv ~ 25).
-constexpr int F3_THREADS = 128, F3_TILE = 128, F3_NW = F3_THREADS / 32;
-constexpr int F3_VPW = MD_MAXV / F3_NW;                       // basis vectors per warp in phase B (16)
-constexpr int F3_MAXV = 52;                                   // two resident blocks per SM: 2 x (52 x 2 KB + 4.7 KB static + 1 KB reserved) = 219 KB of 228
-__device__ __forceinline__ uint32_t f3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool f3_try_wait(void* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done) : "r"(f3_smem_u32(bar)), "r"(parity) : "memory");
-    return done != 0;
-}
-__global__ void __launch_bounds__(F3_THREADS) fused3_axpy_dot_kernel(int n, VecList vl, const double* __restrict__ h1, double* __restrict__ w,
-                                                                      double* partial, unsigned int* counter, double* out,
-                                                                      const P2PArgs pa, const RedEpilogue ep) {
-    extern __shared__ __align__(128) unsigned char f3_raw[];
-    double2* vt = reinterpret_cast<double2*>(f3_raw);           // [nv][F3_TILE]
-    __shared__ double hs[MD_MAXV];
-    __shared__ __align__(16) double2 wt[F3_TILE];
-    __shared__ double wred[F3_NW];
-    __shared__ __align__(8) unsigned long long bar;
-    __shared__ bool last;
-    const int nv = vl.nv, n2 = n >> 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = threadIdx.x; q < nv; q += F3_THREADS) hs[q] = h1[q];
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(f3_smem_u32(&bar)), "r"(1) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    double acc[F3_VPW];
-#pragma unroll
-    for (int j = 0; j < F3_VPW; j++) acc[j] = 0.0;
-    double wwacc = 0.0;
-    double2* w2 = reinterpret_cast<double2*>(w);
-    const int ntiles = (n2 + F3_TILE - 1) / F3_TILE;
-    uint32_t parity = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1u) {
-        const int base = tile * F3_TILE;
-        const int valid = min(F3_TILE, n2 - base);
-        const uint32_t row_bytes = (uint32_t)valid * (uint32_t)sizeof(double2);
-        if (warp == 0) {
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(f3_smem_u32(&bar)), "r"(row_bytes * (uint32_t)nv) : "memory");
-            __syncwarp();
-            for (int q = lane; q < nv; q += 32)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                             ::"r"(f3_smem_u32(vt + (size_t)q * F3_TILE)), "l"(reinterpret_cast<const double2*>(vl.v[q]) + base), "r"(row_bytes),
-                               "r"(f3_smem_u32(&bar)) : "memory");
-        }
-        // this thread's element of w travels as a plain load beside the bulk copies
-        const int i = base + threadIdx.x;
-        const bool ok = (int)threadIdx.x < valid;
-        double2 wi = ok ? w2[i] : make_double2(0.0, 0.0);
-        if (warp == 0) {   // one warp polls, the others sleep at the barrier; a lost copy must fail loudly, never hang the GPU
-            unsigned int polls = 0;
-            const long long t0 = clock64();
-            while (!f3_try_wait(&bar, parity))
-                if ((++polls & 255u) == 0 && clock64() - t0 > 4000000000ll) {
-                    if (lane == 0) printf("fused3_axpy_dot: block %d stuck waiting for its basis tile %d\n", blockIdx.x, tile);
-                    __trap();
-                }
-        }
-        __syncthreads();
-        // ---- phase A: w' = w - V h1 on this thread's element (q order = the order of multi_axpy) ----
-        if (ok) {
-            const double2* col = vt + threadIdx.x;
-#pragma unroll 4
-            for (int q = 0; q < nv; q++) {
-                const double2 v = col[(size_t)q * F3_TILE];
-                wi.x = wi.x - hs[q] * v.x;
-                wi.y = wi.y - hs[q] * v.y;
-            }
-            w2[i] = wi;
-        }
-        wt[threadIdx.x] = wi;
-        wwacc += wi.x * wi.x; wwacc += wi.y * wi.y;
-        __syncthreads();
-        // ---- phase B: h2[q] += V_q[tile] . w'[tile] for this warp's rows of the staged tile ----
-#pragma unroll
-        for (int j = 0; j < F3_VPW; j++) {
-            const int q = warp + F3_NW * j;
-            if (q < nv) {
-                const double2* row = vt + (size_t)q * F3_TILE;
-                double a = acc[j];
-#pragma unroll
-                for (int r = 0; r < F3_TILE / 32; r++) {
-                    const int e = lane + 32 * r;
-                    if (e < valid) {           // (beyond `valid` the row holds what an earlier tile left there)
-                        const double2 v = row[e], wv = wt[e];
-                        a += wv.x * v.x; a += wv.y * v.y;
-                    }
-                }
-                acc[j] = a;
-            }
-        }
-        __syncthreads();   // every read of the staged tile and of wt is done before the next tile's copies and stores
-    }
-    // per-block results: one (warp, j) pair per vector, lanes summed by a shuffle tree; w'.w' over the whole block
-    constexpr int stride = MD_MAXV + 1;
-#pragma unroll
-    for (int j = 0; j < F3_VPW; j++) {
-        double v = acc[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int q = warp + F3_NW * j;
-        if (lane == 0 && q < nv) partial[(size_t)blockIdx.x * stride + q] = v;
-    }
-    {
-        double v = wwacc;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) wred[warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double v = 0.0;
-        for (int ww = 0; ww < F3_NW; ww++) v += wred[ww];
-        partial[(size_t)blockIdx.x * stride + MD_MAXV] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned int t = atomicAdd(counter, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    multi_tail((int)gridDim.x, nv, partial, counter, out, pa, ep);
-}
-
+// (A third variant -- the basis tile staged in SHARED memory by cp.async.bulk / mbarrier, single- and double-buffered, so that phase B
+// re-reads nothing through the L2 -- was built and measured in round 2 (profiles/r02/bench_r02y_cgs3.json, bench_r02z2_cgs3.json,
+// ncu_full_f3_r02z_summary.json): 0.203 ms and 0.272 ms per launch against 0.205 ms of variant 2, correct but not faster; removed.
+// What its profile says about this operation is in DESIGN.md section 3.2.)
 // w -= sum_q h[q] v_q  (applied in q order);  skipped when *skip == 0
 __global__ void __launch_bounds__(256) multi_axpy_kernel(int n, VecList vl, const double* __restrict__ h, const int* __restrict__ skip,
                                                           double* __restrict__ w) {
@@ -1175,23 +1043,6 @@ int fused_axpy_dot_dev(thcmb_ctx* c, int n, int nv, double* const* vecs, const d
     const RedEpilogue ep{d_ww_old, d_flag_out, d_final_out, d_flag2_out};
     // measured (profiles/ncu_full_r01d_fused_cgs2_summary.json): at nv = 11 the shared-memory kernel <16> needs 0.17 ms, the L2-tiled one
     // 0.21 ms; averaged over nv = 1..50 it is 0.47 vs 0.40 ms (the <32..64> instantiations park up to 131 KB per block)
-    if (c->fused_cgs2 == 3 && nv > 16 && nv <= F3_MAXV) {
-        ProfScope prof_(c, KID_MULTIAXPY);
-        const int ntiles = ((n >> 1) + F3_TILE - 1) / F3_TILE;
-        const size_t smem = (size_t)nv * F3_TILE * sizeof(double2);
-        static bool attr_set = false;
-        if (!attr_set) {
-            THCM_CUDA(cudaFuncSetAttribute(fused3_axpy_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_MAXV * F3_TILE * (int)sizeof(double2)));
-            THCM_CUDA(cudaFuncSetAttribute(fused3_axpy_dot_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            attr_set = true;
-        }
-        // resident blocks per SM: what the staged tiles leave room for (228 KB per SM; 4.7 KB static + 1 KB reserved per block), at most 4 (MD_BLOCKS partials)
-        const int bps = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(228 * 1024) / (smem + 6144)));
-        const int grid = std::max(1, std::min(std::min(ntiles, NSM * bps), MD_BLOCKS));
-        fused3_axpy_dot_kernel<<<grid, F3_THREADS, smem, c->stream>>>(n, vl, d_h1, w, c->d_mdpartial, c->d_counter, d_out, p2p_vec_args(c), ep);
-        c->launches++;
-        return 0;
-    }
     if (c->fused_cgs2 >= 2 && nv > 16) {
         ProfScope prof_(c, KID_MULTIAXPY);
         const int ntiles = ((n >> 1) + F2_THREADS - 1) / F2_THREADS;
