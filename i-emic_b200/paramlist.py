@@ -196,6 +196,14 @@ def thcm_setup(thcm_params, rank=0, nranks=1, device=0, balance=0, data_dir=None
     if p["Levitus Internal T/S"]:
         raise InvalidParameter('"Levitus Internal T/S" reads Levitus data files that do not ship with the reference; '
                                "hand the fields to set_internal_forcing instead")
+    # the data-file options of m_global::get_windfield / get_temforcing / get_salforcing (global.F90:425-560): Trenberth winds and Levitus
+    # surface fields are not part of the reference tree -- the same conditions under which the library's getters fail loudly
+    if s.iza < 2:
+        raise InvalidParameter('"Wind Forcing Type" 0 / 1 reads wind/trtau.dat, which does not ship with the reference; insert taux / tauy')
+    if s.coupled_T == 0 and s.ite == 0 and s.TRES != 0:
+        raise InvalidParameter('"Levitus T" = 0 with a restoring temperature profile reads Levitus data that do not ship with the reference')
+    if s.coupled_S == 0 and s.its == 0 and s.SRES != 0:
+        raise InvalidParameter('"Levitus S" = 0 with a restoring salinity profile reads Levitus data that do not ship with the reference')
     for flag, key in (("Read Land Mask", "Land Mask"), ("Read Salinity Perturbation Mask", "Salinity Perturbation Mask")):
         if p[flag]:   # (the Fortran symbols end the process on a missing file, like the reference: find out before calling them)
             base = data_dir if data_dir is not None else os.environ.get("THCM_DATA_DIR", ".")

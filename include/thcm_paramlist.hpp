@@ -89,6 +89,10 @@ THCMSetup setupFromParameterList(ParameterList& p, int rank = 0, int nranks = 1,
     const std::string spertFile = p.template get<std::string>("Salinity Perturbation Mask", "no_mask_specified");
     if (std::abs(su.intSign) != 1) throw std::invalid_argument("Invalid integral sign!");          // THCM.C:265-268
     s.iza = p.template get<int>("Wind Forcing Type", 2);
+    // the data-file options of m_global::get_windfield / get_temforcing / get_salforcing (global.F90:425-560): not in the reference tree
+    if (s.iza < 2 || (s.coupled_T == 0 && s.ite == 0 && s.TRES != 0) || (s.coupled_S == 0 && s.its == 0 && s.SRES != 0))
+        throw std::invalid_argument("THCM: \"Wind Forcing Type\" < 2 / \"Levitus T\" = 0 / \"Levitus S\" = 0 read Trenberth / Levitus data files that do "
+                                    "not ship with the reference; insert the fields instead");
     s.rank = rank; s.nranks = nranks; s.device = device; s.balance = balance;
     su.Nic = p.template get<int>("Integral row coordinate i", -1);
     su.Mic = p.template get<int>("Integral row coordinate j", -1);

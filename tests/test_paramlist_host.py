@@ -107,6 +107,10 @@ def test_constructor_rules(data_dir):
         pl.thcm_setup(variant(**{"Global Bound ymax": 94.0}), data_dir=data_dir)
     with pytest.raises(FileNotFoundError):
         pl.thcm_setup(variant(**{"Land Mask": "no_such_mask"}), data_dir=data_dir)
+    for kw in ({"Wind Forcing Type": 0}, {"Levitus T": 0}, {"Levitus S": 0, "Restoring Salinity Profile": 1}):
+        with pytest.raises(pl.InvalidParameter, match="not ship"):                                                # data files outside the tree
+            pl.thcm_setup(variant(**kw), data_dir=data_dir)
+    pl.thcm_setup(variant(**{"Levitus S": 0}), data_dir=data_dir)          # with SRES = 0 the flux comes through the HDF5 interface: accepted
     su = pl.thcm_setup(variant(**{"Integral row coordinate i": 4, "Integral row coordinate j": 3, "Salinity Integral Sign": 1,
                                   "Fix Pressure Points": True}), data_dir=data_dir)
     assert su["integral_condition"] == (4, 3, 1) and su["fix_pressure_points"] is True
@@ -115,7 +119,7 @@ def test_constructor_rules(data_dir):
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only present in the build container")
 def test_every_ocean_list_the_reference_ships():
     """Each ocean_params.xml of the reference either sets up (its mask found below the reference's data directory) or is refused for a
-    reason the reference itself would stop for (a stale parameter name, a mask file that is not in its tree)."""
+    reason the reference itself would stop for (a stale parameter name, a mask or forcing data file that is not in its tree)."""
     files = sorted(glob.glob(os.path.join(REFERENCE, "**", "*ocean*.xml"), recursive=True))
     ocean = [f for f in files if "THCM" in pl.read_xml(f)]
     assert len(ocean) >= 20
@@ -128,7 +132,8 @@ def test_every_ocean_list_the_reference_ships():
             ok += 1
         except (pl.InvalidParameter, FileNotFoundError) as e:
             refused.append((os.path.relpath(f, REFERENCE), str(e)))
-    assert ok >= 20 and all("Coupled Atmosphere" in m or "mask.glo2" in m for _, m in refused), refused
+    # run/ocean/global asks for Levitus / Trenberth data and for mask.glo2, none of which is in the tree; parameterfiles/ holds a stale key
+    assert ok >= 20 and all("Coupled Atmosphere" in m or "mask.glo2" in m or "do not ship" in m or "does not ship" in m for _, m in refused), refused
     # the three configurations the parity tests build by hand (tests/cases.py, tests/transient_twin.py)
     su = pl.thcm_setup(pl.read_xml(os.path.join(REFERENCE, "test/ocean/ocean_params.xml"))["THCM"], data_dir=os.path.join(REFERENCE, "data"))
     s, landm = cases.natl8(vmix=1, SRES=0)
