@@ -122,6 +122,18 @@ void build_static(thcmb_ctx* c) {
     }
 }
 
+// usrc.F90:353-418 on one instance: the per-cell data, tile descriptors, compact maps and graph-dependent tables follow the new mask
+void set_landmask_ctx(thcmb_ctx* c, const int* landm, bool reinit) {
+    apply_landmask_rules(c, landm, true);
+    THCM_CUDA(cudaStreamSynchronize(c->stream));
+    build_static(c);
+    if (reinit) { vmix_init(c); refresh_params(c); }   // usrc.F90:410-415
+    else {   // no re-initialisation of forcing / lin asked: the mass diagonal and the rows `boundaries` masks in Frc still follow the mask
+        compute_cob(c); zero_cob_of_fixed_rows(c);
+        mask_forcing_rows(c);
+        upload(c->d_cob, c->cob_local); upload(c->d_frc, c->frc_local);
+    }
+}
 void stage_begin(thcmb_ctx* c) { THCM_CUDA(cudaEventRecord(c->ev0, c->stream)); }
 void stage_end(thcmb_ctx* c, const char* label) {  // device time under the reference's profile labels
     THCM_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -339,6 +351,26 @@ void thcmb_enable_intcond(thcmb_ctx* c, int Nic, int Mic, int sign) {
     THCM_CUDA(cudaMalloc(&c->d_iccoeff_c, sizeof(double) * (size_t)std::max(NUN * c->n_ocell, 1)));
     if (c->n_ocell > 0) gather_cells(c, c->d_iccoeff, c->d_iccoeff_c);
     refresh_fix_rows(c);
+}
+/* THCM::setLandMask(global mask, init) (THCM.C:1362-1392) for a handle: with init the instance is rebuilt on the new GLOBAL mask the way
+ * set_landmask_ does with reinit = 1 (same decomposition and cut lines; a preconditioner built before must be rebuilt by the caller);
+ * without init only m_global's copy changes in the reference, i.e. nothing here.  An enabled integral condition keeps its cell and gets
+ * fresh coefficients; -1 (thcmb_last_error) when that cell is land in the new mask. */
+int thcmb_set_landmask(thcmb_ctx* c, const int* landm_global, int init) {
+    if (!init) return 0;
+    const thcmb_settings& s = c->s;
+    int Nic = -1, Mic = -1;
+    if (c->ic_on) {
+        const int cell = c->ic_grow / NUN;
+        Nic = cell % s.N; Mic = (cell / s.N) % s.M;
+        if (landm_global[(size_t)(Nic + 1) + (size_t)(s.N + 2) * ((Mic + 1) + (size_t)(s.M + 2) * s.L)] != 0) {
+            set_error("thcmb_set_landmask: the integral-condition cell (" + std::to_string(Nic) + "," + std::to_string(Mic) + ") is land in the new mask");
+            return -1;
+        }
+    }
+    set_landmask_ctx(c, landm_global, true);
+    if (c->ic_on) thcmb_enable_intcond(c, Nic, Mic, c->ic_sign);
+    return 0;
 }
 /* THCM::setIntCondCorrection (THCM.C:2078-2097): the salinity integral of d_vec becomes the target of the condition */
 double thcmb_set_intcond_correction(thcmb_ctx* c, const double* d_vec) {
@@ -1185,16 +1217,8 @@ void setsres_(int* sres) { thcmb_ctx* c = G(); c->s.SRES = *sres; refresh_params
 void set_landmask_(int* landm, int* periodic, int* reinit) {
     thcmb_ctx* c = G();
     c->s.periodic = *periodic; c->blk.periodic = *periodic; c->blk.wrap_x = (*periodic && c->blk.npN == 1) ? 1 : 0;
-    apply_landmask_rules(c, landm, true);
-    THCM_CUDA(cudaStreamSynchronize(c->stream));
-    build_static(c);
+    set_landmask_ctx(c, landm, *reinit == 1);
     if (g_dbeg) { cudaFree(g_dbeg); cudaFree(g_djco); cudaFree(g_dco); g_dbeg = g_djco = nullptr; g_dco = nullptr; }
-    if (*reinit == 1) { vmix_init(c); refresh_params(c); }   // usrc.F90:410-415
-    else {   // no re-initialisation of forcing / lin asked: the mass diagonal and the rows `boundaries` masks in Frc still follow the mask
-        compute_cob(c); zero_cob_of_fixed_rows(c);
-        mask_forcing_rows(c);
-        upload(c->d_cob, c->cob_local); upload(c->d_frc, c->frc_local);
-    }
 }
 void get_forcing_(double* frc) { thcmb_get_forcing(G(), frc); }
 /* m_inserts (inserts.F90:11-281; THCM.C:85-98): n*m surface fields, i fastest; no recompute until the next setparcs */

@@ -97,7 +97,7 @@ def load_library(path=None):
         "thcmb_set_par": (None, [vp, i, d]), "thcmb_get_par": (d, [vp, i]),
         "thcmb_get_forcing": (None, [vp, vp]), "thcmb_get_cob": (None, [vp, vp]),
         "thcmb_apply_mass_dev": (i, [vp, vp, vp]), "thcmb_theta_rhs_dev": (i, [vp, d, d, vp, vp, vp, vp]), "thcmb_theta_jacobian_dev": (i, [vp, d, d]),
-        "thcmb_enable_intcond": (None, [vp, i, i, i]), "thcmb_set_intcond_correction": (d, [vp, vp]),
+        "thcmb_set_landmask": (i, [vp, vp, i]), "thcmb_enable_intcond": (None, [vp, i, i, i]), "thcmb_set_intcond_correction": (d, [vp, vp]),
         "thcmb_fix_pressure_points": (None, [vp, i]), "thcmb_intcond_row": (i, [vp]),
         "thcmb_insert_field": (None, [vp, i, vp]), "thcmb_set_atmos_parameters": (None, [vp, vp]),
         "thcmb_set_seaice_parameters": (None, [vp, vp]),
@@ -457,6 +457,15 @@ class THCM:
         self._pre()
         return self.L_.thcmb_set_intcond_correction(self.ctx, _dev_ptr(vec))
 
+    def setLandMask(self, landm, init=True):
+        """THCM::setLandMask(global mask, init) (THCM.C:1362-1392): with init the instance follows the new GLOBAL mask [l+2, m+2, n+2]
+        (set_landmask_ with reinit = 1, usrc.F90:353-418); a preconditioner built before must be rebuilt."""
+        lm = np.ascontiguousarray(landm, dtype=np.int32)
+        assert lm.shape == self.landm_global.shape, lm.shape
+        if self.L_.thcmb_set_landmask(self.ctx, _np_ptr(lm), 1 if init else 0) != 0:
+            raise ValueError(last_error())
+        self.landm_global = lm
+
     def fixPressurePoints(self, on=True):
         """"Fix Pressure Points" (THCM.C:749-757, 2258-2296)."""
         self.L_.thcmb_fix_pressure_points(self.ctx, 1 if on else 0)
@@ -586,8 +595,12 @@ class Ocean:
         return 6                       # _NUN_
 
     def getLandMask(self):
-        """The GLOBAL land mask [l+2, m+2, n+2] the model was created with (Ocean::getLandMask's `global_borders`)."""
+        """The GLOBAL land mask [l+2, m+2, n+2] the model works on (Ocean::getLandMask's `global_borders`)."""
         return self.thcm.landm_global.copy()
+
+    def setLandMask(self, landm, init=True):   # Ocean::setLandMask (Ocean.C) -> THCM::setLandMask
+        self.thcm.setLandMask(landm, init)
+        self.jac_valid = self.precon_valid = False
 
     def buildPreconditioner(self):  # Ocean.C:1377-1391
         if not self.precon_valid:

@@ -340,6 +340,10 @@ void thcmb_get_vmix_flags(const thcmb_ctx* c, int* out4);
  * thcmb_fix_pressure_points = "Fix Pressure Points" (identity rows for p of the cells (N-1, M-1, L-1), (N-2, M-1, L-1)).
  * All three also zero the mass diagonal of the replaced rows.  thcmb_intcond_row: global row id (0-based) or -1 */
 void thcmb_enable_intcond(thcmb_ctx* c, int Nic, int Mic, int sign);
+/* THCM::setLandMask (THCM.C:1362-1392) / set_landmask_ with reinit = 1 (usrc.F90:353-418) for a handle: the instance is rebuilt on
+ * the new GLOBAL mask ((N+2)(M+2)(L+2) ints, i fastest), same decomposition.  init = 0: no-op (the reference then only updates m_global's
+ * copy).  Rebuild the preconditioner afterwards.  Returns -1 (thcmb_last_error) when an enabled integral condition's cell became land */
+int thcmb_set_landmask(thcmb_ctx* c, const int* landm_global, int init);
 double thcmb_set_intcond_correction(thcmb_ctx* c, const double* d_vec);
 void thcmb_fix_pressure_points(thcmb_ctx* c, int on);
 int thcmb_intcond_row(const thcmb_ctx* c);

@@ -174,6 +174,10 @@ public:
     // coefficients on ALL owned unknowns (non-zero on the S rows of ocean cells), like the Epetra vector intcondCoeff_; returns the volume
     double getIntCondCoeff(std::vector<double>& coeff) { coeff.resize((size_t)ndim()); return thcmb_intcond_coeff(c_, coeff.data()); }
     void fixMixing(int value) { thcmb_set_vmix_fix(c_, value); }
+    // THCM::setLandMask(global mask, init) (THCM.C:1362-1392): with init the instance follows the new GLOBAL mask (set_landmask_, reinit = 1)
+    void setLandMask(const std::vector<int>& landmGlobal, bool init = true) {
+        if (thcmb_set_landmask(c_, landmGlobal.data(), init ? 1 : 0) != 0) throw std::runtime_error(thcmb_last_error());
+    }
     // coupling setters (THCM.C:1395-1560 -> m_inserts); `which` as in thcmb_insert_field
     void setSurfaceField(int which, const std::vector<double>& fieldGlobal) { thcmb_insert_field(c_, which, fieldGlobal.data()); }
     void setAtmosphereParameters(const double* commPars18) { thcmb_set_atmos_parameters(c_, commPars18); }

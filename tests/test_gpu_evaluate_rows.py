@@ -474,3 +474,52 @@ def test_models_built_from_the_reference_parameter_lists(tmp_path):
     t2.evaluate(torch.zeros(t2.ndim, dtype=torch.float64, device="cuda"), F0, False)
     assert float(F2.norm()) < 1e-10 * float(F0.norm())
     t2.close()
+
+
+def test_set_land_mask_on_the_model_mirror():
+    """Ocean::setLandMask / THCM::setLandMask(mask, init = true) (THCM.C:1362-1392) on a handle: the instance follows the new global mask
+    exactly like one created on it -- residual, Jacobian values, mass diagonal, forcing bit for bit -- with the integral condition kept on
+    its cell; a mask that turns that cell into land is refused."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the THCM B200 path has no CPU fallback")
+    import iemic_b200
+    s, landm = cases.box(9, 7, 4, False, seed=2, land_frac=0.0, SRES=0, vmix=1)
+    n, m, l = s.N, s.M, s.L
+    new = landm.copy()
+    new[1:l + 1, 2:4, 3] = 1                      # two full-depth land columns
+    new[1:3, 5, 6] = 1                            # and a sea mount: the two deepest levels (k = 1 is the bottom; no ocean below land)
+    oc = iemic_b200.Ocean(s, landm)
+    oc.thcm.enableIntegralCondition(-1, -1, -1)
+    ref = iemic_b200.THCM(s, new)
+    ref.enableIntegralCondition(-1, -1, -1)
+    for k, v in PARS.items():
+        oc.setPar(k, v)
+        ref.setParameter(k, v)
+    x0 = cases.consistent_state(s, landm, scale=0.05, seed=6)
+    oc.getState("V").copy_(torch.from_numpy(x0).cuda())
+    oc.computeRHS(); oc.computeJacobian(); oc.buildPreconditioner()      # state of the old mask everywhere, then the change
+    oc.setLandMask(new)
+    assert np.array_equal(oc.getLandMask(), new)
+    x = cases.consistent_state(s, new, scale=0.05, seed=7)
+    oc.getState("V").copy_(torch.from_numpy(x).cuda())
+    oc.computeRHS(); oc.computeJacobian()
+    F = ref.new_vector()
+    ref.evaluate(torch.from_numpy(x).cuda(), F, True)
+    assert np.array_equal(oc.getRHS("V").cpu().numpy(), F.cpu().numpy())
+    assert np.array_equal(oc.thcm.jacobian_values_host(), ref.jacobian_values_host())
+    assert np.array_equal(oc.thcm.getMassDiagonal(), ref.getMassDiagonal())
+    assert np.array_equal(oc.thcm.getForcing(), ref.getForcing())
+    # the ocean-only Krylov space follows the mask as well: one preconditioned solve gives the same iterates on both
+    b = torch.from_numpy(np.random.default_rng(1).standard_normal(ref.ndim) * (ref.getMassDiagonal() != 0)).cuda()
+    oc.buildPreconditioner(); ref.buildPreconditioner(1)
+    sol = ref.new_vector()
+    r1, h1 = ref.gmres(b, sol, tol=1e-6, maxit=30, restart=30, prec=True, flexible=True)
+    oc.solver_params.update(tol=1e-6, maxit=30, restart=30)
+    oc.solve(b)
+    assert np.array_equal(np.asarray(h1), np.asarray(oc.last_history))
+    bad = new.copy()
+    bad[1:l + 1, m, n] = 1                          # the integral-condition cell (N-1, M-1) becomes land
+    with pytest.raises(ValueError, match="integral-condition cell"):
+        oc.setLandMask(bad)
+    ref.close(); oc.thcm.close()
