@@ -163,6 +163,22 @@ def validate_parameters_and_set_defaults(params, defaults, where=None):
     return params
 
 
+def validate_parameters(params, defaults, where=None):
+    """Teuchos::ParameterList::validateParameters: names and types checked as above, nothing added."""
+    where = where or params.name
+    for k, v in params.items():
+        if k not in defaults:
+            raise InvalidParameter(f'the parameter "{k}" in the list "{where}" is not a valid parameter name')
+        d = defaults[k]
+        if isinstance(d, ParameterList) != isinstance(v, ParameterList):
+            raise InvalidParameter(f'"{k}" in "{where}": a sublist and a parameter cannot stand in for each other')
+        if isinstance(v, ParameterList):
+            validate_parameters(v, d, f"{where}->{k}")
+        elif type(v) is not type(d):
+            raise InvalidParameter(f'the parameter "{k}" in the list "{where}" has type {type(v).__name__}, expected {type(d).__name__}')
+    return params
+
+
 def thcm_setup(thcm_params, rank=0, nranks=1, device=0, balance=0, data_dir=None):
     """The host part of the THCM constructor (THCM.C:186-400, 640-760) for the list `thcm_params` (the "THCM" sublist of the ocean list):
     returns a dict with

@@ -193,9 +193,29 @@ class THCM:
             t.enableIntegralCondition(*su["integral_condition"])
         if su["fix_pressure_points"]:
             t.fixPressurePoints(True)
-        for name, value in su["starting_parameters"]:              # THCM.C:781-792
-            t.setParameter(name, value)
+        start = t.paramList_["Starting Parameters"]
+        for name in list(start):                                   # THCM.C:781-792: NaN = "keep stpnt's value", which the list then reports
+            if isinstance(start[name], float) and math.isnan(start[name]):
+                start[name] = t.getParameter(name)
+            else:
+                t.setParameter(name, start[name])
         return t
+
+    def getParameters(self):
+        """THCM::getParameters (THCM.C:2789-2790): the validated list the model was built from, every starting parameter with its value."""
+        if not hasattr(self, "paramList_"):
+            raise RuntimeError("this THCM was not built from a parameter list")
+        return self.paramList_
+
+    def setParameters(self, new_params):
+        """THCM::setParameters (THCM.C:2792-2801): only the "Starting Parameters" may change after construction; NaN entries are skipped."""
+        from . import paramlist as pl
+        pl.validate_parameters(new_params, pl.thcm_default_parameters())
+        for name, value in new_params.get("Starting Parameters", {}).items():
+            if not (isinstance(value, float) and math.isnan(value)):
+                self.setParameter(name, value)
+                if hasattr(self, "paramList_"):
+                    self.paramList_["Starting Parameters"][name] = float(value)
 
     def _init_nccl(self, comm):
         import torch.distributed as dist

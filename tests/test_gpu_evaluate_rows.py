@@ -464,6 +464,23 @@ def test_models_built_from_the_reference_parameter_lists(tmp_path):
     with pytest.raises(ValueError):
         oc.applyMassMat(v, v)
     assert oc.npar() == 30 and oc.int2par(19) == "Combined Forcing" and oc.dof() == 6 and np.array_equal(oc.getLandMask(), landm)
+    # the list the model reports (test_parameterlist.C:326-370): overrides kept, everything else at its default, and every starting
+    # parameter with its current value instead of the NaN placeholder (THCM.C:781-792)
+    cur, dflt = oc.thcm.getParameters(), pl.thcm_default_init_parameters()
+    given = pl.read_xml(xml)["THCM"]
+    for k, v in cur.items():
+        if k != "Starting Parameters":
+            assert v == given.get(k, dflt[k]), k
+    sp = cur["Starting Parameters"]
+    assert len(sp) == 30 and not any(np.isnan(v) for v in sp.values())
+    assert all(sp[k] == oc.getPar(k) for k in sp) and sp["Combined Forcing"] == 0.25 and sp["Rossby-Number"] == oc.getPar("Rossby-Number") != 0.0
+    upd = pl.ParameterList("THCM")
+    upd.sublist("Starting Parameters").update({"Combined Forcing": 0.5, "Wind Forcing": float("nan")})
+    wind = oc.getPar("Wind Forcing")
+    oc.thcm.setParameters(upd)                                             # THCM::setParameters: NaN entries are skipped
+    assert oc.getPar("Combined Forcing") == 0.5 and oc.getPar("Wind Forcing") == wind and sp["Combined Forcing"] == 0.5
+    with pytest.raises(pl.InvalidParameter):
+        oc.thcm.setParameters(pl.ParameterList("THCM", {"Mixing": 2}))    # only the starting parameters may change after construction
     t.close(); oc.thcm.close()
     # the default run: Topography = 1 basin, Forcing Type 2; its stored steady state is a root
     from test_oracle_pins import DEFAULT_RUN_STATE
