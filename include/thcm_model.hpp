@@ -218,6 +218,12 @@ public:
         rhs_ = std::make_shared<Vector>(thcm_->context());
         sol_ = std::make_shared<Vector>(thcm_->context());
     }
+    // over a THCM that exists already (e.g. thcm_b200::makeTHCM of thcm_paramlist.hpp)
+    explicit Ocean(std::shared_ptr<THCM> thcm, SolverParameters sp = SolverParameters()) : thcm_(std::move(thcm)), sp_(sp) {
+        state_ = std::make_shared<Vector>(thcm_->context());
+        rhs_ = std::make_shared<Vector>(thcm_->context());
+        sol_ = std::make_shared<Vector>(thcm_->context());
+    }
     virtual ~Ocean() {}
 
     THCM& getTHCM() { return *thcm_; }

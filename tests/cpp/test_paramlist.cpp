@@ -1,47 +1,29 @@
-// Host-only test of include/thcm_paramlist.hpp (test infrastructure): the THCM constructor's reading of its parameter list over a small
-// stand-in for Teuchos::ParameterList (Teuchos is not available here) -- same accessor signatures: get<T>(name, default) stores the
-// default when the entry is missing, sublist(name) creates the sublist.  Runs without a GPU: only the m_global symbols of the library are
-// called.  Usage: test_paramlist <directory that holds mkmask/>  ; prints "PASS <n>" or the first failed check.
+// Host-only test of include/thcm_paramlist.hpp (test infrastructure): the THCM constructor's reading of its parameter list over
+// thcm_b200::ParameterList (Teuchos's accessor signatures: get<T>(name, default) stores the default when the entry is missing,
+// sublist(name) creates the sublist) and the reader of the reference's XML dialect.  Runs without a GPU: only the m_global symbols of the
+// library are called.
+//   test_paramlist <directory that holds mkmask/> [<fixture directory>]   prints "PASS <n>" or the first failed check
+//   test_paramlist --dump <file.xml>                                      prints the list in canonical form (compared with the Python reader)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iostream>
 #include <map>
 #include <string>
 #include "thcm_paramlist.hpp"
 
-class ParameterList {   // typed entries, Teuchos-style accessors
-    struct Entry { enum { I, D, B, S } t; int i; double d; bool b; std::string s; };
-    std::map<std::string, Entry> e_;
-    std::map<std::string, ParameterList> sub_;
-    template <class T> struct Tag {};
-    static Entry make(int v) { Entry e{}; e.t = Entry::I; e.i = v; return e; }
-    static Entry make(double v) { Entry e{}; e.t = Entry::D; e.d = v; return e; }
-    static Entry make(bool v) { Entry e{}; e.t = Entry::B; e.b = v; return e; }
-    static Entry make(const std::string& v) { Entry e{}; e.t = Entry::S; e.s = v; return e; }
-    static int& ref(Entry& e, Tag<int>) { if (e.t != Entry::I) throw std::invalid_argument("type"); return e.i; }
-    static double& ref(Entry& e, Tag<double>) { if (e.t != Entry::D) throw std::invalid_argument("type"); return e.d; }
-    static bool& ref(Entry& e, Tag<bool>) { if (e.t != Entry::B) throw std::invalid_argument("type"); return e.b; }
-    static std::string& ref(Entry& e, Tag<std::string>) { if (e.t != Entry::S) throw std::invalid_argument("type"); return e.s; }
-
-public:
-    template <class T> ParameterList& set(const std::string& name, T v) { e_[name] = make(v); return *this; }
-    ParameterList& set(const std::string& name, const char* v) { e_[name] = make(std::string(v)); return *this; }
-    template <class T> T& get(const std::string& name, T def) {
-        auto it = e_.find(name);
-        if (it == e_.end()) it = e_.emplace(name, make(def)).first;
-        return ref(it->second, Tag<T>());
-    }
-    template <class T> T& get(const std::string& name, const char* def) { return get<T>(name, std::string(def)); }
-    ParameterList& sublist(const std::string& name) { return sub_[name]; }
-    bool isParameter(const std::string& name) const { return e_.count(name) != 0; }
-};
+using thcm_b200::ParameterList;
 
 static int checks = 0;
 #define CHECK(c) do { checks++; if (!(c)) { printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
 int main(int argc, char** argv) {
-    if (argc > 1) setenv("THCM_DATA_DIR", argv[1], 1);
     using namespace thcm_b200;
+    if (argc > 2 && std::string(argv[1]) == "--dump") {
+        try { parameterListFromXMLFile(argv[2]).dump(std::cout); } catch (const std::exception& e) { printf("ERROR %s\n", e.what()); return 2; }
+        return 0;
+    }
+    if (argc > 1) setenv("THCM_DATA_DIR", argv[1], 1);
     {   // all defaults: the reference's 16 x 16 x 16 North Atlantic box without continents (Topography = 1), restoring salinity
         ParameterList p;
         THCMSetup su = setupFromParameterList(p);
@@ -86,6 +68,44 @@ int main(int argc, char** argv) {
         thrown = false;
         try { setupFromParameterList(t); } catch (const std::invalid_argument&) { thrown = true; }
         CHECK(thrown);
+    }
+    {   // the XML dialect: comments, nested lists, bools as 0 / 1 / true / false, numbers read like istringstream, entities
+        ParameterList p = parameterListFromXMLString(
+            "<?xml version=\"1.0\"?>\n<!-- a comment with <tags> inside -->\n<ParameterList name=\"Ocean\">\n"
+            "  <Parameter name=\"Load state\" type=\"bool\" value=\"0\"/>\n  <Parameter value='1.0-2' type='double' name='odd number'/>\n"
+            "  <ParameterList name=\"THCM\">\n    <Parameter name=\"Global Grid-Size n\" type=\"int\" value=\" 8 \"/>\n"
+            "    <Parameter name=\"Land Mask\" type=\"string\" value=\"a &amp; b\"/>\n    <Parameter name=\"Periodic\" type=\"bool\" value=\"TRUE\"/>\n"
+            "    <ParameterList name=\"Starting Parameters\">\n      <Parameter name=\"SPL1\" type=\"double\" value=\"2.0e3\"/>\n    </ParameterList>\n"
+            "  </ParameterList>\n  <ParameterList name=\"Empty\"/>\n</ParameterList>\n");
+        CHECK(p.name() == "Ocean" && p.get<bool>("Load state") == false && p.get<double>("odd number") == 1.0);
+        CHECK(p.isSublist("THCM") && p.isSublist("Empty") && !p.isParameter("THCM"));
+        ParameterList& t = p.sublist("THCM");
+        CHECK(t.get<int>("Global Grid-Size n") == 8 && t.get<std::string>("Land Mask") == "a & b" && t.get<bool>("Periodic") == true);
+        CHECK(t.sublist("Starting Parameters").get<double>("SPL1") == 2000.0);
+        bool thrown = false;
+        try { t.get<double>("Global Grid-Size n"); } catch (const std::invalid_argument&) { thrown = true; }     // wrong type
+        CHECK(thrown);
+        thrown = false;
+        try { t.get<int>("no such parameter"); } catch (const std::invalid_argument&) { thrown = true; }          // missing name
+        CHECK(thrown);
+        thrown = false;
+        try { parameterListFromXMLString("<ParameterList name='x'><Parameter name='a' type='bool' value='maybe'/></ParameterList>"); }
+        catch (const std::invalid_argument&) { thrown = true; }
+        CHECK(thrown);
+    }
+    if (argc > 2) {   // the committed fixtures through the XML reader and the constructor's rules
+        const std::string dir = argv[2];
+        ParameterList o = parameterListFromXMLFile(dir + "/natl8_integral_condition.xml");
+        THCMSetup su = setupFromParameterList(o.sublist("THCM"));
+        CHECK(su.settings.N == 8 && su.settings.L == 4 && su.settings.SRES == 0 && su.settings.vmix == 1 && su.settings.rho_mixing == 0);
+        CHECK(su.integralCondition && su.Nic == 7 && su.Mic == 7 && su.startingParameters.size() == 5);
+        CHECK(o.sublist("Belos Solver").get<int>("FGMRES iterations") == 120 && o.sublist("Belos Solver").get<double>("FGMRES tolerance") == 1e-6);
+        ParameterList b = parameterListFromXMLFile(dir + "/basin16_topography1.xml");
+        THCMSetup sb = setupFromParameterList(b);
+        CHECK(sb.settings.N == 16 && sb.settings.forcing_type == 2 && sb.settings.SRES == 1 && !sb.integralCondition && sb.startingParameters.size() == 7);
+        size_t ocean = 0;
+        for (int v : sb.landm) ocean += v == 0;
+        CHECK(ocean == 16u * 16 * 16);
     }
     printf("PASS %d\n", checks);
     return 0;

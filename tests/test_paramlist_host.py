@@ -152,10 +152,40 @@ def test_every_ocean_list_the_reference_ships():
 
 
 def test_cpp_mirror_reads_the_same_lists(data_dir):
-    """include/thcm_paramlist.hpp (setupFromParameterList over a stand-in for Teuchos::ParameterList): tests/cpp/test_paramlist.cpp,
-    host-only -- defaults, the mask by name, the integral-condition rules, type checking."""
+    """include/thcm_paramlist.hpp (thcm_b200::ParameterList, the XML reader, setupFromParameterList): tests/cpp/test_paramlist.cpp,
+    host-only -- defaults, the mask by name, the integral-condition rules, type checking, the XML dialect, the committed fixtures; and the
+    C++ reader against the Python reader, entry by entry, on the fixtures and (here) on every ocean list of the reference."""
     import subprocess
     cpp = os.path.join(HERE, "cpp")
     subprocess.run(["make", "-C", cpp, "all"], check=True, capture_output=True)
-    r = subprocess.run([os.path.join(cpp, "_bin", "test_paramlist"), str(data_dir)], capture_output=True, text=True)
+    exe = os.path.join(cpp, "_bin", "test_paramlist")
+    r = subprocess.run([exe, str(data_dir), PARAMS], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr
+
+    def canonical(p, prefix=""):
+        out = []
+        for k, v in p.items():
+            if isinstance(v, pl.ParameterList):
+                out += canonical(v, prefix + k + "/")
+            elif isinstance(v, bool):
+                out.append(f"{prefix}{k} = bool {'true' if v else 'false'}")
+            elif isinstance(v, int):
+                out.append(f"{prefix}{k} = int {v}")
+            elif isinstance(v, float):
+                out.append(f"{prefix}{k} = double {v!r}")
+            else:
+                out.append(f"{prefix}{k} = string {v}")
+        return out
+
+    files = sorted(glob.glob(os.path.join(PARAMS, "*.xml")))
+    if os.path.isdir(REFERENCE):
+        files += sorted(glob.glob(os.path.join(REFERENCE, "**", "*ocean*.xml"), recursive=True))
+    assert len(files) >= 2
+    for f in files:
+        r = subprocess.run([exe, "--dump", f], capture_output=True, text=True)
+        assert r.returncode == 0, (f, r.stdout)
+        got = []
+        for line in r.stdout.splitlines():     # doubles: compare the values, not their spelling
+            head, _, val = line.partition(" = double ")
+            got.append(f"{head} = double {float(val)!r}" if val else line)
+        assert got == canonical(pl.read_xml(f)), f
